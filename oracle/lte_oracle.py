@@ -1,0 +1,464 @@
+"""CPU oracle for the LTE simulate-and-count-BER link chain.
+
+TEST INFRASTRUCTURE ONLY.  This module is a vectorised NumPy (fp64) restatement
+of the algorithm in the reference (Darioxavierl/OFDM-LTE, pure Python/NumPy).
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` may import it; the product path
+(``ofdm-lte_b200/``) never does and fails loudly without its CUDA library.
+
+Parity status: PINNED.  ``tests/golden/make_golden.py`` imports the real
+reference from ``/root/reference`` in the build container, runs it, and commits
+its outputs under ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks
+every function below against those vectors (signals <= 1e-12 relative, bits and
+error counts identical).  The reference's own asserting tests on this path
+(Alamouti identities ``test/test_alamouti_unit.py:49-52,119``; the 2x2 MMSE toy
+``core/mimo_detector.py:387-404``; layer-mapper round trips
+``core/layer_mapper.py:172-219``) are restated in ``tests/test_oracle_kat.py``.
+
+Third-party arithmetic the reference relies on and that is restated by calling
+the same library: ``numpy.fft`` (pocketfft, unitary scaling applied by the
+caller), ``numpy.linalg.inv/pinv`` (LAPACK) and the legacy ``numpy.random``
+MT19937 stream (versions unpinned in ``requirements.txt``; this image has
+numpy 2.3.5).
+
+Every function cites the reference file:line it follows (paths relative to the
+reference root).  All faithfulness quirks are kept: natural-binary raster QAM,
+un-shifted FFT-bin grid, double dB->linear conversion of tap gains, power-2
+Jakes, per-14-symbol channel hold, 1e-6 / 1e-10 regularisers.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# ----------------------------------------------------------------------------
+# L0: numerology and tables                                   (config.py:11-60)
+# ----------------------------------------------------------------------------
+LTE_PROFILES = {1.25: (76, 128), 2.5: (150, 256), 5.0: (300, 512),
+                10.0: (600, 1024), 15.0: (900, 2048), 20.0: (1200, 2048)}
+CP_US = {'normal': 4.7, 'extended_15khz': 16.6, 'extended_7.5khz': 33.0}
+BITS_PER_SYMBOL = {'QPSK': 2, '16-QAM': 4, '64-QAM': 6}
+ITU = {
+    'Pedestrian_A': ([0.0, 0.11, 0.19, 0.41], [0.0, -9.7, -19.2, -22.8]),
+    'Pedestrian_B': ([0.0, 0.2, 0.8, 1.2, 2.3, 3.7], [0.0, -0.9, -4.9, -8.0, -7.8, -23.9]),
+    'Vehicular_A': ([0.0, 0.31, 0.71, 1.09, 1.73, 2.51], [0.0, -1.0, -9.0, -10.0, -15.0, -20.0]),
+    'Vehicular_B': ([0.0, 0.3, 0.7, 1.09, 1.73, 2.51, 3.7, 4.53],
+                    [0.0, -1.0, -9.0, -10.0, -13.0, -16.0, -21.6, -24.0]),
+    'Bad_Urban': ([0.0, 0.1, 0.3, 0.5, 0.9, 1.3, 1.9, 2.6],
+                  [0.0, -3.0, -5.0, -7.0, -9.0, -11.0, -13.0, -15.0]),
+}
+SLOT_SIZE = 14  # core/lte_receiver.py:233
+
+
+class Numerology:
+    """config.py:63-154 (LTEConfig._calculate_parameters)."""
+
+    def __init__(self, bandwidth=5.0, delta_f=15.0, modulation='QPSK', cp_type='normal'):
+        if modulation not in BITS_PER_SYMBOL:
+            raise ValueError(f"Unsupported modulation: {modulation}")
+        self.bandwidth, self.delta_f = bandwidth, delta_f
+        self.modulation, self.cp_type = modulation, cp_type
+        if bandwidth in LTE_PROFILES:                       # config.py:104-107
+            self.Nc, self.N = LTE_PROFILES[bandwidth]
+        else:                                               # config.py:110-111
+            self.Nc = int((bandwidth * 1e3) / delta_f)
+            self.N = int(2 ** np.ceil(np.log2(self.Nc)))
+        self.fs = self.N * delta_f * 1e3                    # config.py:114
+        if cp_type == 'extended':                           # config.py:136-145
+            cp_us = CP_US['extended_15khz'] if delta_f == 15.0 else CP_US['extended_7.5khz']
+        else:
+            cp_us = CP_US['normal']
+        self.cp_duration = cp_us
+        self.cp_length = int(cp_us * 1e-6 * self.fs)        # config.py:124
+        self.bits_per_symbol = BITS_PER_SYMBOL[modulation]
+        self.L = self.N + self.cp_length
+
+
+def grid_indices(N, Nc):
+    """core/resource_mapper.py:45-74: bin classes in raw FFT-bin order."""
+    gl = (N - Nc) // 2
+    gr = N - Nc - gl
+    dc = N // 2
+    k = np.arange(N)
+    useful = (k >= gl) & (k < N - gr) & (k != dc)
+    pilot = useful & (((k - gl) % 6) == 3)
+    data = useful & ~pilot
+    return np.nonzero(data)[0], np.nonzero(pilot)[0]
+
+
+def pilot_signs(cell_id, num_pilots):
+    """core/resource_mapper.py:148-149: seed(cell_id); choice([1,-1], P)."""
+    return np.random.RandomState(cell_id).choice([1, -1], size=num_pilots)
+
+
+def pilots(cell_id, num_pilots):
+    """core/resource_mapper.py:133,151."""
+    return ((1 + 1j) / np.sqrt(2)) * pilot_signs(cell_id, num_pilots)
+
+
+def constellation(modulation):
+    """core/modulator.py:28-59: raster order, real outer loop / imag inner loop."""
+    if modulation == 'QPSK':
+        return np.array([1 + 1j, 1 - 1j, -1 + 1j, -1 - 1j]) / np.sqrt(2)
+    if modulation == '16-QAM':
+        lv, nrm = np.array([-3, -1, 1, 3]), np.sqrt(10)
+    elif modulation == '64-QAM':
+        lv, nrm = np.array([-7, -5, -3, -1, 1, 3, 5, 7]), np.sqrt(42)
+    else:
+        raise ValueError(f"unsupported modulation {modulation}")
+    return (lv[:, None] + 1j * lv[None, :]).reshape(-1) / nrm
+
+
+# ----------------------------------------------------------------------------
+# L1: QAM map / demap                                (core/modulator.py:61-112)
+# ----------------------------------------------------------------------------
+def bits_to_indices(bits, b):
+    """core/modulator.py:74-84: zero-pad to a multiple of b; MSB-first integer."""
+    bits = np.asarray(bits).astype(np.int64)
+    if len(bits) % b:
+        bits = np.concatenate([bits, np.zeros(b - len(bits) % b, dtype=np.int64)])
+    w = 1 << np.arange(b - 1, -1, -1)
+    return (bits.reshape(-1, b) * w).sum(axis=1)
+
+
+def indices_to_bits(idx, b):
+    """core/modulator.py:109-110: format(idx, '0{b}b')."""
+    idx = np.asarray(idx, dtype=np.int64)
+    return ((idx[:, None] >> np.arange(b - 1, -1, -1)) & 1).reshape(-1)
+
+
+def qam_map(bits, modulation):
+    """core/modulator.py:61-88."""
+    c = constellation(modulation)
+    return c[bits_to_indices(bits, BITS_PER_SYMBOL[modulation]) % len(c)]
+
+
+def qam_demap_indices(symbols, modulation):
+    """core/modulator.py:103-106: argmin_i |c_i - y|, first minimum wins.
+
+    Kept as a literal broadcast argmin (chunked) so that ties and the
+    floating-point behaviour of np.abs() are the reference's.
+    """
+    c = constellation(modulation)
+    symbols = np.asarray(symbols, dtype=complex)
+    out = np.empty(len(symbols), dtype=np.int64)
+    for s in range(0, len(symbols), 1 << 14):
+        blk = symbols[s:s + (1 << 14)]
+        out[s:s + len(blk)] = np.argmin(np.abs(c[None, :] - blk[:, None]), axis=1)
+    return out
+
+
+def qam_demap(symbols, modulation):
+    """core/modulator.py:90-112."""
+    return indices_to_bits(qam_demap_indices(symbols, modulation), BITS_PER_SYMBOL[modulation])
+
+
+# ----------------------------------------------------------------------------
+# SC-FDM M-point unitary DFT                    (core/dft_precoding.py:44-54,86-88)
+# ----------------------------------------------------------------------------
+def dft_precode(symbols, inverse=False):
+    """Unitary M-point DFT of each row (last axis).  The reference multiplies by a
+    dense matrix exp(-/+ j 2 pi k n / M)/sqrt(M) (core/dft_precoding.py:54,175);
+    pocketfft computes the same sums more accurately."""
+    M = symbols.shape[-1]
+    if inverse:
+        return np.fft.ifft(symbols, axis=-1) * np.sqrt(M)
+    return np.fft.fft(symbols, axis=-1) / np.sqrt(M)
+
+
+# ----------------------------------------------------------------------------
+# L2: transmitter                      (core/modulator.py:214-302, resource_mapper.py:181-223)
+# ----------------------------------------------------------------------------
+def map_grid(data_symbols, num, cell_id=0):
+    """ResourceMapper.map_symbols for a [S, Nd] block -> [S, N] grids."""
+    data_idx, pilot_idx = grid_indices(num.N, num.Nc)
+    S = data_symbols.shape[0]
+    grid = np.zeros((S, num.N), dtype=complex)
+    grid[:, data_idx[:data_symbols.shape[1]]] = data_symbols
+    grid[:, pilot_idx] = pilots(cell_id, len(pilot_idx))[None, :]
+    return grid
+
+
+def ofdm_modulate_grid(grid, num):
+    """core/modulator.py:242-248: ifft * sqrt(N), prepend the last cp samples."""
+    td = np.fft.ifft(grid, axis=-1) * np.sqrt(num.N)
+    cp = num.cp_length
+    if cp > 0:
+        td = np.concatenate([td[..., -cp:], td], axis=-1)
+    return td
+
+
+def modulate_stream(bits, num, sc_fdm=False, mode='lte'):
+    """OFDMModulator.modulate_stream (core/modulator.py:252-302).
+
+    Returns (signal[S*L], qam_symbols[S, Nd]) for mode 'lte' (and SC-FDM);
+    mode 'simple' puts the first Nc symbols on bins 0..Nc-1 (modulator.py:192-212).
+    """
+    b = num.bits_per_symbol
+    bits = np.asarray(bits).astype(np.int64)
+    if mode == 'simple':
+        n_per = num.Nc
+    else:
+        data_idx, _ = grid_indices(num.N, num.Nc)
+        n_per = len(data_idx)
+    bits_per_ofdm = n_per * b
+    S = int(np.ceil(len(bits) / bits_per_ofdm))
+    if len(bits) < S * bits_per_ofdm:
+        bits = np.concatenate([bits, np.zeros(S * bits_per_ofdm - len(bits), dtype=np.int64)])
+    sym = qam_map(bits, num.modulation).reshape(S, n_per)
+    if mode == 'simple':
+        grid = np.zeros((S, num.N), dtype=complex)
+        grid[:, :n_per] = sym
+    else:
+        pre = dft_precode(sym) if sc_fdm else sym
+        grid = map_grid(pre, num)
+    sig = ofdm_modulate_grid(grid, num)
+    return sig.reshape(-1), sym
+
+
+def papr(signal):
+    """core/ofdm_core.py:131-140."""
+    p = np.abs(signal) ** 2
+    avg = np.mean(p)
+    if avg > 0:
+        lin = np.max(p) / avg
+        return 10 * np.log10(lin), lin
+    return 0.0, 1.0
+
+
+def papr_per_symbol_no_cp(signal, num):
+    """core/ofdm_system.py:173-229 (per-OFDM-symbol PAPR with the CP removed)."""
+    S = len(signal) // num.L
+    x = signal[:S * num.L].reshape(S, num.L)[:, num.cp_length:]
+    p = np.abs(x) ** 2
+    return p.max(axis=1) / p.mean(axis=1)
+
+
+# ----------------------------------------------------------------------------
+# L2: channel             (core/rayleighchannel.py:20-58, core/channel.py:34-68,162-234)
+# ----------------------------------------------------------------------------
+def itu_taps(profile, fs, gain_conversions=2):
+    """core/channel.py:172-186 then core/rayleighchannel.py:16 (and once more in
+    core/channel.py:436 for spatial multiplexing): the dB table is converted to
+    linear `gain_conversions` times.  Delays: core/rayleighchannel.py:52."""
+    if profile not in ITU:
+        raise ValueError(f"Perfil ITU no encontrado: {profile}")
+    delays_us, power_db = ITU[profile]
+    g = np.array(power_db, dtype=float)
+    for _ in range(gain_conversions):
+        g = 10 ** (g / 20)
+    d = np.array([int(np.round(du * 1e-6 * fs)) for du in np.array(delays_us)])
+    return d, g
+
+
+def doppler_hz(frequency_ghz, velocity_kmh):
+    """core/channel.py:118-143."""
+    return ((velocity_kmh / 3.6) * (frequency_ghz * 1e9)) / 3e8
+
+
+def jakes_fading(n_samples, fs, fD, phi):
+    """core/rayleighchannel.py:27-41 with the 16 random phases `phi` injected."""
+    n_s = len(phi)
+    t = np.arange(n_samples) / fs
+    alpha = 2 * np.pi * np.arange(1, n_s + 1) / n_s
+    h = np.zeros(n_samples, dtype=complex)
+    for n in range(n_s):
+        h += np.exp(1j * (2 * np.pi * fD * np.cos(alpha[n]) * t + phi[n]))
+    return h * np.sqrt(2 / n_s)
+
+
+def rayleigh_filter(x, fs, fD, delays, gains, phases):
+    """core/rayleighchannel.py:44-58; phases[tap][16] = 2*pi*rand(16) per tap."""
+    n = len(x)
+    y = np.zeros(n, dtype=complex)
+    for i in range(len(delays)):
+        fading = jakes_fading(n, fs, fD, phases[i])
+        xd = np.concatenate([np.zeros(delays[i]), x])[:n]
+        y += gains[i] * fading * xd
+    return y
+
+
+def awgn(x, snr_db, z_re, z_im):
+    """core/channel.py:46-66 / :216-232 with the unit normals injected:
+    noise_re = normal(0, sqrt(P/snr/2), L) == sqrt(P/snr/2) * z_re."""
+    p = np.mean(np.abs(x) ** 2)
+    sigma = np.sqrt((p / (10 ** (snr_db / 10))) / 2)
+    return x + (sigma * z_re + 1j * (sigma * z_im))
+
+
+class ReferenceDraws:
+    """Reproduces the reference's draws from NumPy's legacy *global* RNG.
+
+    Every ResourceMapper.map_symbols / LTEChannelEstimator.estimate_channel call
+    re-seeds the global RNG with cell_id (core/resource_mapper.py:148), so after
+    the transmitter has run the global state is always `seed(0); choice(P)`.
+    Draw order per link afterwards (measured, see tests/golden/make_golden.py):
+    taps x rand(16) (core/rayleighchannel.py:31), normal(L) for the real part,
+    normal(L) for the imaginary part (core/channel.py:227-228).
+    """
+
+    def __init__(self, num_pilots, cell_id=0, global_seed=None):
+        if global_seed is not None:
+            # mode='simple' never calls map_symbols, so the global RNG is whatever the
+            # caller left it at; the golden generator seeds it explicitly.
+            self.rs = np.random.RandomState(global_seed)
+        else:
+            self.rs = np.random.RandomState(cell_id)
+            self.rs.choice([1, -1], size=num_pilots)
+
+    def phases(self, n_taps, n_s=16):
+        return np.stack([2 * np.pi * self.rs.rand(n_s) for _ in range(n_taps)])
+
+    def unit_normals(self, n):
+        z_re = self.rs.standard_normal(n)
+        z_im = self.rs.standard_normal(n)
+        return z_re, z_im
+
+
+# ----------------------------------------------------------------------------
+# L2: receiver                               (core/lte_receiver.py:40-180,360-491)
+# ----------------------------------------------------------------------------
+def rx_fft_stream(signal, num):
+    """core/lte_receiver.py:444-491: S = len//L (>=1), zero-pad, strip CP, fft/sqrt(N)."""
+    L = num.L
+    S = max(len(signal) // L, 1)
+    buf = np.zeros(S * L, dtype=complex)
+    m = min(len(signal), S * L)
+    buf[:m] = signal[:m]
+    x = buf.reshape(S, L)[:, num.cp_length:]
+    return np.fft.fft(x, axis=-1) / np.sqrt(num.N)
+
+
+def interpolate_channel(pilot_idx, h_p, N):
+    """core/lte_receiver.py:98-133: edge hold + np.linspace between pilots."""
+    h = np.zeros(N, dtype=complex)
+    h[:pilot_idx[0]] = h_p[0]
+    h[pilot_idx[-1]:] = h_p[-1]
+    for i in range(len(pilot_idx) - 1):
+        i1, i2 = pilot_idx[i], pilot_idx[i + 1]
+        h[i1:i2 + 1] = np.linspace(h_p[i], h_p[i + 1], i2 - i1 + 1)
+    return h
+
+
+def estimate_channel(Y_symbol, num, cell_id=0):
+    """core/lte_receiver.py:62-87: LS at pilots, then interpolation."""
+    _, pilot_idx = grid_indices(num.N, num.Nc)
+    h_p = Y_symbol[pilot_idx] / pilots(cell_id, len(pilot_idx))
+    return interpolate_channel(pilot_idx, h_p, num.N)
+
+
+def estimate_channel_periodic(Y, num, cell_id=0):
+    """core/lte_receiver.py:360-411: estimate on symbol 14*j, hold for the slot."""
+    S = Y.shape[0]
+    H = np.zeros_like(Y)
+    for s0 in range(0, S, SLOT_SIZE):
+        H[s0:s0 + SLOT_SIZE] = estimate_channel(Y[s0], num, cell_id)[None, :]
+    return H
+
+
+def zf_equalize(Y, H, reg=1e-6):
+    """core/lte_receiver.py:174."""
+    return Y / (H + reg)
+
+
+def mrc_combine(Y_data, H_data, reg=1e-10):
+    """core/ofdm_core.py:1484-1532: sum_r conj(H_r) Y_r / (sum_r |H_r|^2 + reg).
+    Y_data, H_data: [R, S, Nd].  Accumulation order over antennas is r = 0..R-1."""
+    num_ = np.zeros(Y_data.shape[1:], dtype=complex)
+    den = np.zeros(Y_data.shape[1:], dtype=float)
+    for r in range(Y_data.shape[0]):
+        num_ += np.conj(H_data[r]) * Y_data[r]
+        den += np.abs(H_data[r]) ** 2
+    return num_ / (den + reg)
+
+
+def count_errors(bits_tx, bits_rx):
+    """core/ofdm_core.py:712-718: pad/truncate rx to len(tx); sum(tx != rx)."""
+    n = len(bits_tx)
+    if len(bits_rx) < n:
+        bits_rx = np.concatenate([bits_rx, np.zeros(n - len(bits_rx), dtype=bits_rx.dtype)])
+    else:
+        bits_rx = bits_rx[:n]
+    return int(np.sum(np.asarray(bits_tx) != bits_rx)), bits_rx
+
+
+# ----------------------------------------------------------------------------
+# L3: end-to-end chains                 (core/ofdm_core.py:660-737, 1536-1679)
+# ----------------------------------------------------------------------------
+def channel_link(signal_tx, num, channel_type, snr_db, draws, itu_profile='Pedestrian_A',
+                 frequency_ghz=2.0, velocity_kmh=0.0, gain_conversions=2, phases=None, z=None):
+    """One ChannelSimulator.transmit (core/channel.py:334-345).  Draws come from
+    `draws` (ReferenceDraws) unless phases / z=(z_re, z_im) are injected."""
+    n = len(signal_tx)
+    if channel_type == 'rayleigh_mp':
+        d, g = itu_taps(itu_profile, num.fs, gain_conversions)
+        fD = doppler_hz(frequency_ghz, velocity_kmh)
+        ph = draws.phases(len(d)) if phases is None else phases
+        faded = rayleigh_filter(signal_tx, num.fs, fD, d, g, ph)
+    else:   # unknown channel types mean AWGN (core/ofdm_core.py:644-654)
+        faded = signal_tx
+    z_re, z_im = draws.unit_normals(n) if z is None else z
+    return awgn(faded, snr_db, z_re, z_im), faded
+
+
+def simulate_siso(bits, snr_db, num, channel_type='awgn', mode='lte', sc_fdm=False,
+                  equalize=True, itu_profile='Pedestrian_A', frequency_ghz=2.0,
+                  velocity_kmh=0.0, phases=None, z=None, draws=None):
+    """OFDMSimulator.simulate_siso (core/ofdm_core.py:660-737) with the LTE receiver
+    of core/lte_receiver.py:235-358 and core/demodulator.py:138-147."""
+    bits = np.asarray(bits).astype(np.int64)
+    if bits.size == 0:
+        raise ValueError("Bits array cannot be empty")
+    data_idx, pilot_idx = grid_indices(num.N, num.Nc)
+    signal_tx, sym_tx = modulate_stream(bits, num, sc_fdm=sc_fdm, mode=mode)
+    papr_db, papr_lin = papr(signal_tx)
+    if draws is None and (phases is None or z is None):
+        draws = ReferenceDraws(len(pilot_idx))
+    signal_rx, faded = channel_link(signal_tx, num, channel_type, snr_db, draws, itu_profile,
+                                    frequency_ghz, velocity_kmh, phases=phases, z=z)
+    Y = rx_fft_stream(signal_rx, num)
+    if mode == 'simple':                       # core/demodulator.py:114-118,149-184
+        sym_rx = Y[:, :num.Nc].reshape(-1)
+        H = None
+    else:
+        H = estimate_channel_periodic(Y, num)
+        Yeq = zf_equalize(Y, H) if equalize else Y
+        sym_rx = Yeq[:, data_idx]
+        if sc_fdm:                             # core/lte_receiver.py:319-333
+            sym_rx = dft_precode(sym_rx, inverse=True)
+        sym_rx = sym_rx.reshape(-1)
+    bits_rx_all = qam_demap(sym_rx, num.modulation)
+    errors, bits_rx = count_errors(bits, bits_rx_all)
+    return dict(signal_tx=signal_tx, symbols_tx=sym_tx, signal_faded=faded, signal_rx=signal_rx,
+                Y=Y, H=H, symbols_rx=sym_rx, bits_rx=bits_rx, errors=errors,
+                ber=errors / len(bits), papr_db=papr_db, papr_linear=papr_lin)
+
+
+def simulate_simo(bits, snr_db, num, num_rx=2, channel_type='awgn', itu_profile='Pedestrian_A',
+                  frequency_ghz=2.0, velocity_kmh=0.0, phases=None, z=None):
+    """OFDMSimulator.simulate_simo (core/ofdm_core.py:1536-1679), sequential branch.
+    phases: [R][taps][16]; z: [R][2][n] unit normals (re then im), or None to
+    reproduce the reference's own draws."""
+    bits = np.asarray(bits).astype(np.int64)
+    if bits.size == 0:
+        raise ValueError("Bits array cannot be empty")
+    data_idx, pilot_idx = grid_indices(num.N, num.Nc)
+    signal_tx, sym_tx = modulate_stream(bits, num)
+    papr_db, papr_lin = papr(signal_tx)
+    draws = ReferenceDraws(len(pilot_idx)) if (phases is None or z is None) else None
+    rx_list, faded_list = [], []
+    for r in range(num_rx):                    # core/ofdm_core.py:396-410
+        rx, faded = channel_link(signal_tx, num, channel_type, snr_db, draws, itu_profile,
+                                 frequency_ghz, velocity_kmh,
+                                 phases=None if phases is None else phases[r],
+                                 z=None if z is None else (z[r][0], z[r][1]))
+        rx_list.append(rx)
+        faded_list.append(faded)
+    Y = np.stack([rx_fft_stream(rx, num) for rx in rx_list])                 # [R,S,N]
+    H = np.stack([estimate_channel_periodic(Y[r], num) for r in range(num_rx)])
+    comb = mrc_combine(Y[:, :, data_idx], H[:, :, data_idx]).reshape(-1)
+    bits_rx_all = qam_demap(comb, num.modulation)
+    errors, bits_rx = count_errors(bits, bits_rx_all)
+    return dict(signal_tx=signal_tx, symbols_tx=sym_tx, signal_faded=np.stack(faded_list),
+                signal_rx=np.stack(rx_list), Y=Y, H=H, symbols_combined=comb,
+                bits_rx=bits_rx, errors=errors, ber=errors / len(bits),
+                papr_db=papr_db, papr_linear=papr_lin)

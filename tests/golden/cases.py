@@ -1,0 +1,41 @@
+"""Case table shared by make_golden.py (which runs the reference) and the tests
+(which run the oracle and the CUDA path on the same inputs)."""
+
+SISO_CASES = [
+    # BASELINE.json config 1: SISO 5 MHz QPSK AWGN
+    dict(name='siso_cfg1_5mhz_qpsk_awgn', bw=5.0, mod='QPSK', ch='awgn', prof='Pedestrian_A', v=0.0,
+         nsym=14, snrs=[0.0, 6.0, 12.0], full_snr=6.0, seed=1),
+    # config 2: SISO SC-FDM 10 MHz 16-QAM Pedestrian_A 3 km/h
+    dict(name='siso_cfg2_10mhz_16qam_scfdm_peda', bw=10.0, mod='16-QAM', ch='rayleigh_mp',
+         prof='Pedestrian_A', v=3.0, nsym=14, snrs=[10.0, 20.0], full_snr=20.0, seed=2, sc_fdm=True),
+    # variants reachable through the same API (last paragraph)
+    dict(name='siso_ext_cp_bad_urban', bw=5.0, mod='16-QAM', ch='rayleigh_mp', prof='Bad_Urban', v=60.0,
+         nsym=3, snrs=[12.0], full_snr=12.0, seed=3, drop_bits=7, cp_type='extended'),
+    dict(name='siso_simple_mode', bw=2.5, mod='64-QAM', ch='awgn', prof='Pedestrian_A', v=0.0,
+         nsym=4, snrs=[18.0], full_snr=18.0, seed=4, drop_bits=3, mode='simple', global_seed=1234),
+    dict(name='siso_no_eq_2p5mhz', bw=2.5, mod='QPSK', ch='awgn', prof='Pedestrian_A', v=0.0,
+         nsym=5, snrs=[4.0], full_snr=4.0, seed=5, equalize=False),
+    dict(name='siso_nonprofile_3mhz_vehb', bw=3.0, mod='64-QAM', ch='rayleigh_mp', prof='Vehicular_B',
+         v=120.0, nsym=16, snrs=[25.0], full_snr=25.0, seed=6, drop_bits=11),
+    dict(name='siso_15mhz_pedb_static', bw=15.0, mod='16-QAM', ch='rayleigh_mp', prof='Pedestrian_B',
+         v=0.0, nsym=2, snrs=[15.0], full_snr=15.0, seed=7, big=True),
+]
+
+SIMO_CASES = [
+    # small full-tensor case crossing a 14-symbol slot boundary, ragged bit count
+    dict(name='simo_small_1p25mhz_veha', bw=1.25, mod='64-QAM', ch='rayleigh_mp', prof='Vehicular_A',
+         v=30.0, nsym=15, R=4, snrs=[10.0, 25.0], full_snr=25.0, seed=8, drop_bits=5),
+    dict(name='simo_awgn_5mhz_16qam_r2', bw=5.0, mod='16-QAM', ch='awgn', prof='Pedestrian_A', v=0.0,
+         nsym=3, R=2, snrs=[8.0], full_snr=8.0, seed=9),
+    dict(name='simo_10mhz_qpsk_vehb_r8', bw=10.0, mod='QPSK', ch='rayleigh_mp', prof='Vehicular_B',
+         v=120.0, nsym=2, R=8, snrs=[0.0], full_snr=0.0, seed=10, big=True),
+    # config 3: SIMO 1x4 MRC 20 MHz 64-QAM Vehicular_A 30 km/h, one subframe
+    dict(name='simo_cfg3_20mhz_64qam_veha', bw=20.0, mod='64-QAM', ch='rayleigh_mp', prof='Vehicular_A',
+         v=30.0, nsym=14, R=4, snrs=[10.0, 20.0, 30.0], full_snr=20.0, seed=12, big=True),
+    # headline variant: Pedestrian_A 3 km/h ("EPA-style")
+    dict(name='simo_headline_20mhz_64qam_peda', bw=20.0, mod='64-QAM', ch='rayleigh_mp',
+         prof='Pedestrian_A', v=3.0, nsym=14, R=4, snrs=[0.0, 16.0, 30.0], full_snr=16.0, seed=13,
+         big=True),
+]
+
+BIG_RX_STRIDE = 8   # 'big' SIMO cases store every 8th sample of signal_rx

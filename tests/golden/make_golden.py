@@ -1,0 +1,147 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED
+reference (Darioxavierl/OFDM-LTE) from /root/reference.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference draws its channel phases and noise from NumPy's legacy global RNG,
+which every ResourceMapper.map_symbols() call re-seeds with cell_id
+(core/resource_mapper.py:148).  The draws are therefore a deterministic function
+of the configuration; the tests regenerate them with
+oracle.lte_oracle.ReferenceDraws instead of storing megabytes of noise.
+
+Large complex arrays are stored as complex64 (6e-8 relative rounding, well inside
+the 1e-5 parity budget); small ones as complex128.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+REF = '/root/reference'
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REF)
+
+from config import LTEConfig  # noqa: E402  (reference)
+from core.ofdm_core import OFDMSimulator  # noqa: E402  (reference)
+from core.resource_mapper import LTEResourceGrid, PilotPattern  # noqa: E402
+from core.modulator import QAMModulator  # noqa: E402
+
+sys.path.insert(0, HERE)
+from cases import SISO_CASES, SIMO_CASES, BIG_RX_STRIDE  # noqa: E402
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def make_bits(seed, n):
+    return np.random.RandomState(seed).randint(0, 2, n).astype(np.uint8)
+
+
+def nd_of(cfg):
+    return len(LTEResourceGrid(cfg.N, cfg.Nc).get_data_indices())
+
+
+def tables():
+    out = {}
+    for bw in (1.25, 2.5, 5.0, 10.0, 15.0, 20.0):
+        for cp in ('normal', 'extended'):
+            c = LTEConfig(bw, 15.0, 'QPSK', cp)
+            out[f'num_{bw}_{cp}'] = np.array([c.N, c.Nc, c.cp_length, c.fs], dtype=np.float64)
+        g = LTEResourceGrid(c.N, c.Nc)
+        out[f'data_idx_{bw}'] = g.get_data_indices().astype(np.int32)
+        out[f'pilot_idx_{bw}'] = g.get_pilot_indices().astype(np.int32)
+    c = LTEConfig(3.0, 15.0, 'QPSK')          # non-profile bandwidth, config.py:108-111
+    out['num_3.0_normal'] = np.array([c.N, c.Nc, c.cp_length, c.fs], dtype=np.float64)
+    c = LTEConfig(5.0, 7.5, 'QPSK', 'extended')
+    out['num_5.0_7.5_extended'] = np.array([c.N, c.Nc, c.cp_length, c.fs], dtype=np.float64)
+    for cell in range(4):
+        out[f'pilots_cell{cell}'] = PilotPattern(cell).generate_pilots(200)
+    for mod in ('QPSK', '16-QAM', '64-QAM'):
+        q = QAMModulator(mod)
+        out[f'const_{mod}'] = q.get_constellation()
+        b = int(np.log2(len(q.constellation)))
+        bits = make_bits(11, b * 257 - 1)                     # exercises the zero padding
+        out[f'mapbits_{mod}'] = bits
+        out[f'mapsyms_{mod}'] = q.bits_to_symbols(bits)
+        rs = np.random.RandomState(5)
+        y = (rs.standard_normal(600) + 1j * rs.standard_normal(600)) * 0.8
+        # exact ties and exact constellation points, plus the all-zero symbol
+        lv = np.unique(q.constellation.real)
+        mids = (lv[:-1] + lv[1:]) / 2 if len(lv) > 1 else np.array([0.0])
+        ties = np.array([a + 1j * bb for a in np.concatenate([mids, [0.0]])
+                         for bb in np.concatenate([lv, mids, [0.0]])])
+        y = np.concatenate([y, ties, q.constellation, [0j]])
+        out[f'demapsyms_{mod}'] = y
+        out[f'demapbits_{mod}'] = q.symbols_to_bits(y).astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, 'tables.npz'), **out)
+
+
+def n_bits_of(case, cfg):
+    n_per = cfg.Nc if case.get('mode') == 'simple' else nd_of(cfg)
+    return n_per * cfg.bits_per_symbol * case['nsym'] - case.get('drop_bits', 0)
+
+
+def siso_case(case):
+    cfg = LTEConfig(case['bw'], 15.0, case['mod'], case.get('cp_type', 'normal'))
+    sim = quiet(OFDMSimulator, cfg, channel_type=case['ch'], itu_profile=case['prof'], frequency_ghz=2.0,
+                velocity_kmh=case['v'], mode=case.get('mode', 'lte'),
+                enable_sc_fdm=case.get('sc_fdm', False), enable_equalization=case.get('equalize', True))
+    bits = make_bits(case['seed'], n_bits_of(case, cfg))
+    ctype = np.complex64 if case.get('big') else np.complex128
+    out = dict(bits=np.packbits(bits), nbits=len(bits))
+    for snr in case['snrs']:
+        if 'global_seed' in case:      # mode='simple' does not re-seed the global RNG itself
+            np.random.seed(case['global_seed'])
+        r = quiet(sim.simulate_siso, bits, snr_db=snr)
+        out[f'errors_{snr}'] = r['errors']
+        out[f'bits_rx_{snr}'] = np.packbits(r['bits_received_array'].astype(np.uint8))
+        out[f'papr_db_{snr}'] = r['papr_db']
+        if snr == case['full_snr']:
+            out['signal_tx'] = r['signal_tx'].astype(ctype)
+            out['signal_rx'] = r['signal_rx'].astype(ctype)
+            out['symbols_rx'] = r['symbols_rx'].astype(ctype)
+    np.savez_compressed(os.path.join(HERE, case['name'] + '.npz'), **out)
+    print(case['name'], {s: int(out[f'errors_{s}']) for s in case['snrs']})
+
+
+def simo_case(case):
+    cfg = LTEConfig(case['bw'], 15.0, case['mod'], 'normal')
+    sim = quiet(OFDMSimulator, cfg, channel_type=case['ch'], itu_profile=case['prof'], frequency_ghz=2.0,
+                velocity_kmh=case['v'])
+    bits = make_bits(case['seed'], n_bits_of(case, cfg))
+    big = case.get('big')
+    ctype = np.complex64 if big else np.complex128
+    out = dict(bits=np.packbits(bits), nbits=len(bits))
+    for snr in case['snrs']:
+        r = quiet(sim.simulate_simo, bits, snr_db=snr, num_rx=case['R'], parallel=False)
+        out[f'errors_{snr}'] = r['errors']
+        out[f'bits_rx_{snr}'] = np.packbits(r['bits_received_array'].astype(np.uint8))
+        if snr == case['full_snr']:
+            out['signal_tx'] = r['signal_tx'].astype(ctype)
+            rx = np.stack(r['signal_rx_list'])
+            out['signal_rx'] = (rx[:, ::BIG_RX_STRIDE] if big else rx).astype(ctype)
+            out['symbols_combined'] = r['symbols_rx_combined'].astype(ctype)
+            H = np.array(r['channel_estimates_per_antenna'])               # [R][S][N]
+            out['H'] = H[:, ::14, :].astype(ctype)                         # one per 14-symbol slot
+            out['papr_db'] = r['papr_db']
+    np.savez_compressed(os.path.join(HERE, case['name'] + '.npz'), **out)
+    print(case['name'], {s: int(out[f'errors_{s}']) for s in case['snrs']})
+
+
+def main():
+    tables()
+    for case in SISO_CASES:
+        siso_case(case)
+    for case in SIMO_CASES:
+        simo_case(case)
+
+
+if __name__ == '__main__':
+    main()

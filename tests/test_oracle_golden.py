@@ -1,0 +1,86 @@
+"""Pins oracle/lte_oracle.py against vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from cases import BIG_RX_STRIDE, SIMO_CASES, SISO_CASES
+from helpers import (golden_bits, golden_bits_rx, load_golden, oracle_simo, oracle_siso,
+                     reference_draws, rel_err)
+from oracle import lte_oracle as O
+
+TOL64 = 1e-12     # complex128 fixtures
+TOL32 = 2e-7      # fixtures stored as complex64
+
+
+def test_tables_match_reference():
+    g = load_golden('tables')
+    for bw in (1.25, 2.5, 5.0, 10.0, 15.0, 20.0):
+        for cp in ('normal', 'extended'):
+            n = O.Numerology(bw, 15.0, 'QPSK', cp)
+            assert [n.N, n.Nc, n.cp_length, n.fs] == list(g[f'num_{bw}_{cp}'])
+        d, p = O.grid_indices(n.N, n.Nc)
+        assert np.array_equal(d, g[f'data_idx_{bw}'])
+        assert np.array_equal(p, g[f'pilot_idx_{bw}'])
+    n = O.Numerology(3.0, 15.0, 'QPSK')
+    assert [n.N, n.Nc, n.cp_length, n.fs] == list(g['num_3.0_normal'])
+    n = O.Numerology(5.0, 7.5, 'QPSK', 'extended')
+    assert [n.N, n.Nc, n.cp_length, n.fs] == list(g['num_5.0_7.5_extended'])
+    for cell in range(4):
+        assert np.array_equal(O.pilots(cell, 200), g[f'pilots_cell{cell}'])
+        assert np.array_equal(O.pilots(cell, 50), g[f'pilots_cell{cell}'][:50])   # prefix property
+
+
+@pytest.mark.parametrize('mod', ['QPSK', '16-QAM', '64-QAM'])
+def test_qam_map_demap_match_reference(mod):
+    g = load_golden('tables')
+    assert np.array_equal(O.constellation(mod), g[f'const_{mod}'])
+    assert np.array_equal(O.qam_map(g[f'mapbits_{mod}'], mod), g[f'mapsyms_{mod}'])
+    assert np.array_equal(O.qam_demap(g[f'demapsyms_{mod}'], mod), g[f'demapbits_{mod}'])
+
+
+@pytest.mark.parametrize('case', SISO_CASES, ids=lambda c: c['name'])
+def test_siso_matches_reference(case):
+    g = load_golden(case['name'])
+    bits = golden_bits(g)
+    tol = TOL32 if case.get('big') else TOL64
+    for snr in case['snrs']:
+        o = oracle_siso(case, bits, snr)
+        assert o['errors'] == int(g[f'errors_{snr}'])
+        assert np.array_equal(o['bits_rx'], golden_bits_rx(g, snr))
+        assert abs(o['papr_db'] - float(g[f'papr_db_{snr}'])) < 1e-9
+        if snr == case['full_snr']:
+            assert rel_err(o['signal_tx'], g['signal_tx']) < tol
+            assert rel_err(o['signal_rx'], g['signal_rx']) < tol
+            assert rel_err(o['symbols_rx'], g['symbols_rx']) < tol
+
+
+@pytest.mark.parametrize('case', SIMO_CASES, ids=lambda c: c['name'])
+def test_simo_matches_reference(case):
+    g = load_golden(case['name'])
+    bits = golden_bits(g)
+    big = case.get('big')
+    tol = TOL32 if big else TOL64
+    for snr in case['snrs']:
+        o = oracle_simo(case, bits, snr)
+        assert o['errors'] == int(g[f'errors_{snr}'])
+        assert np.array_equal(o['bits_rx'], golden_bits_rx(g, snr))
+        if snr == case['full_snr']:
+            assert rel_err(o['signal_tx'], g['signal_tx']) < tol
+            rx = o['signal_rx'][:, ::BIG_RX_STRIDE] if big else o['signal_rx']
+            assert rel_err(rx, g['signal_rx']) < tol
+            assert rel_err(o['symbols_combined'], g['symbols_combined']) < tol
+            assert rel_err(o['H'][:, ::14, :], g['H']) < tol
+
+
+def test_injected_draws_equal_reference_draws():
+    """The replay interface (explicit phases / unit normals) reproduces the
+    reference's own global-RNG draws."""
+    case = SIMO_CASES[0]
+    g = load_golden(case['name'])
+    bits = golden_bits(g)
+    snr = case['full_snr']
+    n = len(g['signal_tx'])
+    phases, z = reference_draws(case, n, case['R'])
+    o = oracle_simo(case, bits, snr, phases=phases, z=z)
+    assert o['errors'] == int(g[f'errors_{snr}'])
+    assert rel_err(o['signal_rx'], g['signal_rx']) < TOL64
