@@ -1,0 +1,187 @@
+/*
+ * lte_b200.h -- C ABI of liblte_b200.so, the B200 (sm_100a) native engine for the
+ * LTE simulate-and-count-BER link chain.
+ *
+ * The reference (Darioxavierl/OFDM-LTE) is pure Python/NumPy and has no FFI of its
+ * own; each entry point below replaces the NumPy body of the reference function
+ * cited next to it (paths relative to the reference root).  INTEGRATION.md shows
+ * the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - Every function returns LTE_OK (0) or a negative LTE_ERR_* code; nothing throws.
+ *  - All data pointers are DEVICE pointers owned by the caller unless the name ends
+ *    in _host.  The library allocates only the per-plan constant tables.
+ *  - Launches are asynchronous on `stream` (a cudaStream_t passed as void*).
+ *  - Complex samples are interleaved float pairs (re, im): `lte_c32`.
+ *  - A "stream" is one link realisation: S OFDM symbols back to back, L = N + cp
+ *    samples each.  Batches are stream-major: [B][...].
+ *  - QAM symbols travel as one byte per symbol holding the natural-binary,
+ *    MSB-first constellation index (core/modulator.py:80-86).
+ *  - Frequency-domain tensors cover the bin window [k0, k0 + nk) of the N-point
+ *    grid (raw FFT-bin order, no fftshift -- core/resource_mapper.py:45-74);
+ *    LTE_WINDOW_FULL selects k0 = 0, nk = N, LTE_WINDOW_USEFUL the Nc occupied bins.
+ */
+#ifndef LTE_B200_H
+#define LTE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTE_OK 0
+#define LTE_ERR_INVALID_ARG (-1)
+#define LTE_ERR_UNSUPPORTED (-2)
+#define LTE_ERR_CUDA (-3)
+#define LTE_ERR_NO_DEVICE (-4)
+
+#define LTE_MAX_TAPS 8      /* config.py:34-60: longest ITU-R M.1225 profile has 8 taps */
+#define LTE_JAKES_TONES 16  /* core/rayleighchannel.py:20 (N_s = 16) */
+#define LTE_SLOT_SYMBOLS 14 /* core/lte_receiver.py:233 */
+#define LTE_MAX_RX 8
+#define LTE_MAX_TX 4
+
+#define LTE_WINDOW_FULL 0
+#define LTE_WINDOW_USEFUL 1
+
+typedef struct { float re, im; } lte_c32;
+typedef struct lte_plan lte_plan;
+
+/* Numerology of one link (config.py:101-130) plus the pilot table.
+ * pilots_host: [num_tx_pilot_sets][num_pilots] complex values, zero where a TX
+ * antenna does not own the pilot (core/resource_mapper.py:137-152,
+ * core/mimo_channel_estimator_periodic.py:75-106).  The host generates them
+ * because they come from NumPy's MT19937 stream. */
+typedef struct {
+    int32_t N;                 /* FFT size, power of two, 64..2048 */
+    int32_t Nc;                /* occupied subcarriers */
+    int32_t cp;                /* cyclic-prefix samples */
+    int32_t bits_per_symbol;   /* 2, 4 or 6 */
+    int32_t mode_simple;       /* 1: mode='simple' (symbols on bins 0..Nc-1, no pilots) */
+    int32_t num_tx_pilot_sets; /* 1 for SISO/SIMO */
+    double  fs;                /* sampling rate in Hz (config.py:114) */
+} lte_plan_desc;
+
+/* Tapped-delay-line description after the host-side table work
+ * (core/channel.py:162-186, core/rayleighchannel.py:16,52). */
+typedef struct {
+    int32_t num_taps;                 /* 0 => AWGN only (no fading) */
+    int32_t delay[LTE_MAX_TAPS];      /* int(round(delay_s * fs)) */
+    float   gain[LTE_MAX_TAPS];       /* faithful (double-converted) linear gains */
+    double  doppler_hz;               /* fD = v * fc / c (core/channel.py:141-143) */
+} lte_channel_desc;
+
+int lte_version(void);
+const char* lte_error_string(int code);
+
+/* Plan = device-resident constant tables: bin classes, pilot values, constellation
+ * levels, slicer thresholds, FFT twiddles.  Created on the current CUDA device. */
+int lte_plan_create(const lte_plan_desc* desc, const lte_c32* pilots_host, lte_plan** out);
+int lte_plan_destroy(lte_plan* plan);
+int lte_plan_num_data(const lte_plan* plan);    /* Nd (core/resource_mapper.py:80-83) */
+int lte_plan_num_pilots(const lte_plan* plan);  /* Np (core/resource_mapper.py:85-88) */
+/* copies the data / pilot bin indices to host arrays of Nd / Np int32 */
+int lte_plan_indices_host(const lte_plan* plan, int32_t* data_idx_host, int32_t* pilot_idx_host);
+int lte_plan_window(const lte_plan* plan, int window, int32_t* k0, int32_t* nk);
+
+/* --- bit <-> symbol-index helpers (core/modulator.py:74-84, :109-110) ---------- */
+/* bits: [B][nbits] bytes holding 0/1; idx: [B][nsym]; bits past nbits read as 0.
+ * lte_bits_to_indices only: nbits < 0 means each row is np.packbits() output
+ * (MSB-first bytes, ceil(-nbits/8) bytes per row) holding -nbits bits. */
+int lte_bits_to_indices(const lte_plan*, const uint8_t* bits, int64_t nbits, uint8_t* idx,
+                        int64_t nsym, int32_t B, void* stream);
+int lte_indices_to_bits(const lte_plan*, const uint8_t* idx, int64_t nsym, uint8_t* bits,
+                        int64_t nbits, int32_t B, void* stream);
+
+/* --- stage 1+2 TX: QAM map + resource grid + IFFT*sqrt(N) + CP -------------------
+ * replaces QAMModulator.bits_to_symbols (core/modulator.py:61-88),
+ * ResourceMapper.map_symbols (core/resource_mapper.py:181-223) and
+ * OFDMModulator._modulate_lte / modulate_stream (core/modulator.py:214-302).
+ * idx: [B][S][Nd] symbol indices, or (symbols != NULL) pre-computed complex data
+ * symbols [B*T][S][Nd] (SC-FDM precoded, SFBC/SM encoded), antenna t using pilot
+ * set t.  tx: [B*T][S*L].  qam_out (optional): [B][S][Nd] mapped constellation
+ * points.  stats (optional): [B*T][2] doubles = {max |x|^2, sum |x|^2}, accumulated with
+ * atomics, caller zeroes (OFDMTransmitter.calculate_papr, core/ofdm_core.py:114-147). */
+int lte_tx_map_ifft(const lte_plan*, const uint8_t* idx, const lte_c32* symbols, int32_t T,
+                    lte_c32* tx, lte_c32* qam_out, double* stats, int32_t B, int32_t S,
+                    void* stream);
+
+/* --- stage 3 channel: time-domain tapped delay line with per-sample Jakes fading
+ * replaces RayleighChannel.jakes_fading/.filter (core/rayleighchannel.py:20-58) for
+ * R receive antennas and T transmit antennas (OFDMChannel.transmit_simo,
+ * core/ofdm_core.py:361-412).  tx: [B][T][n]; phases: [B][R][T][taps][16] uniform
+ * draws u in [0,1) (phi = 2*pi*u); faded: [B][R][n], the sum over TX;
+ * power: [B][R] sum of |faded|^2 (double, accumulated with atomics, caller zeroes).
+ * With num_taps == 0 (channel_type 'awgn') the link is the identity: only `power`
+ * (= sum |tx|^2 for every antenna) is produced and `faded` is not written. */
+int lte_channel_tdl(const lte_plan*, const lte_channel_desc* ch, const lte_c32* tx,
+                    const float* phases, lte_c32* faded, double* power, int32_t B, int32_t R,
+                    int32_t T, int64_t n, void* stream);
+
+/* AWGN of AWGNChannel.transmit / RayleighMultiPathChannel.transmit
+ * (core/channel.py:46-66, :216-232): sigma = sqrt(power/n / snr_lin / 2) per row.
+ * z: [rows][n] unit normals (re, im) to replay the reference's draws, or NULL to
+ * draw them from Philox2x32-10 keyed (seed, row_id0 + row, sample).
+ * Output row i reads input row i / x_div, so R antennas can share one TX stream
+ * (x_div = R on the AWGN channel type, 1 otherwise); power: [rows]; snr_lin: [rows]. */
+int lte_awgn_add(const lte_plan*, const lte_c32* x, int32_t x_div, const double* power,
+                 const float* snr_lin, const lte_c32* z, uint64_t seed, uint64_t row_id0,
+                 lte_c32* y, int64_t rows, int64_t n, void* stream);
+
+/* --- stage 2 RX: CP strip + FFT/sqrt(N) -------------------------------------------
+ * replaces LTEReceiver._demodulate_ofdm_stream (core/lte_receiver.py:444-491).
+ * rx: [rows / rx_div][S*L] (row i reads input row i / rx_div); Y: [rows][S][nk] for
+ * the chosen window.
+ * Optional fused noise (engine mode): if power != NULL the kernel adds
+ * sigma*(z_re + j z_im) per sample before the FFT with the same sigma rule and
+ * Philox keying as lte_awgn_add (z == NULL) or the injected normals (z != NULL). */
+int lte_rx_fft(const lte_plan*, const lte_c32* rx, int32_t rx_div, const double* power,
+               const float* snr_lin, const lte_c32* z, uint64_t seed, uint64_t row_id0, lte_c32* Y, int window,
+               int64_t rows, int32_t S, void* stream);
+
+/* --- stage 4: CRS least squares + linear interpolation, one estimate per 14 symbols
+ * replaces LTEChannelEstimator.estimate_channel/_interpolate_channel
+ * (core/lte_receiver.py:40-133) and LTEReceiver._estimate_channel_periodic (:360-411).
+ * Y: [rows][S][nk]; H: [rows][ceil(S/14)][nk]; pilot_set selects the TX pilot table. */
+int lte_crs_ls_interp(const lte_plan*, const lte_c32* Y, lte_c32* H, int window, int pilot_set,
+                      int64_t rows, int32_t S, void* stream);
+
+/* --- stage 5 equalisers --------------------------------------------------------------
+ * ZF: Y/(H+1e-6) on data bins (LTEEqualizerZF.equalize, core/lte_receiver.py:154-180);
+ * H == NULL skips the division (enable_equalization=False, core/lte_receiver.py:294-300).
+ * MRC over R antennas: sum conj(H_r) Y_r / (sum |H_r|^2 + 1e-10)
+ * (OFDMSimulator._combine_symbols_mrc, core/ofdm_core.py:1405-1534).
+ * Y: [B][R][S][nk]; H: [B][R][ceil(S/14)][nk]; out: [B][S][Nd] data symbols. */
+int lte_equalize_zf(const lte_plan*, const lte_c32* Y, const lte_c32* H, lte_c32* out, int window,
+                    int64_t B, int32_t S, void* stream);
+int lte_equalize_mrc(const lte_plan*, const lte_c32* Y, const lte_c32* H, lte_c32* out, int window,
+                     int64_t B, int32_t R, int32_t S, void* stream);
+
+/* --- stage 6: hard demap + bit-error count -------------------------------------------
+ * replaces QAMModulator.symbols_to_bits (core/modulator.py:90-112) and
+ * OFDMReceiver.calculate_ber (core/ofdm_core.py:245-268).  syms: [B][nsym];
+ * idx_tx: [B][nsym] transmitted indices (may be NULL: demap only); idx_rx (optional):
+ * [B][nsym] decided indices; errors: [B] uint64, atomically accumulated (caller zeroes);
+ * only the first nbits bits of each stream are compared (core/ofdm_core.py:712-718). */
+int lte_demap_count(const lte_plan*, const lte_c32* syms, const uint8_t* idx_tx, uint8_t* idx_rx,
+                    unsigned long long* errors, int64_t nsym, int64_t nbits, int64_t B,
+                    void* stream);
+
+/* Fused stage 5+6 for the sweep engine: MRC -> slicer -> XOR/popcount without
+ * writing the combined symbols. */
+int lte_mrc_demap_count(const lte_plan*, const lte_c32* Y, const lte_c32* H, const uint8_t* idx_tx,
+                        unsigned long long* errors, int window, int64_t nbits, int64_t B, int32_t R,
+                        int32_t S, void* stream);
+
+/* Engine helper: Philox-generated uniform symbol indices [B][nsym] keyed (seed, stream id). */
+int lte_random_indices(const lte_plan*, uint8_t* idx, int64_t nsym, int64_t B, uint64_t seed,
+                       uint64_t stream_id0, void* stream);
+/* Engine helper: Philox-generated Jakes phase draws u in [0,1): [B][links][taps][16]. */
+int lte_random_phases(float* phases, int64_t count_per_stream, int64_t B, uint64_t seed,
+                      uint64_t stream_id0, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTE_B200_H */

@@ -1,0 +1,128 @@
+// Shared device/host definitions for liblte_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+
+#include "../../include/lte_b200.h"
+
+#define LTE_CHECK_CUDA(expr)                          \
+    do {                                              \
+        cudaError_t _e = (expr);                      \
+        if (_e != cudaSuccess) return lte_set_cuda_error(_e); \
+    } while (0)
+
+int lte_set_cuda_error(cudaError_t e);
+
+// bin_map encoding (one int16 per FFT bin, TX loader): <0 null, else data/pilot index
+#define BIN_NULL (-1)
+#define BIN_PILOT_FLAG 0x4000
+
+// Device view of a plan; passed to kernels by value.
+struct DevPlan {
+    int N, log2N, Nc, cp, L, Nd, Np, bps;
+    int k0_useful, nk_useful;       // occupied-bin window
+    const int16_t* bin_map;         // [N]
+    const int16_t* data_idx;        // [Nd]
+    const float2* pilots;           // [nsets][Np]  (zero where not owned)
+    // per pilot set: owned pilots (bin, 1/p) and the left-neighbour table for interpolation
+    const int16_t* pset_bin;        // [nsets][Np]
+    const float2* pset_inv;         // [nsets][Np]  1/p in the reference's sense (Y / p)
+    const int16_t* pset_seg;        // [nsets][N]   index of the owned pilot at or left of bin k, -1 before the first
+    const int* pset_cnt;            // [nsets]
+    const float2* twiddle;          // [N] exp(-2 pi i m / N)
+    float lev[8];                   // constellation axis levels in index order
+    float thr[7];                   // slicer thresholds, rounded towards -inf
+    int nlev;                       // 2, 4, 8
+    float inv_sqrt_n;
+};
+
+struct lte_plan {
+    lte_plan_desc desc;
+    DevPlan dev;
+    int device;
+    int nsets;
+    std::vector<int32_t> data_idx_h, pilot_idx_h;
+    void* blob;                     // single device allocation holding all tables
+};
+
+// ------------------------------------------------------------------ complex helpers
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+// conj(a) * b
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.x, b.y, -a.y * b.x));
+}
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+__device__ __forceinline__ float cabs2(float2 a) { return fmaf(a.x, a.x, a.y * a.y); }
+// a / b, IEEE division (no fast-math): used by ZF / MRC / LS so slicer inputs stay accurate
+__device__ __forceinline__ float2 cdiv(float2 a, float2 b) {
+    float d = cabs2(b);
+    float2 n = make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+    return make_float2(__fdiv_rn(n.x, d), __fdiv_rn(n.y, d));
+}
+
+// ------------------------------------------------------------------ Philox2x32-10
+// Counter-based generator (Salmon et al., SC'11).  One call -> 64 random bits.
+__host__ __device__ __forceinline__ void philox2x32_10(uint32_t key, uint32_t c0, uint32_t c1,
+                                                       uint32_t& r0, uint32_t& r1) {
+    const uint32_t M = 0xD256D193u, W = 0x9E3779B9u;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+#ifdef __CUDA_ARCH__
+        uint32_t hi = __umulhi(M, c0);
+#else
+        uint32_t hi = (uint32_t)(((uint64_t)M * c0) >> 32);
+#endif
+        uint32_t lo = M * c0;
+        c0 = hi ^ key ^ c1;
+        c1 = lo;
+        key += W;
+    }
+    r0 = c0;
+    r1 = c1;
+}
+
+// Key derivation: mixes the user seed with a domain tag so that bits, phases and
+// noise never share a stream.
+#define LTE_DOMAIN_NOISE 0x6e6f6973u
+#define LTE_DOMAIN_BITS 0x62697473u
+#define LTE_DOMAIN_PHASE 0x70686173u
+__host__ __device__ __forceinline__ uint32_t lte_key(uint64_t seed, uint32_t domain) {
+    uint32_t a, b;
+    philox2x32_10(domain, (uint32_t)seed, (uint32_t)(seed >> 32), a, b);
+    return a ^ b;
+}
+
+// One complex unit normal (re, im ~ N(0,1)) for (row, sample) by Box-Muller.
+__device__ __forceinline__ float2 lte_noise_sample(uint32_t key, uint32_t row, uint32_t sample) {
+    uint32_t r0, r1;
+    philox2x32_10(key, sample, row, r0, r1);
+    float u1 = ((float)(r0 >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), 24 bits
+    // extend the tail with the 8 low bits when u1 is in the lowest bucket
+    if ((r0 >> 8) == 0) u1 = ((float)(r0 & 0xffu) + 0.5f) * (1.0f / 4294967296.0f);
+    float ang = ((float)(r1 >> 8)) * (1.0f / 16777216.0f) - 0.5f;  // [-0.5, 0.5) turns
+    float rad = sqrtf(-1.3862943611198906f * __log2f(u1));         // sqrt(-2 ln u1)
+    float s, c;
+    __sincosf(6.283185307179586f * ang, &s, &c);
+    return make_float2(rad * c, rad * s);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// sigma of the reference's AWGN: sqrt(mean_power / snr_lin / 2)   (core/channel.py:52,58)
+__device__ __forceinline__ float lte_sigma(double power_sum, double n, float snr_lin) {
+    return (float)sqrt(power_sum / n / (double)snr_lin / 2.0);
+}

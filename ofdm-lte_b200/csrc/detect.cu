@@ -1,0 +1,303 @@
+// Stage 4 (CRS LS + linear interpolation), stage 5 (ZF / MRC) and stage 6 (hard demap +
+// bit-error count), plus the bit <-> symbol-index helpers of the reference-facing API.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------ bits <-> indices
+// core/modulator.py:74-84: zero-pad, read b bits MSB first.
+__global__ void bits_to_indices_kernel(const uint8_t* __restrict__ bits, long long nbits, int packed,
+                                       uint8_t* __restrict__ idx, long long nsym, int bps, long long total) {
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const long long b = g / nsym, q = g % nsym;
+        const long long row_bytes = packed ? (nbits + 7) / 8 : nbits;
+        const uint8_t* src = bits + (size_t)b * row_bytes;
+        int v = 0;
+        for (int i = 0; i < bps; ++i) {
+            const long long bi = q * bps + i;
+            int bit = 0;
+            if (bi < nbits) bit = packed ? (src[bi >> 3] >> (7 - (bi & 7))) & 1 : (src[bi] & 1);
+            v = (v << 1) | bit;
+        }
+        idx[g] = (uint8_t)v;
+    }
+}
+
+// core/modulator.py:109-110: format(idx, '0{b}b'); output truncated to nbits.
+__global__ void indices_to_bits_kernel(const uint8_t* __restrict__ idx, long long nsym, uint8_t* __restrict__ bits,
+                                       long long nbits, int bps, long long total) {
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const long long b = g / nbits, bi = g % nbits;
+        const long long q = bi / bps;
+        const int i = (int)(bi % bps);
+        const int v = q < nsym ? idx[(size_t)b * nsym + q] : 0;
+        bits[g] = (uint8_t)((v >> (bps - 1 - i)) & 1);
+    }
+}
+
+static unsigned grid_for(long long total, int threads) {
+    long long g = (total + threads - 1) / threads;
+    if (g > 148LL * 32) g = 148LL * 32;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+extern "C" int lte_bits_to_indices(const lte_plan* p, const uint8_t* bits, int64_t nbits, uint8_t* idx,
+                                   int64_t nsym, int32_t B, void* stream) {
+    if (!p || !bits || !idx || nsym < 1 || B < 0) return LTE_ERR_INVALID_ARG;
+    if (B == 0) return LTE_OK;
+    const int packed = nbits < 0;        // negative nbits: rows are np.packbits() bytes
+    const long long nb = packed ? -nbits : nbits;
+    const long long total = (long long)B * nsym;
+    bits_to_indices_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(bits, nb, packed, idx, nsym,
+                                                                                  p->dev.bps, total);
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}
+
+extern "C" int lte_indices_to_bits(const lte_plan* p, const uint8_t* idx, int64_t nsym, uint8_t* bits,
+                                   int64_t nbits, int32_t B, void* stream) {
+    if (!p || !bits || !idx || nsym < 1 || nbits < 1 || B < 0) return LTE_ERR_INVALID_ARG;
+    if (B == 0) return LTE_OK;
+    const long long total = (long long)B * nbits;
+    indices_to_bits_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(idx, nsym, bits, nbits,
+                                                                                  p->dev.bps, total);
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}
+
+// ------------------------------------------------------------------------------ stage 4
+// core/lte_receiver.py:62-87 (LS at the pilots) and :98-133 (edge hold + np.linspace).
+// One CTA per (row, slot); the estimate comes from the slot's first symbol (:380-406).
+__global__ void __launch_bounds__(256)
+crs_ls_interp_kernel(const DevPlan P, const float2* __restrict__ Y, float2* __restrict__ H, int k0, int nk,
+                     int set, int S, int nslot) {
+    extern __shared__ float2 hp[];      // LS estimates at the owned pilots
+    const long long row = blockIdx.x / nslot;
+    const int slot = blockIdx.x % nslot;
+    const float2* y = Y + ((size_t)row * S + (size_t)slot * LTE_SLOT_SYMBOLS) * nk;
+    const int cnt = P.pset_cnt[set];
+    const int16_t* pbin = P.pset_bin + (size_t)set * P.Np;
+    const float2* pinv = P.pset_inv + (size_t)set * P.Np;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) hp[i] = cmul(y[pbin[i] - k0], pinv[i]);
+    __syncthreads();
+    const int16_t* seg = P.pset_seg + (size_t)set * P.N;
+    float2* h = H + ((size_t)row * nslot + slot) * nk;
+    for (int kk = threadIdx.x; kk < nk; kk += blockDim.x) {
+        const int k = kk + k0;
+        const int lo = seg[k];
+        float2 v;
+        if (lo < 0) v = hp[0];
+        else if (lo >= cnt - 1) v = hp[cnt - 1];
+        else {
+            const int i1 = pbin[lo], i2 = pbin[lo + 1];
+            const float2 a = hp[lo], b = hp[lo + 1];
+            const float div = (float)(i2 - i1), t = (float)(k - i1);
+            // np.linspace: start + i * (delta / div)
+            v = make_float2(fmaf(t, __fdiv_rn(b.x - a.x, div), a.x), fmaf(t, __fdiv_rn(b.y - a.y, div), a.y));
+            if (k == i1) v = a;
+        }
+        h[kk] = v;
+    }
+}
+
+extern "C" int lte_crs_ls_interp(const lte_plan* p, const lte_c32* Y, lte_c32* H, int window, int pilot_set,
+                                 int64_t rows, int32_t S, void* stream) {
+    if (!p || !Y || !H || rows < 0 || S < 1) return LTE_ERR_INVALID_ARG;
+    if (p->dev.Np == 0 || pilot_set < 0 || pilot_set >= p->nsets) return LTE_ERR_INVALID_ARG;
+    int32_t k0, nk;
+    int rc = lte_plan_window(p, window, &k0, &nk);
+    if (rc) return rc;
+    if (rows == 0) return LTE_OK;
+    const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
+    crs_ls_interp_kernel<<<(unsigned)(rows * nslot), 256, sizeof(float2) * p->dev.Np, (cudaStream_t)stream>>>(
+        p->dev, (const float2*)Y, (float2*)H, k0, nk, pilot_set, S, nslot);
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}
+
+// ------------------------------------------------------------------------------ slicer
+// argmin_i |c_i - y| with first-minimum ties (core/modulator.py:103-106) == per-axis nearest
+// level; thresholds are rounded towards -inf so `y > thr` equals `y > exact midpoint`, and a
+// tie at y == 0 picks the lower level (16/64-QAM) or the positive one (QPSK).
+__device__ __forceinline__ int slice_axis(const DevPlan& P, float y) {
+    if (P.nlev == 2) return y < 0.f ? 1 : 0;
+    int l = 0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) l += (i < P.nlev - 1 && y > P.thr[i]) ? 1 : 0;
+    return l;
+}
+__device__ __forceinline__ int slice_symbol(const DevPlan& P, float2 y) {
+    return (slice_axis(P, y.x) << (P.bps >> 1)) | slice_axis(P, y.y);
+}
+// number of differing bits among the first `valid` (MSB-first) bits of two b-bit indices
+__device__ __forceinline__ int bit_errors(int a, int b, int bps, long long valid) {
+    if (valid <= 0) return 0;
+    int x = a ^ b;
+    if (valid < bps) x &= ~((1 << (bps - (int)valid)) - 1);
+    return __popc(x);
+}
+
+__device__ __forceinline__ void block_add_errors(unsigned int e, unsigned long long* dst) {
+    e = (unsigned int)__reduce_add_sync(0xffffffffu, e);
+    __shared__ unsigned int red[32];
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if ((threadIdx.x & 31) == 0) red[w] = e;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned int t = threadIdx.x < nw ? red[threadIdx.x] : 0u;
+        t = (unsigned int)__reduce_add_sync(0xffffffffu, t);
+        if (threadIdx.x == 0 && t) atomicAdd(dst, (unsigned long long)t);
+    }
+}
+
+// ------------------------------------------------------------------------------ stage 6
+__global__ void __launch_bounds__(256)
+demap_count_kernel(const DevPlan P, const float2* __restrict__ syms, const uint8_t* __restrict__ idx_tx,
+                   uint8_t* __restrict__ idx_rx, unsigned long long* __restrict__ errors, long long nsym,
+                   long long nbits, int gx) {
+    const long long b = blockIdx.x / gx;
+    const int bx = blockIdx.x % gx;
+    unsigned int e = 0;
+    for (long long q = (long long)bx * blockDim.x + threadIdx.x; q < nsym; q += (long long)gx * blockDim.x) {
+        const size_t o = (size_t)b * nsym + q;
+        const int d = slice_symbol(P, syms[o]);
+        if (idx_rx) idx_rx[o] = (uint8_t)d;
+        if (idx_tx) e += bit_errors(d, idx_tx[o], P.bps, nbits - q * P.bps);
+    }
+    if (errors) block_add_errors(e, &errors[b]);
+}
+
+extern "C" int lte_demap_count(const lte_plan* p, const lte_c32* syms, const uint8_t* idx_tx, uint8_t* idx_rx,
+                               unsigned long long* errors, int64_t nsym, int64_t nbits, int64_t B, void* stream) {
+    if (!p || !syms || nsym < 1 || B < 0 || (idx_tx && !errors)) return LTE_ERR_INVALID_ARG;
+    if (B == 0) return LTE_OK;
+    int gx = (int)((nsym + 256 * 4 - 1) / (256 * 4));
+    if (gx < 1) gx = 1;
+    demap_count_kernel<<<(unsigned)((long long)gx * B), 256, 0, (cudaStream_t)stream>>>(
+        p->dev, (const float2*)syms, idx_tx, idx_rx, idx_tx ? errors : nullptr, nsym, nbits, gx);
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}
+
+// ------------------------------------------------------------------------------ stage 5
+// ZF: Y / (H + 1e-6) (core/lte_receiver.py:174), gathered at the data bins (:303-316).
+__global__ void __launch_bounds__(256)
+zf_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restrict__ H, float2* __restrict__ out,
+          int k0, int nk, int S, int nslot, long long total) {
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(g % P.Nd);
+        const long long bs = g / P.Nd;            // b*S + s
+        const int s = (int)(bs % S);
+        const long long b = bs / S;
+        const int kk = P.data_idx[d] - k0;
+        float2 y = Y[(size_t)bs * nk + kk];
+        if (H) {
+            float2 h = H[((size_t)b * nslot + s / LTE_SLOT_SYMBOLS) * nk + kk];
+            h.x += 1e-6f;
+            y = cdiv(y, h);
+        }
+        out[g] = y;
+    }
+}
+
+extern "C" int lte_equalize_zf(const lte_plan* p, const lte_c32* Y, const lte_c32* H, lte_c32* out, int window,
+                               int64_t B, int32_t S, void* stream) {
+    if (!p || !Y || !out || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
+    int32_t k0, nk;
+    int rc = lte_plan_window(p, window, &k0, &nk);
+    if (rc) return rc;
+    if (B == 0) return LTE_OK;
+    const long long total = (long long)B * S * p->dev.Nd;
+    const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
+    zf_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p->dev, (const float2*)Y, (const float2*)H,
+                                                                     (float2*)out, k0, nk, S, nslot, total);
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}
+
+// MRC (core/ofdm_core.py:1484-1532): thread = (stream, data bin); H of the slot is held in
+// registers while the thread walks the slot's symbols, so H is read once per 14 symbols.
+template <int R, bool COUNT>
+__global__ void __launch_bounds__(128)
+mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restrict__ H, float2* __restrict__ out,
+           const uint8_t* __restrict__ idx_tx, unsigned long long* __restrict__ errors, int k0, int nk, int S,
+           int nslot, long long nbits, int gx) {
+    const long long b = blockIdx.x / gx;
+    const int d = (blockIdx.x % gx) * blockDim.x + threadIdx.x;
+    unsigned int e = 0;
+    if (d < P.Nd) {
+        const int kk = P.data_idx[d] - k0;
+        for (int slot = 0; slot < nslot; ++slot) {
+            float2 h[R];
+            float den = 0.f;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                h[r] = H[(((size_t)b * R + r) * nslot + slot) * nk + kk];
+                den += cabs2(h[r]);
+            }
+            den += 1e-10f;
+            const int s_end = min(S, (slot + 1) * LTE_SLOT_SYMBOLS);
+            for (int s = slot * LTE_SLOT_SYMBOLS; s < s_end; ++s) {
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float2 y = Y[(((size_t)b * R + r) * S + s) * nk + kk];
+                    const float2 t = cmulc(h[r], y);
+                    acc.x += t.x;
+                    acc.y += t.y;
+                }
+                const float2 c = make_float2(__fdiv_rn(acc.x, den), __fdiv_rn(acc.y, den));
+                const size_t o = ((size_t)b * S + s) * P.Nd + d;
+                if (COUNT) {
+                    const long long q = (long long)s * P.Nd + d;
+                    e += bit_errors(slice_symbol(P, c), idx_tx[o], P.bps, nbits - q * P.bps);
+                } else {
+                    out[o] = c;
+                }
+            }
+        }
+    }
+    if (COUNT) block_add_errors(e, &errors[b]);
+}
+
+template <bool COUNT>
+static int launch_mrc(const lte_plan* p, const lte_c32* Y, const lte_c32* H, lte_c32* out, const uint8_t* idx_tx,
+                      unsigned long long* errors, int window, int64_t nbits, int64_t B, int32_t R, int32_t S,
+                      void* stream) {
+    int32_t k0, nk;
+    int rc = lte_plan_window(p, window, &k0, &nk);
+    if (rc) return rc;
+    if (B == 0) return LTE_OK;
+    const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
+    const int gx = (p->dev.Nd + 127) / 128;
+    const unsigned grid = (unsigned)((long long)gx * B);
+    cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_MRC(RR)                                                                                        \
+    case RR:                                                                                                  \
+        mrc_kernel<RR, COUNT><<<grid, 128, 0, st>>>(p->dev, (const float2*)Y, (const float2*)H, (float2*)out, \
+                                                    idx_tx, errors, k0, nk, S, nslot, nbits, gx);             \
+        break;
+    switch (R) {
+        LAUNCH_MRC(1) LAUNCH_MRC(2) LAUNCH_MRC(3) LAUNCH_MRC(4) LAUNCH_MRC(5) LAUNCH_MRC(6) LAUNCH_MRC(7)
+        LAUNCH_MRC(8)
+        default: return LTE_ERR_INVALID_ARG;
+    }
+#undef LAUNCH_MRC
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}
+
+extern "C" int lte_equalize_mrc(const lte_plan* p, const lte_c32* Y, const lte_c32* H, lte_c32* out, int window,
+                                int64_t B, int32_t R, int32_t S, void* stream) {
+    if (!p || !Y || !H || !out || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
+    return launch_mrc<false>(p, Y, H, out, nullptr, nullptr, window, 0, B, R, S, stream);
+}
+
+extern "C" int lte_mrc_demap_count(const lte_plan* p, const lte_c32* Y, const lte_c32* H, const uint8_t* idx_tx,
+                                   unsigned long long* errors, int window, int64_t nbits, int64_t B, int32_t R,
+                                   int32_t S, void* stream) {
+    if (!p || !Y || !H || !idx_tx || !errors || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
+    return launch_mrc<true>(p, Y, H, nullptr, idx_tx, errors, window, nbits, B, R, S, stream);
+}

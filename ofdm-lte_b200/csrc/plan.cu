@@ -1,0 +1,198 @@
+// Plan creation: host-side table work of the reference's L0/L1 layers
+// (config.py:101-130, core/resource_mapper.py:45-111, core/modulator.py:28-59)
+// uploaded once per configuration as device constant tables.
+#include <math.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+static thread_local cudaError_t g_last_cuda = cudaSuccess;
+
+int lte_set_cuda_error(cudaError_t e) {
+    g_last_cuda = e;
+    cudaGetLastError();   // clear the sticky-less error state
+    return LTE_ERR_CUDA;
+}
+
+extern "C" int lte_version(void) { return 100; }
+
+extern "C" const char* lte_error_string(int code) {
+    switch (code) {
+        case LTE_OK: return "ok";
+        case LTE_ERR_INVALID_ARG: return "invalid argument";
+        case LTE_ERR_UNSUPPORTED: return "unsupported configuration";
+        case LTE_ERR_CUDA: return cudaGetErrorString(g_last_cuda);
+        case LTE_ERR_NO_DEVICE: return "no CUDA device";
+        default: return "unknown error";
+    }
+}
+
+static float round_down_f32(double x) {
+    float f = (float)x;
+    if ((double)f > x) f = nextafterf(f, -INFINITY);
+    return f;
+}
+
+extern "C" int lte_plan_create(const lte_plan_desc* d, const lte_c32* pilots_host, lte_plan** out) {
+    if (!d || !out) return LTE_ERR_INVALID_ARG;
+    const int N = d->N, Nc = d->Nc;
+    if (N < 64 || N > 2048 || (N & (N - 1))) return LTE_ERR_UNSUPPORTED;
+    if (Nc < 1 || Nc > N || d->cp < 0 || d->cp > N) return LTE_ERR_INVALID_ARG;
+    if (d->bits_per_symbol != 2 && d->bits_per_symbol != 4 && d->bits_per_symbol != 6)
+        return LTE_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return LTE_ERR_NO_DEVICE;
+    }
+    const int nsets = d->mode_simple ? 1 : (d->num_tx_pilot_sets < 1 ? 1 : d->num_tx_pilot_sets);
+    if (nsets > LTE_MAX_TX) return LTE_ERR_INVALID_ARG;
+
+    lte_plan* p = new lte_plan();
+    p->desc = *d;
+    p->nsets = nsets;
+    cudaGetDevice(&p->device);
+
+    // --- bin classes (core/resource_mapper.py:57-74) -------------------------------
+    std::vector<int16_t> bin_map(N, BIN_NULL);
+    int k0, nk;
+    if (d->mode_simple) {          // core/modulator.py:192-212: symbols on bins 0..Nc-1
+        for (int k = 0; k < Nc; ++k) { bin_map[k] = (int16_t)k; p->data_idx_h.push_back(k); }
+        k0 = 0; nk = Nc;
+    } else {
+        const int gl = (N - Nc) / 2, gr = N - Nc - gl, dc = N / 2;
+        for (int k = 0; k < N; ++k) {
+            if (k < gl || k >= N - gr || k == dc) continue;
+            if ((k - gl) % 6 == 3) {
+                bin_map[k] = (int16_t)(BIN_PILOT_FLAG | (int)p->pilot_idx_h.size());
+                p->pilot_idx_h.push_back(k);
+            } else {
+                bin_map[k] = (int16_t)p->data_idx_h.size();
+                p->data_idx_h.push_back(k);
+            }
+        }
+        k0 = gl; nk = Nc;
+    }
+    const int Nd = (int)p->data_idx_h.size(), Np = (int)p->pilot_idx_h.size();
+    if (Np > 0 && !pilots_host) { delete p; return LTE_ERR_INVALID_ARG; }
+
+    // --- pilot sets: owned pilots, LS inverses, interpolation segments ---------------
+    std::vector<float2> pilots((size_t)nsets * (Np ? Np : 1), make_float2(0.f, 0.f));
+    std::vector<int16_t> pset_bin((size_t)nsets * (Np ? Np : 1), 0);
+    std::vector<float2> pset_inv((size_t)nsets * (Np ? Np : 1), make_float2(0.f, 0.f));
+    std::vector<int16_t> pset_seg((size_t)nsets * N, -1);
+    std::vector<int> pset_cnt(nsets, 0);
+    for (int s = 0; s < nsets; ++s) {
+        int cnt = 0;
+        for (int i = 0; i < Np; ++i) {
+            lte_c32 v = pilots_host[(size_t)s * Np + i];
+            pilots[(size_t)s * Np + i] = make_float2(v.re, v.im);
+            if (v.re != 0.f || v.im != 0.f) {
+                pset_bin[(size_t)s * Np + cnt] = (int16_t)p->pilot_idx_h[i];
+                double den = (double)v.re * v.re + (double)v.im * v.im;
+                pset_inv[(size_t)s * Np + cnt] = make_float2((float)(v.re / den), (float)(-v.im / den));
+                ++cnt;
+            }
+        }
+        pset_cnt[s] = cnt;
+        int lo = -1;
+        for (int k = 0; k < N; ++k) {
+            while (lo + 1 < cnt && pset_bin[(size_t)s * Np + lo + 1] <= k) ++lo;
+            pset_seg[(size_t)s * N + k] = (int16_t)lo;
+        }
+    }
+
+    // --- twiddles exp(-2 pi i m / N) from double ---------------------------------------
+    std::vector<float2> tw(N);
+    for (int m = 0; m < N; ++m) {
+        double a = -2.0 * M_PI * (double)m / (double)N;
+        tw[m] = make_float2((float)cos(a), (float)sin(a));
+    }
+
+    // --- single device blob -------------------------------------------------------------
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off_bin = 0;
+    size_t off_didx = align(off_bin + sizeof(int16_t) * N);
+    size_t off_pil = align(off_didx + sizeof(int16_t) * (Nd ? Nd : 1));
+    size_t off_pbin = align(off_pil + sizeof(float2) * pilots.size());
+    size_t off_pinv = align(off_pbin + sizeof(int16_t) * pset_bin.size());
+    size_t off_pseg = align(off_pinv + sizeof(float2) * pset_inv.size());
+    size_t off_pcnt = align(off_pseg + sizeof(int16_t) * pset_seg.size());
+    size_t off_tw = align(off_pcnt + sizeof(int) * nsets);
+    size_t total = align(off_tw + sizeof(float2) * N);
+    std::vector<char> host(total, 0);
+    std::vector<int16_t> didx16(Nd ? Nd : 1, 0);
+    for (int i = 0; i < Nd; ++i) didx16[i] = (int16_t)p->data_idx_h[i];
+    memcpy(&host[off_bin], bin_map.data(), sizeof(int16_t) * N);
+    memcpy(&host[off_didx], didx16.data(), sizeof(int16_t) * didx16.size());
+    memcpy(&host[off_pil], pilots.data(), sizeof(float2) * pilots.size());
+    memcpy(&host[off_pbin], pset_bin.data(), sizeof(int16_t) * pset_bin.size());
+    memcpy(&host[off_pinv], pset_inv.data(), sizeof(float2) * pset_inv.size());
+    memcpy(&host[off_pseg], pset_seg.data(), sizeof(int16_t) * pset_seg.size());
+    memcpy(&host[off_pcnt], pset_cnt.data(), sizeof(int) * nsets);
+    memcpy(&host[off_tw], tw.data(), sizeof(float2) * N);
+    if (cudaMalloc(&p->blob, total) != cudaSuccess ||
+        cudaMemcpy(p->blob, host.data(), total, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaError_t e = cudaGetLastError();
+        delete p;
+        return lte_set_cuda_error(e);
+    }
+    char* b = (char*)p->blob;
+    DevPlan& D = p->dev;
+    memset(&D, 0, sizeof(D));
+    D.N = N; D.Nc = Nc; D.cp = d->cp; D.L = N + d->cp; D.Nd = Nd; D.Np = Np; D.bps = d->bits_per_symbol;
+    D.log2N = 0; while ((1 << D.log2N) < N) ++D.log2N;
+    D.k0_useful = k0; D.nk_useful = nk;
+    D.bin_map = (const int16_t*)(b + off_bin);
+    D.data_idx = (const int16_t*)(b + off_didx);
+    D.pilots = (const float2*)(b + off_pil);
+    D.pset_bin = (const int16_t*)(b + off_pbin);
+    D.pset_inv = (const float2*)(b + off_pinv);
+    D.pset_seg = (const int16_t*)(b + off_pseg);
+    D.pset_cnt = (const int*)(b + off_pcnt);
+    D.twiddle = (const float2*)(b + off_tw);
+    D.inv_sqrt_n = (float)(1.0 / sqrt((double)N));
+
+    // --- constellation axis levels and slicer thresholds (core/modulator.py:28-59) -----
+    if (D.bps == 2) {          // [1+1j, 1-1j, -1+1j, -1-1j]/sqrt(2): index bit 0 -> +, 1 -> -
+        D.nlev = 2;
+        D.lev[0] = (float)(1.0 / sqrt(2.0));
+        D.lev[1] = (float)(-1.0 / sqrt(2.0));
+    } else {
+        D.nlev = 1 << (D.bps / 2);
+        const double nrm = D.bps == 4 ? sqrt(10.0) : sqrt(42.0);
+        for (int i = 0; i < D.nlev; ++i) D.lev[i] = (float)((2 * i - (D.nlev - 1)) / nrm);
+        // midpoints; y > thr[i] (thr rounded towards -inf) <=> y > exact midpoint for every
+        // fp32 y, and a tie (y == 0) resolves to the lower level like np.argmin's first minimum
+        for (int i = 0; i < D.nlev - 1; ++i) D.thr[i] = round_down_f32((2 * i - (D.nlev - 2)) / nrm);
+    }
+    *out = p;
+    return LTE_OK;
+}
+
+extern "C" int lte_plan_destroy(lte_plan* p) {
+    if (!p) return LTE_OK;
+    if (p->blob) cudaFree(p->blob);
+    delete p;
+    return LTE_OK;
+}
+
+extern "C" int lte_plan_num_data(const lte_plan* p) { return p ? p->dev.Nd : LTE_ERR_INVALID_ARG; }
+extern "C" int lte_plan_num_pilots(const lte_plan* p) { return p ? p->dev.Np : LTE_ERR_INVALID_ARG; }
+
+extern "C" int lte_plan_indices_host(const lte_plan* p, int32_t* data_idx, int32_t* pilot_idx) {
+    if (!p) return LTE_ERR_INVALID_ARG;
+    if (data_idx) memcpy(data_idx, p->data_idx_h.data(), sizeof(int32_t) * p->data_idx_h.size());
+    if (pilot_idx) memcpy(pilot_idx, p->pilot_idx_h.data(), sizeof(int32_t) * p->pilot_idx_h.size());
+    return LTE_OK;
+}
+
+extern "C" int lte_plan_window(const lte_plan* p, int window, int32_t* k0, int32_t* nk) {
+    if (!p || !k0 || !nk) return LTE_ERR_INVALID_ARG;
+    if (window == LTE_WINDOW_FULL) { *k0 = 0; *nk = p->dev.N; }
+    else if (window == LTE_WINDOW_USEFUL) { *k0 = p->dev.k0_useful; *nk = p->dev.nk_useful; }
+    else return LTE_ERR_INVALID_ARG;
+    return LTE_OK;
+}

@@ -1,0 +1,271 @@
+"""Batched link-chain engine: torch tensors in HBM, stages launched through the C ABI.
+
+Shapes (B streams, S OFDM symbols per stream, L = N + cp, R/T antennas):
+    idx      uint8      [B, S*Nd]      natural-binary constellation indices
+    tx       complex64  [B*T, S*L]
+    faded    complex64  [B, R, S*L]
+    Y        complex64  [rows, S, nk]  window of the FFT grid (full or occupied bins)
+    H        complex64  [rows, ceil(S/14), nk]
+    errors   int64      [B]
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import tables
+
+
+def chan_for(channel_type, fs, itu_profile='Pedestrian_A', frequency_ghz=2.0, velocity_kmh=0.0,
+             gain_conversions=2, faithful_gains=True):
+    return tables.channel_desc(channel_type, fs, itu_profile, frequency_ghz, velocity_kmh,
+                               gain_conversions, faithful_gains)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class LinkEngine:
+    """One numerology + modulation + pilot layout on one GPU."""
+
+    def __init__(self, N, Nc, cp, bits_per_symbol, fs, mode='lte', pilot_sets=None, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("lte_b200.LinkEngine needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
+        self.N, self.Nc, self.cp, self.L = int(N), int(Nc), int(cp), int(N) + int(cp)
+        self.bps, self.fs = int(bits_per_symbol), float(fs)
+        self.simple = mode == 'simple'
+        if self.simple:
+            self.data_idx, self.pilot_idx = np.arange(self.Nc), np.zeros(0, dtype=np.int64)
+        else:
+            self.data_idx, self.pilot_idx = tables.grid_indices(self.N, self.Nc)
+        self.Nd, self.Np = len(self.data_idx), len(self.pilot_idx)
+        if pilot_sets is None:
+            pilot_sets = tables.pilot_values(0, self.Np)[None, :]
+        pilot_sets = np.ascontiguousarray(np.asarray(pilot_sets, dtype=np.complex64))
+        self.num_pilot_sets = pilot_sets.shape[0]
+        desc = nat.PlanDesc(self.N, self.Nc, self.cp, self.bps, 1 if self.simple else 0,
+                            self.num_pilot_sets, self.fs)
+        self._plan = C.c_void_p()
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib.lte_plan_create(C.byref(desc), pilot_sets.ctypes.data_as(C.c_void_p),
+                                              C.byref(self._plan)), 'lte_plan_create')
+        assert nat.lib.lte_plan_num_data(self._plan) == self.Nd
+        assert nat.lib.lte_plan_num_pilots(self._plan) == self.Np
+        self.gl = (self.N - self.Nc) // 2
+        self.launches = 0          # native kernels launched through this engine (bench accounting)
+
+    @classmethod
+    def from_config(cls, config, mode='lte', pilot_sets=None, device=None):
+        return cls(config.N, config.Nc, config.cp_length, config.bits_per_symbol, config.fs,
+                   mode=mode, pilot_sets=pilot_sets, device=device)
+
+    def __del__(self):
+        try:
+            if getattr(self, '_plan', None):
+                nat.lib.lte_plan_destroy(self._plan)
+                self._plan = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def window(self, window):
+        return (0, self.N) if window == nat.WINDOW_FULL else ((0, self.Nc) if self.simple else (self.gl, self.Nc))
+
+    def symbols_for_bits(self, nbits):
+        """OFDM symbols needed for nbits (reference core/modulator.py:264-275)."""
+        per = self.Nd * self.bps
+        return int(-(-int(nbits) // per))
+
+    def _empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    # ------------------------------------------------------------------ bits
+    def bits_to_indices(self, bits, nbits, S, packed=False):
+        """bits: uint8 [B, nbits] of 0/1 (or np.packbits rows if packed) -> idx [B, S*Nd]."""
+        B = bits.shape[0]
+        idx = self._empty((B, S * self.Nd), torch.uint8)
+        nat.check(nat.lib.lte_bits_to_indices(self._plan, _ptr(bits), -int(nbits) if packed else int(nbits),
+                                              _ptr(idx), S * self.Nd, B, self._stream()), 'lte_bits_to_indices')
+        self.launches += 1
+        return idx
+
+    def indices_to_bits(self, idx, nbits):
+        B, nsym = idx.shape
+        bits = self._empty((B, int(nbits)), torch.uint8)
+        nat.check(nat.lib.lte_indices_to_bits(self._plan, _ptr(idx), nsym, _ptr(bits), int(nbits), B,
+                                              self._stream()), 'lte_indices_to_bits')
+        self.launches += 1
+        return bits
+
+    def random_indices(self, B, S, seed, stream_id0=0, out=None):
+        idx = out if out is not None else self._empty((B, S * self.Nd), torch.uint8)
+        nat.check(nat.lib.lte_random_indices(self._plan, _ptr(idx), S * self.Nd, B, int(seed), int(stream_id0),
+                                             self._stream()), 'lte_random_indices')
+        self.launches += 1
+        return idx
+
+    def random_phases(self, B, per_stream, seed, stream_id0=0, out=None):
+        ph = out if out is not None else self._empty((B, per_stream), torch.float32)
+        nat.check(nat.lib.lte_random_phases(_ptr(ph), per_stream, B, int(seed), int(stream_id0), self._stream()),
+                  'lte_random_phases')
+        self.launches += 1
+        return ph
+
+    # ------------------------------------------------------------------ stage 1+2 TX
+    def modulate(self, S, idx=None, symbols=None, T=1, want_qam=False, want_stats=True, out=None, stats=None):
+        """-> (tx [B*T, S*L], qam [B, S*Nd] or None, stats [B*T, 2] float64 or None)."""
+        if idx is not None:
+            B = idx.shape[0]
+        else:
+            B = symbols.shape[0] // T
+        tx = out if out is not None else self._empty((B * T, S * self.L), torch.complex64)
+        qam = self._empty((B, S * self.Nd), torch.complex64) if (want_qam and idx is not None) else None
+        if want_stats:
+            if stats is None:
+                stats = torch.zeros((B * T, 2), dtype=torch.float64, device=self.device)
+            else:
+                stats.zero_()
+        else:
+            stats = None
+        nat.check(nat.lib.lte_tx_map_ifft(self._plan, _ptr(idx) if symbols is None else None, _ptr(symbols), T,
+                                          _ptr(tx), _ptr(qam), _ptr(stats), B, S, self._stream()),
+                  'lte_tx_map_ifft')
+        self.launches += 1
+        return tx, qam, stats
+
+    # ------------------------------------------------------------------ stage 3 channel
+    def channel(self, tx, chan, B, R, T=1, phases=None, out=None, power=None):
+        """-> (faded [B, R, n] or None for the AWGN channel type, power [B, R] float64)."""
+        n = tx.shape[-1]
+        if power is None:
+            power = torch.zeros((B, R), dtype=torch.float64, device=self.device)
+        else:
+            power.zero_()
+        faded = None
+        if chan.num_taps > 0:
+            faded = out if out is not None else self._empty((B, R, n), torch.complex64)
+            if phases is None:
+                raise ValueError("phases are required for a fading channel")
+        nat.check(nat.lib.lte_channel_tdl(self._plan, C.byref(chan), _ptr(tx), _ptr(phases), _ptr(faded),
+                                          _ptr(power), B, R, T, n, self._stream()), 'lte_channel_tdl')
+        self.launches += 1
+        return faded, power
+
+    def awgn(self, x, x_div, power, snr_lin, rows, z=None, seed=0, row_id0=0, out=None):
+        n = x.shape[-1]
+        y = out if out is not None else self._empty((rows, n), torch.complex64)
+        nat.check(nat.lib.lte_awgn_add(self._plan, _ptr(x), x_div, _ptr(power), _ptr(snr_lin), _ptr(z), int(seed),
+                                       int(row_id0), _ptr(y), rows, n, self._stream()), 'lte_awgn_add')
+        self.launches += 1
+        return y
+
+    # ------------------------------------------------------------------ stage 2 RX
+    def rx_fft(self, rx, rows, S, window=nat.WINDOW_FULL, rx_div=1, power=None, snr_lin=None, z=None, seed=0,
+               row_id0=0, out=None):
+        k0, nk = self.window(window)
+        Y = out if out is not None else self._empty((rows, S, nk), torch.complex64)
+        nat.check(nat.lib.lte_rx_fft(self._plan, _ptr(rx), rx_div, _ptr(power), _ptr(snr_lin), _ptr(z), int(seed),
+                                     int(row_id0), _ptr(Y), window, rows, S, self._stream()), 'lte_rx_fft')
+        self.launches += 1
+        return Y
+
+    # ------------------------------------------------------------------ stage 4
+    def estimate(self, Y, rows, S, window=nat.WINDOW_FULL, pilot_set=0, out=None):
+        k0, nk = self.window(window)
+        nslot = -(-S // nat.LTE_SLOT_SYMBOLS)
+        H = out if out is not None else self._empty((rows, nslot, nk), torch.complex64)
+        nat.check(nat.lib.lte_crs_ls_interp(self._plan, _ptr(Y), _ptr(H), window, pilot_set, rows, S,
+                                            self._stream()), 'lte_crs_ls_interp')
+        self.launches += 1
+        return H
+
+    # ------------------------------------------------------------------ stage 5
+    def zf(self, Y, H, B, S, window=nat.WINDOW_FULL, out=None):
+        o = out if out is not None else self._empty((B, S * self.Nd), torch.complex64)
+        nat.check(nat.lib.lte_equalize_zf(self._plan, _ptr(Y), _ptr(H), _ptr(o), window, B, S, self._stream()),
+                  'lte_equalize_zf')
+        self.launches += 1
+        return o
+
+    def mrc(self, Y, H, B, R, S, window=nat.WINDOW_FULL, out=None):
+        o = out if out is not None else self._empty((B, S * self.Nd), torch.complex64)
+        nat.check(nat.lib.lte_equalize_mrc(self._plan, _ptr(Y), _ptr(H), _ptr(o), window, B, R, S, self._stream()),
+                  'lte_equalize_mrc')
+        self.launches += 1
+        return o
+
+    # ------------------------------------------------------------------ stage 6
+    def demap_count(self, syms, idx_tx=None, nbits=None, want_idx=False, errors=None):
+        """-> (errors int64 [B] or None, idx_rx uint8 [B, nsym] or None)."""
+        B, nsym = syms.shape
+        idx_rx = self._empty((B, nsym), torch.uint8) if want_idx else None
+        if idx_tx is not None:
+            if errors is None:
+                errors = torch.zeros(B, dtype=torch.int64, device=self.device)
+            else:
+                errors.zero_()
+        nb = int(nbits) if nbits is not None else nsym * self.bps
+        nat.check(nat.lib.lte_demap_count(self._plan, _ptr(syms), _ptr(idx_tx), _ptr(idx_rx), _ptr(errors), nsym, nb,
+                                          B, self._stream()), 'lte_demap_count')
+        self.launches += 1
+        return errors, idx_rx
+
+    def mrc_demap_count(self, Y, H, idx_tx, B, R, S, nbits=None, window=nat.WINDOW_USEFUL, errors=None):
+        if errors is None:
+            errors = torch.zeros(B, dtype=torch.int64, device=self.device)
+        else:
+            errors.zero_()
+        nb = int(nbits) if nbits is not None else S * self.Nd * self.bps
+        nat.check(nat.lib.lte_mrc_demap_count(self._plan, _ptr(Y), _ptr(H), _ptr(idx_tx), _ptr(errors), window, nb,
+                                              B, R, S, self._stream()), 'lte_mrc_demap_count')
+        self.launches += 1
+        return errors
+
+    # ------------------------------------------------------------------ batched SIMO chain
+    def workspace(self, B, S, R, fading):
+        """Pre-allocated HBM buffers for `simo_ber` so a sweep re-uses them every step."""
+        k0, nk = self.window(nat.WINDOW_USEFUL)
+        nslot = -(-S // nat.LTE_SLOT_SYMBOLS)
+        n = S * self.L
+        ws = dict(B=B, S=S, R=R,
+                  idx=self._empty((B, S * self.Nd), torch.uint8),
+                  tx=self._empty((B, n), torch.complex64),
+                  stats=torch.zeros((B, 2), dtype=torch.float64, device=self.device),
+                  power=torch.zeros((B, R), dtype=torch.float64, device=self.device),
+                  Y=self._empty((B * R, S, nk), torch.complex64),
+                  H=self._empty((B * R, nslot, nk), torch.complex64),
+                  errors=torch.zeros(B, dtype=torch.int64, device=self.device))
+        if fading:
+            ws['faded'] = self._empty((B, R, n), torch.complex64)
+            ws['phases'] = self._empty((B, R * nat.LTE_MAX_TAPS * nat.LTE_JAKES_TONES), torch.float32)
+        return ws
+
+    def simo_ber(self, ws, chan, snr_lin_rows, seed, stream_id0=0, idx=None, nbits=None):
+        """One pass of the SIMO-MRC link chain over B independent streams.
+
+        ws: workspace(); snr_lin_rows: float32 [B*R] linear SNR per (stream, antenna);
+        idx: transmitted symbol indices [B, S*Nd] or None to draw them with Philox
+        keyed (seed, stream_id0 + b).  Returns the int64 [B] bit-error counts (in ws).
+        """
+        B, S, R = ws['B'], ws['S'], ws['R']
+        if idx is None:
+            idx = self.random_indices(B, S, seed, stream_id0, out=ws['idx'])
+        tx, _, _ = self.modulate(S, idx=idx, want_stats=False, out=ws['tx'])
+        if chan.num_taps > 0:
+            per = R * chan.num_taps * nat.LTE_JAKES_TONES
+            ph = self.random_phases(B, per, seed, stream_id0, out=ws['phases'].view(-1)[:B * per].view(B, per))
+            faded, power = self.channel(tx, chan, B, R, phases=ph, out=ws['faded'], power=ws['power'])
+            rx, div = faded, 1
+        else:
+            _, power = self.channel(tx, chan, B, R, power=ws['power'])
+            rx, div = tx, R
+        Y = self.rx_fft(rx, B * R, S, nat.WINDOW_USEFUL, rx_div=div, power=power, snr_lin=snr_lin_rows, seed=seed,
+                        row_id0=stream_id0 * R, out=ws['Y'])
+        H = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, out=ws['H'])
+        return self.mrc_demap_count(Y, H, idx, B, R, S, nbits=nbits, errors=ws['errors'])
