@@ -309,7 +309,7 @@ def time_stages(eng, ws, chan, snr_rows, idx, nbits, seed, B, S, R, nat, torch, 
         'tx_map_ifft': lambda: eng.modulate(S, idx=idx, want_stats=False, out=ws['tx']),
         'channel_tdl': lambda: eng.channel(ws['tx'], chan, B, R, phases=ph, out=ws['faded'], power=ws['power']),
         'rx_fft': lambda: eng.rx_fft(ws['faded'], B * R, S, nat.WINDOW_USEFUL, power=ws['power'], snr_lin=snr_rows,
-                                     seed=seed, out=ws['Y']),
+                                     seed=seed, out=ws['Y'], noise_domain=1),
         'crs_ls_interp': lambda: eng.estimate(ws['Y'], B * R, S, nat.WINDOW_USEFUL, out=ws['H']),
         'mrc_demap_count': lambda: eng.mrc_demap_count(ws['Y'], ws['H'], idx, B, R, S, nbits=nbits,
                                                        errors=ws['errors']),

@@ -133,11 +133,15 @@ int lte_awgn_add(const lte_plan*, const lte_c32* x, int32_t x_div, const double*
  * replaces LTEReceiver._demodulate_ofdm_stream (core/lte_receiver.py:444-491).
  * rx: [rows / rx_div][S*L] (row i reads input row i / rx_div); Y: [rows][S][nk] for
  * the chosen window.
- * Optional fused noise (engine mode): if power != NULL the kernel adds
- * sigma*(z_re + j z_im) per sample before the FFT with the same sigma rule and
- * Philox keying as lte_awgn_add (z == NULL) or the injected normals (z != NULL). */
+ * Optional fused noise (engine mode): if power != NULL the kernel adds AWGN with the
+ * sigma rule of lte_awgn_add.  noise_domain 0: sigma*(z_re + j z_im) per time sample
+ * before the FFT, from the injected normals z or (z == NULL) from Philox with the very
+ * keying of lte_awgn_add, so fused and unfused paths agree bit for bit.  noise_domain 1
+ * (z must be NULL): the same-variance white Gaussian noise is drawn directly on the
+ * output bins after the unitary FFT -- identical in distribution, fewer draws. */
 int lte_rx_fft(const lte_plan*, const lte_c32* rx, int32_t rx_div, const double* power,
-               const float* snr_lin, const lte_c32* z, uint64_t seed, uint64_t row_id0, lte_c32* Y, int window,
+               const float* snr_lin, const lte_c32* z, int32_t noise_domain, uint64_t seed,
+               uint64_t row_id0, lte_c32* Y, int window,
                int64_t rows, int32_t S, void* stream);
 
 /* --- stage 4: CRS least squares + linear interpolation, one estimate per 14 symbols

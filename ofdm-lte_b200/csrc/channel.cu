@@ -10,41 +10,45 @@
 #include "common.cuh"
 
 #define TDL_THREADS 256
-#define TDL_V 4                         // consecutive samples per thread
-#define TDL_TILE (TDL_THREADS * TDL_V)  // samples per CTA
-#define TDL_K 4                         // polynomial degree
 
 struct TdlParams {
     int num_taps;
     int delay[LTE_MAX_TAPS];
     float gain[LTE_MAX_TAPS];           // includes sqrt(2/16)
     double w_cyc[LTE_JAKES_TONES];      // fD cos(alpha_n) / fs   [cycles per sample]
-    int halo;                           // >= max delay, multiple of 4
-    int pb;                             // polynomial block length (power of two <= TDL_TILE)
+    int halo;                           // >= max delay, multiple of 8
+    int pb;                             // polynomial block length (power of two <= tile)
+    int xs_stride;                      // columns per shared-memory row, == 2 (mod 16)
 };
 
-template <int R>
-__global__ void __launch_bounds__(TDL_THREADS)
+// R receive antennas, V consecutive samples per thread, degree-K Taylor polynomial.
+// Shared-memory sample layout: sample s of the staged window lives at [s & 7][s >> 3], so a
+// warp reading "sample 8*t + c" for consecutive threads t touches consecutive float2 (no
+// bank conflicts for any tap delay) while the global loads that fill it stay coalesced.
+template <int R, int V, int K>
+__global__ void __launch_bounds__(TDL_THREADS, 2)
 tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float* __restrict__ phases,
            float2* __restrict__ faded, double* __restrict__ power, int T, long long n, int tiles) {
+    constexpr int TILE = TDL_THREADS * V;
+    constexpr int NC = 2 * K + 1;                 // K+1 value coefficients, K derivative coefficients
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: x tiles [T][halo + TILE] | coef [nblk][R*T*taps][K+1]
-    float2* sx = (float2*)smem_raw;
-    const int xs_stride = C.halo + TDL_TILE;
-    float2* coef = sx + (size_t)T * xs_stride;
-    const int nblk = TDL_TILE / C.pb;
-    const int nlt = R * T * C.num_taps;            // (rx, tx, tap) triples
+    float2* sx = (float2*)smem_raw;               // [T][8][xs_stride]
+    float2* coef = sx + (size_t)T * 8 * C.xs_stride;   // [nblk][R*T*taps][NC]
+    const int nblk = TILE / C.pb;
+    const int nlt = R * T * C.num_taps;
 
     const long long b = blockIdx.x / tiles;
-    const long long tile0 = (long long)(blockIdx.x % tiles) * TDL_TILE;
+    const long long tile0 = (long long)(blockIdx.x % tiles) * TILE;
     const int tid = threadIdx.x;
 
     // ---- stage the TX samples (with the delay halo) ---------------------------------
+    const int span = C.halo + TILE;
     for (int t = 0; t < T; ++t) {
         const float2* src = tx + ((size_t)b * T + t) * n;
-        for (int i = tid; i < xs_stride; i += TDL_THREADS) {
+        float2* dst = sx + (size_t)t * 8 * C.xs_stride;
+        for (int i = tid; i < span; i += TDL_THREADS) {
             const long long m = tile0 - C.halo + i;
-            sx[(size_t)t * xs_stride + i] = (m >= 0 && m < n) ? src[m] : make_float2(0.f, 0.f);
+            dst[(i & 7) * C.xs_stride + (i >> 3)] = (m >= 0 && m < n) ? __ldg(&src[m]) : make_float2(0.f, 0.f);
         }
     }
 
@@ -53,9 +57,9 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float* __rest
     const int items = nblk * nlt * LTE_JAKES_TONES;
     for (int it0 = 0; it0 < items; it0 += TDL_THREADS) {
         const int it = it0 + tid;
-        float2 a[TDL_K + 1];
+        float2 a[K + 1];
 #pragma unroll
-        for (int k = 0; k <= TDL_K; ++k) a[k] = make_float2(0.f, 0.f);
+        for (int k = 0; k <= K; ++k) a[k] = make_float2(0.f, 0.f);
         int blk = 0, trip = 0;
         if (it < items) {
             const int tone = it & (LTE_JAKES_TONES - 1);
@@ -68,16 +72,18 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float* __rest
             float sn, cs;
             sincospif(2.0f * (float)turns, &sn, &cs);
             const float x = (float)(6.283185307179586 * C.w_cyc[tone]);   // rad / sample
-            // c * (j x)^k / k!
-            const float x2 = x * x;
-            a[0] = make_float2(cs, sn);
-            a[1] = make_float2(-sn * x, cs * x);
-            a[2] = make_float2(-cs * x2 * 0.5f, -sn * x2 * 0.5f);
-            a[3] = make_float2(sn * x2 * x * (1.f / 6.f), -cs * x2 * x * (1.f / 6.f));
-            a[4] = make_float2(cs * x2 * x2 * (1.f / 24.f), sn * x2 * x2 * (1.f / 24.f));
+            // e^{j theta} (j x)^k / k!
+            float2 term = make_float2(cs, sn);
+            a[0] = term;
+#pragma unroll
+            for (int k = 1; k <= K; ++k) {
+                const float f = x / (float)k;
+                term = make_float2(-term.y * f, term.x * f);
+                a[k] = term;
+            }
         }
 #pragma unroll
-        for (int k = 0; k <= TDL_K; ++k) {
+        for (int k = 0; k <= K; ++k) {
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) {
                 a[k].x += __shfl_xor_sync(0xffffffffu, a[k].x, o);
@@ -86,43 +92,57 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float* __rest
         }
         if (it < items && (it & (LTE_JAKES_TONES - 1)) == 0) {
             const float g = C.gain[trip % C.num_taps];
+            float2* c = coef + ((size_t)blk * nlt + trip) * NC;
 #pragma unroll
-            for (int k = 0; k <= TDL_K; ++k)
-                coef[((size_t)blk * nlt + trip) * (TDL_K + 1) + k] = cscale(a[k], g);
+            for (int k = 0; k <= K; ++k) c[k] = cscale(a[k], g);
+#pragma unroll
+            for (int k = 1; k <= K; ++k) c[K + k] = cscale(a[k], g * (float)k);   // derivative: k c_k
         }
     }
     __syncthreads();
 
     // ---- y_r[m] = sum_t sum_i g_i h_{r,t,i}[m] x_t[m - d_i] ----------------------------
-    const int l0 = tid * TDL_V;                     // first local sample of this thread
+    const int l0 = tid * V;                         // first local sample of this thread
     const long long m0 = tile0 + l0;
     const int blk = l0 / C.pb;
-    // evaluate at the centre of the thread's V samples, then step linearly
-    const float tau = (float)(l0 - blk * C.pb) + 0.5f * (TDL_V - 1) - 0.5f * (C.pb - 1);
-    float2 acc[R][TDL_V];
+    // polynomial argument at the centre of the thread's V samples; linear stepping inside
+    const float tau = (float)(l0 - blk * C.pb) + 0.5f * (V - 1) - 0.5f * (C.pb - 1);
+    float2 acc[R][V];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int i = 0; i < TDL_V; ++i) acc[r][i] = make_float2(0.f, 0.f);
+        for (int i = 0; i < V; ++i) acc[r][i] = make_float2(0.f, 0.f);
 
     for (int t = 0; t < T; ++t) {
+        const float2* sxt = sx + (size_t)t * 8 * C.xs_stride;
         for (int tap = 0; tap < C.num_taps; ++tap) {
-            const float2* xp = sx + (size_t)t * xs_stride + C.halo + l0 - C.delay[tap];
-            float2 xv[TDL_V];
+            const int c0 = C.halo - C.delay[tap] + (V == 8 ? 0 : l0 & 7);
+            const int colbase = (V == 8) ? tid : (l0 >> 3);
+            float2 xv[V];
 #pragma unroll
-            for (int i = 0; i < TDL_V; ++i) xv[i] = xp[i];
+            for (int i = 0; i < V; ++i) {
+                const int cc = c0 + i;
+                xv[i] = sxt[(cc & 7) * C.xs_stride + colbase + (cc >> 3)];
+            }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const float2* c = coef + ((size_t)blk * nlt + (r * T + t) * C.num_taps + tap) * (TDL_K + 1);
-                const float2 c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4];
-                float2 h, dh;
-                h.x = fmaf(fmaf(fmaf(fmaf(c4.x, tau, c3.x), tau, c2.x), tau, c1.x), tau, c0.x);
-                h.y = fmaf(fmaf(fmaf(fmaf(c4.y, tau, c3.y), tau, c2.y), tau, c1.y), tau, c0.y);
-                dh.x = fmaf(fmaf(fmaf(4.f * c4.x, tau, 3.f * c3.x), tau, 2.f * c2.x), tau, c1.x);
-                dh.y = fmaf(fmaf(fmaf(4.f * c4.y, tau, 3.f * c3.y), tau, 2.f * c2.y), tau, c1.y);
+                const float2* c = coef + ((size_t)blk * nlt + (r * T + t) * C.num_taps + tap) * NC;
+                float2 h = c[K], dh = c[2 * K];
 #pragma unroll
-                for (int i = 0; i < TDL_V; ++i) {
-                    const float st = (float)i - 0.5f * (TDL_V - 1);
+                for (int k = K - 1; k >= 0; --k) {
+                    const float2 ck = c[k];
+                    h.x = fmaf(h.x, tau, ck.x);
+                    h.y = fmaf(h.y, tau, ck.y);
+                }
+#pragma unroll
+                for (int k = K - 1; k >= 1; --k) {
+                    const float2 dk = c[K + k];
+                    dh.x = fmaf(dh.x, tau, dk.x);
+                    dh.y = fmaf(dh.y, tau, dk.y);
+                }
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    const float st = (float)i - 0.5f * (V - 1);
                     const float2 hi = make_float2(fmaf(st, dh.x, h.x), fmaf(st, dh.y, h.y));
                     acc[r][i].x = fmaf(hi.x, xv[i].x, fmaf(-hi.y, xv[i].y, acc[r][i].x));
                     acc[r][i].y = fmaf(hi.x, xv[i].y, fmaf(hi.y, xv[i].x, acc[r][i].y));
@@ -138,16 +158,16 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float* __rest
     for (int r = 0; r < R; ++r) {
         float pw = 0.f;
         float2* dst = faded + ((size_t)b * R + r) * n + m0;
-        if (m0 + TDL_V <= n && vec) {
+        if (m0 + V <= n && vec) {
             float4* d4 = (float4*)dst;
 #pragma unroll
-            for (int i = 0; i < TDL_V; i += 2) {
+            for (int i = 0; i < V; i += 2) {
                 d4[i / 2] = make_float4(acc[r][i].x, acc[r][i].y, acc[r][i + 1].x, acc[r][i + 1].y);
                 pw += cabs2(acc[r][i]) + cabs2(acc[r][i + 1]);
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < TDL_V; ++i)
+            for (int i = 0; i < V; ++i)
                 if (m0 + i < n) { dst[i] = acc[r][i]; pw += cabs2(acc[r][i]); }
         }
         pw = warp_sum(pw);
@@ -213,35 +233,49 @@ extern "C" int lte_channel_tdl(const lte_plan* p, const lte_channel_desc* ch, co
         if (ch->delay[i] > dmax) dmax = ch->delay[i];
     }
     if (dmax > 4096) return LTE_ERR_UNSUPPORTED;
-    C.halo = (dmax + 3) & ~3;
+    C.halo = (dmax + 7) & ~7;
     const double fs = p->desc.fs;
     double wmax = 0.0;
     for (int nn = 0; nn < LTE_JAKES_TONES; ++nn) {   // alpha_n = 2 pi n / 16, n = 1..16
         C.w_cyc[nn] = ch->doppler_hz * cos(2.0 * M_PI * (double)(nn + 1) / LTE_JAKES_TONES) / fs;
         if (fabs(C.w_cyc[nn]) > wmax) wmax = fabs(C.w_cyc[nn]);
     }
-    // Taylor remainder (x^5/120 with x = 2 pi w PB/2) below 2e-8  =>  x < 0.075
-    C.pb = TDL_TILE;
-    while (C.pb > 32 && M_PI * wmax * C.pb > 0.075) C.pb >>= 1;
-    if (M_PI * wmax * C.pb > 0.075) return LTE_ERR_UNSUPPORTED;   // Doppler too high for this fs
-    const int nblk = TDL_TILE / C.pb;
-    const size_t smem = sizeof(float2) * ((size_t)T * (C.halo + TDL_TILE) +
-                                          (size_t)nblk * R * T * C.num_taps * (TDL_K + 1));
+    const int V = (R <= 4) ? 8 : 4;
+    const int tile = TDL_THREADS * V;
+    // Taylor remainder x^(K+1)/(K+1)! with x = 2 pi w PB/2 kept below 2e-8:
+    //   K = 2 needs x < 4.9e-3, K = 4 needs x < 0.075; PB is halved until K = 4 fits.
+    C.pb = tile;
+    int K = 2;
+    if (M_PI * wmax * C.pb > 4.9e-3) {
+        K = 4;
+        while (C.pb > 32 && M_PI * wmax * C.pb > 0.075) C.pb >>= 1;
+        if (M_PI * wmax * C.pb > 0.075) return LTE_ERR_UNSUPPORTED;   // Doppler too high for this fs
+    }
+    const int nblk = tile / C.pb;
+    const int ncols = (C.halo + tile) / 8;
+    C.xs_stride = ncols + ((2 - ncols % 16) + 16) % 16;
+    const size_t smem = sizeof(float2) * ((size_t)T * 8 * C.xs_stride +
+                                          (size_t)nblk * R * T * C.num_taps * (2 * K + 1));
     if (smem > 200 * 1024) return LTE_ERR_UNSUPPORTED;
-    const int tiles = (int)((n + TDL_TILE - 1) / TDL_TILE);
+    const int tiles = (int)((n + tile - 1) / tile);
     const unsigned grid = (unsigned)((long long)tiles * B);
-#define LAUNCH_TDL(RR)                                                                                   \
-    case RR: {                                                                                           \
-        auto k = tdl_kernel<RR>;                                                                         \
-        LTE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k<<<grid, TDL_THREADS, smem, st>>>(C, (const float2*)tx, phases, (float2*)faded, power, T,       \
-                                           (long long)n, tiles);                                         \
-    } break;
+#define LAUNCH_TDL_K(RR, VV, KK)                                                                          \
+    {                                                                                                     \
+        auto k = tdl_kernel<RR, VV, KK>;                                                                  \
+        LTE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        k<<<grid, TDL_THREADS, smem, st>>>(C, (const float2*)tx, phases, (float2*)faded, power, T,        \
+                                           (long long)n, tiles);                                          \
+    }
+#define LAUNCH_TDL(RR, VV)                                  \
+    case RR:                                                \
+        if (K == 2) LAUNCH_TDL_K(RR, VV, 2) else LAUNCH_TDL_K(RR, VV, 4) \
+        break;
     switch (R) {
-        LAUNCH_TDL(1) LAUNCH_TDL(2) LAUNCH_TDL(3) LAUNCH_TDL(4) LAUNCH_TDL(5) LAUNCH_TDL(6) LAUNCH_TDL(7)
-        LAUNCH_TDL(8)
+        LAUNCH_TDL(1, 8) LAUNCH_TDL(2, 8) LAUNCH_TDL(3, 8) LAUNCH_TDL(4, 8)
+        LAUNCH_TDL(5, 4) LAUNCH_TDL(6, 4) LAUNCH_TDL(7, 4) LAUNCH_TDL(8, 4)
     }
 #undef LAUNCH_TDL
+#undef LAUNCH_TDL_K
     LTE_CHECK_CUDA(cudaGetLastError());
     return LTE_OK;
 }
@@ -252,7 +286,7 @@ __global__ void awgn_kernel(const float2* __restrict__ x, int x_div, const doubl
                             unsigned long long row_id0, float2* __restrict__ y, long long n, int gx) {
     const long long row = blockIdx.x / gx;
     const int bx = blockIdx.x % gx;
-    const float sigma = lte_sigma(power[row], (double)n, snr_lin[row]);
+    const float sigma = lte_sigma(power[row], (float)n, snr_lin[row]);
     const float2* src = x + (size_t)(row / x_div) * n;
     float2* dst = y + (size_t)row * n;
     const uint32_t rid = (uint32_t)(row_id0 + (unsigned long long)row);

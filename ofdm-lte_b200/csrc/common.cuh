@@ -97,15 +97,16 @@ __host__ __device__ __forceinline__ uint32_t lte_key(uint64_t seed, uint32_t dom
     return a ^ b;
 }
 
-// One complex unit normal (re, im ~ N(0,1)) for (row, sample) by Box-Muller.
+// One complex unit normal (re, im ~ N(0,1)) for (row, sample) by Box-Muller; branch-free.
+// u1 = (r0 + 0.5) 2^-32 keeps the full 32-bit tail resolution for small r0 (fp32 is exact
+// below 2^24), so |z| reaches sqrt(-2 ln 2^-33) = 6.8 sigma.
 __device__ __forceinline__ float2 lte_noise_sample(uint32_t key, uint32_t row, uint32_t sample) {
     uint32_t r0, r1;
     philox2x32_10(key, sample, row, r0, r1);
-    float u1 = ((float)(r0 >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), 24 bits
-    // extend the tail with the 8 low bits when u1 is in the lowest bucket
-    if ((r0 >> 8) == 0) u1 = ((float)(r0 & 0xffu) + 0.5f) * (1.0f / 4294967296.0f);
-    float ang = ((float)(r1 >> 8)) * (1.0f / 16777216.0f) - 0.5f;  // [-0.5, 0.5) turns
-    float rad = sqrtf(-1.3862943611198906f * __log2f(u1));         // sqrt(-2 ln u1)
+    const float u1 = fmaf((float)r0, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float ang = fmaf((float)r1, 2.3283064365386963e-10f, -0.5f);      // [-0.5, 0.5] turns
+    float rad;                                                              // sqrt(-2 ln u1)
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * __log2f(u1)));
     float s, c;
     __sincosf(6.283185307179586f * ang, &s, &c);
     return make_float2(rad * c, rad * s);
@@ -123,6 +124,6 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // sigma of the reference's AWGN: sqrt(mean_power / snr_lin / 2)   (core/channel.py:52,58)
-__device__ __forceinline__ float lte_sigma(double power_sum, double n, float snr_lin) {
-    return (float)sqrt(power_sum / n / (double)snr_lin / 2.0);
+__device__ __forceinline__ float lte_sigma(double power_sum, float n, float snr_lin) {
+    return sqrtf((float)power_sum / (n * snr_lin * 2.0f));
 }

@@ -97,7 +97,8 @@ template <int N>
 __global__ void __launch_bounds__(FFT_CTA_THREADS)
 rx_fft_kernel(const DevPlan P, const float2* __restrict__ rx, int rx_div, const double* __restrict__ power,
               const float* __restrict__ snr_lin, const float2* __restrict__ z, uint32_t key,
-              unsigned long long row_id0, float2* __restrict__ Y, int k0, int nk, int S, long long total) {
+              unsigned long long row_id0, float2* __restrict__ Y, int k0, int nk, int S, long long total,
+              int noise_freq) {
     constexpr int TPF = N / FFT_ELEMS, FPC = fft_per_cta(N);
     extern __shared__ float2 smem[];
     const int f_local = threadIdx.x / TPF, j = threadIdx.x % TPF;
@@ -115,8 +116,8 @@ rx_fft_kernel(const DevPlan P, const float2* __restrict__ rx, int rx_div, const 
         const float2* src = rx + (size_t)(row / rx_div) * n_stream + m0;
 #pragma unroll
         for (int e = 0; e < FFT_ELEMS; ++e) v[e] = src[j + e * TPF];
-        if (power) {
-            const float sigma = lte_sigma(power[row], (double)n_stream, snr_lin[row]);
+        if (power && !noise_freq) {
+            const float sigma = lte_sigma(power[row], (float)n_stream, snr_lin[row]);
             if (z) {
                 const float2* zs = z + (size_t)row * n_stream + m0;
 #pragma unroll
@@ -144,10 +145,26 @@ rx_fft_kernel(const DevPlan P, const float2* __restrict__ rx, int rx_div, const 
 
     if (valid) {
         float2* o = Y + ((size_t)row * S + s_sym) * nk;
+        if (power && noise_freq) {
+            // The unitary FFT maps white Gaussian noise to white Gaussian noise of the same
+            // variance, so the engine draws it directly on the bins it keeps.
+            const float sigma = lte_sigma(power[row], (float)n_stream, snr_lin[row]);
+            const uint32_t rid = (uint32_t)(row_id0 + (unsigned long long)row);
 #pragma unroll
-        for (int e = 0; e < FFT_ELEMS; ++e) {
-            const int k = j + e * TPF - k0;
-            if (k >= 0 && k < nk) o[k] = cscale(v[e], P.inv_sqrt_n);
+            for (int e = 0; e < FFT_ELEMS; ++e) {
+                const int kb = j + e * TPF;
+                const int k = kb - k0;
+                if (k >= 0 && k < nk) {
+                    const float2 w = lte_noise_sample(key, rid, (uint32_t)(s_sym * N + kb));
+                    o[k] = make_float2(fmaf(v[e].x, P.inv_sqrt_n, sigma * w.x), fmaf(v[e].y, P.inv_sqrt_n, sigma * w.y));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < FFT_ELEMS; ++e) {
+                const int k = j + e * TPF - k0;
+                if (k >= 0 && k < nk) o[k] = cscale(v[e], P.inv_sqrt_n);
+            }
         }
     }
 }
@@ -185,10 +202,12 @@ extern "C" int lte_tx_map_ifft(const lte_plan* p, const uint8_t* idx, const lte_
 }
 
 extern "C" int lte_rx_fft(const lte_plan* p, const lte_c32* rx, int32_t rx_div, const double* power,
-                          const float* snr_lin, const lte_c32* z, uint64_t seed, uint64_t row_id0, lte_c32* Y,
-                          int window, int64_t rows, int32_t S, void* stream) {
+                          const float* snr_lin, const lte_c32* z, int32_t noise_domain, uint64_t seed,
+                          uint64_t row_id0, lte_c32* Y, int window, int64_t rows, int32_t S, void* stream) {
     if (!p || !rx || !Y || rows < 0 || S < 1 || rx_div < 1) return LTE_ERR_INVALID_ARG;
     if (power && !snr_lin) return LTE_ERR_INVALID_ARG;
+    if (noise_domain != 0 && noise_domain != 1) return LTE_ERR_INVALID_ARG;
+    if (noise_domain == 1 && z) return LTE_ERR_INVALID_ARG;   // replayed normals are time-domain draws
     int32_t k0, nk;
     int rc = lte_plan_window(p, window, &k0, &nk);
     if (rc) return rc;
@@ -203,7 +222,7 @@ extern "C" int lte_rx_fft(const lte_plan* p, const lte_c32* rx, int32_t rx_div, 
         const long long grid = (total + fft_per_cta(N) - 1) / fft_per_cta(N);
         k<<<(unsigned)grid, FFT_CTA_THREADS, smem, (cudaStream_t)stream>>>(
             p->dev, (const float2*)rx, rx_div, power, snr_lin, (const float2*)z, key, row_id0, (float2*)Y, k0, nk,
-            S, total);
+            S, total, noise_domain);
         LTE_CHECK_CUDA(cudaGetLastError());
         return LTE_OK;
     });

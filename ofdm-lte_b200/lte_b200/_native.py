@@ -52,7 +52,7 @@ _SIGS = {
     'lte_tx_map_ifft': ([_P, _P, _P, _I32, _P, _P, _P, _I32, _I32, _P], C.c_int),
     'lte_channel_tdl': ([_P, C.POINTER(ChannelDesc), _P, _P, _P, _P, _I32, _I32, _I32, _I64, _P], C.c_int),
     'lte_awgn_add': ([_P, _P, _I32, _P, _P, _P, _U64, _U64, _P, _I64, _I64, _P], C.c_int),
-    'lte_rx_fft': ([_P, _P, _I32, _P, _P, _P, _U64, _U64, _P, C.c_int, _I64, _I32, _P], C.c_int),
+    'lte_rx_fft': ([_P, _P, _I32, _P, _P, _P, _I32, _U64, _U64, _P, C.c_int, _I64, _I32, _P], C.c_int),
     'lte_crs_ls_interp': ([_P, _P, _P, C.c_int, C.c_int, _I64, _I32, _P], C.c_int),
     'lte_equalize_zf': ([_P, _P, _P, _P, C.c_int, _I64, _I32, _P], C.c_int),
     'lte_equalize_mrc': ([_P, _P, _P, _P, C.c_int, _I64, _I32, _I32, _P], C.c_int),

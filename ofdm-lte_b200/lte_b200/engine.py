@@ -167,11 +167,12 @@ class LinkEngine:
 
     # ------------------------------------------------------------------ stage 2 RX
     def rx_fft(self, rx, rows, S, window=nat.WINDOW_FULL, rx_div=1, power=None, snr_lin=None, z=None, seed=0,
-               row_id0=0, out=None):
+               row_id0=0, out=None, noise_domain=0):
         k0, nk = self.window(window)
         Y = out if out is not None else self._empty((rows, S, nk), torch.complex64)
-        nat.check(nat.lib.lte_rx_fft(self._plan, _ptr(rx), rx_div, _ptr(power), _ptr(snr_lin), _ptr(z), int(seed),
-                                     int(row_id0), _ptr(Y), window, rows, S, self._stream()), 'lte_rx_fft')
+        nat.check(nat.lib.lte_rx_fft(self._plan, _ptr(rx), rx_div, _ptr(power), _ptr(snr_lin), _ptr(z),
+                                     int(noise_domain), int(seed), int(row_id0), _ptr(Y), window, rows, S,
+                                     self._stream()), 'lte_rx_fft')
         self.launches += 1
         return Y
 
@@ -246,7 +247,7 @@ class LinkEngine:
             ws['phases'] = self._empty((B, R * nat.LTE_MAX_TAPS * nat.LTE_JAKES_TONES), torch.float32)
         return ws
 
-    def simo_ber(self, ws, chan, snr_lin_rows, seed, stream_id0=0, idx=None, nbits=None):
+    def simo_ber(self, ws, chan, snr_lin_rows, seed, stream_id0=0, idx=None, nbits=None, noise_domain=1):
         """One pass of the SIMO-MRC link chain over B independent streams.
 
         ws: workspace(); snr_lin_rows: float32 [B*R] linear SNR per (stream, antenna);
@@ -266,6 +267,6 @@ class LinkEngine:
             _, power = self.channel(tx, chan, B, R, power=ws['power'])
             rx, div = tx, R
         Y = self.rx_fft(rx, B * R, S, nat.WINDOW_USEFUL, rx_div=div, power=power, snr_lin=snr_lin_rows, seed=seed,
-                        row_id0=stream_id0 * R, out=ws['Y'])
+                        row_id0=stream_id0 * R, out=ws['Y'], noise_domain=noise_domain)
         H = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, out=ws['H'])
         return self.mrc_demap_count(Y, H, idx, B, R, S, nbits=nbits, errors=ws['errors'])

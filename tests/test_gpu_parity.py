@@ -139,3 +139,49 @@ def test_demap_is_bit_exact_on_reference_vectors(mod):
     idx = eng2.bits_to_indices(torch.from_numpy(bits[None, :]).cuda(), len(bits), S)
     _, qam, _ = eng2.modulate(S, idx=idx, want_qam=True)
     assert np.array_equal(qam.cpu().numpy().reshape(-1)[:nsym], g[f'mapsyms_{mod}'].astype(np.complex64))
+
+
+def test_fused_time_noise_equals_awgn_then_fft():
+    """lte_rx_fft with fused Philox noise (time domain) is bit-identical to lte_awgn_add + lte_rx_fft."""
+    import torch
+    from lte_b200 import LinkEngine
+    from lte_b200 import _native as nat
+    eng = LinkEngine(512, 300, 36, 4, 7.68e6)
+    rows, S = 6, 3
+    g = torch.Generator(device='cuda').manual_seed(1)
+    x = torch.randn(rows, S * eng.L, 2, device='cuda', generator=g)
+    x = torch.view_as_complex(x).contiguous()
+    power = (x.abs() ** 2).sum(dim=1).double()
+    snr = torch.tensor([1.0, 3.0, 10.0, 30.0, 100.0, 1000.0], dtype=torch.float32, device='cuda')
+    y = eng.awgn(x, 1, power, snr, rows, seed=99, row_id0=40)
+    Y1 = eng.rx_fft(y, rows, S, nat.WINDOW_USEFUL)
+    Y2 = eng.rx_fft(x, rows, S, nat.WINDOW_USEFUL, power=power, snr_lin=snr, seed=99, row_id0=40, noise_domain=0)
+    assert torch.equal(Y1, Y2)
+    # a different seed or row id gives different noise
+    Y3 = eng.rx_fft(x, rows, S, nat.WINDOW_USEFUL, power=power, snr_lin=snr, seed=100, row_id0=40, noise_domain=0)
+    assert not torch.equal(Y1, Y3)
+
+
+def test_frequency_domain_noise_statistics():
+    """noise_domain=1 draws CN(0, 2 sigma^2) directly on the kept bins: same variance as the
+    time-domain AWGN pushed through the unitary FFT, white, Gaussian tails."""
+    import torch
+    from lte_b200 import LinkEngine
+    from lte_b200 import _native as nat
+    eng = LinkEngine(2048, 1200, 144, 6, 30.72e6)
+    rows, S = 64, 14
+    x = torch.zeros(rows, S * eng.L, dtype=torch.complex64, device='cuda')
+    n = S * eng.L
+    power = torch.full((rows,), float(n), dtype=torch.float64, device='cuda')       # mean power 1
+    snr = torch.full((rows,), 0.5, dtype=torch.float32, device='cuda')               # sigma^2 = 1 per component
+    for dom in (0, 1):
+        Y = eng.rx_fft(x, rows, S, nat.WINDOW_USEFUL, power=power, snr_lin=snr, seed=5, row_id0=0, noise_domain=dom)
+        v = torch.view_as_real(Y).double().reshape(-1, 2)
+        m = v.shape[0]
+        assert abs(v.mean().item()) < 5 / m ** 0.5
+        assert abs(v.var(dim=0).mean().item() - 1.0) < 5 * (2 / m) ** 0.5
+        assert abs((v[:, 0] * v[:, 1]).mean().item()) < 5 / m ** 0.5
+        kurt = (v ** 4).mean().item()
+        assert abs(kurt - 3.0) < 0.05
+        assert abs((v[:-1, 0] * v[1:, 0]).mean().item()) < 5 / m ** 0.5            # adjacent bins uncorrelated
+        assert v.abs().max().item() > 4.5                                            # tails present (1e6+ draws)
