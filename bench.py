@@ -301,7 +301,7 @@ def run_gpu(args, rank, world):
         dist.destroy_process_group()
 
 
-def time_stages(eng, ws, chan, snr_rows, idx, nbits, seed, B, S, R, nat, torch, dev, reps=5):
+def time_stages(eng, ws, chan, snr_rows, idx, nbits, seed, B, S, R, nat, torch, dev, reps=5, only=None):
     """Average device time of every stage kernel over `reps` launches (after one warm-up)."""
     per = R * chan.num_taps * nat.LTE_JAKES_TONES
     ph = eng.random_phases(B, per, seed, 0, out=ws['phases'].view(-1)[:B * per].view(B, per))
@@ -316,6 +316,8 @@ def time_stages(eng, ws, chan, snr_rows, idx, nbits, seed, B, S, R, nat, torch, 
     }
     out = {}
     for name, fn in calls.items():
+        if only and name not in only:
+            continue
         fn()
         torch.cuda.synchronize(dev)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

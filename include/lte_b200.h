@@ -10,7 +10,9 @@
  * Conventions
  *  - Every function returns LTE_OK (0) or a negative LTE_ERR_* code; nothing throws.
  *  - All data pointers are DEVICE pointers owned by the caller unless the name ends
- *    in _host.  The library allocates only the per-plan constant tables.
+ *    in _host.  The library allocates only the per-plan constant tables and one
+ *    per-plan scratch buffer (Jakes polynomial coefficients of lte_channel_tdl, grown
+ *    on demand); because of that scratch, use one plan per CUDA stream.
  *  - Launches are asynchronous on `stream` (a cudaStream_t passed as void*).
  *  - Complex samples are interleaved float pairs (re, im): `lte_c32`.
  *  - A "stream" is one link realisation: S OFDM symbols back to back, L = N + cp

@@ -53,6 +53,9 @@ extern "C" int lte_plan_create(const lte_plan_desc* d, const lte_c32* pilots_hos
     lte_plan* p = new lte_plan();
     p->desc = *d;
     p->nsets = nsets;
+    p->blob = nullptr;
+    p->scratch = nullptr;
+    p->scratch_bytes = 0;
     cudaGetDevice(&p->device);
 
     // --- bin classes (core/resource_mapper.py:57-74) -------------------------------
@@ -175,6 +178,7 @@ extern "C" int lte_plan_create(const lte_plan_desc* d, const lte_c32* pilots_hos
 extern "C" int lte_plan_destroy(lte_plan* p) {
     if (!p) return LTE_OK;
     if (p->blob) cudaFree(p->blob);
+    if (p->scratch) cudaFree(p->scratch);
     delete p;
     return LTE_OK;
 }

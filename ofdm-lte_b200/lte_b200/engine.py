@@ -154,7 +154,7 @@ class LinkEngine:
                 raise ValueError("phases are required for a fading channel")
         nat.check(nat.lib.lte_channel_tdl(self._plan, C.byref(chan), _ptr(tx), _ptr(phases), _ptr(faded),
                                           _ptr(power), B, R, T, n, self._stream()), 'lte_channel_tdl')
-        self.launches += 1
+        self.launches += 2 if chan.num_taps > 0 else 1     # Jakes coefficient kernel + TDL kernel
         return faded, power
 
     def awgn(self, x, x_div, power, snr_lin, rows, z=None, seed=0, row_id0=0, out=None):
