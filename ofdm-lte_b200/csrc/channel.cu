@@ -108,11 +108,23 @@ template <int PH, int XS> __device__ __forceinline__ void tdl_load8(float2 (&xv)
 // Shared-memory sample layout: sample s of the staged window lives at [s & 7][s >> 3], so a
 // warp reading "sample 8*t + c" for consecutive threads t touches consecutive float2 (no bank
 // conflicts for any tap delay) while the global reads that fill it stay coalesced.
-template <int R, int V, int K, int HALO>
-__global__ void __launch_bounds__(TDL_THREADS, 4)
+// antenna groups per CTA: at most 4 antennas (64 accumulator registers) per thread.  Splitting
+// R = 4 into two groups was measured slower (1.68 vs 1.55 ms per 4096 subframes): the extra
+// sample loads cost more than the added occupancy gains.
+__host__ __device__ constexpr int tdl_groups(int R) {
+    return R <= 4 ? 1 : (R == 5 ? 5 : (R == 6 ? 2 : (R == 7 ? 7 : 2)));
+}
+__host__ __device__ constexpr int tdl_min_blocks(int R) {
+    return tdl_groups(R) == 1 ? 3 : (tdl_groups(R) == 2 ? 2 : 1);
+}
+
+template <int R, int RG, int V, int K, int HALO>
+__global__ void __launch_bounds__(TDL_THREADS * (R / RG), tdl_min_blocks(R))
 tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float2* __restrict__ coef_g,
            float2* __restrict__ faded, double* __restrict__ power, int T, int n, int tiles, int total_tiles,
            int chunk) {
+    // RG antennas per thread; the R/RG thread groups of TDL_THREADS share the staged samples
+    constexpr int NG = R / RG, NT = TDL_THREADS * NG;
     constexpr int TILE = TDL_THREADS * V;
     constexpr int NC = 2 * K + 1;
     constexpr int XS = tdl_xs_stride(HALO, TILE);
@@ -124,7 +136,9 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float2* __res
     const int xs_elems = T * 8 * XS;
     const int stage_elems = xs_elems + ncoef;
     float2* stage_base = (float2*)smem_raw;                  // [STAGES][xs | coef]
-    const int tid = threadIdx.x;
+    const int tid_all = threadIdx.x;
+    const int tid = tid_all % TDL_THREADS;                   // sample-group index
+    const int grp = tid_all / TDL_THREADS;                   // antenna group (warp-uniform)
 
     auto prefetch = [&](int tile_id, int stage) {
         float2* sx = stage_base + stage * stage_elems;
@@ -137,12 +151,12 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float2* __res
             float2* dst = sx + t * 8 * XS;
             if (interior) {
 #pragma unroll
-                for (int i0 = 0; i0 < SPAN; i0 += TDL_THREADS) {
-                    const int i = i0 + tid;
-                    if (i0 + TDL_THREADS <= SPAN || i < SPAN) cp_async8(&dst[(i & 7) * XS + (i >> 3)], &src[i]);
+                for (int i0 = 0; i0 < SPAN; i0 += NT) {
+                    const int i = i0 + tid_all;
+                    if (i0 + NT <= SPAN || i < SPAN) cp_async8(&dst[(i & 7) * XS + (i >> 3)], &src[i]);
                 }
             } else {
-                for (int i = tid; i < SPAN; i += TDL_THREADS) {
+                for (int i = tid_all; i < SPAN; i += NT) {
                     const int m = tile0 - HALO + i;
                     const bool ok = (m >= 0 && m < n);
                     cp_async8_zfill(&dst[(i & 7) * XS + (i >> 3)], ok ? &src[i] : tx, ok);
@@ -150,7 +164,7 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float2* __res
             }
         }
         const float2* cg = coef_g + ((size_t)b * C.nbs + tile0 / C.pb) * nlt * NC;
-        for (int i = tid; i < ncoef; i += TDL_THREADS) cp_async8(&sc[i], &cg[i]);
+        for (int i = tid_all; i < ncoef; i += NT) cp_async8(&sc[i], &cg[i]);
     };
 
     int tile_id = blockIdx.x * chunk;
@@ -162,23 +176,23 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float2* __res
     __shared__ float pw_red[TDL_THREADS / 32][LTE_MAX_RX];
     const int l0 = tid * V;                         // first local sample of this thread
     const bool vec = ((n & 1) == 0);
-    float pw[R];
+    float pw[RG];
 #pragma unroll
-    for (int r = 0; r < R; ++r) pw[r] = 0.f;
+    for (int r = 0; r < RG; ++r) pw[r] = 0.f;
 
     auto flush_power = [&](int b) {                 // block reduction of the per-thread power sums
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
+        for (int r = 0; r < RG; ++r) {
             const float v = warp_sum(pw[r]);
-            if ((tid & 31) == 0) pw_red[tid >> 5][r] = v;
+            if ((tid & 31) == 0) pw_red[tid >> 5][grp * RG + r] = v;
             pw[r] = 0.f;
         }
         __syncthreads();
-        if (tid < R) {
+        if (tid_all < R) {
             float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < TDL_THREADS / 32; ++w) s += pw_red[w][tid];
-            atomicAdd(&power[(size_t)b * R + tid], (double)s);
+            for (int w = 0; w < TDL_THREADS / 32; ++w) s += pw_red[w][tid_all];
+            atomicAdd(&power[(size_t)b * R + tid_all], (double)s);
         }
         __syncthreads();
     };
@@ -198,9 +212,9 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float2* __res
         // polynomial argument at the centre of the thread's V samples; linear stepping inside
         const float tau = (float)(m0 - blk * C.pb) + 0.5f * (V - 1) - 0.5f * (C.pb - 1);
 
-        float2 acc[R][V];
+        float2 acc[RG][V];
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+        for (int r = 0; r < RG; ++r)
 #pragma unroll
             for (int i = 0; i < V; ++i) acc[r][i] = make_float2(0.f, 0.f);
 
@@ -231,8 +245,8 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float2* __res
                     }
                 }
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const float2* c = coef + ((r * T + t) * C.num_taps + tap) * NC;
+                for (int r = 0; r < RG; ++r) {
+                    const float2* c = coef + (((grp * RG + r) * T + t) * C.num_taps + tap) * NC;
                     float2 h = c[K], dh = c[2 * K];
 #pragma unroll
                     for (int k = K - 1; k >= 0; --k) {
@@ -259,8 +273,8 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float2* __res
 
         // ---- store + power ----------------------------------------------------------------
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            float2* dst = faded + ((size_t)b * R + r) * n + m0;
+        for (int r = 0; r < RG; ++r) {
+            float2* dst = faded + ((size_t)b * R + grp * RG + r) * n + m0;
             if (m0 + V <= n && vec) {
                 float4* d4 = (float4*)dst;
 #pragma unroll
@@ -340,7 +354,7 @@ extern "C" int lte_channel_tdl(const lte_plan* p, const lte_channel_desc* ch, co
         C.w_cyc[nn] = ch->doppler_hz * cos(2.0 * M_PI * (double)(nn + 1) / LTE_JAKES_TONES) / fs;
         if (fabs(C.w_cyc[nn]) > wmax) wmax = fabs(C.w_cyc[nn]);
     }
-    const int V = (R <= 4) ? 8 : 4;
+    const int V = 8;
     const int tile = TDL_THREADS * V;
     // Taylor remainder x^(K+1)/(K+1)! with x = 2 pi w PB/2 kept below 2e-8:
     //   K = 2 needs x < 4.9e-3, K = 4 needs x < 0.075.  PB is the largest power of two that fits.
@@ -385,16 +399,17 @@ extern "C" int lte_channel_tdl(const lte_plan* p, const lte_channel_desc* ch, co
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int ctas = sms * 4;
+    int ctas = sms * tdl_min_blocks(R);
     if (ctas > total_tiles) ctas = total_tiles;
     const int chunk = (total_tiles + ctas - 1) / ctas;
     const unsigned grid = (unsigned)((total_tiles + chunk - 1) / chunk);
 #define LAUNCH_TDL_KH(RR, VV, KK, HH)                                                                     \
     {                                                                                                     \
-        auto k = tdl_kernel<RR, VV, KK, HH>;                                                              \
+        constexpr int RG = RR / tdl_groups(RR);                                                           \
+        auto k = tdl_kernel<RR, RG, VV, KK, HH>;                                                          \
         LTE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-        k<<<grid, TDL_THREADS, smem, st>>>(C, (const float2*)tx, coef, (float2*)faded, power, T, (int)n,  \
-                                           tiles, total_tiles, chunk);                                    \
+        k<<<grid, TDL_THREADS * (RR / RG), smem, st>>>(C, (const float2*)tx, coef, (float2*)faded, power, \
+                                                       T, (int)n, tiles, total_tiles, chunk);             \
     }
 #define LAUNCH_TDL_K(RR, VV, KK) \
     if (halo == 16) LAUNCH_TDL_KH(RR, VV, KK, 16) else LAUNCH_TDL_KH(RR, VV, KK, 144)
@@ -404,7 +419,7 @@ extern "C" int lte_channel_tdl(const lte_plan* p, const lte_channel_desc* ch, co
         break;
     switch (R) {
         LAUNCH_TDL(1, 8) LAUNCH_TDL(2, 8) LAUNCH_TDL(3, 8) LAUNCH_TDL(4, 8)
-        LAUNCH_TDL(5, 4) LAUNCH_TDL(6, 4) LAUNCH_TDL(7, 4) LAUNCH_TDL(8, 4)
+        LAUNCH_TDL(5, 8) LAUNCH_TDL(6, 8) LAUNCH_TDL(7, 8) LAUNCH_TDL(8, 8)
     }
 #undef LAUNCH_TDL
 #undef LAUNCH_TDL_K
