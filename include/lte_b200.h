@@ -109,6 +109,15 @@ int lte_tx_map_ifft(const lte_plan*, const uint8_t* idx, const lte_c32* symbols,
                     lte_c32* tx, lte_c32* qam_out, double* stats, int32_t B, int32_t S,
                     void* stream);
 
+/* --- SC-FDM M-point unitary DFT / IDFT ------------------------------------------------
+ * replaces DFTPrecodifier.precoding / IDFTDecodifier.decoding and the SC_FDMPrecodifier /
+ * SC_FDMDecodifier wrappers (core/dft_precoding.py:67-93, :188-216, :254-348):
+ * out[r][k] = sum_n in[r][n] exp(-+ j 2 pi k n / M) / sqrt(M) for every row of M symbols
+ * (inverse != 0 selects the + sign).  Any M <= 1024 (Bluestein chirp-z on the power-of-two
+ * FFT core; the LTE data-subcarrier counts 62..999 are not 2-3-5 smooth). */
+int lte_dft_m(const lte_plan*, const lte_c32* in, lte_c32* out, int32_t M, int32_t inverse,
+              int64_t rows, void* stream);
+
 /* --- stage 3 channel: time-domain tapped delay line with per-sample Jakes fading
  * replaces RayleighChannel.jakes_fading/.filter (core/rayleighchannel.py:20-58) for
  * R receive antennas and T transmit antennas (OFDMChannel.transmit_simo,

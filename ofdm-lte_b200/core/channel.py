@@ -1,0 +1,213 @@
+"""AWGN and ITU-R M.1225 Rayleigh multipath channels (reference core/channel.py).
+
+AWGN is added by `lte_awgn_add` with sigma taken from the measured stream power exactly as the
+reference does (core/channel.py:46-66, :216-232).  Draws come from NumPy's legacy global RNG in
+the reference's order by default, or from Philox when the owner asks for rng='philox'."""
+import numpy as np
+import torch
+
+from config import ITU_CHANNEL_MODELS
+from lte_b200 import tables
+
+from . import _backend as be
+from .rayleighchannel import RayleighChannel, _FsConfig
+
+
+def _awgn_device(x_t, snr_linear, draws, fs_cfg, row_id0=0, power=None):
+    """x_t complex64 CUDA [rows, n]: y = x + sigma z, sigma from each row's measured power
+    (sum |x|^2, produced by the channel kernel or by the power kernel of lte_channel_tdl)."""
+    eng = be.engine_for(fs_cfg)
+    rows, n = x_t.shape
+    if power is None:
+        _, power = eng.channel(x_t, tables.channel_desc('awgn', fs_cfg.fs), rows, 1)
+    power = power.reshape(-1)
+    snr = torch.full((rows,), float(snr_linear), dtype=torch.float32, device=x_t.device)
+    if draws.kind == 'numpy':
+        z = torch.stack([draws.unit_normals(n) for _ in range(rows)])
+        y = eng.awgn(x_t, 1, power, snr, rows, z=z)
+    else:
+        y = eng.awgn(x_t, 1, power, snr, rows, seed=draws.seed, row_id0=row_id0)
+    noise_power = float(power[0].item() / n / snr_linear)
+    return y, noise_power
+
+
+class AWGNChannel:
+    def __init__(self, snr_db=10.0):
+        self.snr_db = snr_db
+        self.snr_linear = 10 ** (snr_db / 10)
+        self.noise_power = None
+        self._draws = be.NumpyDraws()
+
+    def set_snr(self, snr_db):
+        self.snr_db = snr_db
+        self.snr_linear = 10 ** (snr_db / 10)
+
+    def _transmit_device(self, x_t, row_id0=0):
+        y, self.noise_power = _awgn_device(x_t, self.snr_linear, self._draws, _FsConfig(1.92e6), row_id0)
+        return y
+
+    def transmit(self, signal):
+        x_t = be.as_complex_tensor(signal).reshape(1, -1)
+        y = self._transmit_device(x_t)
+        out = be.to_numpy(y.reshape(-1))
+        return out, out - np.asarray(signal, dtype=np.complex64)
+
+    def get_noise_power(self):
+        return self.noise_power
+
+    def get_snr_info(self):
+        return {'SNR (dB)': self.snr_db, 'SNR (lineal)': self.snr_linear, 'Potencia de ruido': self.noise_power}
+
+
+class RayleighMultiPathChannel:
+    """ITU profile wrapper: computes fD and the (double-converted) tap gains
+    (reference core/channel.py:83-245)."""
+
+    def __init__(self, snr_db=10.0, fs=None, itu_profile='Vehicular_A', fD=None,
+                 frequency_ghz=None, velocity_kmh=None, verbose=True):
+        self.snr_db = snr_db
+        self.snr_linear = 10 ** (snr_db / 10)
+        self.itu_profile = itu_profile
+        self.fs = fs
+        self.noise_power = None
+        self.frequency_ghz = frequency_ghz
+        self.velocity_kmh = velocity_kmh
+        self.verbose = verbose
+        delays, gains = self._get_itu_profile_params(itu_profile)
+        if fD is None:
+            fD = tables.channel_desc('rayleigh_mp', fs, itu_profile, frequency_ghz, velocity_kmh).doppler_hz
+        self.rayleigh = RayleighChannel(fs, fD, delays, gains)
+        self._draws = be.NumpyDraws()
+        if self.verbose:
+            print(f"[RayleighMultiPathChannel] Perfil: {itu_profile}")
+            print(f"  - Doppler máximo: {fD:.1f} Hz")
+
+    def _get_itu_profile_params(self, profile_name):
+        if profile_name not in ITU_CHANNEL_MODELS:
+            raise ValueError(f"Perfil ITU no encontrado: {profile_name}. "
+                             f"Opciones disponibles: {list(ITU_CHANNEL_MODELS.keys())}")
+        prof = ITU_CHANNEL_MODELS[profile_name]
+        return np.array(prof['delays_us']) * 1e-6, 10 ** (np.array(prof['power_db']) / 20)
+
+    def set_snr(self, snr_db):
+        self.snr_db = snr_db
+        self.snr_linear = 10 ** (snr_db / 10)
+
+    def set_profile(self, itu_profile):
+        self.itu_profile = itu_profile
+        delays, gains = self._get_itu_profile_params(itu_profile)
+        self.rayleigh.delays = np.array(delays)
+        self.rayleigh.gains = gains
+        self.rayleigh.num_paths = len(delays)
+
+    def _transmit_device(self, x_t, row_id0=0):
+        if self._draws.kind == 'numpy':
+            u = self._draws.phases(self.rayleigh.num_paths)
+        else:
+            eng = be.engine_for(_FsConfig(self.fs))
+            u = eng.random_phases(1, self.rayleigh.num_paths * 16, self._draws.seed, row_id0)
+        faded, power = self.rayleigh._filter_device(x_t, u)
+        y, self.noise_power = _awgn_device(faded, self.snr_linear, self._draws, _FsConfig(self.fs), row_id0,
+                                           power=power)
+        return y
+
+    def transmit(self, signal):
+        x_t = be.as_complex_tensor(signal).reshape(1, -1)
+        return be.to_numpy(self._transmit_device(x_t).reshape(-1)), None
+
+    def get_channel_info(self):
+        return {'type': 'Rayleigh MultiPath (ITU-R M.1225)', 'profile': self.itu_profile, 'SNR_dB': self.snr_db,
+                'num_paths': self.rayleigh.num_paths, 'delays_us': self.rayleigh.delays * 1e6,
+                'gains_dB': 20 * np.log10(self.rayleigh.gains)}
+
+
+class FadingChannel:
+    """Flat per-sample Rayleigh fading + AWGN (reference core/channel.py:248-291)."""
+
+    def __init__(self, snr_db=10.0, fading_type='rayleigh'):
+        self.snr_db = snr_db
+        self.snr_linear = 10 ** (snr_db / 10)
+        self.fading_type = fading_type
+        self.awgn_channel = AWGNChannel(snr_db)
+
+    def set_snr(self, snr_db):
+        self.snr_db = snr_db
+        self.snr_linear = 10 ** (snr_db / 10)
+        self.awgn_channel.set_snr(snr_db)
+
+    def transmit(self, signal):
+        n = len(signal)
+        h = np.random.normal(0, 1 / np.sqrt(2), n) + 1j * np.random.normal(0, 1 / np.sqrt(2), n)
+        x_t = be.as_complex_tensor(signal).reshape(1, -1) * be.as_complex_tensor(h).reshape(1, -1)
+        y = self.awgn_channel._transmit_device(x_t)
+        return be.to_numpy(y.reshape(-1)), h
+
+
+class ChannelSimulator:
+    """Dispatcher over the channel types (reference core/channel.py:294-395)."""
+
+    def __init__(self, channel_type='awgn', snr_db=10.0, fs=None, itu_profile='Vehicular_A',
+                 frequency_ghz=None, velocity_kmh=None, verbose=True):
+        self.channel_type = channel_type
+        self.fs = fs
+        self.itu_profile = itu_profile
+        self.frequency_ghz = frequency_ghz
+        self.velocity_kmh = velocity_kmh
+        if channel_type == 'awgn':
+            self.channel = AWGNChannel(snr_db)
+        elif channel_type == 'fading':
+            self.channel = FadingChannel(snr_db)
+        elif channel_type == 'rayleigh_mp':
+            if fs is None:
+                raise ValueError("Se requiere fs (frecuencia de muestreo) para canal Rayleigh")
+            self.channel = RayleighMultiPathChannel(snr_db, fs, itu_profile, frequency_ghz=frequency_ghz,
+                                                    velocity_kmh=velocity_kmh, verbose=verbose)
+        else:
+            raise ValueError(f"Tipo de canal desconocido: {channel_type}")
+
+    def _set_draws(self, draws):
+        ch = self.channel.awgn_channel if isinstance(self.channel, FadingChannel) else self.channel
+        ch._draws = draws
+
+    def _transmit_device(self, x_t, row_id0=0):
+        if isinstance(self.channel, FadingChannel):
+            y, _ = self.channel.transmit(be.to_numpy(x_t.reshape(-1)))
+            return be.as_complex_tensor(y).reshape(1, -1)
+        return self.channel._transmit_device(x_t, row_id0)
+
+    def transmit(self, signal):
+        received, _ = self.channel.transmit(signal)
+        return received
+
+    def set_snr(self, snr_db):
+        self.channel.set_snr(snr_db)
+
+    def set_channel_type(self, channel_type, **kwargs):
+        snr_db = getattr(self.channel, 'snr_db', 10.0)
+        self.channel_type = channel_type
+        if channel_type == 'awgn':
+            self.channel = AWGNChannel(snr_db)
+        elif channel_type == 'fading':
+            self.channel = FadingChannel(snr_db)
+        elif channel_type == 'rayleigh_mp':
+            if self.fs is None:
+                raise ValueError("Se requiere fs para cambiar a canal Rayleigh")
+            self.itu_profile = kwargs.get('itu_profile', self.itu_profile)
+            self.channel = RayleighMultiPathChannel(snr_db, self.fs, self.itu_profile)
+        else:
+            raise ValueError(f"Tipo de canal desconocido: {channel_type}")
+
+    def set_itu_profile(self, itu_profile):
+        if isinstance(self.channel, RayleighMultiPathChannel):
+            self.channel.set_profile(itu_profile)
+            self.itu_profile = itu_profile
+        else:
+            raise ValueError("Solo se puede cambiar perfil ITU en canal Rayleigh")
+
+    def get_channel(self):
+        return self.channel
+
+    def get_channel_info(self):
+        if hasattr(self.channel, 'get_channel_info'):
+            return self.channel.get_channel_info()
+        return {'type': self.channel_type, 'SNR_dB': getattr(self.channel, 'snr_db', None)}

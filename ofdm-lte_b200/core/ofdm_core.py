@@ -1,0 +1,356 @@
+"""Orchestration layer with the reference's class names, signatures and result-dict keys
+(reference core/ofdm_core.py): OFDMTransmitter / OFDMReceiver / OFDMChannel / OFDMSimulator.
+
+The bodies are sequences of CUDA stage launches on tensors that stay in HBM; NumPy arrays
+appear only at the API boundary.  Engine-only options are keyword-only and default to the
+reference's behaviour:
+
+    rng='numpy'    draw channel phases / noise from NumPy's legacy global RNG in the reference's
+                   order, including its re-seeding side effects (bit-compatible replay);
+    rng='philox'   counter-based draws on the GPU (independent trials), keyed by `seed`.
+"""
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from config import LTEConfig
+from lte_b200 import _native as nat
+from lte_b200 import tables
+
+from . import _backend as be
+from .channel import ChannelSimulator
+from .demodulator import OFDMDemodulator
+from .modulator import OFDMModulator
+
+
+class OFDMTransmitter:
+    """reference core/ofdm_core.py:42-155."""
+
+    def __init__(self, config: LTEConfig, mode: str = 'lte', enable_sc_fdm: bool = False):
+        self.config = config
+        self.mode = mode
+        self.enable_sc_fdm = enable_sc_fdm
+        self.modulator = OFDMModulator(config, mode=mode, enable_sc_fdm=enable_sc_fdm)
+        self.last_signal_tx = None
+        self.last_symbols_tx = None
+        self.last_mapping_infos = None
+
+    def modulate(self, bits) -> Tuple[np.ndarray, List[np.ndarray], Dict]:
+        if not isinstance(bits, (np.ndarray, torch.Tensor)):
+            bits = np.array(bits, dtype=int)
+        if (bits.numel() if isinstance(bits, torch.Tensor) else bits.size) == 0:
+            raise ValueError("Bits array cannot be empty")
+        signal_tx, symbols_tx, mapping_infos = self.modulator.modulate_stream(bits)
+        self.last_signal_tx, self.last_symbols_tx, self.last_mapping_infos = signal_tx, symbols_tx, mapping_infos
+        return signal_tx, symbols_tx, mapping_infos
+
+    @staticmethod
+    def _papr_from_stats(stats, n):
+        peak, total = float(stats[0]), float(stats[1])
+        avg = total / n
+        if avg > 0:
+            lin = peak / avg
+            return {'papr_db': 10 * np.log10(lin), 'papr_linear': lin, 'peak_power': peak, 'avg_power': avg}
+        return {'papr_db': 0.0, 'papr_linear': 1.0, 'peak_power': peak, 'avg_power': avg}
+
+    def calculate_papr(self, signal) -> Dict:
+        """max |x|^2 / mean |x|^2 over the whole stream (reference :114-147)."""
+        x = be.as_complex_tensor(signal).reshape(-1)
+        p = x.real ** 2 + x.imag ** 2
+        return self._papr_from_stats((p.max().item(), p.double().sum().item()), x.numel())
+
+    def get_config(self) -> LTEConfig:
+        return self.config
+
+    def __repr__(self) -> str:
+        return f"OFDMTransmitter({self.config.modulation}, {'SC-FDM' if self.enable_sc_fdm else 'OFDM'})"
+
+
+class OFDMReceiver:
+    """reference core/ofdm_core.py:158-276."""
+
+    def __init__(self, config: LTEConfig, mode: str = 'lte', enable_equalization: bool = True,
+                 enable_sc_fdm: bool = False):
+        self.config = config
+        self.mode = mode
+        self.enable_equalization = enable_equalization
+        self.enable_sc_fdm = enable_sc_fdm
+        self.demodulator = OFDMDemodulator(config, mode=mode, enable_equalization=enable_equalization,
+                                           enable_sc_fdm=enable_sc_fdm)
+        self.last_symbols_rx = None
+        self.last_bits_rx = None
+        self.channel_estimate = None
+
+    def demodulate(self, signal_rx) -> Tuple[np.ndarray, np.ndarray]:
+        if (signal_rx.numel() if isinstance(signal_rx, torch.Tensor) else np.size(signal_rx)) == 0:
+            raise ValueError("Received signal cannot be empty")
+        symbols, bits_rx = self.demodulator.demodulate_stream(signal_rx)
+        self.last_symbols_rx, self.last_bits_rx = symbols, bits_rx
+        return symbols, bits_rx
+
+    def estimate_channel(self) -> Dict:
+        return {'estimated': False, 'method': 'none'}
+
+    def calculate_ber(self, bits_tx, bits_rx) -> float:
+        n = min(len(bits_tx), len(bits_rx))
+        if n == 0:
+            return 0.0
+        return float(np.sum(np.asarray(bits_tx[:n]) != np.asarray(bits_rx[:n])) / n)
+
+    def get_config(self) -> LTEConfig:
+        return self.config
+
+    def __repr__(self) -> str:
+        return f"OFDMReceiver({self.config.modulation}, {'SC-FDM' if self.enable_sc_fdm else 'OFDM'})"
+
+
+class OFDMChannel:
+    """reference core/ofdm_core.py:279-557."""
+
+    def __init__(self, channel_type: str = 'awgn', snr_db: float = 10.0, fs: float = 15.36e6,
+                 itu_profile: str = 'Pedestrian_A', frequency_ghz: float = 2.0, velocity_kmh: float = 0):
+        self.channel_type = channel_type
+        self.snr_db = snr_db
+        self.fs = fs
+        self.profile = itu_profile
+        self.frequency_ghz = frequency_ghz
+        self.velocity_kmh = velocity_kmh
+        if channel_type == 'rayleigh_mp':
+            self.channel = ChannelSimulator(channel_type='rayleigh_mp', snr_db=snr_db, fs=fs, itu_profile=itu_profile,
+                                            frequency_ghz=frequency_ghz, velocity_kmh=velocity_kmh)
+        else:
+            self.channel = ChannelSimulator('awgn', snr_db=snr_db)
+
+    def set_snr(self, snr_db: float) -> None:
+        self.snr_db = snr_db
+        self.channel.set_snr(snr_db)
+
+    def transmit(self, signal_tx) -> np.ndarray:
+        return self.channel.transmit(signal_tx)
+
+    def _chan_desc(self):
+        return tables.channel_desc(self.channel_type, self.fs, self.profile, self.frequency_ghz, self.velocity_kmh)
+
+    def _transmit_simo_device(self, eng, tx_t, num_rx, draws):
+        """R independent links of one TX stream (reference :361-412).
+        -> (rx [R, n], faded [R, n] or None)."""
+        n = tx_t.shape[-1]
+        chan = self._chan_desc()
+        snr = torch.full((num_rx,), float(10 ** (self.snr_db / 10)), dtype=torch.float32, device=tx_t.device)
+        if draws.kind == 'numpy':
+            # reference order per antenna: taps x rand(16), normal(n), normal(n)
+            us, zs = [], []
+            for _ in range(num_rx):
+                us.append(draws.phases(chan.num_taps))
+                zs.append(draws.unit_normals(n))
+            u = torch.stack(us).reshape(1, -1) if chan.num_taps else None
+            z = torch.stack(zs)
+            faded, power = eng.channel(tx_t, chan, 1, num_rx, phases=u)
+            src, div = (faded.reshape(num_rx, n), 1) if faded is not None else (tx_t, num_rx)
+            rx = eng.awgn(src, div, power.reshape(-1), snr, num_rx, z=z)
+        else:
+            sid = draws.next_stream()
+            u = eng.random_phases(1, num_rx * chan.num_taps * nat.LTE_JAKES_TONES, draws.seed, sid) \
+                if chan.num_taps else None
+            faded, power = eng.channel(tx_t, chan, 1, num_rx, phases=u)
+            src, div = (faded.reshape(num_rx, n), 1) if faded is not None else (tx_t, num_rx)
+            rx = eng.awgn(src, div, power.reshape(-1), snr, num_rx, seed=draws.seed, row_id0=sid * num_rx)
+        return rx, (faded.reshape(num_rx, n) if faded is not None else None)
+
+    def transmit_simo(self, signal_tx, num_rx: int = 2) -> List[np.ndarray]:
+        if num_rx < 1:
+            raise ValueError("num_rx must be >= 1")
+        eng = be.engine_for(_FsOnly(self.fs))
+        tx_t = be.as_complex_tensor(signal_tx).reshape(1, -1)
+        rx, _ = self._transmit_simo_device(eng, tx_t, num_rx, be.NumpyDraws())
+        out = be.to_numpy(rx)
+        return [out[r] for r in range(num_rx)]
+
+
+class _FsOnly:
+    N, Nc, cp_length, bits_per_symbol = 128, 76, 9, 2
+
+    def __init__(self, fs):
+        self.fs = fs
+
+
+class OFDMSimulator:
+    """SISO / SIMO orchestrator (reference core/ofdm_core.py:560-737, 1340-1679, 1795-1846)."""
+
+    def __init__(self, config: Optional[LTEConfig] = None, channel_type: str = 'awgn', mode: str = 'lte',
+                 enable_sc_fdm: bool = False, enable_equalization: bool = True, num_channels: int = 1,
+                 itu_profile: str = 'Pedestrian_A', frequency_ghz: float = 2.0, velocity_kmh: float = 0.0,
+                 *, rng: str = 'numpy', seed: int = 0):
+        if config is None:
+            config = LTEConfig()
+        self.config = config
+        self.channel_type = channel_type
+        self.mode = mode
+        self.enable_sc_fdm = enable_sc_fdm
+        self.enable_equalization = enable_equalization
+        self.itu_profile = itu_profile
+        self.frequency_ghz = frequency_ghz
+        self.velocity_kmh = velocity_kmh
+        self._draws = be.make_draws(rng, seed)
+        self.tx = OFDMTransmitter(config, mode=mode, enable_sc_fdm=enable_sc_fdm)
+        self.rx = OFDMReceiver(config, mode=mode, enable_equalization=enable_equalization,
+                               enable_sc_fdm=enable_sc_fdm)
+        if self.rx.demodulator.lte_receiver is not None:
+            self.rx.demodulator.lte_receiver.faithful_rng = (rng == 'numpy')
+        fs = getattr(config, 'fs', 15.36e6)
+        self.channels = []
+        for _ in range(num_channels):
+            if channel_type == 'rayleigh_mp':
+                ch = OFDMChannel(channel_type='rayleigh_mp', snr_db=10.0, fs=fs, itu_profile=itu_profile,
+                                 frequency_ghz=frequency_ghz, velocity_kmh=velocity_kmh)
+            else:        # unknown channel types silently mean AWGN (reference :644-654)
+                ch = OFDMChannel('awgn', snr_db=10.0, fs=fs)
+            ch.channel._set_draws(self._draws)
+            self.channels.append(ch)
+        self.last_results = None
+
+    # ------------------------------------------------------------------ helpers
+    def _engine(self):
+        return self.tx.modulator._engine()
+
+    @staticmethod
+    def _check_bits(bits):
+        if not isinstance(bits, (np.ndarray, torch.Tensor)):
+            bits = np.array(bits, dtype=int)
+        if (bits.numel() if isinstance(bits, torch.Tensor) else bits.size) == 0:
+            raise ValueError("Bits array cannot be empty")
+        return bits
+
+    def _pilot_side_effect(self):
+        if self._draws.kind == 'numpy' and self.mode != 'simple':
+            be.reference_pilot_side_effect(0, self._engine().Np)
+
+    def _finish(self, eng, data, idx_tx, bits, nbits):
+        """slicer + error count + received bits (reference :712-718)."""
+        nsym = idx_tx.shape[1]
+        errors, idx_rx = eng.demap_count(data[:, :nsym].contiguous(), idx_tx=idx_tx, nbits=nbits, want_idx=True)
+        bits_rx = be.to_numpy(eng.indices_to_bits(idx_rx, nbits).reshape(-1), np.int64)
+        return int(errors.item()), bits_rx
+
+    # ------------------------------------------------------------------ SISO
+    def simulate_siso(self, bits, snr_db: float = 10.0) -> Dict:
+        bits = self._check_bits(bits)
+        eng = self._engine()
+        b_t = be.as_bits_tensor(bits)
+        nbits = b_t.shape[1]
+        tx, qam, idx, stats, S = self.tx.modulator._modulate_stream_device(b_t)
+        self._pilot_side_effect()
+        papr = self.tx._papr_from_stats(be.to_numpy(stats)[0], tx.shape[1])
+        self.channels[0].set_snr(snr_db)
+        sid = self._draws.next_stream() if self._draws.kind == 'philox' else 0
+        rx = self.channels[0].channel._transmit_device(tx, row_id0=sid)
+        data = self.rx.demodulator._demodulate_stream_device(rx)
+        bit_errors, bits_rx = self._finish(eng, data, idx, bits, nbits)
+        qam_np = be.to_numpy(qam)
+        results = {
+            'transmitted_bits': int(nbits), 'received_bits': int(nbits), 'bits_received_array': bits_rx,
+            'bit_errors': bit_errors, 'errors': bit_errors, 'ber': float(bit_errors / nbits), 'snr_db': float(snr_db),
+            'papr_db': float(papr['papr_db']), 'papr_linear': float(papr['papr_linear']),
+            'signal_tx': be.to_numpy(tx.reshape(-1)), 'signal_rx': be.to_numpy(rx.reshape(-1)),
+            'symbols_tx': [qam_np[s] for s in range(S)], 'symbols_rx': be.to_numpy(data.reshape(-1)),
+        }
+        self.last_results = results
+        return results
+
+    # ------------------------------------------------------------------ SIMO
+    def _demodulate_with_channel_est(self, signal_rx) -> Tuple[np.ndarray, List[np.ndarray]]:
+        """One antenna: FFT + CRS estimate, no equalisation (reference :1340-1403)."""
+        eng = be.engine_for(self.config)
+        lte = self.rx.demodulator.lte_receiver
+        rx = be.as_complex_tensor(signal_rx).reshape(1, -1)
+        Y, S = lte._fft_device(rx)
+        H = eng.estimate(Y, 1, S, nat.WINDOW_FULL)
+        if self._draws.kind == 'numpy':
+            be.reference_pilot_side_effect(0, eng.Np)
+        data = eng.zf(Y, None, 1, S, nat.WINDOW_FULL)
+        Hn = be.to_numpy(H.reshape(-1, eng.N))
+        return be.to_numpy(data.reshape(-1)), [Hn[s // nat.LTE_SLOT_SYMBOLS] for s in range(S)]
+
+    def _combine_symbols_mrc(self, symbols_rx_list, h_estimates_per_antenna, regularization: float = 1e-10):
+        """sum_i conj(H_i) Y_i / (sum_i |H_i|^2 + reg) on data symbols (reference :1405-1534)."""
+        eng = be.engine_for(self.config)
+        R = len(symbols_rx_list)
+        n = max(len(s) for s in symbols_rx_list) if R else 0
+        if n == 0:
+            raise ValueError("No symbols received from any antenna")
+        dev = be.device()
+        data_idx = torch.from_numpy(eng.data_idx).to(dev)
+        Y = torch.zeros((R, n), dtype=torch.complex64, device=dev)
+        for r, s in enumerate(symbols_rx_list):
+            m = min(len(s), n)
+            Y[r, :m] = be.as_complex_tensor(s).reshape(-1)[:m]
+        S = -(-n // eng.Nd)
+        H = torch.ones((R, S, eng.Nd), dtype=torch.complex64, device=dev)
+        for r, hl in enumerate(h_estimates_per_antenna):
+            for s in range(S):
+                if len(hl):
+                    h = be.as_complex_tensor(hl[min(s, len(hl) - 1)]).reshape(-1)
+                    H[r, s] = h[data_idx]
+        Hf = H.reshape(R, -1)[:, :n]
+        num = (Hf.conj() * Y).sum(dim=0)
+        den = (Hf.real ** 2 + Hf.imag ** 2).sum(dim=0) + regularization
+        return be.to_numpy(num / den)
+
+    def simulate_simo(self, bits, snr_db: float = 10.0, num_rx: int = 2, combining: str = 'mrc',
+                      parallel: bool = True) -> Dict:
+        """1 x num_rx with MRC (reference :1536-1679).  `parallel` is accepted for compatibility:
+        the antennas are a batch dimension of every kernel launch."""
+        bits = self._check_bits(bits)
+        eng = be.engine_for(self.config)
+        b_t = be.as_bits_tensor(bits)
+        nbits = b_t.shape[1]
+        tx, qam, idx, stats, S = self.tx.modulator._modulate_stream_device(b_t)
+        self._pilot_side_effect()
+        papr = self.tx._papr_from_stats(be.to_numpy(stats)[0], tx.shape[1])
+        self.channels[0].set_snr(snr_db)
+        rx, _ = self.channels[0]._transmit_simo_device(eng, tx, num_rx, self._draws)
+        Y, S_rx = self.rx.demodulator.lte_receiver._fft_device(rx)
+        H = eng.estimate(Y, num_rx, S_rx, nat.WINDOW_FULL)
+        self._pilot_side_effect()
+        comb = eng.mrc(Y, H, 1, num_rx, S_rx, nat.WINDOW_FULL)
+        bit_errors, bits_rx = self._finish(eng, comb, idx, bits, nbits)
+        per_ant = eng.zf(Y, None, num_rx, S_rx, nat.WINDOW_FULL)
+        Hn = be.to_numpy(H)                       # [R, nslot, N]
+        rx_np, qam_np, per_np = be.to_numpy(rx), be.to_numpy(qam), be.to_numpy(per_ant)
+        results = {
+            'transmitted_bits': int(nbits), 'received_bits': int(nbits), 'bits_received_array': bits_rx,
+            'bit_errors': bit_errors, 'errors': bit_errors, 'ber': float(bit_errors / nbits), 'snr_db': float(snr_db),
+            'papr_db': float(papr['papr_db']), 'papr_linear': float(papr['papr_linear']),
+            'signal_tx': be.to_numpy(tx.reshape(-1)), 'signal_rx_list': [rx_np[r] for r in range(num_rx)],
+            'symbols_tx': [qam_np[s] for s in range(S)], 'symbols_rx_combined': be.to_numpy(comb.reshape(-1)),
+            'symbols_rx_list': [per_np[r] for r in range(num_rx)],
+            'channel_estimates_per_antenna': [[Hn[r, s // nat.LTE_SLOT_SYMBOLS] for s in range(S_rx)]
+                                              for r in range(num_rx)],
+            'num_rx': num_rx, 'combining_method': combining, 'diversity_level': num_rx,
+            'parallel_processing': parallel,
+        }
+        self.last_results = results
+        return results
+
+    # ------------------------------------------------------------------ sweeps
+    def run_ber_sweep(self, num_bits: int, snr_range, num_trials: int = 1,
+                      progress_callback: Optional[callable] = None) -> Dict:
+        """reference :1795-1846 (one random bit vector, SISO)."""
+        bits = np.random.randint(0, 2, num_bits)
+        snr_values = np.atleast_1d(snr_range)
+        ber_values, papr_values = [], []
+        total, cur = len(snr_values) * num_trials, 0
+        for snr in snr_values:
+            ber_t, papr_t = [], []
+            for trial in range(num_trials):
+                r = self.simulate_siso(bits, snr_db=snr)
+                ber_t.append(r['ber'])
+                papr_t.append(r['papr_db'])
+                cur += 1
+                if progress_callback:
+                    progress_callback(int(cur / total * 100), f"SNR: {snr:.1f} dB - Trial {trial+1}/{num_trials}")
+            ber_values.append(np.mean(ber_t))
+            papr_values.append(np.mean(papr_t))
+        return {'snr_db': snr_values, 'ber_mean': np.array(ber_values), 'ber_values': np.array(ber_values),
+                'papr_values': np.array(papr_values)}

@@ -139,6 +139,16 @@ class LinkEngine:
         self.launches += 1
         return tx, qam, stats
 
+    # ------------------------------------------------------------------ SC-FDM M-point DFT
+    def dft_m(self, x, M, inverse=False, out=None):
+        """Unitary M-point DFT (or IDFT) of every length-M row of x (any leading shape)."""
+        rows = x.numel() // M
+        y = out if out is not None else torch.empty_like(x)
+        nat.check(nat.lib.lte_dft_m(self._plan, _ptr(x), _ptr(y), int(M), 1 if inverse else 0, rows,
+                                    self._stream()), 'lte_dft_m')
+        self.launches += 1
+        return y
+
     # ------------------------------------------------------------------ stage 3 channel
     def channel(self, tx, chan, B, R, T=1, phases=None, out=None, power=None):
         """-> (faded [B, R, n] or None for the AWGN channel type, power [B, R] float64)."""

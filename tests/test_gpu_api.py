@@ -1,0 +1,161 @@
+"""The reference-shaped Python API (config / core.* / ofdm_module in ofdm-lte_b200/) against the
+golden vectors produced by the unmodified reference: same constructor arguments, same global-RNG
+state, results compared key by key.  Integer results identical unless a symbol sits within 1e-5
+of a slicer boundary; signals within 1e-5 relative (fp32 engine vs the reference's fp64)."""
+import numpy as np
+import pytest
+
+from cases import BIG_RX_STRIDE, SIMO_CASES, SISO_CASES
+from helpers import golden_bits, golden_bits_rx, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _bits_close(got, want, symbols, modulation, bps):
+    if np.array_equal(got, want):
+        return True
+    from gpu_chain import boundary_distance
+    bad = np.unique(np.flatnonzero(got != want) // bps)
+    return bool(np.all(boundary_distance(np.asarray(symbols, dtype=complex), modulation)[bad] < 1e-4))
+
+
+def _make_sim(case, **extra):
+    from config import LTEConfig
+    from core.ofdm_core import OFDMSimulator
+    cfg = LTEConfig(case['bw'], 15.0, case['mod'], case.get('cp_type', 'normal'))
+    return cfg, OFDMSimulator(cfg, channel_type=case['ch'], itu_profile=case['prof'], frequency_ghz=2.0,
+                              velocity_kmh=case['v'], mode=case.get('mode', 'lte'),
+                              enable_sc_fdm=case.get('sc_fdm', False),
+                              enable_equalization=case.get('equalize', True), **extra)
+
+
+@pytest.mark.parametrize('case', SISO_CASES, ids=lambda c: c['name'])
+def test_simulate_siso_matches_reference(case, capsys):
+    g = load_golden(case['name'])
+    bits = golden_bits(g)
+    cfg, sim = _make_sim(case)
+    for snr in case['snrs']:
+        if 'global_seed' in case:
+            np.random.seed(case['global_seed'])
+        r = sim.simulate_siso(bits, snr_db=snr)
+        assert set(r) >= {'transmitted_bits', 'received_bits', 'bits_received_array', 'bit_errors', 'errors', 'ber',
+                          'snr_db', 'papr_db', 'papr_linear', 'signal_tx', 'signal_rx', 'symbols_tx', 'symbols_rx'}
+        assert r['transmitted_bits'] == len(bits) and isinstance(r['errors'], int) and isinstance(r['ber'], float)
+        assert abs(r['papr_db'] - float(g[f'papr_db_{snr}'])) < 1e-4
+        want = golden_bits_rx(g, snr)
+        assert _bits_close(r['bits_received_array'], want, r['symbols_rx'], cfg.modulation, cfg.bits_per_symbol)
+        assert abs(r['errors'] - int(g[f'errors_{snr}'])) <= np.count_nonzero(r['bits_received_array'] != want)
+        if snr == case['full_snr']:
+            assert rel_err(r['signal_tx'], g['signal_tx']) < TOL
+            assert rel_err(r['signal_rx'], g['signal_rx']) < TOL
+            sr, sg = r['symbols_rx'], g['symbols_rx']
+            elem = np.abs(sr - sg) / np.maximum(np.abs(sg), 1e-30)
+            assert np.median(elem) < TOL
+            assert np.quantile(elem, 0.99) < 100 * TOL      # ZF bins in deep fades amplify fp32 rounding
+
+
+@pytest.mark.parametrize('case', SIMO_CASES, ids=lambda c: c['name'])
+def test_simulate_simo_matches_reference(case):
+    g = load_golden(case['name'])
+    bits = golden_bits(g)
+    cfg, sim = _make_sim(case)
+    for snr in case['snrs']:
+        r = sim.simulate_simo(bits, snr_db=snr, num_rx=case['R'], parallel=False)
+        want = golden_bits_rx(g, snr)
+        assert _bits_close(r['bits_received_array'], want, r['symbols_rx_combined'], cfg.modulation,
+                           cfg.bits_per_symbol)
+        assert abs(r['errors'] - int(g[f'errors_{snr}'])) <= np.count_nonzero(r['bits_received_array'] != want)
+        assert r['num_rx'] == case['R'] and r['diversity_level'] == case['R'] and r['combining_method'] == 'mrc'
+        assert len(r['signal_rx_list']) == case['R'] and len(r['symbols_rx_list']) == case['R']
+        if snr == case['full_snr']:
+            big = case.get('big')
+            rx = np.stack(r['signal_rx_list'])
+            assert rel_err(r['signal_tx'], g['signal_tx']) < TOL
+            assert rel_err(rx[:, ::BIG_RX_STRIDE] if big else rx, g['signal_rx']) < TOL
+            assert rel_err(r['symbols_rx_combined'], g['symbols_combined']) < TOL
+            H = np.array(r['channel_estimates_per_antenna'])[:, ::14, :]
+            assert rel_err(H, g['H']) < TOL
+
+
+def test_simulation_is_deterministic_like_the_reference():
+    """map_symbols re-seeds the global RNG, so two calls give identical signals."""
+    _, sim = _make_sim(SIMO_CASES[0])
+    bits = golden_bits(load_golden(SIMO_CASES[0]['name']))
+    a = sim.simulate_simo(bits, snr_db=10.0, num_rx=2)
+    b = sim.simulate_simo(bits, snr_db=10.0, num_rx=2)
+    assert np.array_equal(a['signal_rx_list'][1], b['signal_rx_list'][1])
+
+
+def test_philox_mode_gives_independent_trials_and_leaves_numpy_rng_alone():
+    _, sim = _make_sim(SIMO_CASES[0], rng='philox', seed=3)
+    bits = golden_bits(load_golden(SIMO_CASES[0]['name']))
+    np.random.seed(123)
+    expect = np.random.RandomState(123).rand()
+    a = sim.simulate_simo(bits, snr_db=10.0, num_rx=2)
+    b = sim.simulate_simo(bits, snr_db=10.0, num_rx=2)
+    assert np.random.rand() == expect
+    assert not np.array_equal(a['signal_rx_list'][0], b['signal_rx_list'][0])
+    assert 0 < a['ber'] < 0.5 and 0 < b['ber'] < 0.5
+
+
+def test_error_conventions():
+    """ValueError on empty bits / bad modulation / unknown ITU profile / missing fs."""
+    from config import LTEConfig
+    from core.channel import ChannelSimulator
+    from core.ofdm_core import OFDMSimulator
+    with pytest.raises(ValueError):
+        LTEConfig(5.0, 15.0, '8-PSK')
+    sim = OFDMSimulator(LTEConfig())
+    with pytest.raises(ValueError):
+        sim.simulate_siso(np.array([], dtype=int))
+    with pytest.raises(ValueError):
+        sim.simulate_simo([], num_rx=2)
+    with pytest.raises(ValueError):
+        ChannelSimulator('rayleigh_mp', fs=None)
+    with pytest.raises(ValueError):
+        ChannelSimulator('rayleigh_mp', fs=7.68e6, itu_profile='Nowhere_Z', verbose=False)
+    with pytest.raises(ValueError):
+        ChannelSimulator('carrier-pigeon')
+    # unknown channel types in OFDMSimulator mean AWGN (reference core/ofdm_core.py:644-654)
+    assert OFDMSimulator(LTEConfig(), channel_type='rayleigh').channels[0].channel_type == 'awgn'
+
+
+def test_component_classes_round_trip():
+    """QAMModulator / ResourceMapper / SC_FDM classes / OFDMModule through their public methods."""
+    from config import LTEConfig
+    from core.dft_precoding import SC_FDMDecodifier, SC_FDMPrecodifier
+    from core.modulator import QAMModulator
+    from core.resource_mapper import LTEResourceGrid, ResourceMapper
+    from ofdm_module import OFDMModule
+    g = load_golden('tables')
+    for mod in ('QPSK', '16-QAM', '64-QAM'):
+        q = QAMModulator(mod)
+        assert np.array_equal(q.get_constellation(), g[f'const_{mod}'])
+        syms = q.bits_to_symbols(g[f'mapbits_{mod}'])
+        assert np.array_equal(syms, g[f'mapsyms_{mod}'].astype(np.complex64))
+        back = q.symbols_to_bits(syms)
+        nb = len(g[f'mapbits_{mod}'])
+        assert np.array_equal(back[:nb], g[f'mapbits_{mod}'])
+    cfg = LTEConfig(10.0, 15.0, '16-QAM')
+    grid = LTEResourceGrid(cfg.N, cfg.Nc)
+    assert np.array_equal(grid.get_data_indices(), g['data_idx_10.0'])
+    assert np.array_equal(grid.get_pilot_indices(), g['pilot_idx_10.0'])
+    rm = ResourceMapper(cfg)
+    d = (np.arange(499) + 1j).astype(np.complex64)
+    mapped, info = rm.map_symbols(d)
+    assert np.array_equal(mapped[info['data_indices']], d)
+    assert np.allclose(mapped[info['pilot_indices']], g['pilots_cell0'][:100])
+    assert np.count_nonzero(mapped) == 599 and mapped[cfg.N // 2] == 0
+    x = (np.random.RandomState(0).randn(499) + 1j * np.random.RandomState(1).randn(499))
+    pre = SC_FDMPrecodifier(499).precoding(x)
+    assert rel_err(pre, np.fft.fft(x) / np.sqrt(499)) < TOL
+    assert rel_err(SC_FDMDecodifier(499).decoding(pre), x) < TOL
+    with pytest.raises(ValueError):
+        SC_FDMPrecodifier(499).precoding(x[:10])
+    m = OFDMModule(LTEConfig(), channel_type='awgn')
+    bits = np.random.RandomState(2).randint(0, 2, 1000)
+    r = m.transmit(bits, snr_db=30)
+    assert r['errors'] == 0 and r['transmitted_bits'] == 1000
+    sweep = m.run_ber_sweep(600, [0, 30], num_trials=1)
+    assert sweep['ber_mean'][0] > sweep['ber_mean'][1] == 0.0
