@@ -1,0 +1,68 @@
+"""Host-side sharding / reduction logic of the multi-GPU sweep on CPU with the gloo backend,
+world_size 2 (the GPU path itself is covered by tests/test_gpu_sweep.py)."""
+import os
+import socket
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load_sweep():
+    """sweep.py has no CUDA dependency; import it without triggering the package's native loader."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('lte_sweep', os.path.join(ROOT, 'ofdm-lte_b200', 'lte_b200', 'sweep.py'))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def fake_errors(trial_lo, n, n_snr):
+    """Deterministic per-stream 'error count' that depends only on the global stream id."""
+    sid = torch.arange(trial_lo * n_snr, (trial_lo + n) * n_snr, dtype=torch.int64)
+    return (sid * 2654435761 % 97)
+
+
+def _worker(rank, world, port, n_trials, n_snr, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    sweep = _load_sweep()
+    r = sweep.run_sweep(lambda lo, n: fake_errors(lo, n, n_snr), n_snr, n_trials, bits_per_stream=100,
+                        batch_trials=7, rank=rank, world=world)
+    if rank == 0:
+        torch.save(r, out)
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_shard_range_partitions_exactly():
+    sweep = _load_sweep()
+    for n in (0, 1, 7, 64, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [sweep.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_rank_sweep_equals_single_rank(tmp_path):
+    n_trials, n_snr = 53, 5
+    sweep = _load_sweep()
+    single = sweep.run_sweep(lambda lo, n: fake_errors(lo, n, n_snr), n_snr, n_trials, 100, batch_trials=16)
+    out = str(tmp_path / 'r.pt')
+    mp.spawn(_worker, args=(2, _free_port(), n_trials, n_snr, out), nprocs=2, join=True)
+    multi = torch.load(out)
+    assert torch.equal(multi['errors'], single['errors'])
+    assert torch.equal(multi['bits'], single['bits'])
+    assert torch.equal(single['bits'], torch.full((n_snr,), n_trials * 100, dtype=torch.int64))
