@@ -1,0 +1,56 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/lte_b200.h declares
+(no compute calls are made here)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'lte_b200.h')
+LIB = os.path.join(ROOT, 'ofdm-lte_b200', 'csrc', 'liblte_b200.so')
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(lte_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    lib = ctypes.CDLL(LIB)
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f'{n} declared in lte_b200.h but not exported'
+    lib.lte_version.restype = ctypes.c_int
+    assert lib.lte_version() >= 100
+    lib.lte_error_string.restype = ctypes.c_char_p
+    assert lib.lte_error_string(-1) == b'invalid argument'
+
+
+def test_python_binding_covers_the_header():
+    import __graft_entry__ as g
+    g.build()
+    from lte_b200 import _native as nat
+    assert set(nat.EXPORTS) == set(declared_functions())
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='CPU-only behaviour')
+def test_no_cpu_fallback():
+    """Without a GPU the product path refuses to run instead of falling back."""
+    import __graft_entry__ as g
+    g.build()
+    from lte_b200 import LinkEngine
+    from lte_b200 import _native as nat
+    with pytest.raises(RuntimeError):
+        LinkEngine(128, 76, 9, 2, 1.92e6)
+    desc = nat.PlanDesc(128, 76, 9, 2, 0, 1, 1.92e6)
+    plan = ctypes.c_void_p()
+    assert nat.lib.lte_plan_create(ctypes.byref(desc), None, ctypes.byref(plan)) == -4   # LTE_ERR_NO_DEVICE
+    from core.ofdm_core import OFDMSimulator
+    with pytest.raises(RuntimeError):
+        OFDMSimulator().simulate_siso([0, 1, 1, 0])
