@@ -173,6 +173,20 @@ int lte_equalize_zf(const lte_plan*, const lte_c32* Y, const lte_c32* H, lte_c32
 int lte_equalize_mrc(const lte_plan*, const lte_c32* Y, const lte_c32* H, lte_c32* out, int window,
                      int64_t B, int32_t R, int32_t S, void* stream);
 
+/* --- SFBC Alamouti transmit diversity (2 TX) ---------------------------------------------
+ * lte_sfbc_encode replaces SFBCAlamouti.encode (core/sfbc_alamouti.py:45-78) fused with the QAM
+ * map: idx [B][S][2*(Nd/2)] symbol indices (or `symbols`, complex, same shape) ->
+ * out [B][2][S][Nd] per-antenna data symbols ready for lte_tx_map_ifft(symbols=out, T=2) on a
+ * plan with two pilot sets (SFBCResourceMapper.map_sfbc_to_grid, :212-264); with an odd Nd the
+ * last data bin is nulled (:196-200).  qam_out (optional): [B][S][2*(Nd/2)] mapped symbols.
+ * lte_sfbc_decode replaces SFBCAlamouti.decode (:80-163) for every RX antenna followed by the
+ * arithmetic mean over antennas (core/ofdm_core.py:2204): Y [B][R][S][nk]; H0/H1
+ * [B*R][ceil(S/14)][nk] (lte_crs_ls_interp with pilot_set 0 / 1); out [B][S][2*(Nd/2)]. */
+int lte_sfbc_encode(const lte_plan*, const uint8_t* idx, const lte_c32* symbols, lte_c32* out,
+                    lte_c32* qam_out, int64_t B, int32_t S, void* stream);
+int lte_sfbc_decode(const lte_plan*, const lte_c32* Y, const lte_c32* H0, const lte_c32* H1,
+                    lte_c32* out, int window, int64_t B, int32_t R, int32_t S, void* stream);
+
 /* --- stage 6: hard demap + bit-error count -------------------------------------------
  * replaces QAMModulator.symbols_to_bits (core/modulator.py:90-112) and
  * OFDMReceiver.calculate_ber (core/ofdm_core.py:245-268).  syms: [B][nsym];

@@ -168,6 +168,85 @@ class OFDMChannel:
         return [out[r] for r in range(num_rx)]
 
 
+    def _transmit_mimo_device(self, eng, tx_t, num_rx, draws):
+        """T x num_rx links (reference :434-543): every (rx, tx) link is faded independently and, in
+        the reference, carries its own AWGN at 100 dB; the links are summed per RX antenna and one
+        AWGN with noise power (P_rx / T) / snr is added.  tx_t: [T, n] -> (rx [R, n], H [R, T])."""
+        T, n = tx_t.shape
+        chan = self._chan_desc()
+        dev = tx_t.device
+        snr_lin = float(10 ** (self.snr_db / 10))
+        chan_mat = torch.zeros((num_rx, T), dtype=torch.complex128, device=dev)
+        if chan.num_taps == 0:
+            # fixed links h = exp(j pi tx / 2) (reference :479-486)
+            h = torch.tensor([np.exp(1j * (t * np.pi / 2)) if t else 1.0 + 0j for t in range(T)],
+                             dtype=torch.complex64, device=dev)
+            acc = (tx_t * h[:, None]).sum(dim=0, keepdim=True).repeat(num_rx, 1).contiguous()
+            chan_mat[:] = h.to(torch.complex128)[None, :]
+            link_z = None
+        else:
+            if draws.kind == 'numpy':          # per rx, per tx: taps x rand(16), normal(n), normal(n)
+                us, zl, zr = [], [], []
+                for _ in range(num_rx):
+                    ur, zlr = [], []
+                    for _ in range(T):
+                        ur.append(draws.phases(chan.num_taps))
+                        zlr.append(draws.unit_normals(n))
+                    us.append(torch.stack(ur))
+                    zl.append(torch.stack(zlr))
+                    zr.append(draws.unit_normals(n))
+                u = torch.stack(us)             # [R, T, taps, 16]
+                link_z = torch.stack(zl)        # [R, T, n]
+                rx_z = torch.stack(zr)
+            else:
+                sid = draws.next_stream()
+                u = eng.random_phases(1, num_rx * T * chan.num_taps * nat.LTE_JAKES_TONES, draws.seed, sid) \
+                    .reshape(num_rx, T, chan.num_taps, nat.LTE_JAKES_TONES)
+                link_z = None
+            acc = torch.zeros((num_rx, n), dtype=torch.complex64, device=dev)
+            hi_snr = torch.full((num_rx,), 1e10, dtype=torch.float32, device=dev)
+            tx_pow = (tx_t.real.double() ** 2 + tx_t.imag.double() ** 2).mean(dim=1)
+            for t in range(T):
+                faded, power = eng.channel(tx_t[t:t + 1], chan, 1, num_rx, phases=u[:, t].reshape(1, -1))
+                link = faded.reshape(num_rx, n)
+                if link_z is not None:          # the reference's per-link noise at 100 dB (:495-505)
+                    link = eng.awgn(link, 1, power.reshape(-1), hi_snr, num_rx, z=link_z[:, t].contiguous())
+                rx_pow = (link.real.double() ** 2 + link.imag.double() ** 2).mean(dim=1)
+                corr = (link.to(torch.complex128) * tx_t[t].conj().to(torch.complex128)[None, :]).mean(dim=1)
+                chan_mat[:, t] = torch.sqrt(rx_pow / tx_pow[t]) * torch.exp(1j * torch.angle(corr))
+                acc += link
+        _, p_acc = eng.channel(acc, tables.channel_desc('awgn', self.fs), num_rx, 1)
+        snr = torch.full((num_rx,), snr_lin * T, dtype=torch.float32, device=dev)   # (P / T) / snr
+        if draws.kind == 'numpy':
+            if chan.num_taps == 0:
+                rx_z = torch.stack([draws.unit_normals(n) for _ in range(num_rx)])
+            rx = eng.awgn(acc, 1, p_acc.reshape(-1), snr, num_rx, z=rx_z)
+        else:
+            sid2 = draws.next_stream()
+            rx = eng.awgn(acc, 1, p_acc.reshape(-1), snr, num_rx, seed=draws.seed, row_id0=sid2 * num_rx)
+        return rx, chan_mat
+
+    def transmit_mimo(self, signals_tx, num_rx: int = 1):
+        if len(signals_tx) == 0:
+            raise ValueError("No transmitted signals provided")
+        n = len(signals_tx[0])
+        for t, sig in enumerate(signals_tx):
+            if len(sig) != n:
+                raise ValueError(f"TX signal {t} length mismatch")
+        eng = be.engine_for(_FsOnly(self.fs))
+        tx_t = torch.stack([be.as_complex_tensor(s).reshape(-1) for s in signals_tx])
+        rx, H = self._transmit_mimo_device(eng, tx_t, num_rx, be.NumpyDraws())
+        out = be.to_numpy(rx)
+        return [out[r] for r in range(num_rx)], be.to_numpy(H)
+
+    def get_config(self) -> Dict:
+        return {'type': self.channel_type, 'snr_db': self.snr_db, 'fs': self.fs, 'profile': self.profile,
+                'frequency_ghz': self.frequency_ghz, 'velocity_kmh': self.velocity_kmh}
+
+    def __repr__(self) -> str:
+        return f"OFDMChannel({self.channel_type}, SNR={self.snr_db}dB, {self.profile})"
+
+
 class _FsOnly:
     N, Nc, cp_length, bits_per_symbol = 128, 76, 9, 2
 
@@ -332,6 +411,60 @@ class OFDMSimulator:
         }
         self.last_results = results
         return results
+
+    # ------------------------------------------------------------------ SFBC transmit diversity
+    def _simulate_sfbc(self, bits, snr_db, num_rx, mode_name):
+        """2 TX Alamouti SFBC, num_rx RX, averaging combiner (reference :1850-2258)."""
+        bits = self._check_bits(bits)
+        eng0 = be.engine_for(self.config)
+        sets = tables.mimo_pilot_sets(2, eng0.Np)
+        eng = be.engine_for(self.config, pilot_sets=sets)
+        nd2 = 2 * (eng.Nd // 2)
+        b_t = be.as_bits_tensor(bits)
+        nbits = b_t.shape[1]
+        S = int(-(-nbits // (nd2 * eng.bps)))
+        # symbol indices laid out [S, nd2] (bits_per_ofdm = nd2 * b, reference :1888-1892)
+        idx = torch.zeros((1, S * nd2), dtype=torch.uint8, device=b_t.device)
+        nat.check(nat.lib.lte_bits_to_indices(eng._plan, b_t.data_ptr(), nbits, idx.data_ptr(), S * nd2, 1,
+                                              eng._stream()), 'lte_bits_to_indices')
+        data, qam = eng.sfbc_encode(S, idx=idx, want_qam=True)
+        tx, _, _ = eng.modulate(S, symbols=data, T=2, want_stats=False)          # [2, S*L]
+        if self._draws.kind == 'numpy':                 # TX ends on seed(1); choice(len(pilot_idx[1::2]))
+            be.reference_pilot_side_effect(1, len(np.arange(eng.Np)[1::2]))
+        # per-OFDM-symbol PAPR averaged in dB (reference :1946-1953, :2016-2017)
+        p = (tx.real ** 2 + tx.imag ** 2).reshape(2, S, eng.L)
+        papr_sym = 10 * torch.log10(p.max(dim=2).values / p.mean(dim=2))
+        papr0, papr1 = float(papr_sym[0].mean()), float(papr_sym[1].mean())
+        self.channels[0].set_snr(snr_db)
+        rx, chan_mat = self.channels[0]._transmit_mimo_device(eng, tx, num_rx, self._draws)
+        S_rx = rx.shape[1] // eng.L
+        Y = eng.rx_fft(rx[:, :S_rx * eng.L].contiguous(), num_rx, S_rx, nat.WINDOW_FULL)
+        H0 = eng.estimate(Y, num_rx, S_rx, nat.WINDOW_FULL, pilot_set=0)
+        H1 = eng.estimate(Y, num_rx, S_rx, nat.WINDOW_FULL, pilot_set=1)
+        if self._draws.kind == 'numpy':
+            be.reference_pilot_side_effect(1, len(np.arange(eng.Np)[1::2]))
+        dec = eng.sfbc_decode(Y, H0, H1, 1, num_rx, S_rx, nat.WINDOW_FULL)
+        bit_errors, bits_rx = self._finish(eng, dec, idx[:, :S_rx * nd2].contiguous() if S_rx < S else idx, bits,
+                                           min(nbits, S_rx * nd2 * eng.bps))
+        if len(bits_rx) < nbits:
+            bits_rx = np.pad(bits_rx, (0, nbits - len(bits_rx)), 'constant')
+        papr_db = float(np.mean([papr0, papr1]))
+        results = {
+            'transmitted_bits': int(nbits), 'received_bits': int(nbits), 'bits_received_array': bits_rx,
+            'bit_errors': bit_errors, 'errors': bit_errors, 'ber': float(bit_errors / nbits), 'snr_db': float(snr_db),
+            'num_tx': 2, 'num_rx': num_rx, 'mode': mode_name, 'diversity_order': 2 * num_rx,
+            'channel_matrix': be.to_numpy(chan_mat), 'papr_db_tx0': papr0, 'papr_db_tx1': papr1,
+            'papr_db': papr_db, 'papr_linear': 10 ** (papr_db / 10),
+            'symbols_rx': be.to_numpy(dec.reshape(-1)),
+        }
+        self.last_results = results
+        return results
+
+    def simulate_miso(self, bits, snr_db: float = 10.0) -> Dict:
+        return self._simulate_sfbc(bits, snr_db, 1, 'MISO-SFBC')
+
+    def simulate_mimo(self, bits, snr_db: float = 10.0, num_rx: int = 2) -> Dict:
+        return self._simulate_sfbc(bits, snr_db, num_rx, 'MIMO-SFBC')
 
     # ------------------------------------------------------------------ sweeps
     def run_ber_sweep(self, num_bits: int, snr_range, num_trials: int = 1,

@@ -1,0 +1,132 @@
+// Transmit-diversity (SFBC Alamouti) stage kernels.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------ SFBC encode
+// core/sfbc_alamouti.py:45-78: pairs (k, k+1) of data symbols -> TX0 [s0, -conj(s1)],
+// TX1 [s1, conj(s0)].  Input: symbol indices (QAM map fused, core/modulator.py:80-86) or complex
+// symbols, npair pairs per OFDM symbol; output rows of Nd symbols per TX antenna (the bins past
+// 2*npair stay zero: with an odd number of data bins the last one is nulled, :196-200).
+__global__ void __launch_bounds__(256)
+sfbc_encode_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float2* __restrict__ syms,
+                   float2* __restrict__ out, float2* __restrict__ qam_out, int npair, int S, long long total) {
+    const int h = P.bps >> 1, mask = (1 << h) - 1;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int pr = (int)(g % npair);
+        const long long bs = g / npair;                 // b*S + s
+        const long long b = bs / S;
+        const int s = (int)(bs % S);
+        const size_t in0 = (size_t)bs * 2 * npair + 2 * pr;
+        float2 s0, s1;
+        if (syms) {
+            s0 = syms[in0];
+            s1 = syms[in0 + 1];
+        } else {
+            const int i0 = idx[in0], i1 = idx[in0 + 1];
+            s0 = make_float2(P.lev[(i0 >> h) & mask], P.lev[i0 & mask]);
+            s1 = make_float2(P.lev[(i1 >> h) & mask], P.lev[i1 & mask]);
+            if (qam_out) { qam_out[in0] = s0; qam_out[in0 + 1] = s1; }
+        }
+        float2* o0 = out + (((size_t)b * 2 + 0) * S + s) * P.Nd + 2 * pr;
+        float2* o1 = out + (((size_t)b * 2 + 1) * S + s) * P.Nd + 2 * pr;
+        o0[0] = s0;
+        o0[1] = make_float2(-s1.x, s1.y);
+        o1[0] = s1;
+        o1[1] = make_float2(s0.x, -s0.y);
+        if (pr == 0 && 2 * npair < P.Nd) {             // null the unused tail bins
+            for (int k = 2 * npair; k < P.Nd; ++k) {
+                out[(((size_t)b * 2 + 0) * S + s) * P.Nd + k] = make_float2(0.f, 0.f);
+                out[(((size_t)b * 2 + 1) * S + s) * P.Nd + k] = make_float2(0.f, 0.f);
+            }
+        }
+    }
+}
+
+extern "C" int lte_sfbc_encode(const lte_plan* p, const uint8_t* idx, const lte_c32* symbols, lte_c32* out,
+                               lte_c32* qam_out, int64_t B, int32_t S, void* stream) {
+    if (!p || (!idx && !symbols) || !out || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
+    if (B == 0) return LTE_OK;
+    const int npair = p->dev.Nd / 2;
+    if (npair < 1) return LTE_ERR_INVALID_ARG;
+    const long long total = (long long)B * S * npair;
+    long long grid = (total + 255) / 256;
+    if (grid > 148 * 32) grid = 148 * 32;
+    sfbc_encode_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(p->dev, idx, (const float2*)symbols,
+                                                                        (float2*)out, (float2*)qam_out, npair, S,
+                                                                        total);
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}
+
+// ------------------------------------------------------------------------------ SFBC decode
+// core/sfbc_alamouti.py:132-161 per receive antenna, then the plain average over antennas of
+// core/ofdm_core.py:2204.  thread = (stream, pair); channel estimates of the slot stay in registers.
+template <int R>
+__global__ void __launch_bounds__(128)
+sfbc_decode_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restrict__ H0,
+                   const float2* __restrict__ H1, float2* __restrict__ out, int k0, int nk, int S, int nslot,
+                   int npair, int gx) {
+    const long long b = blockIdx.x / gx;
+    const int pr = (blockIdx.x % gx) * blockDim.x + threadIdx.x;
+    if (pr >= npair) return;
+    const int ka = P.data_idx[2 * pr] - k0, kb = P.data_idx[2 * pr + 1] - k0;
+    const float invR = 1.0f / (float)R;
+    for (int slot = 0; slot < nslot; ++slot) {
+        float2 h0a[R], h0b[R], h1a[R], h1b[R];
+        float nrm[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const size_t o = (((size_t)b * R + r) * nslot + slot) * nk;
+            h0a[r] = H0[o + ka]; h0b[r] = H0[o + kb];
+            h1a[r] = H1[o + ka]; h1b[r] = H1[o + kb];
+            const float2 m0 = make_float2(0.5f * (h0a[r].x + h0b[r].x), 0.5f * (h0a[r].y + h0b[r].y));
+            const float2 m1 = make_float2(0.5f * (h1a[r].x + h1b[r].x), 0.5f * (h1a[r].y + h1b[r].y));
+            nrm[r] = cabs2(m0) + cabs2(m1) + 1e-10f;
+        }
+        const int s_end = min(S, (slot + 1) * LTE_SLOT_SYMBOLS);
+        for (int s = slot * LTE_SLOT_SYMBOLS; s < s_end; ++s) {
+            float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const size_t o = (((size_t)b * R + r) * S + s) * nk;
+                const float2 ra = Y[o + ka], rb = Y[o + kb];
+                const float2 rbc = make_float2(rb.x, -rb.y);
+                // s0 = conj(h0a) ra + h1b conj(rb);  s1 = conj(h1a) ra - h0b conj(rb)
+                float2 t0 = cmulc(h0a[r], ra), u0 = cmul(h1b[r], rbc);
+                float2 t1 = cmulc(h1a[r], ra), u1 = cmul(h0b[r], rbc);
+                a0.x += __fdiv_rn(t0.x + u0.x, nrm[r]); a0.y += __fdiv_rn(t0.y + u0.y, nrm[r]);
+                a1.x += __fdiv_rn(t1.x - u1.x, nrm[r]); a1.y += __fdiv_rn(t1.y - u1.y, nrm[r]);
+            }
+            float2* o = out + ((size_t)b * S + s) * 2 * npair + 2 * pr;
+            o[0] = make_float2(a0.x * invR, a0.y * invR);
+            o[1] = make_float2(a1.x * invR, a1.y * invR);
+        }
+    }
+}
+
+extern "C" int lte_sfbc_decode(const lte_plan* p, const lte_c32* Y, const lte_c32* H0, const lte_c32* H1,
+                               lte_c32* out, int window, int64_t B, int32_t R, int32_t S, void* stream) {
+    if (!p || !Y || !H0 || !H1 || !out || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
+    int32_t k0, nk;
+    int rc = lte_plan_window(p, window, &k0, &nk);
+    if (rc) return rc;
+    if (B == 0) return LTE_OK;
+    const int npair = p->dev.Nd / 2;
+    const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
+    const int gx = (npair + 127) / 128;
+    const unsigned grid = (unsigned)((long long)gx * B);
+    cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_SFBC(RR)                                                                                      \
+    case RR:                                                                                                 \
+        sfbc_decode_kernel<RR><<<grid, 128, 0, st>>>(p->dev, (const float2*)Y, (const float2*)H0,            \
+                                                     (const float2*)H1, (float2*)out, k0, nk, S, nslot, npair, gx); \
+        break;
+    switch (R) {
+        LAUNCH_SFBC(1) LAUNCH_SFBC(2) LAUNCH_SFBC(3) LAUNCH_SFBC(4) LAUNCH_SFBC(5) LAUNCH_SFBC(6) LAUNCH_SFBC(7)
+        LAUNCH_SFBC(8)
+        default: return LTE_ERR_INVALID_ARG;
+    }
+#undef LAUNCH_SFBC
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}

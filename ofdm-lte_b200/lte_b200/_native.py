@@ -57,6 +57,8 @@ _SIGS = {
     'lte_crs_ls_interp': ([_P, _P, _P, C.c_int, C.c_int, _I64, _I32, _P], C.c_int),
     'lte_equalize_zf': ([_P, _P, _P, _P, C.c_int, _I64, _I32, _P], C.c_int),
     'lte_equalize_mrc': ([_P, _P, _P, _P, C.c_int, _I64, _I32, _I32, _P], C.c_int),
+    'lte_sfbc_encode': ([_P, _P, _P, _P, _P, _I64, _I32, _P], C.c_int),
+    'lte_sfbc_decode': ([_P, _P, _P, _P, _P, C.c_int, _I64, _I32, _I32, _P], C.c_int),
     'lte_demap_count': ([_P, _P, _P, _P, _P, _I64, _I64, _I64, _P], C.c_int),
     'lte_mrc_demap_count': ([_P, _P, _P, _P, _P, C.c_int, _I64, _I64, _I32, _I32, _P], C.c_int),
     'lte_random_indices': ([_P, _P, _I64, _I64, _U64, _U64, _P], C.c_int),

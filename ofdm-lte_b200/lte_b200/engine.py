@@ -211,6 +211,25 @@ class LinkEngine:
         self.launches += 1
         return o
 
+    # ------------------------------------------------------------------ SFBC Alamouti
+    def sfbc_encode(self, S, idx=None, symbols=None, want_qam=False):
+        """idx / symbols [B, S*2*(Nd//2)] -> (per-antenna data symbols [B*2, S*Nd], qam or None)."""
+        src = idx if idx is not None else symbols
+        B = src.shape[0]
+        out = self._empty((B * 2, S * self.Nd), torch.complex64)
+        qam = self._empty((B, S * 2 * (self.Nd // 2)), torch.complex64) if (want_qam and idx is not None) else None
+        nat.check(nat.lib.lte_sfbc_encode(self._plan, _ptr(idx) if symbols is None else None, _ptr(symbols),
+                                          _ptr(out), _ptr(qam), B, S, self._stream()), 'lte_sfbc_encode')
+        self.launches += 1
+        return out, qam
+
+    def sfbc_decode(self, Y, H0, H1, B, R, S, window=nat.WINDOW_FULL):
+        out = self._empty((B, S * 2 * (self.Nd // 2)), torch.complex64)
+        nat.check(nat.lib.lte_sfbc_decode(self._plan, _ptr(Y), _ptr(H0), _ptr(H1), _ptr(out), window, B, R, S,
+                                          self._stream()), 'lte_sfbc_decode')
+        self.launches += 1
+        return out
+
     # ------------------------------------------------------------------ stage 6
     def demap_count(self, syms, idx_tx=None, nbits=None, want_idx=False, errors=None):
         """-> (errors int64 [B] or None, idx_rx uint8 [B, nsym] or None)."""

@@ -462,3 +462,136 @@ def simulate_simo(bits, snr_db, num, num_rx=2, channel_type='awgn', itu_profile=
                 signal_rx=np.stack(rx_list), Y=Y, H=H, symbols_combined=comb,
                 bits_rx=bits_rx, errors=errors, ber=errors / len(bits),
                 papr_db=papr_db, papr_linear=papr_lin)
+
+
+# ----------------------------------------------------------------------------
+# SFBC-Alamouti transmit diversity      (core/sfbc_alamouti.py, core/ofdm_core.py:434-543,1850-2258)
+# ----------------------------------------------------------------------------
+def sfbc_encode(symbols):
+    """core/sfbc_alamouti.py:45-78: pairs (k, k+1): TX0 [s0, -s1*], TX1 [s1, s0*]."""
+    symbols = np.asarray(symbols, dtype=complex)
+    if symbols.shape[-1] % 2:
+        raise ValueError(f"Number of symbols must be even for Alamouti coding, got {symbols.shape[-1]}")
+    s0, s1 = symbols[..., 0::2], symbols[..., 1::2]
+    tx0 = np.empty_like(symbols)
+    tx1 = np.empty_like(symbols)
+    tx0[..., 0::2], tx0[..., 1::2] = s0, -np.conj(s1)
+    tx1[..., 0::2], tx1[..., 1::2] = s1, np.conj(s0)
+    return tx0, tx1
+
+
+def sfbc_decode(rx, H0, H1, reg=1e-10):
+    """core/sfbc_alamouti.py:80-163."""
+    rx, H0, H1 = (np.asarray(a, dtype=complex) for a in (rx, H0, H1))
+    if rx.shape[-1] % 2:
+        raise ValueError(f"Number of RX symbols must be even, got {rx.shape[-1]}")
+    ra, rb = rx[..., 0::2], rx[..., 1::2]
+    h0a, h0b, h1a, h1b = H0[..., 0::2], H0[..., 1::2], H1[..., 0::2], H1[..., 1::2]
+    norm = np.abs((h0a + h0b) / 2) ** 2 + np.abs((h1a + h1b) / 2) ** 2 + reg
+    out = np.empty_like(rx)
+    out[..., 0::2] = (np.conj(h0a) * ra + h1b * np.conj(rb)) / norm
+    out[..., 1::2] = (np.conj(h1a) * ra - h0b * np.conj(rb)) / norm
+    return out
+
+
+def mimo_pilot_layout(num_tx, pilot_idx):
+    """core/mimo_channel_estimator_periodic.py:75-106 and core/sfbc_alamouti.py:244-262: TX t owns
+    pilot_idx[t % step :: step], step = min(num_tx, 4), with the sign stream of cell t % 4."""
+    step = num_tx if num_tx <= 4 else 4
+    own = [pilot_idx[t % step::step] for t in range(num_tx)]
+    vals = [pilots(t % 4, len(own[t])) for t in range(num_tx)]
+    return own, vals
+
+
+def mimo_estimate_from_grid(Y, num_tx, num):
+    """core/mimo_channel_estimator_periodic.py:108-185: Y [R, N] -> H [R, T, N]."""
+    _, pilot_idx = grid_indices(num.N, num.Nc)
+    own, vals = mimo_pilot_layout(num_tx, pilot_idx)
+    Y = np.atleast_2d(Y)
+    H = np.zeros((Y.shape[0], num_tx, num.N), dtype=complex)
+    for r in range(Y.shape[0]):
+        for t in range(num_tx):
+            H[r, t] = interpolate_channel(own[t], Y[r, own[t]] / vals[t], num.N)
+    return H
+
+
+class SfbcDraws:
+    """Draw order of OFDMChannel.transmit_mimo (core/ofdm_core.py:470-541) after the SFBC
+    transmitter left the global RNG at seed(1); choice(len(pilot_idx[1::2]))
+    (core/sfbc_alamouti.py:252-256)."""
+
+    def __init__(self, num_pilots):
+        self.rs = np.random.RandomState(1)
+        self.rs.choice([1, -1], size=len(np.arange(num_pilots)[1::2]))
+
+    def phases(self, n_taps, n_s=16):
+        return np.stack([2 * np.pi * self.rs.rand(n_s) for _ in range(n_taps)])
+
+    def unit_normals(self, n):
+        return self.rs.standard_normal(n), self.rs.standard_normal(n)
+
+
+def simulate_sfbc(bits, snr_db, num, num_rx=1, channel_type='awgn', itu_profile='Pedestrian_A',
+                  frequency_ghz=2.0, velocity_kmh=0.0, draws=None):
+    """OFDMSimulator.simulate_miso / simulate_mimo (core/ofdm_core.py:1850-2258) with the periodic
+    estimator restated as intended (the HEAD version unpacks 3 values from a 2-value return,
+    core/mimo_channel_estimator_periodic.py:219-222 vs :185 -- SURVEY 0.9): estimate on symbol 14j
+    with estimate_channel_from_grid, hold for the slot."""
+    bits = np.asarray(bits).astype(np.int64)
+    if bits.size == 0:
+        raise ValueError("Bits array cannot be empty")
+    data_idx, pilot_idx = grid_indices(num.N, num.Nc)
+    nd2 = len(data_idx) - (len(data_idx) % 2)                   # core/sfbc_alamouti.py:196-200
+    didx = data_idx[:nd2]
+    b = num.bits_per_symbol
+    S = int(np.ceil(len(bits) / (nd2 * b)))
+    padded = np.concatenate([bits, np.zeros(S * nd2 * b - len(bits), dtype=np.int64)])
+    sym = qam_map(padded, num.modulation).reshape(S, nd2)
+    tx0d, tx1d = sfbc_encode(sym)
+    own, vals = mimo_pilot_layout(2, pilot_idx)
+    grids = np.zeros((2, S, num.N), dtype=complex)
+    grids[0][:, didx], grids[1][:, didx] = tx0d, tx1d
+    grids[0][:, own[0]], grids[1][:, own[1]] = vals[0], vals[1]
+    sig = ofdm_modulate_grid(grids, num)                        # [2, S, L]
+    papr_db = [float(np.mean([papr(sig[t, s])[0] for s in range(S)])) for t in range(2)]
+    tx = sig.reshape(2, -1)
+    n = tx.shape[1]
+    if draws is None:
+        draws = SfbcDraws(len(pilot_idx))
+    snr_lin = 10 ** (snr_db / 10)
+    rx_list, links = [], np.zeros((num_rx, 2, n), dtype=complex)
+    chan_mat = np.zeros((num_rx, 2), dtype=complex)
+    for r in range(num_rx):                                     # core/ofdm_core.py:470-541
+        acc = np.zeros(n, dtype=complex)
+        for t in range(2):
+            if channel_type == 'rayleigh_mp':
+                d, g = itu_taps(itu_profile, num.fs)
+                fD = doppler_hz(frequency_ghz, velocity_kmh)
+                faded = rayleigh_filter(tx[t], num.fs, fD, d, g, draws.phases(len(d)))
+                z_re, z_im = draws.unit_normals(n)
+                link = awgn(faded, 100.0, z_re, z_im)           # the per-link 100 dB noise
+                tp, rp = np.mean(np.abs(tx[t]) ** 2), np.mean(np.abs(link) ** 2)
+                chan_mat[r, t] = np.sqrt(rp / tp) * np.exp(1j * np.angle(np.mean(link * np.conj(tx[t]))))
+            else:
+                h = 1.0 + 0j if t == 0 else np.exp(1j * (t * np.pi / 2))
+                link = tx[t] * h
+                chan_mat[r, t] = h
+            links[r, t] = link
+            acc += link
+        p = np.mean(np.abs(acc) ** 2)
+        sigma = np.sqrt(((p / 2) / snr_lin) / 2)
+        z_re, z_im = draws.unit_normals(n)
+        rx_list.append(acc + (sigma * z_re + 1j * (sigma * z_im)))
+    rx = np.stack(rx_list)
+    Y = np.stack([rx_fft_stream(rx[r], num) for r in range(num_rx)])         # [R, S, N]
+    Srx = Y.shape[1]
+    H = np.zeros((num_rx, 2, Srx, num.N), dtype=complex)
+    for r in range(num_rx):
+        for s0 in range(0, Srx, SLOT_SIZE):
+            H[r, :, s0:s0 + SLOT_SIZE] = mimo_estimate_from_grid(Y[r, s0], 2, num)[0][:, None, :]
+    dec = np.stack([sfbc_decode(Y[r][:, didx], H[r, 0][:, didx], H[r, 1][:, didx]) for r in range(num_rx)])
+    comb = np.mean(dec, axis=0).reshape(-1)                     # core/ofdm_core.py:2204 (plain average)
+    bits_rx_all = qam_demap(comb, num.modulation)
+    errors, bits_rx = count_errors(bits, bits_rx_all)
+    return dict(signal_tx=tx, signal_rx=rx, links=links, Y=Y, H=H, symbols=comb, bits_rx=bits_rx, errors=errors,
+                ber=errors / len(bits), channel_matrix=chan_mat, papr_db_tx0=papr_db[0], papr_db_tx1=papr_db[1])

@@ -38,4 +38,18 @@ SIMO_CASES = [
          big=True),
 ]
 
+SFBC_CASES = [
+    # MISO 2x1 over AWGN (fixed h = exp(j pi tx / 2) links, core/ofdm_core.py:479-486)
+    dict(name='sfbc_miso_5mhz_qpsk_awgn', bw=5.0, mod='QPSK', ch='awgn', prof='Pedestrian_A', v=0.0,
+         nsym=3, R=1, snrs=[4.0], full_snr=4.0, seed=21, drop_bits=1),
+    # small 2x2 crossing a slot boundary
+    dict(name='sfbc_2x2_1p25mhz_16qam_peda', bw=1.25, mod='16-QAM', ch='rayleigh_mp', prof='Pedestrian_A',
+         v=3.0, nsym=16, R=2, snrs=[6.0, 12.0], full_snr=12.0, seed=22, drop_bits=3),
+    dict(name='sfbc_2x4_2p5mhz_64qam_veha', bw=2.5, mod='64-QAM', ch='rayleigh_mp', prof='Vehicular_A',
+         v=30.0, nsym=15, R=4, snrs=[18.0], full_snr=18.0, seed=23),
+    # BASELINE.json config 4: 2x2 SFBC 20 MHz 16-QAM over Rayleigh multipath, one subframe
+    dict(name='sfbc_cfg4_20mhz_16qam_peda', bw=20.0, mod='16-QAM', ch='rayleigh_mp', prof='Pedestrian_A',
+         v=3.0, nsym=14, R=2, snrs=[10.0, 20.0], full_snr=10.0, seed=24, big=True),
+]
+
 BIG_RX_STRIDE = 8   # 'big' SIMO cases store every 8th sample of signal_rx

@@ -32,7 +32,7 @@ from core.resource_mapper import LTEResourceGrid, PilotPattern  # noqa: E402
 from core.modulator import QAMModulator  # noqa: E402
 
 sys.path.insert(0, HERE)
-from cases import SISO_CASES, SIMO_CASES, BIG_RX_STRIDE  # noqa: E402
+from cases import SISO_CASES, SIMO_CASES, SFBC_CASES, BIG_RX_STRIDE  # noqa: E402
 
 
 def quiet(fn, *a, **k):
@@ -135,8 +135,50 @@ def simo_case(case):
     print(case['name'], {s: int(out[f'errors_{s}']) for s in case['snrs']})
 
 
+def install_sfbc_shim():
+    """simulate_miso / simulate_mimo raise at HEAD: estimate_channel_periodic unpacks three values
+    from estimate_channel_from_grid, which returns two (core/mimo_channel_estimator_periodic.py:219-222
+    vs :185).  The runtime patch below is the intended behaviour -- estimate on the
+    first symbol of every 14-symbol slot, hold for the slot -- and touches nothing else."""
+    from core.mimo_channel_estimator_periodic import MIMOChannelEstimatorPeriodic
+
+    def estimate_channel_periodic(self, grids):
+        H0s, H1s = [], []
+        for s0 in range(0, len(grids), self.slot_size):
+            H, _ = self.estimate_channel_from_grid(grids[s0])
+            for _ in range(min(self.slot_size, len(grids) - s0)):
+                H0s.append(H[0, 0, :])
+                H1s.append(H[0, 1, :])
+        return H0s, H1s, 0.0
+
+    MIMOChannelEstimatorPeriodic.estimate_channel_periodic = estimate_channel_periodic
+
+
+def sfbc_case(case):
+    cfg = LTEConfig(case['bw'], 15.0, case['mod'], 'normal')
+    sim = quiet(OFDMSimulator, cfg, channel_type=case['ch'], itu_profile=case['prof'], frequency_ghz=2.0,
+                velocity_kmh=case['v'])
+    nd2 = nd_of(cfg) - nd_of(cfg) % 2
+    bits = make_bits(case['seed'], nd2 * cfg.bits_per_symbol * case['nsym'] - case.get('drop_bits', 0))
+    out = dict(bits=np.packbits(bits), nbits=len(bits))
+    for snr in case['snrs']:
+        if case['R'] == 1:
+            r = quiet(sim.simulate_miso, bits, snr_db=snr)
+        else:
+            r = quiet(sim.simulate_mimo, bits, snr_db=snr, num_rx=case['R'])
+        out[f'errors_{snr}'] = r['errors']
+        out[f'bits_rx_{snr}'] = np.packbits(r['bits_received_array'].astype(np.uint8))
+        out[f'channel_matrix_{snr}'] = r['channel_matrix']
+        out[f'papr_{snr}'] = np.array([r['papr_db_tx0'], r['papr_db_tx1'], r['papr_db'], r['papr_linear']])
+    np.savez_compressed(os.path.join(HERE, case['name'] + '.npz'), **out)
+    print(case['name'], {s: int(out[f'errors_{s}']) for s in case['snrs']})
+
+
 def main():
     tables()
+    install_sfbc_shim()
+    for case in SFBC_CASES:
+        sfbc_case(case)
     for case in SISO_CASES:
         siso_case(case)
     for case in SIMO_CASES:

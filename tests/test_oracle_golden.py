@@ -84,3 +84,21 @@ def test_injected_draws_equal_reference_draws():
     o = oracle_simo(case, bits, snr, phases=phases, z=z)
     assert o['errors'] == int(g[f'errors_{snr}'])
     assert rel_err(o['signal_rx'], g['signal_rx']) < TOL64
+
+
+from cases import SFBC_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize('case', SFBC_CASES, ids=lambda c: c['name'])
+def test_sfbc_matches_reference(case):
+    from helpers import numerology
+    g = load_golden(case['name'])
+    bits = golden_bits(g)
+    num = numerology(case)
+    for snr in case['snrs']:
+        o = O.simulate_sfbc(bits, snr, num, case['R'], case['ch'], case['prof'], 2.0, case['v'])
+        assert o['errors'] == int(g[f'errors_{snr}'])
+        assert np.array_equal(o['bits_rx'], golden_bits_rx(g, snr))
+        assert rel_err(o['channel_matrix'], g[f'channel_matrix_{snr}']) < TOL64
+        assert abs(o['papr_db_tx0'] - g[f'papr_{snr}'][0]) < 1e-9
+        assert abs(o['papr_db_tx1'] - g[f'papr_{snr}'][1]) < 1e-9
