@@ -42,7 +42,13 @@ extern "C" {
 #define LTE_JAKES_TONES 16  /* core/rayleighchannel.py:20 (N_s = 16) */
 #define LTE_SLOT_SYMBOLS 14 /* core/lte_receiver.py:233 */
 #define LTE_MAX_RX 8
-#define LTE_MAX_TX 4
+#define LTE_MAX_TX 8
+#define LTE_MAX_LAYERS 4
+
+#define LTE_DET_MMSE 0
+#define LTE_DET_ZF 1
+#define LTE_DET_SIC 2
+#define LTE_DET_MRC 3
 
 #define LTE_WINDOW_FULL 0
 #define LTE_WINDOW_USEFUL 1
@@ -186,6 +192,28 @@ int lte_sfbc_encode(const lte_plan*, const uint8_t* idx, const lte_c32* symbols,
                     lte_c32* qam_out, int64_t B, int32_t S, void* stream);
 int lte_sfbc_decode(const lte_plan*, const lte_c32* Y, const lte_c32* H0, const lte_c32* H1,
                     lte_c32* out, int window, int64_t B, int32_t R, int32_t S, void* stream);
+
+/* --- spatial multiplexing (TM4-like, up to 8 TX / 8 RX / 4 layers) ------------------------
+ * lte_sm_precode replaces LayerMapper.map_to_layers (core/layer_mapper.py:35-86) and the
+ * per-subcarrier x_k = W layers[:, k] loop of simulate_spatial_multiplexing
+ * (core/ofdm_core.py:2611-2640): idx [B][S][Nd] (or complex `symbols`) -> out [B][T][S][Nd];
+ * only the first ceil(Nd / L) data bins carry data, as in the reference.  W_host: [T][L]
+ * precoder (host memory, row major).
+ * lte_flat_mimo replaces the flat branch of ChannelSimulator.transmit_spatial_multiplexing
+ * (core/channel.py:467-480): out[b][r] = sum_t h[b][r][t] tx[b][t]; power [B][R] accumulates
+ * sum |out|^2 (caller zeroes).  The multipath branch is lte_channel_tdl with T > 1.
+ * lte_mimo_detect replaces MIMODetector.detect (core/mimo_detector.py:55-369) on
+ * H_eff = H W per data position: Y [B][R][S][nk]; H [T][B*R][S][nk] (per-symbol estimates, one
+ * lte_crs_ls_interp per TX pilot set); out [B][S][Nd] in the LayerMapper.demap_from_layers order
+ * (core/layer_mapper.py:88-115).  detector: LTE_DET_*; SIC slices with the plan's constellation. */
+int lte_sm_precode(const lte_plan*, const uint8_t* idx, const lte_c32* symbols, const lte_c32* W_host,
+                   int32_t T, int32_t L, lte_c32* out, lte_c32* qam_out, int64_t B, int32_t S,
+                   void* stream);
+int lte_flat_mimo(const lte_plan*, const lte_c32* tx, const lte_c32* h, lte_c32* out, double* power,
+                  int64_t B, int32_t R, int32_t T, int64_t n, void* stream);
+int lte_mimo_detect(const lte_plan*, const lte_c32* Y, const lte_c32* H, const lte_c32* W_host,
+                    int32_t T, int32_t L, double sigma2, int32_t detector, lte_c32* out, int window,
+                    int64_t B, int32_t R, int32_t S, void* stream);
 
 /* --- stage 6: hard demap + bit-error count -------------------------------------------
  * replaces QAMModulator.symbols_to_bits (core/modulator.py:90-112) and

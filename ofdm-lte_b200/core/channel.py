@@ -182,6 +182,65 @@ class ChannelSimulator:
     def set_snr(self, snr_db):
         self.channel.set_snr(snr_db)
 
+    # -- spatial multiplexing channel (reference core/channel.py:397-493) ----------------------
+    def _transmit_sm_device(self, eng, tx_t, num_rx, draws):
+        """tx_t [T, n] -> (rx [R, n], H_channel [R, T] numpy).  Multipath: R*T independent
+        RayleighChannel links (tap gains converted a third time, :436,444) summed per RX; flat:
+        one CN(0,1) coefficient per link.  One AWGN per RX from that antenna's measured power."""
+        T, n = tx_t.shape
+        dev = tx_t.device
+        snr_lin = float(self.channel.snr_linear)
+        snr = torch.full((num_rx,), snr_lin, dtype=torch.float32, device=dev)
+        if self.channel_type == 'rayleigh_mp':
+            ray = self.channel.rayleigh
+            chan = tables.channel_desc('rayleigh_mp', self.fs, self.itu_profile, self.frequency_ghz,
+                                       self.velocity_kmh, gain_conversions=3)
+            chan.doppler_hz = float(ray.fD)
+            taps = chan.num_taps
+            Hc = np.zeros((num_rx, T), dtype=complex)
+            if draws.kind == 'numpy':
+                # per (rx, tx): taps x rand(16) for filter(), then taps x rand(16) for impulse_response(N=1)
+                u = np.zeros((num_rx, T, taps, 16))
+                g0 = float(10 ** (ray.gains[0] / 20))
+                for r in range(num_rx):
+                    for t in range(T):
+                        u[r, t] = np.stack([np.random.rand(16) for _ in range(taps)])
+                        u2 = np.stack([np.random.rand(16) for _ in range(taps)])
+                        Hc[r, t] = g0 * np.sqrt(2 / 16) * np.sum(np.exp(2j * np.pi * u2[0]))   # jakes_fading(1)[0]
+                ut = torch.from_numpy(u.astype(np.float32)).to(dev).reshape(1, -1)
+            else:
+                sid = draws.next_stream()
+                ut = eng.random_phases(1, num_rx * T * taps * 16, draws.seed, sid)
+            faded, power = eng.channel(tx_t, chan, 1, num_rx, T=T, phases=ut)
+            acc = faded.reshape(num_rx, n)
+        else:
+            if draws.kind == 'numpy':
+                h = np.zeros((num_rx, T), dtype=complex)
+                for r in range(num_rx):
+                    for t in range(T):
+                        h[r, t] = np.random.normal(0, 1 / np.sqrt(2)) + 1j * np.random.normal(0, 1 / np.sqrt(2))
+            else:
+                g = torch.Generator(device='cpu').manual_seed(draws.seed * 1000003 + draws.next_stream())
+                hh = torch.randn((num_rx, T, 2), generator=g, dtype=torch.float64) / np.sqrt(2)
+                h = (hh[..., 0] + 1j * hh[..., 1]).numpy()
+            Hc = h
+            acc, power = eng.flat_mimo(tx_t, be.as_complex_tensor(h).reshape(1, num_rx, T), 1, num_rx, T)
+        if draws.kind == 'numpy':
+            z = torch.stack([draws.unit_normals(n) for _ in range(num_rx)])
+            rx = eng.awgn(acc, 1, power.reshape(-1), snr, num_rx, z=z)
+        else:
+            sid2 = draws.next_stream()
+            rx = eng.awgn(acc, 1, power.reshape(-1), snr, num_rx, seed=draws.seed, row_id0=sid2 * num_rx)
+        return rx, Hc
+
+    def transmit_spatial_multiplexing(self, tx_signals, num_rx=2):
+        n = min(len(sig) for sig in tx_signals)
+        tx_t = torch.stack([be.as_complex_tensor(sig).reshape(-1)[:n] for sig in tx_signals])
+        eng = be.engine_for(_FsConfig(self.fs if self.fs is not None else 1.92e6))
+        rx, Hc = self._transmit_sm_device(eng, tx_t, num_rx, be.NumpyDraws())
+        out = be.to_numpy(rx)
+        return [out[r] for r in range(num_rx)], Hc
+
     def set_channel_type(self, channel_type, **kwargs):
         snr_db = getattr(self.channel, 'snr_db', 10.0)
         self.channel_type = channel_type

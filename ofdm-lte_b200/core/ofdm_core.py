@@ -487,3 +487,70 @@ class OFDMSimulator:
             papr_values.append(np.mean(papr_t))
         return {'snr_db': snr_values, 'ber_mean': np.array(ber_values), 'ber_values': np.array(ber_values),
                 'papr_values': np.array(papr_values)}
+
+
+def simulate_spatial_multiplexing(bits, num_tx=4, num_rx=2, rank='adaptive', detector_type='MMSE',
+                                  modulation='64-QAM', snr_db=15, config=None, channel_type='awgn',
+                                  itu_profile='Pedestrian_A', velocity_kmh=3, frequency_ghz=2.0,
+                                  enable_csi_feedback=True, coherence_time_symbols=None, enable_parallel=False,
+                                  codebook_type='TM4', *, rng='numpy', seed=0):
+    """TM4-like spatial multiplexing (reference core/ofdm_core.py:2489-2815): layer mapping, codebook
+    precoding on the first ceil(Nd / rank) data bins, per-TX interleaved CRS, R x T channel,
+    per-OFDM-symbol CRS estimation and MMSE / ZF / SIC / MRC detection on H_eff = H W."""
+    from .codebook_lte import LTECodebook
+    from .rank_adaptation import RankAdaptation
+    if config is None:
+        config = LTEConfig(modulation=modulation)
+    bits = OFDMSimulator._check_bits(bits) if len(bits) else bits
+    draws = be.make_draws(rng, seed)
+    nbits = len(bits)
+    eng0 = be.engine_for(config, bits_per_symbol={'QPSK': 2, '16-QAM': 4, '64-QAM': 6}[modulation])
+    sets = tables.mimo_pilot_sets(num_tx, eng0.Np)
+    eng = be.engine_for(config, pilot_sets=sets, bits_per_symbol=eng0.bps)
+    S = int(-(-nbits // (eng.Nd * eng.bps)))
+    # H_initial comes from the caller's global RNG state and is unrelated to the channel (:2574)
+    if draws.kind == 'numpy':
+        H_initial = (np.random.randn(num_rx, num_tx) + 1j * np.random.randn(num_rx, num_tx)) / np.sqrt(2 * num_tx)
+    else:
+        rs = np.random.RandomState(seed)
+        H_initial = (rs.randn(num_rx, num_tx) + 1j * rs.randn(num_rx, num_tx)) / np.sqrt(2 * num_tx)
+    if rank == 'adaptive' and enable_csi_feedback:
+        fb = RankAdaptation(num_tx, num_rx, snr_db=snr_db).get_feedback(H_initial)
+        rank_used, pmi_used, W = fb['ri'], fb['pmi'], fb['W']
+    else:
+        rank_used = int(rank) if rank != 'adaptive' else min(num_tx, num_rx)
+        pmi_used = 0
+        W = LTECodebook(num_tx, transmission_mode='TM4', rank=rank_used).get_precoder(0)
+    W = np.asarray(W, dtype=complex)
+    if num_rx < rank_used:
+        raise ValueError(f"num_rx ({num_rx}) debe ser >= num_layers ({rank_used})")
+    b_t = be.as_bits_tensor(bits)
+    idx = eng.bits_to_indices(b_t, nbits, S)
+    data, _ = eng.sm_precode(S, W, idx=idx)
+    tx, _, _ = eng.modulate(S, symbols=data, T=num_tx, want_stats=False)          # [T, S*L]
+    own_last = len(np.arange(eng.Np)[(num_tx - 1) % min(num_tx, 4)::min(num_tx, 4)])
+    if draws.kind == 'numpy':
+        be.reference_pilot_side_effect((num_tx - 1) % 4, own_last)
+    from .channel import ChannelSimulator
+    fs = config.fs if hasattr(config, 'fs') else 15.36e6
+    channel_sim = ChannelSimulator(channel_type=channel_type, snr_db=snr_db, fs=fs, itu_profile=itu_profile,
+                                   frequency_ghz=frequency_ghz, velocity_kmh=velocity_kmh, verbose=False)
+    rx, H_channel = channel_sim._transmit_sm_device(eng, tx, num_rx, draws)
+    Y = eng.rx_fft(rx, num_rx, S, nat.WINDOW_FULL)
+    # CRS estimate on every OFDM symbol (:2743-2752): rows = R*S single-symbol streams per TX pilot set
+    H = torch.stack([eng.estimate(Y.reshape(num_rx * S, 1, eng.N), num_rx * S, 1, nat.WINDOW_FULL, pilot_set=t)
+                     .reshape(num_rx, S, eng.N) for t in range(num_tx)])            # [T, R, S, N]
+    if draws.kind == 'numpy':
+        be.reference_pilot_side_effect((num_tx - 1) % 4, own_last)
+    sym = eng.mimo_detect(Y, H, W, 10 ** (-snr_db / 10), detector_type, 1, num_rx, S, nat.WINDOW_FULL)
+    errors, idx_rx = eng.demap_count(sym, idx_tx=idx, nbits=nbits, want_idx=True)
+    bits_rx = be.to_numpy(eng.indices_to_bits(idx_rx, nbits).reshape(-1), np.int64)
+    bit_errors = int(errors.item())
+    return {
+        'transmitted_bits': int(nbits), 'received_bits': int(nbits), 'bits_received_array': bits_rx,
+        'bit_errors': bit_errors, 'errors': bit_errors, 'ber': float(bit_errors / nbits) if nbits else 0.0,
+        'snr_db': float(snr_db), 'num_tx': num_tx, 'num_rx': num_rx, 'rank': rank_used,
+        'detector_type': detector_type, 'mode': 'Spatial Multiplexing TM4', 'codebook_type': codebook_type,
+        'channel_matrix': H_channel, 'precoder_matrix': W, 'pmi_used': pmi_used, 'velocity_kmh': velocity_kmh,
+        'modulation': modulation, 'symbols_rx': be.to_numpy(sym.reshape(-1)),
+    }

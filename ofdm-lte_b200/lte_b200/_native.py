@@ -20,7 +20,7 @@ LTE_MAX_TAPS = 8
 LTE_JAKES_TONES = 16
 LTE_SLOT_SYMBOLS = 14
 LTE_MAX_RX = 8
-LTE_MAX_TX = 4
+LTE_MAX_TX = 8
 WINDOW_FULL = 0
 WINDOW_USEFUL = 1
 
@@ -59,6 +59,9 @@ _SIGS = {
     'lte_equalize_mrc': ([_P, _P, _P, _P, C.c_int, _I64, _I32, _I32, _P], C.c_int),
     'lte_sfbc_encode': ([_P, _P, _P, _P, _P, _I64, _I32, _P], C.c_int),
     'lte_sfbc_decode': ([_P, _P, _P, _P, _P, C.c_int, _I64, _I32, _I32, _P], C.c_int),
+    'lte_sm_precode': ([_P, _P, _P, _P, _I32, _I32, _P, _P, _I64, _I32, _P], C.c_int),
+    'lte_flat_mimo': ([_P, _P, _P, _P, _P, _I64, _I32, _I32, _I64, _P], C.c_int),
+    'lte_mimo_detect': ([_P, _P, _P, _P, _I32, _I32, C.c_double, _I32, _P, C.c_int, _I64, _I32, _I32, _P], C.c_int),
     'lte_demap_count': ([_P, _P, _P, _P, _P, _I64, _I64, _I64, _P], C.c_int),
     'lte_mrc_demap_count': ([_P, _P, _P, _P, _P, C.c_int, _I64, _I64, _I32, _I32, _P], C.c_int),
     'lte_random_indices': ([_P, _P, _I64, _I64, _U64, _U64, _P], C.c_int),

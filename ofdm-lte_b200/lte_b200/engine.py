@@ -230,6 +230,48 @@ class LinkEngine:
         self.launches += 1
         return out
 
+    # ------------------------------------------------------------------ spatial multiplexing
+    DETECTORS = {'MMSE': 0, 'IRC': 0, 'ZF': 1, 'SIC': 2, 'MRC': 3}
+
+    @staticmethod
+    def _w_host(W):
+        W = np.ascontiguousarray(np.asarray(W, dtype=np.complex64))
+        return W, W.ctypes.data_as(C.c_void_p), W.shape[0], W.shape[1]
+
+    def sm_precode(self, S, W, idx=None, symbols=None, want_qam=False):
+        """idx / symbols [B, S*Nd], W [T, L] -> (per-antenna data symbols [B*T, S*Nd], qam or None)."""
+        Wc, wp, T, L = self._w_host(W)
+        src = idx if idx is not None else symbols
+        B = src.shape[0]
+        out = self._empty((B * T, S * self.Nd), torch.complex64)
+        qam = self._empty((B, S * self.Nd), torch.complex64) if (want_qam and idx is not None) else None
+        nat.check(nat.lib.lte_sm_precode(self._plan, _ptr(idx) if symbols is None else None, _ptr(symbols), wp, T, L,
+                                         _ptr(out), _ptr(qam), B, S, self._stream()), 'lte_sm_precode')
+        self.launches += 1
+        return out, qam
+
+    def flat_mimo(self, tx, h, B, R, T):
+        """tx [B*T, n], h complex64 [B, R, T] -> (out [B*R, n], power [B, R])."""
+        n = tx.shape[-1]
+        out = self._empty((B * R, n), torch.complex64)
+        power = torch.zeros((B, R), dtype=torch.float64, device=self.device)
+        nat.check(nat.lib.lte_flat_mimo(self._plan, _ptr(tx), _ptr(h), _ptr(out), _ptr(power), B, R, T, n,
+                                        self._stream()), 'lte_flat_mimo')
+        self.launches += 1
+        return out, power
+
+    def mimo_detect(self, Y, H, W, sigma2, detector, B, R, S, window=nat.WINDOW_FULL):
+        """Y [B*R, S, nk], H [T, B*R, S, nk] -> detected symbols [B, S*Nd] (demapped layer order)."""
+        Wc, wp, T, L = self._w_host(W)
+        det = self.DETECTORS.get(str(detector).upper())
+        if det is None:
+            raise ValueError(f"Detector '{detector}' no soportado")
+        out = torch.zeros((B, S * self.Nd), dtype=torch.complex64, device=self.device)
+        nat.check(nat.lib.lte_mimo_detect(self._plan, _ptr(Y), _ptr(H), wp, T, L, float(sigma2), det, _ptr(out),
+                                          window, B, R, S, self._stream()), 'lte_mimo_detect')
+        self.launches += 1
+        return out
+
     # ------------------------------------------------------------------ stage 6
     def demap_count(self, syms, idx_tx=None, nbits=None, want_idx=False, errors=None):
         """-> (errors int64 [B] or None, idx_rx uint8 [B, nsym] or None)."""

@@ -595,3 +595,234 @@ def simulate_sfbc(bits, snr_db, num, num_rx=1, channel_type='awgn', itu_profile=
     errors, bits_rx = count_errors(bits, bits_rx_all)
     return dict(signal_tx=tx, signal_rx=rx, links=links, Y=Y, H=H, symbols=comb, bits_rx=bits_rx, errors=errors,
                 ber=errors / len(bits), channel_matrix=chan_mat, papr_db_tx0=papr_db[0], papr_db_tx1=papr_db[1])
+
+
+# ----------------------------------------------------------------------------
+# Spatial multiplexing (TM4-like)   (core/ofdm_core.py:2489-2815, core/mimo_detector.py,
+#                                    core/layer_mapper.py, core/codebook_lte.py, core/rank_adaptation.py)
+# ----------------------------------------------------------------------------
+def _ph(theta):
+    return np.exp(1j * theta)
+
+
+def codebook(num_tx, rank):
+    """core/codebook_lte.py:59-293 ('TM4'; rank 1 re-uses the TM6 vectors, :115-118)."""
+    if rank < 1 or rank > min(num_tx, 4):
+        raise ValueError(f"TM4 con {num_tx} antenas soporta rank 1-{min(num_tx, 4)}, recibido rank={rank}")
+    cb = []
+    if rank == 1:
+        if num_tx == 2:
+            cb = [np.array([[1], [v]]) / np.sqrt(2) for v in (1, -1, 1j, -1j)]
+        elif num_tx in (4, 8):
+            nrm = 2 if num_tx == 4 else np.sqrt(8)
+            cb = [_ph(2 * np.pi * i * np.arange(num_tx) / 16).reshape(-1, 1) / nrm for i in range(16)]
+    elif rank == 2:
+        if num_tx == 2:
+            cb = [np.array([[1, 0], [0, 1]]), np.array([[1, 1], [1, -1]]) / np.sqrt(2),
+                  np.array([[1, 1], [1j, -1j]]) / np.sqrt(2)]
+        elif num_tx == 4:
+            e = [_ph(2 * np.pi * i / 4) for i in range(4)]
+            cb += [np.array([[1, 0], [p, 0], [0, 1], [0, p]]) / np.sqrt(2) for p in e]
+            cb += [np.array([[1, 1], [p, -p], [1, -1], [p, p]]) / 2 for p in e]
+            cb += [np.array([[1, 0], [0, 1], [p, 0], [0, p]]) / np.sqrt(2) for p in e]
+            cb += [np.array([[1, 1], [1, -1], [p, p], [p, -p]]) / 2 for p in e]
+        elif num_tx == 8:
+            for i in range(16):
+                W = np.zeros((8, 2), dtype=complex)
+                W[0:4, 0] = W[4:8, 1] = _ph(2 * np.pi * i / 16 * np.arange(4)) / np.sqrt(4)
+                cb.append(W)
+    elif rank == 3:
+        if num_tx == 4:
+            for i in range(8):
+                p = _ph(2 * np.pi * i / 8)
+                cb.append(np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [p, p, p]]) / np.sqrt(2))
+        elif num_tx == 8:
+            for i in range(16):
+                th = 2 * np.pi * i / 16
+                v = np.array([1, _ph(th), _ph(2 * th)]) / np.sqrt(3)
+                W = np.zeros((8, 3), dtype=complex)
+                W[0:3, 0] = v
+                W[3:6, 1] = v
+                W[5:8, 2] = v
+                cb.append(W)
+    elif rank == 4:
+        if num_tx == 4:
+            ij = np.outer(np.arange(4), np.arange(4))
+            cb = [np.eye(4, dtype=complex), np.exp(-2j * np.pi * ij / 4) / 2,
+                  np.array([[1, 1, 1, 1], [1, -1, 1, -1], [1, 1, -1, -1], [1, -1, -1, 1]]) / 2,
+                  np.array([[1, 1, 1, 1], [1, 1j, -1, -1j], [1, -1, 1, -1], [1, -1j, -1, 1j]]) / 2]
+        elif num_tx == 8:
+            for i in range(8):
+                th = 2 * np.pi * i / 8
+                W = np.zeros((8, 4), dtype=complex)
+                for l in range(4):
+                    W[2 * l:2 * l + 2, l] = np.array([1, _ph(th * (l + 1))]) / np.sqrt(2)
+                cb.append(W)
+    if not cb:
+        raise ValueError(f"num_tx={num_tx} no soportado en TM4 Rank-{rank}")
+    return cb
+
+
+def rank_feedback(H, num_tx, num_rx, snr_db, rank_threshold=0.15):
+    """RankAdaptation.get_feedback (core/rank_adaptation.py:69-265): RI from the eigenvalues of
+    H^H H with SNR gating, PMI maximising log2 det(I + snr/rank H_eff H_eff^H)."""
+    max_rank = min(num_tx, num_rx, 4)
+    ev = np.sort(np.linalg.eigvalsh(H.conj().T @ H))[::-1]
+    if ev[0] < 1e-10:
+        ri = 1
+    else:
+        ri = min(int(np.sum(ev / ev[0] > rank_threshold)), max_rank)
+        if snr_db < 5:
+            ri = 1
+        elif snr_db < 10:
+            ri = min(ri, 2)
+        ri = max(1, ri)
+    snr_lin = 10 ** (snr_db / 10)
+    best, best_val = 0, -np.inf
+    cb = codebook(num_tx, ri)
+    for pmi, W in enumerate(cb):
+        He = H @ W
+        val = np.log2(np.linalg.det(np.eye(num_rx) + (snr_lin / ri) * (He @ He.conj().T)))
+        if val > best_val:
+            best_val, best = val, pmi
+    return ri, best, cb[best]
+
+
+def layer_map(symbols, rank):
+    """core/layer_mapper.py:35-86: round robin, zero padded -> [rank, ceil(n / rank)]."""
+    symbols = np.asarray(symbols)
+    if rank == 1:
+        return symbols.reshape(1, -1)
+    if len(symbols) % rank:
+        symbols = np.concatenate([symbols, np.zeros(rank - len(symbols) % rank, dtype=symbols.dtype)])
+    return symbols.reshape(-1, rank).T
+
+
+def layer_demap(layers, original_length=None):
+    """core/layer_mapper.py:88-115."""
+    s = np.asarray(layers).T.flatten()
+    return s if original_length is None else s[:original_length]
+
+
+def mimo_detect(y, H_eff, sigma2, detector, constellation_points=None):
+    """MIMODetector._detect_single for one subcarrier (core/mimo_detector.py:99-369).
+    y [R]; H_eff [R, L]."""
+    L = H_eff.shape[1]
+    det = detector.upper()
+    if det in ('MMSE', 'IRC'):
+        return np.linalg.inv(H_eff.conj().T @ H_eff + sigma2 * np.eye(L)) @ H_eff.conj().T @ y
+    if det == 'ZF':
+        return np.linalg.pinv(H_eff) @ y
+    if det == 'MRC':
+        if L != 1:
+            raise ValueError("MRC solo soporta num_layers=1 (rank-1)")
+        h = H_eff[:, 0]
+        return np.array([np.dot(h.conj() / (np.linalg.norm(h) ** 2), y)])
+    if det == 'SIC':
+        norms = np.array([np.linalg.norm(H_eff[:, i]) ** 2 for i in range(L)])
+        sinr = np.array([norms[i] / (norms.sum() - norms[i] + sigma2 + 1e-10) for i in range(L)])
+        order = np.argsort(sinr)[::-1]
+        y_res, H_rem, remaining = y.copy(), H_eff.copy(), list(range(L))
+        s_hat = np.zeros(L, dtype=complex)
+        for it in range(L):
+            layer = order[it]
+            rel = remaining.index(layer)
+            if H_rem.shape[1] == 1:
+                h = H_rem[:, 0]
+                s = np.vdot(h, y_res) / (np.linalg.norm(h) ** 2 + sigma2)
+            else:
+                s = (np.linalg.inv(H_rem.conj().T @ H_rem + sigma2 * np.eye(H_rem.shape[1])) @ H_rem.conj().T @ y_res)[rel]
+            s_hard = constellation_points[np.argmin(np.abs(constellation_points - s))]
+            s_hat[layer] = s_hard
+            y_res = y_res - H_eff[:, layer] * s_hard
+            if it < L - 1:
+                H_rem = np.delete(H_rem, rel, axis=1)
+                remaining.pop(rel)
+        return s_hat
+    raise ValueError(f"Detector '{detector}' no soportado")
+
+
+class SmDraws:
+    """Global-RNG draw order of simulate_spatial_multiplexing: H_initial = randn(R,T), randn(R,T)
+    from the caller's state (core/ofdm_core.py:2574), then the transmitter re-seeds with
+    cell (T-1) % 4 (:2651-2654), then transmit_spatial_multiplexing draws (core/channel.py:441-491)."""
+
+    def __init__(self, num_tx, num_pilots, global_seed):
+        self.h_rs = np.random.RandomState(global_seed)
+        t = num_tx - 1
+        step = num_tx if num_tx <= 4 else 4
+        self.rs = np.random.RandomState(t % 4)
+        self.rs.choice([1, -1], size=len(np.arange(num_pilots)[t % step::step]))
+
+    def h_initial(self, num_rx, num_tx):
+        return (self.h_rs.randn(num_rx, num_tx) + 1j * self.h_rs.randn(num_rx, num_tx)) / np.sqrt(2 * num_tx)
+
+
+def simulate_sm(bits, num, num_tx=4, num_rx=2, rank='adaptive', detector='MMSE', snr_db=15.0,
+                channel_type='awgn', itu_profile='Pedestrian_A', velocity_kmh=3.0, frequency_ghz=2.0,
+                enable_csi_feedback=True, global_seed=0):
+    """simulate_spatial_multiplexing (core/ofdm_core.py:2489-2815)."""
+    bits = np.asarray(bits).astype(np.int64)
+    data_idx, pilot_idx = grid_indices(num.N, num.Nc)
+    Nd, b = len(data_idx), num.bits_per_symbol
+    S = int(np.ceil(len(bits) / (Nd * b)))
+    padded = np.concatenate([bits, np.zeros(S * Nd * b - len(bits), dtype=np.int64)])
+    draws = SmDraws(num_tx, len(pilot_idx), global_seed)
+    H_init = draws.h_initial(num_rx, num_tx)
+    if rank == 'adaptive' and enable_csi_feedback:
+        ri, pmi, W = rank_feedback(H_init, num_tx, num_rx, snr_db)
+    else:
+        ri = int(rank) if rank != 'adaptive' else min(num_tx, num_rx)
+        pmi, W = 0, codebook(num_tx, ri)[0]
+    W = np.asarray(W, dtype=complex)
+    sym = qam_map(padded, num.modulation).reshape(S, Nd)
+    own, vals = mimo_pilot_layout(num_tx, pilot_idx)
+    npos = int(np.ceil(Nd / ri))
+    grids = np.zeros((num_tx, S, num.N), dtype=complex)
+    for s in range(S):
+        layers = layer_map(sym[s], ri)                            # [ri, npos]
+        grids[:, s, data_idx[:npos]] = W @ layers                 # core/ofdm_core.py:2630-2640
+        for t in range(num_tx):
+            grids[t, s, own[t]] = vals[t]
+    tx = ofdm_modulate_grid(grids, num).reshape(num_tx, -1)
+    n = tx.shape[1]
+    rs = draws.rs
+    rx = np.zeros((num_rx, n), dtype=complex)
+    Hc = np.zeros((num_rx, num_tx), dtype=complex)
+    if channel_type == 'rayleigh_mp':
+        d, g = itu_taps(itu_profile, num.fs, gain_conversions=3)  # core/channel.py:436,444
+        fD = doppler_hz(frequency_ghz, velocity_kmh)
+        for r in range(num_rx):
+            for t in range(num_tx):
+                ph = np.stack([2 * np.pi * rs.rand(16) for _ in range(len(d))])
+                rx[r] += rayleigh_filter(tx[t], num.fs, fD, d, g, ph)
+                ph2 = np.stack([2 * np.pi * rs.rand(16) for _ in range(len(d))])    # impulse_response(N=1)
+                Hc[r, t] = g[0] * jakes_fading(1, num.fs, fD, ph2[0])[0]
+    else:
+        for r in range(num_rx):
+            for t in range(num_tx):
+                h = rs.normal(0, 1 / np.sqrt(2)) + 1j * rs.normal(0, 1 / np.sqrt(2))
+                Hc[r, t] = h
+                rx[r] += h * tx[t]
+    snr_lin = 10 ** (snr_db / 10)
+    for r in range(num_rx):
+        p = np.mean(np.abs(rx[r]) ** 2)
+        sg = np.sqrt((p / snr_lin) / 2)
+        rx[r] = rx[r] + (sg * rs.standard_normal(n) + 1j * (sg * rs.standard_normal(n)))
+    Y = np.stack([rx_fft_stream(rx[r], num)[:S] for r in range(num_rx)])       # [R, S, N]
+    sigma2 = 10 ** (-snr_db / 10)
+    cpts = constellation(num.modulation)
+    out = np.zeros((S, Nd), dtype=complex)
+    H_all = np.zeros((S, num_rx, num_tx, num.N), dtype=complex)
+    for s in range(min(S, Y.shape[1])):
+        H = mimo_estimate_from_grid(Y[:, s], num_tx, num)         # every OFDM symbol (:2743-2752)
+        H_all[s] = H
+        lay = np.zeros((ri, Nd), dtype=complex)
+        for k in range(npos):                                     # bins past npos are discarded by the demap
+            lay[:, k] = mimo_detect(Y[:, s, data_idx[k]], H[:, :, data_idx[k]] @ W, sigma2, detector, cpts)
+        out[s] = layer_demap(lay[:, :npos], Nd)
+    symbols = out.reshape(-1)
+    bits_rx_all = qam_demap(symbols, num.modulation)
+    errors, bits_rx = count_errors(bits, bits_rx_all)
+    return dict(signal_tx=tx, signal_rx=rx, Y=Y, H=H_all, symbols=symbols, bits_rx=bits_rx, errors=errors,
+                ber=errors / len(bits), rank=ri, pmi=pmi, W=W, channel_matrix=Hc)

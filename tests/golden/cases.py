@@ -52,4 +52,24 @@ SFBC_CASES = [
          v=3.0, nsym=14, R=2, snrs=[10.0, 20.0], full_snr=10.0, seed=24, big=True),
 ]
 
+SM_CASES = [
+    # BASELINE.json config 5: 4x4 spatial multiplexing 20 MHz 64-QAM MMSE (called per OFDM symbol by the GUI)
+    dict(name='sm_cfg5_20mhz_64qam_4x4_mmse_r4', bw=20.0, mod='64-QAM', T=4, R=4, rank=4, det='MMSE',
+         ch='rayleigh_mp', prof='Pedestrian_A', v=3.0, nsym=1, snrs=[15.0, 25.0], gseed=77, big=True),
+    dict(name='sm_1p25mhz_64qam_4x4_mmse_r4', bw=1.25, mod='64-QAM', T=4, R=4, rank=4, det='MMSE',
+         ch='rayleigh_mp', prof='Pedestrian_A', v=3.0, nsym=2, snrs=[25.0], gseed=78, drop_bits=2),
+    dict(name='sm_1p25mhz_16qam_4x4_zf_r2', bw=1.25, mod='16-QAM', T=4, R=4, rank=2, det='ZF',
+         ch='rayleigh_mp', prof='Vehicular_A', v=30.0, nsym=3, snrs=[20.0], gseed=79, drop_bits=2),
+    dict(name='sm_2p5mhz_qpsk_2x2_sic_r2_flat', bw=2.5, mod='QPSK', T=2, R=2, rank=2, det='SIC',
+         ch='awgn', prof='Pedestrian_A', v=3.0, nsym=2, snrs=[3.0], gseed=80),
+    dict(name='sm_1p25mhz_16qam_4x2_mrc_r1_flat', bw=1.25, mod='16-QAM', T=4, R=2, rank=1, det='MRC',
+         ch='awgn', prof='Pedestrian_A', v=3.0, nsym=1, snrs=[6.0], gseed=81),
+    dict(name='sm_5mhz_64qam_4x4_adaptive_mmse', bw=5.0, mod='64-QAM', T=4, R=4, rank='adaptive', det='MMSE',
+         ch='rayleigh_mp', prof='Pedestrian_A', v=3.0, nsym=1, snrs=[7.0, 22.0], gseed=82),
+    dict(name='sm_1p25mhz_16qam_4x4_sic_r3', bw=1.25, mod='16-QAM', T=4, R=4, rank=3, det='SIC',
+         ch='rayleigh_mp', prof='Pedestrian_A', v=3.0, nsym=2, snrs=[25.0], gseed=83, drop_bits=2),
+    dict(name='sm_1p25mhz_qpsk_8x4_mmse_r4_flat', bw=1.25, mod='QPSK', T=8, R=4, rank=4, det='MMSE',
+         ch='awgn', prof='Pedestrian_A', v=3.0, nsym=1, snrs=[18.0], gseed=84),
+]
+
 BIG_RX_STRIDE = 8   # 'big' SIMO cases store every 8th sample of signal_rx

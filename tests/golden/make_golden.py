@@ -32,7 +32,7 @@ from core.resource_mapper import LTEResourceGrid, PilotPattern  # noqa: E402
 from core.modulator import QAMModulator  # noqa: E402
 
 sys.path.insert(0, HERE)
-from cases import SISO_CASES, SIMO_CASES, SFBC_CASES, BIG_RX_STRIDE  # noqa: E402
+from cases import SISO_CASES, SIMO_CASES, SFBC_CASES, SM_CASES, BIG_RX_STRIDE  # noqa: E402
 
 
 def quiet(fn, *a, **k):
@@ -174,8 +174,29 @@ def sfbc_case(case):
     print(case['name'], {s: int(out[f'errors_{s}']) for s in case['snrs']})
 
 
+def sm_case(case):
+    from core.ofdm_core import simulate_spatial_multiplexing
+    cfg = LTEConfig(case['bw'], 15.0, case['mod'], 'normal')
+    bits = make_bits(case['gseed'], nd_of(cfg) * cfg.bits_per_symbol * case['nsym'] - case.get('drop_bits', 0))
+    out = dict(bits=np.packbits(bits), nbits=len(bits))
+    for snr in case['snrs']:
+        np.random.seed(case['gseed'])          # H_initial is drawn from the caller's global RNG state
+        r = quiet(simulate_spatial_multiplexing, bits, num_tx=case['T'], num_rx=case['R'], rank=case['rank'],
+                  detector_type=case['det'], modulation=case['mod'], snr_db=snr, config=cfg,
+                  channel_type=case['ch'], itu_profile=case['prof'], velocity_kmh=case['v'], frequency_ghz=2.0)
+        out[f'errors_{snr}'] = r['errors']
+        out[f'bits_rx_{snr}'] = np.packbits(r['bits_received_array'].astype(np.uint8))
+        out[f'rank_pmi_{snr}'] = np.array([r['rank'], r['pmi_used']])
+        out[f'W_{snr}'] = np.asarray(r['precoder_matrix'], dtype=complex)
+        out[f'channel_matrix_{snr}'] = r['channel_matrix']
+    np.savez_compressed(os.path.join(HERE, case['name'] + '.npz'), **out)
+    print(case['name'], {s: int(out[f'errors_{s}']) for s in case['snrs']})
+
+
 def main():
     tables()
+    for case in SM_CASES:
+        sm_case(case)
     install_sfbc_shim()
     for case in SFBC_CASES:
         sfbc_case(case)

@@ -1,0 +1,126 @@
+"""Spatial multiplexing (BASELINE.json config 5) on the GPU: detector kernels vs the oracle's
+numpy.linalg restatement, API vs golden vectors from the reference."""
+import numpy as np
+import pytest
+
+from cases import SM_CASES
+from helpers import golden_bits, golden_bits_rx, load_golden, numerology, rel_err
+from oracle import lte_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.mark.parametrize('det,L,R,T', [('MMSE', 4, 4, 4), ('MMSE', 2, 4, 4), ('ZF', 2, 4, 4), ('ZF', 4, 4, 4),
+                                       ('SIC', 3, 4, 4), ('SIC', 2, 2, 2), ('MRC', 1, 2, 4), ('MMSE', 4, 8, 8)])
+def test_detector_kernel_matches_numpy(det, L, R, T):
+    from core.mimo_detector import MIMODetector
+    rs = np.random.RandomState(R * 100 + L)
+    K = 300
+    H = (rs.randn(R, T, K) + 1j * rs.randn(R, T, K)) / np.sqrt(2)
+    W = O.codebook(T, L)[min(1, len(O.codebook(T, L)) - 1)]
+    c = O.constellation('16-QAM')
+    s = c[rs.randint(0, 16, (L, K))]
+    y = np.einsum('rtk,tl,lk->rk', H, W, s) + 0.05 * (rs.randn(R, K) + 1j * rs.randn(R, K))
+    # the kernel sees fp32 inputs: give the oracle the same rounded values
+    H32, y32 = H.astype(np.complex64).astype(complex), y.astype(np.complex64).astype(complex)
+    W32 = W.astype(np.complex64).astype(complex)
+    want = np.stack([O.mimo_detect(y32[:, k], H32[:, :, k] @ W32, 0.01, det, c) for k in range(K)], axis=1)
+    d = MIMODetector(R, L, det, constellation=c)
+    got = d.detect(y, H, 0.01, W)
+    assert got.shape == (L, K)
+    if det == 'SIC':
+        assert np.mean(np.abs(got - want) < 1e-6) > 0.995          # hard decisions: identical but for boundary cases
+    else:
+        assert rel_err(got, want) < TOL
+    one = d.detect(y[:, 0], H[:, :, 0], 0.01, W)
+    assert one.shape == (L,) and np.allclose(one, got[:, 0], atol=1e-5)
+
+
+def test_detector_error_conventions():
+    from core.mimo_detector import MIMODetector
+    with pytest.raises(ValueError):
+        MIMODetector(2, 4, 'MMSE')
+    d = MIMODetector(4, 2, 'MRC')
+    with pytest.raises(ValueError):
+        d.detect(np.zeros((4, 3), complex), np.zeros((4, 4, 3), complex), 0.1, np.zeros((4, 2), complex))
+    with pytest.raises(ValueError):
+        MIMODetector(4, 2, 'ML').detect(np.zeros((4, 3), complex), np.zeros((4, 4, 3), complex), 0.1)
+
+
+def test_reference_toy_case_2x2_mmse():
+    """reference core/mimo_detector.py:387-404."""
+    from core.mimo_detector import MIMODetector
+    H = np.array([[1.0 + 0.5j, 0.3 - 0.2j], [0.2 + 0.1j, 0.9 - 0.3j]])
+    s = np.array([1 + 1j, -1 + 1j]) / np.sqrt(2)
+    y = H @ s + 0.1 * (np.array([0.3, -0.2]) + 1j * np.array([0.1, 0.25]))
+    for det in ('MMSE', 'ZF'):
+        assert np.linalg.norm(s - MIMODetector(2, 2, det).detect(y, H, 0.01)) < 1.0
+
+
+@pytest.mark.parametrize('case', SM_CASES, ids=lambda c: c['name'])
+def test_simulate_spatial_multiplexing_matches_reference(case):
+    from config import LTEConfig
+    from core.ofdm_core import simulate_spatial_multiplexing
+    from gpu_chain import boundary_distance
+    g = load_golden(case['name'])
+    bits = golden_bits(g)
+    num = numerology(case)
+    cfg = LTEConfig(case['bw'], 15.0, case['mod'])
+    for snr in case['snrs']:
+        np.random.seed(case['gseed'])
+        r = simulate_spatial_multiplexing(bits, num_tx=case['T'], num_rx=case['R'], rank=case['rank'],
+                                          detector_type=case['det'], modulation=case['mod'], snr_db=snr, config=cfg,
+                                          channel_type=case['ch'], itu_profile=case['prof'],
+                                          velocity_kmh=case['v'], frequency_ghz=2.0)
+        o = O.simulate_sm(bits, num, case['T'], case['R'], case['rank'], case['det'], snr, case['ch'], case['prof'],
+                          case['v'], 2.0, global_seed=case['gseed'])
+        assert [r['rank'], r['pmi_used']] == list(g[f'rank_pmi_{snr}'])
+        assert rel_err(r['precoder_matrix'], g[f'W_{snr}']) < 1e-12
+        assert rel_err(r['channel_matrix'], g[f'channel_matrix_{snr}']) < TOL
+        want = golden_bits_rx(g, snr)
+        diff = np.flatnonzero(r['bits_received_array'] != want)
+        nsym_used = len(o['symbols'])
+        if case['det'] != 'SIC':
+            # detector outputs: median element-wise agreement; ill-conditioned bins amplify fp32 input rounding
+            elem = np.abs(r['symbols_rx'][:nsym_used] - o['symbols']) / np.maximum(np.abs(o['symbols']), 1e-3)
+            assert np.median(elem) < TOL
+            if len(diff):
+                d = boundary_distance(o['symbols'], num.modulation)
+                bad = np.unique(diff // num.bits_per_symbol)
+                assert np.all(d[bad] < 1e-3 * np.maximum(1.0, np.abs(o['symbols'][bad])))
+            assert len(diff) <= 3 * num.bits_per_symbol
+        else:
+            assert len(diff) <= 0.002 * len(want) + 2 * num.bits_per_symbol    # a flipped hard decision propagates
+        assert abs(r['errors'] - int(g[f'errors_{snr}'])) <= len(diff)
+        assert r['mode'] == 'Spatial Multiplexing TM4' and r['num_tx'] == case['T'] and r['detector_type'] == case['det']
+
+
+def test_helper_classes():
+    from core.codebook_lte import LTECodebook
+    from core.layer_mapper import LayerMapper
+    from core.rank_adaptation import RankAdaptation
+    for T in (2, 4, 8):
+        for r in range(1, min(T, 4) + 1):
+            cb = LTECodebook(T, 'TM4', r)
+            ref = O.codebook(T, r)
+            assert cb.codebook_size == len(ref)
+            for a, b in zip(cb.get_codebook(), ref):
+                assert np.array_equal(np.asarray(a, dtype=complex), np.asarray(b, dtype=complex))
+    with pytest.raises(ValueError):
+        LTECodebook(4, 'TM6', 2)
+    with pytest.raises(ValueError):
+        LTECodebook(2, 'TM4', 3)
+    with pytest.raises(ValueError):
+        LTECodebook(4, 'TM4', 1).get_precoder(99)
+    m = LayerMapper(3)
+    x = np.arange(10) + 0j
+    assert np.array_equal(m.demap_from_layers(m.map_to_layers(x), 10), x)
+    assert m.get_padded_length(10) == 12 and m.get_symbols_per_layer(10) == 4
+    with pytest.raises(ValueError):
+        LayerMapper(9)
+    H = (np.random.RandomState(0).randn(4, 4) + 1j * np.random.RandomState(1).randn(4, 4)) / np.sqrt(8)
+    fb = RankAdaptation(4, 4, snr_db=20.0).get_feedback(H)
+    ri, pmi, W = O.rank_feedback(H, 4, 4, 20.0)
+    assert (fb['ri'], fb['pmi']) == (ri, pmi) and np.array_equal(fb['W'], W)
+    assert RankAdaptation(4, 4, snr_db=3.0).get_feedback(H)['ri'] == 1

@@ -102,3 +102,22 @@ def test_sfbc_matches_reference(case):
         assert rel_err(o['channel_matrix'], g[f'channel_matrix_{snr}']) < TOL64
         assert abs(o['papr_db_tx0'] - g[f'papr_{snr}'][0]) < 1e-9
         assert abs(o['papr_db_tx1'] - g[f'papr_{snr}'][1]) < 1e-9
+
+
+from cases import SM_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize('case', SM_CASES, ids=lambda c: c['name'])
+def test_spatial_multiplexing_matches_reference(case):
+    from helpers import numerology
+    g = load_golden(case['name'])
+    bits = golden_bits(g)
+    num = numerology(case)
+    for snr in case['snrs']:
+        o = O.simulate_sm(bits, num, case['T'], case['R'], case['rank'], case['det'], snr, case['ch'], case['prof'],
+                          case['v'], 2.0, global_seed=case['gseed'])
+        assert o['errors'] == int(g[f'errors_{snr}'])
+        assert np.array_equal(o['bits_rx'], golden_bits_rx(g, snr))
+        assert [o['rank'], o['pmi']] == list(g[f'rank_pmi_{snr}'])
+        assert rel_err(o['W'], g[f'W_{snr}']) < TOL64
+        assert rel_err(o['channel_matrix'], g[f'channel_matrix_{snr}']) < TOL64
