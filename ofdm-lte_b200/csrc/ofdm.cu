@@ -1,169 +1,252 @@
 // Stage 1+2 (TX: QAM map + resource grid + IFFT + CP) and stage 2 (RX: noise add +
-// CP strip + FFT) kernels.  One transform per N/16 threads, 128-thread CTAs.
-#include "fft.cuh"
+// CP strip + FFT) kernels on the packed-pair FFT core (fft2.cuh): N/16 threads carry two
+// transforms (consecutive OFDM symbols) at once, 128-thread CTAs.
+#include "fft2.cuh"
 
 // ------------------------------------------------------------------------------ TX
 // Replaces core/modulator.py:61-88 (bits_to_symbols), core/resource_mapper.py:181-223
 // (map_symbols) and core/modulator.py:242-248 (ifft * sqrt(N), CP prepend).
+// The grid synthesis and the CP / statistics epilogue are rolled loops that stage through the
+// pair's shared-memory buffer: the kernel stays inside the instruction cache (a fully unrolled
+// version measured 18 % "no instruction" stalls).
 template <int N>
 __global__ void __launch_bounds__(FFT_CTA_THREADS)
 tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float2* __restrict__ symbols,
                    int T, float2* __restrict__ tx, float2* __restrict__ qam_out,
                    double* __restrict__ stats, int S, long long total) {
-    constexpr int TPF = N / FFT_ELEMS, FPC = fft_per_cta(N);
-    extern __shared__ float2 smem[];
-    const int f_local = threadIdx.x / TPF, j = threadIdx.x % TPF;
-    const long long f = (long long)blockIdx.x * FPC + f_local;   // OFDM symbol id = row*S + s
-    const bool valid = f < total;
-    float2* sA = smem + (size_t)f_local * 2 * fft_smem_elems(N);
-    float2* sB = sA + fft_smem_elems(N);
-
-    const long long row = valid ? f / S : 0;          // row = b*T + t
-    const int t_ant = (int)(row % T);
-    const long long b = row / T;
-    const int s_sym = valid ? (int)(f % S) : 0;
+    constexpr int TPF = N / FFT_ELEMS, PPC = fft2_pairs_per_cta(N);
+    extern __shared__ float4 smem4[];
+    __shared__ float s_lev[8];
+    if (threadIdx.x < 8) s_lev[threadIdx.x] = P.lev[threadIdx.x];
+    __syncthreads();
+    const int p_local = threadIdx.x / TPF, j = threadIdx.x % TPF;
+    float4* sbuf = smem4 + (size_t)p_local * fft_smem_elems(N);
+    const long long f0 = ((long long)blockIdx.x * PPC + p_local) * 2;   // OFDM symbol ids f0, f0+1 (= row*S + s)
     const int h = P.bps >> 1, mask = (1 << h) - 1;
 
-    float2 v[FFT_ELEMS];
+    bool valid[2];
+    long long row[2];
+    int s_sym[2];
+    const float2* pil[2];
+    const float2* srow[2];
+    size_t ibase[2];
 #pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const long long f = f0 + m;
+        valid[m] = f < total;
+        row[m] = valid[m] ? f / S : 0;                 // row = b*T + t
+        s_sym[m] = valid[m] ? (int)(f - row[m] * S) : 0;
+        pil[m] = P.pilots + (size_t)(row[m] % T) * P.Np;
+        srow[m] = symbols ? symbols + ((size_t)row[m] * S + s_sym[m]) * P.Nd : nullptr;
+        ibase[m] = ((size_t)(row[m] / T) * S + s_sym[m]) * P.Nd;
+    }
+#pragma unroll 2
     for (int e = 0; e < FFT_ELEMS; ++e) {
-        const int k = j + e * TPF;
-        float2 val = make_float2(0.f, 0.f);
-        if (valid) {
-            const int m = P.bin_map[k];
-            if (m >= 0) {
-                if (m & BIN_PILOT_FLAG) {
-                    val = P.pilots[(size_t)t_ant * P.Np + (m & (BIN_PILOT_FLAG - 1))];
-                } else if (symbols) {
-                    val = symbols[((size_t)row * S + s_sym) * P.Nd + m];
-                } else {
-                    const size_t o = ((size_t)b * S + s_sym) * P.Nd + m;
-                    const int i = idx[o];
-                    val = make_float2(P.lev[(i >> h) & mask], P.lev[i & mask]);
-                    if (qam_out) qam_out[o] = val;
+        const int kbin = j + e * TPF;
+        const int mm = P.bin_map[kbin];
+        float2 x[2];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            float2 val = make_float2(0.f, 0.f);
+            if (valid[m] && mm >= 0) {
+                if (mm & BIN_PILOT_FLAG) val = pil[m][mm & (BIN_PILOT_FLAG - 1)];
+                else if (srow[m]) val = srow[m][mm];
+                else {
+                    const int i = idx[ibase[m] + mm];
+                    val = make_float2(s_lev[(i >> h) & mask], s_lev[i & mask]);
+                    if (qam_out) qam_out[ibase[m] + mm] = val;
                 }
             }
+            x[m] = val;
         }
-        v[e] = val;
+        sbuf[fft_pad(kbin)] = make_float4(x[0].x, x[1].x, x[0].y, x[1].y);   // read back by this thread only
     }
-
-    fft_run<N, true>(v, sA, sB, P.twiddle, j);
-
-    float pmax = 0.f, psum = 0.f;
-    if (valid) {
-        float2* o = tx + (size_t)row * S * P.L + (size_t)s_sym * P.L;
-        const int tail0 = N - P.cp;
+    c2 v[FFT_ELEMS];
 #pragma unroll
-        for (int e = 0; e < FFT_ELEMS; ++e) {
-            const int n = j + e * TPF;
-            const float2 x = cscale(v[e], P.inv_sqrt_n);
-            o[P.cp + n] = x;
-            const float pw = cabs2(x);
-            pmax = fmaxf(pmax, pw);
-            psum += pw;
-            if (n >= tail0) { o[n - tail0] = x; psum += pw; }
+    for (int e = 0; e < FFT_ELEMS; ++e) {
+        const float4 q = sbuf[fft_pad(j + e * TPF)];
+        v[e] = {pk(q.x, q.y), pk(q.z, q.w)};
+    }
+    __syncthreads();          // the buffer is re-used by the exchanges
+
+    fft2_run<N, true>(v, sbuf, P.twiddle, j);
+
+    __syncthreads();          // all exchange reads are done
+    const f2 scale = pk(P.inv_sqrt_n, P.inv_sqrt_n);
+#pragma unroll
+    for (int e = 0; e < FFT_ELEMS; ++e) {
+        float a, b, c, d;
+        upk(mul2(v[e].re, scale), a, b);
+        upk(mul2(v[e].im, scale), c, d);
+        sbuf[fft_pad(j + e * TPF)] = make_float4(a, b, c, d);
+    }
+    float pmax[2] = {0.f, 0.f}, psum[2] = {0.f, 0.f};
+    const int tail0 = N - P.cp;
+    float2* o[2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) o[m] = tx + (size_t)row[m] * S * P.L + (size_t)s_sym[m] * P.L;
+#pragma unroll 2
+    for (int e = 0; e < FFT_ELEMS; ++e) {
+        const int n = j + e * TPF;
+        const float4 q = sbuf[fft_pad(n)];
+        const float2 xo[2] = {make_float2(q.x, q.z), make_float2(q.y, q.w)};
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            if (valid[m]) {
+                o[m][P.cp + n] = xo[m];
+                const float pw = cabs2(xo[m]);
+                pmax[m] = fmaxf(pmax[m], pw);
+                psum[m] += pw;
+                if (n >= tail0) { o[m][n - tail0] = xo[m]; psum[m] += pw; }
+            }
         }
     }
     if (stats) {
         // per-stream peak and total power including the CP (core/ofdm_core.py:131-133)
-        if constexpr (TPF >= 32) {
-            pmax = warp_max(pmax);
-            psum = warp_sum(psum);
-            __shared__ float red[2][FFT_CTA_THREADS / 32];
-            const int w = threadIdx.x >> 5;
-            if ((threadIdx.x & 31) == 0) { red[0][w] = pmax; red[1][w] = psum; }
-            __syncthreads();
+        __shared__ float red[2][2][FFT_CTA_THREADS / 32];
 #pragma unroll
-            for (int q = 1; q < TPF / 32; ++q) { pmax = fmaxf(pmax, red[0][w + q]); psum += red[1][w + q]; }
-        } else {
+        for (int m = 0; m < 2; ++m) {
+            float mx = pmax[m], sm = psum[m];
+            if constexpr (TPF >= 32) {
+                mx = warp_max(mx);
+                sm = warp_sum(sm);
+                const int w = threadIdx.x >> 5;
+                if ((threadIdx.x & 31) == 0) { red[m][0][w] = mx; red[m][1][w] = sm; }
+            } else {
 #pragma unroll
-            for (int o = TPF / 2; o > 0; o >>= 1) {
-                pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
-                psum += __shfl_xor_sync(0xffffffffu, psum, o);
+                for (int ofs = TPF / 2; ofs > 0; ofs >>= 1) {
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, ofs));
+                    sm += __shfl_xor_sync(0xffffffffu, sm, ofs);
+                }
             }
+            pmax[m] = mx;
+            psum[m] = sm;
         }
-        if (j == 0 && valid) {
-            atomicMax((unsigned long long*)&stats[2 * row],
-                      (unsigned long long)__double_as_longlong((double)pmax));
-            atomicAdd(&stats[2 * row + 1], (double)psum);
+        if constexpr (TPF >= 32) {
+            __syncthreads();
+            const int w = threadIdx.x >> 5;
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int q = 1; q < TPF / 32; ++q) {
+                    pmax[m] = fmaxf(pmax[m], red[m][0][w + q]);
+                    psum[m] += red[m][1][w + q];
+                }
+        }
+        if (j == 0) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+                if (valid[m]) {
+                    atomicMax((unsigned long long*)&stats[2 * row[m]],
+                              (unsigned long long)__double_as_longlong((double)pmax[m]));
+                    atomicAdd(&stats[2 * row[m] + 1], (double)psum[m]);
+                }
         }
     }
 }
 
 // ------------------------------------------------------------------------------ RX
 // Replaces core/lte_receiver.py:444-491 (strip CP, fft / sqrt(N)); optionally adds the
-// AWGN of core/channel.py:216-232 while loading (sigma from the measured stream power).
-template <int N>
+// AWGN of core/channel.py:216-232 (sigma from the measured stream power).
+// NOISE: 0 none, 1 per time sample before the FFT (injected normals or Philox), 2 Philox on the
+// kept output bins after the FFT.  Loader and epilogue are rolled loops through the pair's
+// shared-memory buffer so the Philox/Box-Muller body exists once in the instruction stream.
+template <int N, int NOISE>
 __global__ void __launch_bounds__(FFT_CTA_THREADS)
 rx_fft_kernel(const DevPlan P, const float2* __restrict__ rx, int rx_div, const double* __restrict__ power,
               const float* __restrict__ snr_lin, const float2* __restrict__ z, uint32_t key,
-              unsigned long long row_id0, float2* __restrict__ Y, int k0, int nk, int S, long long total,
-              int noise_freq) {
-    constexpr int TPF = N / FFT_ELEMS, FPC = fft_per_cta(N);
-    extern __shared__ float2 smem[];
-    const int f_local = threadIdx.x / TPF, j = threadIdx.x % TPF;
-    const long long f = (long long)blockIdx.x * FPC + f_local;   // row*S + s
-    const bool valid = f < total;
-    float2* sA = smem + (size_t)f_local * 2 * fft_smem_elems(N);
-    float2* sB = sA + fft_smem_elems(N);
-    const long long row = valid ? f / S : 0;
-    const int s_sym = valid ? (int)(f % S) : 0;
+              unsigned long long row_id0, float2* __restrict__ Y, int k0, int nk, int S, long long total) {
+    constexpr int TPF = N / FFT_ELEMS, PPC = fft2_pairs_per_cta(N);
+    extern __shared__ float4 smem4[];
+    const int p_local = threadIdx.x / TPF, j = threadIdx.x % TPF;
+    float4* sbuf = smem4 + (size_t)p_local * fft_smem_elems(N);
+    const long long f0 = ((long long)blockIdx.x * PPC + p_local) * 2;
     const size_t n_stream = (size_t)S * P.L;
 
-    float2 v[FFT_ELEMS];
-    if (valid) {
-        const size_t m0 = (size_t)s_sym * P.L + P.cp;
-        const float2* src = rx + (size_t)(row / rx_div) * n_stream + m0;
+    bool valid[2];
+    long long row[2];
+    int s_sym[2];
+    float sigma[2] = {0.f, 0.f};
+    uint32_t rid[2];
+    const float2* src[2];
 #pragma unroll
-        for (int e = 0; e < FFT_ELEMS; ++e) v[e] = src[j + e * TPF];
-        if (power && !noise_freq) {
-            const float sigma = lte_sigma(power[row], (float)n_stream, snr_lin[row]);
-            if (z) {
-                const float2* zs = z + (size_t)row * n_stream + m0;
-#pragma unroll
-                for (int e = 0; e < FFT_ELEMS; ++e) {
-                    const float2 w = zs[j + e * TPF];
-                    v[e].x = fmaf(sigma, w.x, v[e].x);
-                    v[e].y = fmaf(sigma, w.y, v[e].y);
-                }
-            } else {
-                const uint32_t rid = (uint32_t)(row_id0 + (unsigned long long)row);
-#pragma unroll
-                for (int e = 0; e < FFT_ELEMS; ++e) {
-                    const float2 w = lte_noise_sample(key, rid, (uint32_t)(m0 + j + e * TPF));
-                    v[e].x = fmaf(sigma, w.x, v[e].x);
-                    v[e].y = fmaf(sigma, w.y, v[e].y);
-                }
-            }
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < FFT_ELEMS; ++e) v[e] = make_float2(0.f, 0.f);
+    for (int m = 0; m < 2; ++m) {
+        const long long f = f0 + m;
+        valid[m] = f < total;
+        row[m] = valid[m] ? f / S : 0;
+        s_sym[m] = valid[m] ? (int)(f - row[m] * S) : 0;
+        src[m] = rx + (size_t)(row[m] / rx_div) * n_stream + (size_t)s_sym[m] * P.L + P.cp;
+        rid[m] = (uint32_t)(row_id0 + (unsigned long long)row[m]);
+        if (NOISE != 0 && valid[m]) sigma[m] = lte_sigma(power[row[m]], (float)n_stream, snr_lin[row[m]]);
     }
 
-    fft_run<N, false>(v, sA, sB, P.twiddle, j);
-
-    if (valid) {
-        float2* o = Y + ((size_t)row * S + s_sym) * nk;
-        if (power && noise_freq) {
-            // The unitary FFT maps white Gaussian noise to white Gaussian noise of the same
-            // variance, so the engine draws it directly on the bins it keeps.
-            const float sigma = lte_sigma(power[row], (float)n_stream, snr_lin[row]);
-            const uint32_t rid = (uint32_t)(row_id0 + (unsigned long long)row);
+    c2 v[FFT_ELEMS];
+    if constexpr (NOISE == 1) {
+#pragma unroll 2
+        for (int e = 0; e < FFT_ELEMS; ++e) {
+            const int n = j + e * TPF;
+            float2 x[2];
 #pragma unroll
-            for (int e = 0; e < FFT_ELEMS; ++e) {
-                const int kb = j + e * TPF;
-                const int k = kb - k0;
-                if (k >= 0 && k < nk) {
-                    const float2 w = lte_noise_sample(key, rid, (uint32_t)(s_sym * N + kb));
-                    o[k] = make_float2(fmaf(v[e].x, P.inv_sqrt_n, sigma * w.x), fmaf(v[e].y, P.inv_sqrt_n, sigma * w.y));
+            for (int m = 0; m < 2; ++m) {
+                x[m] = make_float2(0.f, 0.f);
+                if (valid[m]) {
+                    x[m] = src[m][n];
+                    const size_t ms = (size_t)s_sym[m] * P.L + P.cp + n;
+                    const float2 w = z ? z[(size_t)row[m] * n_stream + ms] : lte_noise_sample(key, rid[m], (uint32_t)ms);
+                    x[m].x = fmaf(sigma[m], w.x, x[m].x);
+                    x[m].y = fmaf(sigma[m], w.y, x[m].y);
                 }
             }
-        } else {
+            sbuf[fft_pad(n)] = make_float4(x[0].x, x[1].x, x[0].y, x[1].y);    // read back by this thread only
+        }
 #pragma unroll
-            for (int e = 0; e < FFT_ELEMS; ++e) {
-                const int k = j + e * TPF - k0;
-                if (k >= 0 && k < nk) o[k] = cscale(v[e], P.inv_sqrt_n);
+        for (int e = 0; e < FFT_ELEMS; ++e) {
+            const float4 q = sbuf[fft_pad(j + e * TPF)];
+            v[e] = {pk(q.x, q.y), pk(q.z, q.w)};
+        }
+        __syncthreads();
+    } else {
+#pragma unroll
+        for (int e = 0; e < FFT_ELEMS; ++e) {
+            const float2 a = valid[0] ? src[0][j + e * TPF] : make_float2(0.f, 0.f);
+            const float2 b = valid[1] ? src[1][j + e * TPF] : make_float2(0.f, 0.f);
+            v[e] = {pk(a.x, b.x), pk(a.y, b.y)};
+        }
+    }
+
+    fft2_run<N, false>(v, sbuf, P.twiddle, j);
+
+    __syncthreads();          // all exchange reads are done
+    const f2 scale = pk(P.inv_sqrt_n, P.inv_sqrt_n);
+#pragma unroll
+    for (int e = 0; e < FFT_ELEMS; ++e) {
+        float a, b, c, d;
+        upk(mul2(v[e].re, scale), a, b);
+        upk(mul2(v[e].im, scale), c, d);
+        sbuf[fft_pad(j + e * TPF)] = make_float4(a, b, c, d);
+    }
+    float2* o[2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) o[m] = Y + ((size_t)row[m] * S + s_sym[m]) * nk;
+#pragma unroll 2
+    for (int e = 0; e < FFT_ELEMS; ++e) {
+        const int kb = j + e * TPF;
+        const int k = kb - k0;
+        if (k >= 0 && k < nk) {
+            const float4 q = sbuf[fft_pad(kb)];
+            float2 out[2] = {make_float2(q.x, q.z), make_float2(q.y, q.w)};
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                if (valid[m]) {
+                    if constexpr (NOISE == 2) {
+                        // The unitary FFT maps white Gaussian noise to white Gaussian noise of the same
+                        // variance, so the engine draws it directly on the bins it keeps.
+                        const float2 w = lte_noise_sample(key, rid[m], (uint32_t)(s_sym[m] * N + kb));
+                        out[m].x = fmaf(sigma[m], w.x, out[m].x);
+                        out[m].y = fmaf(sigma[m], w.y, out[m].y);
+                    }
+                    o[m][k] = out[m];
+                }
             }
         }
     }
@@ -191,9 +274,10 @@ extern "C" int lte_tx_map_ifft(const lte_plan* p, const uint8_t* idx, const lte_
     return dispatch_n(p->dev.N, [&](auto n) -> int {
         constexpr int N = decltype(n)::value;
         auto k = tx_map_ifft_kernel<N>;
-        const int smem = fft_cta_smem_bytes(N);
+        const int smem = fft2_cta_smem_bytes(N);
         LTE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        const long long grid = (total + fft_per_cta(N) - 1) / fft_per_cta(N);
+        const long long per = 2 * fft2_pairs_per_cta(N);
+        const long long grid = (total + per - 1) / per;
         k<<<(unsigned)grid, FFT_CTA_THREADS, smem, (cudaStream_t)stream>>>(
             p->dev, idx, (const float2*)symbols, T, (float2*)tx, (float2*)qam_out, stats, S, total);
         LTE_CHECK_CUDA(cudaGetLastError());
@@ -216,14 +300,19 @@ extern "C" int lte_rx_fft(const lte_plan* p, const lte_c32* rx, int32_t rx_div, 
     const uint32_t key = lte_key(seed, LTE_DOMAIN_NOISE);
     return dispatch_n(p->dev.N, [&](auto n) -> int {
         constexpr int N = decltype(n)::value;
-        auto k = rx_fft_kernel<N>;
-        const int smem = fft_cta_smem_bytes(N);
-        LTE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        const long long grid = (total + fft_per_cta(N) - 1) / fft_per_cta(N);
-        k<<<(unsigned)grid, FFT_CTA_THREADS, smem, (cudaStream_t)stream>>>(
-            p->dev, (const float2*)rx, rx_div, power, snr_lin, (const float2*)z, key, row_id0, (float2*)Y, k0, nk,
-            S, total, noise_domain);
-        LTE_CHECK_CUDA(cudaGetLastError());
-        return LTE_OK;
+        const int smem = fft2_cta_smem_bytes(N);
+        const long long per = 2 * fft2_pairs_per_cta(N);
+        const long long grid = (total + per - 1) / per;
+        auto launch = [&](auto k) -> int {
+            LTE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            k<<<(unsigned)grid, FFT_CTA_THREADS, smem, (cudaStream_t)stream>>>(
+                p->dev, (const float2*)rx, rx_div, power, snr_lin, (const float2*)z, key, row_id0, (float2*)Y, k0,
+                nk, S, total);
+            LTE_CHECK_CUDA(cudaGetLastError());
+            return LTE_OK;
+        };
+        if (!power) return launch(rx_fft_kernel<N, 0>);
+        if (noise_domain == 0) return launch(rx_fft_kernel<N, 1>);
+        return launch(rx_fft_kernel<N, 2>);
     });
 }
