@@ -21,6 +21,8 @@ tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float
     __syncthreads();
     const int p_local = threadIdx.x / TPF, j = threadIdx.x % TPF;
     float4* sbuf = smem4 + (size_t)p_local * fft_smem_elems(N);
+    const int idx_stride = (P.Nd + 15) & ~15;
+    uint8_t* idx_stage = (uint8_t*)(smem4 + (size_t)PPC * fft_smem_elems(N));   // [PPC][2][idx_stride]
     const long long f0 = ((long long)blockIdx.x * PPC + p_local) * 2;   // OFDM symbol ids f0, f0+1 (= row*S + s)
     const int h = P.bps >> 1, mask = (1 << h) - 1;
 
@@ -40,7 +42,23 @@ tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float
         srow[m] = symbols ? symbols + ((size_t)row[m] * S + s_sym[m]) * P.Nd : nullptr;
         ibase[m] = ((size_t)(row[m] / T) * S + s_sym[m]) * P.Nd;
     }
-#pragma unroll 2
+    // Stage the two symbols' index bytes with independent coalesced loads (one 8-byte group per
+    // thread and symbol) so the grid synthesis below never waits on a bin_map -> idx load chain.
+    uint8_t* sidx = idx_stage + (size_t)p_local * 2 * idx_stride;
+    if (!symbols) {
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            if (!valid[m]) continue;
+            const uint8_t* g = idx + ibase[m];
+            for (int c = j * 8; c < P.Nd; c += TPF * 8) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (c + q < P.Nd) sidx[m * idx_stride + c + q] = g[c + q];
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll 4
     for (int e = 0; e < FFT_ELEMS; ++e) {
         const int kbin = j + e * TPF;
         const int mm = P.bin_map[kbin];
@@ -52,7 +70,7 @@ tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float
                 if (mm & BIN_PILOT_FLAG) val = pil[m][mm & (BIN_PILOT_FLAG - 1)];
                 else if (srow[m]) val = srow[m][mm];
                 else {
-                    const int i = idx[ibase[m] + mm];
+                    const int i = sidx[m * idx_stride + mm];
                     val = make_float2(s_lev[(i >> h) & mask], s_lev[i & mask]);
                     if (qam_out) qam_out[ibase[m] + mm] = val;
                 }
@@ -274,7 +292,7 @@ extern "C" int lte_tx_map_ifft(const lte_plan* p, const uint8_t* idx, const lte_
     return dispatch_n(p->dev.N, [&](auto n) -> int {
         constexpr int N = decltype(n)::value;
         auto k = tx_map_ifft_kernel<N>;
-        const int smem = fft2_cta_smem_bytes(N);
+        const int smem = fft2_cta_smem_bytes(N) + fft2_pairs_per_cta(N) * 2 * ((p->dev.Nd + 15) & ~15);
         LTE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         const long long per = 2 * fft2_pairs_per_cta(N);
         const long long grid = (total + per - 1) / per;
