@@ -235,22 +235,43 @@ def run_gpu(args, rank, world):
     nbytes = (nbits + 7) // 8
     host_bits = torch.from_numpy(np.random.RandomState(7 + rank).randint(0, 256, (B, nbytes), dtype=np.uint8)).pin_memory()
     host_err = torch.empty(B, dtype=torch.int64).pin_memory()
-    dev_bits = torch.empty((B, nbytes), dtype=torch.uint8, device=dev)
+    # The host-buffer API double-buffers its device input: the H2D copy of step i+1 runs on a copy
+    # stream while step i computes; both are inside the timed region.
+    dev_bits = [torch.empty((B, nbytes), dtype=torch.uint8, device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream(dev)
 
-    def e2e_step(i):
-        dev_bits.copy_(host_bits, non_blocking=True)
-        ix = eng.bits_to_indices(dev_bits, nbits, S, packed=True)
+    def e2e_upload(i):
+        k = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[k])
+            dev_bits[k].copy_(host_bits, non_blocking=True)
+            ev_copied[k].record(copy_stream)
+
+    def e2e_step(i, last):
+        k = i % 2
+        if not last:
+            e2e_upload(i + 1)
+        main.wait_event(ev_copied[k])
+        ix = eng.bits_to_indices(dev_bits[k], nbits, S, packed=True)
         sid0 = ((i * world) + rank) * B
         err = eng.simo_ber(ws, chan, snr_rows, seed + 1, stream_id0=sid0, idx=ix, nbits=nbits)
         host_err.copy_(err, non_blocking=True)
+        ev_free[k].record(main)
 
+    for k in range(2):
+        ev_free[k].record(main)
+    e2e_upload(0)
     for i in range(2):
-        e2e_step(i)
+        e2e_step(i, last=(i == 1))
     sync()
+    e2e_steps = max(2, min(args.steps, 50))
     e0.record()
-    e2e_steps = max(1, min(args.steps, 10))
+    e2e_upload(2)                               # every upload of a timed step is inside the timed region
     for i in range(e2e_steps):
-        e2e_step(i)
+        e2e_step(2 + i, last=(i == e2e_steps - 1))
     e1.record()
     sync()
     ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
