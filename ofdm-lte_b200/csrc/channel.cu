@@ -112,8 +112,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
 __host__ __device__ constexpr int tdl_xs_stride(int halo, int tile) {
-    return ((halo + tile) / 8) | 1;      // odd row stride: conflict-free 128-bit fills and reads
+    return (halo + tile) / 8 + ((2 - ((halo + tile) / 8) % 16) + 16) % 16;   // == 2 (mod 16): conflict-free 64-bit rows
 }
+__host__ __device__ constexpr int tdl_os_stride(int tile) { return (tile / 8) | 1; }   // odd: conflict-free 128-bit rows
 
 // antennas per thread (RG, a multiple of 2: each FFMA2 serves an antenna pair) and CTAs per SM
 __host__ __device__ constexpr int tdl_rg(int R) { return R <= 2 ? 2 : 4; }
@@ -153,41 +154,41 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float* __rest
     constexpr int NG = (R + RG - 1) / RG, NT = TDL_THREADS * NG, R2 = NG * RG;
     constexpr int TILE = TDL_THREADS * V;
     constexpr int NC = 2 * K + 1;
-    constexpr int XS = tdl_xs_stride(HALO, TILE);
+    constexpr int XS = tdl_xs_stride(HALO, TILE), OS = tdl_os_stride(TILE);
     constexpr int SPAN = HALO + TILE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nblk = C.pb >= TILE ? 1 : TILE / C.pb;         // polynomial blocks per tile
     const int ntt = T * C.num_taps;
     const int ncoef = nblk * ntt * NC * 2 * R2;              // floats per tile
-    // shared memory: plane [T][8][XS] float4 | outb [8][XS] float4 | raw [2][T][SPAN] float2 | coef [2][ncoef]
-    // (plane doubles as output staging buffer 0; outb holds the other NG*RP - 1 antenna pairs)
-    float4* plane = (float4*)smem_raw;
-    float4* outb = plane + (size_t)T * 8 * XS;
-    float2* raw = (float2*)(outb + (size_t)(NG * RP - 1) * 8 * XS);
-    float* scoef = (float*)(raw + (size_t)2 * T * SPAN);
+    // shared memory: outb [NG*RP][8][OS] float4 | plane [2][T][8][XS] float2 | coef [2][ncoef] float
+    // plane: sample s of the staged window at [s & 7][s >> 3] (filled directly by cp.async);
+    // outb: per antenna pair, output sample (8 t + i) at [i][t] for the coalesced stores.
+    float4* outb = (float4*)smem_raw;
+    float2* plane = (float2*)(outb + (size_t)NG * RP * 8 * OS);
+    float* scoef = (float*)(plane + (size_t)2 * T * 8 * XS);
     const int tid_all = threadIdx.x;
     const int tid = tid_all % TDL_THREADS;                   // sample-group index
     const int grp = tid_all / TDL_THREADS;                   // antenna group (warp-uniform)
 
     auto prefetch = [&](int b, int tin, int stage) {
-        float2* sr = raw + (size_t)stage * T * SPAN;
+        float2* sr = plane + (size_t)stage * T * 8 * XS;
         float* sc = scoef + (size_t)stage * ncoef;
         const int tile0 = tin * TILE;
         const bool interior = (tile0 >= HALO) && (tile0 + TILE <= n);
         for (int t = 0; t < T; ++t) {
             const float2* src = tx + ((size_t)b * T + t) * n + (tile0 - HALO);
-            float2* dst = sr + t * SPAN;
+            float2* dst = sr + t * 8 * XS;
             if (interior) {
 #pragma unroll
                 for (int i0 = 0; i0 < SPAN; i0 += NT) {
                     const int i = i0 + tid_all;
-                    if (i0 + NT <= SPAN || i < SPAN) cp_async8(&dst[i], &src[i]);
+                    if (i0 + NT <= SPAN || i < SPAN) cp_async8(&dst[(i & 7) * XS + (i >> 3)], &src[i]);
                 }
             } else {
                 for (int i = tid_all; i < SPAN; i += NT) {
                     const int m = tile0 - HALO + i;
                     const bool ok = (m >= 0 && m < n);
-                    cp_async8_zfill(&dst[i], ok ? &src[i] : tx, ok);
+                    cp_async8_zfill(&dst[(i & 7) * XS + (i >> 3)], ok ? &src[i] : tx, ok);
                 }
             }
         }
@@ -236,20 +237,7 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float* __rest
 
     for (; tile_id < tile_end; ++tile_id, stage ^= 1) {
         cp_async_wait<0>();
-        __syncthreads();                            // raw[stage] / coef[stage] landed; plane is free
-        // ---- raw (re, im) -> plane (re, re, im, im), transposed for conflict-free delayed reads ----
-        for (int t = 0; t < T; ++t) {
-            const float2* sr = raw + ((size_t)stage * T + t) * SPAN;
-            float4* pl = plane + (size_t)t * 8 * XS;
-#pragma unroll
-            for (int i0 = 0; i0 < SPAN; i0 += NT) {
-                const int i = i0 + tid_all;
-                if (i0 + NT <= SPAN || i < SPAN) {
-                    const float2 x = sr[i];
-                    pl[(i & 7) * XS + (i >> 3)] = make_float4(x.x, x.x, x.y, x.y);
-                }
-            }
-        }
+        __syncthreads();                            // plane[stage] / coef[stage] landed; outb and the other stage are free
         const bool last_tile_of_stream = (tin + 1 == tiles);
         const int nb = last_tile_of_stream ? b + 1 : b, ntin = last_tile_of_stream ? 0 : tin + 1;
         if (tile_id + 1 < tile_end) prefetch(nb, ntin, stage ^ 1);
@@ -271,12 +259,12 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float* __rest
             for (int i = 0; i < V; ++i) { are[p][i] = ppk(0.f, 0.f); aim[p][i] = ppk(0.f, 0.f); }
 
         for (int t = 0; t < T; ++t) {
-            const float4* plt = plane + (size_t)t * 8 * XS;
+            const float2* plt = plane + ((size_t)stage * T + t) * 8 * XS;
             for (int tap = 0; tap < (C.debug == 2 ? 1 : C.num_taps); ++tap) {
                 // per-tap offsets of the thread's 8 delayed samples in the transposed plane (uniform)
                 const int4 o0 = *(const int4*)&xoff[tap * 8], o1 = *(const int4*)&xoff[tap * 8 + 4];
-                const float4* base = plt + tid;
-                float4 xv[V];
+                const float2* base = plt + tid;
+                float2 xv[V];
                 xv[0] = base[o0.x]; xv[1] = base[o0.y]; xv[2] = base[o0.z]; xv[3] = base[o0.w];
                 xv[4] = base[o1.x]; xv[5] = base[o1.y]; xv[6] = base[o1.z]; xv[7] = base[o1.w];
                 const float* ct = sc + (size_t)(t * C.num_taps + tap) * NC * 2 * R2;
@@ -295,7 +283,8 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float* __rest
                     for (int i = 0; i < V; ++i) {
                         const float stf = (float)i - 0.5f * (V - 1);
                         const pf2 st = ppk(stf, stf);
-                        const pf2 xre = ppk(xv[i].x, xv[i].y), xim = ppk(xv[i].z, xv[i].w);
+                        // scalar sample broadcast to both antennas (FFMA2 takes a scalar .F32 operand)
+                        const pf2 xre = ppk(xv[i].x, xv[i].x), xim = ppk(xv[i].y, xv[i].y);
                         const pf2 hr = pfma(st, dre, hre), hi = pfma(st, dim, him), nhi = pfma(st, ndim, nhim);
                         pfma_acc(are[p][i], hr, xre);
                         pfma_acc(are[p][i], nhi, xim);
@@ -321,32 +310,29 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float* __rest
                     if (m0 + i < n) { pfma_acc(pw[p], are[p][i], are[p][i]); pfma_acc(pw[p], aim[p][i], aim[p][i]); }
             }
         }
-        __syncthreads();                            // every thread is done reading the sample plane
 #pragma unroll
         for (int p = 0; p < RP; ++p) {
-            const int qb = grp * RP + p;            // element (8 t + i) at [i][t]: (re_r0, re_r1, im_r0, im_r1)
-            float4* ob = qb == 0 ? plane : outb + (size_t)(qb - 1) * 8 * XS;
+            float4* ob = outb + (size_t)(grp * RP + p) * 8 * OS;    // (re_r0, re_r1, im_r0, im_r1) per sample
 #pragma unroll
             for (int i = 0; i < V; ++i) {
                 float a, c, d, e;
                 pupk(are[p][i], a, c);
                 pupk(aim[p][i], d, e);
-                ob[i * XS + tid] = make_float4(a, c, d, e);
+                ob[i * OS + tid] = make_float4(a, c, d, e);
             }
         }
         __syncthreads();
         if (C.debug != 1) {
 #pragma unroll
             for (int p = 0; p < RP; ++p) {
-                const int qb = grp * RP + p;
-                const float4* ob = qb == 0 ? plane : outb + (size_t)(qb - 1) * 8 * XS;
+                const float4* ob = outb + (size_t)(grp * RP + p) * 8 * OS;
                 const int r0 = grp * RG + 2 * p;
                 float2* d0 = faded + ((size_t)b * R + r0) * n + tile0;
                 float2* d1 = d0 + n;
 #pragma unroll
                 for (int k = 0; k < V / 2; ++k) {
                     const int s = 2 * (k * TDL_THREADS + tid);       // this lane's sample pair within the tile
-                    const float4 u = ob[(s & 7) * XS + (s >> 3)], w = ob[((s + 1) & 7) * XS + ((s + 1) >> 3)];
+                    const float4 u = ob[(s & 7) * OS + (s >> 3)], w = ob[((s + 1) & 7) * OS + ((s + 1) >> 3)];
                     if (tile0 + s + 2 <= n && vec) {
                         *(float4*)(d0 + s) = make_float4(u.x, u.z, w.x, w.z);
                         if (r0 + 1 < R) *(float4*)(d1 + s) = make_float4(u.y, u.w, w.y, w.w);
@@ -444,8 +430,9 @@ extern "C" int lte_channel_tdl(const lte_plan* p, const lte_channel_desc* ch, co
     const int NC = 2 * K + 1;
     const size_t ncoef = (size_t)nblk * T * C.num_taps * NC * 2 * R2;              // floats per tile
     const int span = halo + tile, xs = tdl_xs_stride(halo, tile);
-    const size_t smem = ((size_t)T * 8 * xs + (size_t)(R2 / 2 - 1) * 8 * xs) * sizeof(float4) +
-                        (size_t)2 * T * span * sizeof(float2) + 2 * ncoef * sizeof(float);
+    const size_t smem = (size_t)(R2 / 2) * 8 * tdl_os_stride(tile) * sizeof(float4) +
+                        (size_t)2 * T * 8 * xs * sizeof(float2) + 2 * ncoef * sizeof(float);
+    (void)span;
     if (smem > 200 * 1024) return LTE_ERR_UNSUPPORTED;
     const int tiles = (int)((n + tile - 1) / tile);
     const long long total_tiles_ll = (long long)tiles * B;
