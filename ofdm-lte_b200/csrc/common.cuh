@@ -24,6 +24,7 @@ struct DevPlan {
     int k0_useful, nk_useful;       // occupied-bin window
     const int16_t* bin_map;         // [N]
     const int16_t* data_idx;        // [Nd]
+    const int16_t* pilot_idx;       // [Np]
     const float2* pilots;           // [nsets][Np]  (zero where not owned)
     // per pilot set: owned pilots (bin, 1/p) and the left-neighbour table for interpolation
     const int16_t* pset_bin;        // [nsets][Np]

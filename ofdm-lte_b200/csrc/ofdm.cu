@@ -6,79 +6,94 @@
 // ------------------------------------------------------------------------------ TX
 // Replaces core/modulator.py:61-88 (bits_to_symbols), core/resource_mapper.py:181-223
 // (map_symbols) and core/modulator.py:242-248 (ifft * sqrt(N), CP prepend).
-// The grid synthesis and the CP / statistics epilogue are rolled loops that stage through the
-// pair's shared-memory buffer: the kernel stays inside the instruction cache (a fully unrolled
-// version measured 18 % "no instruction" stalls).
-template <int N>
-__global__ void __launch_bounds__(FFT_CTA_THREADS)
+// The grid of the symbol pair is built data-centrically in the pair's shared-memory buffer: one
+// pass over the Nd data symbols (coalesced index bytes -> level LUT -> bin data_idx[d]) and one
+// over the Np pilots; guards and DC stay zero.  Both symbols of the pair share the bin, so each
+// item is a single 128-bit store (re_A, re_B, im_A, im_B).
+template <int N, bool STATS, bool SYM>
+__global__ void __launch_bounds__(FFT_CTA_THREADS, 5)
 tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float2* __restrict__ symbols,
                    int T, float2* __restrict__ tx, float2* __restrict__ qam_out,
-                   double* __restrict__ stats, int S, long long total) {
+                   double* __restrict__ stats, int S, unsigned total) {
     constexpr int TPF = N / FFT_ELEMS, PPC = fft2_pairs_per_cta(N);
     extern __shared__ float4 smem4[];
     __shared__ float s_lev[8];
     if (threadIdx.x < 8) s_lev[threadIdx.x] = P.lev[threadIdx.x];
-    __syncthreads();
     const int p_local = threadIdx.x / TPF, j = threadIdx.x % TPF;
     float4* sbuf = smem4 + (size_t)p_local * fft_smem_elems(N);
-    const int idx_stride = (P.Nd + 15) & ~15;
-    uint8_t* idx_stage = (uint8_t*)(smem4 + (size_t)PPC * fft_smem_elems(N));   // [PPC][2][idx_stride]
-    const long long f0 = ((long long)blockIdx.x * PPC + p_local) * 2;   // OFDM symbol ids f0, f0+1 (= row*S + s)
+    const unsigned f0 = (blockIdx.x * PPC + p_local) * 2u;   // OFDM symbol ids f0, f0+1 (= row*S + s)
     const int h = P.bps >> 1, mask = (1 << h) - 1;
+    const int Nd = P.Nd;
 
     bool valid[2];
-    long long row[2];
-    int s_sym[2];
-    const float2* pil[2];
-    const float2* srow[2];
+    unsigned row[2], s_sym[2];
     size_t ibase[2];
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
-        const long long f = f0 + m;
+        const unsigned f = f0 + m;
         valid[m] = f < total;
-        row[m] = valid[m] ? f / S : 0;                 // row = b*T + t
-        s_sym[m] = valid[m] ? (int)(f - row[m] * S) : 0;
-        pil[m] = P.pilots + (size_t)(row[m] % T) * P.Np;
-        srow[m] = symbols ? symbols + ((size_t)row[m] * S + s_sym[m]) * P.Nd : nullptr;
-        ibase[m] = ((size_t)(row[m] / T) * S + s_sym[m]) * P.Nd;
+        row[m] = valid[m] ? f / (unsigned)S : 0u;      // row = b*T + t
+        s_sym[m] = valid[m] ? f - row[m] * (unsigned)S : 0u;
+        ibase[m] = SYM ? ((size_t)row[m] * S + s_sym[m]) * Nd
+                       : ((size_t)(row[m] / (unsigned)T) * S + s_sym[m]) * Nd;
     }
-    // Stage the two symbols' index bytes with independent coalesced loads (one 8-byte group per
-    // thread and symbol) so the grid synthesis below never waits on a bin_map -> idx load chain.
-    uint8_t* sidx = idx_stage + (size_t)p_local * 2 * idx_stride;
-    if (!symbols) {
+    // all of this thread's loads first (at most 16 data symbols per transform), then the stores
+    int16_t bin[FFT_ELEMS];
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            if (!valid[m]) continue;
-            const uint8_t* g = idx + ibase[m];
-            for (int c = j * 8; c < P.Nd; c += TPF * 8) {
+    for (int e = 0; e < FFT_ELEMS; ++e) {
+        const int d = j + e * TPF;
+        bin[e] = d < Nd ? P.data_idx[d] : (int16_t)-1;
+    }
+    if constexpr (SYM) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (c + q < P.Nd) sidx[m * idx_stride + c + q] = g[c + q];
+        for (int e = 0; e < FFT_ELEMS; ++e) sbuf[fft_pad(j + e * TPF)] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < FFT_ELEMS; ++e) {
+            const int d = j + e * TPF;
+            if (d < Nd) {
+                const float2 a = valid[0] ? symbols[ibase[0] + d] : make_float2(0.f, 0.f);
+                const float2 c = valid[1] ? symbols[ibase[1] + d] : make_float2(0.f, 0.f);
+                sbuf[fft_pad(bin[e])] = make_float4(a.x, c.x, a.y, c.y);
             }
         }
-        __syncthreads();
-    }
-#pragma unroll 4
-    for (int e = 0; e < FFT_ELEMS; ++e) {
-        const int kbin = j + e * TPF;
-        const int mm = P.bin_map[kbin];
-        float2 x[2];
+    } else {
+        uint8_t ib[2][FFT_ELEMS];
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            float2 val = make_float2(0.f, 0.f);
-            if (valid[m] && mm >= 0) {
-                if (mm & BIN_PILOT_FLAG) val = pil[m][mm & (BIN_PILOT_FLAG - 1)];
-                else if (srow[m]) val = srow[m][mm];
-                else {
-                    const int i = sidx[m * idx_stride + mm];
-                    val = make_float2(s_lev[(i >> h) & mask], s_lev[i & mask]);
-                    if (qam_out) qam_out[ibase[m] + mm] = val;
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int e = 0; e < FFT_ELEMS; ++e) {
+                const int d = j + e * TPF;
+                ib[m][e] = (valid[m] && d < Nd) ? idx[ibase[m] + d] : (uint8_t)0;
+            }
+#pragma unroll
+        for (int e = 0; e < FFT_ELEMS; ++e) sbuf[fft_pad(j + e * TPF)] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < FFT_ELEMS; ++e) {
+            const int d = j + e * TPF;
+            if (d < Nd) {
+                const int ia = ib[0][e], ic = ib[1][e];
+                const float2 a = valid[0] ? make_float2(s_lev[(ia >> h) & mask], s_lev[ia & mask]) : make_float2(0.f, 0.f);
+                const float2 c = valid[1] ? make_float2(s_lev[(ic >> h) & mask], s_lev[ic & mask]) : make_float2(0.f, 0.f);
+                sbuf[fft_pad(bin[e])] = make_float4(a.x, c.x, a.y, c.y);
+                if (qam_out) {
+                    if (valid[0]) qam_out[ibase[0] + d] = a;
+                    if (valid[1]) qam_out[ibase[1] + d] = c;
                 }
             }
-            x[m] = val;
         }
-        sbuf[fft_pad(kbin)] = make_float4(x[0].x, x[1].x, x[0].y, x[1].y);   // read back by this thread only
     }
+    {
+        const float2* pa = P.pilots + (size_t)(row[0] % (unsigned)T) * P.Np;
+        const float2* pc = P.pilots + (size_t)(row[1] % (unsigned)T) * P.Np;
+        for (int q = j; q < P.Np; q += TPF) {
+            const float2 a = valid[0] ? pa[q] : make_float2(0.f, 0.f);
+            const float2 c = valid[1] ? pc[q] : make_float2(0.f, 0.f);
+            sbuf[fft_pad(P.pilot_idx[q])] = make_float4(a.x, c.x, a.y, c.y);
+        }
+    }
+    __syncthreads();
     c2 v[FFT_ELEMS];
 #pragma unroll
     for (int e = 0; e < FFT_ELEMS; ++e) {
@@ -89,37 +104,33 @@ tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float
 
     fft2_run<N, true>(v, sbuf, P.twiddle, j);
 
-    __syncthreads();          // all exchange reads are done
     const f2 scale = pk(P.inv_sqrt_n, P.inv_sqrt_n);
-#pragma unroll
-    for (int e = 0; e < FFT_ELEMS; ++e) {
-        float a, b, c, d;
-        upk(mul2(v[e].re, scale), a, b);
-        upk(mul2(v[e].im, scale), c, d);
-        sbuf[fft_pad(j + e * TPF)] = make_float4(a, b, c, d);
-    }
     float pmax[2] = {0.f, 0.f}, psum[2] = {0.f, 0.f};
     const int tail0 = N - P.cp;
     float2* o[2];
 #pragma unroll
-    for (int m = 0; m < 2; ++m) o[m] = tx + (size_t)row[m] * S * P.L + (size_t)s_sym[m] * P.L;
-#pragma unroll 2
+    for (int m = 0; m < 2; ++m) o[m] = tx + (size_t)row[m] * S * P.L + (size_t)s_sym[m] * P.L + P.cp;
+#pragma unroll
     for (int e = 0; e < FFT_ELEMS; ++e) {
         const int n = j + e * TPF;
-        const float4 q = sbuf[fft_pad(n)];
-        const float2 xo[2] = {make_float2(q.x, q.z), make_float2(q.y, q.w)};
+        float re[2], im[2];
+        upk(mul2(v[e].re, scale), re[0], re[1]);
+        upk(mul2(v[e].im, scale), im[0], im[1]);
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
             if (valid[m]) {
-                o[m][P.cp + n] = xo[m];
-                const float pw = cabs2(xo[m]);
-                pmax[m] = fmaxf(pmax[m], pw);
-                psum[m] += pw;
-                if (n >= tail0) { o[m][n - tail0] = xo[m]; psum[m] += pw; }
+                const float2 xo = make_float2(re[m], im[m]);
+                o[m][n] = xo;
+                if (n >= tail0) o[m][n - N] = xo;         // cyclic prefix: last cp samples again in front
+                if (STATS) {
+                    const float pw = cabs2(xo);
+                    pmax[m] = fmaxf(pmax[m], pw);
+                    psum[m] += (n >= tail0) ? 2.f * pw : pw;
+                }
             }
         }
     }
-    if (stats) {
+    if (STATS) {
         // per-stream peak and total power including the CP (core/ofdm_core.py:131-133)
         __shared__ float red[2][2][FFT_CTA_THREADS / 32];
 #pragma unroll
@@ -289,17 +300,21 @@ extern "C" int lte_tx_map_ifft(const lte_plan* p, const uint8_t* idx, const lte_
     if (!p || (!idx && !symbols) || !tx || B < 0 || S < 1 || T < 1 || T > LTE_MAX_TX) return LTE_ERR_INVALID_ARG;
     if (B == 0) return LTE_OK;
     const long long total = (long long)B * T * S;
+    if (total >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
     return dispatch_n(p->dev.N, [&](auto n) -> int {
         constexpr int N = decltype(n)::value;
-        auto k = tx_map_ifft_kernel<N>;
-        const int smem = fft2_cta_smem_bytes(N) + fft2_pairs_per_cta(N) * 2 * ((p->dev.Nd + 15) & ~15);
-        LTE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int smem = fft2_cta_smem_bytes(N);
         const long long per = 2 * fft2_pairs_per_cta(N);
         const long long grid = (total + per - 1) / per;
-        k<<<(unsigned)grid, FFT_CTA_THREADS, smem, (cudaStream_t)stream>>>(
-            p->dev, idx, (const float2*)symbols, T, (float2*)tx, (float2*)qam_out, stats, S, total);
-        LTE_CHECK_CUDA(cudaGetLastError());
-        return LTE_OK;
+        auto launch = [&](auto k) -> int {
+            LTE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            k<<<(unsigned)grid, FFT_CTA_THREADS, smem, (cudaStream_t)stream>>>(
+                p->dev, idx, (const float2*)symbols, T, (float2*)tx, (float2*)qam_out, stats, S, (unsigned)total);
+            LTE_CHECK_CUDA(cudaGetLastError());
+            return LTE_OK;
+        };
+        if (symbols) return stats ? launch(tx_map_ifft_kernel<N, true, true>) : launch(tx_map_ifft_kernel<N, false, true>);
+        return stats ? launch(tx_map_ifft_kernel<N, true, false>) : launch(tx_map_ifft_kernel<N, false, false>);
     });
 }
 

@@ -118,7 +118,8 @@ extern "C" int lte_plan_create(const lte_plan_desc* d, const lte_c32* pilots_hos
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t off_bin = 0;
     size_t off_didx = align(off_bin + sizeof(int16_t) * N);
-    size_t off_pil = align(off_didx + sizeof(int16_t) * (Nd ? Nd : 1));
+    size_t off_pidx = align(off_didx + sizeof(int16_t) * (Nd ? Nd : 1));
+    size_t off_pil = align(off_pidx + sizeof(int16_t) * (Np ? Np : 1));
     size_t off_pbin = align(off_pil + sizeof(float2) * pilots.size());
     size_t off_pinv = align(off_pbin + sizeof(int16_t) * pset_bin.size());
     size_t off_pseg = align(off_pinv + sizeof(float2) * pset_inv.size());
@@ -130,6 +131,9 @@ extern "C" int lte_plan_create(const lte_plan_desc* d, const lte_c32* pilots_hos
     for (int i = 0; i < Nd; ++i) didx16[i] = (int16_t)p->data_idx_h[i];
     memcpy(&host[off_bin], bin_map.data(), sizeof(int16_t) * N);
     memcpy(&host[off_didx], didx16.data(), sizeof(int16_t) * didx16.size());
+    std::vector<int16_t> pidx16(Np ? Np : 1, 0);
+    for (int i = 0; i < Np; ++i) pidx16[i] = (int16_t)p->pilot_idx_h[i];
+    memcpy(&host[off_pidx], pidx16.data(), sizeof(int16_t) * pidx16.size());
     memcpy(&host[off_pil], pilots.data(), sizeof(float2) * pilots.size());
     memcpy(&host[off_pbin], pset_bin.data(), sizeof(int16_t) * pset_bin.size());
     memcpy(&host[off_pinv], pset_inv.data(), sizeof(float2) * pset_inv.size());
@@ -150,6 +154,7 @@ extern "C" int lte_plan_create(const lte_plan_desc* d, const lte_c32* pilots_hos
     D.k0_useful = k0; D.nk_useful = nk;
     D.bin_map = (const int16_t*)(b + off_bin);
     D.data_idx = (const int16_t*)(b + off_didx);
+    D.pilot_idx = (const int16_t*)(b + off_pidx);
     D.pilots = (const float2*)(b + off_pil);
     D.pset_bin = (const int16_t*)(b + off_pbin);
     D.pset_inv = (const float2*)(b + off_pinv);
