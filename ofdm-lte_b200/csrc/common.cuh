@@ -107,7 +107,7 @@ __device__ __forceinline__ float2 lte_noise_sample(uint32_t key, uint32_t row, u
     uint32_t r0, r1;
     philox2x32_10(key, sample, row, r0, r1);
     const float u1 = fmaf((float)r0, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-    const float ang = fmaf((float)r1, 2.3283064365386963e-10f, -0.5f);      // [-0.5, 0.5] turns
+    const float ang = __uint_as_float(0x3f800000u | (r1 >> 9)) - 1.5f;      // [-0.5, 0.5) turns, 23 bits
     float rad;                                                              // sqrt(-2 ln u1)
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * __log2f(u1)));
     float s, c;

@@ -25,18 +25,23 @@ tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float
     const int h = P.bps >> 1, mask = (1 << h) - 1;
     const int Nd = P.Nd;
 
-    bool valid[2];
+    // symbol ids f0, f0+1 -> (row, symbol); one division, the second symbol follows the first
+    const bool valid[2] = {f0 < total, f0 + 1 < total};
     unsigned row[2], s_sym[2];
     size_t ibase[2];
+    row[0] = valid[0] ? f0 / (unsigned)S : 0u;      // row = b*T + t
+    s_sym[0] = valid[0] ? f0 - row[0] * (unsigned)S : 0u;
+    const bool wrap = s_sym[0] + 1 == (unsigned)S;
+    row[1] = valid[1] ? (wrap ? row[0] + 1 : row[0]) : 0u;
+    s_sym[1] = valid[1] ? (wrap ? 0u : s_sym[0] + 1) : 0u;
+    unsigned tq[2], tr[2];                          // row / T, row % T
+    tq[0] = T == 1 ? row[0] : row[0] / (unsigned)T;
+    tr[0] = row[0] - tq[0] * (unsigned)T;
+    tq[1] = row[1] == row[0] ? tq[0] : (T == 1 ? row[1] : row[1] / (unsigned)T);
+    tr[1] = row[1] - tq[1] * (unsigned)T;
 #pragma unroll
-    for (int m = 0; m < 2; ++m) {
-        const unsigned f = f0 + m;
-        valid[m] = f < total;
-        row[m] = valid[m] ? f / (unsigned)S : 0u;      // row = b*T + t
-        s_sym[m] = valid[m] ? f - row[m] * (unsigned)S : 0u;
-        ibase[m] = SYM ? ((size_t)row[m] * S + s_sym[m]) * Nd
-                       : ((size_t)(row[m] / (unsigned)T) * S + s_sym[m]) * Nd;
-    }
+    for (int m = 0; m < 2; ++m)
+        ibase[m] = SYM ? ((size_t)row[m] * S + s_sym[m]) * Nd : ((size_t)tq[m] * S + s_sym[m]) * Nd;
     // all of this thread's loads first (at most 16 data symbols per transform), then the stores
     int16_t bin[FFT_ELEMS];
 #pragma unroll
@@ -85,8 +90,8 @@ tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float
         }
     }
     {
-        const float2* pa = P.pilots + (size_t)(row[0] % (unsigned)T) * P.Np;
-        const float2* pc = P.pilots + (size_t)(row[1] % (unsigned)T) * P.Np;
+        const float2* pa = P.pilots + (size_t)tr[0] * P.Np;
+        const float2* pc = P.pilots + (size_t)tr[1] * P.Np;
         for (int q = j; q < P.Np; q += TPF) {
             const float2 a = valid[0] ? pa[q] : make_float2(0.f, 0.f);
             const float2 c = valid[1] ? pc[q] : make_float2(0.f, 0.f);
@@ -184,33 +189,38 @@ template <int N, int NOISE>
 __global__ void __launch_bounds__(FFT_CTA_THREADS)
 rx_fft_kernel(const DevPlan P, const float2* __restrict__ rx, int rx_div, const double* __restrict__ power,
               const float* __restrict__ snr_lin, const float2* __restrict__ z, uint32_t key,
-              unsigned long long row_id0, float2* __restrict__ Y, int k0, int nk, int S, long long total) {
+              unsigned long long row_id0, float2* __restrict__ Y, int k0, int nk, int S, unsigned total) {
     constexpr int TPF = N / FFT_ELEMS, PPC = fft2_pairs_per_cta(N);
     extern __shared__ float4 smem4[];
+    __shared__ float s_sigma[PPC][2];
     const int p_local = threadIdx.x / TPF, j = threadIdx.x % TPF;
     float4* sbuf = smem4 + (size_t)p_local * fft_smem_elems(N);
-    const long long f0 = ((long long)blockIdx.x * PPC + p_local) * 2;
+    const unsigned f0 = (blockIdx.x * PPC + p_local) * 2u;
     const size_t n_stream = (size_t)S * P.L;
 
-    bool valid[2];
-    long long row[2];
-    int s_sym[2];
-    float sigma[2] = {0.f, 0.f};
+    // symbol ids f0, f0+1 -> (row, symbol); one division, the second symbol follows the first
+    bool valid[2] = {f0 < total, f0 + 1 < total};
+    unsigned row[2], s_sym[2];
+    row[0] = valid[0] ? f0 / (unsigned)S : 0u;
+    s_sym[0] = valid[0] ? f0 - row[0] * (unsigned)S : 0u;
+    const bool wrap = s_sym[0] + 1 == (unsigned)S;
+    row[1] = valid[1] ? (wrap ? row[0] + 1 : row[0]) : 0u;
+    s_sym[1] = valid[1] ? (wrap ? 0u : s_sym[0] + 1) : 0u;
     uint32_t rid[2];
     const float2* src[2];
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
-        const long long f = f0 + m;
-        valid[m] = f < total;
-        row[m] = valid[m] ? f / S : 0;
-        s_sym[m] = valid[m] ? (int)(f - row[m] * S) : 0;
-        src[m] = rx + (size_t)(row[m] / rx_div) * n_stream + (size_t)s_sym[m] * P.L + P.cp;
+        const unsigned srow = rx_div == 1 ? row[m] : row[m] / (unsigned)rx_div;
+        src[m] = rx + (size_t)srow * n_stream + (size_t)s_sym[m] * P.L + P.cp;
         rid[m] = (uint32_t)(row_id0 + (unsigned long long)row[m]);
-        if (NOISE != 0 && valid[m]) sigma[m] = lte_sigma(power[row[m]], (float)n_stream, snr_lin[row[m]]);
     }
+    if (NOISE != 0 && j < 2)       // one thread per symbol turns the stream power into sigma
+        s_sigma[p_local][j] = valid[j] ? lte_sigma(power[row[j]], (float)n_stream, snr_lin[row[j]]) : 0.f;
 
     c2 v[FFT_ELEMS];
     if constexpr (NOISE == 1) {
+        __syncthreads();
+        const float sigma[2] = {s_sigma[p_local][0], s_sigma[p_local][1]};
 #pragma unroll 2
         for (int e = 0; e < FFT_ELEMS; ++e) {
             const int n = j + e * TPF;
@@ -257,6 +267,8 @@ rx_fft_kernel(const DevPlan P, const float2* __restrict__ rx, int rx_div, const 
     float2* o[2];
 #pragma unroll
     for (int m = 0; m < 2; ++m) o[m] = Y + ((size_t)row[m] * S + s_sym[m]) * nk;
+    float sigma[2] = {0.f, 0.f};
+    if (NOISE == 2) { sigma[0] = s_sigma[p_local][0]; sigma[1] = s_sigma[p_local][1]; }
 #pragma unroll 2
     for (int e = 0; e < FFT_ELEMS; ++e) {
         const int kb = j + e * TPF;
@@ -330,6 +342,7 @@ extern "C" int lte_rx_fft(const lte_plan* p, const lte_c32* rx, int32_t rx_div, 
     if (rc) return rc;
     if (rows == 0) return LTE_OK;
     const long long total = (long long)rows * S;
+    if (total >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
     const uint32_t key = lte_key(seed, LTE_DOMAIN_NOISE);
     return dispatch_n(p->dev.N, [&](auto n) -> int {
         constexpr int N = decltype(n)::value;
@@ -340,7 +353,7 @@ extern "C" int lte_rx_fft(const lte_plan* p, const lte_c32* rx, int32_t rx_div, 
             LTE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             k<<<(unsigned)grid, FFT_CTA_THREADS, smem, (cudaStream_t)stream>>>(
                 p->dev, (const float2*)rx, rx_div, power, snr_lin, (const float2*)z, key, row_id0, (float2*)Y, k0,
-                nk, S, total);
+                nk, S, (unsigned)total);
             LTE_CHECK_CUDA(cudaGetLastError());
             return LTE_OK;
         };
