@@ -102,6 +102,10 @@ int lte_bits_to_indices(const lte_plan*, const uint8_t* bits, int64_t nbits, uin
 int lte_indices_to_bits(const lte_plan*, const uint8_t* idx, int64_t nsym, uint8_t* bits,
                         int64_t nbits, int32_t B, void* stream);
 
+/* constellation[idx] alone (QAMModulator.bits_to_symbols, core/modulator.py:84-86): the input of
+ * the SC-FDM precoder.  idx, symbols: n elements. */
+int lte_qam_map(const lte_plan*, const uint8_t* idx, lte_c32* symbols, int64_t n, void* stream);
+
 /* --- stage 1+2 TX: QAM map + resource grid + IFFT*sqrt(N) + CP -------------------
  * replaces QAMModulator.bits_to_symbols (core/modulator.py:61-88),
  * ResourceMapper.map_symbols (core/resource_mapper.py:181-223) and
@@ -114,6 +118,26 @@ int lte_indices_to_bits(const lte_plan*, const uint8_t* idx, int64_t nsym, uint8
 int lte_tx_map_ifft(const lte_plan*, const uint8_t* idx, const lte_c32* symbols, int32_t T,
                     lte_c32* tx, lte_c32* qam_out, double* stats, int32_t B, int32_t S,
                     void* stream);
+
+/* --- PAPR / CCDF engine ------------------------------------------------------
+ * lte_tx_papr: lte_tx_map_ifft with a per-OFDM-symbol PAPR epilogue over the N useful samples
+ * (no CP), replacing OFDMSystem.calculate_papr_without_cp (core/ofdm_system.py:173-229) and the
+ * collection loop of collect_papr_for_all_modulations (:648-735).  tx may be NULL: the
+ * time-domain stream is then never written (sweep mode).  Outputs, each optional (at least one):
+ * papr_db [B*T][S] = 10 log10(peak/mean) (0 for an all-zero symbol); peak_mean [B*T][S][2]
+ * floats; hist [hist_bins] counts of papr_db in bins of width hist_step from hist_lo (values
+ * outside fall into the first / last bin), accumulated with atomics, caller zeroes.
+ * lte_papr_symbols: the same outputs for an existing stream x [rows][S*L]; include_cp != 0
+ * takes all L samples of a symbol (OFDMSystem.calculate_papr_per_symbol, :116-171).
+ * lte_histogram: histogram of any float array with the same bin rule. */
+int lte_tx_papr(const lte_plan*, const uint8_t* idx, const lte_c32* symbols, int32_t T, lte_c32* tx,
+                double* stats, float* papr_db, float* peak_mean, unsigned long long* hist,
+                float hist_lo, float hist_step, int32_t hist_bins, int32_t B, int32_t S, void* stream);
+int lte_papr_symbols(const lte_plan*, const lte_c32* x, int32_t include_cp, float* papr_db,
+                     float* peak_mean, unsigned long long* hist, float hist_lo, float hist_step,
+                     int32_t hist_bins, int64_t rows, int32_t S, void* stream);
+int lte_histogram(const float* x, int64_t n, float lo, float step, int32_t bins,
+                  unsigned long long* hist, void* stream);
 
 /* --- SC-FDM M-point unitary DFT / IDFT ------------------------------------------------
  * replaces DFTPrecodifier.precoding / IDFTDecodifier.decoding and the SC_FDMPrecodifier /

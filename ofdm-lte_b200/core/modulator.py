@@ -97,7 +97,7 @@ class OFDMModulator:
         S = eng.symbols_for_bits(nbits) if num_ofdm_symbols is None else int(num_ofdm_symbols)
         idx = eng.bits_to_indices(bits_t, nbits, S)
         if self.enable_sc_fdm and self.sc_fdm_precoder is not None:
-            _, qam, _ = eng.modulate(S, idx=idx, want_qam=True, want_stats=False)
+            qam = eng.qam_map(idx)
             pre = eng.dft_m(qam.reshape(S, eng.Nd), eng.Nd)
             tx, _, stats = eng.modulate(S, symbols=pre.reshape(1, -1))
         else:
@@ -134,3 +134,13 @@ class OFDMModulator:
         return be.to_numpy(tx.reshape(-1)), [qam_np[s] for s in range(S)], infos
 
     modulate_stream_vectorized = modulate_stream
+
+    def set_sc_fdm_enabled(self, enable):
+        """Switch the DFT precoder on/off (reference :405-416)."""
+        self.enable_sc_fdm = enable
+        self.mode = 'sc-fdm' if enable else 'lte'
+        if self.sc_fdm_precoder is not None:
+            self.sc_fdm_precoder.set_enable(enable)
+
+    def get_qam_modulator(self):
+        return self.qam_modulator

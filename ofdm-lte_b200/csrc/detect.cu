@@ -66,6 +66,23 @@ extern "C" int lte_indices_to_bits(const lte_plan* p, const uint8_t* idx, int64_
     return LTE_OK;
 }
 
+// core/modulator.py:84-86: constellation[idx], without the grid / IFFT (SC-FDM precoder input)
+__global__ void qam_map_kernel(const DevPlan P, const uint8_t* __restrict__ idx, float2* __restrict__ out, long long n) {
+    const int h = P.bps >> 1, mask = (1 << h) - 1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int v = idx[i];
+        out[i] = make_float2(P.lev[(v >> h) & mask], P.lev[v & mask]);
+    }
+}
+
+extern "C" int lte_qam_map(const lte_plan* p, const uint8_t* idx, lte_c32* symbols, int64_t n, void* stream) {
+    if (!p || !idx || !symbols || n < 0) return LTE_ERR_INVALID_ARG;
+    if (n == 0) return LTE_OK;
+    qam_map_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p->dev, idx, (float2*)symbols, n);
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}
+
 // ------------------------------------------------------------------------------ stage 4
 // core/lte_receiver.py:62-87 (LS at the pilots) and :98-133 (edge hold + np.linspace).
 // One CTA per (row, slot); the estimate comes from the slot's first symbol (:380-406).

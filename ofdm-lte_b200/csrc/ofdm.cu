@@ -10,11 +10,66 @@
 // pass over the Nd data symbols (coalesced index bytes -> level LUT -> bin data_idx[d]) and one
 // over the Np pilots; guards and DC stay zero.  Both symbols of the pair share the bin, so each
 // item is a single 128-bit store (re_A, re_B, im_A, im_B).
-template <int N, bool STATS, bool SYM>
+struct PaprOut {                       // per-symbol PAPR outputs of the TX kernel (all optional)
+    float* papr_db;                    // [rows*S]
+    float2* peak_mean;                 // [rows*S] (peak, mean) power of the N useful samples
+    unsigned long long* hist;          // [bins] counts of papr_db
+    float lo, inv_step;
+    int bins;
+};
+
+__device__ __forceinline__ void papr_emit(const PaprOut& po, size_t f, float peak, float sum, int n) {
+    const float mean = sum / (float)n;
+    // core/ofdm_system.py:212-217: 10 log10(peak / mean), 0 when the symbol is all-zero
+    const float db = mean > 0.f ? 10.f * log10f(peak / mean) : 0.f;
+    if (po.papr_db) po.papr_db[f] = db;
+    if (po.peak_mean) po.peak_mean[f] = make_float2(peak, mean);
+    if (po.hist) {
+        int bin = (int)floorf((db - po.lo) * po.inv_step);
+        bin = min(max(bin, 0), po.bins - 1);
+        atomicAdd(&po.hist[bin], 1ull);
+    }
+}
+
+// (max, sum) over the TPF threads of each transform pair, for both transforms of the pair
+template <int TPF>
+__device__ __forceinline__ void pair_reduce(float (&pmax)[2], float (&psum)[2], float (*red)[2][FFT_CTA_THREADS / 32]) {
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        float mx = pmax[m], sm = psum[m];
+        if constexpr (TPF >= 32) {
+            mx = warp_max(mx);
+            sm = warp_sum(sm);
+            const int w = threadIdx.x >> 5;
+            if ((threadIdx.x & 31) == 0) { red[m][0][w] = mx; red[m][1][w] = sm; }
+        } else {
+#pragma unroll
+            for (int ofs = TPF / 2; ofs > 0; ofs >>= 1) {
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, ofs));
+                sm += __shfl_xor_sync(0xffffffffu, sm, ofs);
+            }
+        }
+        pmax[m] = mx;
+        psum[m] = sm;
+    }
+    if constexpr (TPF >= 32) {
+        __syncthreads();
+        const int w = threadIdx.x >> 5;          // only the first warp of a pair ends up with the totals
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int q = 1; q < TPF / 32; ++q) {
+                pmax[m] = fmaxf(pmax[m], red[m][0][(w + q) % (FFT_CTA_THREADS / 32)]);
+                psum[m] += red[m][1][(w + q) % (FFT_CTA_THREADS / 32)];
+            }
+    }
+}
+
+template <int N, bool STATS, bool SYM, bool PAPR>
 __global__ void __launch_bounds__(FFT_CTA_THREADS, 5)
 tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float2* __restrict__ symbols,
                    int T, float2* __restrict__ tx, float2* __restrict__ qam_out,
-                   double* __restrict__ stats, int S, unsigned total) {
+                   double* __restrict__ stats, const PaprOut po, int S, unsigned total) {
     constexpr int TPF = N / FFT_ELEMS, PPC = fft2_pairs_per_cta(N);
     extern __shared__ float4 smem4[];
     __shared__ float s_lev[8];
@@ -110,11 +165,13 @@ tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float
     fft2_run<N, true>(v, sbuf, P.twiddle, j);
 
     const f2 scale = pk(P.inv_sqrt_n, P.inv_sqrt_n);
-    float pmax[2] = {0.f, 0.f}, psum[2] = {0.f, 0.f};
+    float pmax[2] = {0.f, 0.f}, psum[2] = {0.f, 0.f};       // stream statistics (CP counted)
+    float qmax[2] = {0.f, 0.f}, qsum[2] = {0.f, 0.f};       // per-symbol statistics (useful part only)
     const int tail0 = N - P.cp;
     float2* o[2];
 #pragma unroll
     for (int m = 0; m < 2; ++m) o[m] = tx + (size_t)row[m] * S * P.L + (size_t)s_sym[m] * P.L + P.cp;
+    const bool write = !PAPR || tx != nullptr;
 #pragma unroll
     for (int e = 0; e < FFT_ELEMS; ++e) {
         const int n = j + e * TPF;
@@ -125,48 +182,28 @@ tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float
         for (int m = 0; m < 2; ++m) {
             if (valid[m]) {
                 const float2 xo = make_float2(re[m], im[m]);
-                o[m][n] = xo;
-                if (n >= tail0) o[m][n - N] = xo;         // cyclic prefix: last cp samples again in front
-                if (STATS) {
+                if (write) {
+                    o[m][n] = xo;
+                    if (n >= tail0) o[m][n - N] = xo;     // cyclic prefix: last cp samples again in front
+                }
+                if (STATS || PAPR) {
                     const float pw = cabs2(xo);
-                    pmax[m] = fmaxf(pmax[m], pw);
-                    psum[m] += (n >= tail0) ? 2.f * pw : pw;
+                    if (STATS) {
+                        pmax[m] = fmaxf(pmax[m], pw);
+                        psum[m] += (n >= tail0) ? 2.f * pw : pw;
+                    }
+                    if (PAPR) {
+                        qmax[m] = fmaxf(qmax[m], pw);
+                        qsum[m] += pw;
+                    }
                 }
             }
         }
     }
+    __shared__ float red[2][2][FFT_CTA_THREADS / 32];
     if (STATS) {
         // per-stream peak and total power including the CP (core/ofdm_core.py:131-133)
-        __shared__ float red[2][2][FFT_CTA_THREADS / 32];
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            float mx = pmax[m], sm = psum[m];
-            if constexpr (TPF >= 32) {
-                mx = warp_max(mx);
-                sm = warp_sum(sm);
-                const int w = threadIdx.x >> 5;
-                if ((threadIdx.x & 31) == 0) { red[m][0][w] = mx; red[m][1][w] = sm; }
-            } else {
-#pragma unroll
-                for (int ofs = TPF / 2; ofs > 0; ofs >>= 1) {
-                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, ofs));
-                    sm += __shfl_xor_sync(0xffffffffu, sm, ofs);
-                }
-            }
-            pmax[m] = mx;
-            psum[m] = sm;
-        }
-        if constexpr (TPF >= 32) {
-            __syncthreads();
-            const int w = threadIdx.x >> 5;
-#pragma unroll
-            for (int m = 0; m < 2; ++m)
-#pragma unroll
-                for (int q = 1; q < TPF / 32; ++q) {
-                    pmax[m] = fmaxf(pmax[m], red[m][0][w + q]);
-                    psum[m] += red[m][1][w + q];
-                }
-        }
+        pair_reduce<TPF>(pmax, psum, red);
         if (j == 0) {
 #pragma unroll
             for (int m = 0; m < 2; ++m)
@@ -177,6 +214,51 @@ tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float
                 }
         }
     }
+    if (PAPR) {
+        // per-symbol PAPR of the useful part (core/ofdm_system.py:173-229)
+        if (STATS) __syncthreads();
+        pair_reduce<TPF>(qmax, qsum, red);
+        if (j == 0) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+                if (valid[m]) papr_emit(po, (size_t)row[m] * S + s_sym[m], qmax[m], qsum[m], N);
+        }
+    }
+}
+
+// Per-symbol PAPR of an existing time-domain stream (core/ofdm_system.py:116-171 with the CP,
+// :173-229 without); one warp per OFDM symbol.
+__global__ void papr_symbols_kernel(const DevPlan P, const float2* __restrict__ x, int include_cp, const PaprOut po,
+                                    long long total) {
+    const long long f = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (f >= total) return;
+    const int lane = threadIdx.x & 31;
+    const int n0 = include_cp ? 0 : P.cp, cnt = include_cp ? P.L : P.N;
+    const float2* src = x + (size_t)f * P.L + n0;
+    float mx = 0.f, sm = 0.f;
+    for (int i = lane; i < cnt; i += 32) {
+        const float pw = cabs2(src[i]);
+        mx = fmaxf(mx, pw);
+        sm += pw;
+    }
+    mx = warp_max(mx);
+    sm = warp_sum(sm);
+    if (lane == 0) papr_emit(po, (size_t)f, mx, sm, cnt);
+}
+
+__global__ void histogram_kernel(const float* __restrict__ x, long long n, float lo, float inv_step, int bins,
+                                 unsigned long long* __restrict__ hist) {
+    extern __shared__ unsigned int sh[];
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int bin = (int)floorf((x[i] - lo) * inv_step);
+        bin = min(max(bin, 0), bins - 1);
+        atomicAdd(&sh[bin], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < bins; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
 }
 
 // ------------------------------------------------------------------------------ RX
@@ -306,13 +388,12 @@ template <typename F> static int dispatch_n(int N, F&& f) {
     }
 }
 
-extern "C" int lte_tx_map_ifft(const lte_plan* p, const uint8_t* idx, const lte_c32* symbols, int32_t T,
-                               lte_c32* tx, lte_c32* qam_out, double* stats, int32_t B, int32_t S,
-                               void* stream) {
-    if (!p || (!idx && !symbols) || !tx || B < 0 || S < 1 || T < 1 || T > LTE_MAX_TX) return LTE_ERR_INVALID_ARG;
+static int launch_tx(const lte_plan* p, const uint8_t* idx, const lte_c32* symbols, int32_t T, lte_c32* tx,
+                     lte_c32* qam_out, double* stats, const PaprOut* po, int32_t B, int32_t S, void* stream) {
     if (B == 0) return LTE_OK;
     const long long total = (long long)B * T * S;
     if (total >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
+    const PaprOut none = {nullptr, nullptr, nullptr, 0.f, 1.f, 1};
     return dispatch_n(p->dev.N, [&](auto n) -> int {
         constexpr int N = decltype(n)::value;
         const int smem = fft2_cta_smem_bytes(N);
@@ -321,13 +402,75 @@ extern "C" int lte_tx_map_ifft(const lte_plan* p, const uint8_t* idx, const lte_
         auto launch = [&](auto k) -> int {
             LTE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             k<<<(unsigned)grid, FFT_CTA_THREADS, smem, (cudaStream_t)stream>>>(
-                p->dev, idx, (const float2*)symbols, T, (float2*)tx, (float2*)qam_out, stats, S, (unsigned)total);
+                p->dev, idx, (const float2*)symbols, T, (float2*)tx, (float2*)qam_out, stats, po ? *po : none, S,
+                (unsigned)total);
             LTE_CHECK_CUDA(cudaGetLastError());
             return LTE_OK;
         };
-        if (symbols) return stats ? launch(tx_map_ifft_kernel<N, true, true>) : launch(tx_map_ifft_kernel<N, false, true>);
-        return stats ? launch(tx_map_ifft_kernel<N, true, false>) : launch(tx_map_ifft_kernel<N, false, false>);
+        if (po) {
+            if (symbols) return stats ? launch(tx_map_ifft_kernel<N, true, true, true>) : launch(tx_map_ifft_kernel<N, false, true, true>);
+            return stats ? launch(tx_map_ifft_kernel<N, true, false, true>) : launch(tx_map_ifft_kernel<N, false, false, true>);
+        }
+        if (symbols) return stats ? launch(tx_map_ifft_kernel<N, true, true, false>) : launch(tx_map_ifft_kernel<N, false, true, false>);
+        return stats ? launch(tx_map_ifft_kernel<N, true, false, false>) : launch(tx_map_ifft_kernel<N, false, false, false>);
     });
+}
+
+extern "C" int lte_tx_map_ifft(const lte_plan* p, const uint8_t* idx, const lte_c32* symbols, int32_t T,
+                               lte_c32* tx, lte_c32* qam_out, double* stats, int32_t B, int32_t S,
+                               void* stream) {
+    if (!p || (!idx && !symbols) || !tx || B < 0 || S < 1 || T < 1 || T > LTE_MAX_TX) return LTE_ERR_INVALID_ARG;
+    return launch_tx(p, idx, symbols, T, tx, qam_out, stats, nullptr, B, S, stream);
+}
+
+static int make_papr_out(PaprOut& po, float* papr_db, float* peak_mean, unsigned long long* hist, float hist_lo,
+                         float hist_step, int32_t hist_bins) {
+    if (hist && (hist_bins < 1 || !(hist_step > 0.f))) return LTE_ERR_INVALID_ARG;
+    po = {papr_db, (float2*)peak_mean, hist, hist_lo, hist ? 1.f / hist_step : 1.f, hist ? hist_bins : 1};
+    return LTE_OK;
+}
+
+extern "C" int lte_tx_papr(const lte_plan* p, const uint8_t* idx, const lte_c32* symbols, int32_t T, lte_c32* tx,
+                           double* stats, float* papr_db, float* peak_mean, unsigned long long* hist, float hist_lo,
+                           float hist_step, int32_t hist_bins, int32_t B, int32_t S, void* stream) {
+    if (!p || (!idx && !symbols) || B < 0 || S < 1 || T < 1 || T > LTE_MAX_TX) return LTE_ERR_INVALID_ARG;
+    if (!papr_db && !peak_mean && !hist) return LTE_ERR_INVALID_ARG;
+    PaprOut po;
+    int rc = make_papr_out(po, papr_db, peak_mean, hist, hist_lo, hist_step, hist_bins);
+    if (rc) return rc;
+    return launch_tx(p, idx, symbols, T, tx, nullptr, stats, &po, B, S, stream);
+}
+
+extern "C" int lte_papr_symbols(const lte_plan* p, const lte_c32* x, int32_t include_cp, float* papr_db,
+                                float* peak_mean, unsigned long long* hist, float hist_lo, float hist_step,
+                                int32_t hist_bins, int64_t rows, int32_t S, void* stream) {
+    if (!p || !x || rows < 0 || S < 1) return LTE_ERR_INVALID_ARG;
+    if (!papr_db && !peak_mean && !hist) return LTE_ERR_INVALID_ARG;
+    PaprOut po;
+    int rc = make_papr_out(po, papr_db, peak_mean, hist, hist_lo, hist_step, hist_bins);
+    if (rc) return rc;
+    const long long total = (long long)rows * S;
+    if (total == 0) return LTE_OK;
+    const long long grid = (total * 32 + 255) / 256;
+    if (grid >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
+    papr_symbols_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(p->dev, (const float2*)x, include_cp, po, total);
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}
+
+extern "C" int lte_histogram(const float* x, int64_t n, float lo, float step, int32_t bins, unsigned long long* hist,
+                             void* stream) {
+    if (!x || !hist || n < 0 || bins < 1 || bins > 8192 || !(step > 0.f)) return LTE_ERR_INVALID_ARG;
+    if (n == 0) return LTE_OK;
+    int sms = 148;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long want = (n + 255) / 256;
+    const unsigned grid = (unsigned)(want < 4ll * sms ? want : 4ll * sms);
+    histogram_kernel<<<grid, 256, bins * sizeof(unsigned int), (cudaStream_t)stream>>>(x, n, lo, 1.f / step, bins, hist);
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
 }
 
 extern "C" int lte_rx_fft(const lte_plan* p, const lte_c32* rx, int32_t rx_div, const double* power,

@@ -50,6 +50,10 @@ _SIGS = {
     'lte_bits_to_indices': ([_P, _P, _I64, _P, _I64, _I32, _P], C.c_int),
     'lte_indices_to_bits': ([_P, _P, _I64, _P, _I64, _I32, _P], C.c_int),
     'lte_tx_map_ifft': ([_P, _P, _P, _I32, _P, _P, _P, _I32, _I32, _P], C.c_int),
+    'lte_qam_map': ([_P, _P, _P, _I64, _P], C.c_int),
+    'lte_tx_papr': ([_P, _P, _P, _I32, _P, _P, _P, _P, _P, C.c_float, C.c_float, _I32, _I32, _I32, _P], C.c_int),
+    'lte_papr_symbols': ([_P, _P, _I32, _P, _P, _P, C.c_float, C.c_float, _I32, _I64, _I32, _P], C.c_int),
+    'lte_histogram': ([_P, _I64, C.c_float, C.c_float, _I32, _P, _P], C.c_int),
     'lte_dft_m': ([_P, _P, _P, _I32, _I32, _I64, _P], C.c_int),
     'lte_channel_tdl': ([_P, C.POINTER(ChannelDesc), _P, _P, _P, _P, _I32, _I32, _I32, _I64, _P], C.c_int),
     'lte_awgn_add': ([_P, _P, _I32, _P, _P, _P, _U64, _U64, _P, _I64, _I64, _P], C.c_int),

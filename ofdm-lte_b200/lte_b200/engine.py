@@ -139,6 +139,57 @@ class LinkEngine:
         self.launches += 1
         return tx, qam, stats
 
+    def qam_map(self, idx):
+        """Symbol indices (uint8, any shape) -> constellation points (complex64, same shape)."""
+        out = self._empty(tuple(idx.shape), torch.complex64)
+        nat.check(nat.lib.lte_qam_map(self._plan, _ptr(idx), _ptr(out), idx.numel(), self._stream()), 'lte_qam_map')
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ PAPR / CCDF
+    def modulate_papr(self, S, idx=None, symbols=None, T=1, write_tx=False, hist=None, hist_lo=0.0,
+                      hist_step=0.1, want_db=True, want_peak_mean=False):
+        """TX stage with the per-symbol PAPR epilogue (useful part, no CP).
+        -> (papr_db [B*T, S] float32 or None, peak_mean [B*T, S, 2] or None, tx [B*T, S*L] or None).
+        `hist` (int64 [bins], zeroed by the caller) accumulates the papr_db histogram in place."""
+        B = idx.shape[0] if idx is not None else symbols.shape[0] // T
+        tx = self._empty((B * T, S * self.L), torch.complex64) if write_tx else None
+        db = self._empty((B * T, S), torch.float32) if want_db else None
+        pm = self._empty((B * T, S, 2), torch.float32) if want_peak_mean else None
+        nat.check(nat.lib.lte_tx_papr(self._plan, _ptr(idx) if symbols is None else None, _ptr(symbols), T,
+                                      _ptr(tx), None, _ptr(db), _ptr(pm), _ptr(hist), float(hist_lo),
+                                      float(hist_step), 0 if hist is None else hist.numel(), B, S,
+                                      self._stream()), 'lte_tx_papr')
+        self.launches += 1
+        return db, pm, tx
+
+    def papr_symbols(self, x, include_cp=False, hist=None, hist_lo=0.0, hist_step=0.1, want_peak_mean=False):
+        """Per-OFDM-symbol PAPR of time-domain streams x [rows, S*L] -> (papr_db [rows, S], peak_mean or None)."""
+        x = x.reshape(-1, x.shape[-1])
+        rows, S = x.shape[0], x.shape[1] // self.L
+        db = self._empty((rows, S), torch.float32)
+        pm = self._empty((rows, S, 2), torch.float32) if want_peak_mean else None
+        if S == 0:
+            return db, pm
+        if x.shape[1] != S * self.L:
+            x = x[:, :S * self.L].contiguous()
+        nat.check(nat.lib.lte_papr_symbols(self._plan, _ptr(x), 1 if include_cp else 0, _ptr(db), _ptr(pm),
+                                           _ptr(hist), float(hist_lo), float(hist_step),
+                                           0 if hist is None else hist.numel(), rows, S, self._stream()),
+                  'lte_papr_symbols')
+        self.launches += 1
+        return db, pm
+
+    def histogram(self, x, lo, step, bins, hist=None):
+        """Counts of float32 x in `bins` bins of width `step` from `lo` (outliers in the edge bins)."""
+        x = x.reshape(-1).to(torch.float32).contiguous()
+        if hist is None:
+            hist = torch.zeros(bins, dtype=torch.int64, device=self.device)
+        nat.check(nat.lib.lte_histogram(_ptr(x), x.numel(), float(lo), float(step), int(bins), _ptr(hist),
+                                        self._stream()), 'lte_histogram')
+        self.launches += 1
+        return hist
+
     # ------------------------------------------------------------------ SC-FDM M-point DFT
     def dft_m(self, x, M, inverse=False, out=None):
         """Unitary M-point DFT (or IDFT) of every length-M row of x (any leading shape)."""

@@ -226,11 +226,38 @@ def papr(signal):
 
 
 def papr_per_symbol_no_cp(signal, num):
-    """core/ofdm_system.py:173-229 (per-OFDM-symbol PAPR with the CP removed)."""
+    """core/ofdm_system.py:173-229 (per-OFDM-symbol PAPR with the CP removed), linear ratio."""
     S = len(signal) // num.L
     x = signal[:S * num.L].reshape(S, num.L)[:, num.cp_length:]
     p = np.abs(x) ** 2
     return p.max(axis=1) / p.mean(axis=1)
+
+
+def papr_per_symbol_db(signal, num, include_cp=False):
+    """core/ofdm_system.py:116-171 (with the CP) and :173-229 (useful part only):
+    -> (papr_db[S], peak[S], mean[S]); an all-zero symbol reports 0 dB (:212-217)."""
+    S = len(signal) // num.L
+    x = np.asarray(signal)[:S * num.L].reshape(S, num.L)
+    if not include_cp:
+        x = x[:, num.cp_length:]
+    p = np.abs(x) ** 2
+    peak, mean = p.max(axis=1), p.mean(axis=1)
+    db = np.zeros(S)
+    nz = mean > 0
+    db[nz] = 10 * np.log10(peak[nz] / mean[nz])
+    return db, peak, mean
+
+
+def papr_histogram(papr_db, lo, step, bins):
+    """Bin rule of lte_tx_papr / lte_histogram: floor((x-lo)/step) clamped into [0, bins-1]."""
+    b = np.clip(np.floor((np.asarray(papr_db, dtype=np.float64) - lo) / step), 0, bins - 1).astype(np.int64)
+    return np.bincount(b, minlength=bins).astype(np.int64)
+
+
+def ccdf(papr_db, thresholds_db):
+    """P(PAPR > threshold) -- what the reference's CCDF plots draw from the collected values."""
+    v = np.sort(np.asarray(papr_db, dtype=np.float64))
+    return 1.0 - np.searchsorted(v, thresholds_db, side='right') / max(len(v), 1)
 
 
 # ----------------------------------------------------------------------------

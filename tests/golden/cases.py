@@ -73,3 +73,10 @@ SM_CASES = [
 ]
 
 BIG_RX_STRIDE = 8   # 'big' SIMO cases store every 8th sample of signal_rx
+
+# per-symbol PAPR (OFDM and SC-FDM on the same bits), core/ofdm_system.py:116-229
+PAPR_CASES = [
+    dict(name='papr_cfg2_10mhz_16qam', bw=10.0, mod='16-QAM', nsym=14, seed=21),
+    dict(name='papr_5mhz_qpsk_ragged', bw=5.0, mod='QPSK', nsym=6, seed=22, drop_bits=5),
+    dict(name='papr_20mhz_64qam', bw=20.0, mod='64-QAM', nsym=3, seed=23),
+]

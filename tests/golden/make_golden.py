@@ -32,7 +32,7 @@ from core.resource_mapper import LTEResourceGrid, PilotPattern  # noqa: E402
 from core.modulator import QAMModulator  # noqa: E402
 
 sys.path.insert(0, HERE)
-from cases import SISO_CASES, SIMO_CASES, SFBC_CASES, SM_CASES, BIG_RX_STRIDE  # noqa: E402
+from cases import SISO_CASES, SIMO_CASES, SFBC_CASES, SM_CASES, PAPR_CASES, BIG_RX_STRIDE  # noqa: E402
 
 
 def quiet(fn, *a, **k):
@@ -193,8 +193,32 @@ def sm_case(case):
     print(case['name'], {s: int(out[f'errors_{s}']) for s in case['snrs']})
 
 
+def papr_case(case):
+    """Per-symbol PAPR of the reference's OFDMSystem for OFDM and SC-FDM on the same bits."""
+    from core.ofdm_system import OFDMSystem
+    cfg = LTEConfig(case['bw'], 15.0, case['mod'])
+    n = case['nsym'] * nd_of(cfg) * cfg.bits_per_symbol - case.get('drop_bits', 0)
+    bits = make_bits(case['seed'], n)
+    out = {'bits': bits}
+    for tag, flag in (('ofdm', False), ('scfdm', True)):
+        sysm = quiet(OFDMSystem, LTEConfig(case['bw'], 15.0, case['mod']), 'awgn', mode='lte', enable_sc_fdm=flag)
+        sig = quiet(sysm.modulator.modulate_stream, bits)[0]
+        a = sysm.calculate_papr_without_cp(sig)
+        b = sysm.calculate_papr_per_symbol(sig)
+        c = sysm.calculate_papr(sig)
+        out[f'{tag}_no_cp_db'] = np.asarray(a['papr_per_symbol'], dtype=np.float64)
+        out[f'{tag}_cp_db'] = np.asarray(b['papr_per_symbol'], dtype=np.float64)
+        out[f'{tag}_cp_peak'] = np.asarray(b['power_peak_per_symbol'], dtype=np.float64)
+        out[f'{tag}_cp_avg'] = np.asarray(b['power_avg_per_symbol'], dtype=np.float64)
+        out[f'{tag}_stream'] = np.array([c['papr_db'], c['papr_linear'], c['peak_power'], c['avg_power']])
+    np.savez_compressed(os.path.join(HERE, case['name'] + '.npz'), **out)
+    print('wrote', case['name'])
+
+
 def main():
     tables()
+    for case in PAPR_CASES:
+        papr_case(case)
     for case in SM_CASES:
         sm_case(case)
     install_sfbc_shim()
