@@ -20,4 +20,6 @@ def _load():
     return sys.modules['_lte_b200_host.papr']
 
 
-ccdf_from_hist = _load().ccdf_from_hist
+_papr = _load()
+ccdf_from_hist = _papr.ccdf_from_hist
+papr_sweep = _papr.papr_sweep

@@ -66,3 +66,44 @@ def test_two_rank_sweep_equals_single_rank(tmp_path):
     assert torch.equal(multi['errors'], single['errors'])
     assert torch.equal(multi['bits'], single['bits'])
     assert torch.equal(single['bits'], torch.full((n_snr,), n_trials * 100, dtype=torch.int64))
+
+
+class _FakePaprEngine:
+    """CPU stand-in with the three engine calls papr_sweep makes; the 'PAPR' of a symbol is a
+    deterministic function of its global stream id so that sharding can be checked exactly."""
+    device = torch.device('cpu')
+    Nd = 4
+
+    def random_indices(self, B, S, seed, stream_id0=0, out=None):
+        return (torch.arange(stream_id0, stream_id0 + B, dtype=torch.int64)[:, None] * S +
+                torch.arange(S, dtype=torch.int64)[None, :])
+
+    def modulate_papr(self, S, idx=None, symbols=None, T=1, write_tx=False, hist=None, hist_lo=0.0, hist_step=0.1,
+                      want_db=True, want_peak_mean=False):
+        db = ((idx * 2654435761 % 1201).float() / 100.0)
+        b = torch.clamp(torch.floor((db - hist_lo) / hist_step).long(), 0, hist.numel() - 1)
+        hist += torch.bincount(b.reshape(-1), minlength=hist.numel())
+        return db, None, None
+
+
+def _papr_worker(rank, world, port, n_streams, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from lte_b200_papr_host import papr_sweep
+    r = papr_sweep(_FakePaprEngine(), n_streams, symbols_per_stream=3, batch_streams=5, hist_step=0.25, hist_bins=50,
+                   rank=rank, world=world)
+    if rank == 0:
+        torch.save(r, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_papr_histogram_equals_single_rank(tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from lte_b200_papr_host import papr_sweep
+    single = papr_sweep(_FakePaprEngine(), 41, symbols_per_stream=3, batch_streams=16, hist_step=0.25, hist_bins=50)
+    out = str(tmp_path / 'p.pt')
+    mp.spawn(_papr_worker, args=(2, _free_port(), 41, out), nprocs=2, join=True)
+    multi = torch.load(out, weights_only=False)
+    assert (multi['hist'] == single['hist']).all() and multi['count'] == single['count'] == 41 * 3
+    assert abs(multi['mean_db'] - single['mean_db']) < 1e-9 and multi['max_db'] == single['max_db']
+    assert (multi['ccdf'] == single['ccdf']).all()
