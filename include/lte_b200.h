@@ -203,6 +203,24 @@ int lte_equalize_zf(const lte_plan*, const lte_c32* Y, const lte_c32* H, lte_c32
 int lte_equalize_mrc(const lte_plan*, const lte_c32* Y, const lte_c32* H, lte_c32* out, int window,
                      int64_t B, int32_t R, int32_t S, void* stream);
 
+/* --- lazy frequency-domain AWGN for the sweep engine -------------------------------------------
+ * The noise lte_rx_fft(noise_domain = 1) would add to grid element (row, symbol, bin) is a pure
+ * function of (seed, row_id0 + row, symbol, bin).  These variants take a noise-free Y and add that
+ * noise while reading it (bit-identical result), so the noisy grid never exists in HBM and only
+ * the elements that are consumed get a noise sample.  power [rows] as produced by
+ * lte_channel_tdl / lte_channel_rx_fft, snr_lin [rows]; rows = B*R. */
+typedef struct {
+    const double* power;
+    const float* snr_lin;
+    uint64_t seed;
+    uint64_t row_id0;
+} lte_awgn_desc;
+int lte_crs_ls_interp_awgn(const lte_plan*, const lte_c32* Y, lte_c32* H, int window, int pilot_set,
+                           int64_t rows, int32_t S, const lte_awgn_desc* awgn, void* stream);
+int lte_mrc_demap_count_awgn(const lte_plan*, const lte_c32* Y, const lte_c32* H, const uint8_t* idx_tx,
+                             unsigned long long* errors, int window, int64_t nbits, int64_t B, int32_t R,
+                             int32_t S, const lte_awgn_desc* awgn, void* stream);
+
 /* --- SFBC Alamouti transmit diversity (2 TX) ---------------------------------------------
  * lte_sfbc_encode replaces SFBCAlamouti.encode (core/sfbc_alamouti.py:45-78) fused with the QAM
  * map: idx [B][S][2*(Nd/2)] symbol indices (or `symbols`, complex, same shape) ->

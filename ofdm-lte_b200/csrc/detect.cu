@@ -83,12 +83,41 @@ extern "C" int lte_qam_map(const lte_plan* p, const uint8_t* idx, lte_c32* symbo
     return LTE_OK;
 }
 
+// ------------------------------------------------------------------------------ lazy AWGN
+// The sweep engine keeps the frequency-domain AWGN of lte_rx_fft(noise_domain = 1) out of HBM:
+// the noise of grid element (row, symbol, bin) is a pure function of (seed, row id, symbol, bin), so
+// the kernels that consume Y add it on the fly -- bit-identical to adding it in the RX epilogue
+// (same Philox counter, same fmaf), and only for the elements that are actually read.
+struct AwgnArgs {
+    const double* power;        // [rows] sum |y|^2 of the stream (lte_channel_tdl / lte_channel_rx_fft)
+    const float* snr_lin;       // [rows]
+    uint32_t key;
+    unsigned long long row_id0;
+    float n_stream;             // samples per stream, S * L
+};
+
+__device__ __forceinline__ float2 awgn_at(const AwgnArgs& A, float sigma, long long row, int s, int N, int kb, float2 y) {
+    const float2 w = lte_noise_sample(A.key, (uint32_t)(A.row_id0 + (unsigned long long)row), (uint32_t)(s * N + kb));
+    return make_float2(fmaf(sigma, w.x, y.x), fmaf(sigma, w.y, y.y));
+}
+
+static int make_awgn_args(AwgnArgs& A, const lte_plan* p, const lte_awgn_desc* d, int32_t S) {
+    if (!d->power || !d->snr_lin) return LTE_ERR_INVALID_ARG;
+    A.power = d->power;
+    A.snr_lin = d->snr_lin;
+    A.key = lte_key(d->seed, LTE_DOMAIN_NOISE);
+    A.row_id0 = d->row_id0;
+    A.n_stream = (float)((size_t)S * p->dev.L);
+    return LTE_OK;
+}
+
 // ------------------------------------------------------------------------------ stage 4
 // core/lte_receiver.py:62-87 (LS at the pilots) and :98-133 (edge hold + np.linspace).
 // One CTA per (row, slot); the estimate comes from the slot's first symbol (:380-406).
+template <bool NOISY>
 __global__ void __launch_bounds__(256)
 crs_ls_interp_kernel(const DevPlan P, const float2* __restrict__ Y, float2* __restrict__ H, int k0, int nk,
-                     int set, int S, int nslot) {
+                     int set, int S, int nslot, const AwgnArgs A) {
     extern __shared__ float2 hp[];      // LS estimates at the owned pilots
     const long long row = blockIdx.x / nslot;
     const int slot = blockIdx.x % nslot;
@@ -96,7 +125,13 @@ crs_ls_interp_kernel(const DevPlan P, const float2* __restrict__ Y, float2* __re
     const int cnt = P.pset_cnt[set];
     const int16_t* pbin = P.pset_bin + (size_t)set * P.Np;
     const float2* pinv = P.pset_inv + (size_t)set * P.Np;
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) hp[i] = cmul(y[pbin[i] - k0], pinv[i]);
+    float sigma = 0.f;
+    if (NOISY) sigma = lte_sigma(A.power[row], A.n_stream, A.snr_lin[row]);
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        float2 yp = y[pbin[i] - k0];
+        if (NOISY) yp = awgn_at(A, sigma, row, slot * LTE_SLOT_SYMBOLS, P.N, pbin[i], yp);
+        hp[i] = cmul(yp, pinv[i]);
+    }
     __syncthreads();
     const int16_t* seg = P.pset_seg + (size_t)set * P.N;
     float2* h = H + ((size_t)row * nslot + slot) * nk;
@@ -118,19 +153,38 @@ crs_ls_interp_kernel(const DevPlan P, const float2* __restrict__ Y, float2* __re
     }
 }
 
-extern "C" int lte_crs_ls_interp(const lte_plan* p, const lte_c32* Y, lte_c32* H, int window, int pilot_set,
-                                 int64_t rows, int32_t S, void* stream) {
+static int launch_crs(const lte_plan* p, const lte_c32* Y, lte_c32* H, int window, int pilot_set, int64_t rows,
+                      int32_t S, const lte_awgn_desc* awgn, void* stream) {
     if (!p || !Y || !H || rows < 0 || S < 1) return LTE_ERR_INVALID_ARG;
     if (p->dev.Np == 0 || pilot_set < 0 || pilot_set >= p->nsets) return LTE_ERR_INVALID_ARG;
     int32_t k0, nk;
     int rc = lte_plan_window(p, window, &k0, &nk);
     if (rc) return rc;
+    AwgnArgs A = {};
+    if (awgn && (rc = make_awgn_args(A, p, awgn, S))) return rc;
     if (rows == 0) return LTE_OK;
     const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
-    crs_ls_interp_kernel<<<(unsigned)(rows * nslot), 256, sizeof(float2) * p->dev.Np, (cudaStream_t)stream>>>(
-        p->dev, (const float2*)Y, (float2*)H, k0, nk, pilot_set, S, nslot);
+    const unsigned grid = (unsigned)(rows * nslot);
+    const size_t smem = sizeof(float2) * p->dev.Np;
+    if (awgn)
+        crs_ls_interp_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(p->dev, (const float2*)Y, (float2*)H, k0,
+                                                                             nk, pilot_set, S, nslot, A);
+    else
+        crs_ls_interp_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(p->dev, (const float2*)Y, (float2*)H, k0,
+                                                                              nk, pilot_set, S, nslot, A);
     LTE_CHECK_CUDA(cudaGetLastError());
     return LTE_OK;
+}
+
+extern "C" int lte_crs_ls_interp(const lte_plan* p, const lte_c32* Y, lte_c32* H, int window, int pilot_set,
+                                 int64_t rows, int32_t S, void* stream) {
+    return launch_crs(p, Y, H, window, pilot_set, rows, S, nullptr, stream);
+}
+
+extern "C" int lte_crs_ls_interp_awgn(const lte_plan* p, const lte_c32* Y, lte_c32* H, int window, int pilot_set,
+                                      int64_t rows, int32_t S, const lte_awgn_desc* awgn, void* stream) {
+    if (!awgn) return LTE_ERR_INVALID_ARG;
+    return launch_crs(p, Y, H, window, pilot_set, rows, S, awgn, stream);
 }
 
 // ------------------------------------------------------------------------------ slicer
@@ -236,16 +290,22 @@ extern "C" int lte_equalize_zf(const lte_plan* p, const lte_c32* Y, const lte_c3
 
 // MRC (core/ofdm_core.py:1484-1532): thread = (stream, data bin); H of the slot is held in
 // registers while the thread walks the slot's symbols, so H is read once per 14 symbols.
-template <int R, bool COUNT>
+template <int R, bool COUNT, bool NOISY>
 __global__ void __launch_bounds__(128)
 mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restrict__ H, float2* __restrict__ out,
            const uint8_t* __restrict__ idx_tx, unsigned long long* __restrict__ errors, int k0, int nk, int S,
-           int nslot, long long nbits, int gx) {
+           int nslot, long long nbits, int gx, const AwgnArgs A) {
     const long long b = blockIdx.x / gx;
     const int d = (blockIdx.x % gx) * blockDim.x + threadIdx.x;
     unsigned int e = 0;
     if (d < P.Nd) {
-        const int kk = P.data_idx[d] - k0;
+        const int kb = P.data_idx[d];
+        const int kk = kb - k0;
+        float sigma[R];
+        if (NOISY) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) sigma[r] = lte_sigma(A.power[b * R + r], A.n_stream, A.snr_lin[b * R + r]);
+        }
         for (int slot = 0; slot < nslot; ++slot) {
             float2 h[R];
             float den = 0.f;
@@ -260,7 +320,8 @@ mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restri
                 float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const float2 y = Y[(((size_t)b * R + r) * S + s) * nk + kk];
+                    float2 y = Y[(((size_t)b * R + r) * S + s) * nk + kk];
+                    if (NOISY) y = awgn_at(A, sigma[r], b * R + r, s, P.N, kb, y);
                     const float2 t = cmulc(h[r], y);
                     acc.x += t.x;
                     acc.y += t.y;
@@ -282,19 +343,27 @@ mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restri
 template <bool COUNT>
 static int launch_mrc(const lte_plan* p, const lte_c32* Y, const lte_c32* H, lte_c32* out, const uint8_t* idx_tx,
                       unsigned long long* errors, int window, int64_t nbits, int64_t B, int32_t R, int32_t S,
-                      void* stream) {
+                      const lte_awgn_desc* awgn, void* stream) {
     int32_t k0, nk;
     int rc = lte_plan_window(p, window, &k0, &nk);
     if (rc) return rc;
+    AwgnArgs A = {};
+    if (awgn && (rc = make_awgn_args(A, p, awgn, S))) return rc;
     if (B == 0) return LTE_OK;
     const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
     const int gx = (p->dev.Nd + 127) / 128;
     const unsigned grid = (unsigned)((long long)gx * B);
     cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH_MRC(RR)                                                                                        \
-    case RR:                                                                                                  \
-        mrc_kernel<RR, COUNT><<<grid, 128, 0, st>>>(p->dev, (const float2*)Y, (const float2*)H, (float2*)out, \
-                                                    idx_tx, errors, k0, nk, S, nslot, nbits, gx);             \
+#define LAUNCH_MRC(RR)                                                                                          \
+    case RR:                                                                                                    \
+        if (awgn)                                                                                               \
+            mrc_kernel<RR, COUNT, true><<<grid, 128, 0, st>>>(p->dev, (const float2*)Y, (const float2*)H,      \
+                                                              (float2*)out, idx_tx, errors, k0, nk, S, nslot,  \
+                                                              nbits, gx, A);                                    \
+        else                                                                                                    \
+            mrc_kernel<RR, COUNT, false><<<grid, 128, 0, st>>>(p->dev, (const float2*)Y, (const float2*)H,     \
+                                                               (float2*)out, idx_tx, errors, k0, nk, S, nslot, \
+                                                               nbits, gx, A);                                   \
         break;
     switch (R) {
         LAUNCH_MRC(1) LAUNCH_MRC(2) LAUNCH_MRC(3) LAUNCH_MRC(4) LAUNCH_MRC(5) LAUNCH_MRC(6) LAUNCH_MRC(7)
@@ -309,12 +378,19 @@ static int launch_mrc(const lte_plan* p, const lte_c32* Y, const lte_c32* H, lte
 extern "C" int lte_equalize_mrc(const lte_plan* p, const lte_c32* Y, const lte_c32* H, lte_c32* out, int window,
                                 int64_t B, int32_t R, int32_t S, void* stream) {
     if (!p || !Y || !H || !out || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
-    return launch_mrc<false>(p, Y, H, out, nullptr, nullptr, window, 0, B, R, S, stream);
+    return launch_mrc<false>(p, Y, H, out, nullptr, nullptr, window, 0, B, R, S, nullptr, stream);
 }
 
 extern "C" int lte_mrc_demap_count(const lte_plan* p, const lte_c32* Y, const lte_c32* H, const uint8_t* idx_tx,
                                    unsigned long long* errors, int window, int64_t nbits, int64_t B, int32_t R,
                                    int32_t S, void* stream) {
     if (!p || !Y || !H || !idx_tx || !errors || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
-    return launch_mrc<true>(p, Y, H, nullptr, idx_tx, errors, window, nbits, B, R, S, stream);
+    return launch_mrc<true>(p, Y, H, nullptr, idx_tx, errors, window, nbits, B, R, S, nullptr, stream);
+}
+
+extern "C" int lte_mrc_demap_count_awgn(const lte_plan* p, const lte_c32* Y, const lte_c32* H, const uint8_t* idx_tx,
+                                        unsigned long long* errors, int window, int64_t nbits, int64_t B, int32_t R,
+                                        int32_t S, const lte_awgn_desc* awgn, void* stream) {
+    if (!p || !Y || !H || !idx_tx || !errors || !awgn || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
+    return launch_mrc<true>(p, Y, H, nullptr, idx_tx, errors, window, nbits, B, R, S, awgn, stream);
 }

@@ -35,6 +35,10 @@ class ChannelDesc(C.Structure):
                 ('gain', C.c_float * LTE_MAX_TAPS), ('doppler_hz', C.c_double)]
 
 
+class AwgnDesc(C.Structure):
+    _fields_ = [('power', C.c_void_p), ('snr_lin', C.c_void_p), ('seed', C.c_uint64), ('row_id0', C.c_uint64)]
+
+
 _P = C.c_void_p
 _I32, _I64, _U64 = C.c_int32, C.c_int64, C.c_uint64
 
@@ -59,6 +63,9 @@ _SIGS = {
     'lte_awgn_add': ([_P, _P, _I32, _P, _P, _P, _U64, _U64, _P, _I64, _I64, _P], C.c_int),
     'lte_rx_fft': ([_P, _P, _I32, _P, _P, _P, _I32, _U64, _U64, _P, C.c_int, _I64, _I32, _P], C.c_int),
     'lte_crs_ls_interp': ([_P, _P, _P, C.c_int, C.c_int, _I64, _I32, _P], C.c_int),
+    'lte_crs_ls_interp_awgn': ([_P, _P, _P, C.c_int, C.c_int, _I64, _I32, C.POINTER(AwgnDesc), _P], C.c_int),
+    'lte_mrc_demap_count_awgn': ([_P, _P, _P, _P, _P, C.c_int, _I64, _I64, _I32, _I32, C.POINTER(AwgnDesc), _P],
+                                 C.c_int),
     'lte_equalize_zf': ([_P, _P, _P, _P, C.c_int, _I64, _I32, _P], C.c_int),
     'lte_equalize_mrc': ([_P, _P, _P, _P, C.c_int, _I64, _I32, _I32, _P], C.c_int),
     'lte_sfbc_encode': ([_P, _P, _P, _P, _P, _I64, _I32, _P], C.c_int),

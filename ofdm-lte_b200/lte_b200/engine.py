@@ -238,12 +238,22 @@ class LinkEngine:
         return Y
 
     # ------------------------------------------------------------------ stage 4
-    def estimate(self, Y, rows, S, window=nat.WINDOW_FULL, pilot_set=0, out=None):
+    @staticmethod
+    def awgn_desc(power, snr_lin, seed, row_id0=0):
+        """Lazy frequency-domain AWGN: the consumers of a noise-free Y add the noise
+        lte_rx_fft(noise_domain=1) would have added (see include/lte_b200.h)."""
+        return nat.AwgnDesc(power.data_ptr(), snr_lin.data_ptr(), int(seed), int(row_id0))
+
+    def estimate(self, Y, rows, S, window=nat.WINDOW_FULL, pilot_set=0, out=None, awgn=None):
         k0, nk = self.window(window)
         nslot = -(-S // nat.LTE_SLOT_SYMBOLS)
         H = out if out is not None else self._empty((rows, nslot, nk), torch.complex64)
-        nat.check(nat.lib.lte_crs_ls_interp(self._plan, _ptr(Y), _ptr(H), window, pilot_set, rows, S,
-                                            self._stream()), 'lte_crs_ls_interp')
+        if awgn is None:
+            nat.check(nat.lib.lte_crs_ls_interp(self._plan, _ptr(Y), _ptr(H), window, pilot_set, rows, S,
+                                                self._stream()), 'lte_crs_ls_interp')
+        else:
+            nat.check(nat.lib.lte_crs_ls_interp_awgn(self._plan, _ptr(Y), _ptr(H), window, pilot_set, rows, S,
+                                                     C.byref(awgn), self._stream()), 'lte_crs_ls_interp_awgn')
         self.launches += 1
         return H
 
@@ -339,14 +349,19 @@ class LinkEngine:
         self.launches += 1
         return errors, idx_rx
 
-    def mrc_demap_count(self, Y, H, idx_tx, B, R, S, nbits=None, window=nat.WINDOW_USEFUL, errors=None):
+    def mrc_demap_count(self, Y, H, idx_tx, B, R, S, nbits=None, window=nat.WINDOW_USEFUL, errors=None, awgn=None):
         if errors is None:
             errors = torch.zeros(B, dtype=torch.int64, device=self.device)
         else:
             errors.zero_()
         nb = int(nbits) if nbits is not None else S * self.Nd * self.bps
-        nat.check(nat.lib.lte_mrc_demap_count(self._plan, _ptr(Y), _ptr(H), _ptr(idx_tx), _ptr(errors), window, nb,
-                                              B, R, S, self._stream()), 'lte_mrc_demap_count')
+        if awgn is None:
+            nat.check(nat.lib.lte_mrc_demap_count(self._plan, _ptr(Y), _ptr(H), _ptr(idx_tx), _ptr(errors), window,
+                                                  nb, B, R, S, self._stream()), 'lte_mrc_demap_count')
+        else:
+            nat.check(nat.lib.lte_mrc_demap_count_awgn(self._plan, _ptr(Y), _ptr(H), _ptr(idx_tx), _ptr(errors),
+                                                       window, nb, B, R, S, C.byref(awgn), self._stream()),
+                      'lte_mrc_demap_count_awgn')
         self.launches += 1
         return errors
 
@@ -388,6 +403,11 @@ class LinkEngine:
         else:
             _, power = self.channel(tx, chan, B, R, power=ws['power'])
             rx, div = tx, R
+        if noise_domain == 2:       # noise-free grid, AWGN added lazily by the consumers (same draws as 1)
+            Y = self.rx_fft(rx, B * R, S, nat.WINDOW_USEFUL, rx_div=div, out=ws['Y'])
+            awgn = self.awgn_desc(power, snr_lin_rows, seed, stream_id0 * R)
+            H = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, out=ws['H'], awgn=awgn)
+            return self.mrc_demap_count(Y, H, idx, B, R, S, nbits=nbits, errors=ws['errors'], awgn=awgn)
         Y = self.rx_fft(rx, B * R, S, nat.WINDOW_USEFUL, rx_div=div, power=power, snr_lin=snr_lin_rows, seed=seed,
                         row_id0=stream_id0 * R, out=ws['Y'], noise_domain=noise_domain)
         H = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, out=ws['H'])

@@ -49,3 +49,29 @@ def test_time_and_frequency_domain_noise_agree_statistically():
     t = simo_sweep(eng, chan, snr, n_trials=400, num_rx=2, seed=2, noise_domain=0)['ber'].numpy()
     f = simo_sweep(eng, chan, snr, n_trials=400, num_rx=2, seed=2, noise_domain=1)['ber'].numpy()
     assert np.all(np.abs(t - f) / t < 0.05)
+
+
+@pytest.mark.parametrize('bw,mod,R', [(1.25, '16-QAM', 2), (5.0, '64-QAM', 4), (2.5, 'QPSK', 1)])
+def test_lazy_awgn_is_bit_identical_to_noise_in_the_rx_epilogue(bw, mod, R):
+    """noise_domain 2 keeps Y noise-free and lets the CRS / MRC kernels add the very same Philox
+    draws while reading it: every stream's error count must match noise_domain 1 exactly."""
+    from lte_b200 import _native as nat
+    eng, chan = _setup(bw=bw, mod=mod)
+    B, S = 24, 15                                   # two slots, the second one symbol long
+    ws = eng.workspace(B, S, R, fading=True)
+    snr = torch.tensor([10 ** (s / 10) for s in (2.0, 9.0, 17.0)], dtype=torch.float32, device='cuda')
+    rows = snr.repeat(B // 3).repeat_interleave(R).contiguous()
+    e1 = eng.simo_ber(ws, chan, rows, seed=9, stream_id0=7, noise_domain=1).clone()
+    Y1, H1 = ws['Y'].clone(), ws['H'].clone()
+    e2 = eng.simo_ber(ws, chan, rows, seed=9, stream_id0=7, noise_domain=2).clone()
+    assert torch.equal(e1, e2) and int(e1.sum()) > 0
+    # the channel estimate formed from the lazily-noised pilots is the same tensor, bit for bit
+    assert torch.equal(ws['H'], H1)
+    assert not torch.equal(ws['Y'], Y1)             # ...while Y itself stayed noise-free
+    # AWGN channel type (no fading buffer, rx_div = R)
+    from lte_b200 import chan_for
+    awgn = chan_for('awgn', eng.fs, 'Pedestrian_A', 2.0, 0.0)
+    wa = eng.workspace(B, S, R, fading=False)
+    a1 = eng.simo_ber(wa, awgn, rows, seed=3, noise_domain=1).clone()
+    a2 = eng.simo_ber(wa, awgn, rows, seed=3, noise_domain=2).clone()
+    assert torch.equal(a1, a2)
