@@ -48,7 +48,15 @@ def stage_bytes(N=2048, cp=144, Nd=999, Np=200, Nc=1200, b=6, R=R_ANT, S=S_SUBFR
         'rx_fft': R * S * L * 8 + R * S * (Nd + Np) * 8,
         'crs_ls_interp': R * Np * 8 + R * Nd * 8,
         'mrc_demap_count': R * S * Nd * 8 + R * Nd * 8 + S * Nd * b / 8 + 8,
+        # fused pipeline: inputs of the first + outputs of the last fused stage
+        'channel_rx_fft': S * L * 8 + R * S * (Nd + Np) * 8,
     }
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
+NCU_TRAFFIC = {}
+
+STAGED = ('tx_map_ifft', 'channel_tdl', 'rx_fft', 'crs_ls_interp', 'mrc_demap_count')
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -181,7 +189,8 @@ def run_gpu(args, rank, world):
     n_snr = len(SNR_POINTS)
     B = args.trials * n_snr                     # subframes per step per GPU
     S, R = S_SUBFRAME, R_ANT
-    ws = eng.workspace(B, S, R, fading=True)
+    fused = args.pipeline == 'fused'
+    ws = eng.workspace(B, S, R, fading=True, fused=fused)
     snr_lin = torch.tensor([10 ** (s / 10) for s in SNR_POINTS], dtype=torch.float32, device=dev)
     snr_rows = snr_lin.repeat(args.trials).repeat_interleave(R).contiguous()       # [B*R], SNR fastest over b
     nbits = S * eng.Nd * eng.bps
@@ -193,7 +202,8 @@ def run_gpu(args, rank, world):
 
     def step(i):
         sid0 = ((i * world) + rank) * B          # global stream ids: independent of the GPU count
-        err = eng.simo_ber(ws, chan, snr_rows, seed, stream_id0=sid0, idx=idx, nbits=nbits)
+        err = eng.simo_ber(ws, chan, snr_rows, seed, stream_id0=sid0, idx=idx, nbits=nbits, fused=fused,
+                           noise_domain=3 if fused else 1)
         totals.add_(err.view(args.trials, n_snr).sum(0))
 
     def sync():
@@ -257,7 +267,8 @@ def run_gpu(args, rank, world):
         main.wait_event(ev_copied[k])
         ix = eng.bits_to_indices(dev_bits[k], nbits, S, packed=True)
         sid0 = ((i * world) + rank) * B
-        err = eng.simo_ber(ws, chan, snr_rows, seed + 1, stream_id0=sid0, idx=ix, nbits=nbits)
+        err = eng.simo_ber(ws, chan, snr_rows, seed + 1, stream_id0=sid0, idx=ix, nbits=nbits, fused=fused,
+                           noise_domain=3 if fused else 1)
         host_err.copy_(err, non_blocking=True)
         ev_free[k].record(main)
 
@@ -282,7 +293,7 @@ def run_gpu(args, rank, world):
     # ---- per-stage device time (CUDA events on the launching stream), rank 0 ---------------
     stages, roofline, cpu = None, None, None
     if rank == 0:
-        stages = time_stages(eng, ws, chan, snr_rows, idx, nbits, seed, B, S, R, nat, torch, dev)
+        stages = time_stages(eng, ws, chan, snr_rows, idx, nbits, seed, B, S, R, nat, torch, dev, fused=fused)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -292,13 +303,15 @@ def run_gpu(args, rank, world):
         peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
         sb = stage_bytes()
         for k in stages:
-            stages[k]['algo_bytes_per_launch'] = sb[k] * B
-            stages[k]['gbs'] = sb[k] * B / (stages[k]['ms'] * 1e-3) / 1e9
+            kb = sb[k.replace('_awgn', '')]
+            stages[k]['algo_bytes_per_launch'] = kb * B
+            stages[k]['gbs'] = kb * B / (stages[k]['ms'] * 1e-3) / 1e9
             stages[k]['frac'] = stages[k]['gbs'] / peak
         dom = max(stages, key=lambda k: stages[k]['ms'])
         roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': stages[dom]['gbs'], 'peak': peak, 'unit': 'GB/s',
-                    'frac': stages[dom]['frac'], 'traffic': None, 'peak_source': peak_src,
-                    'pipeline_unfused_equivalent_frac': value / world * sum(sb.values()) / 1e9 / peak}
+                    'frac': stages[dom]['frac'], 'traffic': NCU_TRAFFIC.get(dom), 'peak_source': peak_src,
+                    'pipeline_bytes_frac': value / world * sum(sb[k.replace('_awgn', '')] for k in stages) / 1e9 / peak,
+                    'pipeline_unfused_equivalent_frac': value / world * sum(sb[k] for k in STAGED) / 1e9 / peak}
         if world == 1:
             n_cpu = args.cpu_subframes
             v = cpu_subframes_per_s(n_cpu, 1)
@@ -310,8 +323,9 @@ def run_gpu(args, rank, world):
                 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                 'config': {'workload': workload_name(args.trials), 'subframes_per_step_per_gpu': B,
+                           'pipeline': args.pipeline,
                            'l2_policy': 'inputs and intermediates (%.1f GB per step) exceed the 126 MB L2' %
-                                        (B * 1.8e6 / 1e9),
+                                        (B * (0.88e6 if fused else 1.8e6) / 1e9),
                            'parallelism': f'trial sharding x{world}, one int64[16] allreduce'},
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * nbytes,
                         'd2h_bytes_per_step': B * 8},
@@ -322,11 +336,31 @@ def run_gpu(args, rank, world):
         dist.destroy_process_group()
 
 
-def time_stages(eng, ws, chan, snr_rows, idx, nbits, seed, B, S, R, nat, torch, dev, reps=5, only=None):
-    """Average device time of every stage kernel over `reps` launches (after one warm-up)."""
+def time_stages(eng, ws, chan, snr_rows, idx, nbits, seed, B, S, R, nat, torch, dev, reps=5, only=None,
+                fused=False):
+    """Average device time of every stage kernel over `reps` launches (after one warm-up).
+    fused: the stages of the fused pipeline (channel_rx_fft includes its Jakes coefficient kernel)."""
     per = R * chan.num_taps * nat.LTE_JAKES_TONES
     ph = eng.random_phases(B, per, seed, 0, out=ws['phases'].view(-1)[:B * per].view(B, per))
-    calls = {
+    if fused:
+        awgn = eng.awgn_desc(ws['power'], snr_rows, seed, 0, combine=True)
+        calls = {
+            'tx_map_ifft': lambda: eng.modulate(S, idx=idx, want_stats=False, out=ws['tx']),
+            'channel_rx_fft': lambda: eng.channel_rx_fft(ws['tx'], chan, B, R, S, ph, nat.WINDOW_USEFUL, out=ws['Y'],
+                                                         power=ws['power']),
+            'crs_ls_interp_awgn': lambda: eng.estimate(ws['Y'], B * R, S, nat.WINDOW_USEFUL, out=ws['H'], awgn=awgn),
+            'mrc_demap_count_awgn': lambda: eng.mrc_demap_count(ws['Y'], ws['H'], idx, B, R, S, nbits=nbits,
+                                                                errors=ws['errors'], awgn=awgn),
+        }
+    else:
+        if 'faded' not in ws:
+            ws['faded'] = torch.empty((B, R, S * eng.L), dtype=torch.complex64, device=dev)
+        calls = _staged_calls(eng, ws, chan, snr_rows, idx, nbits, seed, B, S, R, nat, ph)
+    return _time_calls(calls, torch, dev, reps, only)
+
+
+def _staged_calls(eng, ws, chan, snr_rows, idx, nbits, seed, B, S, R, nat, ph):
+    return {
         'tx_map_ifft': lambda: eng.modulate(S, idx=idx, want_stats=False, out=ws['tx']),
         'channel_tdl': lambda: eng.channel(ws['tx'], chan, B, R, phases=ph, out=ws['faded'], power=ws['power']),
         'rx_fft': lambda: eng.rx_fft(ws['faded'], B * R, S, nat.WINDOW_USEFUL, power=ws['power'], snr_lin=snr_rows,
@@ -335,6 +369,9 @@ def time_stages(eng, ws, chan, snr_rows, idx, nbits, seed, B, S, R, nat, torch, 
         'mrc_demap_count': lambda: eng.mrc_demap_count(ws['Y'], ws['H'], idx, B, R, S, nbits=nbits,
                                                        errors=ws['errors']),
     }
+
+
+def _time_calls(calls, torch, dev, reps, only):
     out = {}
     for name, fn in calls.items():
         if only and name not in only:
@@ -358,6 +395,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--trials', type=int, default=256, help='trials per SNR point per GPU per step')
+    ap.add_argument('--pipeline', default='fused', choices=['fused', 'staged'],
+                    help='fused: channel + RX FFT in one kernel, AWGN added lazily by the consumers; '
+                         'staged: one kernel per reference stage')
     ap.add_argument('--cpu-subframes', type=int, default=24, help='bounded sample for cpu_baseline')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))

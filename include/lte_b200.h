@@ -203,6 +203,21 @@ int lte_equalize_zf(const lte_plan*, const lte_c32* Y, const lte_c32* H, lte_c32
 int lte_equalize_mrc(const lte_plan*, const lte_c32* Y, const lte_c32* H, lte_c32* out, int window,
                      int64_t B, int32_t R, int32_t S, void* stream);
 
+/* --- fused stage 3 + CP strip + FFT (sweep engine) -----------------------------------------------
+ * lte_channel_tdl followed by lte_rx_fft(noise_domain none) in ONE kernel for T = 1: the faded
+ * time-domain streams [B][R][S*L] are formed in registers / shared memory and never written.
+ * replaces RayleighChannel.jakes_fading/.filter (core/rayleighchannel.py:20-58) for the R links
+ * of OFDMChannel.transmit_simo (core/ofdm_core.py:361-412) and
+ * LTEReceiver._demodulate_ofdm_stream (core/lte_receiver.py:444-491).
+ * tx: [B][S*L]; phases as in lte_channel_tdl with T = 1; Y: [B*R][S][nk] noise-free;
+ * power: [B][R] sum |faded|^2 over the whole stream including the CP samples, accumulated with
+ * atomics, caller zeroes.  The AWGN is then added lazily by the *_awgn consumers below.
+ * Returns LTE_ERR_UNSUPPORTED for the identity link (num_taps = 0) and when the Doppler spread
+ * is too large for one Jakes polynomial per OFDM symbol (> about 330 Hz): use the staged pair. */
+int lte_channel_rx_fft(const lte_plan*, const lte_channel_desc* ch, const lte_c32* tx,
+                       const float* phases, lte_c32* Y, double* power, int window, int32_t B,
+                       int32_t R, int32_t S, void* stream);
+
 /* --- lazy frequency-domain AWGN for the sweep engine -------------------------------------------
  * The noise lte_rx_fft(noise_domain = 1) would add to grid element (row, symbol, bin) is a pure
  * function of (seed, row_id0 + row, symbol, bin).  These variants take a noise-free Y and add that
@@ -214,6 +229,11 @@ typedef struct {
     const float* snr_lin;
     uint64_t seed;
     uint64_t row_id0;
+    /* lte_mrc_demap_count_awgn only.  0: one draw per (antenna, symbol, bin), the very draws of the
+     * RX epilogue.  1: one draw per combiner output, scaled by sqrt(sum_r |H_r|^2 sigma_r^2) -- the
+     * exact distribution of sum_r conj(H_r) sigma_r w_r given H, at 1/R of the generator work
+     * (different sample values, same BER statistics). */
+    int32_t combine;
 } lte_awgn_desc;
 int lte_crs_ls_interp_awgn(const lte_plan*, const lte_c32* Y, lte_c32* H, int window, int pilot_set,
                            int64_t rows, int32_t S, const lte_awgn_desc* awgn, void* stream);

@@ -94,6 +94,7 @@ struct AwgnArgs {
     uint32_t key;
     unsigned long long row_id0;
     float n_stream;             // samples per stream, S * L
+    int combine;                // MRC only: one draw per combiner output (see lte_awgn_desc)
 };
 
 __device__ __forceinline__ float2 awgn_at(const AwgnArgs& A, float sigma, long long row, int s, int N, int kb, float2 y) {
@@ -108,6 +109,7 @@ static int make_awgn_args(AwgnArgs& A, const lte_plan* p, const lte_awgn_desc* d
     A.key = lte_key(d->seed, LTE_DOMAIN_NOISE);
     A.row_id0 = d->row_id0;
     A.n_stream = (float)((size_t)S * p->dev.L);
+    A.combine = d->combine;
     return LTE_OK;
 }
 
@@ -315,17 +317,27 @@ mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restri
                 den += cabs2(h[r]);
             }
             den += 1e-10f;
+            // combined mode: sum_r conj(h_r) sigma_r w_r with independent unit normals w_r is one complex
+            // normal of standard deviation sqrt(sum_r |h_r|^2 sigma_r^2) per component
+            float csig = 0.f;
+            const bool comb = NOISY && A.combine;
+            if (comb) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) csig = fmaf(cabs2(h[r]), sigma[r] * sigma[r], csig);
+                csig = sqrtf(csig);
+            }
             const int s_end = min(S, (slot + 1) * LTE_SLOT_SYMBOLS);
             for (int s = slot * LTE_SLOT_SYMBOLS; s < s_end; ++s) {
                 float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     float2 y = Y[(((size_t)b * R + r) * S + s) * nk + kk];
-                    if (NOISY) y = awgn_at(A, sigma[r], b * R + r, s, P.N, kb, y);
+                    if (NOISY && !comb) y = awgn_at(A, sigma[r], b * R + r, s, P.N, kb, y);
                     const float2 t = cmulc(h[r], y);
                     acc.x += t.x;
                     acc.y += t.y;
                 }
+                if (comb) acc = awgn_at(A, csig, b * R, s, P.N, kb, acc);
                 const float2 c = make_float2(__fdiv_rn(acc.x, den), __fdiv_rn(acc.y, den));
                 const size_t o = ((size_t)b * S + s) * P.Nd + d;
                 if (COUNT) {

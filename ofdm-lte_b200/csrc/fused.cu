@@ -1,0 +1,269 @@
+// Fused stage 3 + stage "a10": tapped-delay-line Rayleigh channel, stream power, CP strip and
+// FFT/sqrt(N) in one kernel (core/rayleighchannel.py:20-58, core/ofdm_core.py:361-412,
+// core/lte_receiver.py:444-491).  The faded time-domain streams -- R x S x L complex samples per
+// subframe, 8 of the 15 GB the staged pipeline moves per 4096 subframes -- never leave the SM:
+// a CTA stages the transmitted samples of its OFDM symbol (plus the delay-spread halo) in shared
+// memory, forms the faded samples of every receive antenna directly in the FFT's register layout
+// (antenna pairs ride in the two lanes of the packed f32x2 transforms of fft2.cuh), accumulates the
+// stream power including the CP samples, transforms, and writes only the kept bins of Y.
+//
+// The AWGN of the link cannot be added here, because sigma depends on the power of the whole
+// stream; the sweep engine adds it lazily in the consumers instead (lte_crs_ls_interp_awgn,
+// lte_mrc_demap_count_awgn -- same draws as lte_rx_fft(noise_domain = 1)).
+//
+// Jakes fading is one Taylor polynomial per (antenna, tap, OFDM symbol) around the symbol centre
+// (jakes_coef_kernel with block length L); the host checks the truncation bound and reports
+// LTE_ERR_UNSUPPORTED when the Doppler spread is too large for one block per symbol, in which
+// case the caller uses the staged lte_channel_tdl + lte_rx_fft pair.
+#include <type_traits>
+
+#include "fft2.cuh"
+#include "tdl.cuh"
+
+template <int N, int K>
+__global__ void __launch_bounds__(FFT_CTA_THREADS, (N == 2048 && K == 4) ? 3 : 4)
+channel_rx_fft_kernel(const DevPlan P, const TdlParams C, const float2* __restrict__ tx,
+                      const float* __restrict__ coef_g, float2* __restrict__ Y, double* __restrict__ power, int k0,
+                      int nk, int S, int R, int R2, int halo, unsigned total) {
+    constexpr int TPF = N / FFT_ELEMS, PPC = fft2_pairs_per_cta(N);     // PPC symbols per CTA
+    constexpr int NC = 2 * K + 1;
+    extern __shared__ float4 smem4[];
+    const int p_local = threadIdx.x / TPF, j = threadIdx.x % TPF;
+    const int L = P.L, cp = P.cp;
+    const int win = halo + L;                                   // staged samples per symbol
+    const int ncoef = C.num_taps * NC * 2 * R2;                  // floats per (stream, symbol)
+    // shared memory: sbuf [PPC][fft_smem_elems] float4 | xw [PPC][win (even)] float2 | coef [PPC][ncoef] float
+    float4* sbuf = smem4 + (size_t)p_local * fft_smem_elems(N);
+    float2* xw_all = (float2*)(smem4 + (size_t)PPC * fft_smem_elems(N));
+    const int win2 = (win + 1) & ~1;
+    float2* xw = xw_all + (size_t)p_local * win2;
+    float* sc_all = (float*)(xw_all + (size_t)PPC * win2);
+    const float* sc = sc_all + (size_t)p_local * ncoef;
+    __shared__ float pw_red[FFT_CTA_THREADS / 32][2];
+
+    const unsigned f = blockIdx.x * PPC + p_local;               // = b * S + s
+    const bool valid = f < total;
+    const unsigned b = valid ? f / (unsigned)S : 0u;
+    const unsigned s = valid ? f - b * (unsigned)S : 0u;
+
+    // ---- stage the symbol's transmitted samples [s L - halo, (s+1) L) and its coefficients -------
+    if (valid) {
+        const long long m_lo = (long long)s * L - halo;
+        const float2* src = tx + (size_t)b * S * L + m_lo;      // may point before the stream for s = 0
+        for (int i = j; i < win; i += TPF) {
+            const bool ok = m_lo + i >= 0;
+            cp_async8_zfill(&xw[i], ok ? &src[i] : tx, ok);
+        }
+        const float* cg = coef_g + (size_t)f * ncoef;
+        float* scw = sc_all + (size_t)p_local * ncoef;
+        for (int i = j; i < ncoef; i += TPF) cp_async4(&scw[i], &cg[i]);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const float tau0 = (float)(cp + j) - 0.5f * (float)(L - 1);  // polynomial argument of useful sample j
+    const int RP = R2 / 2;
+    for (int p = 0; p < RP; ++p) {
+        c2 v[FFT_ELEMS];
+#pragma unroll
+        for (int e = 0; e < FFT_ELEMS; ++e) v[e] = {pk(0.f, 0.f), pk(0.f, 0.f)};
+        float pwa = 0.f, pwb = 0.f;
+        if (valid) {
+            for (int tap = 0; tap < C.num_taps; ++tap) {
+                const float* ct = sc + (size_t)tap * NC * 2 * R2 + 2 * p;
+                f2 cre[K + 1], cim[K + 1];
+#pragma unroll
+                for (int k = 0; k <= K; ++k) {
+                    const float2 a = *(const float2*)(ct + (k * 2 + 0) * R2), c = *(const float2*)(ct + (k * 2 + 1) * R2);
+                    cre[k] = pk(a.x, a.y);
+                    cim[k] = pk(c.x, c.y);
+                }
+                const float2* xt = xw + halo + cp + j - C.delay[tap];
+#pragma unroll
+                for (int e = 0; e < FFT_ELEMS; ++e) {
+                    const float tf = tau0 + (float)(e * TPF);
+                    const f2 tau = pk(tf, tf);
+                    f2 hre = cre[K], him = cim[K];
+#pragma unroll
+                    for (int k = K - 1; k >= 0; --k) { hre = fma2(hre, tau, cre[k]); him = fma2(him, tau, cim[k]); }
+                    const float2 x = xt[e * TPF];
+                    const f2 xre = pk(x.x, x.x), xim = pk(x.y, x.y), nxim = pk(-x.y, -x.y);
+                    v[e].re = fma2(hre, xre, v[e].re);
+                    v[e].re = fma2(him, nxim, v[e].re);
+                    v[e].im = fma2(hre, xim, v[e].im);
+                    v[e].im = fma2(him, xre, v[e].im);
+                }
+            }
+            // power of this thread's 16 useful samples ...
+            f2 acc = pk(0.f, 0.f);
+#pragma unroll
+            for (int e = 0; e < FFT_ELEMS; ++e) { acc = fma2(v[e].re, v[e].re, acc); acc = fma2(v[e].im, v[e].im, acc); }
+            // ... and of its cyclic-prefix samples, which only enter the stream power
+            // (core/channel.py:216-218 measures the whole faded stream)
+            for (int i = j; i < cp; i += TPF) {
+                const float tf = (float)i - 0.5f * (float)(L - 1);
+                const f2 tau = pk(tf, tf);
+                f2 yre = pk(0.f, 0.f), yim = pk(0.f, 0.f);
+                for (int tap = 0; tap < C.num_taps; ++tap) {
+                    const float* ct = sc + (size_t)tap * NC * 2 * R2 + 2 * p;
+                    float2 a = *(const float2*)(ct + (K * 2 + 0) * R2), c = *(const float2*)(ct + (K * 2 + 1) * R2);
+                    f2 hre = pk(a.x, a.y), him = pk(c.x, c.y);
+#pragma unroll
+                    for (int k = K - 1; k >= 0; --k) {
+                        a = *(const float2*)(ct + (k * 2 + 0) * R2);
+                        c = *(const float2*)(ct + (k * 2 + 1) * R2);
+                        hre = fma2(hre, tau, pk(a.x, a.y));
+                        him = fma2(him, tau, pk(c.x, c.y));
+                    }
+                    const float2 x = xw[halo + i - C.delay[tap]];
+                    const f2 xre = pk(x.x, x.x), xim = pk(x.y, x.y), nxim = pk(-x.y, -x.y);
+                    yre = fma2(hre, xre, yre); yre = fma2(him, nxim, yre);
+                    yim = fma2(hre, xim, yim); yim = fma2(him, xre, yim);
+                }
+                acc = fma2(yre, yre, acc);
+                acc = fma2(yim, yim, acc);
+            }
+            upk(acc, pwa, pwb);
+        }
+        // ---- stream power: reduce over the TPF threads of the symbol, one atomic per antenna ------
+        if constexpr (TPF >= 32) {
+            pwa = warp_sum(pwa);
+            pwb = warp_sum(pwb);
+            __syncthreads();                                     // pw_red free (previous pair)
+            if ((threadIdx.x & 31) == 0) { pw_red[threadIdx.x >> 5][0] = pwa; pw_red[threadIdx.x >> 5][1] = pwb; }
+            __syncthreads();
+            if (j == 0) {
+                pwa = 0.f; pwb = 0.f;
+                const int w0 = threadIdx.x >> 5;
+#pragma unroll
+                for (int q = 0; q < TPF / 32; ++q) { pwa += pw_red[w0 + q][0]; pwb += pw_red[w0 + q][1]; }
+            }
+        } else {
+#pragma unroll
+            for (int ofs = TPF / 2; ofs > 0; ofs >>= 1) {
+                pwa += __shfl_xor_sync(0xffffffffu, pwa, ofs);
+                pwb += __shfl_xor_sync(0xffffffffu, pwb, ofs);
+            }
+        }
+        const int r0 = 2 * p;
+        if (valid && j == 0) {
+            atomicAdd(&power[(size_t)b * R + r0], (double)pwa);
+            if (r0 + 1 < R) atomicAdd(&power[(size_t)b * R + r0 + 1], (double)pwb);
+        }
+
+        // ---- FFT of the useful part of both antennas, kept bins to Y --------------------------------
+        fft2_run<N, false>(v, sbuf, P.twiddle, j);
+        if (valid) {
+            const f2 scale = pk(P.inv_sqrt_n, P.inv_sqrt_n);
+            float2* o0 = Y + (((size_t)b * R + r0) * S + s) * nk;
+            float2* o1 = o0 + (size_t)S * nk;
+            const bool two = r0 + 1 < R;
+#pragma unroll
+            for (int e = 0; e < FFT_ELEMS; ++e) {
+                const int k = j + e * TPF - k0;
+                if (k >= 0 && k < nk) {
+                    float a, c, d, g;
+                    upk(mul2(v[e].re, scale), a, c);
+                    upk(mul2(v[e].im, scale), d, g);
+                    o0[k] = make_float2(a, d);
+                    if (two) o1[k] = make_float2(c, g);
+                }
+            }
+        }
+        __syncthreads();                                         // exchange buffer free for the next antenna pair
+    }
+}
+
+template <typename F> static int dispatch_n(int N, F&& f) {
+    switch (N) {
+        case 64: return f(std::integral_constant<int, 64>());
+        case 128: return f(std::integral_constant<int, 128>());
+        case 256: return f(std::integral_constant<int, 256>());
+        case 512: return f(std::integral_constant<int, 512>());
+        case 1024: return f(std::integral_constant<int, 1024>());
+        case 2048: return f(std::integral_constant<int, 2048>());
+        default: return LTE_ERR_UNSUPPORTED;
+    }
+}
+
+extern "C" int lte_channel_rx_fft(const lte_plan* p, const lte_channel_desc* ch, const lte_c32* tx,
+                                  const float* phases, lte_c32* Y, double* power, int window, int32_t B, int32_t R,
+                                  int32_t S, void* stream) {
+    if (!p || !ch || !tx || !phases || !Y || !power || B < 0 || R < 1 || R > LTE_MAX_RX || S < 1)
+        return LTE_ERR_INVALID_ARG;
+    if (ch->num_taps < 0 || ch->num_taps > LTE_MAX_TAPS) return LTE_ERR_INVALID_ARG;
+    if (ch->num_taps == 0) return LTE_ERR_UNSUPPORTED;          // identity link: lte_rx_fft with rx_div = R
+    int32_t k0, nk;
+    int rc = lte_plan_window(p, window, &k0, &nk);
+    if (rc) return rc;
+    if (B == 0) return LTE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int L = p->dev.L;
+
+    TdlParams C;
+    memset(&C, 0, sizeof(C));
+    C.num_taps = ch->num_taps;
+    int dmax = 0;
+    for (int i = 0; i < ch->num_taps; ++i) {
+        if (ch->delay[i] < 0) return LTE_ERR_INVALID_ARG;
+        C.delay[i] = ch->delay[i];
+        C.gain[i] = (float)((double)ch->gain[i] * sqrt(2.0 / LTE_JAKES_TONES));
+        if (ch->delay[i] > dmax) dmax = ch->delay[i];
+    }
+    if (dmax > 144) return LTE_ERR_UNSUPPORTED;
+    const int halo = (dmax + 1) & ~1;
+    double wmax = 0.0;
+    for (int nn = 0; nn < LTE_JAKES_TONES; ++nn) {
+        C.w_cyc[nn] = ch->doppler_hz * cos(2.0 * M_PI * (double)(nn + 1) / LTE_JAKES_TONES) / p->desc.fs;
+        if (fabs(C.w_cyc[nn]) > wmax) wmax = fabs(C.w_cyc[nn]);
+    }
+    // one polynomial block per OFDM symbol; same truncation bounds as lte_channel_tdl
+    const double x = M_PI * wmax * L;
+    int K;
+    if (x <= 4.9e-3) K = 2;
+    else if (x <= 0.075) K = 4;
+    else return LTE_ERR_UNSUPPORTED;
+    C.pb = L;
+    C.nbs = S;
+    const long long total = (long long)B * S;
+    if (total >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
+
+    const int R2 = (R + 1) & ~1;
+    const int NC = 2 * K + 1;
+    const size_t ncoef = (size_t)C.num_taps * NC * 2 * R2;
+    const size_t coef_bytes = sizeof(float) * (size_t)total * ncoef;
+    lte_plan* pm = const_cast<lte_plan*>(p);
+    if (pm->scratch_bytes < coef_bytes) {
+        if (pm->scratch) LTE_CHECK_CUDA(cudaFree(pm->scratch));
+        pm->scratch = nullptr;
+        pm->scratch_bytes = 0;
+        LTE_CHECK_CUDA(cudaMalloc(&pm->scratch, coef_bytes));
+        pm->scratch_bytes = coef_bytes;
+    }
+    float* coef = (float*)pm->scratch;
+    if (R2 != R) LTE_CHECK_CUDA(cudaMemsetAsync(coef, 0, coef_bytes, st));
+    const long long items = total * R * C.num_taps * LTE_JAKES_TONES;
+    const unsigned cgrid = (unsigned)((items + 255) / 256);
+    if (K == 2) jakes_coef_kernel<2><<<cgrid, 256, 0, st>>>(C, phases, coef, R, 1, R2, items);
+    else jakes_coef_kernel<4><<<cgrid, 256, 0, st>>>(C, phases, coef, R, 1, R2, items);
+    LTE_CHECK_CUDA(cudaGetLastError());
+
+    return dispatch_n(p->dev.N, [&](auto nn) -> int {
+        constexpr int N = decltype(nn)::value;
+        constexpr int PPC = fft2_pairs_per_cta(N);
+        const int win2 = (halo + L + 1) & ~1;
+        const size_t smem = (size_t)fft2_cta_smem_bytes(N) + (size_t)PPC * win2 * sizeof(float2) +
+                            (size_t)PPC * ncoef * sizeof(float);
+        if (smem > 200 * 1024) return LTE_ERR_UNSUPPORTED;
+        const unsigned grid = (unsigned)((total + PPC - 1) / PPC);
+        auto launch = [&](auto k) -> int {
+            LTE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k<<<grid, FFT_CTA_THREADS, smem, st>>>(p->dev, C, (const float2*)tx, coef, (float2*)Y, power, k0, nk, S, R,
+                                                   R2, halo, (unsigned)total);
+            LTE_CHECK_CUDA(cudaGetLastError());
+            return LTE_OK;
+        };
+        return K == 2 ? launch(channel_rx_fft_kernel<N, 2>) : launch(channel_rx_fft_kernel<N, 4>);
+    });
+}

@@ -17,6 +17,7 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 LTE_MAX_TAPS = 8
+LTE_ERR_UNSUPPORTED = -2
 LTE_JAKES_TONES = 16
 LTE_SLOT_SYMBOLS = 14
 LTE_MAX_RX = 8
@@ -36,7 +37,8 @@ class ChannelDesc(C.Structure):
 
 
 class AwgnDesc(C.Structure):
-    _fields_ = [('power', C.c_void_p), ('snr_lin', C.c_void_p), ('seed', C.c_uint64), ('row_id0', C.c_uint64)]
+    _fields_ = [('power', C.c_void_p), ('snr_lin', C.c_void_p), ('seed', C.c_uint64), ('row_id0', C.c_uint64),
+                ('combine', C.c_int32)]
 
 
 _P = C.c_void_p
@@ -60,6 +62,7 @@ _SIGS = {
     'lte_histogram': ([_P, _I64, C.c_float, C.c_float, _I32, _P, _P], C.c_int),
     'lte_dft_m': ([_P, _P, _P, _I32, _I32, _I64, _P], C.c_int),
     'lte_channel_tdl': ([_P, C.POINTER(ChannelDesc), _P, _P, _P, _P, _I32, _I32, _I32, _I64, _P], C.c_int),
+    'lte_channel_rx_fft': ([_P, C.POINTER(ChannelDesc), _P, _P, _P, _P, C.c_int, _I32, _I32, _I32, _P], C.c_int),
     'lte_awgn_add': ([_P, _P, _I32, _P, _P, _P, _U64, _U64, _P, _I64, _I64, _P], C.c_int),
     'lte_rx_fft': ([_P, _P, _I32, _P, _P, _P, _I32, _U64, _U64, _P, C.c_int, _I64, _I32, _P], C.c_int),
     'lte_crs_ls_interp': ([_P, _P, _P, C.c_int, C.c_int, _I64, _I32, _P], C.c_int),

@@ -218,6 +218,23 @@ class LinkEngine:
         self.launches += 2 if chan.num_taps > 0 else 1     # Jakes coefficient kernel + TDL kernel
         return faded, power
 
+    def channel_rx_fft(self, tx, chan, B, R, S, phases, window=nat.WINDOW_FULL, out=None, power=None):
+        """Fused fading channel + CP strip + FFT (T = 1): -> (Y [B*R, S, nk] noise-free, power [B, R]),
+        or None when the configuration needs the staged `channel` + `rx_fft` pair."""
+        k0, nk = self.window(window)
+        if power is None:
+            power = torch.zeros((B, R), dtype=torch.float64, device=self.device)
+        else:
+            power.zero_()
+        Y = out if out is not None else self._empty((B * R, S, nk), torch.complex64)
+        rc = nat.lib.lte_channel_rx_fft(self._plan, C.byref(chan), _ptr(tx), _ptr(phases), _ptr(Y), _ptr(power),
+                                        window, B, R, S, self._stream())
+        if rc == nat.LTE_ERR_UNSUPPORTED:
+            return None
+        nat.check(rc, 'lte_channel_rx_fft')
+        self.launches += 2                                   # Jakes coefficient kernel + fused kernel
+        return Y, power
+
     def awgn(self, x, x_div, power, snr_lin, rows, z=None, seed=0, row_id0=0, out=None):
         n = x.shape[-1]
         y = out if out is not None else self._empty((rows, n), torch.complex64)
@@ -239,10 +256,11 @@ class LinkEngine:
 
     # ------------------------------------------------------------------ stage 4
     @staticmethod
-    def awgn_desc(power, snr_lin, seed, row_id0=0):
+    def awgn_desc(power, snr_lin, seed, row_id0=0, combine=False):
         """Lazy frequency-domain AWGN: the consumers of a noise-free Y add the noise
-        lte_rx_fft(noise_domain=1) would have added (see include/lte_b200.h)."""
-        return nat.AwgnDesc(power.data_ptr(), snr_lin.data_ptr(), int(seed), int(row_id0))
+        lte_rx_fft(noise_domain=1) would have added (see include/lte_b200.h).  combine: the MRC
+        kernel draws one equivalent sample per combiner output instead of one per antenna."""
+        return nat.AwgnDesc(power.data_ptr(), snr_lin.data_ptr(), int(seed), int(row_id0), 1 if combine else 0)
 
     def estimate(self, Y, rows, S, window=nat.WINDOW_FULL, pilot_set=0, out=None, awgn=None):
         k0, nk = self.window(window)
@@ -366,8 +384,9 @@ class LinkEngine:
         return errors
 
     # ------------------------------------------------------------------ batched SIMO chain
-    def workspace(self, B, S, R, fading):
-        """Pre-allocated HBM buffers for `simo_ber` so a sweep re-uses them every step."""
+    def workspace(self, B, S, R, fading, fused=False):
+        """Pre-allocated HBM buffers for `simo_ber` so a sweep re-uses them every step
+        (fused: no buffer for the faded streams)."""
         k0, nk = self.window(nat.WINDOW_USEFUL)
         nslot = -(-S // nat.LTE_SLOT_SYMBOLS)
         n = S * self.L
@@ -380,21 +399,41 @@ class LinkEngine:
                   H=self._empty((B * R, nslot, nk), torch.complex64),
                   errors=torch.zeros(B, dtype=torch.int64, device=self.device))
         if fading:
-            ws['faded'] = self._empty((B, R, n), torch.complex64)
+            if not fused:
+                ws['faded'] = self._empty((B, R, n), torch.complex64)
             ws['phases'] = self._empty((B, R * nat.LTE_MAX_TAPS * nat.LTE_JAKES_TONES), torch.float32)
         return ws
 
-    def simo_ber(self, ws, chan, snr_lin_rows, seed, stream_id0=0, idx=None, nbits=None, noise_domain=1):
+    def simo_ber(self, ws, chan, snr_lin_rows, seed, stream_id0=0, idx=None, nbits=None, noise_domain=1,
+                 fused=False):
         """One pass of the SIMO-MRC link chain over B independent streams.
 
         ws: workspace(); snr_lin_rows: float32 [B*R] linear SNR per (stream, antenna);
         idx: transmitted symbol indices [B, S*Nd] or None to draw them with Philox
         keyed (seed, stream_id0 + b).  Returns the int64 [B] bit-error counts (in ws).
+        noise_domain: 0 time-domain AWGN, 1 on the kept bins in the RX epilogue, 2 the same draws
+        added lazily by the CRS / MRC kernels, 3 like 2 but one equivalent draw per MRC output
+        (statistically identical, 1/R of the generator work).  fused: fading channel + RX FFT in
+        one kernel (the faded streams are never written; needs noise_domain 2 or 3 -- 1 is promoted
+        to 2; falls back to the staged kernels when lte_channel_rx_fft reports the configuration
+        unsupported).
         """
         B, S, R = ws['B'], ws['S'], ws['R']
         if idx is None:
             idx = self.random_indices(B, S, seed, stream_id0, out=ws['idx'])
         tx, _, _ = self.modulate(S, idx=idx, want_stats=False, out=ws['tx'])
+        if fused and chan.num_taps > 0:
+            per = R * chan.num_taps * nat.LTE_JAKES_TONES
+            ph = self.random_phases(B, per, seed, stream_id0, out=ws['phases'].view(-1)[:B * per].view(B, per))
+            got = self.channel_rx_fft(tx, chan, B, R, S, ph, nat.WINDOW_USEFUL, out=ws['Y'], power=ws['power'])
+            if got is not None:
+                Y, power = got
+                awgn = self.awgn_desc(power, snr_lin_rows, seed, stream_id0 * R, combine=(noise_domain == 3))
+                H = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, out=ws['H'], awgn=awgn)
+                return self.mrc_demap_count(Y, H, idx, B, R, S, nbits=nbits, errors=ws['errors'], awgn=awgn)
+            noise_domain = 3 if noise_domain == 3 else 2
+            if 'faded' not in ws:
+                ws['faded'] = self._empty((B, R, S * self.L), torch.complex64)
         if chan.num_taps > 0:
             per = R * chan.num_taps * nat.LTE_JAKES_TONES
             ph = self.random_phases(B, per, seed, stream_id0, out=ws['phases'].view(-1)[:B * per].view(B, per))
@@ -403,9 +442,9 @@ class LinkEngine:
         else:
             _, power = self.channel(tx, chan, B, R, power=ws['power'])
             rx, div = tx, R
-        if noise_domain == 2:       # noise-free grid, AWGN added lazily by the consumers (same draws as 1)
+        if noise_domain >= 2:       # noise-free grid, AWGN added lazily by the consumers (2: same draws as 1)
             Y = self.rx_fft(rx, B * R, S, nat.WINDOW_USEFUL, rx_div=div, out=ws['Y'])
-            awgn = self.awgn_desc(power, snr_lin_rows, seed, stream_id0 * R)
+            awgn = self.awgn_desc(power, snr_lin_rows, seed, stream_id0 * R, combine=(noise_domain == 3))
             H = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, out=ws['H'], awgn=awgn)
             return self.mrc_demap_count(Y, H, idx, B, R, S, nbits=nbits, errors=ws['errors'], awgn=awgn)
         Y = self.rx_fft(rx, B * R, S, nat.WINDOW_USEFUL, rx_div=div, power=power, snr_lin=snr_lin_rows, seed=seed,

@@ -45,8 +45,9 @@ def run_sweep(count_batch, n_snr, n_trials, bits_per_stream, batch_trials=256, r
 
 
 def simo_sweep(engine, chan, snr_db, n_trials, num_rx, symbols_per_stream=14, seed=0, batch_trials=256,
-               rank=0, world=1, noise_domain=1):
-    """BER of the SIMO-MRC chain at every SNR point, `n_trials` independent streams per point."""
+               rank=0, world=1, noise_domain=1, fused=False):
+    """BER of the SIMO-MRC chain at every SNR point, `n_trials` independent streams per point.
+    noise_domain / fused: see LinkEngine.simo_ber."""
     n_snr = len(snr_db)
     S, R = symbols_per_stream, num_rx
     snr_lin = torch.tensor([10 ** (s / 10) for s in snr_db], dtype=torch.float32, device=engine.device)
@@ -56,10 +57,10 @@ def simo_sweep(engine, chan, snr_db, n_trials, num_rx, symbols_per_stream=14, se
         B = n * n_snr
         if state.get('B') != B:
             state['B'] = B
-            state['ws'] = engine.workspace(B, S, R, fading=chan.num_taps > 0)
+            state['ws'] = engine.workspace(B, S, R, fading=chan.num_taps > 0, fused=fused)
             state['snr_rows'] = snr_lin.repeat(n).repeat_interleave(R).contiguous()
         return engine.simo_ber(state['ws'], chan, state['snr_rows'], seed, stream_id0=trial_lo * n_snr,
-                               noise_domain=noise_domain).clone()
+                               noise_domain=noise_domain, fused=fused).clone()
 
     return run_sweep(count_batch, n_snr, n_trials, S * engine.Nd * engine.bps, batch_trials, rank, world,
                      engine.device)

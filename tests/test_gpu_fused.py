@@ -1,0 +1,107 @@
+"""Fused fading-channel + RX-FFT kernel (lte_channel_rx_fft): the faded streams never reach HBM.
+
+Checked against (a) the oracle on the reference's own phase draws, (b) the staged kernels it
+replaces, and (c) through the error counts of the sweep path built on it."""
+import numpy as np
+import pytest
+import torch
+
+from cases import SIMO_CASES
+from gpu_chain import draws_to_device
+from helpers import golden_bits, load_golden, numerology, reference_draws, rel_err
+from oracle import lte_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FADING = [c for c in SIMO_CASES if c['ch'] == 'rayleigh_mp']
+
+
+def _engine(num):
+    from lte_b200 import LinkEngine
+    return LinkEngine(num.N, num.Nc, num.cp_length, num.bits_per_symbol, num.fs)
+
+
+@pytest.mark.parametrize('case', FADING, ids=[c['name'] for c in FADING])
+def test_fused_grid_and_power_match_oracle(case):
+    from lte_b200 import _native as nat
+    from lte_b200 import chan_for
+    g = load_golden(case['name'])
+    num = numerology(case)
+    bits = golden_bits(g)
+    eng = _engine(num)
+    R = case['R']
+    S = eng.symbols_for_bits(len(bits))
+    idx = eng.bits_to_indices(torch.from_numpy(bits.astype(np.uint8)).cuda()[None, :], len(bits), S)
+    tx, _, _ = eng.modulate(S, idx=idx)
+    chan = chan_for('rayleigh_mp', num.fs, case['prof'], 2.0, case['v'])
+    phases, z = reference_draws(case, S * num.L, R)
+    u, _ = draws_to_device(phases, z)
+    got = eng.channel_rx_fft(tx, chan, 1, R, S, u, nat.WINDOW_FULL)
+    assert got is not None
+    Y, power = got
+    # oracle: fp64 time-domain TDL of the oracle's own TX signal, then CP strip + FFT
+    sig, _ = O.modulate_stream(bits, num)
+    delays, gains = O.itu_taps(case['prof'], num.fs)
+    fD = O.doppler_hz(2.0, case['v'])
+    Yn, pw = Y.cpu().numpy(), power.cpu().numpy().reshape(-1)
+    for r in range(R):
+        faded = O.rayleigh_filter(sig, num.fs, fD, delays, gains, phases[r])
+        want = O.rx_fft_stream(faded, num)
+        assert rel_err(Yn[r], want) < 1e-5
+        assert abs(pw[r] / np.sum(np.abs(faded) ** 2) - 1) < 1e-5
+    # the staged kernels give the same grid (to fp32 rounding) and the useful window is a slice of it
+    faded_d, power_s = eng.channel(tx, chan, 1, R, phases=u)
+    Ys = eng.rx_fft(faded_d.view(R, -1), R, S, nat.WINDOW_FULL)
+    assert rel_err(Yn, Ys.cpu().numpy()) < 2e-6
+    assert np.allclose(pw, power_s.cpu().numpy().reshape(-1), rtol=2e-6)
+    k0, nk = eng.window(nat.WINDOW_USEFUL)
+    Yu, _ = eng.channel_rx_fft(tx, chan, 1, R, S, u, nat.WINDOW_USEFUL)
+    assert torch.equal(Yu, Y[:, :, k0:k0 + nk])
+
+
+@pytest.mark.parametrize('bw,mod,R,prof,v', [(1.25, '16-QAM', 2, 'Pedestrian_A', 3.0), (5.0, '64-QAM', 4, 'Vehicular_A', 60.0),
+                                             (2.5, 'QPSK', 1, 'Pedestrian_B', 3.0), (10.0, '16-QAM', 3, 'Vehicular_B', 120.0),
+                                             (20.0, '64-QAM', 4, 'Pedestrian_A', 3.0)])
+def test_fused_sweep_counts_track_the_staged_path(bw, mod, R, prof, v):
+    """Same draws, same algorithm, different fp32 evaluation order of the fading polynomial: the
+    per-stream error counts may differ only through symbols that sit on a slicer boundary."""
+    from config import LTEConfig
+    from lte_b200 import LinkEngine, chan_for
+    cfg = LTEConfig(bw, 15.0, mod)
+    eng = LinkEngine.from_config(cfg)
+    chan = chan_for('rayleigh_mp', cfg.fs, prof, 2.0, v)
+    B, S = 12, 15
+    ws = eng.workspace(B, S, R, fading=True)
+    wf = eng.workspace(B, S, R, fading=True, fused=True)
+    assert 'faded' not in wf
+    snr = torch.tensor([10 ** (s / 10) for s in (4.0, 12.0, 22.0)], dtype=torch.float32, device='cuda')
+    rows = snr.repeat(B // 3).repeat_interleave(R).contiguous()
+    e_staged = eng.simo_ber(ws, chan, rows, seed=4, stream_id0=11, noise_domain=1).clone()
+    e_fused = eng.simo_ber(wf, chan, rows, seed=4, stream_id0=11, fused=True).clone()
+    assert 'faded' not in wf                                        # the fused kernel really ran
+    bits = S * eng.Nd * eng.bps
+    assert int(e_staged.sum()) > 0
+    assert int((e_staged - e_fused).abs().max()) <= max(2, bits // 20000)
+    assert abs(int(e_staged.sum()) - int(e_fused.sum())) <= max(3, int(e_staged.sum()) // 2000)
+
+
+def test_fused_reports_unsupported_and_sweep_falls_back():
+    from config import LTEConfig
+    from lte_b200 import LinkEngine, chan_for
+    from lte_b200 import _native as nat
+    cfg = LTEConfig(1.25, 15.0, 'QPSK')
+    eng = LinkEngine.from_config(cfg)
+    B, S, R = 4, 14, 2
+    tx = torch.zeros((B, S * eng.L), dtype=torch.complex64, device='cuda')
+    ph = torch.zeros((B, R * 8 * 16), dtype=torch.float32, device='cuda')
+    awgn = chan_for('awgn', cfg.fs, 'Pedestrian_A', 2.0, 0.0)
+    assert eng.channel_rx_fft(tx, awgn, B, R, S, ph) is None          # identity link
+    fast = chan_for('rayleigh_mp', cfg.fs, 'Vehicular_A', 2.0, 350.0)  # fD = 648 Hz: beyond one block per symbol
+    assert eng.channel_rx_fft(tx, fast, B, R, S, ph) is None
+    # the sweep path silently uses the staged kernels then, with the same lazy-noise draws
+    wf = eng.workspace(B, S, R, fading=True, fused=True)
+    ws = eng.workspace(B, S, R, fading=True)
+    rows = torch.full((B * R,), 10.0, dtype=torch.float32, device='cuda')
+    a = eng.simo_ber(wf, fast, rows, seed=1, fused=True).clone()
+    b = eng.simo_ber(ws, fast, rows, seed=1, noise_domain=1).clone()
+    assert torch.equal(a, b) and 'faded' in wf

@@ -23,23 +23,24 @@ def main():
     ap.add_argument('--reps', type=int, default=5)
     ap.add_argument('--profile', default=bench.PROFILE)
     ap.add_argument('--velocity', type=float, default=bench.VELOCITY)
+    ap.add_argument('--fused', action='store_true', help='stages of the fused pipeline')
     a = ap.parse_args()
     dev = torch.device('cuda', 0)
     cfg = LTEConfig(20.0, 15.0, '64-QAM')
     eng = LinkEngine.from_config(cfg, device=dev)
     chan = chan_for('rayleigh_mp', cfg.fs, a.profile, bench.FC_GHZ, a.velocity)
     B, S, R = a.trials * 16, 14, 4
-    ws = eng.workspace(B, S, R, fading=True)
+    ws = eng.workspace(B, S, R, fading=True, fused=a.fused)
     snr = torch.tensor([10 ** (s / 10) for s in bench.SNR_POINTS], dtype=torch.float32, device=dev)
     snr_rows = snr.repeat(a.trials).repeat_interleave(R).contiguous()
     idx = eng.random_indices(B, S, 1, 0)
     nbits = S * eng.Nd * eng.bps
-    eng.simo_ber(ws, chan, snr_rows, 1, 0, idx=idx, nbits=nbits)      # populate every buffer
+    eng.simo_ber(ws, chan, snr_rows, 1, 0, idx=idx, nbits=nbits, fused=a.fused)      # populate every buffer
     res = bench.time_stages(eng, ws, chan, snr_rows, idx, nbits, 1, B, S, R, nat, torch, dev, reps=a.reps,
-                            only=a.stages or None)
+                            only=a.stages or None, fused=a.fused)
     sb = bench.stage_bytes()
     for k, v in res.items():
-        v['frac'] = sb[k] * B / (v['ms'] * 1e-3) / 1e9 / 6467.7
+        v['frac'] = sb[k.replace('_awgn', '')] * B / (v['ms'] * 1e-3) / 1e9 / 6467.7
     print(json.dumps(res))
 
 
