@@ -1,5 +1,7 @@
 // Stage 4 (CRS LS + linear interpolation), stage 5 (ZF / MRC) and stage 6 (hard demap +
 // bit-error count), plus the bit <-> symbol-index helpers of the reference-facing API.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------ bits <-> indices
@@ -292,13 +294,21 @@ extern "C" int lte_equalize_zf(const lte_plan* p, const lte_c32* Y, const lte_c3
 
 // MRC (core/ofdm_core.py:1484-1532): thread = (stream, data bin); H of the slot is held in
 // registers while the thread walks the slot's symbols, so H is read once per 14 symbols.
+#ifndef MRC_CHUNK
+#define MRC_CHUNK 1
+#endif
 template <int R, bool COUNT, bool NOISY>
 __global__ void __launch_bounds__(128)
 mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restrict__ H, float2* __restrict__ out,
            const uint8_t* __restrict__ idx_tx, unsigned long long* __restrict__ errors, int k0, int nk, int S,
-           int nslot, long long nbits, int gx, const AwgnArgs A) {
-    const long long b = blockIdx.x / gx;
-    const int d = (blockIdx.x % gx) * blockDim.x + threadIdx.x;
+           int nslot, long long nbits, int gx, int sps, const AwgnArgs A) {
+    // block = (stream b, part of a slot, chunk of 128 data bins); a part is `sps` consecutive symbols
+    const int pps = LTE_SLOT_SYMBOLS / sps, nparts = nslot * pps;
+    const int chunk = blockIdx.x % gx;
+    const long long bp = blockIdx.x / gx;
+    const long long b = bp / nparts;
+    const int part = (int)(bp - b * nparts);
+    const int d = chunk * blockDim.x + threadIdx.x;
     unsigned int e = 0;
     if (d < P.Nd) {
         const int kb = P.data_idx[d];
@@ -308,7 +318,8 @@ mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restri
 #pragma unroll
             for (int r = 0; r < R; ++r) sigma[r] = lte_sigma(A.power[b * R + r], A.n_stream, A.snr_lin[b * R + r]);
         }
-        for (int slot = 0; slot < nslot; ++slot) {
+        {
+            const int slot = part / pps;
             float2 h[R];
             float den = 0.f;
 #pragma unroll
@@ -326,25 +337,57 @@ mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restri
                 for (int r = 0; r < R; ++r) csig = fmaf(cabs2(h[r]), sigma[r] * sigma[r], csig);
                 csig = sqrtf(csig);
             }
-            const int s_end = min(S, (slot + 1) * LTE_SLOT_SYMBOLS);
-            for (int s = slot * LTE_SLOT_SYMBOLS; s < s_end; ++s) {
-                float2 acc = make_float2(0.f, 0.f);
+            const int s0 = slot * LTE_SLOT_SYMBOLS + (part - slot * pps) * sps;
+            const int s_end = min(S, s0 + sps);
+            // register double buffering: the loads of the next group of symbols are in flight while this
+            // group is combined, sliced and (noisy variants) gets its Philox / Box-Muller samples
+            const float2* yb = Y + ((size_t)b * R * S) * nk + kk;
+            constexpr int CH = MRC_CHUNK;                   // symbols per prefetch group
+            float2 yn[CH][R];
+            uint8_t in[CH];
+            auto fetch = [&](int sf) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    float2 y = Y[(((size_t)b * R + r) * S + s) * nk + kk];
-                    if (NOISY && !comb) y = awgn_at(A, sigma[r], b * R + r, s, P.N, kb, y);
-                    const float2 t = cmulc(h[r], y);
-                    acc.x += t.x;
-                    acc.y += t.y;
+                for (int c = 0; c < CH; ++c) {
+                    in[c] = 0;
+                    if (sf + c < s_end) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) yn[c][r] = yb[((size_t)r * S + sf + c) * nk];
+                        if (COUNT) in[c] = idx_tx[((size_t)b * S + sf + c) * P.Nd + d];
+                    }
                 }
-                if (comb) acc = awgn_at(A, csig, b * R, s, P.N, kb, acc);
-                const float2 c = make_float2(__fdiv_rn(acc.x, den), __fdiv_rn(acc.y, den));
-                const size_t o = ((size_t)b * S + s) * P.Nd + d;
-                if (COUNT) {
-                    const long long q = (long long)s * P.Nd + d;
-                    e += bit_errors(slice_symbol(P, c), idx_tx[o], P.bps, nbits - q * P.bps);
-                } else {
-                    out[o] = c;
+            };
+            fetch(s0);
+            for (int sg = s0; sg < s_end; sg += CH) {
+                float2 y[CH][R];
+                uint8_t ic[CH];
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    ic[c] = in[c];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) y[c][r] = yn[c][r];
+                }
+                fetch(sg + CH);
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int s = sg + c;
+                    if (s < s_end) {
+                        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            if (NOISY && !comb) y[c][r] = awgn_at(A, sigma[r], b * R + r, s, P.N, kb, y[c][r]);
+                            const float2 t = cmulc(h[r], y[c][r]);
+                            acc.x += t.x;
+                            acc.y += t.y;
+                        }
+                        if (comb) acc = awgn_at(A, csig, b * R, s, P.N, kb, acc);
+                        const float2 cc = make_float2(__fdiv_rn(acc.x, den), __fdiv_rn(acc.y, den));
+                        if (COUNT) {
+                            const long long q = (long long)s * P.Nd + d;
+                            e += bit_errors(slice_symbol(P, cc), ic[c], P.bps, nbits - q * P.bps);
+                        } else {
+                            out[((size_t)b * S + s) * P.Nd + d] = cc;
+                        }
+                    }
                 }
             }
         }
@@ -364,18 +407,25 @@ static int launch_mrc(const lte_plan* p, const lte_c32* Y, const lte_c32* H, lte
     if (B == 0) return LTE_OK;
     const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
     const int gx = (p->dev.Nd + 127) / 128;
-    const unsigned grid = (unsigned)((long long)gx * B);
+    // symbols per thread: H of the slot is re-read once per part (from L2); short parts expose more
+    // parallelism, which the noisy variants need to hide the generator's dependent chains
+    int sps = LTE_SLOT_SYMBOLS;
+    if (getenv("LTE_MRC_SPS")) sps = atoi(getenv("LTE_MRC_SPS"));
+    if (sps != 1 && sps != 2 && sps != 7 && sps != 14) return LTE_ERR_INVALID_ARG;
+    const long long grid_ll = (long long)gx * B * nslot * (LTE_SLOT_SYMBOLS / sps);
+    if (grid_ll >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
+    const unsigned grid = (unsigned)grid_ll;
     cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_MRC(RR)                                                                                          \
     case RR:                                                                                                    \
         if (awgn)                                                                                               \
             mrc_kernel<RR, COUNT, true><<<grid, 128, 0, st>>>(p->dev, (const float2*)Y, (const float2*)H,      \
                                                               (float2*)out, idx_tx, errors, k0, nk, S, nslot,  \
-                                                              nbits, gx, A);                                    \
+                                                              nbits, gx, sps, A);                                    \
         else                                                                                                    \
             mrc_kernel<RR, COUNT, false><<<grid, 128, 0, st>>>(p->dev, (const float2*)Y, (const float2*)H,     \
                                                                (float2*)out, idx_tx, errors, k0, nk, S, nslot, \
-                                                               nbits, gx, A);                                   \
+                                                               nbits, gx, sps, A);                                   \
         break;
     switch (R) {
         LAUNCH_MRC(1) LAUNCH_MRC(2) LAUNCH_MRC(3) LAUNCH_MRC(4) LAUNCH_MRC(5) LAUNCH_MRC(6) LAUNCH_MRC(7)

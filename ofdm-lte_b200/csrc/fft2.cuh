@@ -27,6 +27,12 @@ __device__ __forceinline__ c2 csub2(c2 a, c2 b) { return {sub2(a.re, b.re), sub2
 __device__ __forceinline__ c2 cmul2(c2 a, c2 w) {
     return {sub2(mul2(a.re, w.re), mul2(a.im, w.im)), fma2(a.re, w.im, mul2(a.im, w.re))};
 }
+// a * w with the same scalar twiddle for both transforms: the broadcast operands fold into the
+// scalar form of FFMA2 / FMUL2, and the twiddle powers themselves stay on scalar (full-rate) ops
+__device__ __forceinline__ c2 cmul2s(c2 a, float2 w) {
+    const f2 wx = pk(w.x, w.x), wy = pk(w.y, w.y), nwy = pk(-w.y, -w.y);
+    return {fma2(a.re, wx, mul2(a.im, nwy)), fma2(a.re, wy, mul2(a.im, wx))};
+}
 // a + (-j) b forward / a + (+j) b inverse, and the matching differences, without materialising j*b
 template <bool INV> __device__ __forceinline__ c2 add_mj(c2 a, c2 b) {
     return INV ? c2{sub2(a.re, b.im), add2(a.im, b.re)} : c2{add2(a.re, b.im), sub2(a.im, b.re)};
@@ -97,14 +103,13 @@ __device__ __forceinline__ void fft2_pass(c2 (&v)[FFT_ELEMS], const float2* __re
         for (int t = 0; t < R; ++t) a[t] = v[q + Q * t];
         if constexpr (NS > 1) {
             const int k = (j + q * TPF) & (NS - 1);
-            float2 w1 = __ldg(&tw[k * (N / (NS * R))]);
-            if (INV) w1.y = -w1.y;
-            c2 w[R];
-            w[1] = {pk(w1.x, w1.x), pk(w1.y, w1.y)};
+            float2 w[R];
+            w[1] = __ldg(&tw[k * (N / (NS * R))]);
+            if (INV) w[1].y = -w[1].y;
 #pragma unroll
-            for (int t = 2; t < R; ++t) w[t] = cmul2(w[t >> 1], w[(t + 1) >> 1]);
+            for (int t = 2; t < R; ++t) w[t] = cmul(w[t >> 1], w[(t + 1) >> 1]);
 #pragma unroll
-            for (int t = 1; t < R; ++t) a[t] = cmul2(a[t], w[t]);
+            for (int t = 1; t < R; ++t) a[t] = cmul2s(a[t], w[t]);
         }
         dftRp<R, INV>(a);
 #pragma unroll
