@@ -331,7 +331,7 @@ extern "C" int lte_channel_tdl(const lte_plan* p, const lte_channel_desc* ch, co
     }
     float* coef = (float*)pm->scratch;
     if (R2 != R) LTE_CHECK_CUDA(cudaMemsetAsync(coef, 0, coef_bytes, st));   // padding antennas stay zero
-    const long long items = (long long)B * C.nbs * R * T * C.num_taps * LTE_JAKES_TONES;
+    const long long items = (long long)B * C.nbs * R * T * C.num_taps;
     const unsigned cgrid = (unsigned)((items + 255) / 256);
     if (K == 2) jakes_coef_kernel<2><<<cgrid, 256, 0, st>>>(C, phases, coef, R, T, R2, items);
     else jakes_coef_kernel<4><<<cgrid, 256, 0, st>>>(C, phases, coef, R, T, R2, items);

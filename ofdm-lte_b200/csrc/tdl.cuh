@@ -25,66 +25,62 @@ struct TdlParams {
 // slot k = 0..K:   sum_n g e^{j theta_n} (j x_n)^k / k!      (value coefficients)
 // slot K+k, k>=1:  k times slot k                           (derivative coefficients)
 // with theta_n = 2 pi (w_n m_c + u_n) reduced in fp64 at the block centre m_c.
-// work item = (b, blk, triple, tone), triple = (r*T + t)*taps + tap as in `phases`;
-// 16 consecutive lanes reduce one sum.
+// work item = (b, blk, triple), triple = (r*T + t)*taps + tap as in `phases`; the thread walks the
+// 16 tones itself (no shuffles; the 64 bytes of phases are four 128-bit loads).
 template <int K>
 __global__ void __launch_bounds__(256)
 jakes_coef_kernel(const TdlParams C, const float* __restrict__ phases, float* __restrict__ coef, int R, int T,
                   int R2, long long total_items) {
     constexpr int NC = 2 * K + 1;
     const int nlt = R * T * C.num_taps;
-    const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (b*nbs + blk)*nlt + trip
+    if (it >= total_items) return;
+    const int trip = (int)(it % nlt);
+    const long long q = it / nlt;                       // b*nbs + blk
+    const int blk = (int)(q % C.nbs);
+    const long long b = q / C.nbs;
+    const double mc = (double)blk * C.pb + 0.5 * (C.pb - 1);
+    const float4* up = (const float4*)(phases + ((size_t)b * nlt + trip) * LTE_JAKES_TONES);
+    float u[LTE_JAKES_TONES];
+#pragma unroll
+    for (int i = 0; i < LTE_JAKES_TONES / 4; ++i) {
+        const float4 v = __ldg(&up[i]);
+        u[4 * i] = v.x; u[4 * i + 1] = v.y; u[4 * i + 2] = v.z; u[4 * i + 3] = v.w;
+    }
     float2 a[K + 1];
 #pragma unroll
     for (int k = 0; k <= K; ++k) a[k] = make_float2(0.f, 0.f);
-    long long q = 0;
-    int trip = 0;
-    if (it < total_items) {
-        const int tone = (int)(it & (LTE_JAKES_TONES - 1));
-        const long long grp = it >> 4;                  // (b*nbs + blk)*nlt + trip
-        trip = (int)(grp % nlt);
-        q = grp / nlt;                                  // b*nbs + blk
-        const int blk = (int)(q % C.nbs);
-        const long long b = q / C.nbs;
-        const double mc = (double)blk * C.pb + 0.5 * (C.pb - 1);
-        const float u = phases[((size_t)b * nlt + trip) * LTE_JAKES_TONES + tone];
-        double turns = C.w_cyc[tone] * mc + (double)u;
+#pragma unroll 4
+    for (int tone = 0; tone < LTE_JAKES_TONES; ++tone) {
+        double turns = C.w_cyc[tone] * mc + (double)u[tone];
         turns -= floor(turns);
         float sn, cs;
         sincospif(2.0f * (float)turns, &sn, &cs);
         const float x = (float)(6.283185307179586 * C.w_cyc[tone]);   // rad / sample
         float2 term = make_float2(cs, sn);
-        a[0] = term;
+        a[0].x += term.x;
+        a[0].y += term.y;
 #pragma unroll
         for (int k = 1; k <= K; ++k) {
             const float f = x / (float)k;
             term = make_float2(-term.y * f, term.x * f);
-            a[k] = term;
+            a[k].x += term.x;
+            a[k].y += term.y;
         }
     }
+    const int tap = trip % C.num_taps, rt = trip / C.num_taps;
+    const int t = rt % T, r = rt / T;
+    const float g = C.gain[tap];
+    float* c = coef + ((((size_t)q * T + t) * C.num_taps + tap) * NC) * 2 * R2 + r;
 #pragma unroll
     for (int k = 0; k <= K; ++k) {
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-            a[k].x += __shfl_xor_sync(0xffffffffu, a[k].x, o);
-            a[k].y += __shfl_xor_sync(0xffffffffu, a[k].y, o);
-        }
+        c[(k * 2 + 0) * R2] = a[k].x * g;
+        c[(k * 2 + 1) * R2] = a[k].y * g;
     }
-    if (it < total_items && (it & (LTE_JAKES_TONES - 1)) == 0) {
-        const int tap = trip % C.num_taps, rt = trip / C.num_taps;
-        const int t = rt % T, r = rt / T;
-        const float g = C.gain[tap];
-        float* c = coef + ((((size_t)q * T + t) * C.num_taps + tap) * NC) * 2 * R2 + r;
 #pragma unroll
-        for (int k = 0; k <= K; ++k) {
-            c[(k * 2 + 0) * R2] = a[k].x * g;
-            c[(k * 2 + 1) * R2] = a[k].y * g;
-        }
-#pragma unroll
-        for (int k = 1; k <= K; ++k) {
-            c[((K + k) * 2 + 0) * R2] = a[k].x * g * (float)k;
-            c[((K + k) * 2 + 1) * R2] = a[k].y * g * (float)k;
-        }
+    for (int k = 1; k <= K; ++k) {
+        c[((K + k) * 2 + 0) * R2] = a[k].x * g * (float)k;
+        c[((K + k) * 2 + 1) * R2] = a[k].y * g * (float)k;
     }
 }
 

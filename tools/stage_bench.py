@@ -35,7 +35,7 @@ def main():
     snr_rows = snr.repeat(a.trials).repeat_interleave(R).contiguous()
     idx = eng.random_indices(B, S, 1, 0)
     nbits = S * eng.Nd * eng.bps
-    eng.simo_ber(ws, chan, snr_rows, 1, 0, idx=idx, nbits=nbits, fused=a.fused)      # populate every buffer
+    eng.simo_ber(ws, chan, snr_rows, 1, 0, idx=idx, nbits=nbits, fused=a.fused, noise_domain=3 if a.fused else 1)      # populate every buffer
     res = bench.time_stages(eng, ws, chan, snr_rows, idx, nbits, 1, B, S, R, nat, torch, dev, reps=a.reps,
                             only=a.stages or None, fused=a.fused)
     sb = bench.stage_bytes()
