@@ -137,6 +137,13 @@ crs_ls_interp_kernel(const DevPlan P, const float2* __restrict__ Y, float2* __re
         hp[i] = cmul(yp, pinv[i]);
     }
     __syncthreads();
+    // np.linspace step of every pilot-to-pilot segment, (b - a) / div, once per segment
+    float2* step = hp + P.Np;
+    for (int i = threadIdx.x; i < cnt - 1; i += blockDim.x) {
+        const float div = (float)(pbin[i + 1] - pbin[i]);
+        step[i] = make_float2(__fdiv_rn(hp[i + 1].x - hp[i].x, div), __fdiv_rn(hp[i + 1].y - hp[i].y, div));
+    }
+    __syncthreads();
     const int16_t* seg = P.pset_seg + (size_t)set * P.N;
     float2* h = H + ((size_t)row * nslot + slot) * nk;
     for (int kk = threadIdx.x; kk < nk; kk += blockDim.x) {
@@ -146,11 +153,11 @@ crs_ls_interp_kernel(const DevPlan P, const float2* __restrict__ Y, float2* __re
         if (lo < 0) v = hp[0];
         else if (lo >= cnt - 1) v = hp[cnt - 1];
         else {
-            const int i1 = pbin[lo], i2 = pbin[lo + 1];
-            const float2 a = hp[lo], b = hp[lo + 1];
-            const float div = (float)(i2 - i1), t = (float)(k - i1);
+            const int i1 = pbin[lo];
+            const float2 a = hp[lo], st = step[lo];
+            const float t = (float)(k - i1);
             // np.linspace: start + i * (delta / div)
-            v = make_float2(fmaf(t, __fdiv_rn(b.x - a.x, div), a.x), fmaf(t, __fdiv_rn(b.y - a.y, div), a.y));
+            v = make_float2(fmaf(t, st.x, a.x), fmaf(t, st.y, a.y));
             if (k == i1) v = a;
         }
         h[kk] = v;
@@ -169,7 +176,7 @@ static int launch_crs(const lte_plan* p, const lte_c32* Y, lte_c32* H, int windo
     if (rows == 0) return LTE_OK;
     const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
     const unsigned grid = (unsigned)(rows * nslot);
-    const size_t smem = sizeof(float2) * p->dev.Np;
+    const size_t smem = 2 * sizeof(float2) * p->dev.Np;
     if (awgn)
         crs_ls_interp_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(p->dev, (const float2*)Y, (float2*)H, k0,
                                                                              nk, pilot_set, S, nslot, A);
