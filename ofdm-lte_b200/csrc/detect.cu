@@ -204,9 +204,10 @@ extern "C" int lte_crs_ls_interp_awgn(const lte_plan* p, const lte_c32* Y, lte_c
 // tie at y == 0 picks the lower level (16/64-QAM) or the positive one (QPSK).
 __device__ __forceinline__ int slice_axis(const DevPlan& P, float y) {
     if (P.nlev == 2) return y < 0.f ? 1 : 0;
-    int l = 0;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) l += (i < P.nlev - 1 && y > P.thr[i]) ? 1 : 0;
+    // number of thresholds below y by bisection; unused entries of thr[] are +inf (plan.cu)
+    int l = (y > P.thr[3]) ? 4 : 0;
+    l += (y > P.thr[l + 1]) ? 2 : 0;
+    l += (y > P.thr[l]) ? 1 : 0;
     return l;
 }
 __device__ __forceinline__ int slice_symbol(const DevPlan& P, float2 y) {
@@ -335,6 +336,7 @@ mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restri
                 den += cabs2(h[r]);
             }
             den += 1e-10f;
+            const float inv_den = __frcp_rn(den);
             // combined mode: sum_r conj(h_r) sigma_r w_r with independent unit normals w_r is one complex
             // normal of standard deviation sqrt(sum_r |h_r|^2 sigma_r^2) per component
             float csig = 0.f;
@@ -349,6 +351,8 @@ mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restri
             // register double buffering: the loads of the next group of symbols are in flight while this
             // group is combined, sliced and (noisy variants) gets its Philox / Box-Muller samples
             const float2* yb = Y + ((size_t)b * R * S) * nk + kk;
+            const int sym_bits = P.Nd * P.bps;
+            const long long valid0 = nbits - ((long long)s0 * P.Nd + d) * P.bps;   // bits left from symbol s0 on
             constexpr int CH = MRC_CHUNK;                   // symbols per prefetch group
             float2 yn[CH][R];
             uint8_t in[CH];
@@ -387,10 +391,9 @@ mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restri
                             acc.y += t.y;
                         }
                         if (comb) acc = awgn_at(A, csig, b * R, s, P.N, kb, acc);
-                        const float2 cc = make_float2(__fdiv_rn(acc.x, den), __fdiv_rn(acc.y, den));
+                        const float2 cc = make_float2(acc.x * inv_den, acc.y * inv_den);
                         if (COUNT) {
-                            const long long q = (long long)s * P.Nd + d;
-                            e += bit_errors(slice_symbol(P, cc), ic[c], P.bps, nbits - q * P.bps);
+                            e += bit_errors(slice_symbol(P, cc), ic[c], P.bps, valid0 - (long long)(s - s0) * sym_bits);
                         } else {
                             out[((size_t)b * S + s) * P.Nd + d] = cc;
                         }

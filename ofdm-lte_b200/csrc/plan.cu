@@ -164,6 +164,7 @@ extern "C" int lte_plan_create(const lte_plan_desc* d, const lte_c32* pilots_hos
     D.inv_sqrt_n = (float)(1.0 / sqrt((double)N));
 
     // --- constellation axis levels and slicer thresholds (core/modulator.py:28-59) -----
+    for (int i = 0; i < 7; ++i) D.thr[i] = INFINITY;     // unused thresholds never fire (slicer bisection)
     if (D.bps == 2) {          // [1+1j, 1-1j, -1+1j, -1-1j]/sqrt(2): index bit 0 -> +, 1 -> -
         D.nlev = 2;
         D.lev[0] = (float)(1.0 / sqrt(2.0));

@@ -13,9 +13,10 @@ struct SmPrecoder {
 
 __device__ __forceinline__ int slice_axis_sm(const DevPlan& P, float y) {
     if (P.nlev == 2) return y < 0.f ? 1 : 0;
-    int l = 0;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) l += (i < P.nlev - 1 && y > P.thr[i]) ? 1 : 0;
+    // number of thresholds below y by bisection; unused entries of thr[] are +inf (plan.cu)
+    int l = (y > P.thr[3]) ? 4 : 0;
+    l += (y > P.thr[l + 1]) ? 2 : 0;
+    l += (y > P.thr[l]) ? 1 : 0;
     return l;
 }
 
