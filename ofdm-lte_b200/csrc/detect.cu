@@ -6,22 +6,30 @@
 
 // ------------------------------------------------------------------------------ bits <-> indices
 // core/modulator.py:74-84: zero-pad, read b bits MSB first.
-__global__ void bits_to_indices_kernel(const uint8_t* __restrict__ bits, long long nbits, int packed,
-                                       uint8_t* __restrict__ idx, long long nsym, int bps, long long total) {
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
-         g += (long long)gridDim.x * blockDim.x) {
-        const long long b = g / nsym, q = g % nsym;
-        const long long row_bytes = packed ? (nbits + 7) / 8 : nbits;
-        const uint8_t* src = bits + (size_t)b * row_bytes;
-        int v = 0;
-        for (int i = 0; i < bps; ++i) {
-            const long long bi = q * bps + i;
-            int bit = 0;
-            if (bi < nbits) bit = packed ? (src[bi >> 3] >> (7 - (bi & 7))) & 1 : (src[bi] & 1);
-            v = (v << 1) | bit;
-        }
-        idx[g] = (uint8_t)v;
+// One thread per symbol; block = (row, chunk of 256 symbols).  Packed rows (np.packbits layout) are
+// read through a 16-bit window, so a symbol costs two byte loads instead of `bps` of them.
+__global__ void __launch_bounds__(256)
+bits_to_indices_kernel(const uint8_t* __restrict__ bits, long long nbits, int packed, uint8_t* __restrict__ idx,
+                       unsigned nsym, int bps, unsigned chunks) {
+    const unsigned row = blockIdx.x / chunks;
+    const unsigned q = (blockIdx.x - row * chunks) * 256u + threadIdx.x;
+    if (q >= nsym) return;
+    const long long bi0 = (long long)q * bps;            // first bit of the symbol within the row
+    int v = 0;
+    if (packed) {
+        const long long row_bytes = (nbits + 7) >> 3;
+        const uint8_t* src = bits + (size_t)row * row_bytes;
+        const long long by = bi0 >> 3;
+        const int off = (int)(bi0 & 7);
+        const unsigned hi = by < row_bytes ? src[by] : 0u, lo = by + 1 < row_bytes ? src[by + 1] : 0u;
+        v = (int)((((hi << 8) | lo) >> (16 - off - bps)) & ((1u << bps) - 1u));
+        const long long left = nbits - bi0;              // bits of this symbol inside the row
+        if (left < bps) v = left <= 0 ? 0 : (v & ~((1 << (bps - (int)left)) - 1));
+    } else {
+        const uint8_t* src = bits + (size_t)row * nbits + bi0;
+        for (int i = 0; i < bps; ++i) v = (v << 1) | ((bi0 + i < nbits) ? (src[i] & 1) : 0);
     }
+    idx[(size_t)row * nsym + q] = (uint8_t)v;
 }
 
 // core/modulator.py:109-110: format(idx, '0{b}b'); output truncated to nbits.
@@ -50,9 +58,12 @@ extern "C" int lte_bits_to_indices(const lte_plan* p, const uint8_t* bits, int64
     if (B == 0) return LTE_OK;
     const int packed = nbits < 0;        // negative nbits: rows are np.packbits() bytes
     const long long nb = packed ? -nbits : nbits;
-    const long long total = (long long)B * nsym;
-    bits_to_indices_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(bits, nb, packed, idx, nsym,
-                                                                                  p->dev.bps, total);
+    if (nsym >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
+    const unsigned chunks = (unsigned)((nsym + 255) / 256);
+    const long long grid = (long long)chunks * B;
+    if (grid >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
+    bits_to_indices_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(bits, nb, packed, idx, (unsigned)nsym,
+                                                                            p->dev.bps, chunks);
     LTE_CHECK_CUDA(cudaGetLastError());
     return LTE_OK;
 }
