@@ -367,14 +367,19 @@ mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restri
             constexpr int CH = MRC_CHUNK;                   // symbols per prefetch group
             float2 yn[CH][R];
             uint8_t in[CH];
+            // running pointers (one per antenna) instead of 64-bit index arithmetic per load
+            const float2* yp[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) yp[r] = yb + ((size_t)r * S + s0) * nk;
+            const uint8_t* ip = COUNT ? idx_tx + ((size_t)b * S + s0) * P.Nd + d : nullptr;
             auto fetch = [&](int sf) {
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     in[c] = 0;
                     if (sf + c < s_end) {
 #pragma unroll
-                        for (int r = 0; r < R; ++r) yn[c][r] = yb[((size_t)r * S + sf + c) * nk];
-                        if (COUNT) in[c] = idx_tx[((size_t)b * S + sf + c) * P.Nd + d];
+                        for (int r = 0; r < R; ++r) { yn[c][r] = *yp[r]; yp[r] += nk; }
+                        if (COUNT) { in[c] = *ip; ip += P.Nd; }
                     }
                 }
             };
