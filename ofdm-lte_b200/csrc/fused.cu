@@ -24,7 +24,7 @@ template <int N, int K>
 __global__ void __launch_bounds__(FFT_CTA_THREADS, (N == 2048 && K == 4) ? 3 : 4)
 channel_rx_fft_kernel(const DevPlan P, const TdlParams C, const float2* __restrict__ tx,
                       const float* __restrict__ coef_g, float2* __restrict__ Y, double* __restrict__ power, int k0,
-                      int nk, int S, int R, int R2, int halo, unsigned total) {
+                      int nk, int S, int R, int R2, int halo, unsigned total, bool wide) {
     constexpr int TPF = N / FFT_ELEMS, PPC = fft2_pairs_per_cta(N);     // PPC symbols per CTA
     constexpr int NC = 2 * K + 1;
     extern __shared__ float4 smem4[];
@@ -50,9 +50,17 @@ channel_rx_fft_kernel(const DevPlan P, const TdlParams C, const float2* __restri
     if (valid) {
         const long long m_lo = (long long)s * L - halo;
         const float2* src = tx + (size_t)b * S * L + m_lo;      // may point before the stream for s = 0
-        for (int i = j; i < win; i += TPF) {
-            const bool ok = m_lo + i >= 0;
-            cp_async8_zfill(&xw[i], ok ? &src[i] : tx, ok);
+        if (wide) {
+            // halo and L are even and tx is 16-byte aligned: sample pairs move as 16-byte copies
+            for (int i = 2 * j; i < win; i += 2 * TPF) {
+                const bool ok = m_lo + i >= 0;
+                cp_async16_zfill(&xw[i], ok ? &src[i] : tx, ok);
+            }
+        } else {
+            for (int i = j; i < win; i += TPF) {
+                const bool ok = m_lo + i >= 0;
+                cp_async8_zfill(&xw[i], ok ? &src[i] : tx, ok);
+            }
         }
         const float* cg = coef_g + (size_t)f * ncoef;
         float* scw = sc_all + (size_t)p_local * ncoef;
@@ -220,8 +228,10 @@ extern "C" int lte_channel_rx_fft(const lte_plan* p, const lte_channel_desc* ch,
     }
     // one polynomial block per OFDM symbol; same truncation bounds as lte_channel_tdl
     const double x = M_PI * wmax * L;
+    // K = 1 uses the economised linear fit (tdl.cuh): remainder x^2/4 <= 5e-7 of |h|
     int K;
-    if (x <= 4.9e-3) K = 2;
+    if (x <= 1.41e-3) K = 1;
+    else if (x <= 4.9e-3) K = 2;
     else if (x <= 0.075) K = 4;
     else return LTE_ERR_UNSUPPORTED;
     C.pb = L;
@@ -245,7 +255,8 @@ extern "C" int lte_channel_rx_fft(const lte_plan* p, const lte_channel_desc* ch,
     if (R2 != R) LTE_CHECK_CUDA(cudaMemsetAsync(coef, 0, coef_bytes, st));
     const long long items = total * R * C.num_taps;
     const unsigned cgrid = (unsigned)((items + 255) / 256);
-    if (K == 2) jakes_coef_kernel<2><<<cgrid, 256, 0, st>>>(C, phases, coef, R, 1, R2, items);
+    if (K == 1) jakes_coef_kernel<1><<<cgrid, 256, 0, st>>>(C, phases, coef, R, 1, R2, items);
+    else if (K == 2) jakes_coef_kernel<2><<<cgrid, 256, 0, st>>>(C, phases, coef, R, 1, R2, items);
     else jakes_coef_kernel<4><<<cgrid, 256, 0, st>>>(C, phases, coef, R, 1, R2, items);
     LTE_CHECK_CUDA(cudaGetLastError());
 
@@ -257,13 +268,15 @@ extern "C" int lte_channel_rx_fft(const lte_plan* p, const lte_channel_desc* ch,
                             (size_t)PPC * ncoef * sizeof(float);
         if (smem > 200 * 1024) return LTE_ERR_UNSUPPORTED;
         const unsigned grid = (unsigned)((total + PPC - 1) / PPC);
+        const bool wide = (L & 1) == 0 && ((uintptr_t)tx & 15) == 0;
         auto launch = [&](auto k) -> int {
             LTE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k<<<grid, FFT_CTA_THREADS, smem, st>>>(p->dev, C, (const float2*)tx, coef, (float2*)Y, power, k0, nk, S, R,
-                                                   R2, halo, (unsigned)total);
+                                                   R2, halo, (unsigned)total, wide);
             LTE_CHECK_CUDA(cudaGetLastError());
             return LTE_OK;
         };
+        if (K == 1) return launch(channel_rx_fft_kernel<N, 1>);
         return K == 2 ? launch(channel_rx_fft_kernel<N, 2>) : launch(channel_rx_fft_kernel<N, 4>);
     });
 }

@@ -58,8 +58,17 @@ jakes_coef_kernel(const TdlParams C, const float* __restrict__ phases, float* __
         sincospif(2.0f * (float)turns, &sn, &cs);
         const float x = (float)(6.283185307179586 * C.w_cyc[tone]);   // rad / sample
         float2 term = make_float2(cs, sn);
-        a[0].x += term.x;
-        a[0].y += term.y;
+        if constexpr (K == 1) {
+            // economised (Chebyshev) linear fit of e^{j phi} over |phi| <= X = x pb/2:
+            // cos phi ~ 1 - X^2/4 (max error X^2/4 instead of Taylor's X^2/2), sin phi ~ phi
+            const float X = x * 0.5f * (float)C.pb;
+            const float c0 = 1.0f - 0.25f * X * X;
+            a[0].x += term.x * c0;
+            a[0].y += term.y * c0;
+        } else {
+            a[0].x += term.x;
+            a[0].y += term.y;
+        }
 #pragma unroll
         for (int k = 1; k <= K; ++k) {
             const float f = x / (float)k;
@@ -92,6 +101,11 @@ __device__ __forceinline__ void cp_async8_zfill(void* smem_dst, const void* gsrc
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     const int sz = valid ? 8 : 0;     // src-size 0 => zero fill
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz));
 }
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
