@@ -39,7 +39,6 @@ channel_rx_fft_kernel(const DevPlan P, const TdlParams C, const float2* __restri
     float2* xw = xw_all + (size_t)p_local * win2;
     float* sc_all = (float*)(xw_all + (size_t)PPC * win2);
     const float* sc = sc_all + (size_t)p_local * ncoef;
-    __shared__ float pw_red[FFT_CTA_THREADS / 32][2];
 
     const unsigned f = blockIdx.x * PPC + p_local;               // = b * S + s
     const bool valid = f < total;
@@ -134,48 +133,56 @@ channel_rx_fft_kernel(const DevPlan P, const TdlParams C, const float2* __restri
             }
             upk(acc, pwa, pwb);
         }
-        // ---- stream power: reduce over the TPF threads of the symbol, one atomic per antenna ------
+        // ---- stream power: one atomic per warp (or per symbol when a warp carries several) ---------
+        // the tap gains carry the FFT's 1/sqrt(N) (host side), so the power is scaled back by N here
+        bool leader;
         if constexpr (TPF >= 32) {
             pwa = warp_sum(pwa);
             pwb = warp_sum(pwb);
-            __syncthreads();                                     // pw_red free (previous pair)
-            if ((threadIdx.x & 31) == 0) { pw_red[threadIdx.x >> 5][0] = pwa; pw_red[threadIdx.x >> 5][1] = pwb; }
-            __syncthreads();
-            if (j == 0) {
-                pwa = 0.f; pwb = 0.f;
-                const int w0 = threadIdx.x >> 5;
-#pragma unroll
-                for (int q = 0; q < TPF / 32; ++q) { pwa += pw_red[w0 + q][0]; pwb += pw_red[w0 + q][1]; }
-            }
+            leader = (threadIdx.x & 31) == 0;
         } else {
 #pragma unroll
             for (int ofs = TPF / 2; ofs > 0; ofs >>= 1) {
                 pwa += __shfl_xor_sync(0xffffffffu, pwa, ofs);
                 pwb += __shfl_xor_sync(0xffffffffu, pwb, ofs);
             }
+            leader = j == 0;
         }
         const int r0 = 2 * p;
-        if (valid && j == 0) {
-            atomicAdd(&power[(size_t)b * R + r0], (double)pwa);
-            if (r0 + 1 < R) atomicAdd(&power[(size_t)b * R + r0 + 1], (double)pwb);
+        const bool two = r0 + 1 < R;
+        if (valid && leader) {
+            atomicAdd(&power[(size_t)b * R + r0], (double)pwa * (double)N);
+            if (two) atomicAdd(&power[(size_t)b * R + r0 + 1], (double)pwb * (double)N);
         }
 
         // ---- FFT of the useful part of both antennas, kept bins to Y --------------------------------
         fft2_run<N, false>(v, sbuf, P.twiddle, j);
         if (valid) {
-            const f2 scale = pk(P.inv_sqrt_n, P.inv_sqrt_n);
-            float2* o0 = Y + (((size_t)b * R + r0) * S + s) * nk;
+            // base pointers are formed once; every store is base + compile-time offset under one
+            // unsigned range check (the pointer may lie before the row, it is only dereferenced in range)
+            float2* o0 = Y + (((size_t)b * R + r0) * S + s) * nk + (j - k0);
             float2* o1 = o0 + (size_t)S * nk;
-            const bool two = r0 + 1 < R;
+            const unsigned kb = (unsigned)(j - k0);
+            if (two) {
 #pragma unroll
-            for (int e = 0; e < FFT_ELEMS; ++e) {
-                const int k = j + e * TPF - k0;
-                if (k >= 0 && k < nk) {
-                    float a, c, d, g;
-                    upk(mul2(v[e].re, scale), a, c);
-                    upk(mul2(v[e].im, scale), d, g);
-                    o0[k] = make_float2(a, d);
-                    if (two) o1[k] = make_float2(c, g);
+                for (int e = 0; e < FFT_ELEMS; ++e) {
+                    if (kb + (unsigned)(e * TPF) < (unsigned)nk) {
+                        float a, c, d, g;
+                        upk(v[e].re, a, c);
+                        upk(v[e].im, d, g);
+                        o0[e * TPF] = make_float2(a, d);
+                        o1[e * TPF] = make_float2(c, g);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < FFT_ELEMS; ++e) {
+                    if (kb + (unsigned)(e * TPF) < (unsigned)nk) {
+                        float a, c, d, g;
+                        upk(v[e].re, a, c);
+                        upk(v[e].im, d, g);
+                        o0[e * TPF] = make_float2(a, d);
+                    }
                 }
             }
         }
@@ -216,7 +223,8 @@ extern "C" int lte_channel_rx_fft(const lte_plan* p, const lte_channel_desc* ch,
     for (int i = 0; i < ch->num_taps; ++i) {
         if (ch->delay[i] < 0) return LTE_ERR_INVALID_ARG;
         C.delay[i] = ch->delay[i];
-        C.gain[i] = (float)((double)ch->gain[i] * sqrt(2.0 / LTE_JAKES_TONES));
+        // sqrt(2/16) of the Jakes sum and the receiver FFT's 1/sqrt(N) ride on the tap gain
+        C.gain[i] = (float)((double)ch->gain[i] * sqrt(2.0 / LTE_JAKES_TONES) / sqrt((double)p->dev.N));
         if (ch->delay[i] > dmax) dmax = ch->delay[i];
     }
     if (dmax > 144) return LTE_ERR_UNSUPPORTED;
