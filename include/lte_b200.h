@@ -50,6 +50,9 @@ extern "C" {
 #define LTE_DET_SIC 2
 #define LTE_DET_MRC 3
 
+#define LTE_BF_MRT 0       /* BeamformingPrecoder.calculate_mrt_weights (update_mode='adaptive') */
+#define LTE_BF_CODEBOOK 1  /* LTECodebook.select_best_pmi precoder (update_mode='static') */
+
 #define LTE_WINDOW_FULL 0
 #define LTE_WINDOW_USEFUL 1
 
@@ -276,6 +279,33 @@ int lte_flat_mimo(const lte_plan*, const lte_c32* tx, const lte_c32* h, lte_c32*
 int lte_mimo_detect(const lte_plan*, const lte_c32* Y, const lte_c32* H, const lte_c32* W_host,
                     int32_t T, int32_t L, double sigma2, int32_t detector, lte_c32* out, int window,
                     int64_t B, int32_t R, int32_t S, void* stream);
+
+/* --- beamforming (rank-1 precoding over a flat R x T channel) ---------------
+ * The reference path OFDMSimulator.simulate_beamforming (core/ofdm_core.py:2260-2477) stays in
+ * the frequency domain: per OFDM symbol  x = W s,  y = H x + n,  MRC with H_eff = H W.
+ * lte_random_channel: h [B][R][T] ~ CN(0,1), the (randn + j randn)/sqrt(2) draw of :2347-2348,
+ * Philox keyed (seed, stream_id0 + b).
+ * lte_bf_weights replaces CSIFeedback.generate_feedback -> LTECodebook.select_best_pmi
+ * (core/csi_feedback.py:166-196, core/codebook_lte.py:332-373) and
+ * BeamformingPrecoder.calculate_mrt_weights / calculate_beamforming_gain
+ * (core/beamforming_precoder.py:41-66, :176-201) for B channel matrices at once:
+ * codebook_host [ncb][T] rank-1 precoders (host memory); mode LTE_BF_MRT | LTE_BF_CODEBOOK selects
+ * which precoder is written to W [B][T]; heff [B][R] = H W; pmi [B] (optional) is always the
+ * codebook argmax, first maximum wins; gain_db [B] (optional).
+ * lte_bf_link replaces the per-symbol loop, the MRC and the demap/BER of :2359-2439:
+ * idx [B][S][Nd]; noise_std [B] = sqrt(10^(-snr/10) / 2); z (optional) [B][S][2][R][Nd] replayed
+ * unit normals (real block, then imaginary block, as the reference draws them), else Philox keyed
+ * (seed, row_id0 + b*R + r, s*Nd + d); out (optional) [B][S][Nd] equalised symbols; errors
+ * (optional) [B] uint64 accumulated over the first nbits bits of each stream (caller zeroes). */
+int lte_random_channel(lte_c32* h, int64_t B, int32_t R, int32_t T, uint64_t seed, uint64_t stream_id0,
+                       void* stream);
+int lte_bf_weights(const lte_c32* h, const lte_c32* codebook_host, int32_t ncb, int32_t mode, lte_c32* W,
+                   lte_c32* heff, int32_t* pmi, float* gain_db, int64_t B, int32_t R, int32_t T,
+                   void* stream);
+int lte_bf_link(const lte_plan*, const uint8_t* idx, const lte_c32* h, const lte_c32* W,
+                const lte_c32* heff, const float* noise_std, const float* z, uint64_t seed,
+                uint64_t row_id0, lte_c32* out, unsigned long long* errors, int64_t nbits, int64_t B,
+                int32_t R, int32_t T, int32_t S, void* stream);
 
 /* --- stage 6: hard demap + bit-error count -------------------------------------------
  * replaces QAMModulator.symbols_to_bits (core/modulator.py:90-112) and

@@ -466,6 +466,67 @@ class OFDMSimulator:
     def simulate_mimo(self, bits, snr_db: float = 10.0, num_rx: int = 2) -> Dict:
         return self._simulate_sfbc(bits, snr_db, num_rx, 'MIMO-SFBC')
 
+    # ------------------------------------------------------------------ beamforming
+    def simulate_beamforming(self, bits, snr_db: float = 10.0, num_tx: int = 2, num_rx: int = 1,
+                             codebook_type: str = 'TM6', velocity_kmh: float = 3.0,
+                             update_mode: str = 'adaptive') -> Dict:
+        """Codebook / MRT beamforming over a flat num_rx x num_tx channel (reference :2260-2477):
+        per OFDM symbol x = W s, y = H x + n, then MRC with H_eff = H W, slicer and BER.  The whole
+        per-symbol loop is one `lte_bf_link` launch; PMI, W, H_eff and the array gain come from
+        `lte_bf_weights`.  With rng='numpy' H and the noise replay the caller's global RNG exactly
+        as the reference consumes it (randn(R,T) x2, then randn(R,Nd) x2 per OFDM symbol)."""
+        from .beamforming_precoder import AdaptiveBeamforming
+        from .csi_feedback import CSIFeedback
+        bits = self._check_bits(bits)
+        eng = be.engine_for(self.config)
+        csi = CSIFeedback(num_tx, num_rx, codebook_type=codebook_type)
+        b_t = be.as_bits_tensor(bits)
+        nbits = b_t.shape[1]
+        S = eng.symbols_for_bits(nbits)
+        idx = eng.bits_to_indices(b_t, nbits, S)
+        Nd = eng.Nd
+        if self._draws.kind == 'numpy':
+            H = (np.random.randn(num_rx, num_tx) + 1j * np.random.randn(num_rx, num_tx)) / np.sqrt(2)
+            h = be.as_complex_tensor(H.astype(np.complex64)[None])
+            z = np.empty((S, 2, num_rx, Nd), dtype=np.float32)
+            for s in range(S):
+                z[s, 0] = np.random.randn(num_rx, Nd)
+                z[s, 1] = np.random.randn(num_rx, Nd)
+            z_d, seed, sid = torch.from_numpy(z).to(h.device), 0, 0
+        else:
+            sid = self._draws.next_stream()
+            seed = self._draws.seed
+            h = eng.random_channel(1, num_rx, num_tx, seed, sid)
+            H = be.to_numpy(h[0]).astype(complex)
+            z_d = None
+        adaptive = update_mode == 'adaptive'
+        W, heff, pmi, gain = eng.bf_weights(h, csi.codebook.codebook, mode='MRT' if adaptive else 'CODEBOOK')
+        noise_std = torch.full((1,), float(np.sqrt(10 ** (-snr_db / 10) / 2)), dtype=torch.float32, device=h.device)
+        errors, sym = eng.bf_link(idx, h, W, heff, noise_std, S, nbits=nbits, z=z_d, seed=seed, row_id0=sid * num_rx,
+                                  want_symbols=True)
+        _, idx_rx = eng.demap_count(sym, want_idx=True)
+        bits_rx = be.to_numpy(eng.indices_to_bits(idx_rx, nbits).reshape(-1), np.int64)
+        bit_errors = int(errors.item())
+        pmi0 = int(pmi.item())
+        # the channel is static over the call, so every symbol reports the same PMI (reference :2366-2369)
+        pmi_history = [pmi0] * S
+        csi.pmi_history.extend(pmi_history)
+        csi.total_feedbacks += S
+        # update_mode='static': the reference's precoder object never gets a W, so its gain reads 0.0 (:190-191)
+        avg_gain = float(gain.item()) if adaptive else 0.0
+        results = {
+            'transmitted_bits': int(nbits), 'received_bits': int(nbits), 'bits_received_array': bits_rx,
+            'bit_errors': bit_errors, 'errors': bit_errors, 'ber': float(bit_errors / nbits), 'snr_db': float(snr_db),
+            'num_tx': num_tx, 'num_rx': num_rx, 'mode': 'Beamforming', 'codebook_type': codebook_type,
+            'beamforming_gain_db': avg_gain, 'channel_matrix': H, 'pmi_history': pmi_history,
+            'unique_pmis': len(set(pmi_history)), 'velocity_kmh': velocity_kmh,
+            'precoder': be.to_numpy(W[0]).astype(complex).reshape(-1, 1), 'symbols_rx': be.to_numpy(sym.reshape(-1)),
+        }
+        if adaptive:
+            results['update_period'] = int(AdaptiveBeamforming(num_tx, velocity_kmh, 2.0).update_period)
+        self.last_results = results
+        return results
+
     # ------------------------------------------------------------------ sweeps
     def run_ber_sweep(self, num_bits: int, snr_range, num_trials: int = 1,
                       progress_callback: Optional[callable] = None) -> Dict:

@@ -1,6 +1,7 @@
 // Stage 4 (CRS LS + linear interpolation), stage 5 (ZF / MRC) and stage 6 (hard demap +
 // bit-error count), plus the bit <-> symbol-index helpers of the reference-facing API.
 #include <stdlib.h>
+#include "slicer.cuh"
 
 #include "common.cuh"
 
@@ -207,42 +208,6 @@ extern "C" int lte_crs_ls_interp_awgn(const lte_plan* p, const lte_c32* Y, lte_c
                                       int64_t rows, int32_t S, const lte_awgn_desc* awgn, void* stream) {
     if (!awgn) return LTE_ERR_INVALID_ARG;
     return launch_crs(p, Y, H, window, pilot_set, rows, S, awgn, stream);
-}
-
-// ------------------------------------------------------------------------------ slicer
-// argmin_i |c_i - y| with first-minimum ties (core/modulator.py:103-106) == per-axis nearest
-// level; thresholds are rounded towards -inf so `y > thr` equals `y > exact midpoint`, and a
-// tie at y == 0 picks the lower level (16/64-QAM) or the positive one (QPSK).
-__device__ __forceinline__ int slice_axis(const DevPlan& P, float y) {
-    if (P.nlev == 2) return y < 0.f ? 1 : 0;
-    // number of thresholds below y by bisection; unused entries of thr[] are +inf (plan.cu)
-    int l = (y > P.thr[3]) ? 4 : 0;
-    l += (y > P.thr[l + 1]) ? 2 : 0;
-    l += (y > P.thr[l]) ? 1 : 0;
-    return l;
-}
-__device__ __forceinline__ int slice_symbol(const DevPlan& P, float2 y) {
-    return (slice_axis(P, y.x) << (P.bps >> 1)) | slice_axis(P, y.y);
-}
-// number of differing bits among the first `valid` (MSB-first) bits of two b-bit indices
-__device__ __forceinline__ int bit_errors(int a, int b, int bps, long long valid) {
-    if (valid <= 0) return 0;
-    int x = a ^ b;
-    if (valid < bps) x &= ~((1 << (bps - (int)valid)) - 1);
-    return __popc(x);
-}
-
-__device__ __forceinline__ void block_add_errors(unsigned int e, unsigned long long* dst) {
-    e = (unsigned int)__reduce_add_sync(0xffffffffu, e);
-    __shared__ unsigned int red[32];
-    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    if ((threadIdx.x & 31) == 0) red[w] = e;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        unsigned int t = threadIdx.x < nw ? red[threadIdx.x] : 0u;
-        t = (unsigned int)__reduce_add_sync(0xffffffffu, t);
-        if (threadIdx.x == 0 && t) atomicAdd(dst, (unsigned long long)t);
-    }
 }
 
 // ------------------------------------------------------------------------------ stage 6

@@ -22,6 +22,8 @@ LTE_JAKES_TONES = 16
 LTE_SLOT_SYMBOLS = 14
 LTE_MAX_RX = 8
 LTE_MAX_TX = 8
+BF_MRT = 0
+BF_CODEBOOK = 1
 WINDOW_FULL = 0
 WINDOW_USEFUL = 1
 
@@ -80,6 +82,9 @@ _SIGS = {
     'lte_mrc_demap_count': ([_P, _P, _P, _P, _P, C.c_int, _I64, _I64, _I32, _I32, _P], C.c_int),
     'lte_random_indices': ([_P, _P, _I64, _I64, _U64, _U64, _P], C.c_int),
     'lte_random_phases': ([_P, _I64, _I64, _U64, _U64, _P], C.c_int),
+    'lte_random_channel': ([_P, _I64, _I32, _I32, _U64, _U64, _P], C.c_int),
+    'lte_bf_weights': ([_P, _P, _I32, _I32, _P, _P, _P, _P, _I64, _I32, _I32, _P], C.c_int),
+    'lte_bf_link': ([_P, _P, _P, _P, _P, _P, _P, _U64, _U64, _P, _P, _I64, _I64, _I32, _I32, _I32, _P], C.c_int),
 }
 for _name, (_args, _res) in _SIGS.items():
     _fn = getattr(lib, _name)      # AttributeError here = header / library mismatch

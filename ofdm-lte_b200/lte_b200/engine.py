@@ -351,6 +351,51 @@ class LinkEngine:
         self.launches += 1
         return out
 
+    # ------------------------------------------------------------------ beamforming
+    def random_channel(self, B, R, T, seed, stream_id0=0):
+        """Flat channel matrices h [B, R, T] ~ CN(0, 1), Philox keyed (seed, stream_id0 + b)."""
+        h = self._empty((B, R, T), torch.complex64)
+        nat.check(nat.lib.lte_random_channel(_ptr(h), B, R, T, int(seed), int(stream_id0), self._stream()),
+                  'lte_random_channel')
+        self.launches += 1
+        return h
+
+    def bf_weights(self, h, codebook, mode='MRT'):
+        """h complex64 [B, R, T]; codebook: list of [T, 1] rank-1 precoders (host) ->
+        (W [B, T], heff [B, R], pmi int32 [B], gain_db float32 [B])."""
+        B, R, T = h.shape
+        cb = np.ascontiguousarray(np.stack([np.asarray(w).reshape(-1) for w in codebook]).astype(np.complex64)) \
+            if codebook is not None and len(codebook) else np.zeros((0, T), np.complex64)
+        W = self._empty((B, T), torch.complex64)
+        heff = self._empty((B, R), torch.complex64)
+        pmi = self._empty((B,), torch.int32)
+        gain = self._empty((B,), torch.float32)
+        m = {'MRT': nat.BF_MRT, 'CODEBOOK': nat.BF_CODEBOOK}[str(mode).upper()]
+        nat.check(nat.lib.lte_bf_weights(_ptr(h), cb.ctypes.data_as(C.c_void_p), cb.shape[0], m, _ptr(W), _ptr(heff),
+                                         _ptr(pmi), _ptr(gain), B, R, T, self._stream()), 'lte_bf_weights')
+        self.launches += 1
+        return W, heff, pmi, gain
+
+    def bf_link(self, idx, h, W, heff, noise_std, S, nbits=None, z=None, seed=0, row_id0=0, want_symbols=False,
+                errors=None, count=True):
+        """idx uint8 [B, S*Nd]; h [B, R, T]; W [B, T]; heff [B, R]; noise_std float32 [B]; z optional float32
+        [B, S, 2, R, Nd] replayed normals -> (errors int64 [B] or None, equalised symbols [B, S*Nd] or None)."""
+        B, R, T = h.shape
+        out = self._empty((B, S * self.Nd), torch.complex64) if want_symbols else None
+        if count:
+            if errors is None:
+                errors = torch.zeros(B, dtype=torch.int64, device=self.device)
+            else:
+                errors.zero_()
+        else:
+            errors = None
+        nb = int(nbits) if nbits is not None else S * self.Nd * self.bps
+        nat.check(nat.lib.lte_bf_link(self._plan, _ptr(idx), _ptr(h), _ptr(W), _ptr(heff), _ptr(noise_std), _ptr(z),
+                                      int(seed), int(row_id0), _ptr(out), _ptr(errors), nb, B, R, T, S,
+                                      self._stream()), 'lte_bf_link')
+        self.launches += 1
+        return errors, out
+
     # ------------------------------------------------------------------ stage 6
     def demap_count(self, syms, idx_tx=None, nbits=None, want_idx=False, errors=None):
         """-> (errors int64 [B] or None, idx_rx uint8 [B, nsym] or None)."""

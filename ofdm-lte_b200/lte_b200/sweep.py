@@ -64,3 +64,35 @@ def simo_sweep(engine, chan, snr_db, n_trials, num_rx, symbols_per_stream=14, se
 
     return run_sweep(count_batch, n_snr, n_trials, S * engine.Nd * engine.bps, batch_trials, rank, world,
                      engine.device)
+
+
+def beamforming_sweep(engine, codebook, snr_db, n_trials, num_tx, num_rx, mode='MRT', symbols_per_stream=14, seed=0,
+                      batch_trials=1024, rank=0, world=1):
+    """BER of the rank-1 beamforming link (reference OFDMSimulator.simulate_beamforming,
+    core/ofdm_core.py:2260-2477) at every SNR point: each stream draws its own flat R x T channel,
+    selects its precoder (mode 'MRT' = update_mode 'adaptive', 'CODEBOOK' = 'static'), and runs
+    S OFDM symbols through x = W s, y = H x + n, MRC, slicer, count.  Also returns the mean array
+    gain in dB and the PMI histogram, reduced like the error counters."""
+    n_snr = len(snr_db)
+    S, R, T = symbols_per_stream, num_rx, num_tx
+    nstd = torch.tensor([(10 ** (-s / 10) / 2) ** 0.5 for s in snr_db], dtype=torch.float32, device=engine.device)
+    ncb = len(codebook)
+    extra = torch.zeros(2 + ncb, dtype=torch.float64, device=engine.device)     # sum gain_db, streams, PMI histogram
+
+    def count_batch(trial_lo, n):
+        B = n * n_snr
+        sid0 = trial_lo * n_snr
+        idx = engine.random_indices(B, S, seed, sid0)
+        h = engine.random_channel(B, R, T, seed, sid0)
+        W, heff, pmi, gain = engine.bf_weights(h, codebook, mode=mode)
+        err, _ = engine.bf_link(idx, h, W, heff, nstd.repeat(n).contiguous(), S, seed=seed, row_id0=sid0 * R)
+        extra[0] += gain.double().sum()
+        extra[1] += B
+        extra[2:] += torch.bincount(pmi.long(), minlength=ncb).double()
+        return err
+
+    out = run_sweep(count_batch, n_snr, n_trials, S * engine.Nd * engine.bps, batch_trials, rank, world, engine.device)
+    reduce_counts(extra)
+    out['mean_gain_db'] = float(extra[0] / extra[1].clamp(min=1))
+    out['pmi_hist'] = extra[2:].long().cpu()
+    return out

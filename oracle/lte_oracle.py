@@ -853,3 +853,95 @@ def simulate_sm(bits, num, num_tx=4, num_rx=2, rank='adaptive', detector='MMSE',
     errors, bits_rx = count_errors(bits, bits_rx_all)
     return dict(signal_tx=tx, signal_rx=rx, Y=Y, H=H_all, symbols=symbols, bits_rx=bits_rx, errors=errors,
                 ber=errors / len(bits), rank=ri, pmi=pmi, W=W, channel_matrix=Hc)
+
+
+# ----------------------------------------------------------------------------
+# Beamforming (TM6-like rank-1 precoding over a flat channel)
+#   (core/ofdm_core.py:2260-2477, core/csi_feedback.py, core/beamforming_precoder.py)
+# ----------------------------------------------------------------------------
+def select_best_pmi(H, cb):
+    """LTECodebook.select_best_pmi, metric 'capacity' (core/codebook_lte.py:332-373):
+    argmax_i ||H w_i||^2, first maximum wins (strict >)."""
+    best, best_m = 0, -np.inf
+    for i, W in enumerate(cb):
+        m = np.sum(np.abs(H @ W) ** 2)
+        if m > best_m:
+            best_m, best = m, i
+    return best, best_m
+
+
+def mrt_weights(H):
+    """BeamformingPrecoder.calculate_mrt_weights (core/beamforming_precoder.py:41-66): conjugate of
+    the RX-averaged channel row, unit norm."""
+    h = np.conj(np.mean(H, axis=0)) if H.ndim == 2 else np.conj(H)
+    return (h / np.sqrt(np.sum(np.abs(h) ** 2))).reshape(-1, 1)
+
+
+def beamforming_gain_db(H, W, num_tx):
+    """calculate_beamforming_gain (core/beamforming_precoder.py:176-201)."""
+    return 10 * np.log10(np.sum(np.abs(H @ W) ** 2) / (np.sum(np.abs(H) ** 2) / num_tx))
+
+
+def sinr_to_cqi(sinr_db):
+    """CSIFeedback._sinr_to_cqi (core/csi_feedback.py:106-137): 2 dB steps from -6 dB, CQI 0..15."""
+    if sinr_db < -6.0:
+        return 0
+    return int(min(15, np.floor((sinr_db + 6.0) / 2.0) + 1))
+
+
+def beamforming_update_period(velocity_kmh, frequency_ghz=2.0):
+    """AdaptiveBeamforming._calculate_update_period (core/beamforming_precoder.py:231-263)."""
+    fd = (velocity_kmh / 3.6) * (frequency_ghz * 1e9) / 3e8
+    if fd == 0:
+        return 100
+    return int(np.clip(int(0.1 * (9 / (16 * np.pi * fd)) / (1 / 15000)), 1, 140))
+
+
+def simulate_beamforming(bits, snr_db, num, num_tx=2, num_rx=1, update_mode='adaptive', global_seed=0):
+    """OFDMSimulator.simulate_beamforming (core/ofdm_core.py:2260-2477).  Draw order from the caller's
+    global RNG state (nothing on this path re-seeds it): randn(R,T), randn(R,T) for H, then per OFDM
+    symbol randn(R,Nd), randn(R,Nd) for the noise.  The codebook is the rank-1 one for both 'TM6'
+    and 'TM4' (core/codebook_lte.py:114-118)."""
+    rs = np.random.RandomState(global_seed)
+    bits = np.asarray(bits).astype(np.int64)
+    n = len(bits)
+    data_idx, _ = grid_indices(num.N, num.Nc)
+    Nd, b = len(data_idx), num.bits_per_symbol
+    S = int(np.ceil(n / (Nd * b)))
+    padded = np.concatenate([bits, np.zeros(S * Nd * b - n, dtype=np.int64)])
+    sym = qam_map(padded, num.modulation).reshape(S, Nd)
+    H = (rs.randn(num_rx, num_tx) + 1j * rs.randn(num_rx, num_tx)) / np.sqrt(2)
+    cb = codebook(num_tx, 1)
+    nv = 10 ** (-snr_db / 10)
+    rx_all, gains, pmis = [], [], []
+    W = None
+    for s in range(S):
+        pmi, _ = select_best_pmi(H, cb)                       # CSI feedback every symbol (:2366-2369)
+        pmis.append(pmi)
+        if update_mode == 'adaptive':
+            W = mrt_weights(H)                                # update_precoder every symbol (:2372-2375)
+            gains.append(beamforming_gain_db(H, W, num_tx))
+        else:
+            W = cb[pmi]
+            gains.append(0.0)                                 # precoder.W stays None => 0.0 (:190-191)
+        x = W @ sym[s].reshape(1, -1)                         # [T, Nd]
+        rx = np.zeros((num_rx, Nd), dtype=complex)
+        for r in range(num_rx):
+            for t in range(num_tx):
+                rx[r] += H[r, t] * x[t]
+        noise = (rs.randn(num_rx, Nd) + 1j * rs.randn(num_rx, Nd)) * np.sqrt(nv / 2)
+        rx_all.append(rx + noise)
+    H_eff = H @ W                                             # last symbol's precoder (:2411)
+    pn = np.sum(np.abs(H_eff) ** 2)
+    eq = []
+    for s in range(S):
+        c = np.zeros(Nd, dtype=complex)
+        for r in range(num_rx):
+            c += np.conj(H_eff[r, 0]) * rx_all[s][r]
+        eq.append(c / pn)
+    symbols = np.concatenate(eq)
+    bits_rx = qam_demap(symbols, num.modulation)[:n]
+    errors = int(np.sum(bits != bits_rx))
+    return dict(symbols=symbols, bits_rx=bits_rx, errors=errors, ber=errors / n, channel_matrix=H, W=W,
+                H_eff=H_eff, pmi_history=pmis, beamforming_gain_db=float(np.mean(gains)),
+                unique_pmis=len(set(pmis)))

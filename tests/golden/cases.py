@@ -80,3 +80,19 @@ PAPR_CASES = [
     dict(name='papr_5mhz_qpsk_ragged', bw=5.0, mod='QPSK', nsym=6, seed=22, drop_bits=5),
     dict(name='papr_20mhz_64qam', bw=20.0, mod='64-QAM', nsym=3, seed=23),
 ]
+
+# beamforming path, OFDMSimulator.simulate_beamforming (core/ofdm_core.py:2260-2477).
+# gseed seeds the caller's global RNG (nothing on this path re-seeds it).
+BF_CASES = [
+    dict(name='bf_2x1_adaptive_1p25mhz_qpsk', bw=1.25, mod='QPSK', T=2, R=1, cb='TM6', upd='adaptive', v=3.0,
+         nsym=3, snrs=[0.0, 10.0], gseed=91, drop_bits=1),
+    dict(name='bf_4x2_static_tm6_2p5mhz_16qam', bw=2.5, mod='16-QAM', T=4, R=2, cb='TM6', upd='static', v=3.0,
+         nsym=2, snrs=[8.0], gseed=92),
+    dict(name='bf_8x1_adaptive_5mhz_64qam', bw=5.0, mod='64-QAM', T=8, R=1, cb='TM6', upd='adaptive', v=30.0,
+         nsym=2, snrs=[6.0, 15.0], gseed=93),
+    dict(name='bf_4x4_static_tm4_1p25mhz_64qam', bw=1.25, mod='64-QAM', T=4, R=4, cb='TM4', upd='static', v=3.0,
+         nsym=4, snrs=[12.0], gseed=94, drop_bits=5),
+    # the configuration of results/beamforming/resultados_comparacion.txt: 10 MHz, 64-QAM, 15 dB, 3 km/h
+    dict(name='bf_2x2_adaptive_10mhz_64qam', bw=10.0, mod='64-QAM', T=2, R=2, cb='TM6', upd='adaptive', v=3.0,
+         nsym=2, snrs=[15.0], gseed=95),
+]

@@ -32,7 +32,7 @@ from core.resource_mapper import LTEResourceGrid, PilotPattern  # noqa: E402
 from core.modulator import QAMModulator  # noqa: E402
 
 sys.path.insert(0, HERE)
-from cases import SISO_CASES, SIMO_CASES, SFBC_CASES, SM_CASES, PAPR_CASES, BIG_RX_STRIDE  # noqa: E402
+from cases import SISO_CASES, SIMO_CASES, SFBC_CASES, SM_CASES, PAPR_CASES, BF_CASES, BIG_RX_STRIDE  # noqa: E402
 
 
 def quiet(fn, *a, **k):
@@ -215,8 +215,33 @@ def papr_case(case):
     print('wrote', case['name'])
 
 
+def bf_case(case):
+    """OFDMSimulator.simulate_beamforming with the caller's global RNG seeded explicitly."""
+    cfg = LTEConfig(case['bw'], 15.0, case['mod'], 'normal')
+    sim = quiet(OFDMSimulator, cfg, channel_type='awgn')
+    bits = make_bits(case['gseed'], nd_of(cfg) * cfg.bits_per_symbol * case['nsym'] - case.get('drop_bits', 0))
+    out = dict(bits=np.packbits(bits), nbits=len(bits))
+    for snr in case['snrs']:
+        np.random.seed(case['gseed'])
+        r = quiet(sim.simulate_beamforming, bits, snr_db=snr, num_tx=case['T'], num_rx=case['R'],
+                  codebook_type=case['cb'], velocity_kmh=case['v'], update_mode=case['upd'])
+        out[f'errors_{snr}'] = r['errors']
+        out[f'bits_rx_{snr}'] = np.packbits(r['bits_received_array'].astype(np.uint8))
+        out[f'channel_matrix_{snr}'] = r['channel_matrix']
+        out[f'pmi_history_{snr}'] = np.array(r['pmi_history'])
+        out[f'gain_unique_{snr}'] = np.array([r['beamforming_gain_db'], r['unique_pmis']])
+    np.savez_compressed(os.path.join(HERE, case['name'] + '.npz'), **out)
+    print(case['name'], {s: int(out[f'errors_{s}']) for s in case['snrs']})
+
+
 def main():
+    if 'bf' in sys.argv[1:]:          # only the beamforming fixtures
+        for case in BF_CASES:
+            bf_case(case)
+        return
     tables()
+    for case in BF_CASES:
+        bf_case(case)
     for case in PAPR_CASES:
         papr_case(case)
     for case in SM_CASES:

@@ -121,3 +121,32 @@ def test_spatial_multiplexing_matches_reference(case):
         assert [o['rank'], o['pmi']] == list(g[f'rank_pmi_{snr}'])
         assert rel_err(o['W'], g[f'W_{snr}']) < TOL64
         assert rel_err(o['channel_matrix'], g[f'channel_matrix_{snr}']) < TOL64
+
+
+from cases import BF_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize('case', BF_CASES, ids=lambda c: c['name'])
+def test_beamforming_matches_reference(case):
+    """OFDMSimulator.simulate_beamforming (core/ofdm_core.py:2260-2477)."""
+    from helpers import numerology
+    g = load_golden(case['name'])
+    bits = golden_bits(g)
+    num = numerology(case)
+    for snr in case['snrs']:
+        o = O.simulate_beamforming(bits, snr, num, case['T'], case['R'], case['upd'], global_seed=case['gseed'])
+        assert o['errors'] == int(g[f'errors_{snr}'])
+        assert np.array_equal(o['bits_rx'], golden_bits_rx(g, snr))
+        assert rel_err(o['channel_matrix'], g[f'channel_matrix_{snr}']) < TOL64
+        assert o['pmi_history'] == list(g[f'pmi_history_{snr}'])
+        assert abs(o['beamforming_gain_db'] - g[f'gain_unique_{snr}'][0]) < 1e-9
+        assert o['unique_pmis'] == int(g[f'gain_unique_{snr}'][1])
+
+
+def test_beamforming_helpers_match_reference_tables():
+    """CQI table (core/csi_feedback.py:106-137) and update period (core/beamforming_precoder.py:231-263)."""
+    edges = [-7.0, -6.0, -4.1, -4.0, 0.0, 1.99, 2.0, 11.0, 21.99, 22.0, 40.0]
+    assert [O.sinr_to_cqi(x) for x in edges] == [0, 1, 1, 2, 4, 4, 5, 9, 14, 15, 15]
+    assert O.beamforming_update_period(0.0) == 100
+    assert O.beamforming_update_period(3.0) == 48           # values printed by the reference's AdaptiveBeamforming
+    assert O.beamforming_update_period(120.0) == 1
