@@ -550,6 +550,19 @@ class OFDMSimulator:
                 'papr_values': np.array(papr_values)}
 
 
+    def run_full_sweep(self, bits, snr_range, n_iterations: int = 1, modulations=('QPSK', '16-QAM', '64-QAM'),
+                       num_rx_values=(1, 2, 4, 8), progress_callback: Optional[callable] = None, seed: int = 0) -> Dict:
+        """The GUIs' modulations x num_rx x SNR x iterations sweep over one payload
+        (reference SIMO/gui/main_window.py:128-273) as batched GPU launches; same result dict as the
+        worker thread emits.  See lte_b200.sweep.payload_sweep."""
+        from lte_b200.sweep import payload_sweep
+        bits = self._check_bits(bits)
+        return payload_sweep(self.config, bits, snr_range, n_iterations, modulations, num_rx_values,
+                             channel_type=self.channel_type, itu_profile=self.itu_profile,
+                             frequency_ghz=self.frequency_ghz, velocity_kmh=self.velocity_kmh, seed=seed,
+                             progress_callback=progress_callback)
+
+
 def simulate_spatial_multiplexing(bits, num_tx=4, num_rx=2, rank='adaptive', detector_type='MMSE',
                                   modulation='64-QAM', snr_db=15, config=None, channel_type='awgn',
                                   itu_profile='Pedestrian_A', velocity_kmh=3, frequency_ghz=2.0,

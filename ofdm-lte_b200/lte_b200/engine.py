@@ -351,6 +351,27 @@ class LinkEngine:
         self.launches += 1
         return out
 
+    def siso_ber(self, chan, snr_lin_rows, S, seed, stream_id0=0, idx=None, nbits=None):
+        """One pass of the SISO chain with the zero-forcing equaliser Y / (H + 1e-6)
+        (reference simulate_siso, core/ofdm_core.py:660-737) over B independent streams: what the GUIs
+        run for num_rx = 1.  AWGN on the kept bins in the RX epilogue (noise_domain 1)."""
+        B = snr_lin_rows.shape[0]
+        if idx is None:
+            idx = self.random_indices(B, S, seed, stream_id0)
+        tx, _, _ = self.modulate(S, idx=idx, want_stats=False)
+        if chan.num_taps > 0:
+            ph = self.random_phases(B, chan.num_taps * nat.LTE_JAKES_TONES, seed, stream_id0)
+            rx, power = self.channel(tx, chan, B, 1, phases=ph)
+        else:
+            _, power = self.channel(tx, chan, B, 1)
+            rx = tx
+        Y = self.rx_fft(rx, B, S, nat.WINDOW_USEFUL, power=power, snr_lin=snr_lin_rows, seed=seed,
+                        row_id0=stream_id0, noise_domain=1)
+        H = self.estimate(Y, B, S, nat.WINDOW_USEFUL)
+        data = self.zf(Y, H, B, S, nat.WINDOW_USEFUL)
+        errors, _ = self.demap_count(data, idx_tx=idx, nbits=nbits)
+        return errors
+
     # ------------------------------------------------------------------ beamforming (SURVEY 8 f-3)
     def random_channel(self, B, R, T, seed, stream_id0=0):
         """Flat channel matrices h [B, R, T] ~ CN(0, 1), Philox keyed (seed, stream_id0 + b)."""

@@ -96,3 +96,68 @@ def beamforming_sweep(engine, codebook, snr_db, n_trials, num_tx, num_rx, mode='
     out['mean_gain_db'] = float(extra[0] / extra[1].clamp(min=1))
     out['pmi_hist'] = extra[2:].long().cpu()
     return out
+
+
+def payload_sweep(config, bits, snr_range, n_iterations, modulations=('QPSK', '16-QAM', '64-QAM'),
+                  num_rx_values=(1, 2, 4, 8), channel_type='rayleigh_mp', itu_profile='Pedestrian_A',
+                  frequency_ghz=2.0, velocity_kmh=3.0, seed=0, rank=0, world=1, max_batch_bytes=4 << 30,
+                  progress_callback=None, device=None):
+    """The GUIs' full diversity sweep -- modulations x num_rx x SNR x iterations over one payload
+    (reference SIMO/gui/main_window.py:128-273: four nested Python loops around simulate_siso /
+    simulate_simo) -- as batched launches: for every (modulation, num_rx) all SNR points and
+    iterations of a shard run as one batch of streams carrying the same payload bits, with
+    independent Philox channel / noise draws keyed by the global stream id
+    iteration * n_snr + snr_index.  num_rx = 1 uses the SISO zero-forcing chain, num_rx > 1 MRC.
+    Returns the worker's result dict: {'mode': 'sweep_full', 'modulations', 'num_rx_values',
+    'data': {mod: {'<n>RX': {'snr_values', 'ber_values', 'num_rx', 'errors', 'bits'}}}}."""
+    import copy
+
+    import numpy as np
+
+    from .engine import LinkEngine, chan_for
+    bits_t = torch.as_tensor(np.ascontiguousarray(np.asarray(bits).astype(np.uint8))) if not isinstance(bits, torch.Tensor) \
+        else bits.to(torch.uint8)
+    nbits = int(bits_t.numel())
+    if nbits == 0:
+        raise ValueError("Bits array cannot be empty")
+    snr_range = [float(s) for s in np.atleast_1d(snr_range)]
+    n_snr = len(snr_range)
+    total = len(modulations) * len(num_rx_values)
+    done = 0
+    data = {}
+    for mod in modulations:
+        cfg = copy.copy(config)
+        cfg.modulation = mod
+        cfg._calculate_parameters()
+        eng = LinkEngine.from_config(cfg, device=device)
+        chan = chan_for(channel_type, cfg.fs, itu_profile, frequency_ghz, velocity_kmh)
+        S = eng.symbols_for_bits(nbits)
+        idx1 = eng.bits_to_indices(bits_t.to(eng.device).reshape(1, -1), nbits, S)
+        snr_lin = torch.tensor([10 ** (s / 10) for s in snr_range], dtype=torch.float32, device=eng.device)
+        data[mod] = {}
+        for R in num_rx_values:
+            # bytes per stream: tx + faded + Y + equalised symbols, with slack; whole iterations per batch
+            per_stream = 8 * S * (eng.L * (1 + R) + eng.Nc * R + eng.Nd) + S * eng.Nd
+            batch_trials = max(1, int(max_batch_bytes // (per_stream * n_snr)))
+            state = {}
+
+            def count_batch(trial_lo, n, R=R, state=state):
+                B = n * n_snr
+                if state.get('B') != B:
+                    state['B'] = B
+                    state['idx'] = idx1.expand(B, -1).contiguous()
+                    state['rows'] = snr_lin.repeat(n).repeat_interleave(R).contiguous()
+                    state['ws'] = eng.workspace(B, S, R, fading=chan.num_taps > 0, fused=True) if R > 1 else None
+                if R == 1:
+                    return eng.siso_ber(chan, state['rows'], S, seed, trial_lo * n_snr, idx=state['idx'], nbits=nbits)
+                return eng.simo_ber(state['ws'], chan, state['rows'], seed, stream_id0=trial_lo * n_snr,
+                                    idx=state['idx'], nbits=nbits, noise_domain=2, fused=True).clone()
+
+            r = run_sweep(count_batch, n_snr, n_iterations, nbits, batch_trials, rank, world, eng.device)
+            data[mod][f'{R}RX'] = {'snr_values': np.array(snr_range), 'ber_values': r['ber'].numpy(), 'num_rx': R,
+                                   'errors': r['errors'].numpy(), 'bits': r['bits'].numpy()}
+            state.clear()
+            done += 1
+            if progress_callback:
+                progress_callback(int(15 + 80 * done / total), f"{mod} | {R}RX")
+    return {'mode': 'sweep_full', 'modulations': list(modulations), 'num_rx_values': list(num_rx_values), 'data': data}
