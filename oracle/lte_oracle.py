@@ -945,3 +945,283 @@ def simulate_beamforming(bits, snr_db, num, num_tx=2, num_rx=1, update_mode='ada
     return dict(symbols=symbols, bits_rx=bits_rx, errors=errors, ber=errors / n, channel_matrix=H, W=W,
                 H_eff=H_eff, pmi_history=pmis, beamforming_gain_db=float(np.mean(gains)),
                 unique_pmis=len(set(pmis)))
+
+
+# ----------------------------------------------------------------------------
+# Coded chain: CRC + segmentation + turbo code + rate matching + soft demapping
+#   (core/ofdm_core.py:739-1338, core/channel_coding/*.py)
+# ----------------------------------------------------------------------------
+CRC24A_POLY, CRC24B_POLY = 0x1864CFB, 0x1800063      # core/channel_coding/crc.py:32-33
+
+
+def crc24(bits, poly=CRC24A_POLY):
+    """_calculate_crc (core/channel_coding/crc.py:78-124): remainder of bits * D^24 by the generator,
+    zero initial state, MSB first -- as a 24-bit shift register."""
+    reg = 0
+    for b in np.asarray(bits).astype(np.int64):
+        top = ((reg >> 23) & 1) ^ int(b)
+        reg = (reg << 1) & 0xFFFFFF
+        if top:
+            reg ^= poly & 0xFFFFFF
+    return np.array([(reg >> (23 - i)) & 1 for i in range(24)], dtype=np.uint8)
+
+
+TURBO_K = ([40 + 8 * i for i in range(60)] + [528 + 16 * i for i in range(32)] +
+           [1056 + 32 * i for i in range(32)] + [2112 + 64 * i for i in range(64)])   # segmentation.py:28-45
+
+def find_interleaver_size(n):
+    for k in TURBO_K:
+        if k >= n:
+            return k
+    raise ValueError(f"No valid interleaver size found for min_size={n}")
+
+
+def segmentation_layout(B):
+    """segment_code_blocks (core/channel_coding/segmentation.py:66-199) as a layout:
+    list of (K_r, F_r filler bits, info bits, has_crc24b) per code block."""
+    Z, L = 6144, 24
+    if B <= Z:
+        K = find_interleaver_size(B)
+        return [(K, K - B, B, False)]
+    C = int(np.ceil(B / (Z - L)))
+    Bp = B + C * L
+    Kp = find_interleaver_size(int(np.ceil(Bp / C)))
+    i = TURBO_K.index(Kp) - 1
+    Km = TURBO_K[i] if i >= 0 else Kp
+    dK = Kp - Km
+    Cm = (C * Kp - Bp) // dK if dK > 0 else 0
+    out, remaining = [], B
+    for r in range(C):
+        Kr = Km if r < Cm else Kp
+        n = remaining if r == C - 1 else min(Kr - L, remaining // (C - r))
+        remaining -= n
+        out.append((Kr, (Kr - L) - n, n, True))
+    return out
+
+
+def segment_code_blocks(tb):
+    blocks, pos = [], 0
+    for Kr, F, n, has_crc in segmentation_layout(len(tb)):
+        body = np.zeros(Kr - (24 if has_crc else 0), dtype=np.uint8)
+        body[F:F + n] = tb[pos:pos + n]
+        pos += n
+        blocks.append(np.concatenate([body, crc24(body, CRC24B_POLY)]) if has_crc else body)
+    return blocks
+
+
+def desegment_code_blocks(blocks, B):
+    out = []
+    for cb, (Kr, F, n, has_crc) in zip(blocks, segmentation_layout(B)):
+        out.append(cb[F:F + n])
+    return np.concatenate(out)
+
+
+def qpp_indices(K, f1, f2):
+    i = np.arange(K, dtype=np.int64)
+    return (f1 * i + f2 * i * i) % K
+
+
+def rsc_encode(u):
+    """rsc_encode (core/channel_coding/turbo_encoder.py:112-169): the 'systematic' output is the
+    FEEDBACK bit a_k = u_k + s1 + s2 (not u_k); parity = a_k + s0 + s2; 3 termination steps."""
+    s0 = s1 = s2 = 0
+    sys_, par = [], []
+    for bit in list(np.asarray(u).astype(int)) + [None] * 3:
+        if bit is None:
+            bit = (s1 + s2) % 2
+        fb = (bit + s1 + s2) % 2
+        sys_.append(fb)
+        par.append((fb + s0 + s2) % 2)
+        s0, s1, s2 = fb, s0, s1
+    return np.array(sys_, dtype=np.uint8), np.array(par, dtype=np.uint8)
+
+
+def turbo_encode(u, f1, f2):
+    """turbo_encode (turbo_encoder.py:172-259): [s_k, p1_k, p2_k] interleaved for k < K, then
+    tail_sys1(3) tail_par1(3) tail_sys2(3) tail_par2(3)."""
+    K = len(u)
+    s1_, p1 = rsc_encode(u)
+    s2_, p2 = rsc_encode(np.asarray(u)[qpp_indices(K, f1, f2)])
+    out = np.zeros(3 * K + 12, dtype=np.uint8)
+    out[0:3 * K:3], out[1:3 * K:3], out[2:3 * K:3] = s1_[:K], p1[:K], p2[:K]
+    out[3 * K:] = np.concatenate([s1_[K:], p1[K:], s2_[K:], p2[K:]])
+    return out
+
+
+_SBI_P = np.array([0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30,
+                   1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31])
+
+
+def sub_block_permutation(n):
+    """sub_block_interleaver (core/channel_coding/rate_matching.py:27-77) as an index vector:
+    out[j] = in[perm[j]].  The matrix is filled COLUMN by column with the nulls at the end,
+    columns are permuted, rows are read out and nulls dropped (the reference's own variant)."""
+    R = int(np.ceil(n / 32))
+    m = np.full(R * 32, -1, dtype=np.int64)
+    m[:n] = np.arange(n)
+    m = m.reshape(32, R).T[:, _SBI_P].reshape(-1)
+    return m[m >= 0]
+
+
+def rate_match_table(K):
+    """rate_match_turbo with E = 3K + 12, rv 0 (rate_matching.py:163-229, core/ofdm_core.py:993-1001):
+    out[i] = encoded[table[i]], -1 = constant 0 (padding of the shorter parity streams)."""
+    enc = np.arange(3 * K + 12)
+    d0 = np.concatenate([enc[0:3 * K:3], enc[3 * K:3 * K + 3], enc[3 * K + 6:3 * K + 9]])
+    d1 = np.concatenate([enc[1:3 * K:3], enc[3 * K + 3:3 * K + 6]])
+    d2 = np.concatenate([enc[2:3 * K:3], enc[3 * K + 9:3 * K + 12]])
+    v = [d[sub_block_permutation(len(d))] for d in (d0, d1, d2)]
+    n = max(len(x) for x in v)
+    cb = np.full(3 * n, -1, dtype=np.int64)
+    for j, x in enumerate(v):
+        cb[j:3 * len(x):3] = x
+    return cb[:3 * K + 12]
+
+
+def rate_dematch_table(K):
+    """rate_dematching_turbo (rate_matching.py:297-396): out[j] = llr[table[j]], -1 = 0.0 (never sent)."""
+    src = rate_match_table(K)
+    t = np.full(3 * K + 12, -1, dtype=np.int64)
+    ok = src >= 0
+    t[src[ok]] = np.flatnonzero(ok)
+    return t
+
+
+def llr_noise_var(H, snr_db, awgn_channel):
+    """core/ofdm_core.py:1228-1250."""
+    s2 = 1.0 / (10 ** (snr_db / 10))
+    if awgn_channel:
+        return np.full(len(H), s2)
+    return np.maximum(s2 / np.clip(np.abs(H) ** 2, 1e-6, 1e6), s2 / 4.0)
+
+
+def soft_demap(symbols, noise_var, modulation):
+    """_calculate_llrs_qpsk/_16qam/_64qam (core/ofdm_core.py:791-923): QPSK exact and unclipped;
+    16/64-QAM max-log over the natural-binary raster constellation, clipped to +-10."""
+    y = np.asarray(symbols)
+    nv = np.broadcast_to(np.asarray(noise_var, dtype=float), y.shape)
+    if modulation == 'QPSK':
+        out = np.zeros(2 * len(y))
+        out[0::2] = (2.0 / nv) * y.real * np.sqrt(2)
+        out[1::2] = (2.0 / nv) * y.imag * np.sqrt(2)
+        return out
+    c = constellation(modulation)
+    b = BITS_PER_SYMBOL[modulation]
+    bitmap = (np.arange(len(c))[:, None] >> (b - 1 - np.arange(b))[None, :]) & 1
+    d = np.abs(y[:, None] - c[None, :]) ** 2
+    out = np.zeros((len(y), b))
+    for p in range(b):
+        d0 = np.min(d[:, bitmap[:, p] == 0], axis=1)
+        d1 = np.min(d[:, bitmap[:, p] == 1], axis=1)
+        out[:, p] = np.clip((d1 - d0) / (2.0 * nv), -10.0, 10.0)
+    return out.reshape(-1)
+
+
+def _trellis():
+    ns, so, po = np.zeros((8, 2), int), np.zeros((8, 2), int), np.zeros((8, 2), int)
+    for st in range(8):
+        s0, s1, s2 = (st >> 2) & 1, (st >> 1) & 1, st & 1
+        for u in range(2):
+            fb = (u + s1 + s2) % 2
+            ns[st, u], so[st, u], po[st, u] = (fb << 2) | (s0 << 1) | s1, fb, (fb + s0 + s2) % 2
+    return ns, so, po
+
+
+def maxlog_bcjr(Ls, Lp, La, extrinsic=True):
+    """LogMAPDecoder.decode in its default max-log mode (core/channel_coding/turbo_decoder.py:158-293):
+    start and end in state 0, gamma = (+-Ls +-Lp +-La)/2 with Ls signed by the FEEDBACK bit of the
+    branch and La by its input bit."""
+    ns, so, po = _trellis()
+    n = len(Ls)
+    g = ((1 - 2 * so)[None] * (Ls[:, None, None] / 2.0) + (1 - 2 * po)[None] * (Lp[:, None, None] / 2.0)) + \
+        (1 - 2 * np.arange(2))[None, None, :] * (La[:, None, None] / 2.0)
+    alpha = np.full((n + 1, 8), -np.inf)
+    beta = np.full((n + 1, 8), -np.inf)
+    alpha[0, 0] = beta[n, 0] = 0.0
+    for k in range(n):
+        cand = alpha[k][:, None] + g[k]
+        nxt = np.full(8, -np.inf)
+        np.maximum.at(nxt, ns.reshape(-1), cand.reshape(-1))
+        alpha[k + 1] = nxt
+    for k in range(n - 1, -1, -1):
+        beta[k] = np.max(beta[k + 1][ns] + g[k], axis=1)
+    val = (alpha[:n, :, None] + g) + beta[1:][:, ns]
+    apost = np.max(val[:, :, 0], axis=1) - np.max(val[:, :, 1], axis=1)
+    return (apost < 0).astype(np.uint8), (apost - La - Ls) if extrinsic else apost
+
+
+def turbo_decode(llr, K, f1, f2, num_iterations=8):
+    """turbo_decode (turbo_decoder.py:340-446)."""
+    pi = qpp_indices(K, f1, f2)
+    inv = np.empty(K, dtype=np.int64)
+    inv[pi] = np.arange(K)
+    Ls = np.concatenate([llr[0:3 * K:3], llr[3 * K:3 * K + 3]])
+    Lp1 = np.concatenate([llr[1:3 * K:3], llr[3 * K + 3:3 * K + 6]])
+    Lp2 = np.concatenate([llr[2:3 * K:3], llr[3 * K + 9:3 * K + 12]])
+    Ls2 = np.concatenate([Ls[:K][pi], llr[3 * K + 6:3 * K + 9]])
+    e21 = np.zeros(K)
+    z3 = np.zeros(3)
+    for _ in range(num_iterations):
+        _, e12 = maxlog_bcjr(Ls, Lp1, np.concatenate([e21, z3]))
+        _, e21i = maxlog_bcjr(Ls2, Lp2, np.concatenate([e12[:K][pi], z3]))
+        e21 = e21i[:K][inv]
+    bits, _ = maxlog_bcjr(Ls, Lp1, np.concatenate([e21, z3]), extrinsic=False)
+    return bits[:K]
+
+
+def symbol_interleave(sym, ncols):
+    """core/ofdm_core.py:1037-1060: write row-wise into [rows, ncols] (zero padded), read column-wise."""
+    rows = int(np.ceil(len(sym) / ncols))
+    m = np.zeros(rows * ncols, dtype=complex)
+    m[:len(sym)] = sym
+    return m.reshape(rows, ncols).T.reshape(-1), rows
+
+
+def simulate_siso_coded(bits, snr_db, num, qpp, channel_type='awgn', itu_profile='Pedestrian_A',
+                        frequency_ghz=2.0, velocity_kmh=0.0, phases=None, z=None, draws=None):
+    """OFDMSimulator.simulate_siso_coded (core/ofdm_core.py:925-1338).  qpp: {K: (f1, f2)}."""
+    bits = np.asarray(bits).astype(np.uint8)
+    if bits.size == 0:
+        raise ValueError("Bits array cannot be empty")
+    data_idx, pilot_idx = grid_indices(num.N, num.Nc)
+    Nd, b = len(data_idx), num.bits_per_symbol
+    tb = np.concatenate([bits, crc24(bits, CRC24A_POLY)])
+    blocks = segment_code_blocks(tb)
+    coded = np.concatenate([turbo_encode(cb, *qpp[len(cb)])[np.maximum(rate_match_table(len(cb)), 0)] *
+                            (rate_match_table(len(cb)) >= 0) for cb in blocks]).astype(np.uint8)
+    sym = qam_map(coded, num.modulation)
+    inter, rows = symbol_interleave(sym, Nd)
+    sig = ofdm_modulate_grid(map_grid(inter.reshape(rows, Nd), num), num).reshape(-1)
+    papr_db, papr_lin = papr(sig)
+    if draws is None and (phases is None or z is None):
+        draws = ReferenceDraws(len(pilot_idx))
+    rx, _ = channel_link(sig, num, channel_type, snr_db, draws, itu_profile, frequency_ghz, velocity_kmh,
+                         phases=phases, z=z)
+    Y = rx_fft_stream(rx, num)
+    H = estimate_channel_periodic(Y, num)
+    eq = zf_equalize(Y, H)[:, data_idx].reshape(-1)
+    Hd = H[:, data_idx].reshape(-1)
+    nsym = len(coded) // b
+    rrows = int(np.ceil(nsym / Nd))
+    tot = rrows * Nd
+    eq = np.pad(eq, (0, max(0, tot - len(eq))))[:tot]
+    Hd = np.pad(Hd, (0, max(0, tot - len(Hd))), mode='edge')[:tot]
+    sym_rx = eq.reshape(Nd, rrows).T.reshape(-1)[:nsym]
+    H_rx = Hd.reshape(Nd, rrows).T.reshape(-1)[:nsym]
+    nv = llr_noise_var(H_rx, snr_db, channel_type != 'rayleigh_mp')
+    llr = soft_demap(sym_rx, nv, num.modulation)[:len(coded)]
+    dec, off = [], 0
+    for cb in blocks:
+        K = len(cb)
+        blk = llr[off:off + 3 * K + 12]
+        off += 3 * K + 12
+        t = rate_dematch_table(K)
+        dec.append(turbo_decode(np.where(t >= 0, blk[np.maximum(t, 0)], 0.0), K, *qpp[K]))
+    tb_rx = desegment_code_blocks(dec, len(tb))
+    crc_ok = bool(np.array_equal(tb_rx[-24:], crc24(tb_rx[:-24], CRC24A_POLY)))
+    bits_rx = tb_rx[:-24][:len(bits)]
+    errors = int(np.sum(bits != bits_rx))
+    return dict(signal_tx=sig, signal_rx=rx, coded_bits=coded, symbols_tx=sym, symbols_rx=sym_rx, H_estimate=H_rx,
+                llr=llr, noise_var_mean=float(np.mean(nv)), bits_rx=bits_rx, errors=errors, ber=errors / len(bits),
+                crc_pass=crc_ok, coded_bits_length=len(coded), papr_db=papr_db, papr_linear=papr_lin,
+                decoded_blocks=dec, code_blocks=blocks)

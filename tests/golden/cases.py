@@ -96,3 +96,16 @@ BF_CASES = [
     dict(name='bf_2x2_adaptive_10mhz_64qam', bw=10.0, mod='64-QAM', T=2, R=2, cb='TM6', upd='adaptive', v=3.0,
          nsym=2, snrs=[15.0], gseed=95),
 ]
+
+# coded chain, OFDMSimulator.simulate_siso_coded (core/ofdm_core.py:925-1338)
+CODED_CASES = [
+    dict(name='coded_1p25mhz_qpsk_awgn', bw=1.25, mod='QPSK', ch='awgn', prof='Pedestrian_A', v=0.0,
+         nbits=200, snrs=[-1.0, 3.0], seed=61),
+    dict(name='coded_1p25mhz_16qam_peda', bw=1.25, mod='16-QAM', ch='rayleigh_mp', prof='Pedestrian_A', v=3.0,
+         nbits=333, snrs=[8.0, 16.0], seed=62),
+    dict(name='coded_2p5mhz_64qam_veha', bw=2.5, mod='64-QAM', ch='rayleigh_mp', prof='Vehicular_A', v=30.0,
+         nbits=500, snrs=[16.0, 26.0], seed=63),
+    # two code blocks (B = 6224 > 6144: K- / K+ split, CRC-24B per block)
+    dict(name='coded_5mhz_qpsk_awgn_2blocks', bw=5.0, mod='QPSK', ch='awgn', prof='Pedestrian_A', v=0.0,
+         nbits=6200, snrs=[1.0, 5.0], seed=64),
+]

@@ -32,7 +32,7 @@ from core.resource_mapper import LTEResourceGrid, PilotPattern  # noqa: E402
 from core.modulator import QAMModulator  # noqa: E402
 
 sys.path.insert(0, HERE)
-from cases import SISO_CASES, SIMO_CASES, SFBC_CASES, SM_CASES, PAPR_CASES, BF_CASES, BIG_RX_STRIDE  # noqa: E402
+from cases import SISO_CASES, SIMO_CASES, SFBC_CASES, SM_CASES, PAPR_CASES, BF_CASES, CODED_CASES, BIG_RX_STRIDE  # noqa: E402
 
 
 def quiet(fn, *a, **k):
@@ -234,12 +234,84 @@ def bf_case(case):
     print(case['name'], {s: int(out[f'errors_{s}']) for s in case['snrs']})
 
 
+def coding_tables():
+    """Known-answer vectors of the channel-coding building blocks (core/channel_coding/*.py) and of the
+    soft demappers (core/ofdm_core.py:791-923)."""
+    from core.channel_coding.crc import calculate_crc24a, calculate_crc24b
+    from core.channel_coding.rate_matching import rate_dematching_turbo, rate_match_turbo
+    from core.channel_coding.segmentation import segment_code_blocks
+    from core.channel_coding.turbo_decoder import turbo_decode
+    from core.channel_coding.turbo_encoder import QPP_INTERLEAVER_PARAMS, turbo_encode
+    out = {'qpp': np.array([[k, f1, f2] for k, (f1, f2) in sorted(QPP_INTERLEAVER_PARAMS.items())], dtype=np.int32)}
+    rs = np.random.RandomState(7)
+    for n in (1, 24, 100, 1001):
+        b = rs.randint(0, 2, n).astype(np.uint8)
+        out[f'crc_in_{n}'] = b
+        out[f'crc24a_{n}'] = calculate_crc24a(b)
+        out[f'crc24b_{n}'] = calculate_crc24b(b)
+    for B in (40, 41, 100, 6144, 6145, 13000, 20011):
+        tb = rs.randint(0, 2, B).astype(np.uint8)
+        blocks, meta = quiet(segment_code_blocks, tb)
+        out[f'seg_in_{B}'] = tb
+        out[f'seg_sizes_{B}'] = np.array(meta['block_sizes'])
+        out[f'seg_out_{B}'] = np.concatenate(blocks)
+    for K in (40, 104, 512, 6144):
+        u = rs.randint(0, 2, K).astype(np.uint8)
+        enc = turbo_encode(u)
+        out[f'enc_in_{K}'], out[f'enc_out_{K}'] = u, enc
+        out[f'rm_out_{K}'] = rate_match_turbo(enc, len(enc), K, rv_idx=0)
+        l = rs.randn(3 * K + 12)
+        out[f'dm_in_{K}'], out[f'dm_out_{K}'] = l, rate_dematching_turbo(l, K, rv_idx=0)
+    for K, sigma in ((40, 0.9), (104, 1.1), (512, 1.25)):
+        u = rs.randint(0, 2, K).astype(np.uint8)
+        enc = turbo_encode(u)
+        l = 2.0 * (1.0 - 2.0 * enc + sigma * rs.randn(len(enc))) / sigma ** 2
+        out[f'dec_bits_{K}'], out[f'dec_llr_{K}'] = u, l
+        out[f'dec_out_{K}'] = turbo_decode(l, K=K, num_iterations=8)
+    sim = quiet(OFDMSimulator, LTEConfig(1.25, 15.0, 'QPSK'))
+    y = (rs.randn(300) + 1j * rs.randn(300)) * 0.8
+    nv = 0.05 + rs.rand(300)
+    out['llr_sym'], out['llr_nv'] = y, nv
+    out['llr_QPSK'] = sim._calculate_llrs_qpsk(y, nv)
+    out['llr_16-QAM'] = sim._calculate_llrs_16qam(y, nv)
+    out['llr_64-QAM'] = sim._calculate_llrs_64qam(y, nv)
+    np.savez_compressed(os.path.join(HERE, 'coding_tables.npz'), **out)
+    print('wrote coding_tables')
+
+
+def coded_case(case):
+    cfg = LTEConfig(case['bw'], 15.0, case['mod'], 'normal')
+    sim = quiet(OFDMSimulator, cfg, channel_type=case['ch'], itu_profile=case['prof'], frequency_ghz=2.0,
+                velocity_kmh=case['v'])
+    bits = make_bits(case['seed'], case['nbits'])
+    out = dict(bits=np.packbits(bits), nbits=len(bits))
+    for snr in case['snrs']:
+        r = quiet(sim.simulate_siso_coded, bits, snr_db=snr)
+        out[f'errors_{snr}'] = r['bit_errors']
+        out[f'bits_rx_{snr}'] = np.packbits(r['bits_received_array'].astype(np.uint8))
+        out[f'scalars_{snr}'] = np.array([float(r['crc_pass']), r['coded_bits_length'], r['papr_db'],
+                                          r['noise_var_mean']])
+        out[f'symbols_rx_{snr}'] = r['symbols_rx']
+        out[f'H_{snr}'] = r['H_estimate']
+    out['signal_tx'] = r['signal_tx']
+    np.savez_compressed(os.path.join(HERE, case['name'] + '.npz'), **out)
+    print(case['name'], {s: int(out[f'errors_{s}']) for s in case['snrs']})
+
+
 def main():
+    if 'coded' in sys.argv[1:]:       # only the channel-coding fixtures
+        coding_tables()
+        for case in CODED_CASES:
+            coded_case(case)
+        return
     if 'bf' in sys.argv[1:]:          # only the beamforming fixtures
         for case in BF_CASES:
             bf_case(case)
         return
     tables()
+    coding_tables()
+    for case in CODED_CASES:
+        coded_case(case)
     for case in BF_CASES:
         bf_case(case)
     for case in PAPR_CASES:
