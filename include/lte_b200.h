@@ -53,6 +53,8 @@ extern "C" {
 #define LTE_BF_MRT 0       /* BeamformingPrecoder.calculate_mrt_weights (update_mode='adaptive') */
 #define LTE_BF_CODEBOOK 1  /* LTECodebook.select_best_pmi precoder (update_mode='static') */
 
+#define LTE_BLK_COLS 8     /* int32 columns of the code-block layout table (lte_tb_encode / lte_tb_decode) */
+
 #define LTE_WINDOW_FULL 0
 #define LTE_WINDOW_USEFUL 1
 
@@ -306,6 +308,44 @@ int lte_bf_link(const lte_plan*, const uint8_t* idx, const lte_c32* h, const lte
                 const lte_c32* heff, const float* noise_std, const float* z, uint64_t seed,
                 uint64_t row_id0, lte_c32* out, unsigned long long* errors, int64_t nbits, int64_t B,
                 int32_t R, int32_t T, int32_t S, void* stream);
+
+/* --- coded chain (CRC + turbo code + soft demapping) ----------------------
+ * Replaces the channel-coding layers OFDMSimulator.simulate_siso_coded adds around the SISO chain
+ * (core/ofdm_core.py:925-1338).  One stream = one transport block of A bits.  The block structure
+ * depends only on A; the host lays it out once (lte_b200/coding.py) as device-resident int32 tables:
+ *   blk [C][LTE_BLK_COLS] = {K, filler F, info bits n, offset into (bits ++ crc24a), offset into the
+ *        code-block row, offset into the encoded row, has CRC-24B, offset into pi_tab}
+ *   rm_table [sumE], dm_table [sumE] (sumE = sum_r 3 K_r + 12; -1 = constant 0), pi_tab (QPP
+ *   permutations pi(i) = (f1 i + f2 i^2) mod K of the distinct K).
+ * lte_tb_encode: attach_crc24a (core/channel_coding/crc.py:204-232), segment_code_blocks
+ *   (segmentation.py:66-199), turbo_encode (turbo_encoder.py:112-259, whose RSC emits the feedback
+ *   bit as "systematic"), rate_match_turbo with E = 3K+12, rv 0 (rate_matching.py:27-229).
+ *   bits [B][A] bytes 0/1 -> coded [B][sumE]; crc [B][24], cb [B][sumK], enc [B][sumE] are scratch.
+ * lte_symbol_interleave: QAM map + the rows x Nd block interleaver of core/ofdm_core.py:1037-1060
+ *   (complex-zero padding): idx [B][nsym] -> out [B][rows*Nd], ready for lte_tx_map_ifft(symbols=out).
+ * lte_soft_demap: de-interleave (:1180-1215), per-symbol noise variance (:1228-1250) and the LLRs of
+ *   _calculate_llrs_qpsk/_16qam/_64qam (:791-923): data [B][rows*Nd] equalised symbols in received
+ *   order, H [B][ceil(rows/14)][nk] channel estimates (window as in lte_crs_ls_interp), sigma2 [B] =
+ *   10^(-snr/10), fading != 0 selects the |H|^2-scaled variance -> llr [B][nsym*bits_per_symbol].
+ * lte_tb_decode: rate_dematching_turbo (rate_matching.py:297-396), turbo_decode in its default
+ *   max-log mode (turbo_decoder.py:158-446; `iterations` full iterations + the final decoder-1
+ *   pass), desegment_code_blocks (segmentation.py:202-270), check_crc24a and the BER count
+ *   (core/ofdm_core.py:1283-1307).  llr [B][sumE]; dematched [B][sumE] and work
+ *   [B*C][lte_tb_decode_work_floats(Kmax)] floats and cbdec [B][sumK] are scratch; bits_tx (optional)
+ *   [B][A]; outputs (each optional) bits_rx [B][A], crc_ok [B] int32, errors [B] uint64. */
+int lte_tb_encode(const uint8_t* bits, int64_t A, const int32_t* blk, int32_t C, int64_t sumK,
+                  int64_t sumE, const int32_t* rm_table, const int32_t* pi_tab, uint8_t* crc,
+                  uint8_t* cb, uint8_t* enc, uint8_t* coded, int64_t B, void* stream);
+int lte_symbol_interleave(const lte_plan*, const uint8_t* idx, int64_t nsym, int32_t rows, lte_c32* out,
+                          int64_t B, void* stream);
+int lte_soft_demap(const lte_plan*, const lte_c32* data, const lte_c32* H, int window,
+                   const float* sigma2, int32_t fading, int64_t nsym, int32_t rows, float* llr, int64_t B,
+                   void* stream);
+int64_t lte_tb_decode_work_floats(int32_t Kmax);
+int lte_tb_decode(const float* llr, const int32_t* blk, int32_t C, int64_t sumK, int64_t sumE, int32_t Kmax,
+                  const int32_t* dm_table, const int32_t* pi_tab, int32_t iterations, float* dematched,
+                  float* work, uint8_t* cbdec, int64_t A, const uint8_t* bits_tx, uint8_t* bits_rx,
+                  int32_t* crc_ok, unsigned long long* errors, int64_t B, void* stream);
 
 /* --- stage 6: hard demap + bit-error count -------------------------------------------
  * replaces QAMModulator.symbols_to_bits (core/modulator.py:90-112) and

@@ -466,6 +466,62 @@ class OFDMSimulator:
     def simulate_mimo(self, bits, snr_db: float = 10.0, num_rx: int = 2) -> Dict:
         return self._simulate_sfbc(bits, snr_db, num_rx, 'MIMO-SFBC')
 
+    # ------------------------------------------------------------------ coded SISO
+    def calculate_noise_var_zf(self, H_estimate, snr_db: float) -> float:
+        """Effective noise variance after ZF from the harmonic mean of |H|^2 (reference :739-789)."""
+        H = np.atleast_1d(np.asarray(H_estimate))
+        nv = 1.0 / (10 ** (snr_db / 10))
+        if H.size == 0:
+            return nv
+        hp = np.maximum(np.abs(H) ** 2, 1e-12)
+        return float(nv / hp[0]) if len(hp) == 1 else float(nv / (len(hp) / np.sum(1.0 / hp)))
+
+    def simulate_siso_coded(self, bits, snr_db: float = 10.0) -> Dict:
+        """SISO link with CRC-24A, code-block segmentation, the rate-1/3 turbo code, rate matching, a
+        symbol block interleaver, max-log LLRs and 8 max-log BCJR iterations (reference :925-1338).
+        TX coding, interleaving, soft demapping and decoding are the kernels of csrc/coding.cu; the OFDM
+        transmitter, channel, FFT, CRS estimate and ZF equaliser are the ones simulate_siso uses."""
+        bits = self._check_bits(bits)
+        eng = be.engine_for(self.config)
+        b_t = be.as_bits_tensor(bits)
+        nbits = b_t.shape[1]
+        plan = eng.coding_plan(nbits)
+        tx, rows, nsym, stats = eng.coded_tx(b_t, plan)
+        self._pilot_side_effect()
+        papr = self.tx._papr_from_stats(be.to_numpy(stats)[0], tx.shape[1])
+        self.channels[0].set_snr(snr_db)
+        sid = self._draws.next_stream() if self._draws.kind == 'philox' else 0
+        rx = self.channels[0].channel._transmit_device(tx, row_id0=sid)
+        fading = self.channels[0].channel_type != 'awgn'
+        sigma2 = torch.full((1,), 1.0 / (10 ** (snr_db / 10)), dtype=torch.float32, device=tx.device)
+        r = eng.coded_rx(rx.reshape(1, -1), plan, rows, nsym, sigma2, fading, bits_tx=b_t)
+        self._pilot_side_effect()
+        bits_rx = be.to_numpy(r['bits_rx'].reshape(-1), np.int64)
+        bit_errors = int(r['errors'].item())
+        # de-interleaved views of what the demapper consumed (reference result keys)
+        Nd = eng.Nd
+        k0, nk = eng.window(nat.WINDOW_USEFUL)
+        data = r['data'].reshape(Nd, rows).T.reshape(-1)[:nsym]
+        didx = torch.as_tensor(np.asarray(eng.data_idx) - k0, device=tx.device, dtype=torch.long)
+        Hd = r['H'].reshape(-1, nk)[:, didx].repeat_interleave(nat.LTE_SLOT_SYMBOLS, dim=0)[:rows]
+        Hd = Hd.reshape(-1).reshape(Nd, rows).T.reshape(-1)[:nsym]
+        s2 = 1.0 / (10 ** (snr_db / 10))
+        if fading:
+            nv = torch.clamp(s2 / torch.clamp(Hd.abs() ** 2, 1e-6, 1e6), min=s2 / 4.0)
+            nv_mean = float(nv.mean())
+        else:
+            nv_mean = s2
+        results = {
+            'transmitted_bits': int(nbits), 'received_bits': int(nbits), 'bits_received_array': bits_rx,
+            'bit_errors': bit_errors, 'ber': float(bit_errors / nbits), 'crc_pass': bool(r['crc_ok'].item()),
+            'snr_db': float(snr_db), 'papr_db': float(papr['papr_db']), 'papr_linear': float(papr['papr_linear']),
+            'coded_bits_length': int(plan.sumE), 'signal_tx': be.to_numpy(tx.reshape(-1)),
+            'signal_rx': be.to_numpy(rx.reshape(-1)), 'symbols_rx': be.to_numpy(data), 'H_estimate': be.to_numpy(Hd),
+            'channel_snr_db': 0.0, 'noise_var_mean': nv_mean, 'llrs': be.to_numpy(r['llr'].reshape(-1)),
+        }
+        self.last_results = results
+        return results
+
     # ------------------------------------------------------------------ beamforming (SURVEY 8 f-3)
     def simulate_beamforming(self, bits, snr_db: float = 10.0, num_tx: int = 2, num_rx: int = 1,
                              codebook_type: str = 'TM6', velocity_kmh: float = 3.0,

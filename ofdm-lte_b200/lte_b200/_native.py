@@ -22,6 +22,7 @@ LTE_JAKES_TONES = 16
 LTE_SLOT_SYMBOLS = 14
 LTE_MAX_RX = 8
 LTE_MAX_TX = 8
+LTE_BLK_COLS = 8
 BF_MRT = 0
 BF_CODEBOOK = 1
 WINDOW_FULL = 0
@@ -82,6 +83,12 @@ _SIGS = {
     'lte_mrc_demap_count': ([_P, _P, _P, _P, _P, C.c_int, _I64, _I64, _I32, _I32, _P], C.c_int),
     'lte_random_indices': ([_P, _P, _I64, _I64, _U64, _U64, _P], C.c_int),
     'lte_random_phases': ([_P, _I64, _I64, _U64, _U64, _P], C.c_int),
+    'lte_tb_encode': ([_P, _I64, _P, _I32, _I64, _I64, _P, _P, _P, _P, _P, _P, _I64, _P], C.c_int),
+    'lte_symbol_interleave': ([_P, _P, _I64, _I32, _P, _I64, _P], C.c_int),
+    'lte_soft_demap': ([_P, _P, _P, C.c_int, _P, _I32, _I64, _I32, _P, _I64, _P], C.c_int),
+    'lte_tb_decode_work_floats': ([_I32], C.c_int64),
+    'lte_tb_decode': ([_P, _P, _I32, _I64, _I64, _I32, _P, _P, _I32, _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _P],
+                      C.c_int),
     'lte_random_channel': ([_P, _I64, _I32, _I32, _U64, _U64, _P], C.c_int),
     'lte_bf_weights': ([_P, _P, _I32, _I32, _P, _P, _P, _P, _I64, _I32, _I32, _P], C.c_int),
     'lte_bf_link': ([_P, _P, _P, _P, _P, _P, _P, _U64, _U64, _P, _P, _I64, _I64, _I32, _I32, _I32, _P], C.c_int),

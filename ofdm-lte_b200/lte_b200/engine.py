@@ -372,6 +372,112 @@ class LinkEngine:
         errors, _ = self.demap_count(data, idx_tx=idx, nbits=nbits)
         return errors
 
+    # ------------------------------------------------------------------ coded chain
+    def coding_plan(self, A):
+        """Cached layout tables of a transport block of A bits (lte_b200/coding.py)."""
+        from .coding import CodingPlan
+        plans = self.__dict__.setdefault('_coding_plans', {})
+        if A not in plans:
+            plans[A] = CodingPlan(A, self.device)
+        return plans[A]
+
+    def tb_encode(self, bits, plan):
+        """bits uint8 [B, A] of 0/1 -> rate-matched coded bits uint8 [B, sumE]
+        (CRC-24A, segmentation + CRC-24B, turbo encoder, rate matching)."""
+        B = bits.shape[0]
+        crc = self._empty((B, 24), torch.uint8)
+        cb = self._empty((B, plan.sumK), torch.uint8)
+        enc = self._empty((B, plan.sumE), torch.uint8)
+        coded = self._empty((B, plan.sumE), torch.uint8)
+        nat.check(nat.lib.lte_tb_encode(_ptr(bits), plan.A, _ptr(plan.blk), plan.C, plan.sumK, plan.sumE,
+                                        _ptr(plan.rm_table), _ptr(plan.pi_tab), _ptr(crc), _ptr(cb), _ptr(enc),
+                                        _ptr(coded), B, self._stream()), 'lte_tb_encode')
+        self.launches += 4
+        return coded
+
+    def symbol_interleave(self, idx, rows):
+        """idx uint8 [B, nsym] -> QAM symbols through the rows x Nd block interleaver, complex64 [B, rows*Nd]."""
+        B, nsym = idx.shape
+        out = self._empty((B, rows * self.Nd), torch.complex64)
+        nat.check(nat.lib.lte_symbol_interleave(self._plan, _ptr(idx), nsym, rows, _ptr(out), B, self._stream()),
+                  'lte_symbol_interleave')
+        self.launches += 1
+        return out
+
+    def soft_demap(self, data, H, sigma2, fading, nsym, rows, window=nat.WINDOW_FULL):
+        """data [B, rows*Nd] equalised symbols (received order), H [B, nslot, nk], sigma2 float32 [B] ->
+        de-interleaved LLRs float32 [B, nsym*bps]."""
+        B = data.shape[0]
+        llr = self._empty((B, nsym * self.bps), torch.float32)
+        nat.check(nat.lib.lte_soft_demap(self._plan, _ptr(data), _ptr(H), window, _ptr(sigma2), 1 if fading else 0,
+                                         nsym, rows, _ptr(llr), B, self._stream()), 'lte_soft_demap')
+        self.launches += 1
+        return llr
+
+    def tb_decode(self, llr, plan, iterations=8, bits_tx=None, want_bits=True):
+        """llr float32 [B, sumE] -> (bits_rx uint8 [B, A] or None, crc_ok int32 [B], errors int64 [B] or None)."""
+        B = llr.shape[0]
+        dem = self._empty((B, plan.sumE), torch.float32)
+        work = self._empty((B * plan.C, plan.work_floats), torch.float32)
+        cbdec = self._empty((B, plan.sumK), torch.uint8)
+        bits_rx = self._empty((B, plan.A), torch.uint8) if want_bits else None
+        crc_ok = self._empty((B,), torch.int32)
+        errors = torch.zeros(B, dtype=torch.int64, device=self.device) if bits_tx is not None else None
+        nat.check(nat.lib.lte_tb_decode(_ptr(llr), _ptr(plan.blk), plan.C, plan.sumK, plan.sumE, plan.Kmax,
+                                        _ptr(plan.dm_table), _ptr(plan.pi_tab), int(iterations), _ptr(dem), _ptr(work),
+                                        _ptr(cbdec), plan.A, _ptr(bits_tx), _ptr(bits_rx), _ptr(crc_ok), _ptr(errors),
+                                        B, self._stream()), 'lte_tb_decode')
+        self.launches += 3
+        return bits_rx, crc_ok, errors
+
+    def coded_tx(self, bits, plan):
+        """bits [B, A] -> (tx [B, rows*L], rows, nsym): coding chain, QAM map, interleaver, grid + IFFT + CP."""
+        coded = self.tb_encode(bits, plan)
+        nsym = -(-plan.sumE // self.bps)
+        idx = self._coded_indices(coded, plan, nsym)
+        rows = -(-nsym // self.Nd)
+        sym = self.symbol_interleave(idx, rows)
+        tx, _, stats = self.modulate(rows, symbols=sym, want_stats=True)
+        return tx, rows, nsym, stats
+
+    def _coded_indices(self, coded, plan, nsym):
+        B = coded.shape[0]
+        idx = self._empty((B, nsym), torch.uint8)
+        nat.check(nat.lib.lte_bits_to_indices(self._plan, _ptr(coded), plan.sumE, _ptr(idx), nsym, B, self._stream()),
+                  'lte_bits_to_indices')
+        self.launches += 1
+        return idx
+
+    def coded_rx(self, rx, plan, rows, nsym, sigma2, fading, bits_tx=None, iterations=8, want_bits=True):
+        """rx [B, rows*L] noisy received streams -> dict(bits_rx, crc_ok, errors, symbols, H, llr)."""
+        B = rx.shape[0]
+        Y = self.rx_fft(rx, B, rows, nat.WINDOW_USEFUL)
+        H = self.estimate(Y, B, rows, nat.WINDOW_USEFUL)
+        data = self.zf(Y, H, B, rows, nat.WINDOW_USEFUL)
+        llr = self.soft_demap(data, H, sigma2, fading, nsym, rows, nat.WINDOW_USEFUL)
+        bits_rx, crc_ok, errors = self.tb_decode(llr[:, :plan.sumE].contiguous(), plan, iterations, bits_tx, want_bits)
+        return dict(bits_rx=bits_rx, crc_ok=crc_ok, errors=errors, data=data, H=H, llr=llr)
+
+    def siso_coded_ber(self, bits, chan, snr_db_rows, seed, stream_id0=0, iterations=8):
+        """One pass of the coded SISO chain over B streams with Philox channel / noise draws (time-domain
+        AWGN from the measured stream power, as the reference).  bits uint8 [B, A]; snr_db_rows: float32 [B] in dB.
+        Returns (errors int64 [B], crc_ok int32 [B])."""
+        B, A = bits.shape
+        plan = self.coding_plan(A)
+        tx, rows, nsym, _ = self.coded_tx(bits, plan)
+        snr_lin = torch.pow(10.0, snr_db_rows / 10.0).contiguous()
+        if chan.num_taps > 0:
+            ph = self.random_phases(B, chan.num_taps * nat.LTE_JAKES_TONES, seed, stream_id0)
+            faded, power = self.channel(tx, chan, B, 1, phases=ph)
+            rx = self.awgn(faded.view(B, -1), 1, power, snr_lin, B, seed=seed, row_id0=stream_id0)
+        else:
+            _, power = self.channel(tx, chan, B, 1)
+            rx = self.awgn(tx, 1, power, snr_lin, B, seed=seed, row_id0=stream_id0)
+        sigma2 = (1.0 / snr_lin).contiguous()
+        r = self.coded_rx(rx, plan, rows, nsym, sigma2, chan.num_taps > 0, bits_tx=bits, iterations=iterations,
+                          want_bits=False)
+        return r['errors'], r['crc_ok']
+
     # ------------------------------------------------------------------ beamforming (SURVEY 8 f-3)
     def random_channel(self, B, R, T, seed, stream_id0=0):
         """Flat channel matrices h [B, R, T] ~ CN(0, 1), Philox keyed (seed, stream_id0 + b)."""

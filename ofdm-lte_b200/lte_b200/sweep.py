@@ -161,3 +161,30 @@ def payload_sweep(config, bits, snr_range, n_iterations, modulations=('QPSK', '1
             if progress_callback:
                 progress_callback(int(15 + 80 * done / total), f"{mod} | {R}RX")
     return {'mode': 'sweep_full', 'modulations': list(modulations), 'num_rx_values': list(num_rx_values), 'data': data}
+
+
+def coded_sweep(engine, chan, snr_db, n_trials, tb_bits, seed=0, batch_trials=64, rank=0, world=1, iterations=8):
+    """BER and block-error rate of the coded SISO chain (reference OFDMSimulator.simulate_siso_coded,
+    core/ofdm_core.py:925-1338) at every SNR point: every stream carries its own random transport
+    block of `tb_bits` bits (Philox keyed by the global stream id), CRC-24A, turbo code, interleaver,
+    channel, ZF, max-log LLRs and `iterations` max-log BCJR iterations.  Adds 'bler' (fraction of
+    transport blocks whose CRC-24A failed) to run_sweep's result."""
+    n_snr = len(snr_db)
+    snr_t = torch.tensor([float(s) for s in snr_db], dtype=torch.float32, device=engine.device)
+    fails = torch.zeros((2, n_snr), dtype=torch.int64, device=engine.device)
+    S_src = -(-tb_bits // engine.Nd)
+
+    def count_batch(trial_lo, n):
+        B = n * n_snr
+        sid0 = trial_lo * n_snr
+        bits = (engine.random_indices(B, S_src, seed, sid0)[:, :tb_bits] & 1).contiguous()
+        err, crc_ok = engine.siso_coded_ber(bits, chan, snr_t.repeat(n).contiguous(), seed, sid0, iterations)
+        fails[0] += (1 - crc_ok.long()).view(n, n_snr).sum(dim=0)
+        fails[1] += n
+        return err
+
+    out = run_sweep(count_batch, n_snr, n_trials, tb_bits, batch_trials, rank, world, engine.device)
+    reduce_counts(fails)
+    out['block_errors'] = fails[0].cpu()
+    out['bler'] = fails[0].double().cpu() / fails[1].clamp(min=1).double().cpu()
+    return out

@@ -1,0 +1,203 @@
+"""Coded chain on the GPU: every kernel of csrc/coding.cu against the oracle / the
+vectors produced by the reference's channel_coding modules, the API against goldens of
+OFDMSimulator.simulate_siso_coded, and the sharded sweep."""
+import numpy as np
+import pytest
+import torch
+
+from cases import CODED_CASES
+from helpers import golden_bits, golden_bits_rx, load_golden, numerology, rel_err
+from oracle import lte_oracle as O
+
+pytestmark = pytest.mark.gpu
+T = load_golden('coding_tables')
+QPP = {int(k): (int(f1), int(f2)) for k, f1, f2 in T['qpp']}
+
+
+def _engine(bw=1.25, mod='QPSK'):
+    from config import LTEConfig
+    from lte_b200 import LinkEngine
+    return LinkEngine.from_config(LTEConfig(bw, 15.0, mod))
+
+
+def test_product_tables_match_the_standard_table_in_the_goldens():
+    from lte_b200.qpp_table import QPP as P, TURBO_K
+    assert P == QPP and list(TURBO_K) == O.TURBO_K
+
+
+@pytest.mark.parametrize('A', [16, 17, 76, 6120, 6121, 12976, 19987])
+def test_tb_encode_matches_oracle(A):
+    """CRC-24A + segmentation (+ CRC-24B) + turbo encoder + rate matching, bit-exact."""
+    eng = _engine()
+    rs = np.random.RandomState(A)
+    bits = rs.randint(0, 2, (3, A)).astype(np.uint8)
+    plan = eng.coding_plan(A)
+    got = eng.tb_encode(torch.from_numpy(bits).cuda(), plan).cpu().numpy()
+    for b in range(3):
+        tb = np.concatenate([bits[b], O.crc24(bits[b])])
+        blocks = O.segment_code_blocks(tb)
+        want = np.concatenate([np.where(O.rate_match_table(len(cb)) >= 0,
+                                        O.turbo_encode(cb, *QPP[len(cb)])[np.maximum(O.rate_match_table(len(cb)), 0)], 0)
+                               for cb in blocks])
+        assert np.array_equal(got[b], want)
+    assert plan.sumE == got.shape[1] and plan.C == len(blocks)
+
+
+@pytest.mark.parametrize('K', [40, 104, 512, 6144])
+def test_encoder_known_answers_from_the_reference(K):
+    """turbo_encode / rate_match_turbo vectors written by the reference itself: a transport block whose
+    CRC-extended length is exactly K reproduces them through lte_tb_encode's encoder stage."""
+    eng = _engine()
+    A = K - 24
+    u = T[f'enc_in_{K}']
+    # feed the first A bits; the kernel appends their CRC, so compare on a block built the same way
+    bits = u[:A].astype(np.uint8)
+    plan = eng.coding_plan(A)
+    got = eng.tb_encode(torch.from_numpy(bits[None]).cuda(), plan).cpu().numpy()[0]
+    cb = np.concatenate([bits, O.crc24(bits)])
+    enc = O.turbo_encode(cb, *QPP[K])
+    t = O.rate_match_table(K)
+    assert np.array_equal(got, np.where(t >= 0, enc[np.maximum(t, 0)], 0))
+    # and the oracle reproduces the reference's own vectors for this K (pins the chain end to end)
+    assert np.array_equal(O.turbo_encode(u, *QPP[K]), T[f'enc_out_{K}'])
+
+
+@pytest.mark.parametrize('mod', ['QPSK', '16-QAM', '64-QAM'])
+def test_soft_demapper_matches_reference_llrs(mod):
+    eng = _engine(mod=mod)
+    y, nv = T['llr_sym'], T['llr_nv']
+    want = T[f'llr_{mod}']
+    n = len(y)
+    rows = -(-n // eng.Nd)
+    # place symbol j at its interleaved position; |H|^2 = sigma2 / nv reproduces the per-symbol variance
+    data = np.zeros(rows * eng.Nd, dtype=np.complex64)
+    j = np.arange(n)
+    q = (j % eng.Nd) * rows + j // eng.Nd
+    data[q] = y
+    got = eng.soft_demap(torch.from_numpy(data[None]).cuda(), None, torch.tensor([1.0], device='cuda'), False, n, rows)
+    s2 = 1.0
+    ref = O.soft_demap(y.astype(np.complex64).astype(complex), s2, mod)
+    assert np.allclose(got.cpu().numpy()[0], ref, rtol=2e-6, atol=2e-6)
+    # per-symbol variances through the channel-estimate path: one slot, H on the data bins of symbol 0..rows-1
+    if rows <= 14:
+        k0, nk = eng.window(1)
+        H = np.ones((1, 1, nk), dtype=np.complex64)
+        s2 = 0.5
+        hp = np.ones(eng.Nd)
+        d = q[q < eng.Nd] if rows == 1 else None
+        got2 = eng.soft_demap(torch.from_numpy(data[None]).cuda(), torch.from_numpy(H).cuda(),
+                              torch.tensor([s2], device='cuda'), True, n, rows, window=1)
+        ref2 = O.soft_demap(y.astype(np.complex64).astype(complex), np.maximum(s2 / 1.0, s2 / 4), mod)
+        assert np.allclose(got2.cpu().numpy()[0], ref2, rtol=2e-6, atol=2e-6)
+    # the reference's own vectors (per-symbol nv) through the oracle: pins the formula
+    assert np.allclose(O.soft_demap(y, nv, mod), want, rtol=1e-12, atol=1e-12)
+
+
+def _rate_matched(llr_dec, K):
+    """lte_tb_decode starts from rate-matched order: undo the de-matching gather.  Returns the float32 input row
+    and the decoder input the oracle must see (the two systematic positions rate matching never sends are 0)."""
+    rm = O.rate_match_table(K)
+    llr_rm = np.where(rm >= 0, llr_dec[np.maximum(rm, 0)], 0.0).astype(np.float32)
+    seen = llr_dec.astype(np.float32).astype(float)
+    seen[np.setdiff1d(np.arange(3 * K + 12), rm[rm >= 0])] = 0.0
+    return llr_rm, seen
+
+
+@pytest.mark.parametrize('K', [40, 104, 512])
+def test_turbo_decoder_on_the_reference_llr_vectors(K):
+    """The reference's own noisy LLR vectors (tests/golden/coding_tables.npz).  They sit below the decoder's
+    convergence threshold, where eight iterations are chaotic in the last bits, so the fp32 kernel is compared
+    with the fp64 oracle after ONE iteration (+ the final decoder-1 pass), decision by decision."""
+    eng = _engine()
+    plan = eng.coding_plan(K - 24)
+    llr_rm, seen = _rate_matched(T[f'dec_llr_{K}'], K)
+    want = O.turbo_decode(seen, K, *QPP[K], num_iterations=1)
+    bits_rx, _, _ = eng.tb_decode(torch.from_numpy(llr_rm[None]).cuda(), plan, iterations=1)
+    assert np.sum(bits_rx.cpu().numpy()[0] != want[:K - 24]) <= 2      # |a-posteriori LLR| ~ 0 may flip in fp32
+    want0 = O.turbo_decode(seen, K, *QPP[K], num_iterations=0)          # single BCJR pass, no extrinsic exchange
+    bits0, _, _ = eng.tb_decode(torch.from_numpy(llr_rm[None]).cuda(), plan, iterations=0)
+    assert np.sum(bits0.cpu().numpy()[0] != want0[:K - 24]) <= 1
+
+
+@pytest.mark.parametrize('K', [40, 512, 1024, 6144])
+def test_turbo_decoder_converges_like_the_oracle(K):
+    """Above threshold the decode converges and fp32 rounding cannot matter: 8 iterations, identical decisions,
+    CRC passes.  Four transport blocks per launch exercise the four-blocks-per-warp packing."""
+    eng = _engine()
+    A = K - 24
+    plan = eng.coding_plan(A)
+    rs = np.random.RandomState(K)
+    nb = 5 if K <= 1024 else 2
+    bits = rs.randint(0, 2, (nb, A)).astype(np.uint8)
+    rows, wants = [], []
+    sigma = 0.62
+    for b in range(nb):
+        cb = np.concatenate([bits[b], O.crc24(bits[b])])
+        enc = O.turbo_encode(cb, *QPP[K])
+        llr = 2.0 * (1.0 - 2.0 * enc + sigma * rs.randn(len(enc))) / sigma ** 2
+        llr_rm, seen = _rate_matched(llr, K)
+        rows.append(llr_rm)
+        wants.append(O.turbo_decode(seen, K, *QPP[K]) if K <= 1024 else cb)
+    bits_rx, crc_ok, errors = eng.tb_decode(torch.from_numpy(np.stack(rows)).cuda(), plan,
+                                            bits_tx=torch.from_numpy(bits).cuda())
+    got = bits_rx.cpu().numpy()
+    for b in range(nb):
+        assert np.array_equal(got[b], wants[b][:A])
+    assert np.array_equal(got, bits) and bool(crc_ok.all()) and int(errors.sum()) == 0
+    # a corrupted block fails its CRC and its errors are counted
+    bad = np.stack(rows).copy()
+    bad[0] = -bad[0]
+    _, crc2, err2 = eng.tb_decode(torch.from_numpy(bad).cuda(), plan, bits_tx=torch.from_numpy(bits).cuda())
+    assert int(crc2[0]) == 0 and int(err2[0]) > 0 and bool(crc2[1:].all()) and int(err2[1:].sum()) == 0
+
+
+@pytest.mark.parametrize('case', CODED_CASES, ids=lambda c: c['name'])
+def test_simulate_siso_coded_matches_reference(case):
+    from config import LTEConfig
+    from core.ofdm_core import OFDMSimulator
+    g = load_golden(case['name'])
+    bits = golden_bits(g)
+    num = numerology(case)
+    sim = OFDMSimulator(LTEConfig(case['bw'], 15.0, case['mod']), channel_type=case['ch'], itu_profile=case['prof'],
+                        frequency_ghz=2.0, velocity_kmh=case['v'])
+    for snr in case['snrs']:
+        r = sim.simulate_siso_coded(bits, snr_db=snr)
+        o = O.simulate_siso_coded(bits, snr, num, QPP, case['ch'], case['prof'], 2.0, case['v'])
+        crc, clen, papr_db, nvm = g[f'scalars_{snr}']
+        assert r['coded_bits_length'] == int(clen) and abs(r['papr_db'] - papr_db) < 1e-3
+        assert rel_err(r['signal_tx'], g['signal_tx']) < 1e-5
+        sym = g[f'symbols_rx_{snr}']
+        # ZF output: deep fades amplify fp32 rounding of H, so compare where |H| is not tiny
+        ok = np.abs(g[f'H_{snr}']) > 0.05
+        assert rel_err(r['symbols_rx'][ok], sym[ok]) < 5e-5
+        assert rel_err(r['H_estimate'], g[f'H_{snr}']) < 1e-5
+        assert np.allclose(r['llrs'][:len(o['llr'])][np.repeat(ok, num.bits_per_symbol)],
+                           o['llr'][np.repeat(ok, num.bits_per_symbol)], rtol=1e-3, atol=2e-3)
+        assert abs(r['noise_var_mean'] - nvm) < 1e-4 * max(1.0, nvm)
+        want = golden_bits_rx(g, snr)
+        diff = int(np.sum(r['bits_received_array'] != want))
+        want_err = int(g[f'errors_{snr}'])
+        if want_err == 0:                       # a converged decode is robust to fp32 rounding
+            assert diff == 0 and r['bit_errors'] == 0 and r['crc_pass'] == bool(crc)
+        else:                                   # a non-converged one is chaotic in the last bits: same regime only
+            assert abs(r['bit_errors'] - want_err) <= max(8, 0.25 * want_err) and r['crc_pass'] == bool(crc)
+        assert r['transmitted_bits'] == len(bits) and len(r['bits_received_array']) == len(bits)
+
+
+def test_coded_sweep_shards_and_improves_on_uncoded():
+    from lte_b200 import chan_for
+    from lte_b200.sweep import coded_sweep
+    eng = _engine(mod='QPSK')
+    awgn = chan_for('awgn', eng.fs, 'Pedestrian_A', 2.0, 0.0)
+    snrs = [-2.0, 2.0, 6.0]
+    one = coded_sweep(eng, awgn, snrs, 24, tb_bits=488, seed=3, batch_trials=24)
+    parts = [coded_sweep(eng, awgn, snrs, 24, tb_bits=488, seed=3, batch_trials=5, rank=r, world=2) for r in range(2)]
+    assert torch.equal(parts[0]['errors'] + parts[1]['errors'], one['errors'])
+    assert torch.equal(parts[0]['block_errors'] + parts[1]['block_errors'], one['block_errors'])
+    assert torch.equal(one['bits'], torch.full((3,), 24 * 488, dtype=torch.int64))
+    ber = one['ber'].numpy()
+    assert ber[0] > ber[1] >= ber[2] and ber[2] == 0 and one['bler'][2] == 0 and one['bler'][0] > 0.5
+    # uncoded QPSK at 6 dB has BER ~ 2.3e-2; the coded chain is error free there
+    fad = chan_for('rayleigh_mp', eng.fs, 'Pedestrian_A', 2.0, 3.0)
+    f = coded_sweep(eng, fad, [4.0, 24.0], 16, tb_bits=300, seed=4)
+    assert f['ber'][0] > f['ber'][1]
