@@ -331,7 +331,7 @@ int lte_bf_link(const lte_plan*, const uint8_t* idx, const lte_c32* h, const lte
  *   max-log mode (turbo_decoder.py:158-446; `iterations` full iterations + the final decoder-1
  *   pass), desegment_code_blocks (segmentation.py:202-270), check_crc24a and the BER count
  *   (core/ofdm_core.py:1283-1307).  llr [B][sumE]; dematched [B][sumE] and work
- *   [B*C][lte_tb_decode_work_floats(Kmax)] floats and cbdec [B][sumK] are scratch; bits_tx (optional)
+ *   [ceil(B*C/4)*4][lte_tb_decode_work_floats(Kmax)] floats and cbdec [B][sumK] are scratch; bits_tx (optional)
  *   [B][A]; outputs (each optional) bits_rx [B][A], crc_ok [B] int32, errors [B] uint64. */
 int lte_tb_encode(const uint8_t* bits, int64_t A, const int32_t* blk, int32_t C, int64_t sumK,
                   int64_t sumE, const int32_t* rm_table, const int32_t* pi_tab, uint8_t* crc,

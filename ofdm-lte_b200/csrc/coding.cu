@@ -259,7 +259,7 @@ extern "C" int lte_soft_demap(const lte_plan* p, const lte_c32* data, const lte_
 //   state = (s0 << 2) | (s1 << 1) | s2;  branch u: a = u ^ s1 ^ s2, parity = a ^ s0 ^ s2, next = (a << 2) | (s0 << 1) | s1
 //   gamma = (+-Ls +-Lp +-La) / 2 with Ls signed by a (the reference's "systematic" bit), La by u
 //   alpha_0 = beta_n = (0, -inf, ...) over n = K + 3 steps (tail included, a-priori 0 there)
-// Forward pass stores alpha in HBM scratch ([n + 1][8] floats per block, 32 B per step, lane-contiguous);
+// Forward pass stores alpha in HBM scratch ([n + 1][32] floats per warp = four blocks, one 128 B line per step);
 // the backward pass fuses the a-posteriori max over the 16 branches (xor-shuffle reductions in the 8-lane
 // group).  Extrinsic values cross the QPP interleaver through HBM scratch as well.
 struct Bcjr {
@@ -268,11 +268,16 @@ struct Bcjr {
     const float* ls_tail; const float* lp_tail;          // 3 tail LLRs each
 };
 
+// All shuffles use the full warp mask: the four code blocks of a warp step in lockstep over the longest of
+// their trellises (nch_w chunks), shorter or absent blocks just predicate their updates off.  (A per-group
+// mask makes nvcc wrap every shuffle in a MATCH/VOTE convergence loop -- 3x the instructions.)
+#define FULLMASK 0xffffffffu
+
 template <bool EXTRINSIC_OUT>
-__device__ __forceinline__ void bcjr_pass(const Bcjr in, int K, float* __restrict__ alpha, float* __restrict__ ext_out,
-                                          const int* __restrict__ scatter, uint8_t* __restrict__ bits_out,
-                                          unsigned gmask, int st) {
-    const int n = K + 3;
+__device__ __forceinline__ void bcjr_pass(const Bcjr in, int K, int nch_w, float* __restrict__ alpha,
+                                          float* __restrict__ ext_out, bool scatter, uint8_t* __restrict__ bits_out,
+                                          int st) {
+    const int n = K > 0 ? K + 3 : 0;                     // K == 0: padding group of the last warp
     const int s0 = (st >> 2) & 1, s1 = (st >> 1) & 1, s2 = st & 1;
     // outgoing branches of this state
     const int a0 = s1 ^ s2, a1 = 1 ^ s1 ^ s2;
@@ -288,53 +293,90 @@ __device__ __forceinline__ void bcjr_pass(const Bcjr in, int K, float* __restric
     const float ip0 = (pa ^ pp0 ^ 0) ? -0.5f : 0.5f, ip1 = (pa ^ pp0 ^ 1) ? -0.5f : 0.5f;
     const float iu0 = pu0 ? -0.5f : 0.5f, iu1 = pu1 ? -0.5f : 0.5f;
 
-    auto load = [&](int k, float& Ls, float& Lp, float& La) {
+    // The LLRs of a step are the same for the eight lanes, and the recursion consumes them one step at a
+    // time, so each lane fetches the inputs of ONE step of an 8-step chunk (a dependent pi[k] -> LLR chain
+    // for decoder 2) and the chunk after the current one is already in flight while this one is processed;
+    // the values reach the other lanes by shuffle.  One global-memory latency per 8 steps, hidden.
+    auto fetch = [&](int k, float& Ls, float& Lp, float& La, int& kk) {
+        Ls = Lp = La = 0.f;
+        kk = k;
         if (k < K) {
-            const int kk = in.perm ? in.perm[k] : k;
+            kk = in.perm ? in.perm[k] : k;
             Ls = in.ls[3 * kk];
             Lp = in.lp[3 * k];
             La = in.la[kk];
-        } else {
+        } else if (k < n) {
             Ls = in.ls_tail[k - K];
             Lp = in.lp_tail[k - K];
-            La = 0.f;
         }
     };
     // ---- forward
     float a = st == 0 ? 0.f : -INFINITY;
-    alpha[st] = a;
-    for (int k = 0; k < n; ++k) {
-        float Ls, Lp, La;
-        load(k, Ls, Lp, La);
-        const float g0 = (is0 * Ls + ip0 * Lp) + iu0 * La;
-        const float g1 = (is0 * Ls + ip1 * Lp) + iu1 * La;
-        const float x0 = __shfl_sync(gmask, a, pr0, 8) + g0;
-        const float x1 = __shfl_sync(gmask, a, pr1, 8) + g1;
-        a = fmaxf(x0, x1);
-        alpha[(size_t)(k + 1) * 8 + st] = a;
-    }
-    // ---- backward + a-posteriori
-    float bt = st == 0 ? 0.f : -INFINITY;
-    for (int k = n - 1; k >= 0; --k) {
-        float Ls, Lp, La;
-        load(k, Ls, Lp, La);
-        const float g0 = (ss0 * Ls + sp0 * Lp) + 0.5f * La;
-        const float g1 = (ss1 * Ls + sp1 * Lp) - 0.5f * La;
-        const float b0 = __shfl_sync(gmask, bt, nx0, 8), b1 = __shfl_sync(gmask, bt, nx1, 8);
-        const float ak = alpha[(size_t)k * 8 + st];
-        float v0 = (ak + g0) + b0, v1 = (ak + g1) + b1;
-        bt = fmaxf(b0 + g0, b1 + g1);
-        if (k < K) {
+    if (n) alpha[0] = a;
+    {
+        float cLs, cLp, cLa, nLs, nLp, nLa;
+        int ckk, nkk;
+        fetch(st, cLs, cLp, cLa, ckk);
+        for (int c = 0; c < nch_w; ++c) {
+            fetch((c + 1) * 8 + st, nLs, nLp, nLa, nkk);
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
-                v0 = fmaxf(v0, __shfl_xor_sync(gmask, v0, o, 8));
-                v1 = fmaxf(v1, __shfl_xor_sync(gmask, v1, o, 8));
+            for (int j = 0; j < 8; ++j) {
+                const int k = c * 8 + j;
+                const float Ls = __shfl_sync(FULLMASK, cLs, j, 8), Lp = __shfl_sync(FULLMASK, cLp, j, 8),
+                            La = __shfl_sync(FULLMASK, cLa, j, 8);
+                const float g0 = (is0 * Ls + ip0 * Lp) + iu0 * La;
+                const float g1 = (is0 * Ls + ip1 * Lp) + iu1 * La;
+                const float x0 = __shfl_sync(FULLMASK, a, pr0, 8) + g0;
+                const float x1 = __shfl_sync(FULLMASK, a, pr1, 8) + g1;
+                if (k < n) {
+                    a = fmaxf(x0, x1);
+                    alpha[(size_t)(k + 1) * 32] = a;
+                }
             }
-            if (st == 0) {
-                const float ap = v0 - v1;
-                if (EXTRINSIC_OUT) ext_out[scatter ? scatter[k] : k] = (ap - La) - Ls;
-                else bits_out[k] = ap < 0.f ? 1 : 0;
+            cLs = nLs; cLp = nLp; cLa = nLa; ckk = nkk;
+        }
+    }
+    // ---- backward + a-posteriori (alpha of the chunk below is prefetched too)
+    float bt = st == 0 ? 0.f : -INFINITY;
+    {
+        float cLs, cLp, cLa, nLs = 0.f, nLp = 0.f, nLa = 0.f, ca[8], na[8];
+        int ckk, nkk = 0;
+        fetch((nch_w - 1) * 8 + st, cLs, cLp, cLa, ckk);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int k = (nch_w - 1) * 8 + j; ca[j] = k < n ? alpha[(size_t)k * 32] : 0.f; }
+        for (int c = nch_w - 1; c >= 0; --c) {
+            if (c > 0) {
+                fetch((c - 1) * 8 + st, nLs, nLp, nLa, nkk);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const int k = (c - 1) * 8 + j; na[j] = k < n ? alpha[(size_t)k * 32] : 0.f; }
             }
+#pragma unroll
+            for (int j = 7; j >= 0; --j) {
+                const int k = c * 8 + j;
+                const float Ls = __shfl_sync(FULLMASK, cLs, j, 8), Lp = __shfl_sync(FULLMASK, cLp, j, 8),
+                            La = __shfl_sync(FULLMASK, cLa, j, 8);
+                const int kk = __shfl_sync(FULLMASK, ckk, j, 8);
+                const float g0 = (ss0 * Ls + sp0 * Lp) + 0.5f * La;
+                const float g1 = (ss1 * Ls + sp1 * Lp) - 0.5f * La;
+                const float b0 = __shfl_sync(FULLMASK, bt, nx0, 8), b1 = __shfl_sync(FULLMASK, bt, nx1, 8);
+                float v0 = (ca[j] + g0) + b0, v1 = (ca[j] + g1) + b1;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {
+                    v0 = fmaxf(v0, __shfl_xor_sync(FULLMASK, v0, o, 8));
+                    v1 = fmaxf(v1, __shfl_xor_sync(FULLMASK, v1, o, 8));
+                }
+                if (k < n) {
+                    bt = fmaxf(b0 + g0, b1 + g1);
+                    if (k < K && st == 0) {
+                        const float ap = v0 - v1;
+                        if (EXTRINSIC_OUT) ext_out[scatter ? kk : k] = (ap - La) - Ls;
+                        else bits_out[k] = ap < 0.f ? 1 : 0;
+                    }
+                }
+            }
+            cLs = nLs; cLp = nLp; cLa = nLa; ckk = nkk;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ca[j] = na[j];
         }
     }
 }
@@ -343,30 +385,37 @@ __global__ void __launch_bounds__(128)
 turbo_decode_kernel(const float* __restrict__ dl, const int* __restrict__ blk, int C, long long sumK, long long sumE,
                     const int* __restrict__ pi_tab, int iterations, float* __restrict__ work, long long work_per_blk,
                     int Kmax, uint8_t* __restrict__ cbdec, long long total) {
-    const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;      // (stream, code block)
-    if (g >= total) return;
+    long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;            // (stream, code block)
+    if ((g & ~3ll) >= total) return;                       // whole warp beyond the work: warp-uniform exit
+    const bool live = g < total;
+    const long long gw = g;
+    if (!live) g = total - 1;                              // padding group of the last warp: valid pointers, K = 0
     const int lane = threadIdx.x & 31, st = lane & 7;
-    const unsigned gmask = 0xFFu << (lane & 24);
     const long long b = g / C;
     const int r = (int)(g - b * C);
     const int* q = blk + r * LTE_BLK_COLS;
-    const int K = q[BLK_K];
+    const int K = live ? q[BLK_K] : 0;
+    const int nch_w = (__reduce_max_sync(FULLMASK, K) + 3 + 7) >> 3;
     const float* x = dl + (size_t)b * sumE + q[BLK_ENC];
     const int* pi = pi_tab + q[BLK_PI];
-    float* alpha = work + (size_t)g * work_per_blk;
-    float* e12 = alpha + (size_t)(Kmax + 4) * 8;          // decoder 1 -> 2, natural order
-    float* e21 = e12 + Kmax;                              // decoder 2 -> 1, natural order (scattered through pi)
+    // scratch of the four code blocks of a warp: alpha interleaved [step][lane] so that a warp's store of one
+    // step is one 128-byte line, then e12 / e21 (extrinsic, natural order) per block
+    float* wbase = work + (size_t)(gw & ~3ll) * work_per_blk;
+    float* alpha = wbase + lane;
+    float* e12 = wbase + (size_t)(Kmax + 4) * 32 + (size_t)(gw & 3) * 2 * Kmax;   // decoder 1 -> 2
+    float* e21 = e12 + Kmax;                                                     // decoder 2 -> 1 (scattered through pi)
     for (int k = st; k < K; k += 8) e21[k] = 0.f;
-    __syncwarp(gmask);
-    const Bcjr d1 = {x, x + 1, e21, nullptr, x + 3 * K, x + 3 * K + 3};
-    const Bcjr d2 = {x, x + 2, e12, pi, x + 3 * K + 6, x + 3 * K + 9};
+    __syncwarp();
+    const int Kq = live ? q[BLK_K] : 0;
+    const Bcjr d1 = {x, x + 1, e21, nullptr, x + 3 * Kq, x + 3 * Kq + 3};
+    const Bcjr d2 = {x, x + 2, e12, pi, x + 3 * Kq + 6, x + 3 * Kq + 9};
     for (int it = 0; it < iterations; ++it) {
-        bcjr_pass<true>(d1, K, alpha, e12, nullptr, nullptr, gmask, st);
-        __syncwarp(gmask);
-        bcjr_pass<true>(d2, K, alpha, e21, pi, nullptr, gmask, st);      // e21[pi[k]] = ext2[k]: the de-interleave
-        __syncwarp(gmask);
+        bcjr_pass<true>(d1, K, nch_w, alpha, e12, false, nullptr, st);
+        __syncwarp();
+        bcjr_pass<true>(d2, K, nch_w, alpha, e21, true, nullptr, st);    // e21[pi[k]] = ext2[k]: the de-interleave
+        __syncwarp();
     }
-    bcjr_pass<false>(d1, K, alpha, nullptr, nullptr, cbdec + (size_t)b * sumK + q[BLK_CB], gmask, st);
+    bcjr_pass<false>(d1, K, nch_w, alpha, nullptr, false, cbdec + (size_t)b * sumK + q[BLK_CB], st);
 }
 
 // ------------------------------------------------------------------ RX: de-segmentation, CRC check, errors

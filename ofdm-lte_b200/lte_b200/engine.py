@@ -418,7 +418,7 @@ class LinkEngine:
         """llr float32 [B, sumE] -> (bits_rx uint8 [B, A] or None, crc_ok int32 [B], errors int64 [B] or None)."""
         B = llr.shape[0]
         dem = self._empty((B, plan.sumE), torch.float32)
-        work = self._empty((B * plan.C, plan.work_floats), torch.float32)
+        work = self._empty((-(-B * plan.C // 4) * 4, plan.work_floats), torch.float32)     # whole warps of 4 blocks
         cbdec = self._empty((B, plan.sumK), torch.uint8)
         bits_rx = self._empty((B, plan.A), torch.uint8) if want_bits else None
         crc_ok = self._empty((B,), torch.int32)
