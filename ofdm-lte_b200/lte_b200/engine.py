@@ -372,6 +372,34 @@ class LinkEngine:
         errors, _ = self.demap_count(data, idx_tx=idx, nbits=nbits)
         return errors
 
+    def sfbc_ber(self, chan, snr_lin_rows, S, R, seed, stream_id0=0, idx=None):
+        """One pass of the 2-TX Alamouti SFBC chain (reference simulate_miso / simulate_mimo,
+        core/ofdm_core.py:1850-2258) over B independent streams: SFBC encode, per-TX interleaved CRS,
+        R x 2 independently faded links summed per RX antenna, AWGN of power (P_rx / 2) / snr, CRS
+        estimates of both TX antennas per 14-symbol slot, Alamouti decode averaged over RX, slicer, count.
+        The engine must have been built with tables.mimo_pilot_sets(2, Np); snr_lin_rows: float32 [B*R]
+        linear SNR per (stream, antenna).  Returns int64 [B] bit errors over S * 2 * (Nd // 2) symbols."""
+        if self.num_pilot_sets != 2:
+            raise ValueError("sfbc_ber needs an engine with the two SFBC pilot sets")
+        B = snr_lin_rows.shape[0] // R
+        nd2 = 2 * (self.Nd // 2)
+        if idx is None:
+            idx = self.random_indices(B, S, seed, stream_id0)[:, :S * nd2].contiguous()
+        data, _ = self.sfbc_encode(S, idx=idx)
+        tx, _, _ = self.modulate(S, symbols=data, T=2, want_stats=False)
+        if chan.num_taps > 0:
+            ph = self.random_phases(B, R * 2 * chan.num_taps * nat.LTE_JAKES_TONES, seed, stream_id0)
+            rx, power = self.channel(tx, chan, B, R, T=2, phases=ph)
+        else:
+            raise ValueError("sfbc_ber models the fading links of the reference's MIMO channel (rayleigh_mp)")
+        Y = self.rx_fft(rx.view(B * R, -1), B * R, S, nat.WINDOW_USEFUL, power=power,
+                        snr_lin=(snr_lin_rows * 2.0).contiguous(), seed=seed, row_id0=stream_id0 * R, noise_domain=1)
+        H0 = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, pilot_set=0)
+        H1 = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, pilot_set=1)
+        dec = self.sfbc_decode(Y, H0, H1, B, R, S, nat.WINDOW_USEFUL)
+        errors, _ = self.demap_count(dec, idx_tx=idx, nbits=S * nd2 * self.bps)
+        return errors
+
     # ------------------------------------------------------------------ coded chain (SURVEY 8 f-2)
     def coding_plan(self, A):
         """Cached layout tables of a transport block of A bits (lte_b200/coding.py)."""

@@ -188,3 +188,24 @@ def coded_sweep(engine, chan, snr_db, n_trials, tb_bits, seed=0, batch_trials=64
     out['block_errors'] = fails[0].cpu()
     out['bler'] = fails[0].double().cpu() / fails[1].clamp(min=1).double().cpu()
     return out
+
+
+def sfbc_sweep(config, snr_db, n_trials, num_rx=2, itu_profile='Pedestrian_A', frequency_ghz=2.0, velocity_kmh=3.0,
+               symbols_per_stream=14, seed=0, batch_trials=128, rank=0, world=1, device=None):
+    """BASELINE config 4: Monte-Carlo BER of 2 x num_rx SFBC-Alamouti transmit diversity over Rayleigh
+    multipath (reference simulate_miso / simulate_mimo), trials sharded over ranks like simo_sweep."""
+    from .engine import LinkEngine, chan_for
+    from . import tables
+    eng0 = LinkEngine.from_config(config, device=device)
+    eng = LinkEngine.from_config(config, pilot_sets=tables.mimo_pilot_sets(2, eng0.Np), device=device)
+    chan = chan_for('rayleigh_mp', config.fs, itu_profile, frequency_ghz, velocity_kmh)
+    n_snr = len(snr_db)
+    S, R = symbols_per_stream, num_rx
+    snr_lin = torch.tensor([10 ** (s / 10) for s in snr_db], dtype=torch.float32, device=eng.device)
+
+    def count_batch(trial_lo, n):
+        rows = snr_lin.repeat(n).repeat_interleave(R).contiguous()
+        return eng.sfbc_ber(chan, rows, S, R, seed, stream_id0=trial_lo * n_snr)
+
+    return run_sweep(count_batch, n_snr, n_trials, S * 2 * (eng.Nd // 2) * eng.bps, batch_trials, rank, world,
+                     eng.device)
