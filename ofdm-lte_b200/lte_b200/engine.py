@@ -400,6 +400,33 @@ class LinkEngine:
         errors, _ = self.demap_count(dec, idx_tx=idx, nbits=S * nd2 * self.bps)
         return errors
 
+    def sm_ber(self, chan, W, snr_db, B, S, R, detector, seed, stream_id0=0, idx=None):
+        """One pass of the TM4-like spatial-multiplexing chain (reference simulate_spatial_multiplexing,
+        core/ofdm_core.py:2489-2815) over B independent streams that share the precoder W [T, L] and the
+        SNR (the detectors take sigma^2 = 10^(-snr/10) as one scalar per launch): layer mapping +
+        precoding, per-TX interleaved CRS, R x T independently faded links summed per RX antenna
+        (`chan` built with gain_conversions=3 as that path does), AWGN from each antenna's measured power,
+        CRS estimate of every TX antenna on EVERY OFDM symbol, MMSE / ZF / SIC / MRC detection on
+        H_eff = H W, slicer, count.  The engine must carry tables.mimo_pilot_sets(T, Np)."""
+        W = np.asarray(W, dtype=complex)
+        T = W.shape[0]
+        if self.num_pilot_sets != T:
+            raise ValueError("sm_ber needs an engine built with the pilot sets of its T TX antennas")
+        if idx is None:
+            idx = self.random_indices(B, S, seed, stream_id0)
+        data, _ = self.sm_precode(S, W, idx=idx)
+        tx, _, _ = self.modulate(S, symbols=data, T=T, want_stats=False)
+        ph = self.random_phases(B, R * T * chan.num_taps * nat.LTE_JAKES_TONES, seed, stream_id0)
+        rx, power = self.channel(tx, chan, B, R, T=T, phases=ph)
+        snr_rows = torch.full((B * R,), float(10 ** (snr_db / 10)), dtype=torch.float32, device=self.device)
+        Y = self.rx_fft(rx.view(B * R, -1), B * R, S, nat.WINDOW_FULL, power=power, snr_lin=snr_rows, seed=seed,
+                        row_id0=stream_id0 * R, noise_domain=1)
+        H = torch.stack([self.estimate(Y.view(B * R * S, 1, self.N), B * R * S, 1, nat.WINDOW_FULL, pilot_set=t)
+                         .view(B * R, S, self.N) for t in range(T)])
+        sym = self.mimo_detect(Y, H, W, 10 ** (-snr_db / 10), detector, B, R, S, nat.WINDOW_FULL)
+        errors, _ = self.demap_count(sym, idx_tx=idx, nbits=S * self.Nd * self.bps)
+        return errors
+
     # ------------------------------------------------------------------ coded chain (SURVEY 8 f-2)
     def coding_plan(self, A):
         """Cached layout tables of a transport block of A bits (lte_b200/coding.py)."""

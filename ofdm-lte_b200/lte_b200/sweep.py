@@ -209,3 +209,59 @@ def sfbc_sweep(config, snr_db, n_trials, num_rx=2, itu_profile='Pedestrian_A', f
 
     return run_sweep(count_batch, n_snr, n_trials, S * 2 * (eng.Nd // 2) * eng.bps, batch_trials, rank, world,
                      eng.device)
+
+
+def sm_sweep(config, snr_db, n_trials, num_tx=4, num_rx=4, rank=4, detector='MMSE', itu_profile='Pedestrian_A',
+             frequency_ghz=2.0, velocity_kmh=3.0, symbols_per_stream=1, seed=0, batch_trials=64, rank_id=0, world=1,
+             device=None, precoder=None, feedback=None, feedback_block=16):
+    """BASELINE config 5: Monte-Carlo BER of T x R spatial multiplexing with codebook precoding and an
+    MMSE / ZF / SIC / MRC detector (reference simulate_spatial_multiplexing), trials sharded over ranks.
+
+    The detectors take sigma^2 as one scalar per launch, so a launch is (one SNR point, a run of
+    consecutive trials); stream ids are SNR-major here: id = snr_index * n_trials + trial.
+    rank 1..4: `precoder(rank) -> W [T, rank]` (codebook entry 0, the reference's fixed-rank branch).
+    rank 'adaptive': the reference draws an H_initial unrelated to the channel and feeds it to
+    RankAdaptation; here one H_initial is drawn on the host per (SNR point, block of `feedback_block`
+    consecutive global trials) -- keyed by (seed, snr_index, block), so sharding cannot change it -- and
+    `feedback(H, snr_db) -> (ri, pmi, W)` (core.rank_adaptation's rule) picks the precoder of the block.
+    Adds 'rank_hist' [n_snr, 4] (streams per rank) to run_sweep's result."""
+    import numpy as np
+
+    from . import tables
+    from .engine import LinkEngine, chan_for
+    eng0 = LinkEngine.from_config(config, device=device)
+    eng = LinkEngine.from_config(config, pilot_sets=tables.mimo_pilot_sets(num_tx, eng0.Np), device=device)
+    chan = chan_for('rayleigh_mp', config.fs, itu_profile, frequency_ghz, velocity_kmh, gain_conversions=3)
+    n_snr = len(snr_db)
+    S, R = symbols_per_stream, num_rx
+    adaptive = rank == 'adaptive'
+    if adaptive and feedback is None:
+        raise ValueError("rank='adaptive' needs feedback(H, snr_db) -> (ri, pmi, W)")
+    if not adaptive and precoder is None:
+        raise ValueError("a fixed rank needs precoder(rank) -> W")
+    rank_hist = torch.zeros((n_snr, 4), dtype=torch.int64, device=eng.device)
+
+    def count_batch(trial_lo, n):
+        err = torch.zeros((n, n_snr), dtype=torch.int64, device=eng.device)
+        for si, snr in enumerate(snr_db):
+            t = trial_lo
+            while t < trial_lo + n:
+                if adaptive:
+                    blk = t // feedback_block
+                    end = min(trial_lo + n, (blk + 1) * feedback_block)
+                    rs = np.random.RandomState([seed & 0x7fffffff, si, blk])
+                    Hi = (rs.randn(num_rx, num_tx) + 1j * rs.randn(num_rx, num_tx)) / np.sqrt(2 * num_tx)
+                    ri, _, W = feedback(Hi, float(snr))
+                else:
+                    end, ri, W = trial_lo + n, int(rank), precoder(int(rank))
+                m = end - t
+                err[t - trial_lo:end - trial_lo, si] = eng.sm_ber(chan, W, float(snr), m, S, R, detector, seed,
+                                                                  stream_id0=si * n_trials + t)
+                rank_hist[si, ri - 1] += m
+                t = end
+        return err.reshape(-1)
+
+    out = run_sweep(count_batch, n_snr, n_trials, S * eng.Nd * eng.bps, batch_trials, rank_id, world, eng.device)
+    reduce_counts(rank_hist)
+    out['rank_hist'] = rank_hist.cpu()
+    return out

@@ -124,3 +124,46 @@ def test_helper_classes():
     ri, pmi, W = O.rank_feedback(H, 4, 4, 20.0)
     assert (fb['ri'], fb['pmi']) == (ri, pmi) and np.array_equal(fb['W'], W)
     assert RankAdaptation(4, 4, snr_db=3.0).get_feedback(H)['ri'] == 1
+
+
+def test_sm_sweep_fixed_and_adaptive_rank():
+    """BASELINE config 5 as a batched sweep: sharding invariance (fixed and adaptive rank), the rank
+    histogram of the adaptive rule, and statistical agreement with looping simulate_spatial_multiplexing."""
+    import torch
+    from config import LTEConfig
+    from core.codebook_lte import LTECodebook
+    from core.ofdm_core import simulate_spatial_multiplexing
+    from core.rank_adaptation import RankAdaptation
+    from lte_b200.sweep import sm_sweep
+    cfg = LTEConfig(1.25, 15.0, '16-QAM')
+    snrs = [8.0, 20.0]
+
+    def precoder(r):
+        return LTECodebook(4, transmission_mode='TM4', rank=r).get_precoder(0)
+
+    def feedback(H, snr_db):
+        fb = RankAdaptation(4, 4, snr_db=snr_db).get_feedback(H)
+        return fb['ri'], fb['pmi'], fb['W']
+
+    kw = dict(num_tx=4, num_rx=4, detector='MMSE', symbols_per_stream=2, seed=5)
+    one = sm_sweep(cfg, snrs, 40, rank=2, precoder=precoder, batch_trials=40, **kw)
+    parts = [sm_sweep(cfg, snrs, 40, rank=2, precoder=precoder, batch_trials=9, rank_id=r, world=2, **kw) for r in range(2)]
+    assert torch.equal(parts[0]['errors'] + parts[1]['errors'], one['errors'])
+    assert one['rank_hist'][:, 1].tolist() == [40, 40] and int(one['rank_hist'].sum()) == 80
+    assert one['ber'][0] > one['ber'][1]
+    ad = sm_sweep(cfg, snrs, 40, rank='adaptive', feedback=feedback, feedback_block=8, batch_trials=40, **kw)
+    ad2 = [sm_sweep(cfg, snrs, 40, rank='adaptive', feedback=feedback, feedback_block=8, batch_trials=7, rank_id=r,
+                    world=3, **kw) for r in range(3)]
+    assert torch.equal(sum(p['errors'] for p in ad2), ad['errors'])
+    assert torch.equal(sum(p['rank_hist'] for p in ad2), ad['rank_hist'])
+    assert ad['rank_hist'].sum(dim=1).tolist() == [40, 40]
+    # per-call API with independent Philox draws: same BER regime at rank 2, 20 dB
+    bits = np.random.RandomState(0).randint(0, 2, 2 * 62 * 4)
+    loop = np.mean([simulate_spatial_multiplexing(bits, num_tx=4, num_rx=4, rank=2, detector_type='MMSE',
+                                                  modulation='16-QAM', snr_db=20.0, config=cfg,
+                                                  channel_type='rayleigh_mp', rng='philox', seed=i)['ber']
+                    for i in range(120)])
+    big = sm_sweep(cfg, [20.0], 240, rank=2, precoder=precoder, **kw)['ber'].numpy()[0]
+    assert abs(loop - big) / max(big, 1e-9) < 0.35
+    with pytest.raises(ValueError):
+        sm_sweep(cfg, snrs, 4, rank='adaptive', **kw)
