@@ -99,6 +99,28 @@ def main():
     out['payload_sweep'] = {'workload': '1.25MHz, 3 modulations x RX{1,2,4,8} x 8 SNR x 32 iterations, 20 kbit payload',
                             'seconds': dt, 'simulate_calls_equivalent': calls, 'calls_per_s': calls / dt}
 
+    # ---- BASELINE config 4: 2x2 SFBC 20 MHz 16-QAM over Pedestrian_A, 16 SNR points x 64 trials of one subframe
+    from lte_b200 import tables
+    from lte_b200.sweep import sfbc_sweep, sm_sweep
+    cfg4 = LTEConfig(20.0, 15.0, '16-QAM')
+    e4 = LinkEngine.from_config(cfg4, pilot_sets=tables.mimo_pilot_sets(2, 200), device=dev)
+    ch4 = chan_for('rayleigh_mp', cfg4.fs, 'Pedestrian_A', 2.0, 3.0)
+    B4, R4 = 1024, 2
+    rows4 = torch.tensor([10 ** (s / 10) for s in range(0, 32, 2)], dtype=torch.float32, device=dev) \
+        .repeat(B4 // 16).repeat_interleave(R4).contiguous()
+    ms4 = timed(lambda: e4.sfbc_ber(ch4, rows4, 14, R4, 1, 0), a.reps)
+    out['sfbc_cfg4'] = {'workload': f'20MHz 16-QAM 2x2 SFBC Pedestrian_A, {B4} subframes per pass', 'pass_ms': ms4,
+                        'subframes_per_s': B4 / (ms4 * 1e-3)}
+    # ---- BASELINE config 5: 4x4 SM 20 MHz 64-QAM MMSE rank 4, 256 subframes at one SNR point per launch
+    cfg5 = LTEConfig(20.0, 15.0, '64-QAM')
+    e5 = LinkEngine.from_config(cfg5, pilot_sets=tables.mimo_pilot_sets(4, 200), device=dev)
+    ch5 = chan_for('rayleigh_mp', cfg5.fs, 'Pedestrian_A', 2.0, 3.0, gain_conversions=3)
+    W5 = LTECodebook(4, transmission_mode='TM4', rank=4).get_precoder(0)
+    B5 = 256
+    ms5 = timed(lambda: e5.sm_ber(ch5, W5, 20.0, B5, 14, 4, 'MMSE', 1, 0), a.reps)
+    out['sm_cfg5'] = {'workload': f'20MHz 64-QAM 4x4 SM rank 4 MMSE Pedestrian_A, {B5} subframes per pass',
+                      'pass_ms': ms5, 'subframes_per_s': B5 / (ms5 * 1e-3)}
+
     if a.cpu:
         from oracle import lte_oracle as O
         T_ = np.load(os.path.join(ROOT, 'tests', 'golden', 'coding_tables.npz'))
@@ -115,6 +137,16 @@ def main():
         for i in range(n):
             O.simulate_beamforming(bb, 15.0, num2, 4, 2, 'static', global_seed=i)
         out['beamforming']['cpu_oracle_stream_symbols_per_s'] = n * 14 / (time.perf_counter() - t0)
+        num4 = O.Numerology(20.0, 15.0, '16-QAM')
+        b4 = np.random.RandomState(0).randint(0, 2, 14 * 998 * 4)
+        t0 = time.perf_counter()
+        O.simulate_sfbc(b4, 10.0, num4, 2, 'rayleigh_mp', 'Pedestrian_A', 2.0, 3.0)
+        out['sfbc_cfg4']['cpu_oracle_subframes_per_s'] = 1 / (time.perf_counter() - t0)
+        num5 = O.Numerology(20.0, 15.0, '64-QAM')
+        b5 = np.random.RandomState(0).randint(0, 2, 999 * 6)
+        t0 = time.perf_counter()
+        O.simulate_sm(b5, num5, 4, 4, 4, 'MMSE', 20.0, 'rayleigh_mp', 'Pedestrian_A', 3.0, 2.0, global_seed=1)
+        out['sm_cfg5']['cpu_oracle_subframes_per_s'] = 1 / 14 / (time.perf_counter() - t0)
     print(json.dumps(out))
 
 
