@@ -54,9 +54,10 @@ def stage_bytes(N=2048, cp=144, Nd=999, Np=200, Nc=1200, b=6, R=R_ANT, S=S_SUBFR
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
-# (round 1, 4096 subframes per launch; summaries: profiles/r01_fused_ncu_summary.md, r01_staged_ncu_summary.md)
+# (round 1, 4096 subframes per launch; summaries: profiles/r01_fused_k1_ncu_summary.md for channel_rx_fft,
+# r01_fused_ncu_summary.md and r01_staged_ncu_summary.md for the others)
 NCU_TRAFFIC = {
-    'tx_map_ifft': 1.0118e9, 'channel_rx_fft': 3.1886e9, 'crs_ls_interp_awgn': 0.2719e9,
+    'tx_map_ifft': 1.0118e9, 'channel_rx_fft': 3.1742e9, 'crs_ls_interp_awgn': 0.2719e9,
     'mrc_demap_count_awgn': 2.4214e9, 'channel_tdl': 4.99e9, 'rx_fft': 5.93e9,
 }
 

@@ -25,7 +25,7 @@ def test_product_tables_match_the_standard_table_in_the_goldens():
     assert P == QPP and list(TURBO_K) == O.TURBO_K
 
 
-@pytest.mark.parametrize('A', [16, 17, 76, 6120, 6121, 12976, 19987])
+@pytest.mark.parametrize('A', [1, 16, 17, 76, 6120, 6121, 12976, 19987])
 def test_tb_encode_matches_oracle(A):
     """CRC-24A + segmentation (+ CRC-24B) + turbo encoder + rate matching, bit-exact."""
     eng = _engine()
@@ -201,3 +201,19 @@ def test_coded_sweep_shards_and_improves_on_uncoded():
     fad = chan_for('rayleigh_mp', eng.fs, 'Pedestrian_A', 2.0, 3.0)
     f = coded_sweep(eng, fad, [4.0, 24.0], 16, tb_bits=300, seed=4)
     assert f['ber'][0] > f['ber'][1]
+
+
+def test_coded_api_error_conventions_and_ragged_payloads():
+    from config import LTEConfig
+    from core.ofdm_core import OFDMSimulator
+    sim = OFDMSimulator(LTEConfig(1.25, 15.0, '16-QAM'), channel_type='awgn', rng='philox', seed=2)
+    with pytest.raises(ValueError):
+        sim.simulate_siso_coded([], snr_db=5.0)
+    for n in (1, 7, 61):                        # far less than one OFDM symbol, not a multiple of anything
+        bits = np.random.RandomState(n).randint(0, 2, n)
+        r = sim.simulate_siso_coded(bits, snr_db=25.0)
+        assert r['bit_errors'] == 0 and r['crc_pass'] and np.array_equal(r['bits_received_array'], bits)
+        assert r['coded_bits_length'] == 3 * 40 + 12 or r['coded_bits_length'] == 3 * 88 + 12
+    assert sim.calculate_noise_var_zf(np.array([]), 10.0) == pytest.approx(0.1)
+    assert sim.calculate_noise_var_zf(np.array([2.0]), 10.0) == pytest.approx(0.025)
+    assert sim.calculate_noise_var_zf(np.array([1.0, 0.5]), 10.0) == pytest.approx(0.1 / (2 / (1 + 4)))
