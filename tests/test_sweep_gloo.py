@@ -107,3 +107,80 @@ def test_two_rank_papr_histogram_equals_single_rank(tmp_path):
     assert (multi['hist'] == single['hist']).all() and multi['count'] == single['count'] == 41 * 3
     assert abs(multi['mean_db'] - single['mean_db']) < 1e-9 and multi['max_db'] == single['max_db']
     assert (multi['ccdf'] == single['ccdf']).all()
+
+
+class _FakeBfEngine:
+    """CPU stand-in with the four engine calls beamforming_sweep makes; every quantity is a deterministic
+    function of the global stream id, so the gloo reduction of errors / gain / PMI histogram can be checked
+    exactly against a single-rank run."""
+    device = torch.device('cpu')
+    Nd, bps = 5, 2
+
+    def random_indices(self, B, S, seed, stream_id0=0, out=None):
+        return torch.arange(stream_id0, stream_id0 + B, dtype=torch.int64)[:, None].repeat(1, S * self.Nd)
+
+    def random_channel(self, B, R, T, seed, stream_id0=0):
+        return torch.arange(stream_id0, stream_id0 + B, dtype=torch.float64)
+
+    def bf_weights(self, h, codebook, mode='MRT'):
+        pmi = (h.long() * 7) % len(codebook)
+        return h, h, pmi.to(torch.int32), (h % 5).float() * 0.5          # gains are multiples of 0.5: exact sums
+
+    def bf_link(self, idx, h, W, heff, noise_std, S, seed=0, row_id0=0, **kw):
+        return (idx[:, 0] * 2654435761 % 11), None
+
+
+def _bf_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    sweep = _load_sweep()
+    r = sweep.beamforming_sweep(_FakeBfEngine(), [None] * 4, [0.0, 5.0, 10.0], 37, 4, 2, mode='CODEBOOK',
+                                symbols_per_stream=2, batch_trials=6, rank=rank, world=world)
+    if rank == 0:
+        torch.save(r, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_beamforming_sweep_equals_single_rank(tmp_path):
+    sweep = _load_sweep()
+    single = sweep.beamforming_sweep(_FakeBfEngine(), [None] * 4, [0.0, 5.0, 10.0], 37, 4, 2, mode='CODEBOOK',
+                                     symbols_per_stream=2, batch_trials=16)
+    out = str(tmp_path / 'bf.pt')
+    mp.spawn(_bf_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    multi = torch.load(out, weights_only=False)
+    assert torch.equal(multi['errors'], single['errors']) and torch.equal(multi['bits'], single['bits'])
+    assert torch.equal(multi['pmi_hist'], single['pmi_hist']) and int(single['pmi_hist'].sum()) == 37 * 3
+    assert multi['mean_gain_db'] == single['mean_gain_db']
+
+
+class _FakeCodedEngine:
+    device = torch.device('cpu')
+    Nd = 8
+
+    def random_indices(self, B, S, seed, stream_id0=0, out=None):
+        return torch.arange(stream_id0, stream_id0 + B, dtype=torch.int64)[:, None].repeat(1, S * self.Nd)
+
+    def siso_coded_ber(self, bits, chan, snr_db_rows, seed, stream_id0=0, iterations=8):
+        sid = torch.arange(stream_id0, stream_id0 + bits.shape[0], dtype=torch.int64)
+        err = sid * 40503 % 13
+        return err, (err == 0).to(torch.int32)
+
+
+def _coded_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    sweep = _load_sweep()
+    r = sweep.coded_sweep(_FakeCodedEngine(), None, [1.0, 4.0], 29, tb_bits=20, batch_trials=4, rank=rank, world=world)
+    if rank == 0:
+        torch.save(r, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_coded_sweep_equals_single_rank(tmp_path):
+    sweep = _load_sweep()
+    single = sweep.coded_sweep(_FakeCodedEngine(), None, [1.0, 4.0], 29, tb_bits=20, batch_trials=29)
+    out = str(tmp_path / 'c.pt')
+    mp.spawn(_coded_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    multi = torch.load(out, weights_only=False)
+    assert torch.equal(multi['errors'], single['errors']) and torch.equal(multi['block_errors'], single['block_errors'])
+    assert torch.equal(multi['bler'], single['bler']) and torch.equal(single['bits'], torch.tensor([29 * 20] * 2))
