@@ -347,6 +347,26 @@ int lte_tb_decode(const float* llr, const int32_t* blk, int32_t C, int64_t sumK,
                   float* work, uint8_t* cbdec, int64_t A, const uint8_t* bits_tx, uint8_t* bits_rx,
                   int32_t* crc_ok, unsigned long long* errors, int64_t B, void* stream);
 
+/* Stage-level entry points behind the reference's module functions (core/channel_coding/__init__.py):
+ * lte_crc_bits -> calculate_crc24a/24b/16 (crc.py:89-209; poly without its leading term, e.g. 0x864CFB);
+ * lte_turbo_encode_blocks -> turbo_encode (turbo_encoder.py:214-313) on ready code blocks cb [B][sumK];
+ * lte_turbo_decode_blocks -> turbo_decode (turbo_decoder.py:338-446) on decoder-order LLRs dl [B][sumE];
+ *   with iterations = 0 it is one LogMAPDecoder.decode pass (:158-293): apriori (optional) [B][sumK] a-priori
+ *   LLRs of the K data steps, apost (optional) [B][sumK + 3C] a-posteriori LLRs of all K+3 steps per block;
+ * lte_gather_u8 / lte_gather_f32 -> qpp_interleave / qpp_deinterleave, sub_block_interleaver /
+ *   _deinterleaver, rate_match_turbo / rate_dematching_turbo as index tables (-1 = constant 0). */
+int lte_crc_bits(const uint8_t* bits, int64_t n, uint32_t poly, int32_t len, uint8_t* out, int64_t B,
+                 void* stream);
+int lte_turbo_encode_blocks(const uint8_t* cb, const int32_t* blk, int32_t C, int64_t sumK, int64_t sumE,
+                            const int32_t* pi_tab, uint8_t* enc, int64_t B, void* stream);
+int lte_turbo_decode_blocks(const float* dl, const int32_t* blk, int32_t C, int64_t sumK, int64_t sumE,
+                            int32_t Kmax, const int32_t* pi_tab, int32_t iterations, float* work,
+                            uint8_t* cbdec, const float* apriori, float* apost, int64_t B, void* stream);
+int lte_gather_u8(const uint8_t* src, int64_t n_src, const int32_t* table, int64_t n, uint8_t* out, int64_t B,
+                  void* stream);
+int lte_gather_f32(const float* src, int64_t n_src, const int32_t* table, int64_t n, float* out, int64_t B,
+                   void* stream);
+
 /* --- stage 6: hard demap + bit-error count -------------------------------------------
  * replaces QAMModulator.symbols_to_bits (core/modulator.py:90-112) and
  * OFDMReceiver.calculate_ber (core/ofdm_core.py:245-268).  syms: [B][nsym];

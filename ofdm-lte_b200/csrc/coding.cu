@@ -110,21 +110,21 @@ __global__ void turbo_encode_kernel(const uint8_t* __restrict__ cb, const int* _
 }
 
 // ------------------------------------------------------------------ gathers (rate matching / de-matching)
-__global__ void gather_u8_kernel(const uint8_t* __restrict__ src, const int* __restrict__ table, long long n,
-                                 uint8_t* __restrict__ out, long long total) {
+__global__ void gather_u8_kernel(const uint8_t* __restrict__ src, long long n_src, const int* __restrict__ table,
+                                 long long n, uint8_t* __restrict__ out, long long total) {
     const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= total) return;
     const long long b = it / n;
     const int t = table[it - b * n];
-    out[it] = t >= 0 ? src[(size_t)b * n + t] : (uint8_t)0;
+    out[it] = t >= 0 ? src[(size_t)b * n_src + t] : (uint8_t)0;
 }
-__global__ void gather_f32_kernel(const float* __restrict__ src, const int* __restrict__ table, long long n,
-                                  float* __restrict__ out, long long total) {
+__global__ void gather_f32_kernel(const float* __restrict__ src, long long n_src, const int* __restrict__ table,
+                                  long long n, float* __restrict__ out, long long total) {
     const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= total) return;
     const long long b = it / n;
     const int t = table[it - b * n];
-    out[it] = t >= 0 ? src[(size_t)b * n + t] : 0.f;
+    out[it] = t >= 0 ? src[(size_t)b * n_src + t] : 0.f;
 }
 
 extern "C" int lte_tb_encode(const uint8_t* bits, int64_t A, const int32_t* blk, int32_t C, int64_t sumK,
@@ -140,7 +140,7 @@ extern "C" int lte_tb_encode(const uint8_t* bits, int64_t A, const int32_t* blk,
     segment_kernel<<<(unsigned)((t1 + 63) / 64), 64, 0, st>>>(bits, crc, A, blk, C, sumK, cb, t1);
     turbo_encode_kernel<<<(unsigned)((2 * t1 + 63) / 64), 64, 0, st>>>(cb, blk, C, sumK, sumE, pi_tab, enc, 2 * t1);
     const long long t2 = B * sumE;
-    gather_u8_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>(enc, rm_table, sumE, coded, t2);
+    gather_u8_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>(enc, sumE, rm_table, sumE, coded, t2);
     LTE_CHECK_CUDA(cudaGetLastError());
     return LTE_OK;
 }
@@ -276,7 +276,7 @@ struct Bcjr {
 template <bool EXTRINSIC_OUT>
 __device__ __forceinline__ void bcjr_pass(const Bcjr in, int K, int nch_w, float* __restrict__ alpha,
                                           float* __restrict__ ext_out, bool scatter, uint8_t* __restrict__ bits_out,
-                                          int st) {
+                                          int st, float* __restrict__ apost_out = nullptr) {
     const int n = K > 0 ? K + 3 : 0;                     // K == 0: padding group of the last warp
     const int s0 = (st >> 2) & 1, s1 = (st >> 1) & 1, s2 = st & 1;
     // outgoing branches of this state
@@ -367,10 +367,13 @@ __device__ __forceinline__ void bcjr_pass(const Bcjr in, int K, int nch_w, float
                 }
                 if (k < n) {
                     bt = fmaxf(b0 + g0, b1 + g1);
-                    if (k < K && st == 0) {
+                    if (st == 0) {
                         const float ap = v0 - v1;
-                        if (EXTRINSIC_OUT) ext_out[scatter ? kk : k] = (ap - La) - Ls;
-                        else bits_out[k] = ap < 0.f ? 1 : 0;
+                        if (k < K) {
+                            if (EXTRINSIC_OUT) ext_out[scatter ? kk : k] = (ap - La) - Ls;
+                            else bits_out[k] = ap < 0.f ? 1 : 0;
+                        }
+                        if (!EXTRINSIC_OUT && apost_out) apost_out[k] = ap;
                     }
                 }
             }
@@ -384,7 +387,8 @@ __device__ __forceinline__ void bcjr_pass(const Bcjr in, int K, int nch_w, float
 __global__ void __launch_bounds__(128)
 turbo_decode_kernel(const float* __restrict__ dl, const int* __restrict__ blk, int C, long long sumK, long long sumE,
                     const int* __restrict__ pi_tab, int iterations, float* __restrict__ work, long long work_per_blk,
-                    int Kmax, uint8_t* __restrict__ cbdec, long long total) {
+                    int Kmax, uint8_t* __restrict__ cbdec, long long total, const float* __restrict__ apriori,
+                    float* __restrict__ apost) {
     long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;            // (stream, code block)
     if ((g & ~3ll) >= total) return;                       // whole warp beyond the work: warp-uniform exit
     const bool live = g < total;
@@ -404,7 +408,7 @@ turbo_decode_kernel(const float* __restrict__ dl, const int* __restrict__ blk, i
     float* alpha = wbase + lane;
     float* e12 = wbase + (size_t)(Kmax + 4) * 32 + (size_t)(gw & 3) * 2 * Kmax;   // decoder 1 -> 2
     float* e21 = e12 + Kmax;                                                     // decoder 2 -> 1 (scattered through pi)
-    for (int k = st; k < K; k += 8) e21[k] = 0.f;
+    for (int k = st; k < K; k += 8) e21[k] = apriori ? apriori[(size_t)b * sumK + q[BLK_CB] + k] : 0.f;
     __syncwarp();
     const int Kq = live ? q[BLK_K] : 0;
     const Bcjr d1 = {x, x + 1, e21, nullptr, x + 3 * Kq, x + 3 * Kq + 3};
@@ -415,7 +419,8 @@ turbo_decode_kernel(const float* __restrict__ dl, const int* __restrict__ blk, i
         bcjr_pass<true>(d2, K, nch_w, alpha, e21, true, nullptr, st);    // e21[pi[k]] = ext2[k]: the de-interleave
         __syncwarp();
     }
-    bcjr_pass<false>(d1, K, nch_w, alpha, nullptr, false, cbdec + (size_t)b * sumK + q[BLK_CB], st);
+    bcjr_pass<false>(d1, K, nch_w, alpha, nullptr, false, cbdec + (size_t)b * sumK + q[BLK_CB], st,
+                     apost ? apost + (size_t)b * (sumK + 3 * C) + q[BLK_CB] + 3 * r : nullptr);
 }
 
 // ------------------------------------------------------------------ RX: de-segmentation, CRC check, errors
@@ -461,12 +466,88 @@ extern "C" int lte_tb_decode(const float* llr, const int32_t* blk, int32_t C, in
     if (B == 0) return LTE_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const long long t2 = B * sumE;
-    gather_f32_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>(llr, dm_table, sumE, dematched, t2);
+    gather_f32_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>(llr, sumE, dm_table, sumE, dematched, t2);
     const long long nblk = B * C;
     turbo_decode_kernel<<<(unsigned)((nblk * 8 + 127) / 128), 128, 0, st>>>(
-        dematched, blk, C, sumK, sumE, pi_tab, iterations, work, lte_tb_decode_work_floats(Kmax), Kmax, cbdec, nblk);
+        dematched, blk, C, sumK, sumE, pi_tab, iterations, work, lte_tb_decode_work_floats(Kmax), Kmax, cbdec, nblk, nullptr,
+        nullptr);
     tb_check_kernel<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(cbdec, blk, C, sumK, A, bits_tx, bits_rx, crc_ok,
                                                               errors, B);
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}
+
+// ------------------------------------------------------------------ stage-level entry points
+// The reference exposes its coding stages as module functions (core/channel_coding/__init__.py); these
+// launch the same kernels one stage at a time so that API can sit on the GPU as well.
+
+// CRC of B rows of n bits each: generator `poly` of degree `len` (16 or 24) without its leading term,
+// zero initial state, MSB first (core/channel_coding/crc.py:89-134).  out [B][len] bits.
+__global__ void crc_rows_kernel(const uint8_t* __restrict__ bits, long long n, uint32_t poly, int len,
+                                uint8_t* __restrict__ out, long long B) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint8_t* x = bits + (size_t)b * n;
+    const uint32_t msk = len == 32 ? 0xFFFFFFFFu : ((1u << len) - 1u);
+    uint32_t reg = 0;
+    for (long long i = 0; i < n; ++i) {
+        const uint32_t top = ((reg >> (len - 1)) & 1u) ^ (x[i] & 1u);
+        reg = (reg << 1) & msk;
+        if (top) reg ^= poly;
+    }
+    for (int i = 0; i < len; ++i) out[(size_t)b * len + i] = (reg >> (len - 1 - i)) & 1u;
+}
+
+extern "C" int lte_crc_bits(const uint8_t* bits, int64_t n, uint32_t poly, int32_t len, uint8_t* out, int64_t B,
+                            void* stream) {
+    if (!bits || !out || n < 0 || len < 1 || len > 32 || B < 0) return LTE_ERR_INVALID_ARG;
+    if (B == 0) return LTE_OK;
+    crc_rows_kernel<<<(unsigned)((B + 63) / 64), 64, 0, (cudaStream_t)stream>>>(bits, n, poly, len, out, B);
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}
+
+extern "C" int lte_turbo_encode_blocks(const uint8_t* cb, const int32_t* blk, int32_t C, int64_t sumK, int64_t sumE,
+                                       const int32_t* pi_tab, uint8_t* enc, int64_t B, void* stream) {
+    if (!cb || !blk || !pi_tab || !enc || C < 1 || sumK < 40 || sumE != 3 * sumK + 12 * (int64_t)C || B < 0)
+        return LTE_ERR_INVALID_ARG;
+    if (B == 0) return LTE_OK;
+    const long long t = 2 * B * C;
+    turbo_encode_kernel<<<(unsigned)((t + 63) / 64), 64, 0, (cudaStream_t)stream>>>(cb, blk, C, sumK, sumE, pi_tab, enc, t);
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}
+
+extern "C" int lte_turbo_decode_blocks(const float* dl, const int32_t* blk, int32_t C, int64_t sumK, int64_t sumE,
+                                       int32_t Kmax, const int32_t* pi_tab, int32_t iterations, float* work,
+                                       uint8_t* cbdec, const float* apriori, float* apost, int64_t B, void* stream) {
+    if (!dl || !blk || !pi_tab || !work || !cbdec || C < 1 || sumK < 1 || Kmax < 1 || Kmax > 6144 ||
+        sumE != 3 * sumK + 12 * (int64_t)C || iterations < 0 || B < 0)
+        return LTE_ERR_INVALID_ARG;
+    if (B == 0) return LTE_OK;
+    const long long nblk = B * C;
+    turbo_decode_kernel<<<(unsigned)((nblk * 8 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        dl, blk, C, sumK, sumE, pi_tab, iterations, work, lte_tb_decode_work_floats(Kmax), Kmax, cbdec, nblk, apriori, apost);
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}
+
+// out[b][i] = table[i] >= 0 ? src[b][table[i]] : 0 -- interleavers, rate matching and their inverses as tables
+extern "C" int lte_gather_u8(const uint8_t* src, int64_t n_src, const int32_t* table, int64_t n, uint8_t* out, int64_t B,
+                             void* stream) {
+    if (!src || !table || !out || n < 1 || n_src < 1 || B < 0) return LTE_ERR_INVALID_ARG;
+    if (B == 0) return LTE_OK;
+    const long long t = B * n;
+    gather_u8_kernel<<<(unsigned)((t + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, n_src, table, n, out, t);
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}
+extern "C" int lte_gather_f32(const float* src, int64_t n_src, const int32_t* table, int64_t n, float* out, int64_t B,
+                              void* stream) {
+    if (!src || !table || !out || n < 1 || n_src < 1 || B < 0) return LTE_ERR_INVALID_ARG;
+    if (B == 0) return LTE_OK;
+    const long long t = B * n;
+    gather_f32_kernel<<<(unsigned)((t + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, n_src, table, n, out, t);
     LTE_CHECK_CUDA(cudaGetLastError());
     return LTE_OK;
 }
