@@ -144,3 +144,44 @@ class OFDMModulator:
 
     def get_qam_modulator(self):
         return self.qam_modulator
+
+
+# ------------------------------------------------------------------ soft demapping (reference :423-540)
+class _OneBinConfig:
+    """simple-mode plan with a single data position: every symbol is its own stream, so each one can carry
+    its own noise variance through lte_soft_demap's per-stream sigma2."""
+    N, Nc, cp_length, fs = 64, 1, 0, 1.92e6
+
+    def __init__(self, bits_per_symbol):
+        self.bits_per_symbol = bits_per_symbol
+
+
+def symbols_to_llrs(symbols, noise_var, bits_per_symbol):
+    """Max-log LLRs of `symbols` with a scalar or per-symbol noise variance on `lte_soft_demap`
+    (QPSK: exact, unclipped; 16/64-QAM: clipped to +-10) -- the arithmetic of
+    OFDMSimulator._calculate_llrs_qpsk/_16qam/_64qam (reference core/ofdm_core.py:791-923)."""
+    import torch
+    y = np.asarray(symbols)
+    if y.size == 0:
+        return np.array([], dtype=np.float64)
+    eng = be.engine_for(_OneBinConfig(bits_per_symbol), mode='simple')
+    nv = np.broadcast_to(np.asarray(noise_var, dtype=np.float32), y.shape)
+    data = be.as_complex_tensor(y.reshape(-1, 1))
+    s2 = torch.from_numpy(np.array(nv.reshape(-1), dtype=np.float32)).to(data.device)
+    llr = eng.soft_demap(data, None, s2, False, 1, 1)
+    return be.to_numpy(llr.reshape(-1)).astype(np.float64)
+
+
+def qpsk_to_llrs(symbols, noise_var):
+    """[LLR_I0, LLR_Q0, LLR_I1, ...] = (2 / noise_var) * Re/Im(y) * sqrt(2) (reference :423-475)."""
+    return symbols_to_llrs(symbols, noise_var, 2)
+
+
+def qam16_to_llrs(symbols, noise_var):
+    """The reference leaves this module function unimplemented (:478-500) and does the 16-QAM LLRs in
+    OFDMSimulator._calculate_llrs_16qam; the error is kept so callers that probe for it see the same thing."""
+    raise NotImplementedError("16-QAM LLR generation not yet implemented")
+
+
+def qam64_to_llrs(symbols, noise_var):
+    raise NotImplementedError("64-QAM LLR generation not yet implemented")

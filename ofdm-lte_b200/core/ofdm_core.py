@@ -476,6 +476,21 @@ class OFDMSimulator:
         hp = np.maximum(np.abs(H) ** 2, 1e-12)
         return float(nv / hp[0]) if len(hp) == 1 else float(nv / (len(hp) / np.sum(1.0 / hp)))
 
+    def _calculate_llrs_qpsk(self, symbols, noise_var):
+        """reference :791-815."""
+        from .modulator import symbols_to_llrs
+        return symbols_to_llrs(symbols, noise_var, 2)
+
+    def _calculate_llrs_16qam(self, symbols, noise_var):
+        """reference :817-869 (max-log over the natural-binary raster constellation, clipped to +-10)."""
+        from .modulator import symbols_to_llrs
+        return symbols_to_llrs(symbols, noise_var, 4)
+
+    def _calculate_llrs_64qam(self, symbols, noise_var):
+        """reference :871-923."""
+        from .modulator import symbols_to_llrs
+        return symbols_to_llrs(symbols, noise_var, 6)
+
     def simulate_siso_coded(self, bits, snr_db: float = 10.0) -> Dict:
         """SISO link with CRC-24A, code-block segmentation, the rate-1/3 turbo code, rate matching, a
         symbol block interleaver, max-log LLRs and 8 max-log BCJR iterations (reference :925-1338).

@@ -245,3 +245,21 @@ def test_multi_block_round_trip_with_mixed_block_sizes(A, B):
     wrong[0, A // 2] ^= 1
     _, crc2, err2 = eng.tb_decode(llr, plan, bits_tx=wrong)
     assert int(err2[0]) == 1 and bool(crc2.all())          # the decode itself is right; only the comparison differs
+
+
+@pytest.mark.parametrize('mod,name', [('QPSK', '_calculate_llrs_qpsk'), ('16-QAM', '_calculate_llrs_16qam'),
+                                      ('64-QAM', '_calculate_llrs_64qam')])
+def test_llr_api_matches_the_reference_vectors(mod, name):
+    """Per-symbol noise variances through the reference-shaped entry points, against the reference's own output."""
+    from config import LTEConfig
+    from core.modulator import qam16_to_llrs, qpsk_to_llrs
+    from core.ofdm_core import OFDMSimulator
+    sim = OFDMSimulator(LTEConfig(1.25, 15.0, mod))
+    got = getattr(sim, name)(T['llr_sym'], T['llr_nv'])
+    assert np.allclose(got, T[f'llr_{mod}'], rtol=3e-6, atol=3e-6)
+    assert len(getattr(sim, name)(np.array([]), 0.1)) == 0
+    if mod == 'QPSK':
+        assert np.allclose(qpsk_to_llrs(T['llr_sym'], 0.37), O.soft_demap(T['llr_sym'], 0.37, 'QPSK'), rtol=3e-6, atol=3e-6)
+    else:
+        with pytest.raises(NotImplementedError):
+            qam16_to_llrs(T['llr_sym'], 0.1)
