@@ -329,7 +329,7 @@ int lte_bf_link(const lte_plan*, const uint8_t* idx, const lte_c32* h, const lte
  *   10^(-snr/10), fading != 0 selects the |H|^2-scaled variance -> llr [B][nsym*bits_per_symbol].
  * lte_tb_decode: rate_dematching_turbo (rate_matching.py:297-396), turbo_decode in its default
  *   max-log mode (turbo_decoder.py:158-446; `iterations` full iterations + the final decoder-1
- *   pass), desegment_code_blocks (segmentation.py:202-270), check_crc24a and the BER count
+ *   pass; logmap != 0 selects the exact max* = log(e^a + e^b) of set_decoder_mode(False), :35-120), desegment_code_blocks (segmentation.py:202-270), check_crc24a and the BER count
  *   (core/ofdm_core.py:1283-1307).  llr [B][sumE]; dematched [B][sumE] and work
  *   [ceil(B*C/4)*4][lte_tb_decode_work_floats(Kmax)] floats and cbdec [B][sumK] are scratch; bits_tx (optional)
  *   [B][A]; outputs (each optional) bits_rx [B][A], crc_ok [B] int32, errors [B] uint64. */
@@ -343,7 +343,7 @@ int lte_soft_demap(const lte_plan*, const lte_c32* data, const lte_c32* H, int w
                    void* stream);
 int64_t lte_tb_decode_work_floats(int32_t Kmax);
 int lte_tb_decode(const float* llr, const int32_t* blk, int32_t C, int64_t sumK, int64_t sumE, int32_t Kmax,
-                  const int32_t* dm_table, const int32_t* pi_tab, int32_t iterations, float* dematched,
+                  const int32_t* dm_table, const int32_t* pi_tab, int32_t iterations, int32_t logmap, float* dematched,
                   float* work, uint8_t* cbdec, int64_t A, const uint8_t* bits_tx, uint8_t* bits_rx,
                   int32_t* crc_ok, unsigned long long* errors, int64_t B, void* stream);
 
@@ -360,8 +360,9 @@ int lte_crc_bits(const uint8_t* bits, int64_t n, uint32_t poly, int32_t len, uin
 int lte_turbo_encode_blocks(const uint8_t* cb, const int32_t* blk, int32_t C, int64_t sumK, int64_t sumE,
                             const int32_t* pi_tab, uint8_t* enc, int64_t B, void* stream);
 int lte_turbo_decode_blocks(const float* dl, const int32_t* blk, int32_t C, int64_t sumK, int64_t sumE,
-                            int32_t Kmax, const int32_t* pi_tab, int32_t iterations, float* work,
-                            uint8_t* cbdec, const float* apriori, float* apost, int64_t B, void* stream);
+                            int32_t Kmax, const int32_t* pi_tab, int32_t iterations, int32_t logmap,
+                            float* work, uint8_t* cbdec, const float* apriori, float* apost, int64_t B,
+                            void* stream);
 int lte_gather_u8(const uint8_t* src, int64_t n_src, const int32_t* table, int64_t n, uint8_t* out, int64_t B,
                   void* stream);
 int lte_gather_f32(const float* src, int64_t n_src, const int32_t* table, int64_t n, float* out, int64_t B,

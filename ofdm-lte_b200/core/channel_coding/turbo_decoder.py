@@ -1,6 +1,6 @@
-"""Max-log BCJR turbo decoder (reference core/channel_coding/turbo_decoder.py:24-446) on
-`lte_turbo_decode_blocks`.  Only the reference's default mode (USE_MAX_LOG_MAP = True) is implemented on the
-GPU; asking for the exact log-MAP mode raises instead of silently decoding differently."""
+"""BCJR turbo decoder (reference core/channel_coding/turbo_decoder.py:24-446) on `lte_turbo_decode_blocks`:
+max-log-MAP (the reference's default, USE_MAX_LOG_MAP = True) or, after set_decoder_mode(False), the exact
+Jacobian logarithm max*(a, b) = max + log1p(e^-|a-b|)."""
 import numpy as np
 import torch
 
@@ -14,13 +14,20 @@ USE_MAX_LOG_MAP = True
 
 def set_decoder_mode(use_max_log_map=True):
     global USE_MAX_LOG_MAP
-    if not use_max_log_map:
-        raise NotImplementedError("the CUDA decoder implements the reference's default max-log-MAP mode only")
-    USE_MAX_LOG_MAP = True
+    USE_MAX_LOG_MAP = bool(use_max_log_map)
+    print(f"Turbo Decoder mode set to: {'Max-Log-MAP (fast)' if USE_MAX_LOG_MAP else 'True Log-MAP (exact)'}")
+
+
+def log_sum_exp(a, b):
+    if np.isinf(a) and a < 0:
+        return b
+    if np.isinf(b) and b < 0:
+        return a
+    return max(a, b) + np.log1p(np.exp(-abs(a - b)))
 
 
 def max_star(a, b):
-    return max(a, b)
+    return max(a, b) if USE_MAX_LOG_MAP else log_sum_exp(a, b)
 
 
 def _run(dl, K, iterations, apriori=None, want_apost=False, with_pi=True):
@@ -32,7 +39,7 @@ def _run(dl, K, iterations, apriori=None, want_apost=False, with_pi=True):
     ap = torch.from_numpy(np.ascontiguousarray(apriori, dtype=np.float32)[None]).to(dev) if apriori is not None else None
     apost = torch.empty((1, K + 3), dtype=torch.float32, device=dev) if want_apost else None
     nat.check(nat.lib.lte_turbo_decode_blocks(g.ptr(x), g.ptr(blk), 1, K, 3 * K + 12, K, g.ptr(pi), int(iterations),
-                                              g.ptr(work), g.ptr(bits), g.ptr(ap), g.ptr(apost), 1, g.stream()),
+                                              0 if USE_MAX_LOG_MAP else 1, g.ptr(work), g.ptr(bits), g.ptr(ap), g.ptr(apost), 1, g.stream()),
               'lte_turbo_decode_blocks')
     return bits.cpu().numpy()[0], (apost.cpu().numpy()[0].astype(np.float64) if want_apost else None)
 

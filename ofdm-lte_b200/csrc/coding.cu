@@ -268,12 +268,22 @@ struct Bcjr {
     const float* ls_tail; const float* lp_tail;          // 3 tail LLRs each
 };
 
+// max*(a, b): max-log-MAP (the reference's default, USE_MAX_LOG_MAP = True) or the exact Jacobian logarithm
+// log(e^a + e^b) = max + log1p(e^-|a-b|) of its "true Log-MAP" mode (turbo_decoder.py:64-120); -inf is the
+// neutral element in both.
+template <bool LOGMAP> __device__ __forceinline__ float max_star(float a, float b) {
+    const float m = fmaxf(a, b);
+    if (!LOGMAP) return m;
+    if (m == -INFINITY) return m;
+    return m + log1pf(expf(-fabsf(a - b)));
+}
+
 // All shuffles use the full warp mask: the four code blocks of a warp step in lockstep over the longest of
 // their trellises (nch_w chunks), shorter or absent blocks just predicate their updates off.  (A per-group
 // mask makes nvcc wrap every shuffle in a MATCH/VOTE convergence loop -- 3x the instructions.)
 #define FULLMASK 0xffffffffu
 
-template <bool EXTRINSIC_OUT>
+template <bool EXTRINSIC_OUT, bool LOGMAP>
 __device__ __forceinline__ void bcjr_pass(const Bcjr in, int K, int nch_w, float* __restrict__ alpha,
                                           float* __restrict__ ext_out, bool scatter, uint8_t* __restrict__ bits_out,
                                           int st, float* __restrict__ apost_out = nullptr) {
@@ -329,7 +339,7 @@ __device__ __forceinline__ void bcjr_pass(const Bcjr in, int K, int nch_w, float
                 const float x0 = __shfl_sync(FULLMASK, a, pr0, 8) + g0;
                 const float x1 = __shfl_sync(FULLMASK, a, pr1, 8) + g1;
                 if (k < n) {
-                    a = fmaxf(x0, x1);
+                    a = max_star<LOGMAP>(x0, x1);
                     alpha[(size_t)(k + 1) * 32] = a;
                 }
             }
@@ -362,11 +372,11 @@ __device__ __forceinline__ void bcjr_pass(const Bcjr in, int K, int nch_w, float
                 float v0 = (ca[j] + g0) + b0, v1 = (ca[j] + g1) + b1;
 #pragma unroll
                 for (int o = 4; o > 0; o >>= 1) {
-                    v0 = fmaxf(v0, __shfl_xor_sync(FULLMASK, v0, o, 8));
-                    v1 = fmaxf(v1, __shfl_xor_sync(FULLMASK, v1, o, 8));
+                    v0 = max_star<LOGMAP>(v0, __shfl_xor_sync(FULLMASK, v0, o, 8));
+                    v1 = max_star<LOGMAP>(v1, __shfl_xor_sync(FULLMASK, v1, o, 8));
                 }
                 if (k < n) {
-                    bt = fmaxf(b0 + g0, b1 + g1);
+                    bt = max_star<LOGMAP>(b0 + g0, b1 + g1);
                     if (st == 0) {
                         const float ap = v0 - v1;
                         if (k < K) {
@@ -384,6 +394,7 @@ __device__ __forceinline__ void bcjr_pass(const Bcjr in, int K, int nch_w, float
     }
 }
 
+template <bool LOGMAP>
 __global__ void __launch_bounds__(128)
 turbo_decode_kernel(const float* __restrict__ dl, const int* __restrict__ blk, int C, long long sumK, long long sumE,
                     const int* __restrict__ pi_tab, int iterations, float* __restrict__ work, long long work_per_blk,
@@ -414,12 +425,12 @@ turbo_decode_kernel(const float* __restrict__ dl, const int* __restrict__ blk, i
     const Bcjr d1 = {x, x + 1, e21, nullptr, x + 3 * Kq, x + 3 * Kq + 3};
     const Bcjr d2 = {x, x + 2, e12, pi, x + 3 * Kq + 6, x + 3 * Kq + 9};
     for (int it = 0; it < iterations; ++it) {
-        bcjr_pass<true>(d1, K, nch_w, alpha, e12, false, nullptr, st);
+        bcjr_pass<true, LOGMAP>(d1, K, nch_w, alpha, e12, false, nullptr, st);
         __syncwarp();
-        bcjr_pass<true>(d2, K, nch_w, alpha, e21, true, nullptr, st);    // e21[pi[k]] = ext2[k]: the de-interleave
+        bcjr_pass<true, LOGMAP>(d2, K, nch_w, alpha, e21, true, nullptr, st);    // e21[pi[k]] = ext2[k]: the de-interleave
         __syncwarp();
     }
-    bcjr_pass<false>(d1, K, nch_w, alpha, nullptr, false, cbdec + (size_t)b * sumK + q[BLK_CB], st,
+    bcjr_pass<false, LOGMAP>(d1, K, nch_w, alpha, nullptr, false, cbdec + (size_t)b * sumK + q[BLK_CB], st,
                      apost ? apost + (size_t)b * (sumK + 3 * C) + q[BLK_CB] + 3 * r : nullptr);
 }
 
@@ -457,7 +468,7 @@ __global__ void tb_check_kernel(const uint8_t* __restrict__ cbdec, const int* __
 extern "C" int64_t lte_tb_decode_work_floats(int32_t Kmax) { return (int64_t)(Kmax + 4) * 8 + 2 * (int64_t)Kmax; }
 
 extern "C" int lte_tb_decode(const float* llr, const int32_t* blk, int32_t C, int64_t sumK, int64_t sumE, int32_t Kmax,
-                             const int32_t* dm_table, const int32_t* pi_tab, int32_t iterations, float* dematched,
+                             const int32_t* dm_table, const int32_t* pi_tab, int32_t iterations, int32_t logmap, float* dematched,
                              float* work, uint8_t* cbdec, int64_t A, const uint8_t* bits_tx, uint8_t* bits_rx,
                              int32_t* crc_ok, unsigned long long* errors, int64_t B, void* stream) {
     if (!llr || !blk || !dm_table || !pi_tab || !dematched || !work || !cbdec || C < 1 || sumK < 40 || Kmax < 40 ||
@@ -468,9 +479,14 @@ extern "C" int lte_tb_decode(const float* llr, const int32_t* blk, int32_t C, in
     const long long t2 = B * sumE;
     gather_f32_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>(llr, sumE, dm_table, sumE, dematched, t2);
     const long long nblk = B * C;
-    turbo_decode_kernel<<<(unsigned)((nblk * 8 + 127) / 128), 128, 0, st>>>(
-        dematched, blk, C, sumK, sumE, pi_tab, iterations, work, lte_tb_decode_work_floats(Kmax), Kmax, cbdec, nblk, nullptr,
-        nullptr);
+    if (logmap)
+        turbo_decode_kernel<true><<<(unsigned)((nblk * 8 + 127) / 128), 128, 0, st>>>(
+            dematched, blk, C, sumK, sumE, pi_tab, iterations, work, lte_tb_decode_work_floats(Kmax), Kmax, cbdec, nblk,
+            nullptr, nullptr);
+    else
+        turbo_decode_kernel<false><<<(unsigned)((nblk * 8 + 127) / 128), 128, 0, st>>>(
+            dematched, blk, C, sumK, sumE, pi_tab, iterations, work, lte_tb_decode_work_floats(Kmax), Kmax, cbdec, nblk,
+            nullptr, nullptr);
     tb_check_kernel<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(cbdec, blk, C, sumK, A, bits_tx, bits_rx, crc_ok,
                                                               errors, B);
     LTE_CHECK_CUDA(cudaGetLastError());
@@ -519,15 +535,20 @@ extern "C" int lte_turbo_encode_blocks(const uint8_t* cb, const int32_t* blk, in
 }
 
 extern "C" int lte_turbo_decode_blocks(const float* dl, const int32_t* blk, int32_t C, int64_t sumK, int64_t sumE,
-                                       int32_t Kmax, const int32_t* pi_tab, int32_t iterations, float* work,
-                                       uint8_t* cbdec, const float* apriori, float* apost, int64_t B, void* stream) {
+                                       int32_t Kmax, const int32_t* pi_tab, int32_t iterations, int32_t logmap,
+                                       float* work, uint8_t* cbdec, const float* apriori, float* apost, int64_t B,
+                                       void* stream) {
     if (!dl || !blk || !pi_tab || !work || !cbdec || C < 1 || sumK < 1 || Kmax < 1 || Kmax > 6144 ||
         sumE != 3 * sumK + 12 * (int64_t)C || iterations < 0 || B < 0)
         return LTE_ERR_INVALID_ARG;
     if (B == 0) return LTE_OK;
     const long long nblk = B * C;
-    turbo_decode_kernel<<<(unsigned)((nblk * 8 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        dl, blk, C, sumK, sumE, pi_tab, iterations, work, lte_tb_decode_work_floats(Kmax), Kmax, cbdec, nblk, apriori, apost);
+    if (logmap)
+        turbo_decode_kernel<true><<<(unsigned)((nblk * 8 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+            dl, blk, C, sumK, sumE, pi_tab, iterations, work, lte_tb_decode_work_floats(Kmax), Kmax, cbdec, nblk, apriori, apost);
+    else
+        turbo_decode_kernel<false><<<(unsigned)((nblk * 8 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+            dl, blk, C, sumK, sumE, pi_tab, iterations, work, lte_tb_decode_work_floats(Kmax), Kmax, cbdec, nblk, apriori, apost);
     LTE_CHECK_CUDA(cudaGetLastError());
     return LTE_OK;
 }

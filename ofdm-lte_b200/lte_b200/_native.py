@@ -87,11 +87,11 @@ _SIGS = {
     'lte_symbol_interleave': ([_P, _P, _I64, _I32, _P, _I64, _P], C.c_int),
     'lte_soft_demap': ([_P, _P, _P, C.c_int, _P, _I32, _I64, _I32, _P, _I64, _P], C.c_int),
     'lte_tb_decode_work_floats': ([_I32], C.c_int64),
-    'lte_tb_decode': ([_P, _P, _I32, _I64, _I64, _I32, _P, _P, _I32, _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _P],
+    'lte_tb_decode': ([_P, _P, _I32, _I64, _I64, _I32, _P, _P, _I32, _I32, _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _P],
                       C.c_int),
     'lte_crc_bits': ([_P, _I64, C.c_uint32, _I32, _P, _I64, _P], C.c_int),
     'lte_turbo_encode_blocks': ([_P, _P, _I32, _I64, _I64, _P, _P, _I64, _P], C.c_int),
-    'lte_turbo_decode_blocks': ([_P, _P, _I32, _I64, _I64, _I32, _P, _I32, _P, _P, _P, _P, _I64, _P], C.c_int),
+    'lte_turbo_decode_blocks': ([_P, _P, _I32, _I64, _I64, _I32, _P, _I32, _I32, _P, _P, _P, _P, _I64, _P], C.c_int),
     'lte_gather_u8': ([_P, _I64, _P, _I64, _P, _I64, _P], C.c_int),
     'lte_gather_f32': ([_P, _I64, _P, _I64, _P, _I64, _P], C.c_int),
     'lte_random_channel': ([_P, _I64, _I32, _I32, _U64, _U64, _P], C.c_int),

@@ -469,7 +469,7 @@ class LinkEngine:
         self.launches += 1
         return llr
 
-    def tb_decode(self, llr, plan, iterations=8, bits_tx=None, want_bits=True):
+    def tb_decode(self, llr, plan, iterations=8, bits_tx=None, want_bits=True, logmap=False):
         """llr float32 [B, sumE] -> (bits_rx uint8 [B, A] or None, crc_ok int32 [B], errors int64 [B] or None)."""
         B = llr.shape[0]
         dem = self._empty((B, plan.sumE), torch.float32)
@@ -479,7 +479,8 @@ class LinkEngine:
         crc_ok = self._empty((B,), torch.int32)
         errors = torch.zeros(B, dtype=torch.int64, device=self.device) if bits_tx is not None else None
         nat.check(nat.lib.lte_tb_decode(_ptr(llr), _ptr(plan.blk), plan.C, plan.sumK, plan.sumE, plan.Kmax,
-                                        _ptr(plan.dm_table), _ptr(plan.pi_tab), int(iterations), _ptr(dem), _ptr(work),
+                                        _ptr(plan.dm_table), _ptr(plan.pi_tab), int(iterations), 1 if logmap else 0, _ptr(dem),
+                                        _ptr(work),
                                         _ptr(cbdec), plan.A, _ptr(bits_tx), _ptr(bits_rx), _ptr(crc_ok), _ptr(errors),
                                         B, self._stream()), 'lte_tb_decode')
         self.launches += 3

@@ -1127,10 +1127,13 @@ def _trellis():
     return ns, so, po
 
 
-def maxlog_bcjr(Ls, Lp, La, extrinsic=True):
-    """LogMAPDecoder.decode in its default max-log mode (core/channel_coding/turbo_decoder.py:158-293):
+def maxlog_bcjr(Ls, Lp, La, extrinsic=True, logmap=False):
+    """LogMAPDecoder.decode (core/channel_coding/turbo_decoder.py:158-293), default max-log mode or
+    (logmap=True) the exact max*(a, b) = log(e^a + e^b) of set_decoder_mode(False) (:64-120):
     start and end in state 0, gamma = (+-Ls +-Lp +-La)/2 with Ls signed by the FEEDBACK bit of the
     branch and La by its input bit."""
+    if logmap:
+        return _logmap_bcjr(Ls, Lp, La, extrinsic)
     ns, so, po = _trellis()
     n = len(Ls)
     g = ((1 - 2 * so)[None] * (Ls[:, None, None] / 2.0) + (1 - 2 * po)[None] * (Lp[:, None, None] / 2.0)) + \
@@ -1150,7 +1153,28 @@ def maxlog_bcjr(Ls, Lp, La, extrinsic=True):
     return (apost < 0).astype(np.uint8), (apost - La - Ls) if extrinsic else apost
 
 
-def turbo_decode(llr, K, f1, f2, num_iterations=8):
+def _logmap_bcjr(Ls, Lp, La, extrinsic):
+    ns, so, po = _trellis()
+    n = len(Ls)
+    g = ((1 - 2 * so)[None] * (Ls[:, None, None] / 2.0) + (1 - 2 * po)[None] * (Lp[:, None, None] / 2.0)) + \
+        (1 - 2 * np.arange(2))[None, None, :] * (La[:, None, None] / 2.0)
+    alpha = np.full((n + 1, 8), -np.inf)
+    beta = np.full((n + 1, 8), -np.inf)
+    alpha[0, 0] = beta[n, 0] = 0.0
+    with np.errstate(invalid='ignore'):
+        for k in range(n):
+            cand = alpha[k][:, None] + g[k]
+            nxt = np.full(8, -np.inf)
+            np.logaddexp.at(nxt, ns.reshape(-1), cand.reshape(-1))
+            alpha[k + 1] = nxt
+        for k in range(n - 1, -1, -1):
+            beta[k] = np.logaddexp.reduce(beta[k + 1][ns] + g[k], axis=1)
+        val = (alpha[:n, :, None] + g) + beta[1:][:, ns]
+        apost = np.logaddexp.reduce(val[:, :, 0], axis=1) - np.logaddexp.reduce(val[:, :, 1], axis=1)
+    return (apost < 0).astype(np.uint8), (apost - La - Ls) if extrinsic else apost
+
+
+def turbo_decode(llr, K, f1, f2, num_iterations=8, logmap=False):
     """turbo_decode (turbo_decoder.py:340-446)."""
     pi = qpp_indices(K, f1, f2)
     inv = np.empty(K, dtype=np.int64)
@@ -1162,10 +1186,10 @@ def turbo_decode(llr, K, f1, f2, num_iterations=8):
     e21 = np.zeros(K)
     z3 = np.zeros(3)
     for _ in range(num_iterations):
-        _, e12 = maxlog_bcjr(Ls, Lp1, np.concatenate([e21, z3]))
-        _, e21i = maxlog_bcjr(Ls2, Lp2, np.concatenate([e12[:K][pi], z3]))
+        _, e12 = maxlog_bcjr(Ls, Lp1, np.concatenate([e21, z3]), logmap=logmap)
+        _, e21i = maxlog_bcjr(Ls2, Lp2, np.concatenate([e12[:K][pi], z3]), logmap=logmap)
         e21 = e21i[:K][inv]
-    bits, _ = maxlog_bcjr(Ls, Lp1, np.concatenate([e21, z3]), extrinsic=False)
+    bits, _ = maxlog_bcjr(Ls, Lp1, np.concatenate([e21, z3]), extrinsic=False, logmap=logmap)
     return bits[:K]
 
 

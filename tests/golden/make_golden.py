@@ -268,6 +268,18 @@ def coding_tables():
         l = 2.0 * (1.0 - 2.0 * enc + sigma * rs.randn(len(enc))) / sigma ** 2
         out[f'dec_bits_{K}'], out[f'dec_llr_{K}'] = u, l
         out[f'dec_out_{K}'] = turbo_decode(l, K=K, num_iterations=8)
+    # exact log-MAP mode (set_decoder_mode(False)): decisions and one BCJR pass with a-priori input
+    from core.channel_coding import turbo_decoder as td
+    quiet(td.set_decoder_mode, False)
+    for K in (40, 104):
+        out[f'dec_out_logmap_{K}'] = td.turbo_decode(out[f'dec_llr_{K}'], K=K, num_iterations=8)
+    l = out['dec_llr_40']
+    Ls, Lp = np.concatenate([l[0:120:3], l[120:123]]), np.concatenate([l[1:120:3], l[123:126]])
+    La = np.concatenate([0.4 * np.cos(np.arange(40)), np.zeros(3)])
+    out['bcjr_logmap_in'] = np.stack([Ls, Lp, La])
+    out['bcjr_logmap_ext'] = td.LogMAPDecoder().decode(Ls, Lp, La, return_extrinsic=True)[1]
+    quiet(td.set_decoder_mode, True)
+    out['bcjr_maxlog_ext'] = td.LogMAPDecoder().decode(Ls, Lp, La, return_extrinsic=True)[1]
     sim = quiet(OFDMSimulator, LTEConfig(1.25, 15.0, 'QPSK'))
     y = (rs.randn(300) + 1j * rs.randn(300)) * 0.8
     nv = 0.05 + rs.rand(300)

@@ -100,6 +100,24 @@ def test_turbo_decode_function(K):
     assert np.allclose(ap, O.maxlog_bcjr(Ls, Lp, np.zeros(K + 3), extrinsic=False)[1], rtol=1e-4, atol=2e-4)
     with pytest.raises(ValueError):
         LogMAPDecoder().decode(Ls, Lp, np.ones(K + 3))
-    from core.channel_coding.turbo_decoder import set_decoder_mode
-    with pytest.raises(NotImplementedError):
-        set_decoder_mode(False)
+
+
+def test_exact_log_map_mode():
+    """set_decoder_mode(False): max*(a, b) = log(e^a + e^b) in the kernel, against the reference's vectors."""
+    from core.channel_coding import LogMAPDecoder, turbo_decode
+    from core.channel_coding import turbo_decoder as td
+    Ls, Lp, La = T['bcjr_logmap_in']
+    try:
+        td.set_decoder_mode(False)
+        assert td.max_star(0.0, 0.0) == pytest.approx(np.log(2.0)) and td.max_star(-np.inf, 1.5) == 1.5
+        _, ext = LogMAPDecoder().decode(Ls, Lp, La, return_extrinsic=True)
+        assert np.allclose(ext, T['bcjr_logmap_ext'], rtol=1e-4, atol=1e-4)
+        got = turbo_decode(T['dec_llr_40'], 40, num_iterations=8)
+        assert np.array_equal(got, T['dec_out_logmap_40'])
+        one = turbo_decode(T['dec_llr_104'], 104, num_iterations=1)
+        l32 = T['dec_llr_104'].astype(np.float32).astype(float)
+        assert np.sum(one != O.turbo_decode(l32, 104, *QPP[104], num_iterations=1, logmap=True)) <= 2
+    finally:
+        td.set_decoder_mode(True)
+    _, ext = LogMAPDecoder().decode(Ls, Lp, La, return_extrinsic=True)
+    assert np.allclose(ext, T['bcjr_maxlog_ext'], rtol=1e-4, atol=1e-4) and td.max_star(0.0, 0.0) == 0.0

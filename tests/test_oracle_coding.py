@@ -71,3 +71,12 @@ def test_simulate_siso_coded_matches_reference(case):
         assert o['crc_pass'] == bool(crc) and o['coded_bits_length'] == int(clen)
         assert abs(o['papr_db'] - papr_db) < 1e-9 and abs(o['noise_var_mean'] - nvm) < 1e-12 * max(1, nvm)
     assert rel_err(o['signal_tx'], g['signal_tx']) < 1e-12
+
+
+def test_bcjr_modes_match_the_reference():
+    """One LogMAPDecoder.decode pass in both modes, and the exact log-MAP decoder's decisions."""
+    Ls, Lp, La = T['bcjr_logmap_in']
+    assert np.allclose(O.maxlog_bcjr(Ls, Lp, La)[1], T['bcjr_maxlog_ext'], rtol=1e-12, atol=1e-12)
+    assert np.allclose(O.maxlog_bcjr(Ls, Lp, La, logmap=True)[1], T['bcjr_logmap_ext'], rtol=1e-10, atol=1e-10)
+    for K in (40, 104):
+        assert np.array_equal(O.turbo_decode(T[f'dec_llr_{K}'], K, *QPP[K], logmap=True), T[f'dec_out_logmap_{K}'])
