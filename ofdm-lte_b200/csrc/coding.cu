@@ -259,7 +259,7 @@ extern "C" int lte_soft_demap(const lte_plan* p, const lte_c32* data, const lte_
 //   state = (s0 << 2) | (s1 << 1) | s2;  branch u: a = u ^ s1 ^ s2, parity = a ^ s0 ^ s2, next = (a << 2) | (s0 << 1) | s1
 //   gamma = (+-Ls +-Lp +-La) / 2 with Ls signed by a (the reference's "systematic" bit), La by u
 //   alpha_0 = beta_n = (0, -inf, ...) over n = K + 3 steps (tail included, a-priori 0 there)
-// Forward pass stores alpha in HBM scratch ([n + 1][32] floats per warp = four blocks, one 128 B line per step);
+// Forward pass stores every 8th alpha in HBM scratch ([n / 8 + 1][32] floats per warp = four blocks, one 128 B line);
 // the backward pass fuses the a-posteriori max over the 16 branches (xor-shuffle reductions in the 8-lane
 // group).  Extrinsic values cross the QPP interleaver through HBM scratch as well.
 struct Bcjr {
@@ -338,27 +338,37 @@ __device__ __forceinline__ void bcjr_pass(const Bcjr in, int K, int nch_w, float
                 const float g1 = (is0 * Ls + ip1 * Lp) + iu1 * La;
                 const float x0 = __shfl_sync(FULLMASK, a, pr0, 8) + g0;
                 const float x1 = __shfl_sync(FULLMASK, a, pr1, 8) + g1;
-                if (k < n) {
-                    a = max_star<LOGMAP>(x0, x1);
-                    alpha[(size_t)(k + 1) * 32] = a;
-                }
+                if (k < n) a = max_star<LOGMAP>(x0, x1);
             }
+            if ((c + 1) * 8 < n) alpha[(size_t)(c + 1) * 32] = a;       // checkpoint: alpha before step 8 (c + 1)
             cLs = nLs; cLp = nLp; cLa = nLa; ckk = nkk;
         }
     }
-    // ---- backward + a-posteriori (alpha of the chunk below is prefetched too)
+    // ---- backward + a-posteriori.  Only every 8th alpha was stored: the chunk's other seven are recomputed from
+    // its checkpoint with the very operations of the forward pass (bit-identical), which trades ~40 % more
+    // arithmetic for an 8x smaller scratch stream -- the decoder is memory-latency bound once the batch fills the SMs.
     float bt = st == 0 ? 0.f : -INFINITY;
     {
-        float cLs, cLp, cLa, nLs = 0.f, nLp = 0.f, nLa = 0.f, ca[8], na[8];
+        float cLs, cLp, cLa, nLs = 0.f, nLp = 0.f, nLa = 0.f, ck, nck = 0.f;
         int ckk, nkk = 0;
         fetch((nch_w - 1) * 8 + st, cLs, cLp, cLa, ckk);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { const int k = (nch_w - 1) * 8 + j; ca[j] = k < n ? alpha[(size_t)k * 32] : 0.f; }
+        ck = (nch_w - 1) * 8 < n ? alpha[(size_t)(nch_w - 1) * 32] : 0.f;
         for (int c = nch_w - 1; c >= 0; --c) {
             if (c > 0) {
                 fetch((c - 1) * 8 + st, nLs, nLp, nLa, nkk);
+                nck = (c - 1) * 8 < n ? alpha[(size_t)(c - 1) * 32] : 0.f;
+            }
+            float ca[8];
+            ca[0] = ck;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { const int k = (c - 1) * 8 + j; na[j] = k < n ? alpha[(size_t)k * 32] : 0.f; }
+            for (int j = 0; j < 7; ++j) {
+                const float Ls = __shfl_sync(FULLMASK, cLs, j, 8), Lp = __shfl_sync(FULLMASK, cLp, j, 8),
+                            La = __shfl_sync(FULLMASK, cLa, j, 8);
+                const float g0 = (is0 * Ls + ip0 * Lp) + iu0 * La;
+                const float g1 = (is0 * Ls + ip1 * Lp) + iu1 * La;
+                const float x0 = __shfl_sync(FULLMASK, ca[j], pr0, 8) + g0;
+                const float x1 = __shfl_sync(FULLMASK, ca[j], pr1, 8) + g1;
+                ca[j + 1] = max_star<LOGMAP>(x0, x1);
             }
 #pragma unroll
             for (int j = 7; j >= 0; --j) {
@@ -387,15 +397,16 @@ __device__ __forceinline__ void bcjr_pass(const Bcjr in, int K, int nch_w, float
                     }
                 }
             }
-            cLs = nLs; cLp = nLp; cLa = nLa; ckk = nkk;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ca[j] = na[j];
+            cLs = nLs; cLp = nLp; cLa = nLa; ckk = nkk; ck = nck;
         }
     }
 }
 
+#ifndef TURBO_MIN_CTAS
+#define TURBO_MIN_CTAS 4
+#endif
 template <bool LOGMAP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, TURBO_MIN_CTAS)
 turbo_decode_kernel(const float* __restrict__ dl, const int* __restrict__ blk, int C, long long sumK, long long sumE,
                     const int* __restrict__ pi_tab, int iterations, float* __restrict__ work, long long work_per_blk,
                     int Kmax, uint8_t* __restrict__ cbdec, long long total, const float* __restrict__ apriori,
@@ -417,7 +428,7 @@ turbo_decode_kernel(const float* __restrict__ dl, const int* __restrict__ blk, i
     // step is one 128-byte line, then e12 / e21 (extrinsic, natural order) per block
     float* wbase = work + (size_t)(gw & ~3ll) * work_per_blk;
     float* alpha = wbase + lane;
-    float* e12 = wbase + (size_t)(Kmax + 4) * 32 + (size_t)(gw & 3) * 2 * Kmax;   // decoder 1 -> 2
+    float* e12 = wbase + (size_t)((Kmax + 10) / 8 + 1) * 32 + (size_t)(gw & 3) * 2 * Kmax;   // decoder 1 -> 2
     float* e21 = e12 + Kmax;                                                     // decoder 2 -> 1 (scattered through pi)
     for (int k = st; k < K; k += 8) e21[k] = apriori ? apriori[(size_t)b * sumK + q[BLK_CB] + k] : 0.f;
     __syncwarp();
@@ -465,7 +476,8 @@ __global__ void tb_check_kernel(const uint8_t* __restrict__ cbdec, const int* __
     if (errors) errors[b] = e;
 }
 
-extern "C" int64_t lte_tb_decode_work_floats(int32_t Kmax) { return (int64_t)(Kmax + 4) * 8 + 2 * (int64_t)Kmax; }
+// per code block: one alpha checkpoint (8 states) per 8 trellis steps + the two extrinsic vectors
+extern "C" int64_t lte_tb_decode_work_floats(int32_t Kmax) { return (int64_t)((Kmax + 10) / 8 + 1) * 8 + 2 * (int64_t)Kmax; }
 
 extern "C" int lte_tb_decode(const float* llr, const int32_t* blk, int32_t C, int64_t sumK, int64_t sumE, int32_t Kmax,
                              const int32_t* dm_table, const int32_t* pi_tab, int32_t iterations, int32_t logmap, float* dematched,
