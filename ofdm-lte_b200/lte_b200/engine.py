@@ -487,7 +487,8 @@ class LinkEngine:
         return bits_rx, crc_ok, errors
 
     def coded_tx(self, bits, plan):
-        """bits [B, A] -> (tx [B, rows*L], rows, nsym): coding chain, QAM map, interleaver, grid + IFFT + CP."""
+        """bits [B, A] -> (tx [B, rows*L], rows, nsym, stats [B, 2] peak / power sums): coding chain, QAM map,
+        block interleaver, resource grid + IFFT + CP."""
         coded = self.tb_encode(bits, plan)
         nsym = -(-plan.sumE // self.bps)
         idx = self._coded_indices(coded, plan, nsym)

@@ -64,33 +64,34 @@ def test_encoder_known_answers_from_the_reference(K):
 
 @pytest.mark.parametrize('mod', ['QPSK', '16-QAM', '64-QAM'])
 def test_soft_demapper_matches_reference_llrs(mod):
+    """lte_soft_demap with its de-interleaving address map: symbol j is read from interleaved position
+    (j % Nd) * rows + j // Nd.  AWGN variance and the |H|^2-scaled variance of the fading branch."""
     eng = _engine(mod=mod)
-    y, nv = T['llr_sym'], T['llr_nv']
-    want = T[f'llr_{mod}']
+    y = T['llr_sym']
     n = len(y)
     rows = -(-n // eng.Nd)
-    # place symbol j at its interleaved position; |H|^2 = sigma2 / nv reproduces the per-symbol variance
     data = np.zeros(rows * eng.Nd, dtype=np.complex64)
     j = np.arange(n)
+    data[(j % eng.Nd) * rows + j // eng.Nd] = y
+    y32 = y.astype(np.complex64).astype(complex)
+    d_t = torch.from_numpy(data[None]).cuda()
+    got = eng.soft_demap(d_t, None, torch.tensor([1.0], device='cuda'), False, n, rows)
+    assert np.allclose(got.cpu().numpy()[0], O.soft_demap(y32, 1.0, mod), rtol=2e-6, atol=2e-6)
+    # fading branch: one estimate per 14-symbol slot; |H|^2 = 4 on slot 0 and 1e-8 on slot 1 exercise the
+    # sigma2 / 4 floor and the 1e-6 clip of core/ofdm_core.py:1238-1250
+    k0, nk = eng.window(1)
+    nslot = -(-rows // 14)
+    H = np.ones((1, nslot, nk), dtype=np.complex64) * 2.0
+    if nslot > 1:
+        H[0, 1] = 1e-4
+    s2 = 0.5
+    got2 = eng.soft_demap(d_t, torch.from_numpy(H).cuda(), torch.tensor([s2], device='cuda'), True, n, rows, window=1)
     q = (j % eng.Nd) * rows + j // eng.Nd
-    data[q] = y
-    got = eng.soft_demap(torch.from_numpy(data[None]).cuda(), None, torch.tensor([1.0], device='cuda'), False, n, rows)
-    s2 = 1.0
-    ref = O.soft_demap(y.astype(np.complex64).astype(complex), s2, mod)
-    assert np.allclose(got.cpu().numpy()[0], ref, rtol=2e-6, atol=2e-6)
-    # per-symbol variances through the channel-estimate path: one slot, H on the data bins of symbol 0..rows-1
-    if rows <= 14:
-        k0, nk = eng.window(1)
-        H = np.ones((1, 1, nk), dtype=np.complex64)
-        s2 = 0.5
-        hp = np.ones(eng.Nd)
-        d = q[q < eng.Nd] if rows == 1 else None
-        got2 = eng.soft_demap(torch.from_numpy(data[None]).cuda(), torch.from_numpy(H).cuda(),
-                              torch.tensor([s2], device='cuda'), True, n, rows, window=1)
-        ref2 = O.soft_demap(y.astype(np.complex64).astype(complex), np.maximum(s2 / 1.0, s2 / 4), mod)
-        assert np.allclose(got2.cpu().numpy()[0], ref2, rtol=2e-6, atol=2e-6)
+    hp = np.where((q // eng.Nd) // 14 == 1, 1e-8, 4.0) if nslot > 1 else np.full(n, 4.0)
+    nv = np.maximum(s2 / np.clip(hp, 1e-6, 1e6), s2 / 4.0)
+    assert np.allclose(got2.cpu().numpy()[0], O.soft_demap(y32, nv, mod), rtol=3e-6, atol=3e-6)
     # the reference's own vectors (per-symbol nv) through the oracle: pins the formula
-    assert np.allclose(O.soft_demap(y, nv, mod), want, rtol=1e-12, atol=1e-12)
+    assert np.allclose(O.soft_demap(y, T['llr_nv'], mod), T[f'llr_{mod}'], rtol=1e-12, atol=1e-12)
 
 
 def _rate_matched(llr_dec, K):
