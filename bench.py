@@ -317,6 +317,10 @@ def run_gpu(args, rank, world):
                     'frac': stages[dom]['frac'], 'traffic': NCU_TRAFFIC.get(dom), 'peak_source': peak_src,
                     'pipeline_bytes_frac': value / world * sum(sb[k.replace('_awgn', '')] for k in stages) / 1e9 / peak,
                     'pipeline_unfused_equivalent_frac': value / world * sum(sb[k] for k in STAGED) / 1e9 / peak}
+        if dom == 'channel_rx_fft':
+            # the fused kernel trades HBM traffic for arithmetic: ncu (profiles/r01_fused_ncu_summary.md) has it at
+            # 63 % fp32-FMA-pipe busy / 57 % issue-active with DRAM at 27 %, i.e. bound by the FMA pipe, not by HBM
+            roofline['limiter'] = 'fp32 FMA pipe (ncu: pipe_fma_cycles_active 63 %, dram 27 % of peak); see DESIGN.md 4.3'
         if world == 1:
             n_cpu = args.cpu_subframes
             v = cpu_subframes_per_s(n_cpu, 1)
