@@ -47,6 +47,18 @@ template <bool INV> __device__ __forceinline__ c2 mul_w2(c2 a, float c, float s)
                : c2{fma2(a.re, cc, mul2(a.im, ss)), fma2(a.im, cc, mul2(a.re, ns))};
 }
 
+// (e + w o, e - w o) for a compile-time twiddle w = c - j s (forward) / c + j s (inverse) in six FFMA2:
+// w o = c [(o.re + t o.im) + j (o.im - t o.re)] with t = s / c (Linzer-Feig form), so the twiddle product
+// and the butterfly's add / subtract share their multiplies -- two packed instructions fewer than
+// mul_w2 followed by cadd2 / csub2.
+template <bool INV> __device__ __forceinline__ void bfly_w2(c2 e, c2 o, float c, float s, c2& x, c2& y) {
+    const float t = INV ? -s / c : s / c;
+    const f2 tt = pk(t, t), nt = pk(-t, -t), cc = pk(c, c), nc = pk(-c, -c);
+    const f2 ur = fma2(tt, o.im, o.re), ui = fma2(nt, o.re, o.im);
+    x = {fma2(cc, ur, e.re), fma2(cc, ui, e.im)};
+    y = {fma2(nc, ur, e.re), fma2(nc, ui, e.im)};
+}
+
 template <bool INV> __device__ __forceinline__ void bfly4p(c2& a0, c2& a1, c2& a2, c2& a3) {
     const c2 b0 = cadd2(a0, a2), b1 = csub2(a0, a2), b2 = cadd2(a1, a3), d = csub2(a1, a3);
     a0 = cadd2(b0, b2);
@@ -59,12 +71,11 @@ template <bool INV> __device__ __forceinline__ void dft8p(c2 (&a)[8]) {
     const float h = 0.70710678118654752440f;
     bfly4p<INV>(a[0], a[2], a[4], a[6]);
     bfly4p<INV>(a[1], a[3], a[5], a[7]);
-    const c2 o1 = mul_w2<INV>(a[3], h, h), o3 = mul_w2<INV>(a[7], -h, h);
-    const c2 e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6], o0 = a[1], o2 = a[5];
+    const c2 e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6], o0 = a[1], o1 = a[3], o2 = a[5], o3 = a[7];
     a[0] = cadd2(e0, o0); a[4] = csub2(e0, o0);
-    a[1] = cadd2(e1, o1); a[5] = csub2(e1, o1);
+    bfly_w2<INV>(e1, o1, h, h, a[1], a[5]);
     a[2] = add_mj<INV>(e2, o2); a[6] = sub_mj<INV>(e2, o2);
-    a[3] = cadd2(e3, o3); a[7] = csub2(e3, o3);
+    bfly_w2<INV>(e3, o3, -h, h, a[3], a[7]);
 }
 
 template <bool INV> __device__ __forceinline__ void dft16p(c2 (&a)[16]) {
@@ -74,17 +85,14 @@ template <bool INV> __device__ __forceinline__ void dft16p(c2 (&a)[16]) {
     dft8p<INV>(e);
     dft8p<INV>(o);
     const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
-    o[1] = mul_w2<INV>(o[1], c1, s1);
-    o[2] = mul_w2<INV>(o[2], h, h);
-    o[3] = mul_w2<INV>(o[3], s1, c1);
-    o[5] = mul_w2<INV>(o[5], -s1, c1);
-    o[6] = mul_w2<INV>(o[6], -h, h);
-    o[7] = mul_w2<INV>(o[7], -c1, s1);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        if (i == 4) { a[4] = add_mj<INV>(e[4], o[4]); a[12] = sub_mj<INV>(e[4], o[4]); }
-        else { a[i] = cadd2(e[i], o[i]); a[i + 8] = csub2(e[i], o[i]); }
-    }
+    a[0] = cadd2(e[0], o[0]); a[8] = csub2(e[0], o[0]);
+    bfly_w2<INV>(e[1], o[1], c1, s1, a[1], a[9]);
+    bfly_w2<INV>(e[2], o[2], h, h, a[2], a[10]);
+    bfly_w2<INV>(e[3], o[3], s1, c1, a[3], a[11]);
+    a[4] = add_mj<INV>(e[4], o[4]); a[12] = sub_mj<INV>(e[4], o[4]);
+    bfly_w2<INV>(e[5], o[5], -s1, c1, a[5], a[13]);
+    bfly_w2<INV>(e[6], o[6], -h, h, a[6], a[14]);
+    bfly_w2<INV>(e[7], o[7], -c1, s1, a[7], a[15]);
 }
 
 template <int R, bool INV> __device__ __forceinline__ void dftRp(c2 (&a)[R]) {
