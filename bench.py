@@ -54,10 +54,10 @@ def stage_bytes(N=2048, cp=144, Nd=999, Np=200, Nc=1200, b=6, R=R_ANT, S=S_SUBFR
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
-# (round 1, 4096 subframes per launch; summaries: profiles/r01_fused_k1_ncu_summary.md for channel_rx_fft,
-# r01_fused_ncu_summary.md and r01_staged_ncu_summary.md for the others)
+# (round 1, 4096 subframes per launch; summaries: profiles/r01_fused_ncu_summary.md for the fused pipeline,
+# r01_staged_ncu_summary.md for channel_tdl / rx_fft)
 NCU_TRAFFIC = {
-    'tx_map_ifft': 1.0118e9, 'channel_rx_fft': 3.1742e9, 'crs_ls_interp_awgn': 0.2719e9,
+    'tx_map_ifft': 1.0118e9, 'channel_rx_fft': 3.1757e9, 'crs_ls_interp_awgn': 0.2719e9,
     'mrc_demap_count_awgn': 2.4214e9, 'channel_tdl': 4.99e9, 'rx_fft': 5.93e9,
 }
 
@@ -319,8 +319,8 @@ def run_gpu(args, rank, world):
                     'pipeline_unfused_equivalent_frac': value / world * sum(sb[k] for k in STAGED) / 1e9 / peak}
         if dom == 'channel_rx_fft':
             # the fused kernel trades HBM traffic for arithmetic: ncu (profiles/r01_fused_ncu_summary.md) has it at
-            # 63 % fp32-FMA-pipe busy / 57 % issue-active with DRAM at 27 %, i.e. bound by the FMA pipe, not by HBM
-            roofline['limiter'] = 'fp32 FMA pipe (ncu: pipe_fma_cycles_active 63 %, dram 27 % of peak); see DESIGN.md 4.3'
+            # 62 % fp32-FMA-pipe busy / 57 % issue-active with DRAM at 28 %, i.e. bound by the FMA pipe, not by HBM
+            roofline['limiter'] = 'fp32 FMA pipe (ncu: pipe_fma_cycles_active 62 %, dram 28 % of peak); see DESIGN.md 4.3'
         if world == 1:
             n_cpu = args.cpu_subframes
             v = cpu_subframes_per_s(n_cpu, 1)
