@@ -110,3 +110,27 @@ def test_full_sweep_api_tracks_the_per_call_api():
     assert abs(loop1 - b1[1]) / b1[1] < 0.25 and abs(loop2 - b2[1]) / b2[1] < 0.3
     with pytest.raises(ValueError):
         sim.run_full_sweep([], [0.0])
+
+
+@pytest.mark.gpu
+def test_run_ber_sweep_batched_matches_the_per_call_loop_statistically():
+    """OFDMSimulator / OFDMModule.run_ber_sweep with rng='philox': one batch for the whole SNR x trials grid."""
+    from config import LTEConfig
+    from core.ofdm_core import OFDMSimulator
+    from ofdm_module import OFDMModule
+    cfg = LTEConfig(1.25, 15.0, 'QPSK')
+    sim = OFDMSimulator(cfg, channel_type='rayleigh_mp', itu_profile='Pedestrian_A', velocity_kmh=3.0, rng='philox', seed=4)
+    np.random.seed(1)
+    seen = []
+    r = sim.run_ber_sweep(62 * 2 * 14, [0.0, 8.0, 16.0], num_trials=200, progress_callback=lambda p, m: seen.append(p))
+    assert list(r['snr_db']) == [0.0, 8.0, 16.0] and r['ber_mean'].shape == (3,) and seen == [100]
+    assert np.all(np.diff(r['ber_mean']) < 0) and np.array_equal(r['ber_mean'], r['ber_values'])
+    assert np.allclose(r['papr_values'], r['papr_values'][0]) and 3.0 < r['papr_values'][0] < 14.0
+    bits = np.random.RandomState(3).randint(0, 2, 62 * 2 * 14)
+    loop = np.mean([sim.simulate_siso(bits, 8.0)['ber'] for _ in range(200)])
+    assert abs(loop - r['ber_mean'][1]) / r['ber_mean'][1] < 0.25
+    # the replaying mode still goes call by call (and OFDMModule delegates)
+    m = OFDMModule(cfg, channel_type='awgn')
+    np.random.seed(2)
+    r2 = m.run_ber_sweep(300, [2.0, 6.0], num_trials=2)
+    assert r2['ber_mean'].shape == (2,) and r2['ber_mean'][0] >= r2['ber_mean'][1]
