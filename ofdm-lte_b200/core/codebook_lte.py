@@ -8,6 +8,85 @@ def _ph(theta):
     return np.exp(1j * theta)
 
 
+def _cols(*columns):
+    """Column vectors -> [T, L] matrix."""
+    return np.stack([np.asarray(c, dtype=complex) for c in columns], axis=1)
+
+
+def _steer(n, step, count):
+    """DFT steering vector: exp(j step m), m = 0..n-1, for `count` equally spaced steps of 2 pi / count."""
+    return [_ph(2 * np.pi * i / count * np.arange(n)) for i in range(count)]
+
+
+# ---- rank 1 (TM6 vectors, re-used by TM4 rank 1; reference :59-118) ---------------------------------------
+def _r1_t2():
+    return [_cols([1, v]) / np.sqrt(2) for v in (1, -1, 1j, -1j)]
+
+
+def _r1_dft(T):
+    return lambda: [_cols(v) / np.sqrt(T) for v in _steer(T, None, 16)]
+
+
+# ---- rank 2 (reference :120-207) ---------------------------------------------------------------------------
+def _r2_t2():
+    return [np.eye(2), _cols([1, 1], [1, -1]) / np.sqrt(2), _cols([1, 1j], [1, -1j]) / np.sqrt(2)]
+
+
+def _r2_t4():
+    ph = [_ph(2 * np.pi * i / 4) for i in range(4)]
+    groups = ([_cols([1, p, 0, 0], [0, 0, 1, p]) / np.sqrt(2) for p in ph],
+              [_cols([1, p, 1, p], [1, -p, -1, p]) / 2 for p in ph],
+              [_cols([1, 0, p, 0], [0, 1, 0, p]) / np.sqrt(2) for p in ph],
+              [_cols([1, 1, p, p], [1, -1, p, -p]) / 2 for p in ph])
+    return [W for g in groups for W in g]
+
+
+def _r2_t8():
+    out = []
+    for v in _steer(4, None, 16):
+        W = np.zeros((8, 2), dtype=complex)
+        W[:4, 0] = W[4:, 1] = v / 2
+        out.append(W)
+    return out
+
+
+# ---- rank 3 (reference :209-252) ---------------------------------------------------------------------------
+def _r3_t4():
+    return [_cols([1, 0, 0, p], [0, 1, 0, p], [0, 0, 1, p]) / np.sqrt(2) for p in (_ph(2 * np.pi * i / 8) for i in range(8))]
+
+
+def _r3_t8():
+    out = []
+    for v in _steer(3, None, 16):
+        W = np.zeros((8, 3), dtype=complex)
+        for col, row in enumerate((0, 3, 5)):
+            W[row:row + 3, col] = v / np.sqrt(3)
+        out.append(W)
+    return out
+
+
+# ---- rank 4 (reference :254-311) ---------------------------------------------------------------------------
+def _r4_t4():
+    m = np.arange(4)
+    had = np.array([[1, 1, 1, 1], [1, -1, 1, -1], [1, 1, -1, -1], [1, -1, -1, 1]])
+    quad = np.array([[1, 1, 1, 1], [1, 1j, -1, -1j], [1, -1, 1, -1], [1, -1j, -1, 1j]])
+    return [np.eye(4), np.exp(-2j * np.pi * np.outer(m, m) / 4) / 2, had / 2, quad / 2]
+
+
+def _r4_t8():
+    out = []
+    for i in range(8):
+        W = np.zeros((8, 4), dtype=complex)
+        for layer in range(4):
+            W[2 * layer:2 * layer + 2, layer] = np.array([1, _ph(2 * np.pi * i / 8 * (layer + 1))]) / np.sqrt(2)
+        out.append(W)
+    return out
+
+
+_BUILDERS = {(1, 2): _r1_t2, (1, 4): _r1_dft(4), (1, 8): _r1_dft(8), (2, 2): _r2_t2, (2, 4): _r2_t4, (2, 8): _r2_t8,
+             (3, 4): _r3_t4, (3, 8): _r3_t8, (4, 4): _r4_t4, (4, 8): _r4_t8}
+
+
 class LTECodebook:
     def __init__(self, num_tx, transmission_mode='TM6', rank=1):
         self.num_tx = num_tx
@@ -23,57 +102,11 @@ class LTECodebook:
         self.codebook_size = len(self.codebook)
 
     def _generate_codebook(self):
-        T, r = self.num_tx, self.rank
-        cb = []
-        if r == 1:                                           # reference :59-118
-            if T == 2:
-                cb = [np.array([[1], [v]]) / np.sqrt(2) for v in (1, -1, 1j, -1j)]
-            elif T in (4, 8):
-                nrm = 2 if T == 4 else np.sqrt(8)
-                cb = [_ph(2 * np.pi * i * np.arange(T) / 16).reshape(-1, 1) / nrm for i in range(16)]
-        elif r == 2:                                         # reference :120-207
-            if T == 2:
-                cb = [np.array([[1, 0], [0, 1]]), np.array([[1, 1], [1, -1]]) / np.sqrt(2),
-                      np.array([[1, 1], [1j, -1j]]) / np.sqrt(2)]
-            elif T == 4:
-                e = [_ph(2 * np.pi * i / 4) for i in range(4)]
-                cb += [np.array([[1, 0], [p, 0], [0, 1], [0, p]]) / np.sqrt(2) for p in e]
-                cb += [np.array([[1, 1], [p, -p], [1, -1], [p, p]]) / 2 for p in e]
-                cb += [np.array([[1, 0], [0, 1], [p, 0], [0, p]]) / np.sqrt(2) for p in e]
-                cb += [np.array([[1, 1], [1, -1], [p, p], [p, -p]]) / 2 for p in e]
-            elif T == 8:
-                for i in range(16):
-                    W = np.zeros((8, 2), dtype=complex)
-                    W[0:4, 0] = W[4:8, 1] = _ph(2 * np.pi * i / 16 * np.arange(4)) / np.sqrt(4)
-                    cb.append(W)
-        elif r == 3:                                         # reference :209-252
-            if T == 4:
-                cb = [np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [p, p, p]]) / np.sqrt(2)
-                      for p in (_ph(2 * np.pi * i / 8) for i in range(8))]
-            elif T == 8:
-                for i in range(16):
-                    th = 2 * np.pi * i / 16
-                    v = np.array([1, _ph(th), _ph(2 * th)]) / np.sqrt(3)
-                    W = np.zeros((8, 3), dtype=complex)
-                    W[0:3, 0], W[3:6, 1] = v, v
-                    W[5:8, 2] = v
-                    cb.append(W)
-        elif r == 4:                                         # reference :254-311
-            if T == 4:
-                ij = np.outer(np.arange(4), np.arange(4))
-                cb = [np.eye(4, dtype=complex), np.exp(-2j * np.pi * ij / 4) / 2,
-                      np.array([[1, 1, 1, 1], [1, -1, 1, -1], [1, 1, -1, -1], [1, -1, -1, 1]]) / 2,
-                      np.array([[1, 1, 1, 1], [1, 1j, -1, -1j], [1, -1, 1, -1], [1, -1j, -1, 1j]]) / 2]
-            elif T == 8:
-                for i in range(8):
-                    th = 2 * np.pi * i / 8
-                    W = np.zeros((8, 4), dtype=complex)
-                    for l in range(4):
-                        W[2 * l:2 * l + 2, l] = np.array([1, _ph(th * (l + 1))]) / np.sqrt(2)
-                    cb.append(W)
-        if not cb:
-            raise ValueError(f"num_tx={T} no soportado en {self.transmission_mode} Rank-{r}")
-        return cb
+        """Tables keyed by (rank, num_tx); each builder returns the list of [T, rank] precoders."""
+        build = _BUILDERS.get((self.rank, self.num_tx))
+        if build is None:
+            raise ValueError(f"num_tx={self.num_tx} no soportado en {self.transmission_mode} Rank-{self.rank}")
+        return [np.asarray(W, dtype=complex) for W in build()]
 
     def get_codebook(self):
         return self.codebook

@@ -1,90 +1,106 @@
-"""Image <-> bit payload adapters of the GUIs and image tests (reference utils/image_processing.py:9-255).
-Pure host-side I/O (PIL + NumPy): the bits produced here are what simulate_* / payload_sweep carry,
-so the existing front-ends can drive the GPU engine unchanged.  Bit order is np.unpackbits /
-np.packbits (MSB first), the same order `lte_bits_to_indices` consumes."""
+"""Image <-> bit payload adapters used by the GUIs and the image tests of the reference
+(utils/image_processing.py:9-255).  Host-side I/O only: the bit vectors made here are what simulate_* and
+lte_b200.sweep.payload_sweep carry.  Bit order is MSB first per byte, row-major RGB -- the order
+`lte_bits_to_indices` consumes."""
 import numpy as np
 
+_RGB = 'RGB'
+_PEAK = 255.0
 
-def _pil():
-    from PIL import Image
+
+def _image_module():
+    from PIL import Image              # imported lazily: the engine itself never needs PIL
     return Image
 
 
+def _open_rgb(path):
+    im = _image_module().open(path)
+    return im if im.mode == _RGB else im.convert(_RGB)
+
+
+def _pixels(obj):
+    """PIL image or array-like -> ndarray."""
+    return np.array(obj) if isinstance(obj, _image_module().Image) else np.asarray(obj)
+
+
+def _same_shape(ref, other):
+    """Resize `other` to the height / width of `ref` when they differ (the reference's behaviour)."""
+    if ref.shape == other.shape:
+        return other
+    resized = _image_module().fromarray(other).resize((ref.shape[1], ref.shape[0]))
+    return np.array(resized)
+
+
+def _psnr(mse):
+    return float('inf') if mse == 0 else 20.0 * np.log10(_PEAK / np.sqrt(mse))
+
+
+def _mse(a, b):
+    d = a.astype(np.float64) - b.astype(np.float64)
+    return float(np.mean(d * d))
+
+
 class ImageProcessor:
+    """Static helpers with the reference's names and return conventions."""
+
+    @staticmethod
+    def load_image_pil(image_path):
+        return _open_rgb(image_path)
+
     @staticmethod
     def image_to_bits(image_path):
-        """-> (bits uint8 [H*W*3*8], metadata dict) (reference :12-48)."""
-        img = _pil().open(image_path)
-        if img.mode != 'RGB':
-            img = img.convert('RGB')
-        arr = np.array(img)
-        h, w, c = arr.shape
-        return np.unpackbits(arr.flatten()), {'height': h, 'width': w, 'channels': c, 'dtype': str(arr.dtype)}
+        """-> (uint8 bit vector of H*W*3*8 entries, {'height', 'width', 'channels', 'dtype'})."""
+        px = np.array(_open_rgb(image_path))
+        rows, cols, planes = px.shape
+        meta = dict(height=rows, width=cols, channels=planes, dtype=str(px.dtype))
+        return np.unpackbits(px.reshape(-1)), meta
 
     @staticmethod
     def bits_to_image(bits, metadata):
-        """Truncate / zero-pad to the image size and rebuild it (reference :50-89)."""
-        Image = _pil()
-        h, w, c = metadata['height'], metadata['width'], metadata['channels']
-        need = h * w * c * 8
-        bits = np.asarray(bits)
-        bits = np.pad(bits, (0, need - len(bits)), 'constant') if len(bits) < need else bits[:need]
+        """Zero-pad or cut the stream to the image size and rebuild the picture; a black image of the right
+        size if the stream cannot be reshaped."""
+        Image = _image_module()
+        shape = (metadata['height'], metadata['width'], metadata['channels'])
+        want = int(np.prod(shape)) * 8
+        stream = np.zeros(want, dtype=np.uint8)
+        have = np.asarray(bits).astype(np.uint8)[:want]
+        stream[:len(have)] = have
         try:
-            return Image.fromarray(np.packbits(bits.astype(np.uint8)).reshape(h, w, c).astype(np.uint8), 'RGB')
-        except Exception as e:      # the reference returns a black image of the right size
-            print(f"Error al reconstruir imagen: {e}")
-            return Image.new('RGB', (w, h), color='black')
+            return Image.fromarray(np.packbits(stream).reshape(shape), _RGB)
+        except Exception as exc:
+            print(f"Error al reconstruir imagen: {exc}")
+            return Image.new(_RGB, (shape[1], shape[0]), color='black')
 
     @staticmethod
     def calculate_psnr(original_img, reconstructed_img):
-        Image = _pil()
-        a = np.array(original_img) if isinstance(original_img, Image.Image) else np.asarray(original_img)
-        b = np.array(reconstructed_img) if isinstance(reconstructed_img, Image.Image) else np.asarray(reconstructed_img)
-        if a.shape != b.shape:
-            b = np.array(Image.fromarray(b).resize((a.shape[1], a.shape[0])))
-        mse = np.mean((a.astype(float) - b.astype(float)) ** 2)
-        return float('inf') if mse == 0 else 20 * np.log10(255.0 / np.sqrt(mse))
+        ref = _pixels(original_img)
+        return _psnr(_mse(ref, _same_shape(ref, _pixels(reconstructed_img))))
 
     @staticmethod
     def calculate_psnr_bits(original_bits, reconstructed_bits):
-        """PSNR of the byte streams the two bit arrays pack to (reference :131-168)."""
+        """PSNR between the byte streams the two bit vectors pack to, over their common prefix."""
         n = min(len(original_bits), len(reconstructed_bits))
-        a, b = np.asarray(original_bits[:n]), np.asarray(reconstructed_bits[:n])
-        pad = (8 - n % 8) % 8
-        if pad:
-            a = np.concatenate([a, np.zeros(pad, dtype=int)])
-            b = np.concatenate([b, np.zeros(pad, dtype=int)])
-        mse = np.mean((np.packbits(a.astype(np.uint8)).astype(float) - np.packbits(b.astype(np.uint8)).astype(float)) ** 2)
-        return float('inf') if mse == 0 else 20 * np.log10(255.0 / np.sqrt(mse))
+        packed = [np.packbits(np.asarray(v[:n]).astype(np.uint8)) for v in (original_bits, reconstructed_bits)]
+        return _psnr(_mse(packed[0], packed[1]))          # packbits zero-fills the last partial byte on both sides
 
     @staticmethod
     def calculate_ssim(original_img, reconstructed_img):
         try:
-            from skimage.metrics import structural_similarity as ssim
+            from skimage.metrics import structural_similarity
         except ImportError:
             print("scikit-image no disponible para calcular SSIM")
             return None
-        Image = _pil()
-        a = np.array(original_img) if isinstance(original_img, Image.Image) else np.asarray(original_img)
-        b = np.array(reconstructed_img) if isinstance(reconstructed_img, Image.Image) else np.asarray(reconstructed_img)
-        if a.shape != b.shape:
-            b = np.array(Image.fromarray(b).resize((a.shape[1], a.shape[0])))
-        return ssim(a, b, channel_axis=2, data_range=255)
+        ref = _pixels(original_img)
+        return structural_similarity(ref, _same_shape(ref, _pixels(reconstructed_img)), channel_axis=2, data_range=255)
 
     @staticmethod
     def save_comparison(original_path, reconstructed_img, output_path):
-        Image = _pil()
-        orig = Image.open(original_path)
-        if orig.size != reconstructed_img.size:
-            reconstructed_img = reconstructed_img.resize(orig.size)
-        w, h = orig.size
-        comp = Image.new('RGB', (w * 2, h))
-        comp.paste(orig, (0, 0))
-        comp.paste(reconstructed_img, (w, 0))
-        comp.save(output_path)
-        return comp
-
-    @staticmethod
-    def load_image_pil(image_path):
-        img = _pil().open(image_path)
-        return img.convert('RGB') if img.mode != 'RGB' else img
+        """Original and reconstruction side by side."""
+        Image = _image_module()
+        left = Image.open(original_path)
+        right = reconstructed_img if reconstructed_img.size == left.size else reconstructed_img.resize(left.size)
+        canvas = Image.new(_RGB, (2 * left.size[0], left.size[1]))
+        for k, im in enumerate((left, right)):
+            canvas.paste(im, (k * left.size[0], 0))
+        canvas.save(output_path)
+        return canvas
