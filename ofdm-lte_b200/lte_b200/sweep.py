@@ -66,6 +66,50 @@ def simo_sweep(engine, chan, snr_db, n_trials, num_rx, symbols_per_stream=14, se
                      engine.device)
 
 
+def simo_sweep_shared_channel(engine, chan, snr_db, n_trials, num_rx, symbols_per_stream=14, seed=0, batch_trials=4096,
+                             rank=0, world=1, combine=True):
+    """BER curve with the fading realisation of a trial shared by all SNR points (common random numbers along
+    the SNR axis, the usual way to get smooth curves): per trial ONE pass of TX + fused channel + RX FFT gives the
+    noise-free grid and the stream power; every SNR point then only runs the lazy-AWGN CRS estimate and the
+    MRC / demap / count kernels on it, with its own noise draws.  Bits, Jakes phases and the channel are keyed by
+    the global trial id, the noise by (SNR index, trial), so the counts do not depend on batching or sharding.
+    Per SNR point this costs (TX + channel) / n_snr + CRS + MRC instead of the whole chain; the headline bench
+    does NOT use it (there every (trial, SNR) pair is a fully independent link realisation)."""
+    if chan.num_taps == 0:
+        raise ValueError("a shared channel realisation only makes sense for a fading channel")
+    n_snr = len(snr_db)
+    S, R = symbols_per_stream, num_rx
+    snr_lin = [float(10 ** (s / 10)) for s in snr_db]
+    lo, hi = shard_range(n_trials, rank, world)
+    counts = torch.zeros((2, n_snr), dtype=torch.int64, device=engine.device)
+    nbits = S * engine.Nd * engine.bps
+    from . import _native as nat
+    t, ws = lo, None
+    while t < hi:
+        n = min(batch_trials, hi - t)
+        if ws is None or ws['B'] != n:
+            ws = engine.workspace(n, S, R, fading=True, fused=True)
+        idx = engine.random_indices(n, S, seed, t, out=ws['idx'])
+        tx, _, _ = engine.modulate(S, idx=idx, want_stats=False, out=ws['tx'])
+        per = R * chan.num_taps * nat.LTE_JAKES_TONES
+        ph = engine.random_phases(n, per, seed, t, out=ws['phases'].view(-1)[:n * per].view(n, per))
+        got = engine.channel_rx_fft(tx, chan, n, R, S, ph, nat.WINDOW_USEFUL, out=ws['Y'], power=ws['power'])
+        if got is None:
+            raise ValueError("Doppler spread too large for the fused channel kernel; use simo_sweep")
+        Y, power = got
+        for si, sl in enumerate(snr_lin):
+            rows = torch.full((n * R,), sl, dtype=torch.float32, device=engine.device)
+            awgn = engine.awgn_desc(power, rows, seed, (si * n_trials + t) * R, combine=combine)
+            H = engine.estimate(Y, n * R, S, nat.WINDOW_USEFUL, out=ws['H'], awgn=awgn)
+            err = engine.mrc_demap_count(Y, H, idx, n, R, S, nbits=nbits, errors=ws['errors'], awgn=awgn)
+            counts[0, si] += err.sum()
+        counts[1] += n * nbits
+        t += n
+    reduce_counts(counts)
+    errors, bits = counts[0].cpu(), counts[1].cpu()
+    return {'errors': errors, 'bits': bits, 'ber': errors.double() / bits.clamp(min=1).double()}
+
+
 def beamforming_sweep(engine, codebook, snr_db, n_trials, num_tx, num_rx, mode='MRT', symbols_per_stream=14, seed=0,
                       batch_trials=1024, rank=0, world=1):
     """BER of the rank-1 beamforming link (reference OFDMSimulator.simulate_beamforming,

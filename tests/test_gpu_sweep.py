@@ -93,3 +93,23 @@ def test_combined_mrc_noise_and_fused_path_agree_statistically():
     assert np.all(np.abs(fused['ber'].numpy() - b0) / b0 < 0.05)
     # per-antenna draws through the fused kernel: only slicer-boundary flips separate it from the staged path
     assert np.all(np.abs(same['errors'].numpy() - base['errors'].numpy()) <= np.maximum(3, base['errors'].numpy() // 2000))
+
+
+def test_shared_channel_sweep_matches_the_independent_sweep_statistically():
+    """Common random numbers along the SNR axis: same BER curve as fully independent streams (within Monte-Carlo
+    error), invariant to batching and sharding, and the first SNR point of a 1-point sweep reproduces exactly."""
+    from lte_b200.sweep import simo_sweep, simo_sweep_shared_channel
+    eng, chan = _setup(bw=1.25, mod='16-QAM')
+    snr = [2.0, 8.0, 14.0, 20.0]
+    a = simo_sweep_shared_channel(eng, chan, snr, 600, 2, seed=3, batch_trials=600)
+    b = simo_sweep_shared_channel(eng, chan, snr, 600, 2, seed=3, batch_trials=77)
+    assert torch.equal(a['errors'], b['errors'])
+    parts = [simo_sweep_shared_channel(eng, chan, snr, 600, 2, seed=3, batch_trials=128, rank=r, world=3) for r in range(3)]
+    assert torch.equal(sum(p['errors'] for p in parts), a['errors'])
+    assert torch.equal(a['bits'], torch.full((4,), 600 * 14 * eng.Nd * eng.bps, dtype=torch.int64))
+    ind = simo_sweep(eng, chan, snr, n_trials=600, num_rx=2, seed=4, noise_domain=3, fused=True)
+    ba, bi = a['ber'].numpy(), ind['ber'].numpy()
+    assert np.all(np.diff(ba) < 0) and np.all(np.abs(ba - bi) / bi < 0.2)
+    awgn_only = __import__('lte_b200').chan_for('awgn', eng.fs, 'Pedestrian_A', 2.0, 0.0)
+    with pytest.raises(ValueError):
+        simo_sweep_shared_channel(eng, awgn_only, snr, 4, 2)

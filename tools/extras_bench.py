@@ -121,6 +121,25 @@ def main():
     out['sm_cfg5'] = {'workload': f'20MHz 64-QAM 4x4 SM rank 4 MMSE Pedestrian_A, {B5} subframes per pass',
                       'pass_ms': ms5, 'subframes_per_s': B5 / (ms5 * 1e-3)}
 
+    # ---- shared-channel sweep (common random numbers along the SNR axis) on the headline geometry
+    from lte_b200.sweep import simo_sweep_shared_channel
+    cfgh = LTEConfig(20.0, 15.0, '64-QAM')
+    eh = LinkEngine.from_config(cfgh, device=dev)
+    chh = chan_for('rayleigh_mp', cfgh.fs, 'Pedestrian_A', 2.0, 3.0)
+    snrs16 = [float(x) for x in range(0, 32, 2)]
+    simo_sweep_shared_channel(eh, chh, snrs16, 4096, 4, seed=1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        simo_sweep_shared_channel(eh, chh, snrs16, 4096, 4, seed=1)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    out['shared_channel_sweep'] = {'workload': '20MHz 64-QAM SIMO-4 MRC Pedestrian_A, 4096 trials x 16 SNR points, one '
+                                               'channel realisation per trial shared by its SNR points',
+                                   'seconds_per_sweep': dt, 'link_evaluations_per_s': 4096 * 16 / dt,
+                                   'channel_realisations_per_s': 4096 / dt}
+
     if a.cpu:
         from oracle import lte_oracle as O
         T_ = np.load(os.path.join(ROOT, 'tests', 'golden', 'coding_tables.npz'))
