@@ -329,56 +329,62 @@ mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restri
             const float2* yb = Y + ((size_t)b * R * S) * nk + kk;
             const int sym_bits = P.Nd * P.bps;
             const long long valid0 = nbits - ((long long)s0 * P.Nd + d) * P.bps;   // bits left from symbol s0 on
-            constexpr int CH = MRC_CHUNK;                   // symbols per prefetch group
-            float2 yn[CH][R];
-            uint8_t in[CH];
             // running pointers (one per antenna) instead of 64-bit index arithmetic per load
             const float2* yp[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) yp[r] = yb + ((size_t)r * S + s0) * nk;
             const uint8_t* ip = COUNT ? idx_tx + ((size_t)b * S + s0) * P.Nd + d : nullptr;
-            auto fetch = [&](int sf) {
+            // every bit of every symbol of this part is inside the first nbits: no per-symbol 64-bit bit budget
+            const bool all_valid = valid0 - (long long)(s_end - 1 - s0) * sym_bits >= P.bps;
+            // the loads of the next symbol are in flight while this one is combined, sliced and (noisy variants) gets
+            // its Philox / Box-Muller sample
+            auto fetch = [&](float2 (&y)[R], uint8_t& in, int s) {
+                in = 0;
+                if (s < s_end) {
 #pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    in[c] = 0;
-                    if (sf + c < s_end) {
-#pragma unroll
-                        for (int r = 0; r < R; ++r) { yn[c][r] = *yp[r]; yp[r] += nk; }
-                        if (COUNT) { in[c] = *ip; ip += P.Nd; }
-                    }
+                    for (int r = 0; r < R; ++r) { y[r] = *yp[r]; yp[r] += nk; }
+                    if (COUNT) { in = *ip; ip += P.Nd; }
                 }
             };
-            fetch(s0);
-            for (int sg = s0; sg < s_end; sg += CH) {
-                float2 y[CH][R];
-                uint8_t ic[CH];
+            auto combine = [&](float2 (&y)[R], uint8_t in, int s) {
+                float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    ic[c] = in[c];
-#pragma unroll
-                    for (int r = 0; r < R; ++r) y[c][r] = yn[c][r];
+                for (int r = 0; r < R; ++r) {
+                    if (NOISY && !comb) y[r] = awgn_at(A, sigma[r], b * R + r, s, P.N, kb, y[r]);
+                    const float2 t = cmulc(h[r], y[r]);
+                    acc.x += t.x;
+                    acc.y += t.y;
                 }
-                fetch(sg + CH);
+                if (comb) acc = awgn_at(A, csig, b * R, s, P.N, kb, acc);
+                const float2 cc = make_float2(acc.x * inv_den, acc.y * inv_den);
+                if (COUNT) {
+                    const int dec = slice_symbol(P, cc);
+                    e += all_valid ? __popc(dec ^ (int)in)
+                                   : bit_errors(dec, in, P.bps, valid0 - (long long)(s - s0) * sym_bits);
+                } else {
+                    out[((size_t)b * S + s) * P.Nd + d] = cc;
+                }
+            };
+            float2 ya[R], yc[R];
+            uint8_t ia, ic;
+            fetch(ya, ia, s0);
+            if constexpr (!NOISY) {
+                // plain MRC is bandwidth bound: two register sets in ping-pong, no set is ever copied
+                for (int sg = s0; sg < s_end; sg += 2) {
+                    fetch(yc, ic, sg + 1);
+                    combine(ya, ia, sg);
+                    fetch(ya, ia, sg + 2);
+                    if (sg + 1 < s_end) combine(yc, ic, sg + 1);
+                }
+            } else {
+                // the lazy-AWGN variants are issue bound and live on occupancy (72 registers, 7 CTAs / SM): one
+                // prefetched set, copied into the working set every symbol
+                for (int sg = s0; sg < s_end; ++sg) {
 #pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    const int s = sg + c;
-                    if (s < s_end) {
-                        float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            if (NOISY && !comb) y[c][r] = awgn_at(A, sigma[r], b * R + r, s, P.N, kb, y[c][r]);
-                            const float2 t = cmulc(h[r], y[c][r]);
-                            acc.x += t.x;
-                            acc.y += t.y;
-                        }
-                        if (comb) acc = awgn_at(A, csig, b * R, s, P.N, kb, acc);
-                        const float2 cc = make_float2(acc.x * inv_den, acc.y * inv_den);
-                        if (COUNT) {
-                            e += bit_errors(slice_symbol(P, cc), ic[c], P.bps, valid0 - (long long)(s - s0) * sym_bits);
-                        } else {
-                            out[((size_t)b * S + s) * P.Nd + d] = cc;
-                        }
-                    }
+                    for (int r = 0; r < R; ++r) yc[r] = ya[r];
+                    ic = ia;
+                    fetch(ya, ia, sg + 1);
+                    combine(yc, ic, sg);
                 }
             }
         }
