@@ -282,7 +282,7 @@ extern "C" int lte_equalize_zf(const lte_plan* p, const lte_c32* Y, const lte_c3
 #define MRC_CHUNK 1
 #endif
 template <int R, bool COUNT, bool NOISY>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, NOISY ? 8 : 1)
 mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restrict__ H, float2* __restrict__ out,
            const uint8_t* __restrict__ idx_tx, unsigned long long* __restrict__ errors, int k0, int nk, int S,
            int nslot, long long nbits, int gx, int sps, const AwgnArgs A) {
