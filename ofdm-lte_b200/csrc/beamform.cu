@@ -131,7 +131,7 @@ extern "C" int lte_bf_weights(const lte_c32* h, const lte_c32* codebook_host, in
 // (z: [B][S][2][R][Nd], the reference's randn(R, Nd) real block then imaginary block per symbol)
 // or Philox keyed (seed, row_id0 + b*R + r, s*Nd + d).
 template <bool REPLAY>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 bf_link_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float2* __restrict__ h,
                const float2* __restrict__ W, const float2* __restrict__ heff, const float* __restrict__ noise_std,
                const float* __restrict__ z, uint32_t key, unsigned long long row_id0, float2* __restrict__ out,
