@@ -33,6 +33,34 @@ bits_to_indices_kernel(const uint8_t* __restrict__ bits, long long nbits, int pa
     idx[(size_t)row * nsym + q] = (uint8_t)v;
 }
 
+// Packed rows, four symbols per thread: 4 * bps bits are 1, 2 or 3 whole bytes, so the group starts on a byte
+// boundary, is read with at most three byte loads and leaves as one 32-bit store (the sweep's e2e path:
+// 57 M symbols per step).  Requires nsym % 4 == 0 and a 4-byte aligned idx; bits past nbits read as 0.
+__global__ void __launch_bounds__(256)
+bits_to_indices_x4_kernel(const uint8_t* __restrict__ bits, long long nbits, uint8_t* __restrict__ idx, unsigned nsym,
+                          int bps, unsigned chunks) {
+    const unsigned row = blockIdx.x / chunks;
+    const unsigned g = (blockIdx.x - row * chunks) * 256u + threadIdx.x;      // group of 4 symbols
+    if (g * 4u >= nsym) return;
+    const long long row_bytes = (nbits + 7) >> 3;
+    const uint8_t* src = bits + (size_t)row * row_bytes;
+    const int nb = bps >> 1;                                                  // bytes per group
+    const long long by = (long long)g * nb;
+    unsigned w = 0;                                                           // the group's bits, MSB first, left aligned in 24
+#pragma unroll
+    for (int i = 0; i < 3; ++i) w = (w << 8) | ((i < nb && by + i < row_bytes) ? (unsigned)src[by + i] : 0u);
+    const long long bit0 = by * 8;
+    if (nbits - bit0 < 4 * bps) {                                             // the row ends inside this group: clear the tail
+        const long long keep = nbits - bit0;
+        w = keep <= 0 ? 0u : (w & ~((1u << (24 - (int)keep)) - 1u));
+    }
+    const unsigned m = (1u << bps) - 1u;
+    unsigned out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out |= ((w >> (24 - (k + 1) * bps)) & m) << (8 * k);
+    *(unsigned*)(idx + (size_t)row * nsym + 4u * g) = out;
+}
+
 // core/modulator.py:109-110: format(idx, '0{b}b'); output truncated to nbits.
 __global__ void indices_to_bits_kernel(const uint8_t* __restrict__ idx, long long nsym, uint8_t* __restrict__ bits,
                                        long long nbits, int bps, long long total) {
@@ -60,6 +88,14 @@ extern "C" int lte_bits_to_indices(const lte_plan* p, const uint8_t* bits, int64
     const int packed = nbits < 0;        // negative nbits: rows are np.packbits() bytes
     const long long nb = packed ? -nbits : nbits;
     if (nsym >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
+    if (packed && nsym % 4 == 0 && ((uintptr_t)idx & 3) == 0) {
+        const unsigned ch4 = (unsigned)((nsym / 4 + 255) / 256);
+        if ((long long)ch4 * B >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
+        bits_to_indices_x4_kernel<<<(unsigned)((long long)ch4 * B), 256, 0, (cudaStream_t)stream>>>(
+            bits, nb, idx, (unsigned)nsym, p->dev.bps, ch4);
+        LTE_CHECK_CUDA(cudaGetLastError());
+        return LTE_OK;
+    }
     const unsigned chunks = (unsigned)((nsym + 255) / 256);
     const long long grid = (long long)chunks * B;
     if (grid >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;

@@ -185,3 +185,25 @@ def test_frequency_domain_noise_statistics():
         assert abs(kurt - 3.0) < 0.05
         assert abs((v[:-1, 0] * v[1:, 0]).mean().item()) < 5 / m ** 0.5            # adjacent bins uncorrelated
         assert v.abs().max().item() > 4.5                                            # tails present (1e6+ draws)
+
+
+@pytest.mark.parametrize('mod', ['QPSK', '16-QAM', '64-QAM'])
+@pytest.mark.parametrize('nbits_off', [0, 1, 5, 13, 47])
+def test_packed_bits_to_indices_matches_the_byte_per_bit_path(mod, nbits_off):
+    """np.packbits rows (the e2e path of bench.py): the four-symbols-per-thread kernel and the scalar fallback give
+    the indices of QAMModulator.bits_to_symbols, including rows that end inside a symbol / a group of four."""
+    import torch
+    from config import LTEConfig
+    from lte_b200 import LinkEngine
+    eng = LinkEngine.from_config(LTEConfig(1.25, 15.0, mod))
+    b = eng.bps
+    for S in (4, 3):                                   # S * Nd = 248 (x4 kernel) and 186 (not a multiple of 4: fallback)
+        nsym = S * eng.Nd
+        nbits = nsym * b - nbits_off
+        rs = np.random.RandomState(nbits)
+        bits = rs.randint(0, 2, (3, nbits)).astype(np.uint8)
+        packed = np.stack([np.packbits(r) for r in bits])
+        want = np.stack([O.bits_to_indices(np.concatenate([r, np.zeros(nsym * b - nbits, dtype=np.uint8)]), b) for r in bits])
+        got_p = eng.bits_to_indices(torch.from_numpy(packed).cuda(), nbits, S, packed=True).cpu().numpy()
+        got_u = eng.bits_to_indices(torch.from_numpy(bits).cuda(), nbits, S).cpu().numpy()
+        assert np.array_equal(got_u, want) and np.array_equal(got_p, want)
