@@ -33,32 +33,50 @@ bits_to_indices_kernel(const uint8_t* __restrict__ bits, long long nbits, int pa
     idx[(size_t)row * nsym + q] = (uint8_t)v;
 }
 
-// Packed rows, four symbols per thread: 4 * bps bits are 1, 2 or 3 whole bytes, so the group starts on a byte
-// boundary, is read with at most three byte loads and leaves as one 32-bit store (the sweep's e2e path:
-// 57 M symbols per step).  Requires nsym % 4 == 0 and a 4-byte aligned idx; bits past nbits read as 0.
+// Packed rows, one 4-byte-aligned group of idx per thread (the sweep's e2e path: 57 M symbols per step).  The
+// group's four symbols span 4 * bps <= 24 bits at an arbitrary bit offset, i.e. at most four bytes of the row:
+// they are read once into a big-endian window and leave as one 32-bit store.  Rows need not be a multiple of four
+// symbols long: the (at most two) groups a row shares with its neighbours fall back to byte stores of the
+// symbols that belong to this row.  Bits past nbits read as 0.
+__device__ __forceinline__ unsigned packed_symbol(const uint8_t* src, long long row_bytes, long long nbits, long long q,
+                                                  int bps) {
+    const long long bi0 = q * bps, by = bi0 >> 3;
+    const int off = (int)(bi0 & 7);
+    const unsigned hi = by < row_bytes ? src[by] : 0u, lo = by + 1 < row_bytes ? src[by + 1] : 0u;
+    unsigned v = (((hi << 8) | lo) >> (16 - off - bps)) & ((1u << bps) - 1u);
+    const long long left = nbits - bi0;
+    if (left < bps) v = left <= 0 ? 0u : (v & ~((1u << (bps - (int)left)) - 1u));
+    return v;
+}
+
 __global__ void __launch_bounds__(256)
 bits_to_indices_x4_kernel(const uint8_t* __restrict__ bits, long long nbits, uint8_t* __restrict__ idx, unsigned nsym,
                           int bps, unsigned chunks) {
     const unsigned row = blockIdx.x / chunks;
-    const unsigned g = (blockIdx.x - row * chunks) * 256u + threadIdx.x;      // group of 4 symbols
-    if (g * 4u >= nsym) return;
+    const unsigned g = (blockIdx.x - row * chunks) * 256u + threadIdx.x;
+    const unsigned long long row0 = (unsigned long long)row * nsym;           // address of the row's first index
+    const unsigned long long A = ((row0 >> 2) + g) << 2;                      // this thread's aligned group
+    const long long q0 = (long long)A - (long long)row0;                      // its first symbol (may be < 0)
+    if (q0 >= (long long)nsym) return;
     const long long row_bytes = (nbits + 7) >> 3;
     const uint8_t* src = bits + (size_t)row * row_bytes;
-    const int nb = bps >> 1;                                                  // bytes per group
-    const long long by = (long long)g * nb;
-    unsigned w = 0;                                                           // the group's bits, MSB first, left aligned in 24
-#pragma unroll
-    for (int i = 0; i < 3; ++i) w = (w << 8) | ((i < nb && by + i < row_bytes) ? (unsigned)src[by + i] : 0u);
-    const long long bit0 = by * 8;
-    if (nbits - bit0 < 4 * bps) {                                             // the row ends inside this group: clear the tail
-        const long long keep = nbits - bit0;
-        w = keep <= 0 ? 0u : (w & ~((1u << (24 - (int)keep)) - 1u));
+    if (q0 < 0 || q0 + 3 >= (long long)nsym || (q0 + 4) * bps > nbits) {       // shared with a neighbour row / ragged end
+        for (int k = 0; k < 4; ++k) {
+            const long long q = q0 + k;
+            if (q >= 0 && q < (long long)nsym) idx[A + k] = (uint8_t)packed_symbol(src, row_bytes, nbits, q, bps);
+        }
+        return;
     }
+    const long long bi0 = q0 * bps, by = bi0 >> 3;
+    const int off = (int)(bi0 & 7);
+    unsigned w = 0;                                                           // bytes by .. by+3, big endian
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w = (w << 8) | (by + i < row_bytes ? (unsigned)src[by + i] : 0u);
     const unsigned m = (1u << bps) - 1u;
     unsigned out = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) out |= ((w >> (24 - (k + 1) * bps)) & m) << (8 * k);
-    *(unsigned*)(idx + (size_t)row * nsym + 4u * g) = out;
+    for (int k = 0; k < 4; ++k) out |= ((w >> (32 - off - (k + 1) * bps)) & m) << (8 * k);
+    *(unsigned*)(idx + A) = out;
 }
 
 // core/modulator.py:109-110: format(idx, '0{b}b'); output truncated to nbits.
@@ -88,8 +106,8 @@ extern "C" int lte_bits_to_indices(const lte_plan* p, const uint8_t* bits, int64
     const int packed = nbits < 0;        // negative nbits: rows are np.packbits() bytes
     const long long nb = packed ? -nbits : nbits;
     if (nsym >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
-    if (packed && nsym % 4 == 0 && ((uintptr_t)idx & 3) == 0) {
-        const unsigned ch4 = (unsigned)((nsym / 4 + 255) / 256);
+    if (packed && ((uintptr_t)idx & 3) == 0) {
+        const unsigned ch4 = (unsigned)(((nsym + 3) / 4 + 1 + 255) / 256);     // + 1: a row may straddle one more group
         if ((long long)ch4 * B >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
         bits_to_indices_x4_kernel<<<(unsigned)((long long)ch4 * B), 256, 0, (cudaStream_t)stream>>>(
             bits, nb, idx, (unsigned)nsym, p->dev.bps, ch4);
