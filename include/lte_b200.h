@@ -85,7 +85,7 @@ typedef struct {
     double  doppler_hz;               /* fD = v * fc / c (core/channel.py:141-143) */
 } lte_channel_desc;
 
-int lte_version(void);
+int lte_version(void);               /* 100 * major + 10 * minor; 130 = first ABI with the beamforming and coded-chain entry points */
 const char* lte_error_string(int code);
 
 /* Plan = device-resident constant tables: bin classes, pilot values, constellation

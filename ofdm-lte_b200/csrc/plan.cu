@@ -16,7 +16,7 @@ int lte_set_cuda_error(cudaError_t e) {
     return LTE_ERR_CUDA;
 }
 
-extern "C" int lte_version(void) { return 100; }
+extern "C" int lte_version(void) { return 130; }   // 1.3: + beamforming, coded chain, stage-level coding entry points
 
 extern "C" const char* lte_error_string(int code) {
     switch (code) {
