@@ -244,10 +244,10 @@ static int launch_crs(const lte_plan* p, const lte_c32* Y, lte_c32* H, int windo
     const unsigned grid = (unsigned)(rows * nslot);
     const size_t smem = 2 * sizeof(float2) * p->dev.Np;
     if (awgn)
-        crs_ls_interp_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(p->dev, (const float2*)Y, (float2*)H, k0,
+        crs_ls_interp_kernel<true><<<grid, 128, smem, (cudaStream_t)stream>>>(p->dev, (const float2*)Y, (float2*)H, k0,
                                                                              nk, pilot_set, S, nslot, A);
     else
-        crs_ls_interp_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(p->dev, (const float2*)Y, (float2*)H, k0,
+        crs_ls_interp_kernel<false><<<grid, 128, smem, (cudaStream_t)stream>>>(p->dev, (const float2*)Y, (float2*)H, k0,
                                                                               nk, pilot_set, S, nslot, A);
     LTE_CHECK_CUDA(cudaGetLastError());
     return LTE_OK;
