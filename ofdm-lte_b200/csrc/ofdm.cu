@@ -97,25 +97,32 @@ tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float
 #pragma unroll
     for (int m = 0; m < 2; ++m)
         ibase[m] = SYM ? ((size_t)row[m] * S + s_sym[m]) * Nd : ((size_t)tq[m] * S + s_sym[m]) * Nd;
-    // all of this thread's loads first (at most 16 data symbols per transform), then the stores
-    int16_t bin[FFT_ELEMS];
+    // Bin-centric build straight into the IFFT's register layout (thread j owns bins j + e TPF): the
+    // class of every bin comes from the plan's bin_map (data slot / pilot / null), all index or
+    // symbol loads are issued first, then the constellation lookups; no shared-memory grid, no
+    // barrier before the first butterfly pass.
+    __syncthreads();          // s_lev
+    const float2* pa = P.pilots + (size_t)tr[0] * P.Np;
+    const float2* pc = P.pilots + (size_t)tr[1] * P.Np;
+    int code[FFT_ELEMS];
 #pragma unroll
-    for (int e = 0; e < FFT_ELEMS; ++e) {
-        const int d = j + e * TPF;
-        bin[e] = d < Nd ? P.data_idx[d] : (int16_t)-1;
-    }
+    for (int e = 0; e < FFT_ELEMS; ++e) code[e] = __ldg(&P.bin_map[j + e * TPF]);
+    c2 v[FFT_ELEMS];
     if constexpr (SYM) {
 #pragma unroll
-        for (int e = 0; e < FFT_ELEMS; ++e) sbuf[fft_pad(j + e * TPF)] = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncthreads();
-#pragma unroll
         for (int e = 0; e < FFT_ELEMS; ++e) {
-            const int d = j + e * TPF;
-            if (d < Nd) {
-                const float2 a = valid[0] ? symbols[ibase[0] + d] : make_float2(0.f, 0.f);
-                const float2 c = valid[1] ? symbols[ibase[1] + d] : make_float2(0.f, 0.f);
-                sbuf[fft_pad(bin[e])] = make_float4(a.x, c.x, a.y, c.y);
+            const int c = code[e];
+            const bool pil = c >= 0 && (c & BIN_PILOT_FLAG), dat = c >= 0 && !pil;
+            const int q = c & (BIN_PILOT_FLAG - 1);
+            float2 a = make_float2(0.f, 0.f), g = make_float2(0.f, 0.f);
+            if (dat) {
+                if (valid[0]) a = symbols[ibase[0] + q];
+                if (valid[1]) g = symbols[ibase[1] + q];
+            } else if (pil) {
+                if (valid[0]) a = pa[q];
+                if (valid[1]) g = pc[q];
             }
+            v[e] = {pk(a.x, g.x), pk(a.y, g.y)};
         }
     } else {
         uint8_t ib[2][FFT_ELEMS];
@@ -123,44 +130,30 @@ tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float
         for (int m = 0; m < 2; ++m)
 #pragma unroll
             for (int e = 0; e < FFT_ELEMS; ++e) {
-                const int d = j + e * TPF;
-                ib[m][e] = (valid[m] && d < Nd) ? idx[ibase[m] + d] : (uint8_t)0;
+                const int c = code[e];
+                ib[m][e] = (valid[m] && c >= 0 && !(c & BIN_PILOT_FLAG)) ? idx[ibase[m] + c] : (uint8_t)0;
             }
-#pragma unroll
-        for (int e = 0; e < FFT_ELEMS; ++e) sbuf[fft_pad(j + e * TPF)] = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncthreads();
 #pragma unroll
         for (int e = 0; e < FFT_ELEMS; ++e) {
-            const int d = j + e * TPF;
-            if (d < Nd) {
+            const int c = code[e];
+            const bool pil = c >= 0 && (c & BIN_PILOT_FLAG), dat = c >= 0 && !pil;
+            float2 a = make_float2(0.f, 0.f), g = make_float2(0.f, 0.f);
+            if (dat) {
                 const int ia = ib[0][e], ic = ib[1][e];
-                const float2 a = valid[0] ? make_float2(s_lev[(ia >> h) & mask], s_lev[ia & mask]) : make_float2(0.f, 0.f);
-                const float2 c = valid[1] ? make_float2(s_lev[(ic >> h) & mask], s_lev[ic & mask]) : make_float2(0.f, 0.f);
-                sbuf[fft_pad(bin[e])] = make_float4(a.x, c.x, a.y, c.y);
+                if (valid[0]) a = make_float2(s_lev[(ia >> h) & mask], s_lev[ia & mask]);
+                if (valid[1]) g = make_float2(s_lev[(ic >> h) & mask], s_lev[ic & mask]);
                 if (qam_out) {
-                    if (valid[0]) qam_out[ibase[0] + d] = a;
-                    if (valid[1]) qam_out[ibase[1] + d] = c;
+                    if (valid[0]) qam_out[ibase[0] + c] = a;
+                    if (valid[1]) qam_out[ibase[1] + c] = g;
                 }
+            } else if (pil) {
+                const int q = c & (BIN_PILOT_FLAG - 1);
+                if (valid[0]) a = pa[q];
+                if (valid[1]) g = pc[q];
             }
+            v[e] = {pk(a.x, g.x), pk(a.y, g.y)};
         }
     }
-    {
-        const float2* pa = P.pilots + (size_t)tr[0] * P.Np;
-        const float2* pc = P.pilots + (size_t)tr[1] * P.Np;
-        for (int q = j; q < P.Np; q += TPF) {
-            const float2 a = valid[0] ? pa[q] : make_float2(0.f, 0.f);
-            const float2 c = valid[1] ? pc[q] : make_float2(0.f, 0.f);
-            sbuf[fft_pad(P.pilot_idx[q])] = make_float4(a.x, c.x, a.y, c.y);
-        }
-    }
-    __syncthreads();
-    c2 v[FFT_ELEMS];
-#pragma unroll
-    for (int e = 0; e < FFT_ELEMS; ++e) {
-        const float4 q = sbuf[fft_pad(j + e * TPF)];
-        v[e] = {pk(q.x, q.y), pk(q.z, q.w)};
-    }
-    __syncthreads();          // the buffer is re-used by the exchanges
 
     fft2_run<N, true>(v, sbuf, P.twiddle, j);
 
