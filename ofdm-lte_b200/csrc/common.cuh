@@ -19,6 +19,10 @@ int lte_set_cuda_error(cudaError_t e);
 #define BIN_PILOT_FLAG 0x4000
 
 // Device view of a plan; passed to kernels by value.
+// entries behind the N-point twiddle table: per-pass tables of the packed FFT (fft2.cuh, plan.cu)
+#define FFT2_TW_PASS3 256
+#define FFT2_TW_EXTRA 2048
+
 struct DevPlan {
     int N, log2N, Nc, cp, L, Nd, Np, bps;
     int k0_useful, nk_useful;       // occupied-bin window

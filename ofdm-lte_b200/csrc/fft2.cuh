@@ -11,6 +11,14 @@
 #pragma once
 #include "fft.cuh"
 
+// per-pass twiddle tables behind the plan's exp(-2 pi i m / N) table (plan.cu): 0 = powers by repeated
+// multiplication, 1 = second pass from the table, 2 = second and third pass.  Measured on the fused
+// channel + FFT kernel (N = 2048): 1.402 / 1.388 / 1.415 ms -- the 2 KB second-pass table stays in L1,
+// the 14 KB third-pass table does not pay for its 14 loads per thread.
+#ifndef FFT2_TW_TABLE
+#define FFT2_TW_TABLE 1
+#endif
+
 struct f2 { unsigned long long v; };
 struct c2 { f2 re, im; };   // one complex sample of transform A (low) and of transform B (high)
 
@@ -112,10 +120,21 @@ __device__ __forceinline__ void fft2_pass(c2 (&v)[FFT_ELEMS], const float2* __re
         if constexpr (NS > 1) {
             const int k = (j + q * TPF) & (NS - 1);
             float2 w[R];
-            w[1] = __ldg(&tw[k * (N / (NS * R))]);
-            if (INV) w[1].y = -w[1].y;
+            if constexpr (FFT2_TW_TABLE >= (NS <= 16 ? 1 : 2)) {
+                // every twiddle power from the plan's per-pass table: consecutive threads read consecutive
+                // entries (one L1 line per warp and power) instead of spending 4 (R - 2) scalar FMA-pipe ops
+                const float2* tp = tw + N + (NS <= 16 ? 0 : FFT2_TW_PASS3) + k;
 #pragma unroll
-            for (int t = 2; t < R; ++t) w[t] = cmul(w[t >> 1], w[(t + 1) >> 1]);
+                for (int t = 1; t < R; ++t) {
+                    w[t] = __ldg(tp + (t - 1) * NS);
+                    if (INV) w[t].y = -w[t].y;
+                }
+            } else {
+                w[1] = __ldg(&tw[k * (N / (NS * R))]);
+                if (INV) w[1].y = -w[1].y;
+#pragma unroll
+                for (int t = 2; t < R; ++t) w[t] = cmul(w[t >> 1], w[(t + 1) >> 1]);
+            }
 #pragma unroll
             for (int t = 1; t < R; ++t) a[t] = cmul2s(a[t], w[t]);
         }

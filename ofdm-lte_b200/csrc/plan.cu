@@ -108,10 +108,34 @@ extern "C" int lte_plan_create(const lte_plan_desc* d, const lte_c32* pilots_hos
     }
 
     // --- twiddles exp(-2 pi i m / N) from double ---------------------------------------
-    std::vector<float2> tw(N);
+    // followed by the per-pass tables of the packed FFT (fft2.cuh): for a pass of radix R over stride NS,
+    // T[(t - 1) NS + k] = exp(-2 pi i k t / (NS R)), t = 1..R-1, k < NS, so that the threads of a warp
+    // (consecutive k) read consecutive entries; second pass at N, third pass at N + FFT2_TW_PASS3
+    std::vector<float2> tw((size_t)N + FFT2_TW_EXTRA, make_float2(0.f, 0.f));
     for (int m = 0; m < N; ++m) {
         double a = -2.0 * M_PI * (double)m / (double)N;
         tw[m] = make_float2((float)cos(a), (float)sin(a));
+    }
+    {
+        int sched[2][2] = {{0, 0}, {0, 0}};                   // (R, NS) of the twiddled passes
+        switch (N) {
+            case 2048: sched[0][0] = 16; sched[0][1] = 16; sched[1][0] = 8; sched[1][1] = 256; break;
+            case 1024: sched[0][0] = 8; sched[0][1] = 16; sched[1][0] = 8; sched[1][1] = 128; break;
+            case 512: sched[0][0] = 8; sched[0][1] = 8; sched[1][0] = 8; sched[1][1] = 64; break;
+            case 256: sched[0][0] = 16; sched[0][1] = 16; break;
+            case 128: sched[0][0] = 8; sched[0][1] = 16; break;
+            case 64: sched[0][0] = 4; sched[0][1] = 16; break;
+            default: break;
+        }
+        for (int ps = 0; ps < 2; ++ps) {
+            const int R = sched[ps][0], NS = sched[ps][1];
+            float2* T = tw.data() + N + (ps ? FFT2_TW_PASS3 : 0);
+            for (int t = 1; t < R; ++t)
+                for (int k = 0; k < NS; ++k) {
+                    double a = -2.0 * M_PI * (double)k * (double)t / ((double)NS * (double)R);
+                    T[(size_t)(t - 1) * NS + k] = make_float2((float)cos(a), (float)sin(a));
+                }
+        }
     }
 
     // --- single device blob -------------------------------------------------------------
@@ -125,7 +149,7 @@ extern "C" int lte_plan_create(const lte_plan_desc* d, const lte_c32* pilots_hos
     size_t off_pseg = align(off_pinv + sizeof(float2) * pset_inv.size());
     size_t off_pcnt = align(off_pseg + sizeof(int16_t) * pset_seg.size());
     size_t off_tw = align(off_pcnt + sizeof(int) * nsets);
-    size_t total = align(off_tw + sizeof(float2) * N);
+    size_t total = align(off_tw + sizeof(float2) * tw.size());
     std::vector<char> host(total, 0);
     std::vector<int16_t> didx16(Nd ? Nd : 1, 0);
     for (int i = 0; i < Nd; ++i) didx16[i] = (int16_t)p->data_idx_h[i];
@@ -139,7 +163,7 @@ extern "C" int lte_plan_create(const lte_plan_desc* d, const lte_c32* pilots_hos
     memcpy(&host[off_pinv], pset_inv.data(), sizeof(float2) * pset_inv.size());
     memcpy(&host[off_pseg], pset_seg.data(), sizeof(int16_t) * pset_seg.size());
     memcpy(&host[off_pcnt], pset_cnt.data(), sizeof(int) * nsets);
-    memcpy(&host[off_tw], tw.data(), sizeof(float2) * N);
+    memcpy(&host[off_tw], tw.data(), sizeof(float2) * tw.size());
     if (cudaMalloc(&p->blob, total) != cudaSuccess ||
         cudaMemcpy(p->blob, host.data(), total, cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaError_t e = cudaGetLastError();
