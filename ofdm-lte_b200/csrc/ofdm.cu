@@ -104,52 +104,68 @@ tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float
     __syncthreads();          // s_lev
     const float2* pa = P.pilots + (size_t)tr[0] * P.Np;
     const float2* pc = P.pilots + (size_t)tr[1] * P.Np;
+    // element e of every thread of the transform covers bins [e TPF, (e + 1) TPF): outside the occupied
+    // window [k0_useful, k0_useful + nk_useful) the whole group is null and skips its loads (a uniform branch)
+    const int used_lo = P.k0_useful, used_hi = P.k0_useful + P.nk_useful;
     int code[FFT_ELEMS];
 #pragma unroll
-    for (int e = 0; e < FFT_ELEMS; ++e) code[e] = __ldg(&P.bin_map[j + e * TPF]);
+    for (int e = 0; e < FFT_ELEMS; ++e) {
+        const bool used = (e + 1) * TPF > used_lo && e * TPF < used_hi;
+        code[e] = used ? (int)__ldg(&P.bin_map[j + e * TPF]) : BIN_NULL;
+    }
     c2 v[FFT_ELEMS];
     if constexpr (SYM) {
+        const float2* sp0 = symbols + ibase[0];
+        const float2* sp1 = symbols + ibase[1];
 #pragma unroll
         for (int e = 0; e < FFT_ELEMS; ++e) {
-            const int c = code[e];
-            const bool pil = c >= 0 && (c & BIN_PILOT_FLAG), dat = c >= 0 && !pil;
-            const int q = c & (BIN_PILOT_FLAG - 1);
             float2 a = make_float2(0.f, 0.f), g = make_float2(0.f, 0.f);
-            if (dat) {
-                if (valid[0]) a = symbols[ibase[0] + q];
-                if (valid[1]) g = symbols[ibase[1] + q];
-            } else if (pil) {
-                if (valid[0]) a = pa[q];
-                if (valid[1]) g = pc[q];
+            if ((e + 1) * TPF > used_lo && e * TPF < used_hi) {
+                const int c = code[e];
+                const bool pil = c >= 0 && (c & BIN_PILOT_FLAG), dat = c >= 0 && !pil;
+                const int q = c & (BIN_PILOT_FLAG - 1);
+                if (dat) {
+                    if (valid[0]) a = sp0[q];
+                    if (valid[1]) g = sp1[q];
+                } else if (pil) {
+                    if (valid[0]) a = pa[q];
+                    if (valid[1]) g = pc[q];
+                }
             }
             v[e] = {pk(a.x, g.x), pk(a.y, g.y)};
         }
     } else {
+        const uint8_t* ip[2] = {idx + ibase[0], idx + ibase[1]};
         uint8_t ib[2][FFT_ELEMS];
 #pragma unroll
         for (int m = 0; m < 2; ++m)
 #pragma unroll
             for (int e = 0; e < FFT_ELEMS; ++e) {
-                const int c = code[e];
-                ib[m][e] = (valid[m] && c >= 0 && !(c & BIN_PILOT_FLAG)) ? idx[ibase[m] + c] : (uint8_t)0;
+                ib[m][e] = 0;
+                if ((e + 1) * TPF > used_lo && e * TPF < used_hi) {
+                    const int c = code[e];
+                    if (valid[m] && c >= 0 && !(c & BIN_PILOT_FLAG)) ib[m][e] = ip[m][c];
+                }
             }
 #pragma unroll
         for (int e = 0; e < FFT_ELEMS; ++e) {
-            const int c = code[e];
-            const bool pil = c >= 0 && (c & BIN_PILOT_FLAG), dat = c >= 0 && !pil;
             float2 a = make_float2(0.f, 0.f), g = make_float2(0.f, 0.f);
-            if (dat) {
-                const int ia = ib[0][e], ic = ib[1][e];
-                if (valid[0]) a = make_float2(s_lev[(ia >> h) & mask], s_lev[ia & mask]);
-                if (valid[1]) g = make_float2(s_lev[(ic >> h) & mask], s_lev[ic & mask]);
-                if (qam_out) {
-                    if (valid[0]) qam_out[ibase[0] + c] = a;
-                    if (valid[1]) qam_out[ibase[1] + c] = g;
+            if ((e + 1) * TPF > used_lo && e * TPF < used_hi) {
+                const int c = code[e];
+                const bool pil = c >= 0 && (c & BIN_PILOT_FLAG), dat = c >= 0 && !pil;
+                if (dat) {
+                    const int ia = ib[0][e], ic = ib[1][e];
+                    if (valid[0]) a = make_float2(s_lev[(ia >> h) & mask], s_lev[ia & mask]);
+                    if (valid[1]) g = make_float2(s_lev[(ic >> h) & mask], s_lev[ic & mask]);
+                    if (qam_out) {
+                        if (valid[0]) qam_out[ibase[0] + c] = a;
+                        if (valid[1]) qam_out[ibase[1] + c] = g;
+                    }
+                } else if (pil) {
+                    const int q = c & (BIN_PILOT_FLAG - 1);
+                    if (valid[0]) a = pa[q];
+                    if (valid[1]) g = pc[q];
                 }
-            } else if (pil) {
-                const int q = c & (BIN_PILOT_FLAG - 1);
-                if (valid[0]) a = pa[q];
-                if (valid[1]) g = pc[q];
             }
             v[e] = {pk(a.x, g.x), pk(a.y, g.y)};
         }
