@@ -9,11 +9,13 @@
 // tie at y == 0 picks the lower level (16/64-QAM) or the positive one (QPSK).
 __device__ __forceinline__ int slice_axis(const DevPlan& P, float y) {
     if (P.nlev == 2) return y < 0.f ? 1 : 0;
-    // number of thresholds below y by bisection; unused entries of thr[] are +inf (plan.cu)
-    int l = (y > P.thr[3]) ? 4 : 0;
-    l += (y > P.thr[l + 1]) ? 2 : 0;
-    l += (y > P.thr[l]) ? 1 : 0;
-    return l;
+    // number of thresholds below y by bisection; unused entries of thr[] are +inf (plan.cu).  The
+    // threshold of each step is picked with selects between constant-bank operands: thr[l + 1] and
+    // thr[l] with a run-time l would be indexed constant loads on the dependent chain
+    const bool b4 = y > P.thr[3];
+    const bool b2 = y > (b4 ? P.thr[5] : P.thr[1]);
+    const float t1 = b4 ? (b2 ? P.thr[6] : P.thr[4]) : (b2 ? P.thr[2] : P.thr[0]);
+    return (b4 ? 4 : 0) + (b2 ? 2 : 0) + (y > t1 ? 1 : 0);
 }
 __device__ __forceinline__ int slice_symbol(const DevPlan& P, float2 y) {
     return (slice_axis(P, y.x) << (P.bps >> 1)) | slice_axis(P, y.y);
