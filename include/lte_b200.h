@@ -10,9 +10,12 @@
  * Conventions
  *  - Every function returns LTE_OK (0) or a negative LTE_ERR_* code; nothing throws.
  *  - All data pointers are DEVICE pointers owned by the caller unless the name ends
- *    in _host.  The library allocates only the per-plan constant tables and one
- *    per-plan scratch buffer (Jakes polynomial coefficients of lte_channel_tdl, grown
- *    on demand); because of that scratch, use one plan per CUDA stream.
+ *    in _host.  The library allocates nothing but the per-plan constant tables at
+ *    lte_plan_create: kernels that need scratch take a caller-owned `workspace` whose
+ *    size comes from the matching *_workspace_bytes() query (16-byte aligned, contents
+ *    undefined afterwards).  No entry point allocates, frees or synchronises, so one plan
+ *    may be used from several CUDA streams at once (with one workspace per stream).
+ *  - No environment variable changes what a kernel computes.
  *  - Launches are asynchronous on `stream` (a cudaStream_t passed as void*).
  *  - Complex samples are interleaved float pairs (re, im): `lte_c32`.
  *  - A "stream" is one link realisation: S OFDM symbols back to back, L = N + cp
@@ -85,7 +88,7 @@ typedef struct {
     double  doppler_hz;               /* fD = v * fc / c (core/channel.py:141-143) */
 } lte_channel_desc;
 
-int lte_version(void);               /* 100 * major + 10 * minor; 130 = first ABI with the beamforming and coded-chain entry points */
+int lte_version(void);               /* 100 * major + 10 * minor; 200 = caller-owned workspaces, spectral link, compact sweep layout */
 const char* lte_error_string(int code);
 
 /* Plan = device-resident constant tables: bin classes, pilot values, constellation
@@ -160,10 +163,17 @@ int lte_dft_m(const lte_plan*, const lte_c32* in, lte_c32* out, int32_t M, int32
  * draws u in [0,1) (phi = 2*pi*u); faded: [B][R][n], the sum over TX;
  * power: [B][R] sum of |faded|^2 (double, accumulated with atomics, caller zeroes).
  * With num_taps == 0 (channel_type 'awgn') the link is the identity: only `power`
- * (= sum |tx|^2 for every antenna) is produced and `faded` is not written. */
+ * (= sum |tx|^2 for every antenna) is produced and `faded` is not written.
+ * workspace: lte_channel_tdl_workspace_bytes() bytes (Jakes polynomial coefficients; may be NULL
+ * for the identity link).  Accuracy: the fading process is a Taylor polynomial per block of samples
+ * (remainder < 2e-8 of |h|) stepped linearly inside each thread's 8 samples, which adds
+ * (2 pi fD/fs 3.5)^2 / 2 -- 3e-6 for Vehicular_B at 120 km/h and 1.92 MHz; configurations where this
+ * term exceeds 1e-4 (fD/fs > 6.4e-4) return LTE_ERR_UNSUPPORTED. */
+int64_t lte_channel_tdl_workspace_bytes(const lte_plan*, const lte_channel_desc* ch, int32_t B,
+                                        int32_t R, int32_t T, int64_t n);   /* bytes, or LTE_ERR_* (< 0) */
 int lte_channel_tdl(const lte_plan*, const lte_channel_desc* ch, const lte_c32* tx,
-                    const float* phases, lte_c32* faded, double* power, int32_t B, int32_t R,
-                    int32_t T, int64_t n, void* stream);
+                    const float* phases, lte_c32* faded, double* power, void* workspace, int32_t B,
+                    int32_t R, int32_t T, int64_t n, void* stream);
 
 /* AWGN of AWGNChannel.transmit / RayleighMultiPathChannel.transmit
  * (core/channel.py:46-66, :216-232): sigma = sqrt(power/n / snr_lin / 2) per row.
@@ -219,9 +229,39 @@ int lte_equalize_mrc(const lte_plan*, const lte_c32* Y, const lte_c32* H, lte_c3
  * atomics, caller zeroes.  The AWGN is then added lazily by the *_awgn consumers below.
  * Returns LTE_ERR_UNSUPPORTED for the identity link (num_taps = 0) and when the Doppler spread
  * is too large for one Jakes polynomial per OFDM symbol (> about 330 Hz): use the staged pair. */
+int64_t lte_channel_rx_fft_workspace_bytes(const lte_plan*, const lte_channel_desc* ch, int32_t B,
+                                           int32_t R, int32_t S);             /* bytes, or LTE_ERR_* (< 0) */
 int lte_channel_rx_fft(const lte_plan*, const lte_channel_desc* ch, const lte_c32* tx,
-                       const float* phases, lte_c32* Y, double* power, int window, int32_t B,
-                       int32_t R, int32_t S, void* stream);
+                       const float* phases, lte_c32* Y, double* power, void* workspace, int window,
+                       int32_t B, int32_t R, int32_t S, void* stream);
+
+/* --- spectral fading link (sweep engine, T = 1, low Doppler) -------------------------------------
+ * The same reference stages as lte_tx_map_ifft + lte_channel_rx_fft -- QAMModulator.bits_to_symbols,
+ * ResourceMapper.map_symbols, OFDMModulator ifft (core/modulator.py:61-88,214-302,
+ * core/resource_mapper.py:181-223), RayleighChannel.jakes_fading/.filter for the R links
+ * (core/rayleighchannel.py:20-58, core/ofdm_core.py:361-412), the stream power behind the AWGN
+ * (core/channel.py:216-218) and LTEReceiver._demodulate_ofdm_stream (core/lte_receiver.py:444-491) --
+ * without a time-domain stream in HBM and with one forward transform per OFDM symbol instead of one
+ * per antenna.  Valid when every Jakes process is linear over one OFDM symbol to 5e-7
+ * (pi fD L / fs <= 1.41e-3, i.e. 3 km/h at 2 GHz) and every tap delay fits in the cyclic prefix:
+ *   Y_r[k] = sum_t exp(-2 pi j k d_t / N) { (c0 + d_t c1) X[k] + c1 (G[k] - N T_t[k]) }
+ * (csrc/spectral.cu).  lte_tx_spectral: idx [B][S][Nd] -> G [B*S][Nc] = fft((n - n_c) u[n]) / sqrt(N)
+ * on the occupied window and tail [B*S][cp] = the last cp samples of every symbol.
+ * lte_channel_spectral: idx, G, tail, phases [B][R][taps][16] -> Y [B*R][S][Nc] (LTE_WINDOW_USEFUL,
+ * noise-free) and power [B][R] (accumulated, caller zeroes) exactly as lte_channel_rx_fft defines
+ * them.  With Ypilot != NULL the grid leaves in the COMPACT layout of the sweep consumers
+ * (lte_crs_ls_compact, lte_mrc_demap_count_compact): Y [B*R][S][Nd] holds the data bins only, in
+ * data-symbol order, and Ypilot [B*R][ceil(S/14)][Np] the pilot bins of every slot's first symbol --
+ * the only pilots LTEReceiver._estimate_channel_periodic (core/lte_receiver.py:360-411) reads.  workspace: lte_channel_spectral_workspace_bytes() bytes of device memory owned by the caller
+ * (Jakes coefficients; contents are scratch).  Both the size query and the launcher return
+ * LTE_ERR_UNSUPPORTED outside the validity range: use lte_tx_map_ifft + lte_channel_rx_fft. */
+int lte_tx_spectral(const lte_plan*, const uint8_t* idx, lte_c32* G, lte_c32* tail, int32_t B, int32_t S,
+                    void* stream);
+int64_t lte_channel_spectral_workspace_bytes(const lte_plan*, const lte_channel_desc* ch, int32_t B,
+                                             int32_t R, int32_t S);
+int lte_channel_spectral(const lte_plan*, const lte_channel_desc* ch, const uint8_t* idx, const lte_c32* G,
+                         const lte_c32* tail, const float* phases, lte_c32* Y, lte_c32* Ypilot, double* power,
+                         void* workspace, int32_t B, int32_t R, int32_t S, void* stream);
 
 /* --- lazy frequency-domain AWGN for the sweep engine -------------------------------------------
  * The noise lte_rx_fft(noise_domain = 1) would add to grid element (row, symbol, bin) is a pure
@@ -245,6 +285,22 @@ int lte_crs_ls_interp_awgn(const lte_plan*, const lte_c32* Y, lte_c32* H, int wi
 int lte_mrc_demap_count_awgn(const lte_plan*, const lte_c32* Y, const lte_c32* H, const uint8_t* idx_tx,
                              unsigned long long* errors, int window, int64_t nbits, int64_t B, int32_t R,
                              int32_t S, const lte_awgn_desc* awgn, void* stream);
+
+/* Compact sweep layout (produced by lte_channel_spectral with Ypilot != NULL): the grid travels as
+ * Ydata [B*R][S][Nd] (data bins only, data-symbol order) + Ypilot [B*R][ceil(S/14)][Np] (pilot bins of
+ * every slot's first symbol), i.e. exactly the elements LTEReceiver._estimate_channel_periodic
+ * (core/lte_receiver.py:360-411) and _combine_symbols_mrc (core/ofdm_core.py:1484-1532) read.
+ * lte_crs_ls_compact: the LS step of LTEChannelEstimator.estimate_channel (core/lte_receiver.py:62-87),
+ * Hp [B*R][ceil(S/14)][Np] = (Ypilot [+ AWGN]) / pilot; lte_mrc_demap_count_compact interpolates
+ * between the two pilots around each data bin (core/lte_receiver.py:98-133: edge hold + np.linspace, the
+ * very operations of lte_crs_ls_interp), combines, slices and counts.  awgn may be NULL (noise-free
+ * grid); with awgn the draws are those of lte_crs_ls_interp_awgn / lte_mrc_demap_count_awgn, so the
+ * error counts are bit-identical to the windowed layout.  Single pilot set (T = 1) only. */
+int lte_crs_ls_compact(const lte_plan*, const lte_c32* Ypilot, lte_c32* Hp, int64_t rows, int32_t S,
+                       const lte_awgn_desc* awgn, void* stream);
+int lte_mrc_demap_count_compact(const lte_plan*, const lte_c32* Ydata, const lte_c32* Hp,
+                                const uint8_t* idx_tx, unsigned long long* errors, int64_t nbits, int64_t B,
+                                int32_t R, int32_t S, const lte_awgn_desc* awgn, void* stream);
 
 /* --- SFBC Alamouti transmit diversity (2 TX) ---------------------------------------------
  * lte_sfbc_encode replaces SFBCAlamouti.encode (core/sfbc_alamouti.py:45-78) fused with the QAM

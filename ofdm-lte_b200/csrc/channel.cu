@@ -5,10 +5,9 @@
 // Jakes fading  h_i[m] = sqrt(2/16) * sum_n exp(j(2 pi fD cos(a_n) m / fs + phi_n))
 // is evaluated per polynomial block of PB samples: the 16-tone sum and its first K
 // derivatives are formed once at the block centre (phase reduced in fp64), then every
-// thread evaluates the degree-K Taylor polynomial at its own samples.  PB is chosen on
-// the host so that the truncation error stays below 2e-8 (see lte_channel_tdl).
-#include <stdlib.h>
-
+// thread evaluates the degree-K Taylor polynomial (and its derivative) at the centre of its
+// own 8 samples and steps linearly inside them.  PB is chosen on the host so that the block
+// truncation error stays below 2e-8; the linear stepping adds (2 pi fD/fs 3.5)^2 / 2, see tdl_setup.
 #include "tdl.cuh"
 
 // Sample tile of the 8-samples-per-thread layout: sample s lives at [s & 7][s >> 3]; one element is
@@ -140,7 +139,7 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float* __rest
 
         for (int t = 0; t < T; ++t) {
             const float2* plt = plane + ((size_t)stage * T + t) * 8 * XS;
-            for (int tap = 0; tap < (C.debug == 2 ? 1 : C.num_taps); ++tap) {
+            for (int tap = 0; tap < C.num_taps; ++tap) {
                 // per-tap offsets of the thread's 8 delayed samples in the transposed plane (uniform)
                 const int4 o0 = *(const int4*)&xoff[tap * 8], o1 = *(const int4*)&xoff[tap * 8 + 4];
                 const float2* base = plt + tid;
@@ -202,7 +201,7 @@ tdl_kernel(const TdlParams C, const float2* __restrict__ tx, const float* __rest
             }
         }
         __syncthreads();
-        if (C.debug != 1) {
+        {
 #pragma unroll
             for (int p = 0; p < RP; ++p) {
                 const float4* ob = outb + (size_t)(grp * RP + p) * 8 * OS;
@@ -250,9 +249,87 @@ __global__ void power_kernel(const float2* __restrict__ x, int x_div, double* __
     }
 }
 
+// Host-side choice of the polynomial (degree K, block length pb) and the launch geometry of lte_channel_tdl;
+// shared by the workspace-size query and the launcher.
+struct TdlSetup {
+    TdlParams C;
+    int K, halo, R2, tiles, total_tiles;
+    size_t smem, coef_bytes;
+};
+
+static int tdl_setup(const lte_plan* p, const lte_channel_desc* ch, int32_t B, int32_t R, int32_t T, int64_t n,
+                     TdlSetup& U) {
+    if (!p || !ch || B < 0 || R < 1 || R > LTE_MAX_RX || T < 1 || T > LTE_MAX_TX || n < 1) return LTE_ERR_INVALID_ARG;
+    if (ch->num_taps < 1 || ch->num_taps > LTE_MAX_TAPS) return LTE_ERR_INVALID_ARG;
+    TdlParams& C = U.C;
+    memset(&C, 0, sizeof(C));
+    C.num_taps = ch->num_taps;
+    int dmax = 0;
+    for (int i = 0; i < ch->num_taps; ++i) {
+        if (ch->delay[i] < 0) return LTE_ERR_INVALID_ARG;
+        C.delay[i] = ch->delay[i];
+        C.gain[i] = (float)((double)ch->gain[i] * sqrt(2.0 / LTE_JAKES_TONES));
+        if (ch->delay[i] > dmax) dmax = ch->delay[i];
+    }
+    if (dmax > 144) return LTE_ERR_UNSUPPORTED;     // longest ITU-R M.1225 delay at 30.72 MHz is 139 samples
+    U.halo = dmax <= 16 ? 16 : 144;
+    if (n > (1LL << 30) || (long long)B * n > (1LL << 40)) return LTE_ERR_UNSUPPORTED;
+    const double fs = p->desc.fs;
+    double wmax = 0.0;
+    for (int nn = 0; nn < LTE_JAKES_TONES; ++nn) {   // alpha_n = 2 pi n / 16, n = 1..16
+        C.w_cyc[nn] = ch->doppler_hz * cos(2.0 * M_PI * (double)(nn + 1) / LTE_JAKES_TONES) / fs;
+        if (fabs(C.w_cyc[nn]) > wmax) wmax = fabs(C.w_cyc[nn]);
+    }
+    const int tile = TDL_THREADS * 8;
+    // Two error terms, both relative to |h|.  (1) Taylor remainder of the block polynomial, x^(K+1)/(K+1)! with
+    // x = pi w PB: K = 2 needs x < 4.9e-3, K = 4 needs x < 0.075 to stay below 2e-8; PB is the largest power of
+    // two that fits.  (2) Inside a thread the polynomial is stepped linearly over its 8 samples, which drops
+    // (2 pi w 3.5)^2 / 2: 3e-6 for Vehicular_B 120 km/h at 1.92 MHz, 1e-5 at fD / fs = 2e-4 (390 Hz at 1.92 MHz).
+    // Beyond 1e-4 (fD / fs > 6.4e-4) the configuration is refused rather than silently degraded.
+    const double lin = 2.0 * M_PI * wmax * 3.5;
+    if (0.5 * lin * lin > 1e-4) return LTE_ERR_UNSUPPORTED;
+    U.K = 2;
+    C.pb = TDL_MAX_PB;
+    while (C.pb > tile && M_PI * wmax * C.pb > 4.9e-3) C.pb >>= 1;
+    if (M_PI * wmax * C.pb > 4.9e-3) {
+        U.K = 4;
+        C.pb = TDL_MAX_PB;
+        while (C.pb > 32 && M_PI * wmax * C.pb > 0.075) C.pb >>= 1;
+        if (M_PI * wmax * C.pb > 0.075) return LTE_ERR_UNSUPPORTED;   // Doppler too high for this fs
+    }
+    C.pb_log2 = 0;
+    while ((1 << C.pb_log2) < C.pb) ++C.pb_log2;
+    const int nblk = C.pb >= tile ? 1 : tile / C.pb;
+    U.tiles = (int)((n + tile - 1) / tile);
+    // the kernel prefetches the coefficients of WHOLE tiles: every block of the last tile must exist even when
+    // the stream ends inside it
+    C.nbs = C.pb >= tile ? (int)((n + C.pb - 1) / C.pb) : U.tiles * nblk;
+    const int RG = tdl_rg(R), NG = (R + RG - 1) / RG;
+    U.R2 = NG * RG;
+    const int NC = 2 * U.K + 1;
+    const size_t ncoef = (size_t)nblk * T * C.num_taps * NC * 2 * U.R2;            // floats per tile
+    const int xs = tdl_xs_stride(U.halo, tile);
+    U.smem = (size_t)(U.R2 / 2) * 8 * tdl_os_stride(tile) * sizeof(float4) +
+             (size_t)2 * T * 8 * xs * sizeof(float2) + 2 * ncoef * sizeof(float);
+    if (U.smem > 200 * 1024) return LTE_ERR_UNSUPPORTED;
+    const long long total_tiles_ll = (long long)U.tiles * B;
+    if (total_tiles_ll > (1LL << 30)) return LTE_ERR_UNSUPPORTED;
+    U.total_tiles = (int)total_tiles_ll;
+    U.coef_bytes = sizeof(float) * (size_t)B * C.nbs * T * C.num_taps * NC * 2 * U.R2;
+    return LTE_OK;
+}
+
+extern "C" int64_t lte_channel_tdl_workspace_bytes(const lte_plan* p, const lte_channel_desc* ch, int32_t B, int32_t R,
+                                                   int32_t T, int64_t n) {
+    if (ch && ch->num_taps == 0) return 0;          // identity link: nothing to stage
+    TdlSetup U;
+    const int rc = tdl_setup(p, ch, B, R, T, n, U);
+    return rc ? (int64_t)rc : (int64_t)U.coef_bytes + 16;
+}
+
 extern "C" int lte_channel_tdl(const lte_plan* p, const lte_channel_desc* ch, const lte_c32* tx,
-                               const float* phases, lte_c32* faded, double* power, int32_t B, int32_t R,
-                               int32_t T, int64_t n, void* stream) {
+                               const float* phases, lte_c32* faded, double* power, void* workspace, int32_t B,
+                               int32_t R, int32_t T, int64_t n, void* stream) {
     if (!p || !ch || !tx || !power || B < 0 || R < 1 || R > LTE_MAX_RX || T < 1 || T > LTE_MAX_TX || n < 1)
         return LTE_ERR_INVALID_ARG;
     if (ch->num_taps < 0 || ch->num_taps > LTE_MAX_TAPS) return LTE_ERR_INVALID_ARG;
@@ -268,78 +345,25 @@ extern "C" int lte_channel_tdl(const lte_plan* p, const lte_channel_desc* ch, co
         LTE_CHECK_CUDA(cudaGetLastError());
         return LTE_OK;
     }
-    if (!phases || !faded) return LTE_ERR_INVALID_ARG;
+    if (!phases || !faded || !workspace || ((uintptr_t)workspace & 15)) return LTE_ERR_INVALID_ARG;
+    TdlSetup U;
+    int rc = tdl_setup(p, ch, B, R, T, n, U);
+    if (rc) return rc;
+    const TdlParams& C = U.C;
+    const int K = U.K, halo = U.halo, R2 = U.R2, tiles = U.tiles, total_tiles = U.total_tiles;
+    const size_t smem = U.smem;
 
-    TdlParams C;
-    memset(&C, 0, sizeof(C));
-    C.num_taps = ch->num_taps;
-    int dmax = 0;
-    for (int i = 0; i < ch->num_taps; ++i) {
-        if (ch->delay[i] < 0) return LTE_ERR_INVALID_ARG;
-        C.delay[i] = ch->delay[i];
-        C.gain[i] = (float)((double)ch->gain[i] * sqrt(2.0 / LTE_JAKES_TONES));
-        if (ch->delay[i] > dmax) dmax = ch->delay[i];
-    }
-    if (dmax > 144) return LTE_ERR_UNSUPPORTED;     // longest ITU-R M.1225 delay at 30.72 MHz is 139 samples
-    const int halo = dmax <= 16 ? 16 : 144;
-    if (n > (1LL << 30) || (long long)B * n > (1LL << 40)) return LTE_ERR_UNSUPPORTED;
-    const double fs = p->desc.fs;
-    double wmax = 0.0;
-    for (int nn = 0; nn < LTE_JAKES_TONES; ++nn) {   // alpha_n = 2 pi n / 16, n = 1..16
-        C.w_cyc[nn] = ch->doppler_hz * cos(2.0 * M_PI * (double)(nn + 1) / LTE_JAKES_TONES) / fs;
-        if (fabs(C.w_cyc[nn]) > wmax) wmax = fabs(C.w_cyc[nn]);
-    }
-    const int tile = TDL_THREADS * 8;
-    // Taylor remainder x^(K+1)/(K+1)! with x = 2 pi w PB/2 kept below 2e-8:
-    //   K = 2 needs x < 4.9e-3, K = 4 needs x < 0.075.  PB is the largest power of two that fits.
-    int K = 2;
-    C.pb = TDL_MAX_PB;
-    while (C.pb > tile && M_PI * wmax * C.pb > 4.9e-3) C.pb >>= 1;
-    if (M_PI * wmax * C.pb > 4.9e-3) {
-        K = 4;
-        C.pb = TDL_MAX_PB;
-        while (C.pb > 32 && M_PI * wmax * C.pb > 0.075) C.pb >>= 1;
-        if (M_PI * wmax * C.pb > 0.075) return LTE_ERR_UNSUPPORTED;   // Doppler too high for this fs
-    }
-    C.nbs = (int)((n + C.pb - 1) / C.pb);
-    C.debug = getenv("LTE_TDL_DEBUG") ? atoi(getenv("LTE_TDL_DEBUG")) : 0;
-    C.pb_log2 = 0;
-    while ((1 << C.pb_log2) < C.pb) ++C.pb_log2;
-    const int nblk = C.pb >= tile ? 1 : tile / C.pb;
-    const int RG = tdl_rg(R), NG = (R + RG - 1) / RG, R2 = NG * RG;
-    const int NC = 2 * K + 1;
-    const size_t ncoef = (size_t)nblk * T * C.num_taps * NC * 2 * R2;              // floats per tile
-    const int span = halo + tile, xs = tdl_xs_stride(halo, tile);
-    const size_t smem = (size_t)(R2 / 2) * 8 * tdl_os_stride(tile) * sizeof(float4) +
-                        (size_t)2 * T * 8 * xs * sizeof(float2) + 2 * ncoef * sizeof(float);
-    (void)span;
-    if (smem > 200 * 1024) return LTE_ERR_UNSUPPORTED;
-    const int tiles = (int)((n + tile - 1) / tile);
-    const long long total_tiles_ll = (long long)tiles * B;
-    if (total_tiles_ll > (1LL << 30)) return LTE_ERR_UNSUPPORTED;
-    const int total_tiles = (int)total_tiles_ll;
-
-    // per-block polynomial coefficients (scratch owned by the plan, grown on demand)
-    const size_t coef_bytes = sizeof(float) * (size_t)B * C.nbs * T * C.num_taps * NC * 2 * R2;
-    lte_plan* pm = const_cast<lte_plan*>(p);
-    if (pm->scratch_bytes < coef_bytes) {
-        if (pm->scratch) LTE_CHECK_CUDA(cudaFree(pm->scratch));
-        pm->scratch = nullptr;
-        pm->scratch_bytes = 0;
-        LTE_CHECK_CUDA(cudaMalloc(&pm->scratch, coef_bytes));
-        pm->scratch_bytes = coef_bytes;
-    }
-    float* coef = (float*)pm->scratch;
-    if (R2 != R) LTE_CHECK_CUDA(cudaMemsetAsync(coef, 0, coef_bytes, st));   // padding antennas stay zero
+    // per-block polynomial coefficients in the caller's workspace
+    float* coef = (float*)workspace;
+    if (R2 != R) LTE_CHECK_CUDA(cudaMemsetAsync(coef, 0, U.coef_bytes, st));   // padding antennas stay zero
     const long long items = (long long)B * C.nbs * R * T * C.num_taps;
     const unsigned cgrid = (unsigned)((items + 255) / 256);
     if (K == 2) jakes_coef_kernel<2><<<cgrid, 256, 0, st>>>(C, phases, coef, R, T, R2, items);
     else jakes_coef_kernel<4><<<cgrid, 256, 0, st>>>(C, phases, coef, R, T, R2, items);
     LTE_CHECK_CUDA(cudaGetLastError());
 
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
     int ctas = sms * tdl_min_blocks(R);
     if (ctas > total_tiles) ctas = total_tiles;
     const int chunk = (total_tiles + ctas - 1) / ctas;

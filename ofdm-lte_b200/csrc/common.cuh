@@ -49,8 +49,6 @@ struct lte_plan {
     int nsets;
     std::vector<int32_t> data_idx_h, pilot_idx_h;
     void* blob;                     // single device allocation holding all tables
-    void* scratch;                  // library-owned scratch (Jakes polynomial coefficients), grown on demand
-    size_t scratch_bytes;
 };
 
 // ------------------------------------------------------------------ complex helpers

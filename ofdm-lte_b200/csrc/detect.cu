@@ -1,6 +1,5 @@
 // Stage 4 (CRS LS + linear interpolation), stage 5 (ZF / MRC) and stage 6 (hard demap +
 // bit-error count), plus the bit <-> symbol-index helpers of the reference-facing API.
-#include <stdlib.h>
 #include "slicer.cuh"
 
 #include "common.cuh"
@@ -335,7 +334,10 @@ extern "C" int lte_equalize_zf(const lte_plan* p, const lte_c32* Y, const lte_c3
 #ifndef MRC_CHUNK
 #define MRC_CHUNK 1
 #endif
-template <int R, bool COUNT, bool NOISY>
+// COMPACT: Y is [B*R][S][Nd] (data bins only, data-symbol order) and H is the pilot-position estimate
+// Hp [B*R][nslot][Np] of lte_crs_ls_compact; the thread interpolates its own bin between its two neighbouring
+// pilots with the very operations of crs_ls_interp_kernel (edge hold, start + i * (delta / div)).
+template <int R, bool COUNT, bool NOISY, bool COMPACT>
 __global__ void __launch_bounds__(128, NOISY ? 8 : 1)
 mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restrict__ H, float2* __restrict__ out,
            const uint8_t* __restrict__ idx_tx, unsigned long long* __restrict__ errors, int k0, int nk, int S,
@@ -350,7 +352,8 @@ mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restri
     unsigned int e = 0;
     if (d < P.Nd) {
         const int kb = P.data_idx[d];
-        const int kk = kb - k0;
+        const int kk = COMPACT ? d : kb - k0;                  // position inside a Y row
+        const int ystride = COMPACT ? P.Nd : nk;
         float sigma[R];
         if (NOISY) {
 #pragma unroll
@@ -360,10 +363,32 @@ mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restri
             const int slot = part / pps;
             float2 h[R];
             float den = 0.f;
+            if constexpr (COMPACT) {
+                const int cnt = P.pset_cnt[0];
+                const int lo = P.pset_seg[kb];
+                const int la = lo < 0 ? 0 : (lo >= cnt - 1 ? cnt - 1 : lo);
+                const bool inner = lo >= 0 && lo < cnt - 1;
+                const int i1 = P.pset_bin[la];
+                const float div = inner ? (float)(P.pset_bin[la + 1] - i1) : 1.f;
+                const float t = (float)(kb - i1);
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                h[r] = H[(((size_t)b * R + r) * nslot + slot) * nk + kk];
-                den += cabs2(h[r]);
+                for (int r = 0; r < R; ++r) {
+                    const float2* hp = H + (((size_t)b * R + r) * nslot + slot) * P.Np;
+                    const float2 a = hp[la];
+                    float2 v = a;
+                    if (inner && kb != i1) {
+                        const float2 c = hp[la + 1];
+                        v = make_float2(fmaf(t, __fdiv_rn(c.x - a.x, div), a.x), fmaf(t, __fdiv_rn(c.y - a.y, div), a.y));
+                    }
+                    h[r] = v;
+                    den += cabs2(h[r]);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    h[r] = H[(((size_t)b * R + r) * nslot + slot) * nk + kk];
+                    den += cabs2(h[r]);
+                }
             }
             den += 1e-10f;
             const float inv_den = __frcp_rn(den);
@@ -380,13 +405,13 @@ mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restri
             const int s_end = min(S, s0 + sps);
             // register double buffering: the loads of the next group of symbols are in flight while this
             // group is combined, sliced and (noisy variants) gets its Philox / Box-Muller samples
-            const float2* yb = Y + ((size_t)b * R * S) * nk + kk;
+            const float2* yb = Y + ((size_t)b * R * S) * ystride + kk;
             const int sym_bits = P.Nd * P.bps;
             const long long valid0 = nbits - ((long long)s0 * P.Nd + d) * P.bps;   // bits left from symbol s0 on
             // running pointers (one per antenna) instead of 64-bit index arithmetic per load
             const float2* yp[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) yp[r] = yb + ((size_t)r * S + s0) * nk;
+            for (int r = 0; r < R; ++r) yp[r] = yb + ((size_t)r * S + s0) * ystride;
             const uint8_t* ip = COUNT ? idx_tx + ((size_t)b * S + s0) * P.Nd + d : nullptr;
             // every bit of every symbol of this part is inside the first nbits: no per-symbol 64-bit bit budget
             const bool all_valid = valid0 - (long long)(s_end - 1 - s0) * sym_bits >= P.bps;
@@ -396,7 +421,7 @@ mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restri
                 in = 0;
                 if (s < s_end) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) { y[r] = *yp[r]; yp[r] += nk; }
+                    for (int r = 0; r < R; ++r) { y[r] = *yp[r]; yp[r] += ystride; }
                     if (COUNT) { in = *ip; ip += P.Nd; }
                 }
             };
@@ -446,13 +471,14 @@ mrc_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restri
     if (COUNT) block_add_errors(e, &errors[b]);
 }
 
-template <bool COUNT>
+template <bool COUNT, bool COMPACT = false>
 static int launch_mrc(const lte_plan* p, const lte_c32* Y, const lte_c32* H, lte_c32* out, const uint8_t* idx_tx,
                       unsigned long long* errors, int window, int64_t nbits, int64_t B, int32_t R, int32_t S,
                       const lte_awgn_desc* awgn, void* stream) {
     int32_t k0, nk;
     int rc = lte_plan_window(p, window, &k0, &nk);
     if (rc) return rc;
+    if (COMPACT && (p->dev.Np == 0 || p->nsets != 1)) return LTE_ERR_UNSUPPORTED;
     AwgnArgs A = {};
     if (awgn && (rc = make_awgn_args(A, p, awgn, S))) return rc;
     if (B == 0) return LTE_OK;
@@ -460,9 +486,7 @@ static int launch_mrc(const lte_plan* p, const lte_c32* Y, const lte_c32* H, lte
     const int gx = (p->dev.Nd + 127) / 128;
     // symbols per thread: H of the slot is re-read once per part (from L2); short parts expose more
     // parallelism, which the noisy variants need to hide the generator's dependent chains
-    int sps = LTE_SLOT_SYMBOLS;
-    if (getenv("LTE_MRC_SPS")) sps = atoi(getenv("LTE_MRC_SPS"));
-    if (sps != 1 && sps != 2 && sps != 7 && sps != 14) return LTE_ERR_INVALID_ARG;
+    const int sps = LTE_SLOT_SYMBOLS;
     const long long grid_ll = (long long)gx * B * nslot * (LTE_SLOT_SYMBOLS / sps);
     if (grid_ll >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
     const unsigned grid = (unsigned)grid_ll;
@@ -470,11 +494,11 @@ static int launch_mrc(const lte_plan* p, const lte_c32* Y, const lte_c32* H, lte
 #define LAUNCH_MRC(RR)                                                                                          \
     case RR:                                                                                                    \
         if (awgn)                                                                                               \
-            mrc_kernel<RR, COUNT, true><<<grid, 128, 0, st>>>(p->dev, (const float2*)Y, (const float2*)H,      \
+            mrc_kernel<RR, COUNT, true, COMPACT><<<grid, 128, 0, st>>>(p->dev, (const float2*)Y, (const float2*)H,      \
                                                               (float2*)out, idx_tx, errors, k0, nk, S, nslot,  \
                                                               nbits, gx, sps, A);                                    \
         else                                                                                                    \
-            mrc_kernel<RR, COUNT, false><<<grid, 128, 0, st>>>(p->dev, (const float2*)Y, (const float2*)H,     \
+            mrc_kernel<RR, COUNT, false, COMPACT><<<grid, 128, 0, st>>>(p->dev, (const float2*)Y, (const float2*)H,     \
                                                                (float2*)out, idx_tx, errors, k0, nk, S, nslot, \
                                                                nbits, gx, sps, A);                                   \
         break;
@@ -506,4 +530,55 @@ extern "C" int lte_mrc_demap_count_awgn(const lte_plan* p, const lte_c32* Y, con
                                         int32_t S, const lte_awgn_desc* awgn, void* stream) {
     if (!p || !Y || !H || !idx_tx || !errors || !awgn || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
     return launch_mrc<true>(p, Y, H, nullptr, idx_tx, errors, window, nbits, B, R, S, awgn, stream);
+}
+
+// ------------------------------------------------------------------------------ compact sweep layout
+// LS estimate at the pilot positions only (core/lte_receiver.py:62-87 without the interpolation, which the
+// compact MRC kernel does per data bin): Yp [rows][nslot][Np] pilot bins of every slot's first symbol ->
+// Hp [rows][nslot][Np] = (Yp [+ lazy AWGN]) / pilot.  One thread per pilot.
+template <bool NOISY>
+__global__ void __launch_bounds__(256)
+crs_ls_compact_kernel(const DevPlan P, const float2* __restrict__ Yp, float2* __restrict__ Hp, int nslot, long long total,
+                      const AwgnArgs A) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const int i = (int)(g % P.Np);
+    const long long rs = g / P.Np;                  // row * nslot + slot
+    const int slot = (int)(rs % nslot);
+    const long long row = rs / nslot;
+    float2 yp = Yp[g];
+    if (NOISY) {
+        const float sigma = lte_sigma(A.power[row], A.n_stream, A.snr_lin[row]);
+        yp = awgn_at(A, sigma, row, slot * LTE_SLOT_SYMBOLS, P.N, P.pset_bin[i], yp);
+    }
+    Hp[g] = cmul(yp, P.pset_inv[i]);
+}
+
+extern "C" int lte_crs_ls_compact(const lte_plan* p, const lte_c32* Ypilot, lte_c32* Hp, int64_t rows, int32_t S,
+                                  const lte_awgn_desc* awgn, void* stream) {
+    if (!p || !Ypilot || !Hp || rows < 0 || S < 1) return LTE_ERR_INVALID_ARG;
+    if (p->dev.Np == 0 || p->nsets != 1) return LTE_ERR_UNSUPPORTED;
+    AwgnArgs A = {};
+    int rc;
+    if (awgn && (rc = make_awgn_args(A, p, awgn, S))) return rc;
+    if (rows == 0) return LTE_OK;
+    const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
+    const long long total = (long long)rows * nslot * p->dev.Np;
+    const long long grid = (total + 255) / 256;
+    if (grid >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
+    if (awgn)
+        crs_ls_compact_kernel<true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(p->dev, (const float2*)Ypilot,
+                                                                                      (float2*)Hp, nslot, total, A);
+    else
+        crs_ls_compact_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(p->dev, (const float2*)Ypilot,
+                                                                                       (float2*)Hp, nslot, total, A);
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}
+
+extern "C" int lte_mrc_demap_count_compact(const lte_plan* p, const lte_c32* Ydata, const lte_c32* Hp,
+                                           const uint8_t* idx_tx, unsigned long long* errors, int64_t nbits, int64_t B,
+                                           int32_t R, int32_t S, const lte_awgn_desc* awgn, void* stream) {
+    if (!p || !Ydata || !Hp || !idx_tx || !errors || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
+    return launch_mrc<true, true>(p, Ydata, Hp, nullptr, idx_tx, errors, LTE_WINDOW_USEFUL, nbits, B, R, S, awgn, stream);
 }

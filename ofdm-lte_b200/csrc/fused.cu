@@ -202,21 +202,19 @@ template <typename F> static int dispatch_n(int N, F&& f) {
     }
 }
 
-extern "C" int lte_channel_rx_fft(const lte_plan* p, const lte_channel_desc* ch, const lte_c32* tx,
-                                  const float* phases, lte_c32* Y, double* power, int window, int32_t B, int32_t R,
-                                  int32_t S, void* stream) {
-    if (!p || !ch || !tx || !phases || !Y || !power || B < 0 || R < 1 || R > LTE_MAX_RX || S < 1)
-        return LTE_ERR_INVALID_ARG;
+// Host-side checks and polynomial choice of lte_channel_rx_fft; shared with the workspace-size query.
+struct FusedSetup {
+    TdlParams C;
+    int K, halo, R2;
+    size_t ncoef, coef_bytes;
+};
+
+static int fused_setup(const lte_plan* p, const lte_channel_desc* ch, int32_t B, int32_t R, int32_t S, FusedSetup& U) {
+    if (!p || !ch || B < 0 || R < 1 || R > LTE_MAX_RX || S < 1) return LTE_ERR_INVALID_ARG;
     if (ch->num_taps < 0 || ch->num_taps > LTE_MAX_TAPS) return LTE_ERR_INVALID_ARG;
     if (ch->num_taps == 0) return LTE_ERR_UNSUPPORTED;          // identity link: lte_rx_fft with rx_div = R
-    int32_t k0, nk;
-    int rc = lte_plan_window(p, window, &k0, &nk);
-    if (rc) return rc;
-    if (B == 0) return LTE_OK;
-    cudaStream_t st = (cudaStream_t)stream;
     const int L = p->dev.L;
-
-    TdlParams C;
+    TdlParams& C = U.C;
     memset(&C, 0, sizeof(C));
     C.num_taps = ch->num_taps;
     int dmax = 0;
@@ -228,7 +226,7 @@ extern "C" int lte_channel_rx_fft(const lte_plan* p, const lte_channel_desc* ch,
         if (ch->delay[i] > dmax) dmax = ch->delay[i];
     }
     if (dmax > 144) return LTE_ERR_UNSUPPORTED;
-    const int halo = (dmax + 1) & ~1;
+    U.halo = (dmax + 1) & ~1;
     double wmax = 0.0;
     for (int nn = 0; nn < LTE_JAKES_TONES; ++nn) {
         C.w_cyc[nn] = ch->doppler_hz * cos(2.0 * M_PI * (double)(nn + 1) / LTE_JAKES_TONES) / p->desc.fs;
@@ -237,30 +235,47 @@ extern "C" int lte_channel_rx_fft(const lte_plan* p, const lte_channel_desc* ch,
     // one polynomial block per OFDM symbol; same truncation bounds as lte_channel_tdl
     const double x = M_PI * wmax * L;
     // K = 1 uses the economised linear fit (tdl.cuh): remainder x^2/4 <= 5e-7 of |h|
-    int K;
-    if (x <= 1.41e-3) K = 1;
-    else if (x <= 4.9e-3) K = 2;
-    else if (x <= 0.075) K = 4;
+    if (x <= 1.41e-3) U.K = 1;
+    else if (x <= 4.9e-3) U.K = 2;
+    else if (x <= 0.075) U.K = 4;
     else return LTE_ERR_UNSUPPORTED;
     C.pb = L;
     C.nbs = S;
     const long long total = (long long)B * S;
     if (total >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
+    U.R2 = (R + 1) & ~1;
+    const int NC = 2 * U.K + 1;
+    U.ncoef = (size_t)C.num_taps * NC * 2 * U.R2;
+    U.coef_bytes = sizeof(float) * (size_t)total * U.ncoef;
+    return LTE_OK;
+}
 
-    const int R2 = (R + 1) & ~1;
-    const int NC = 2 * K + 1;
-    const size_t ncoef = (size_t)C.num_taps * NC * 2 * R2;
-    const size_t coef_bytes = sizeof(float) * (size_t)total * ncoef;
-    lte_plan* pm = const_cast<lte_plan*>(p);
-    if (pm->scratch_bytes < coef_bytes) {
-        if (pm->scratch) LTE_CHECK_CUDA(cudaFree(pm->scratch));
-        pm->scratch = nullptr;
-        pm->scratch_bytes = 0;
-        LTE_CHECK_CUDA(cudaMalloc(&pm->scratch, coef_bytes));
-        pm->scratch_bytes = coef_bytes;
-    }
-    float* coef = (float*)pm->scratch;
-    if (R2 != R) LTE_CHECK_CUDA(cudaMemsetAsync(coef, 0, coef_bytes, st));
+extern "C" int64_t lte_channel_rx_fft_workspace_bytes(const lte_plan* p, const lte_channel_desc* ch, int32_t B,
+                                                      int32_t R, int32_t S) {
+    FusedSetup U;
+    const int rc = fused_setup(p, ch, B, R, S, U);
+    return rc ? (int64_t)rc : (int64_t)U.coef_bytes + 16;
+}
+
+extern "C" int lte_channel_rx_fft(const lte_plan* p, const lte_channel_desc* ch, const lte_c32* tx,
+                                  const float* phases, lte_c32* Y, double* power, void* workspace, int window,
+                                  int32_t B, int32_t R, int32_t S, void* stream) {
+    FusedSetup U;
+    int rc = fused_setup(p, ch, B, R, S, U);
+    if (rc) return rc;
+    if (!tx || !phases || !Y || !power || !workspace || ((uintptr_t)workspace & 15)) return LTE_ERR_INVALID_ARG;
+    int32_t k0, nk;
+    rc = lte_plan_window(p, window, &k0, &nk);
+    if (rc) return rc;
+    if (B == 0) return LTE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int L = p->dev.L;
+    const TdlParams& C = U.C;
+    const int K = U.K, halo = U.halo, R2 = U.R2;
+    const size_t ncoef = U.ncoef;
+    const long long total = (long long)B * S;
+    float* coef = (float*)workspace;
+    if (R2 != R) LTE_CHECK_CUDA(cudaMemsetAsync(coef, 0, U.coef_bytes, st));
     const long long items = total * R * C.num_taps;
     const unsigned cgrid = (unsigned)((items + 255) / 256);
     if (K == 1) jakes_coef_kernel<1><<<cgrid, 256, 0, st>>>(C, phases, coef, R, 1, R2, items);

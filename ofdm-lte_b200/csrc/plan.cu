@@ -16,7 +16,7 @@ int lte_set_cuda_error(cudaError_t e) {
     return LTE_ERR_CUDA;
 }
 
-extern "C" int lte_version(void) { return 130; }   // 1.3: + beamforming, coded chain, stage-level coding entry points
+extern "C" int lte_version(void) { return 200; }   // 2.0: caller-owned workspaces, spectral link, compact sweep layout
 
 extern "C" const char* lte_error_string(int code) {
     switch (code) {
@@ -54,8 +54,6 @@ extern "C" int lte_plan_create(const lte_plan_desc* d, const lte_c32* pilots_hos
     p->desc = *d;
     p->nsets = nsets;
     p->blob = nullptr;
-    p->scratch = nullptr;
-    p->scratch_bytes = 0;
     cudaGetDevice(&p->device);
 
     // --- bin classes (core/resource_mapper.py:57-74) -------------------------------
@@ -208,7 +206,6 @@ extern "C" int lte_plan_create(const lte_plan_desc* d, const lte_c32* pilots_hos
 extern "C" int lte_plan_destroy(lte_plan* p) {
     if (!p) return LTE_OK;
     if (p->blob) cudaFree(p->blob);
-    if (p->scratch) cudaFree(p->scratch);
     delete p;
     return LTE_OK;
 }

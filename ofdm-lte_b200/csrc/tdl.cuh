@@ -15,8 +15,7 @@ struct TdlParams {
     double w_cyc[LTE_JAKES_TONES];      // fD cos(alpha_n) / fs   [cycles per sample]
     int pb;                             // polynomial block length in samples (power of two)
     int pb_log2;
-    int debug;                          // LTE_TDL_DEBUG: 1 = skip the stores, 2 = skip the multiply-accumulates (profiling only)
-    int nbs;                            // polynomial blocks per stream = ceil(n / pb)
+    int nbs;                            // polynomial blocks per stream (every block a tile touches exists)
 };
 
 // Taylor coefficients of every (rx, tx, tap) fading process for every polynomial block, laid out

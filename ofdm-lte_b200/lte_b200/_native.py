@@ -64,14 +64,21 @@ _SIGS = {
     'lte_papr_symbols': ([_P, _P, _I32, _P, _P, _P, C.c_float, C.c_float, _I32, _I64, _I32, _P], C.c_int),
     'lte_histogram': ([_P, _I64, C.c_float, C.c_float, _I32, _P, _P], C.c_int),
     'lte_dft_m': ([_P, _P, _P, _I32, _I32, _I64, _P], C.c_int),
-    'lte_channel_tdl': ([_P, C.POINTER(ChannelDesc), _P, _P, _P, _P, _I32, _I32, _I32, _I64, _P], C.c_int),
-    'lte_channel_rx_fft': ([_P, C.POINTER(ChannelDesc), _P, _P, _P, _P, C.c_int, _I32, _I32, _I32, _P], C.c_int),
+    'lte_channel_tdl_workspace_bytes': ([_P, C.POINTER(ChannelDesc), _I32, _I32, _I32, _I64], C.c_int64),
+    'lte_channel_tdl': ([_P, C.POINTER(ChannelDesc), _P, _P, _P, _P, _P, _I32, _I32, _I32, _I64, _P], C.c_int),
+    'lte_channel_rx_fft_workspace_bytes': ([_P, C.POINTER(ChannelDesc), _I32, _I32, _I32], C.c_int64),
+    'lte_channel_rx_fft': ([_P, C.POINTER(ChannelDesc), _P, _P, _P, _P, _P, C.c_int, _I32, _I32, _I32, _P], C.c_int),
+    'lte_tx_spectral': ([_P, _P, _P, _P, _I32, _I32, _P], C.c_int),
+    'lte_channel_spectral_workspace_bytes': ([_P, C.POINTER(ChannelDesc), _I32, _I32, _I32], C.c_int64),
+    'lte_channel_spectral': ([_P, C.POINTER(ChannelDesc), _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P], C.c_int),
     'lte_awgn_add': ([_P, _P, _I32, _P, _P, _P, _U64, _U64, _P, _I64, _I64, _P], C.c_int),
     'lte_rx_fft': ([_P, _P, _I32, _P, _P, _P, _I32, _U64, _U64, _P, C.c_int, _I64, _I32, _P], C.c_int),
     'lte_crs_ls_interp': ([_P, _P, _P, C.c_int, C.c_int, _I64, _I32, _P], C.c_int),
     'lte_crs_ls_interp_awgn': ([_P, _P, _P, C.c_int, C.c_int, _I64, _I32, C.POINTER(AwgnDesc), _P], C.c_int),
     'lte_mrc_demap_count_awgn': ([_P, _P, _P, _P, _P, C.c_int, _I64, _I64, _I32, _I32, C.POINTER(AwgnDesc), _P],
                                  C.c_int),
+    'lte_crs_ls_compact': ([_P, _P, _P, _I64, _I32, C.POINTER(AwgnDesc), _P], C.c_int),
+    'lte_mrc_demap_count_compact': ([_P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, C.POINTER(AwgnDesc), _P], C.c_int),
     'lte_equalize_zf': ([_P, _P, _P, _P, C.c_int, _I64, _I32, _P], C.c_int),
     'lte_equalize_mrc': ([_P, _P, _P, _P, C.c_int, _I64, _I32, _I32, _P], C.c_int),
     'lte_sfbc_encode': ([_P, _P, _P, _P, _P, _I64, _I32, _P], C.c_int),

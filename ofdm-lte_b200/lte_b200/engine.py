@@ -9,6 +9,7 @@ Shapes (B streams, S OFDM symbols per stream, L = N + cp, R/T antennas):
     errors   int64      [B]
 """
 import ctypes as C
+import functools
 
 import numpy as np
 import torch
@@ -73,6 +74,16 @@ class LinkEngine:
     # ------------------------------------------------------------------ helpers
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _scratch(self, nbytes):
+        """Caller-owned workspace for the C ABI (the library never allocates): one cached buffer per CUDA
+        stream of this engine, grown on demand, 256-byte aligned by the torch allocator."""
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        pool = self.__dict__.setdefault('_scratch_pool', {})
+        buf = pool.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = pool[key] = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+        return buf
 
     def window(self, window):
         return (0, self.N) if window == nat.WINDOW_FULL else ((0, self.Nc) if self.simple else (self.gl, self.Nc))
@@ -213,8 +224,12 @@ class LinkEngine:
             faded = out if out is not None else self._empty((B, R, n), torch.complex64)
             if phases is None:
                 raise ValueError("phases are required for a fading channel")
+        need = nat.lib.lte_channel_tdl_workspace_bytes(self._plan, C.byref(chan), B, R, T, n)
+        if need < 0:
+            nat.check(int(need), 'lte_channel_tdl_workspace_bytes')
+        work = self._scratch(need) if need > 0 else None
         nat.check(nat.lib.lte_channel_tdl(self._plan, C.byref(chan), _ptr(tx), _ptr(phases), _ptr(faded),
-                                          _ptr(power), B, R, T, n, self._stream()), 'lte_channel_tdl')
+                                          _ptr(power), _ptr(work), B, R, T, n, self._stream()), 'lte_channel_tdl')
         self.launches += 2 if chan.num_taps > 0 else 1     # Jakes coefficient kernel + TDL kernel
         return faded, power
 
@@ -222,18 +237,73 @@ class LinkEngine:
         """Fused fading channel + CP strip + FFT (T = 1): -> (Y [B*R, S, nk] noise-free, power [B, R]),
         or None when the configuration needs the staged `channel` + `rx_fft` pair."""
         k0, nk = self.window(window)
+        need = nat.lib.lte_channel_rx_fft_workspace_bytes(self._plan, C.byref(chan), B, R, S)
+        if need == nat.LTE_ERR_UNSUPPORTED:
+            return None
+        if need < 0:
+            nat.check(int(need), 'lte_channel_rx_fft_workspace_bytes')
+        work = self._scratch(need)
         if power is None:
             power = torch.zeros((B, R), dtype=torch.float64, device=self.device)
         else:
             power.zero_()
         Y = out if out is not None else self._empty((B * R, S, nk), torch.complex64)
         rc = nat.lib.lte_channel_rx_fft(self._plan, C.byref(chan), _ptr(tx), _ptr(phases), _ptr(Y), _ptr(power),
-                                        window, B, R, S, self._stream())
-        if rc == nat.LTE_ERR_UNSUPPORTED:
-            return None
+                                        _ptr(work), window, B, R, S, self._stream())
         nat.check(rc, 'lte_channel_rx_fft')
         self.launches += 2                                   # Jakes coefficient kernel + fused kernel
         return Y, power
+
+    # ------------------------------------------------------------------ spectral fading link
+    def tx_spectral(self, S, idx, out_G=None, out_tail=None):
+        """TX side of the spectral link (csrc/spectral.cu): idx [B, S*Nd] ->
+        (G [B*S, Nc] ramp-weighted spectrum on the occupied window, tail [B*S, cp] symbol tails)."""
+        B = idx.shape[0]
+        k0, nk = self.window(nat.WINDOW_USEFUL)
+        G = out_G if out_G is not None else self._empty((B * S, nk), torch.complex64)
+        tail = out_tail if out_tail is not None else self._empty((B * S, self.cp), torch.complex64)
+        nat.check(nat.lib.lte_tx_spectral(self._plan, _ptr(idx), _ptr(G), _ptr(tail), B, S, self._stream()),
+                  'lte_tx_spectral')
+        self.launches += 1
+        return G, tail
+
+    def spectral_workspace_bytes(self, chan, B, R, S):
+        """Bytes of caller-owned scratch lte_channel_spectral needs, or None when the configuration is
+        outside the spectral link's validity range (Doppler, delay spread, identity link)."""
+        n = nat.lib.lte_channel_spectral_workspace_bytes(self._plan, C.byref(chan), B, R, S)
+        if n == nat.LTE_ERR_UNSUPPORTED:
+            return None
+        if n < 0:
+            nat.check(int(n), 'lte_channel_spectral_workspace_bytes')
+        return int(n)
+
+    def channel_spectral(self, idx, G, tail, chan, B, R, S, phases, out=None, power=None, workspace=None,
+                         compact=False, out_pilots=None):
+        """Channel side of the spectral link: -> (Y [B*R, S, Nc] noise-free on the occupied window,
+        power [B, R]), or None when unsupported (use modulate + channel_rx_fft).
+        compact: -> ((Yd [B*R, S, Nd] data bins, Yp [B*R, slots, Np] slot-head pilot bins), power)."""
+        need = self.spectral_workspace_bytes(chan, B, R, S)
+        if need is None:
+            return None
+        if workspace is None or workspace.numel() * workspace.element_size() < need:
+            workspace = self._scratch(need)
+        k0, nk = self.window(nat.WINDOW_USEFUL)
+        if power is None:
+            power = torch.zeros((B, R), dtype=torch.float64, device=self.device)
+        else:
+            power.zero_()
+        Yp = None
+        if compact:
+            nslot = -(-S // nat.LTE_SLOT_SYMBOLS)
+            Y = out if out is not None else self._empty((B * R, S, self.Nd), torch.complex64)
+            Yp = out_pilots if out_pilots is not None else self._empty((B * R, nslot, self.Np), torch.complex64)
+        else:
+            Y = out if out is not None else self._empty((B * R, S, nk), torch.complex64)
+        nat.check(nat.lib.lte_channel_spectral(self._plan, C.byref(chan), _ptr(idx), _ptr(G), _ptr(tail),
+                                               _ptr(phases), _ptr(Y), _ptr(Yp), _ptr(power), _ptr(workspace), B, R, S,
+                                               self._stream()), 'lte_channel_spectral')
+        self.launches += 2                                   # Jakes coefficient kernel + channel kernel
+        return ((Y, Yp) if compact else Y), power
 
     def awgn(self, x, x_div, power, snr_lin, rows, z=None, seed=0, row_id0=0, out=None):
         n = x.shape[-1]
@@ -274,6 +344,16 @@ class LinkEngine:
                                                      C.byref(awgn), self._stream()), 'lte_crs_ls_interp_awgn')
         self.launches += 1
         return H
+
+    def estimate_compact(self, Yp, rows, S, out=None, awgn=None):
+        """LS estimate at the pilot positions of the compact layout: Yp [rows, slots, Np] -> Hp, same shape
+        (awgn: lazy frequency-domain AWGN, the draws of `estimate(..., awgn=...)`)."""
+        Hp = out if out is not None else torch.empty_like(Yp)
+        nat.check(nat.lib.lte_crs_ls_compact(self._plan, _ptr(Yp), _ptr(Hp), rows, S,
+                                             C.byref(awgn) if awgn is not None else None, self._stream()),
+                  'lte_crs_ls_compact')
+        self.launches += 1
+        return Hp
 
     # ------------------------------------------------------------------ stage 5
     def zf(self, Y, H, B, S, window=nat.WINDOW_FULL, out=None):
@@ -612,29 +692,61 @@ class LinkEngine:
         self.launches += 1
         return errors
 
+    def mrc_demap_count_compact(self, Yd, Hp, idx_tx, B, R, S, nbits=None, errors=None, awgn=None):
+        """MRC + slicer + bit-error count on the compact layout (Yd [B*R, S, Nd], Hp [B*R, slots, Np]): every
+        thread interpolates its own bin between its two pilots; counts are bit-identical to
+        estimate + mrc_demap_count on the windowed layout."""
+        if errors is None:
+            errors = torch.zeros(B, dtype=torch.int64, device=self.device)
+        else:
+            errors.zero_()
+        nb = int(nbits) if nbits is not None else S * self.Nd * self.bps
+        nat.check(nat.lib.lte_mrc_demap_count_compact(self._plan, _ptr(Yd), _ptr(Hp), _ptr(idx_tx), _ptr(errors), nb, B,
+                                                      R, S, C.byref(awgn) if awgn is not None else None,
+                                                      self._stream()), 'lte_mrc_demap_count_compact')
+        self.launches += 1
+        return errors
+
     # ------------------------------------------------------------------ batched SIMO chain
-    def workspace(self, B, S, R, fading, fused=False):
+    def workspace(self, B, S, R, fading, fused=False, lazy=False):
         """Pre-allocated HBM buffers for `simo_ber` so a sweep re-uses them every step
-        (fused: no buffer for the faded streams)."""
+        (fused: no buffer for the faded streams; lazy: the time-domain stream and the windowed grid are only
+        allocated if a step actually takes the fused / staged path -- the spectral link needs neither)."""
         k0, nk = self.window(nat.WINDOW_USEFUL)
         nslot = -(-S // nat.LTE_SLOT_SYMBOLS)
         n = S * self.L
         ws = dict(B=B, S=S, R=R,
                   idx=self._empty((B, S * self.Nd), torch.uint8),
-                  tx=self._empty((B, n), torch.complex64),
                   stats=torch.zeros((B, 2), dtype=torch.float64, device=self.device),
                   power=torch.zeros((B, R), dtype=torch.float64, device=self.device),
-                  Y=self._empty((B * R, S, nk), torch.complex64),
-                  H=self._empty((B * R, nslot, nk), torch.complex64),
                   errors=torch.zeros(B, dtype=torch.int64, device=self.device))
+        if not lazy:
+            ws.update(tx=self._empty((B, n), torch.complex64), Y=self._empty((B * R, S, nk), torch.complex64),
+                      H=self._empty((B * R, nslot, nk), torch.complex64))
         if fading:
             if not fused:
                 ws['faded'] = self._empty((B, R, n), torch.complex64)
             ws['phases'] = self._empty((B, R * nat.LTE_MAX_TAPS * nat.LTE_JAKES_TONES), torch.float32)
         return ws
 
+    def _spectral_buffers(self, ws, chan):
+        """Lazily adds the spectral link's buffers to a workspace; False when the link is unsupported."""
+        if 'spectral' not in ws:
+            B, S, R = ws['B'], ws['S'], ws['R']
+            ok = self.Np > 0 and self.num_pilot_sets == 1 and self.spectral_workspace_bytes(chan, B, R, S) is not None
+            ws['spectral'] = ok
+            if ok:
+                k0, nk = self.window(nat.WINDOW_USEFUL)
+                nslot = -(-S // nat.LTE_SLOT_SYMBOLS)
+                ws['G'] = self._empty((B * S, nk), torch.complex64)
+                ws['tail'] = self._empty((B * S, self.cp), torch.complex64)
+                ws['Yd'] = self._empty((B * R, S, self.Nd), torch.complex64)
+                ws['Yp'] = self._empty((B * R, nslot, self.Np), torch.complex64)
+                ws['Hp'] = self._empty((B * R, nslot, self.Np), torch.complex64)
+        return ws['spectral']
+
     def simo_ber(self, ws, chan, snr_lin_rows, seed, stream_id0=0, idx=None, nbits=None, noise_domain=1,
-                 fused=False):
+                 fused=False, spectral=None):
         """One pass of the SIMO-MRC link chain over B independent streams.
 
         ws: workspace(); snr_lin_rows: float32 [B*R] linear SNR per (stream, antenna);
@@ -645,11 +757,31 @@ class LinkEngine:
         (statistically identical, 1/R of the generator work).  fused: fading channel + RX FFT in
         one kernel (the faded streams are never written; needs noise_domain 2 or 3 -- 1 is promoted
         to 2; falls back to the staged kernels when lte_channel_rx_fft reports the configuration
-        unsupported).
+        unsupported).  spectral (default: same as fused): at low Doppler use the spectral link
+        (lte_tx_spectral + lte_channel_spectral, compact grid) instead of the fused time-domain kernel;
+        silently falls back to `fused` outside its validity range.
         """
         B, S, R = ws['B'], ws['S'], ws['R']
         if idx is None:
             idx = self.random_indices(B, S, seed, stream_id0, out=ws['idx'])
+        if spectral is None:
+            spectral = fused
+        if spectral and chan.num_taps > 0 and self._spectral_buffers(ws, chan):
+            # low Doppler: the spectral link (csrc/spectral.cu) -- no time-domain stream, one forward transform
+            # per OFDM symbol, compact grid; the lazy AWGN draws are those of the other paths
+            per = R * chan.num_taps * nat.LTE_JAKES_TONES
+            ph = self.random_phases(B, per, seed, stream_id0, out=ws['phases'].view(-1)[:B * per].view(B, per))
+            G, tail = self.tx_spectral(S, idx, out_G=ws['G'], out_tail=ws['tail'])
+            (Yd, Yp), power = self.channel_spectral(idx, G, tail, chan, B, R, S, ph, out=ws['Yd'], power=ws['power'],
+                                                    compact=True, out_pilots=ws['Yp'])
+            awgn = self.awgn_desc(power, snr_lin_rows, seed, stream_id0 * R, combine=(noise_domain == 3))
+            Hp = self.estimate_compact(Yp, B * R, S, out=ws['Hp'], awgn=awgn)
+            return self.mrc_demap_count_compact(Yd, Hp, idx, B, R, S, nbits=nbits, errors=ws['errors'], awgn=awgn)
+        if 'tx' not in ws:
+            ws['tx'] = self._empty((B, S * self.L), torch.complex64)
+            k0, nk = self.window(nat.WINDOW_USEFUL)
+            ws['Y'] = self._empty((B * R, S, nk), torch.complex64)
+            ws['H'] = self._empty((B * R, -(-S // nat.LTE_SLOT_SYMBOLS), nk), torch.complex64)
         tx, _, _ = self.modulate(S, idx=idx, want_stats=False, out=ws['tx'])
         if fused and chan.num_taps > 0:
             per = R * chan.num_taps * nat.LTE_JAKES_TONES
@@ -680,3 +812,21 @@ class LinkEngine:
                         row_id0=stream_id0 * R, out=ws['Y'], noise_domain=noise_domain)
         H = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, out=ws['H'])
         return self.mrc_demap_count(Y, H, idx, B, R, S, nbits=nbits, errors=ws['errors'])
+
+
+def _on_own_device(fn):
+    """Every native call runs with the engine's device current: streams, workspaces and the SM-count queries
+    of the launchers belong to it (an engine on cuda:1 may be driven from a process whose current device is 0)."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *a, **k)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapped
+
+
+for _name, _fn in list(vars(LinkEngine).items()):
+    if not _name.startswith('_') and not isinstance(_fn, (staticmethod, classmethod, property)) and callable(_fn) \
+            and _name not in ('window', 'symbols_for_bits'):
+        setattr(LinkEngine, _name, _on_own_device(_fn))

@@ -1,0 +1,162 @@
+"""Spectral fading link (lte_tx_spectral + lte_channel_spectral): checked against the oracle's
+sample-by-sample path, against the fp64 restatement of its own algebra (tests/spectral_ref.py), against the
+fused time-domain kernel it stands in for, and through the error counts of the sweep built on it."""
+import numpy as np
+import pytest
+import torch
+
+import spectral_ref as SR
+from gpu_chain import to_dev
+from helpers import rel_err
+from oracle import lte_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(20.0, '64-QAM', 'Pedestrian_A', 4, 14, 3.0), (5.0, 'QPSK', 'Pedestrian_A', 2, 15, 3.0),
+         (1.25, '16-QAM', 'Pedestrian_B', 3, 5, 3.0), (10.0, '16-QAM', 'Vehicular_A', 1, 3, 3.0),
+         (2.5, '64-QAM', 'Vehicular_B', 8, 2, 2.0), (20.0, '16-QAM', 'Bad_Urban', 5, 2, 1.0)]
+
+
+def _setup(bw, mod, prof, R, S, v, B=2, seed=5):
+    from lte_b200 import LinkEngine, chan_for
+    num = O.Numerology(bw, 15.0, mod)
+    eng = LinkEngine(num.N, num.Nc, num.cp_length, num.bits_per_symbol, num.fs)
+    rs = np.random.RandomState(seed)
+    nbits = eng.Nd * eng.bps * S
+    bits = rs.randint(0, 2, (B, nbits))
+    idx = eng.bits_to_indices(to_dev(bits.astype(np.uint8), torch.uint8), nbits, S)
+    chan = chan_for('rayleigh_mp', num.fs, prof, 2.0, v)
+    d, g = O.itu_taps(prof, num.fs)
+    ph = 2 * np.pi * rs.rand(B, R, len(d), 16)
+    return num, eng, bits, idx, chan, d, g, ph
+
+
+@pytest.mark.parametrize('bw,mod,prof,R,S,v', CASES)
+def test_spectral_grid_and_power_match_oracle(bw, mod, prof, R, S, v):
+    from lte_b200 import _native as nat
+    num, eng, bits, idx, chan, d, g, ph = _setup(bw, mod, prof, R, S, v)
+    B = bits.shape[0]
+    G, tail = eng.tx_spectral(S, idx)
+    u = to_dev(ph / (2 * np.pi), torch.float32)
+    got = eng.channel_spectral(idx, G, tail, chan, B, R, S, u)
+    assert got is not None
+    Y, power = got
+    Yn, pw = Y.cpu().numpy().reshape(B, R, S, -1), power.cpu().numpy()
+    k0, nk = eng.window(nat.WINDOW_USEFUL)
+    kept = np.arange(k0, k0 + nk)
+    fD = O.doppler_hz(2.0, v)
+    Gn, tn = G.cpu().numpy().reshape(B, S, nk), tail.cpu().numpy().reshape(B, S, -1)
+    for b in range(B):
+        sig, _ = O.modulate_stream(bits[b], num)
+        x = sig.reshape(S, num.L)
+        # TX side: symbol tails and the ramp-weighted spectrum
+        assert rel_err(tn[b], x[:, num.N:]) < 2e-6
+        nc = 0.5 * (num.L - 1) - num.cp_length
+        Gw = np.fft.fft((np.arange(num.N) - nc)[None, :] * x[:, num.cp_length:], axis=-1) / np.sqrt(num.N)
+        assert rel_err(Gn[b], Gw[:, kept]) < 2e-6
+        # channel side vs the oracle's time-domain path (budget 1e-5) and vs its own algebra in fp64 (tighter)
+        Yt, Pt = SR.time_domain_rx(sig, num, fD, list(d), g, ph[b])
+        Ys, Ps = SR.spectral_rx(sig, num, fD, list(d), g, ph[b], kept)
+        for r in range(R):
+            assert rel_err(Yn[b, r], Yt[r][:, kept]) < 1e-5
+            assert rel_err(Yn[b, r], Ys[r][:, kept]) < 2e-6
+            assert abs(pw[b, r] / Pt[r] - 1) < 1e-5
+            assert abs(pw[b, r] / Ps[r] - 1) < 2e-6
+        assert np.abs(Yn[b] - Yt[:, :, kept]).max() / np.abs(Yt[:, :, kept]).max() < 1e-5
+
+
+@pytest.mark.parametrize('bw,mod,prof,R,S,v', CASES[:4])
+def test_spectral_matches_fused_time_domain_kernel(bw, mod, prof, R, S, v):
+    from lte_b200 import _native as nat
+    num, eng, bits, idx, chan, d, g, ph = _setup(bw, mod, prof, R, S, v, B=3)
+    B = bits.shape[0]
+    u = to_dev(ph / (2 * np.pi), torch.float32)
+    G, tail = eng.tx_spectral(S, idx)
+    Y, power = eng.channel_spectral(idx, G, tail, chan, B, R, S, u)
+    tx, _, _ = eng.modulate(S, idx=idx, want_stats=False)
+    Yf, pf = eng.channel_rx_fft(tx, chan, B, R, S, u, nat.WINDOW_USEFUL)
+    assert rel_err(Y.cpu().numpy(), Yf.cpu().numpy()) < 2e-6
+    assert np.allclose(power.cpu().numpy(), pf.cpu().numpy(), rtol=2e-6)
+
+
+@pytest.mark.parametrize('bw,mod,prof,R,S,v', [CASES[0], CASES[1], (5.0, '16-QAM', 'Pedestrian_A', 3, 29, 3.0)])
+def test_compact_layout_is_a_gather_of_the_window(bw, mod, prof, R, S, v):
+    """COMPACT output = data bins in data-symbol order + the pilot bins of every slot's first symbol."""
+    from lte_b200 import _native as nat
+    num, eng, bits, idx, chan, d, g, ph = _setup(bw, mod, prof, R, S, v, B=3)
+    B = bits.shape[0]
+    u = to_dev(ph / (2 * np.pi), torch.float32)
+    G, tail = eng.tx_spectral(S, idx)
+    Y, power = eng.channel_spectral(idx, G, tail, chan, B, R, S, u)
+    (Yd, Yp), power_c = eng.channel_spectral(idx, G, tail, chan, B, R, S, u, compact=True)
+    k0, nk = eng.window(nat.WINDOW_USEFUL)
+    di = torch.as_tensor(eng.data_idx - k0, device='cuda')
+    pi = torch.as_tensor(eng.pilot_idx - k0, device='cuda')
+    assert torch.equal(Yd, Y[:, :, di])
+    assert torch.equal(Yp, Y[:, ::14, :][:, :, pi])
+    assert torch.equal(power, power_c)
+
+
+@pytest.mark.parametrize('combine', [False, True])
+@pytest.mark.parametrize('bw,mod,prof,R,S,v', [CASES[0], (5.0, '16-QAM', 'Pedestrian_A', 3, 29, 3.0)])
+def test_compact_consumers_count_exactly_like_the_windowed_ones(bw, mod, prof, R, S, v, combine):
+    """lte_crs_ls_compact + lte_mrc_demap_count_compact vs lte_crs_ls_interp_awgn + lte_mrc_demap_count_awgn on the
+    same noise-free grid and the same lazy AWGN draws: per-stream error counts must be identical."""
+    from lte_b200 import _native as nat
+    num, eng, bits, idx, chan, d, g, ph = _setup(bw, mod, prof, R, S, v, B=6)
+    B = bits.shape[0]
+    u = to_dev(ph / (2 * np.pi), torch.float32)
+    G, tail = eng.tx_spectral(S, idx)
+    Y, power = eng.channel_spectral(idx, G, tail, chan, B, R, S, u)
+    (Yd, Yp), _ = eng.channel_spectral(idx, G, tail, chan, B, R, S, u, compact=True)
+    snr = torch.tensor([10 ** (x / 10) for x in (2.0, 8.0, 14.0, 20.0, 26.0, 40.0)], dtype=torch.float32, device='cuda')
+    rows = snr.repeat_interleave(R).contiguous()
+    nbits = S * eng.Nd * eng.bps - 5
+    for awgn in (None, eng.awgn_desc(power, rows, 9, 77, combine=combine)):
+        H = eng.estimate(Y, B * R, S, nat.WINDOW_USEFUL, awgn=awgn)
+        want = eng.mrc_demap_count(Y, H, idx, B, R, S, nbits=nbits, awgn=awgn).clone()
+        Hp = eng.estimate_compact(Yp, B * R, S, awgn=awgn)
+        got = eng.mrc_demap_count_compact(Yd, Hp, idx, B, R, S, nbits=nbits, awgn=awgn)
+        assert torch.equal(got, want)
+        if awgn is not None:
+            assert int(want.sum()) > 0
+        k0, nk = eng.window(nat.WINDOW_USEFUL)
+        pi = torch.as_tensor(eng.pilot_idx - k0, device='cuda')
+        assert torch.equal(Hp, H[:, :, pi])
+
+
+@pytest.mark.parametrize('bw,mod,R,prof', [(1.25, '16-QAM', 2, 'Pedestrian_A'), (5.0, '64-QAM', 4, 'Vehicular_A'),
+                                           (2.5, 'QPSK', 1, 'Pedestrian_B'), (20.0, '64-QAM', 4, 'Pedestrian_A')])
+def test_spectral_sweep_counts_track_the_fused_path(bw, mod, R, prof):
+    """Same draws, same fading polynomial, different evaluation (bin by bin instead of sample by sample): per-stream
+    error counts may differ only through symbols that sit on a slicer boundary."""
+    from config import LTEConfig
+    from lte_b200 import LinkEngine, chan_for
+    cfg = LTEConfig(bw, 15.0, mod)
+    eng = LinkEngine.from_config(cfg)
+    chan = chan_for('rayleigh_mp', cfg.fs, prof, 2.0, 3.0)
+    B, S = 12, 15
+    wf = eng.workspace(B, S, R, fading=True, fused=True)
+    wsp = eng.workspace(B, S, R, fading=True, fused=True, lazy=True)
+    snr = torch.tensor([10 ** (s / 10) for s in (4.0, 12.0, 22.0)], dtype=torch.float32, device='cuda')
+    rows = snr.repeat(B // 3).repeat_interleave(R).contiguous()
+    for nd in (2, 3):
+        e_fused = eng.simo_ber(wf, chan, rows, seed=4, stream_id0=11, fused=True, spectral=False, noise_domain=nd).clone()
+        e_spec = eng.simo_ber(wsp, chan, rows, seed=4, stream_id0=11, fused=True, noise_domain=nd).clone()
+        assert wsp['spectral'] and 'tx' not in wsp                  # the spectral link really ran
+        bits = S * eng.Nd * eng.bps
+        assert int(e_fused.sum()) > 0
+        assert int((e_fused - e_spec).abs().max()) <= max(2, bits // 20000)
+        assert abs(int(e_fused.sum()) - int(e_spec.sum())) <= max(3, int(e_fused.sum()) // 2000)
+
+
+def test_spectral_reports_unsupported():
+    from lte_b200 import chan_for
+    num, eng, bits, idx, chan, d, g, ph = _setup(5.0, 'QPSK', 'Pedestrian_A', 2, 2, 3.0)
+    assert eng.spectral_workspace_bytes(chan_for('awgn', num.fs), 2, 2, 2) is None
+    assert eng.spectral_workspace_bytes(chan_for('rayleigh_mp', num.fs, 'Pedestrian_A', 2.0, 30.0), 2, 2, 2) is None
+    assert eng.spectral_workspace_bytes(chan_for('rayleigh_mp', num.fs, 'Pedestrian_A', 2.0, 3.0), 2, 2, 2) > 0
+    num2 = O.Numerology(1.25, 15.0, 'QPSK')                    # Vehicular_B at 1.92 MHz: 8.7 samples... fits; Bad_Urban too
+    from lte_b200 import LinkEngine
+    eng2 = LinkEngine(num2.N, num2.Nc, 4, 2, num2.fs)           # a 4-sample prefix cannot hold Vehicular_B's delay spread
+    assert eng2.spectral_workspace_bytes(chan_for('rayleigh_mp', num2.fs, 'Vehicular_B', 2.0, 1.0), 1, 1, 1) is None
