@@ -36,6 +36,11 @@ struct DevPlan {
     const int16_t* pset_seg;        // [nsets][N]   index of the owned pilot at or left of bin k, -1 before the first
     const int* pset_cnt;            // [nsets]
     const float2* twiddle;          // [N] exp(-2 pi i m / N)
+    // bin pairs of the spectral link / compact sweep layout (spectral.cu): every bin of the occupied window
+    // exactly once, as ndp pairs of consecutive DATA symbols, then npp pairs of consecutive pilots, then the
+    // window's remaining null bins; -1 pads an odd count
+    const int16_t* pair_bin;        // [npairs][2]
+    int ndp, npp, npairs;
     float lev[8];                   // constellation axis levels in index order
     float thr[7];                   // slicer thresholds, rounded towards -inf
     int nlev;                       // 2, 4, 8

@@ -136,6 +136,27 @@ extern "C" int lte_plan_create(const lte_plan_desc* d, const lte_c32* pilots_hos
         }
     }
 
+    // --- bin pairs of the compact sweep layout --------------------------------------------
+    std::vector<int16_t> pair_bin;
+    int ndp, npp;
+    {
+        std::vector<int> nulls;                                   // null bins inside the occupied window (DC)
+        for (int k = k0; k < k0 + nk; ++k)
+            if (bin_map[k] == BIN_NULL) nulls.push_back(k);
+        size_t nu = 0;
+        auto pad = [&]() {
+            if (pair_bin.size() & 1) pair_bin.push_back(nu < nulls.size() ? (int16_t)nulls[nu++] : (int16_t)-1);
+        };
+        for (int i = 0; i < Nd; ++i) pair_bin.push_back((int16_t)p->data_idx_h[i]);
+        pad();
+        ndp = (int)pair_bin.size() / 2;
+        for (int i = 0; i < Np; ++i) pair_bin.push_back((int16_t)p->pilot_idx_h[i]);
+        pad();
+        npp = (int)pair_bin.size() / 2 - ndp;
+        while (nu < nulls.size()) pair_bin.push_back((int16_t)nulls[nu++]);
+        pad();
+    }
+
     // --- single device blob -------------------------------------------------------------
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t off_bin = 0;
@@ -147,7 +168,8 @@ extern "C" int lte_plan_create(const lte_plan_desc* d, const lte_c32* pilots_hos
     size_t off_pseg = align(off_pinv + sizeof(float2) * pset_inv.size());
     size_t off_pcnt = align(off_pseg + sizeof(int16_t) * pset_seg.size());
     size_t off_tw = align(off_pcnt + sizeof(int) * nsets);
-    size_t total = align(off_tw + sizeof(float2) * tw.size());
+    size_t off_pair = align(off_tw + sizeof(float2) * tw.size());
+    size_t total = align(off_pair + sizeof(int16_t) * pair_bin.size());
     std::vector<char> host(total, 0);
     std::vector<int16_t> didx16(Nd ? Nd : 1, 0);
     for (int i = 0; i < Nd; ++i) didx16[i] = (int16_t)p->data_idx_h[i];
@@ -162,6 +184,7 @@ extern "C" int lte_plan_create(const lte_plan_desc* d, const lte_c32* pilots_hos
     memcpy(&host[off_pseg], pset_seg.data(), sizeof(int16_t) * pset_seg.size());
     memcpy(&host[off_pcnt], pset_cnt.data(), sizeof(int) * nsets);
     memcpy(&host[off_tw], tw.data(), sizeof(float2) * tw.size());
+    memcpy(&host[off_pair], pair_bin.data(), sizeof(int16_t) * pair_bin.size());
     if (cudaMalloc(&p->blob, total) != cudaSuccess ||
         cudaMemcpy(p->blob, host.data(), total, cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaError_t e = cudaGetLastError();
@@ -183,6 +206,8 @@ extern "C" int lte_plan_create(const lte_plan_desc* d, const lte_c32* pilots_hos
     D.pset_seg = (const int16_t*)(b + off_pseg);
     D.pset_cnt = (const int*)(b + off_pcnt);
     D.twiddle = (const float2*)(b + off_tw);
+    D.pair_bin = (const int16_t*)(b + off_pair);
+    D.ndp = ndp; D.npp = npp; D.npairs = (int)pair_bin.size() / 2;
     D.inv_sqrt_n = (float)(1.0 / sqrt((double)N));
 
     // --- constellation axis levels and slicer thresholds (core/modulator.py:28-59) -----
@@ -212,6 +237,13 @@ extern "C" int lte_plan_destroy(lte_plan* p) {
 
 extern "C" int lte_plan_num_data(const lte_plan* p) { return p ? p->dev.Nd : LTE_ERR_INVALID_ARG; }
 extern "C" int lte_plan_num_pilots(const lte_plan* p) { return p ? p->dev.Np : LTE_ERR_INVALID_ARG; }
+
+extern "C" int lte_plan_compact_shape(const lte_plan* p, int32_t* ndp, int32_t* npp) {
+    if (!p || !ndp || !npp) return LTE_ERR_INVALID_ARG;
+    *ndp = p->dev.ndp;
+    *npp = p->dev.npp;
+    return LTE_OK;
+}
 
 extern "C" int lte_plan_indices_host(const lte_plan* p, int32_t* data_idx, int32_t* pilot_idx) {
     if (!p) return LTE_ERR_INVALID_ARG;

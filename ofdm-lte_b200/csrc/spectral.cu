@@ -142,12 +142,12 @@ struct SpecParams {
     int dmax;
 };
 
-#define SPEC_MAX_THREADS 608
-#define SPEC_XMAX 352               // staged time samples per symbol: dmax + cp <= 160 + 192
-#define SPEC_GMAX 1216              // window bins staged per symbol (2 per thread)
+#define SPEC_MAX_WARPS 19           // warps per CTA: ceil(600 bin pairs / 32) at 20 MHz
+#define SPEC_DMAX 160               // longest supported delay spread in samples
 
 // Linear Jakes fit per (OFDM symbol, antenna, tap) in the layout the channel kernel stages verbatim:
-//   coef[f][sorted tap][slot][re|im][R2],  slot 0: a = c0 + d c1,  1: c1,  2: c0
+//   coef[f] = { [sorted tap][R2] (a.re, a.im, c1.re, c1.im) | [sorted tap][R2] (c0.re, c0.im) },  a = c0 + d c1
+// (one 128-bit shared-memory load per (tap, antenna) in the bin loop; c0 only enters the CP samples)
 // c0 / c1 are the economised K = 1 coefficients of jakes_coef_kernel<1> (tdl.cuh): fp64 phase reduction at the
 // symbol centre, c0 = g sum_n e^{j theta_n} (1 - X_n^2 / 4), c1 = g sum_n e^{j theta_n} j x_n.
 __global__ void __launch_bounds__(256)
@@ -188,13 +188,9 @@ spectral_coef_kernel(const SpecParams C, const float* __restrict__ phases, float
     const int ts = C.pos[tap];
     const float d = (float)C.delay[ts];
     a0.x *= g; a0.y *= g; a1.x *= g; a1.y *= g;
-    float* c = coef + ((size_t)f * C.num_taps + ts) * 6 * R2 + r;
-    c[0 * R2] = fmaf(d, a1.x, a0.x);
-    c[1 * R2] = fmaf(d, a1.y, a0.y);
-    c[2 * R2] = a1.x;
-    c[3 * R2] = a1.y;
-    c[4 * R2] = a0.x;
-    c[5 * R2] = a0.y;
+    float* cf = coef + (size_t)f * C.num_taps * 6 * R2;
+    *(float4*)(cf + ((size_t)ts * R2 + r) * 4) = make_float4(fmaf(d, a1.x, a0.x), fmaf(d, a1.y, a0.y), a1.x, a1.y);
+    *(float2*)(cf + (size_t)C.num_taps * R2 * 4 + ((size_t)ts * R2 + r) * 2) = a0;
 }
 
 __device__ __forceinline__ void cp_async8_s(unsigned d, const void* g) {
@@ -210,247 +206,414 @@ __device__ __forceinline__ void cp_async16_s(unsigned d, const void* g) {
 __device__ __forceinline__ f2 neg2(f2 a) { float x, y; upk(a, x, y); return pk(-x, -y); }
 // acc += a * b in place: the read-write constraint keeps the accumulator in the same register pair
 __device__ __forceinline__ void fma2_acc(f2& acc, f2 a, f2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.v) : "l"(a.v), "l"(b.v)); }
+// base + off * scale as ONE instruction (IMAD.WIDE.U32): all per-symbol addresses are a uniform 64-bit
+// base plus a per-lane 32-bit element offset
+__device__ __forceinline__ unsigned long long gaddr(unsigned long long base, unsigned off, unsigned scale) {
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(off), "r"(scale), "l"(base));
+    return r;
+}
+__device__ __forceinline__ void stg64(unsigned long long a, float x, float y) {
+    asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ float2 ldg64(unsigned long long a) {
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned ldgu8(unsigned long long a) {
+    unsigned v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(unsigned a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 lds128(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
 
-// Persistent CTAs, each walking whole streams (b = blockIdx.x, += gridDim.x) symbol by symbol.  A thread
-// owns the SAME two bins kk = tid and kk + half of the occupied window for its whole life, so everything
-// that depends on the bin only -- bin class, pilot value, exp(-2 pi j k / N) and its powers e_t[k] -- sits in
-// registers, and the antenna-independent arithmetic (Horner sweep over the symbol tail, V_t = e_t X,
-// W_t = e_t G - Q_t) runs packed over the two bins.  The combine runs packed over receive-antenna pairs with
-// the bin's V / W as scalar-broadcast operands and the coefficients as 128-bit shared-memory broadcasts.
-// Per symbol the CTA stages with cp.async (double buffered, one barrier) the symbol's G window, its Jakes
-// coefficients and the dmax + cp time samples around the cyclic prefix: the next symbol's bytes are in
-// flight while the current one is computed, and no register holds them.  Stream power stays in registers
-// across the stream's symbols and leaves as one atomic per warp and antenna.
-// COMPACT: Y holds the data bins only ([B*R][S][Nd]) and the pilot bins of every slot's first symbol go
-// to Yp ([B*R][slots][Np]) -- nothing else is ever read downstream.
-template <int NT, int RP, bool COMPACT, bool Z0>
-__global__ void __launch_bounds__(SPEC_MAX_THREADS, 1)
+__device__ __forceinline__ void stg128(unsigned long long a, float x, float y, float z, float w) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float ldg32(unsigned long long a) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(a));
+    return v;
+}
+// scalar (both lanes) operand of a packed multiply-add: SASS takes it as a .F32 broadcast, no register pair
+__device__ __forceinline__ f2 bc(float x) { return pk(x, x); }
+
+// ---- mbarrier / bulk-copy (TMA engine) primitives ------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// one contiguous run of global memory -> shared memory by the bulk-copy engine; completion is signalled on `bar`
+__device__ __forceinline__ void bulk_g2s(unsigned dst, unsigned long long src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float lds32(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+
+// both halves of a packed register pair straight from two shared-memory words
+__device__ __forceinline__ f2 lds32x2(unsigned a, unsigned b) {
+    f2 r;
+    asm volatile("{\n.reg .f32 lo, hi;\nld.shared.f32 lo, [%1];\nld.shared.f32 hi, [%2];\nmov.b64 %0, {lo, hi};\n}"
+                 : "=l"(r.v) : "r"(a), "r"(b));
+    return r;
+}
+// Horner steps acc <- u + w acc on the packed accumulator (hre, him), in place: two steps / one step.
+// One asm statement each, so the loop-carried accumulator keeps its register pair (no copies at the back edge).
+__device__ __forceinline__ void horner2(f2& hre, f2& him, f2 wre, f2 wim, f2 nwim, float2 u0, float2 u1) {
+    asm("{\n.reg .b64 tr, ti, a, b, c, d;\n"
+        "mov.b64 a, {%5, %5};\nmov.b64 b, {%6, %6};\nmov.b64 c, {%7, %7};\nmov.b64 d, {%8, %8};\n"
+        "fma.rn.f32x2 tr, %2, %0, a;\nfma.rn.f32x2 ti, %2, %1, b;\n"
+        "fma.rn.f32x2 tr, %4, %1, tr;\nfma.rn.f32x2 ti, %3, %0, ti;\n"
+        "fma.rn.f32x2 %0, %2, tr, c;\nfma.rn.f32x2 %1, %2, ti, d;\n"
+        "fma.rn.f32x2 %0, %4, ti, %0;\nfma.rn.f32x2 %1, %3, tr, %1;\n}"
+        : "+l"(hre.v), "+l"(him.v)
+        : "l"(wre.v), "l"(wim.v), "l"(nwim.v), "f"(u0.x), "f"(u0.y), "f"(u1.x), "f"(u1.y));
+}
+__device__ __forceinline__ void horner1(f2& hre, f2& him, f2 wre, f2 wim, f2 nwim, float2 u0) {
+    asm("{\n.reg .b64 tr, a, b;\n"
+        "mov.b64 a, {%5, %5};\nmov.b64 b, {%6, %6};\n"
+        "fma.rn.f32x2 tr, %2, %0, a;\n"
+        "fma.rn.f32x2 tr, %4, %1, tr;\n"
+        "fma.rn.f32x2 %1, %2, %1, b;\n"
+        "fma.rn.f32x2 %1, %3, %0, %1;\n"
+        "mov.b64 %0, tr;\n}"
+        : "+l"(hre.v), "+l"(him.v)
+        : "l"(wre.v), "l"(wim.v), "l"(nwim.v), "f"(u0.x), "f"(u0.y));
+}
+
+#define SPEC_STAGES 3
+
+// Persistent, warp-specialised kernel.  A CTA walks whole streams (b = blockIdx.x, += gridDim.x) symbol by
+// symbol.  ONE producer warp feeds a 3-stage shared-memory ring with the bulk-copy (TMA) engine: per OFDM
+// symbol three contiguous runs -- the symbol's G window, the dmax + cp time samples around its cyclic prefix,
+// its Jakes coefficients -- each one cp.async.bulk that completes on the stage's `full` mbarrier; compute
+// warps hand a stage back through its `empty` mbarrier.  No thread ever spends an instruction on staging and
+// there is no CTA-wide barrier in the loop.
+// Lane l of compute warp w owns the SAME bin pair 32 w + l of the plan's pair table (two consecutive data
+// symbols, or two consecutive pilots, plus the window's null bins) for its whole life, so everything that
+// depends on the bin only -- class, pilot value, exp(-2 pi j k / N) and its powers e_t[k] -- sits in
+// registers.  ALL arithmetic on the bins runs packed over the pair (f32x2 lanes = the two bins): the Horner
+// sweep over the symbol tail, V_t = e_t X, W_t = e_t G - Q_t, and the per-antenna combine, whose
+// coefficients enter as scalar-broadcast operands straight from 128-bit shared-memory loads -- no packing
+// or unpacking instruction on the path.  The cyclic-prefix samples (time domain, power only) are spread over
+// the first cp / 32 warps.  Stream power stays in registers across the stream's symbols and leaves as one
+// atomic per warp and antenna.
+// PLANAR (the sweep's compact layout): a data pair leaves as ONE 128-bit store (re0, re1, im0, im1) into
+// Y [B*R][S][ndp][4]; pilot pairs only on every slot's first symbol, into Yp [B*R][slots][npp][4]; nothing
+// else is ever read downstream.  Otherwise Y is the windowed grid [B*R][S][nk] of interleaved complex.
+template <int NT, int R2, bool PLANAR, bool Z0>
+__global__ void __launch_bounds__(32 * (SPEC_MAX_WARPS + 1), 1)
 channel_spectral_kernel(const DevPlan P, const SpecParams C, const uint8_t* __restrict__ idx,
                         const float2* __restrict__ G, const float2* __restrict__ tail,
-                        const float* __restrict__ coef_g, float2* __restrict__ Y, float2* __restrict__ Yp,
-                        double* __restrict__ power, int k0, int nk, int half, int S, int R, int B) {
-    constexpr int R2 = 2 * RP, NCF = NT * 6 * R2;               // coefficient floats per symbol
-    __shared__ __align__(16) float s_cf[2][NCF];
-    __shared__ __align__(16) float2 s_x[2][SPEC_XMAX];          // x[local index i - dmax], i in [-dmax, cp)
-    __shared__ __align__(16) float2 s_g[2][SPEC_GMAX];
-    __shared__ float s_lev[8];
-    const int tid = threadIdx.x;
-    const int cp = P.cp, L = P.L, dmax = C.dmax, nx = dmax + cp;
+                        const float* __restrict__ coef_g, float* __restrict__ Y, float* __restrict__ Yp,
+                        double* __restrict__ power, int k0, int nk, int S, int R, int B, int nwarps, int dmax2) {
+    constexpr int RP = R2 / 2, NCF = NT * 6 * R2;               // antenna pairs, coefficient floats per symbol
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int cp = P.cp, L = P.L;
     const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
-    if (tid < 8) s_lev[tid] = P.lev[tid];
-
-    // ---- per-thread constants of its two bins ---------------------------------------------------
-    const int kkA = tid, kkB = tid + half;
-    const bool okA = tid < half, okB = tid < half && kkB < nk;
-    const int kA = (okA ? kkA : 0) + k0, kB = (okB ? kkB : 0) + k0;
-    const int codeA = okA ? (int)__ldg(&P.bin_map[kA]) : BIN_NULL, codeB = okB ? (int)__ldg(&P.bin_map[kB]) : BIN_NULL;
-    const bool datA = codeA >= 0 && !(codeA & BIN_PILOT_FLAG), datB = codeB >= 0 && !(codeB & BIN_PILOT_FLAG);
-    const bool pilA = codeA >= 0 && !datA, pilB = codeB >= 0 && !datB;
-    const int slotA = codeA & (BIN_PILOT_FLAG - 1), slotB = codeB & (BIN_PILOT_FLAG - 1);   // data index or pilot index
-    const float2 pvA = pilA ? P.pilots[slotA] : make_float2(0.f, 0.f);
-    const float2 pvB = pilB ? P.pilots[slotB] : make_float2(0.f, 0.f);
-    f2 wre, wim, ere[NT], eim[NT];
+    // shared memory: [mbarriers full[3], empty[3]] [X lookup: re[64], im[64]] stages x {G row | x region | coefficients}
+    const unsigned s0 = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned bar_full = s0, bar_empty = s0 + 8u * SPEC_STAGES;
+    const unsigned lut = s0 + 64u;
+    const unsigned gbytes = (unsigned)nk * 8u, xbytes = (unsigned)(dmax2 + cp) * 8u, cbytes = (unsigned)(NCF * sizeof(float));
+    const unsigned stage_bytes = gbytes + xbytes + cbytes;
+    const unsigned stage0 = s0 + 64u + 512u;
     {
-        const float2 a = __ldg(&P.twiddle[kA]), c = __ldg(&P.twiddle[kB]);
+        const int hb0 = P.bps >> 1, mask0 = (1 << hb0) - 1;
+        float* l = (float*)(smem_raw + 64);
+        for (int v = threadIdx.x; v < 64; v += blockDim.x) {
+            l[v] = P.lev[(v >> hb0) & mask0];
+            l[64 + v] = P.lev[v & mask0];
+        }
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int st = 0; st < SPEC_STAGES; ++st) {
+            mbar_init(bar_full + 8u * st, 1u);
+            mbar_init(bar_empty + 8u * st, (unsigned)nwarps + 1u);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const unsigned xo = gbytes + 8u * (unsigned)dmax2;         // local sample 0 (first CP sample) of the symbol
+    const unsigned co = gbytes + xbytes;                        // coefficients: [ts][R2] x 16 B, then c0 [ts][R2] x 8 B
+    constexpr unsigned C0OFF = (unsigned)(NT * R2 * 16);
+
+    // ================================ producer + cyclic-prefix warp ============================
+    // Lane 0 keeps the ring two symbols ahead: at the top of symbol i it waits for the stage of symbol i - 1 to
+    // be handed back by every warp and refills it with symbol i + 2.  Then the whole warp evaluates the CP samples
+    // of symbol i: they only enter the stream power (core/channel.py:216-218 measures the whole faded stream) but
+    // carry the inter-symbol leakage, so they are done in the time domain, y_r[i] = sum_t (c0 + c1 tau_i) x[i - d_t],
+    // packed over sample pairs (i, i + 1) with the coefficients as scalar-broadcast operands like in the bin loop.
+    // Its work per symbol is a little under that of a bin warp, so it never is the one the others wait for.
+    if (w == nwarps) {
+        auto produce = [&](unsigned f, unsigned st) {
+            const unsigned dst = stage0 + st * stage_bytes, bar = bar_full + 8u * st;
+            // samples [f cp - dmax2, f cp + cp) of the tail array; the very first symbol has nothing before it
+            const unsigned skip = f == 0 ? (unsigned)dmax2 * 8u : 0u;
+            mbar_expect_tx(bar, stage_bytes - skip);
+            bulk_g2s(dst, gaddr((unsigned long long)G, f, gbytes), gbytes, bar);
+            bulk_g2s(dst + gbytes + skip,
+                     gaddr((unsigned long long)tail, f, (unsigned)cp * 8u) - (unsigned long long)dmax2 * 8ull + skip,
+                     xbytes - skip, bar);
+            bulk_g2s(dst + gbytes + xbytes, gaddr((unsigned long long)coef_g, f, cbytes), cbytes, bar);
+        };
+        // the CTA's symbol sequence: (b, s), b = blockIdx.x + k gridDim.x; `pb, ps` run two symbols ahead of `b, s`
+        unsigned pb = blockIdx.x, ps = 0, pstage = 0, pphase = 0;
+        auto produce_next = [&]() {
+            if (pb < (unsigned)B) {
+                if (lane == 0) {
+                    mbar_wait(bar_empty + 8u * pstage, pphase ^ 1u);
+                    produce(pb * (unsigned)S + ps, pstage);
+                }
+                if (++ps == (unsigned)S) { ps = 0; pb += gridDim.x; }
+                if (++pstage == SPEC_STAGES) { pstage = 0; pphase ^= 1u; }
+            }
+        };
+        produce_next();
+        produce_next();
+        f2 pwc[R2];
+#pragma unroll
+        for (int r = 0; r < R2; ++r) pwc[r] = pk(0.f, 0.f);
+        unsigned stage = 0, phase = 0;
+        for (unsigned b = blockIdx.x; b < (unsigned)B; b += gridDim.x) {
+            for (unsigned s = 0; s < (unsigned)S; ++s) {
+                produce_next();
+                __syncwarp();
+                mbar_wait(bar_full + 8u * stage, phase);
+                const unsigned sb = stage0 + stage * stage_bytes;
+                for (int i0 = 2 * lane; i0 < cp; i0 += 64) {
+                    const float tf = (float)i0 - 0.5f * (float)(L - 1);
+                    const f2 tau = pk(tf, tf + 1.f);
+                    f2 yre[R2], yim[R2];
+#pragma unroll
+                    for (int r = 0; r < R2; ++r) { yre[r] = pk(0.f, 0.f); yim[r] = pk(0.f, 0.f); }
+#pragma unroll
+                    for (int ts = 0; ts < NT; ++ts) {
+                        const int d = C.delay[ts];
+                        const unsigned xa = sb + xo + 8u * (unsigned)(i0 + dmax2 - d) - 8u * (unsigned)dmax2;
+                        f2 xr = lds32x2(xa, xa + 8u), xi = lds32x2(xa + 4u, xa + 12u);
+                        if (s == 0 && i0 < d) {                                     // nothing precedes the stream
+                            const f2 m = pk(0.f, i0 + 1 < d ? 0.f : 1.f);
+                            xr = mul2(xr, m);
+                            xi = mul2(xi, m);
+                        }
+                        const unsigned ct = sb + co + (unsigned)(ts * R2 * 16);
+#pragma unroll
+                        for (int r = 0; r < R2; ++r) {
+                            const float4 ac = lds128(ct + 16u * r);                 // (a.re, a.im, c1.re, c1.im)
+                            const float2 c0 = lds64(sb + co + C0OFF + (unsigned)(ts * R2 * 8) + 8u * r);
+                            const f2 hr = fma2(tau, bc(ac.z), bc(c0.x)), hi = fma2(tau, bc(ac.w), bc(c0.y));
+                            fma2_acc(yre[r], hr, xr); fma2_acc(yre[r], neg2(hi), xi);
+                            fma2_acc(yim[r], hr, xi); fma2_acc(yim[r], hi, xr);
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < R2; ++r) {
+                        fma2_acc(pwc[r], yre[r], yre[r]);
+                        fma2_acc(pwc[r], yim[r], yim[r]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8u * stage);
+                if (++stage == SPEC_STAGES) { stage = 0; phase ^= 1u; }
+            }
+#pragma unroll
+            for (int r = 0; r < R2; ++r) {
+                float a, c;
+                upk(pwc[r], a, c);
+                const float t = warp_sum(a + c);
+                if (lane == 0 && r < R) atomicAdd(&power[(size_t)b * R + r], (double)t);
+                pwc[r] = pk(0.f, 0.f);
+            }
+        }
+        return;
+    }
+
+    // ================================ bin warps ==================================================
+    // ---- per-lane constants of its bin pair -------------------------------------------------------
+    const int pi = 32 * w + lane;
+    const bool live = pi < P.npairs;
+    const int binA = live ? (int)P.pair_bin[2 * pi] : -1, binB = live ? (int)P.pair_bin[2 * pi + 1] : -1;
+    const bool okA = binA >= 0, okB = binB >= 0;
+    const bool isdat = pi < P.ndp, ispil = !isdat && pi < P.ndp + P.npp;
+    const int codeA = okA ? (int)__ldg(&P.bin_map[binA]) : BIN_NULL, codeB = okB ? (int)__ldg(&P.bin_map[binB]) : BIN_NULL;
+    const bool datA = isdat && codeA >= 0, datB = isdat && codeB >= 0;      // a data pair may end in a null pad
+    const unsigned slotA = (unsigned)(codeA & (BIN_PILOT_FLAG - 1)), slotB = (unsigned)(codeB & (BIN_PILOT_FLAG - 1));
+    float2 pvA = make_float2(0.f, 0.f), pvB = pvA;
+    if (ispil && codeA >= 0) pvA = P.pilots[slotA];
+    if (ispil && codeB >= 0) pvB = P.pilots[slotB];
+    const unsigned kkA = (unsigned)((okA ? binA : k0) - k0), kkB = (unsigned)((okB ? binB : k0) - k0);
+    f2 wre, wim, nwim, ere[NT], eim[NT];
+    {
+        const float2 z = make_float2(0.f, 0.f);
+        const float2 a = okA ? __ldg(&P.twiddle[binA]) : z, c = okB ? __ldg(&P.twiddle[binB]) : z;
         wre = pk(a.x, c.x);
         wim = pk(a.y, c.y);
+        nwim = pk(-a.y, -c.y);
 #pragma unroll
         for (int ts = 0; ts < NT; ++ts) {
             const int d = C.delay[ts];
-            const float2 ea = __ldg(&P.twiddle[(kA * d) & (P.N - 1)]), ec = __ldg(&P.twiddle[(kB * d) & (P.N - 1)]);
+            const float2 ea = okA ? __ldg(&P.twiddle[(binA * d) & (P.N - 1)]) : z;
+            const float2 ec = okB ? __ldg(&P.twiddle[(binB * d) & (P.N - 1)]) : z;
             ere[ts] = pk(ea.x, ec.x);
             eim[ts] = pk(ea.y, ec.y);
         }
     }
-    const int hb = P.bps >> 1, mask = (1 << hb) - 1;
+    const f2 vmask = pk(okA ? 1.f : 0.f, okB ? 1.f : 0.f);      // a missing bin contributes nothing
+    const bool partial = live && !(okA && okB);
     const float sqn = sqrtf((float)P.N);
     const f2 nsq = pk(-sqn, -sqn);
-    const float tf = (float)tid - 0.5f * (float)(L - 1);        // polynomial argument of CP sample i = tid
-    const f2 tau = pk(tf, tf);
-    // where this thread's outputs go inside one (antenna, symbol) row, and whether they go anywhere
-    const int strideY = COMPACT ? P.Nd : nk;
-    const int offA = COMPACT ? slotA : kkA, offB = COMPACT ? slotB : kkB;
-    const bool stA = COMPACT ? datA : okA, stB = COMPACT ? datB : okB;
+    const unsigned gA = 8u * kkA, gB = 8u * kkB;                // byte offsets of the pair's G values inside a stage
+    const unsigned long long iA = (unsigned long long)idx + slotA, iB = (unsigned long long)idx + slotB;
 
-    f2 pw[RP];
+    f2 pw[R2];                                                  // lanes: the two bins
 #pragma unroll
-    for (int p = 0; p < RP; ++p) pw[p] = pk(0.f, 0.f);
+    for (int r = 0; r < R2; ++r) pw[r] = pk(0.f, 0.f);
 
-    // ---- staging: cp.async of symbol f into buffer `buf`; index bytes into registers -----------
-    // shared addresses and per-thread global offsets are formed once; per symbol only f * row-length is added
-    const unsigned sgA = (unsigned)__cvta_generic_to_shared(&s_g[0][kkA]);
-    const unsigned sxT = (unsigned)__cvta_generic_to_shared(&s_x[0][tid < SPEC_XMAX ? tid : 0]);
-    const unsigned scT = (unsigned)__cvta_generic_to_shared(&s_cf[0][tid < NCF / 4 ? 4 * tid : 0]);
-    const float2* gT = G + kkA;
-    const float2* xT = tail + (tid - dmax);                     // local sample index tid - dmax; < 0: the previous symbol's tail
-    const float* cT = coef_g + 4 * tid;
-    const uint8_t* iA = idx + slotA;
-    const uint8_t* iB = idx + slotB;
-    const bool xrow = tid < nx, xhist = tid < dmax, crow = tid < NCF / 4;
-    int ibA = 0, ibB = 0;
-    auto prefetch = [&](unsigned f, unsigned s, unsigned buf) {
-        const float2* g = gT + (unsigned long long)f * (unsigned)nk;
-        const unsigned sg = sgA + buf * (unsigned)(SPEC_GMAX * sizeof(float2));
-        if (okA) cp_async8_s(sg, g);
-        if (okB) cp_async8_s(sg + (unsigned)half * 8u, g + half);
-        if (xrow) {
-            const bool have = !xhist || s > 0;
-            cp_async8_zfill_s(sxT + buf * (unsigned)(SPEC_XMAX * sizeof(float2)),
-                              have ? (const void*)(xT + (unsigned long long)f * (unsigned)cp) : (const void*)tail, have);
-        }
-        if (crow) cp_async16_s(scT + buf * (unsigned)(NCF * sizeof(float)), cT + (unsigned long long)f * (unsigned)NCF);
-        const unsigned long long io = (unsigned long long)f * (unsigned)P.Nd;
-        if (datA) ibA = iA[io];
-        if (datB) ibB = iB[io];
-    };
-
+    unsigned stage = 0, phase = 0;
     unsigned b = blockIdx.x, s = 0;
-    unsigned cur = 0;
-    if (b < (unsigned)B) prefetch(b * (unsigned)S, 0, 0);
-    cp_async_commit();
+    unsigned ibA = 0, ibB = 0;                                  // index bytes of the NEXT symbol to compute
+    if (b < (unsigned)B) {
+        const unsigned f = b * (unsigned)S;
+        if (datA) ibA = ldgu8(gaddr(iA, f, (unsigned)P.Nd));
+        if (datB) ibB = ldgu8(gaddr(iB, f, (unsigned)P.Nd));
+    }
     while (b < (unsigned)B) {
-        cp_async_wait<0>();
-        __syncthreads();                                        // buffer `cur` landed; everyone is done with `cur ^ 1`
-        // transmitted grid values of the two bins (the index bytes were loaded a symbol ahead)
-        float2 xa = pvA, xb = pvB;
-        if (datA) xa = make_float2(s_lev[(ibA >> hb) & mask], s_lev[ibA & mask]);
-        if (datB) xb = make_float2(s_lev[(ibB >> hb) & mask], s_lev[ibB & mask]);
+        // ---- transmitted grid values of the pair from the symbol's index bytes; next symbol's bytes in flight -----
+        f2 xre = pk(pvA.x, pvB.x), xim = pk(pvA.y, pvB.y);
+        if (isdat) {
+            xre = lds32x2(lut + 4u * ibA, lut + 4u * ibB);
+            xim = lds32x2(lut + 256u + 4u * ibA, lut + 256u + 4u * ibB);
+            if (!datB) { xre = mul2(xre, pk(1.f, 0.f)); xim = mul2(xim, pk(1.f, 0.f)); }   // null pad of an odd data count
+        }
         unsigned nb = b, ns = s + 1;
         if (ns == (unsigned)S) { ns = 0; nb = b + gridDim.x; }
-        if (nb < (unsigned)B) prefetch(nb * (unsigned)S + ns, ns, cur ^ 1u);
-        cp_async_commit();
-        const float* cf = s_cf[cur];
+        if (nb < (unsigned)B) {
+            const unsigned f = nb * (unsigned)S + ns;
+            if (datA) ibA = ldgu8(gaddr(iA, f, (unsigned)P.Nd));
+            if (datB) ibB = ldgu8(gaddr(iB, f, (unsigned)P.Nd));
+        }
+        mbar_wait(bar_full + 8u * stage, phase);                // the symbol's bytes have landed
+        const unsigned sb = stage0 + stage * stage_bytes;
+        const f2 gre = lds32x2(sb + gA, sb + gB), gim = lds32x2(sb + gA + 4u, sb + gB + 4u);
 
-        // ---- cyclic-prefix samples: time domain, only into the stream power -----------------------
-        if (tid < cp) {
-            f2 yre[RP], yim[RP];
+        f2 hre = pk(0.f, 0.f), him = pk(0.f, 0.f);              // Horner accumulator
+        f2 yre[R2], yim[R2];
+        unsigned up = sb + xo + 8u * (unsigned)(cp - 1);        // u[N - 1 - p] at up - 8 p
+        int pstep = 0;
 #pragma unroll
-            for (int p = 0; p < RP; ++p) { yre[p] = pk(0.f, 0.f); yim[p] = pk(0.f, 0.f); }
-#pragma unroll
-            for (int ts = 0; ts < NT; ++ts) {
-                const float2 x = s_x[cur][dmax + tid - C.delay[ts]];
-                const f2 xre = pk(x.x, x.x), xim = pk(x.y, x.y), nxim = pk(-x.y, -x.y);
-                const float* ct = cf + ts * 6 * R2;
-#pragma unroll
-                for (int p = 0; p < RP; ++p) {
-                    const float2 c1r = *(const float2*)(ct + 2 * R2 + 2 * p), c1i = *(const float2*)(ct + 3 * R2 + 2 * p);
-                    const float2 c0r = *(const float2*)(ct + 4 * R2 + 2 * p), c0i = *(const float2*)(ct + 5 * R2 + 2 * p);
-                    const f2 hre = fma2(pk(c1r.x, c1r.y), tau, pk(c0r.x, c0r.y));
-                    const f2 him = fma2(pk(c1i.x, c1i.y), tau, pk(c0i.x, c0i.y));
-                    yre[p] = fma2(hre, xre, yre[p]); yre[p] = fma2(him, nxim, yre[p]);
-                    yim[p] = fma2(hre, xim, yim[p]); yim[p] = fma2(him, xre, yim[p]);
+        for (int ts = 0; ts < NT; ++ts) {
+            if (!(Z0 && ts == 0)) {
+                // Horner steps up to this tap's delay, two per trip: acc <- u + w acc
+                int n = C.delay[ts] - pstep;
+                pstep = C.delay[ts];
+#pragma unroll 1
+                for (; n >= 2; n -= 2, up -= 16u) horner2(hre, him, wre, wim, nwim, lds64(up), lds64(up - 8u));
+                if (n) {
+                    horner1(hre, him, wre, wim, nwim, lds64(up));
+                    up -= 8u;
                 }
             }
+            f2 vre, vim, qre, qim;
+            if (Z0 && ts == 0) {
+                vre = xre; vim = xim; qre = gre; qim = gim;
+            } else {
+                vre = fma2(neg2(eim[ts]), xim, mul2(ere[ts], xre));
+                vim = fma2(eim[ts], xre, mul2(ere[ts], xim));
+                qre = fma2(neg2(eim[ts]), gim, fma2(ere[ts], gre, mul2(nsq, hre)));
+                qim = fma2(eim[ts], gre, fma2(ere[ts], gim, mul2(nsq, him)));
+            }
+            const unsigned ct = sb + co + (unsigned)(ts * R2 * 16);
 #pragma unroll
-            for (int p = 0; p < RP; ++p) {
-                pw[p] = fma2(yre[p], yre[p], pw[p]);
-                pw[p] = fma2(yim[p], yim[p], pw[p]);
+            for (int r = 0; r < R2; ++r) {
+                const float4 ac = lds128(ct + 16u * r);         // (a.re, a.im, c1.re, c1.im) of antenna r
+                if (ts == 0) {
+                    yre[r] = mul2(vre, bc(ac.x));
+                    yim[r] = mul2(vim, bc(ac.x));
+                } else {
+                    fma2_acc(yre[r], vre, bc(ac.x));
+                    fma2_acc(yim[r], vim, bc(ac.x));
+                }
+                fma2_acc(yre[r], vim, bc(-ac.y)); fma2_acc(yim[r], vre, bc(ac.y));
+                fma2_acc(yre[r], qre, bc(ac.z));  fma2_acc(yim[r], qim, bc(ac.z));
+                fma2_acc(yre[r], qim, bc(-ac.w)); fma2_acc(yim[r], qre, bc(ac.w));
             }
         }
+        // every shared-memory read of this stage is done: hand it back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8u * stage);
+        if (++stage == SPEC_STAGES) { stage = 0; phase ^= 1u; }
 
-        // ---- the thread's two bins ------------------------------------------------------------------
-        if (okA) {
-            const float2 cgA = s_g[cur][kkA], cgB = okB ? s_g[cur][kkB] : make_float2(0.f, 0.f);
-            const f2 xre = pk(xa.x, xb.x), xim = pk(xa.y, xb.y);
-            const f2 gre_ = pk(cgA.x, cgB.x), gim_ = pk(cgA.y, cgB.y);
-            f2 hre = pk(0.f, 0.f), him = pk(0.f, 0.f);          // Horner accumulator, packed over the two bins
-            f2 yreA[RP], yimA[RP], yreB[RP], yimB[RP];           // packed over the antenna pair
-            const float2* up = &s_x[cur][nx - 1];               // u[N - 1 - p] = up[-p]
-            const f2 nwim = neg2(wim);
-            int pstep = 0;
+        if (partial) {
 #pragma unroll
-            for (int ts = 0; ts < NT; ++ts) {
-                if (!(Z0 && ts == 0)) {
-                    // Horner steps up to this tap's delay, two per trip so the accumulator ping-pongs between
-                    // two register sets instead of being copied: acc <- u + w acc
-                    int n = C.delay[ts] - pstep;
-                    pstep = C.delay[ts];
-#pragma unroll 1
-                    for (; n >= 2; n -= 2, up -= 2) {
-                        const float2 u0 = up[0], u1 = up[-1];
-                        f2 gre = fma2(wre, hre, pk(u0.x, u0.x)), gim = fma2(wre, him, pk(u0.y, u0.y));
-                        fma2_acc(gre, nwim, him);
-                        fma2_acc(gim, wim, hre);
-                        hre = fma2(wre, gre, pk(u1.x, u1.x));
-                        him = fma2(wre, gim, pk(u1.y, u1.y));
-                        fma2_acc(hre, nwim, gim);
-                        fma2_acc(him, wim, gre);
-                    }
-                    if (n) {
-                        const float2 u0 = up[0];
-                        f2 gre = fma2(wre, hre, pk(u0.x, u0.x)), gim = fma2(wre, him, pk(u0.y, u0.y));
-                        fma2_acc(gre, nwim, him);
-                        fma2_acc(gim, wim, hre);
-                        hre = gre;
-                        him = gim;
-                        up -= 1;
+            for (int r = 0; r < R2; ++r) { yre[r] = mul2(yre[r], vmask); yim[r] = mul2(yim[r], vmask); }
+        }
+
+        // ---- power and stores ---------------------------------------------------------------------
+        if (live) {
+            const unsigned row0 = b * (unsigned)(R * S) + s;        // row of antenna 0; antenna r is S rows further
+            if (PLANAR) {
+                const bool head = ispil && s % LTE_SLOT_SYMBOLS == 0;
+                const unsigned long long yb = gaddr((unsigned long long)Y, row0, (unsigned)P.ndp * 16u) + 16u * (unsigned)pi;
+                const unsigned long long pb = gaddr((unsigned long long)Yp, b * (unsigned)(R * nslot) + s / LTE_SLOT_SYMBOLS,
+                                                    (unsigned)P.npp * 16u) + 16u * (unsigned)(pi - P.ndp);
+#pragma unroll
+                for (int r = 0; r < R2; ++r) {
+                    fma2_acc(pw[r], yre[r], yre[r]);
+                    fma2_acc(pw[r], yim[r], yim[r]);
+                    if (r < R) {
+                        float a, c, d, e;
+                        upk(yre[r], a, c);
+                        upk(yim[r], d, e);
+                        if (isdat) stg128(gaddr(yb, (unsigned)(r * S) * (unsigned)P.ndp, 16u), a, c, d, e);
+                        else if (head) stg128(gaddr(pb, (unsigned)(r * nslot) * (unsigned)P.npp, 16u), a, c, d, e);
                     }
                 }
-                f2 vre, vim, qre, qim;
-                if (Z0 && ts == 0) {
-                    vre = xre; vim = xim; qre = gre_; qim = gim_;
-                } else {
-                    vre = fma2(neg2(eim[ts]), xim, mul2(ere[ts], xre));
-                    vim = fma2(eim[ts], xre, mul2(ere[ts], xim));
-                    qre = fma2(neg2(eim[ts]), gim_, fma2(ere[ts], gre_, mul2(nsq, hre)));
-                    qim = fma2(eim[ts], gre_, fma2(ere[ts], gim_, mul2(nsq, him)));
-                }
-                float vAr, vBr, vAi, vBi, qAr, qBr, qAi, qBi;
-                upk(vre, vAr, vBr); upk(vim, vAi, vBi); upk(qre, qAr, qBr); upk(qim, qAi, qBi);
-                const float* ct = cf + ts * 6 * R2;
+            } else {
+                const unsigned long long yb = gaddr((unsigned long long)Y, row0, (unsigned)nk * 8u);
 #pragma unroll
-                for (int p = 0; p < RP; ++p) {
-                    const float2 ar = *(const float2*)(ct + 2 * p), ai = *(const float2*)(ct + R2 + 2 * p);
-                    const float2 cr = *(const float2*)(ct + 2 * R2 + 2 * p), ci = *(const float2*)(ct + 3 * R2 + 2 * p);
-                    const f2 are = pk(ar.x, ar.y), aim = pk(ai.x, ai.y), cre = pk(cr.x, cr.y), cim = pk(ci.x, ci.y);
-                    if (ts == 0) {
-                        yreA[p] = mul2(are, pk(vAr, vAr)); yimA[p] = mul2(are, pk(vAi, vAi));
-                        yreB[p] = mul2(are, pk(vBr, vBr)); yimB[p] = mul2(are, pk(vBi, vBi));
-                    } else {
-                        fma2_acc(yreA[p], are, pk(vAr, vAr)); fma2_acc(yimA[p], are, pk(vAi, vAi));
-                        fma2_acc(yreB[p], are, pk(vBr, vBr)); fma2_acc(yimB[p], are, pk(vBi, vBi));
-                    }
-                    fma2_acc(yreA[p], aim, pk(-vAi, -vAi)); fma2_acc(yimA[p], aim, pk(vAr, vAr));
-                    fma2_acc(yreB[p], aim, pk(-vBi, -vBi)); fma2_acc(yimB[p], aim, pk(vBr, vBr));
-                    fma2_acc(yreA[p], cre, pk(qAr, qAr)); fma2_acc(yimA[p], cre, pk(qAi, qAi));
-                    fma2_acc(yreB[p], cre, pk(qBr, qBr)); fma2_acc(yimB[p], cre, pk(qBi, qBi));
-                    fma2_acc(yreA[p], cim, pk(-qAi, -qAi)); fma2_acc(yimA[p], cim, pk(qAr, qAr));
-                    fma2_acc(yreB[p], cim, pk(-qBi, -qBi)); fma2_acc(yimB[p], cim, pk(qBr, qBr));
-                }
-            }
-            // rows (b R + r) S + s of the output; pilots of a slot's first symbol go to their own tensor
-            float2* yrow = Y + (unsigned long long)(b * (unsigned)(R * S) + s) * (unsigned)strideY;
-            const unsigned rstride = (unsigned)(S * strideY);
-            const bool head = COMPACT && s % LTE_SLOT_SYMBOLS == 0;
-            float2* prow = head ? Yp + (unsigned long long)(b * (unsigned)(R * nslot) + s / LTE_SLOT_SYMBOLS) * (unsigned)P.Np : nullptr;
-            const unsigned pstride = (unsigned)(nslot * P.Np);
-#pragma unroll
-            for (int p = 0; p < RP; ++p) {
-                const int r0 = 2 * p;
-                const bool two = r0 + 1 < R;
-                pw[p] = fma2(yreA[p], yreA[p], pw[p]);
-                pw[p] = fma2(yimA[p], yimA[p], pw[p]);
-                float a, c, d, e;
-                upk(yreA[p], a, c);
-                upk(yimA[p], d, e);
-                if (stA) {
-                    yrow[r0 * rstride + offA] = make_float2(a, d);
-                    if (two) yrow[(r0 + 1) * rstride + offA] = make_float2(c, e);
-                } else if (head && pilA) {
-                    prow[r0 * pstride + slotA] = make_float2(a, d);
-                    if (two) prow[(r0 + 1) * pstride + slotA] = make_float2(c, e);
-                }
-                if (okB) {
-                    pw[p] = fma2(yreB[p], yreB[p], pw[p]);
-                    pw[p] = fma2(yimB[p], yimB[p], pw[p]);
-                    upk(yreB[p], a, c);
-                    upk(yimB[p], d, e);
-                    if (stB) {
-                        yrow[r0 * rstride + offB] = make_float2(a, d);
-                        if (two) yrow[(r0 + 1) * rstride + offB] = make_float2(c, e);
-                    } else if (head && pilB) {
-                        prow[r0 * pstride + slotB] = make_float2(a, d);
-                        if (two) prow[(r0 + 1) * pstride + slotB] = make_float2(c, e);
+                for (int r = 0; r < R2; ++r) {
+                    fma2_acc(pw[r], yre[r], yre[r]);
+                    fma2_acc(pw[r], yim[r], yim[r]);
+                    if (r < R) {
+                        float a, c, d, e;
+                        upk(yre[r], a, c);
+                        upk(yim[r], d, e);
+                        if (okA) stg64(gaddr(yb, kkA + (unsigned)(r * S) * (unsigned)nk, 8u), a, d);
+                        if (okB) stg64(gaddr(yb, kkB + (unsigned)(r * S) * (unsigned)nk, 8u), c, e);
                     }
                 }
             }
@@ -459,21 +622,16 @@ channel_spectral_kernel(const DevPlan P, const SpecParams C, const uint8_t* __re
         // ---- end of the stream: its power leaves as one atomic per warp and antenna ----------------
         if (ns == 0) {
 #pragma unroll
-            for (int p = 0; p < RP; ++p) {
+            for (int r = 0; r < R2; ++r) {
                 float a, c;
-                upk(pw[p], a, c);
-                a = warp_sum(a);
-                c = warp_sum(c);
-                if ((tid & 31) == 0) {
-                    atomicAdd(&power[(size_t)b * R + 2 * p], (double)a);
-                    if (2 * p + 1 < R) atomicAdd(&power[(size_t)b * R + 2 * p + 1], (double)c);
-                }
-                pw[p] = pk(0.f, 0.f);
+                upk(pw[r], a, c);
+                const float t = warp_sum(a + c);
+                if (lane == 0 && r < R) atomicAdd(&power[(size_t)b * R + r], (double)t);
+                pw[r] = pk(0.f, 0.f);
             }
         }
         b = nb;
         s = ns;
-        cur ^= 1;
     }
 }
 
@@ -529,9 +687,11 @@ static int spectral_setup(const lte_plan* p, const lte_channel_desc* ch, int32_t
         }
     for (int i = 0; i < ch->num_taps; ++i) { C.delay[i] = ch->delay[C.ord[i]]; C.pos[C.ord[i]] = i; }
     C.dmax = C.delay[ch->num_taps - 1];
-    // delayed copies must stay inside the symbol's own cyclic prefix; the kernel stages dmax + cp samples
-    if (C.dmax > p->dev.cp || C.dmax + p->dev.cp > SPEC_XMAX) return LTE_ERR_UNSUPPORTED;
-    if (p->dev.nk_useful > SPEC_GMAX) return LTE_ERR_UNSUPPORTED;
+    // delayed copies must stay inside the symbol's own cyclic prefix
+    if (C.dmax > p->dev.cp || C.dmax > SPEC_DMAX) return LTE_ERR_UNSUPPORTED;
+    if (p->dev.npairs > 32 * SPEC_MAX_WARPS) return LTE_ERR_UNSUPPORTED;
+    // the bulk-copy engine moves 16-byte aligned runs: rows of G (nk) and of the tail array (cp) must be even
+    if ((p->dev.cp & 1) || (p->dev.nk_useful & 1) || p->dev.bps > 6) return LTE_ERR_UNSUPPORTED;
     double wmax = 0.0;
     for (int nn = 0; nn < LTE_JAKES_TONES; ++nn) {
         C.w_cyc[nn] = ch->doppler_hz * cos(2.0 * M_PI * (double)(nn + 1) / LTE_JAKES_TONES) / p->desc.fs;
@@ -553,17 +713,18 @@ extern "C" int64_t lte_channel_spectral_workspace_bytes(const lte_plan* p, const
 }
 
 extern "C" int lte_channel_spectral(const lte_plan* p, const lte_channel_desc* ch, const uint8_t* idx, const lte_c32* G,
-                                    const lte_c32* tail, const float* phases, lte_c32* Y, lte_c32* Ypilot,
+                                    const lte_c32* tail, const float* phases, void* Y, float* Ypilot,
                                     double* power, void* workspace, int32_t B, int32_t R, int32_t S, void* stream) {
     SpecParams C;
     int rc = spectral_setup(p, ch, R, C);
     if (rc) return rc;
     if (((uintptr_t)workspace & 15) || ((uintptr_t)G & 7) || ((uintptr_t)tail & 7)) return LTE_ERR_INVALID_ARG;
+    if (Ypilot && ((((uintptr_t)Y) | ((uintptr_t)Ypilot)) & 15)) return LTE_ERR_INVALID_ARG;
     if (!idx || !G || !tail || !phases || !Y || !power || !workspace || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
     if (Ypilot && p->dev.Np == 0) return LTE_ERR_INVALID_ARG;
     if (B == 0) return LTE_OK;
     const long long total = (long long)B * S;
-    if (total >= (1ll << 31) - 1) return LTE_ERR_UNSUPPORTED;
+    if (total * R >= (1ll << 31) - 1) return LTE_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const int R2 = (R + 1) & ~1;
     float* coef = (float*)workspace;
@@ -573,20 +734,24 @@ extern "C" int lte_channel_spectral(const lte_plan* p, const lte_channel_desc* c
     spectral_coef_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(C, phases, coef, R, R2, S, p->dev.L, items);
     LTE_CHECK_CUDA(cudaGetLastError());
     const int k0 = p->dev.k0_useful, nk = p->dev.nk_useful;
-    const int half = (nk + 1) / 2;
-    int need = half > C.dmax + p->dev.cp ? half : C.dmax + p->dev.cp;
-    if (need < 64) need = 64;
-    const int threads = (need + 31) & ~31;
-    if (threads > SPEC_MAX_THREADS || C.dmax + p->dev.cp > SPEC_XMAX) return LTE_ERR_UNSUPPORTED;
+    const int nwarps = (p->dev.npairs + 31) / 32;               // bin warps; one more warp feeds the ring and does the CP samples
+    if (nwarps > SPEC_MAX_WARPS) return LTE_ERR_UNSUPPORTED;
+    const int threads = 32 * (nwarps + 1);
+    const int NCF = ch->num_taps * 6 * R2;
+    const int dmax2 = (C.dmax + 1) & ~1;
+    const size_t stage = (size_t)nk * 8 + (size_t)(dmax2 + p->dev.cp) * 8 + (size_t)NCF * 4;
+    const size_t smem = 64 + 512 + SPEC_STAGES * stage;
+    if (smem > 200 * 1024) return LTE_ERR_UNSUPPORTED;
     const bool z0 = C.delay[0] == 0;
     auto launch = [&](auto k) -> int {
-        int per_sm = 1, dev = p->device, sms = 148;
-        LTE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, 0));
-        LTE_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        int per_sm = 1, sms = 148;
+        LTE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LTE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem));
+        LTE_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device));
         long long grid = (long long)sms * (per_sm < 1 ? 1 : per_sm);
         if (grid > B) grid = B;
-        k<<<(unsigned)grid, threads, 0, st>>>(p->dev, C, idx, (const float2*)G, (const float2*)tail, coef, (float2*)Y,
-                                             (float2*)Ypilot, power, k0, nk, half, S, R, B);
+        k<<<(unsigned)grid, threads, smem, st>>>(p->dev, C, idx, (const float2*)G, (const float2*)tail, coef, (float*)Y,
+                                                 (float*)Ypilot, power, k0, nk, S, R, B, nwarps, dmax2);
         LTE_CHECK_CUDA(cudaGetLastError());
         return LTE_OK;
     };
@@ -595,11 +760,11 @@ extern "C" int lte_channel_spectral(const lte_plan* p, const lte_channel_desc* c
             : (z0 ? launch(channel_spectral_kernel<NT, RP, false, true>) : launch(channel_spectral_kernel<NT, RP, false, false>)))
 #define LAUNCH_SPEC(NT)                                                     \
     case NT:                                                                \
-        return R2 == 2 ? LAUNCH_SPEC_RP(NT, 1) : R2 == 4 ? LAUNCH_SPEC_RP(NT, 2) \
-             : R2 == 6 ? LAUNCH_SPEC_RP(NT, 3) : LAUNCH_SPEC_RP(NT, 4);
+        return R2 == 2 ? LAUNCH_SPEC_RP(NT, 2) : R2 == 4 ? LAUNCH_SPEC_RP(NT, 4) \
+             : R2 == 6 ? LAUNCH_SPEC_RP(NT, 6) : LAUNCH_SPEC_RP(NT, 8);
     switch (ch->num_taps) {
 #ifdef SPEC_DEV                     // development builds: the headline shape only (seconds instead of a minute)
-        case 4: return LAUNCH_SPEC_RP(4, 2);
+        case 4: return LAUNCH_SPEC_RP(4, 4);
 #else
         LAUNCH_SPEC(1) LAUNCH_SPEC(2) LAUNCH_SPEC(3) LAUNCH_SPEC(4) LAUNCH_SPEC(5) LAUNCH_SPEC(6) LAUNCH_SPEC(7)
         LAUNCH_SPEC(8)

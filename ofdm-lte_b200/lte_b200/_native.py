@@ -55,6 +55,7 @@ _SIGS = {
     'lte_plan_num_data': ([_P], C.c_int),
     'lte_plan_num_pilots': ([_P], C.c_int),
     'lte_plan_indices_host': ([_P, _P, _P], C.c_int),
+    'lte_plan_compact_shape': ([_P, C.POINTER(_I32), C.POINTER(_I32)], C.c_int),
     'lte_plan_window': ([_P, C.c_int, C.POINTER(_I32), C.POINTER(_I32)], C.c_int),
     'lte_bits_to_indices': ([_P, _P, _I64, _P, _I64, _I32, _P], C.c_int),
     'lte_indices_to_bits': ([_P, _P, _I64, _P, _I64, _I32, _P], C.c_int),

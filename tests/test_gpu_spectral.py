@@ -13,8 +13,14 @@ from oracle import lte_oracle as O
 pytestmark = pytest.mark.gpu
 
 CASES = [(20.0, '64-QAM', 'Pedestrian_A', 4, 14, 3.0), (5.0, 'QPSK', 'Pedestrian_A', 2, 15, 3.0),
-         (1.25, '16-QAM', 'Pedestrian_B', 3, 5, 3.0), (10.0, '16-QAM', 'Vehicular_A', 1, 3, 3.0),
+         (2.5, '16-QAM', 'Pedestrian_B', 3, 5, 3.0), (10.0, '16-QAM', 'Vehicular_A', 1, 3, 3.0),
          (2.5, '64-QAM', 'Vehicular_B', 8, 2, 2.0), (20.0, '16-QAM', 'Bad_Urban', 5, 2, 1.0)]
+
+
+def _unpair(P4, n):
+    """Planar bin pairs (re0, re1, im0, im1) [..., pairs, 4] -> complex [..., n]."""
+    c = torch.complex(P4[..., 0:2], P4[..., 2:4])
+    return c.reshape(*P4.shape[:-2], -1)[..., :n]
 
 
 def _setup(bw, mod, prof, R, S, v, B=2, seed=5):
@@ -92,8 +98,8 @@ def test_compact_layout_is_a_gather_of_the_window(bw, mod, prof, R, S, v):
     k0, nk = eng.window(nat.WINDOW_USEFUL)
     di = torch.as_tensor(eng.data_idx - k0, device='cuda')
     pi = torch.as_tensor(eng.pilot_idx - k0, device='cuda')
-    assert torch.equal(Yd, Y[:, :, di])
-    assert torch.equal(Yp, Y[:, ::14, :][:, :, pi])
+    assert torch.equal(_unpair(Yd, eng.Nd), Y[:, :, di])
+    assert torch.equal(_unpair(Yp, eng.Np), Y[:, ::14, :][:, :, pi])
     assert torch.equal(power, power_c)
 
 
@@ -125,7 +131,7 @@ def test_compact_consumers_count_exactly_like_the_windowed_ones(bw, mod, prof, R
         assert torch.equal(Hp, H[:, :, pi])
 
 
-@pytest.mark.parametrize('bw,mod,R,prof', [(1.25, '16-QAM', 2, 'Pedestrian_A'), (5.0, '64-QAM', 4, 'Vehicular_A'),
+@pytest.mark.parametrize('bw,mod,R,prof', [(2.5, '16-QAM', 2, 'Pedestrian_A'), (5.0, '64-QAM', 4, 'Vehicular_A'),
                                            (2.5, 'QPSK', 1, 'Pedestrian_B'), (20.0, '64-QAM', 4, 'Pedestrian_A')])
 def test_spectral_sweep_counts_track_the_fused_path(bw, mod, R, prof):
     """Same draws, same fading polynomial, different evaluation (bin by bin instead of sample by sample): per-stream
@@ -156,7 +162,9 @@ def test_spectral_reports_unsupported():
     assert eng.spectral_workspace_bytes(chan_for('awgn', num.fs), 2, 2, 2) is None
     assert eng.spectral_workspace_bytes(chan_for('rayleigh_mp', num.fs, 'Pedestrian_A', 2.0, 30.0), 2, 2, 2) is None
     assert eng.spectral_workspace_bytes(chan_for('rayleigh_mp', num.fs, 'Pedestrian_A', 2.0, 3.0), 2, 2, 2) > 0
-    num2 = O.Numerology(1.25, 15.0, 'QPSK')                    # Vehicular_B at 1.92 MHz: 8.7 samples... fits; Bad_Urban too
+    num2 = O.Numerology(1.25, 15.0, 'QPSK')
     from lte_b200 import LinkEngine
     eng2 = LinkEngine(num2.N, num2.Nc, 4, 2, num2.fs)           # a 4-sample prefix cannot hold Vehicular_B's delay spread
     assert eng2.spectral_workspace_bytes(chan_for('rayleigh_mp', num2.fs, 'Vehicular_B', 2.0, 1.0), 1, 1, 1) is None
+    eng3 = LinkEngine(num2.N, num2.Nc, num2.cp_length, 2, num2.fs)   # cp = 9: rows of the tail array are not 16-byte runs
+    assert eng3.spectral_workspace_bytes(chan_for('rayleigh_mp', num2.fs, 'Pedestrian_A', 2.0, 3.0), 1, 1, 1) is None

@@ -46,6 +46,19 @@ def main():
     out = {'B': B, 'profile': prof}
     out['tx_spectral_ms'] = timeit(lambda: eng.tx_spectral(S, idx, out_G=G, out_tail=tail))
     out['channel_spectral_ms'] = timeit(lambda: eng.channel_spectral(idx, G, tail, chan, B, R, S, ph, out=Y, power=power, workspace=ws))
+    nslot = 1
+    Yd = torch.empty((B * R, S, eng.ndp, 4), dtype=torch.float32, device='cuda')
+    Yp = torch.empty((B * R, nslot, eng.npp, 4), dtype=torch.float32, device='cuda')
+    Hp = torch.empty((B * R, nslot, eng.Np), dtype=torch.complex64, device='cuda')
+    errors = torch.zeros(B, dtype=torch.int64, device='cuda')
+    out['channel_spectral_compact_ms'] = timeit(lambda: eng.channel_spectral(idx, G, tail, chan, B, R, S, ph, out=Yd, power=power,
+                                                                             workspace=ws, compact=True, out_pilots=Yp))
+    snr = torch.full((B * R,), 100.0, dtype=torch.float32, device='cuda')
+    awgn = eng.awgn_desc(power, snr, 3, 0, combine=True)
+    out['crs_ls_compact_ms'] = timeit(lambda: eng.estimate_compact(Yp, B * R, S, out=Hp, awgn=awgn))
+    out['mrc_compact_ms'] = timeit(lambda: eng.mrc_demap_count_compact(Yd, Hp, idx, B, R, S, errors=errors, awgn=awgn))
+    wsl = eng.workspace(B, S, R, fading=True, fused=True, lazy=True)
+    out['simo_ber_spectral_ms'] = timeit(lambda: eng.simo_ber(wsl, chan, snr, 5, idx=idx, fused=True, noise_domain=3))
     out['tx_map_ifft_ms'] = timeit(lambda: eng.modulate(S, idx=idx, want_stats=False, out=tx))
     out['channel_rx_fft_ms'] = timeit(lambda: eng.channel_rx_fft(tx, chan, B, R, S, ph, nat.WINDOW_USEFUL, out=Y, power=power))
     print(json.dumps(out))
