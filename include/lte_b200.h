@@ -252,7 +252,7 @@ int lte_channel_rx_fft(const lte_plan*, const lte_channel_desc* ch, const lte_c3
  * them.  With Ypilot != NULL the grid leaves in the COMPACT layout of the sweep consumers
  * (lte_crs_ls_compact, lte_mrc_demap_count_compact, described there): Y = Ydata holds the data bins
  * only and Ypilot the pilot bins of every slot's first symbol -- the only pilots
- * LTEReceiver._estimate_channel_periodic (core/lte_receiver.py:360-411) reads -- both as planar bin pairs.  workspace: lte_channel_spectral_workspace_bytes() bytes of device memory owned by the caller
+ * LTEReceiver._estimate_channel_periodic (core/lte_receiver.py:360-411) reads.  workspace: lte_channel_spectral_workspace_bytes() bytes of device memory owned by the caller
  * (Jakes coefficients; contents are scratch).  Both the size query and the launcher return
  * LTE_ERR_UNSUPPORTED outside the validity range: use lte_tx_map_ifft + lte_channel_rx_fft. */
 int lte_tx_spectral(const lte_plan*, const uint8_t* idx, lte_c32* G, lte_c32* tail, int32_t B, int32_t S,
@@ -260,7 +260,7 @@ int lte_tx_spectral(const lte_plan*, const uint8_t* idx, lte_c32* G, lte_c32* ta
 int64_t lte_channel_spectral_workspace_bytes(const lte_plan*, const lte_channel_desc* ch, int32_t B,
                                              int32_t R, int32_t S);
 int lte_channel_spectral(const lte_plan*, const lte_channel_desc* ch, const uint8_t* idx, const lte_c32* G,
-                         const lte_c32* tail, const float* phases, void* Y, float* Ypilot, double* power,
+                         const lte_c32* tail, const float* phases, lte_c32* Y, lte_c32* Ypilot, double* power,
                          void* workspace, int32_t B, int32_t R, int32_t S, void* stream);
 
 /* --- lazy frequency-domain AWGN for the sweep engine -------------------------------------------
@@ -286,23 +286,23 @@ int lte_mrc_demap_count_awgn(const lte_plan*, const lte_c32* Y, const lte_c32* H
                              unsigned long long* errors, int window, int64_t nbits, int64_t B, int32_t R,
                              int32_t S, const lte_awgn_desc* awgn, void* stream);
 
-/* Compact sweep layout (produced by lte_channel_spectral with Ypilot != NULL): the grid travels as bin
- * PAIRS in planar form (re0, re1, im0, im1), 16 bytes per pair:
- *   Ydata  [B*R][S][ndp][4]            pair i = data symbols 2 i and 2 i + 1 of the OFDM symbol, ndp = ceil(Nd / 2)
- *                                      (odd Nd: the second half of the last pair belongs to no data symbol)
- *   Ypilot [B*R][ceil(S/14)][npp][4]   pair j = pilots 2 j and 2 j + 1 of every slot's first symbol, npp = ceil(Np / 2)
+/* Compact sweep layout (produced by lte_channel_spectral with Ypilot != NULL): the grid travels as
+ *   Ydata  [B*R][S][2 ndp]            data symbol d of the OFDM symbol at element d, ndp = ceil(Nd / 2)
+ *                                     (odd Nd: the last element of a row is padding)
+ *   Ypilot [B*R][ceil(S/14)][2 npp]   pilot i of every slot's first symbol at element i, npp = ceil(Np / 2)
  * i.e. exactly the elements LTEReceiver._estimate_channel_periodic (core/lte_receiver.py:360-411) and
- * _combine_symbols_mrc (core/ofdm_core.py:1484-1532) read.  lte_plan_compact_shape gives ndp and npp.
+ * _combine_symbols_mrc (core/ofdm_core.py:1484-1532) read, in rows of 16-byte pairs.  lte_plan_compact_shape
+ * gives ndp and npp.
  * lte_crs_ls_compact: the LS step of LTEChannelEstimator.estimate_channel (core/lte_receiver.py:62-87),
- * Hp [B*R][ceil(S/14)][Np] (complex) = (Ypilot [+ AWGN]) / pilot; lte_mrc_demap_count_compact interpolates
+ * Hp [B*R][ceil(S/14)][Np] = (Ypilot [+ AWGN]) / pilot; lte_mrc_demap_count_compact interpolates
  * between the two pilots around each data bin (core/lte_receiver.py:98-133: edge hold + np.linspace, the
  * very operations of lte_crs_ls_interp), combines, slices and counts.  awgn may be NULL (noise-free
  * grid); with awgn the draws are those of lte_crs_ls_interp_awgn / lte_mrc_demap_count_awgn, so the
  * error counts are bit-identical to the windowed layout.  Single pilot set (T = 1) only. */
 int lte_plan_compact_shape(const lte_plan*, int32_t* ndp, int32_t* npp);
-int lte_crs_ls_compact(const lte_plan*, const float* Ypilot, lte_c32* Hp, int64_t rows, int32_t S,
+int lte_crs_ls_compact(const lte_plan*, const lte_c32* Ypilot, lte_c32* Hp, int64_t rows, int32_t S,
                        const lte_awgn_desc* awgn, void* stream);
-int lte_mrc_demap_count_compact(const lte_plan*, const float* Ydata, const lte_c32* Hp,
+int lte_mrc_demap_count_compact(const lte_plan*, const lte_c32* Ydata, const lte_c32* Hp,
                                 const uint8_t* idx_tx, unsigned long long* errors, int64_t nbits, int64_t B,
                                 int32_t R, int32_t S, const lte_awgn_desc* awgn, void* stream);
 

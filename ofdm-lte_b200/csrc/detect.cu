@@ -506,17 +506,16 @@ extern "C" int lte_mrc_demap_count_awgn(const lte_plan* p, const lte_c32* Y, con
 }
 
 // ------------------------------------------------------------------------------ compact sweep layout
-// The spectral link (spectral.cu) leaves the grid as bin PAIRS in planar form (re0, re1, im0, im1):
-//   Yd [rows][S][ndp][4]       pair i = data symbols 2 i, 2 i + 1 of the OFDM symbol (odd Nd: the last pair's
-//                              second half belongs to no data symbol and is ignored here)
-//   Yp [rows][nslot][npp][4]   pair j = pilots 2 j, 2 j + 1 of every slot's first symbol
-// i.e. exactly the elements the receiver reads, each 16 bytes per thread and access.
+// The spectral link (spectral.cu) leaves the grid as exactly the elements the receiver reads:
+//   Yd [rows][S][2 ndp]       data symbol d of the OFDM symbol at element d (ndp = ceil(Nd / 2); with an odd Nd
+//                             the last element of a row is padding)
+//   Yp [rows][nslot][2 npp]   pilot i of every slot's first symbol at element i (npp = ceil(Np / 2))
 
 // LS estimate at the pilot positions only (core/lte_receiver.py:62-87 without the interpolation, which the
-// planar MRC kernel does per data bin): Hp [rows][nslot][Np] = (Yp [+ lazy AWGN]) / pilot.  One thread per pilot.
+// compact MRC kernel does per data bin): Hp [rows][nslot][Np] = (Yp [+ lazy AWGN]) / pilot.  One thread per pilot.
 template <bool NOISY>
 __global__ void __launch_bounds__(256)
-crs_ls_compact_kernel(const DevPlan P, const float* __restrict__ Yp, float2* __restrict__ Hp, int nslot, long long total,
+crs_ls_compact_kernel(const DevPlan P, const float2* __restrict__ Yp, float2* __restrict__ Hp, int nslot, long long total,
                       const AwgnArgs A) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= total) return;
@@ -524,8 +523,7 @@ crs_ls_compact_kernel(const DevPlan P, const float* __restrict__ Yp, float2* __r
     const long long rs = g / P.Np;                  // row * nslot + slot
     const int slot = (int)(rs % nslot);
     const long long row = rs / nslot;
-    const float* q = Yp + ((size_t)rs * P.npp + (i >> 1)) * 4 + (i & 1);
-    float2 yp = make_float2(q[0], q[2]);
+    float2 yp = Yp[(size_t)rs * (2 * P.npp) + i];
     if (NOISY) {
         const float sigma = lte_sigma(A.power[row], A.n_stream, A.snr_lin[row]);
         yp = awgn_at(A, sigma, row, slot * LTE_SLOT_SYMBOLS, P.N, P.pset_bin[i], yp);
@@ -533,7 +531,7 @@ crs_ls_compact_kernel(const DevPlan P, const float* __restrict__ Yp, float2* __r
     Hp[g] = cmul(yp, P.pset_inv[i]);
 }
 
-extern "C" int lte_crs_ls_compact(const lte_plan* p, const float* Ypilot, lte_c32* Hp, int64_t rows, int32_t S,
+extern "C" int lte_crs_ls_compact(const lte_plan* p, const lte_c32* Ypilot, lte_c32* Hp, int64_t rows, int32_t S,
                                   const lte_awgn_desc* awgn, void* stream) {
     if (!p || !Ypilot || !Hp || rows < 0 || S < 1) return LTE_ERR_INVALID_ARG;
     if (p->dev.Np == 0 || p->nsets != 1) return LTE_ERR_UNSUPPORTED;
@@ -546,129 +544,123 @@ extern "C" int lte_crs_ls_compact(const lte_plan* p, const float* Ypilot, lte_c3
     const long long grid = (total + 255) / 256;
     if (grid >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
     if (awgn)
-        crs_ls_compact_kernel<true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(p->dev, Ypilot, (float2*)Hp, nslot, total, A);
+        crs_ls_compact_kernel<true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(p->dev, (const float2*)Ypilot,
+                                                                                      (float2*)Hp, nslot, total, A);
     else
-        crs_ls_compact_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(p->dev, Ypilot, (float2*)Hp, nslot, total, A);
+        crs_ls_compact_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(p->dev, (const float2*)Ypilot,
+                                                                                       (float2*)Hp, nslot, total, A);
     LTE_CHECK_CUDA(cudaGetLastError());
     return LTE_OK;
 }
 
-// MRC + slicer + bit-error count on the planar layout (core/ofdm_core.py:1484-1532, core/modulator.py:90-112,
-// core/ofdm_core.py:245-268).  thread = (stream, data pair): it interpolates H of its two bins between their
+// MRC + slicer + bit-error count on the compact layout (core/ofdm_core.py:1484-1532, core/modulator.py:90-112,
+// core/ofdm_core.py:245-268).  thread = (stream, data symbol d): it interpolates H of its bin between the two
 // neighbouring pilots with the very operations of crs_ls_interp_kernel (edge hold, start + i * (delta / div)),
-// holds it for the slot, and walks the slot's symbols with one 128-bit load per antenna and symbol.  The
-// lazy AWGN draws are those of mrc_kernel, so the counts are bit-identical to the windowed layout.
+// holds it for the slot, and walks the slot's symbols with one 64-bit load per antenna and symbol (a warp reads 256
+// contiguous bytes).  The lazy-AWGN variant is bound by the noise generator (Philox + Box-Muller per output) and
+// lives on occupancy like mrc_kernel: one bin per thread, 64 registers, 8 CTAs / SM.  Measured alternatives on
+// the headline shape: planar pairs (re0, re1, im0, im1) read as two 32-bit loads 0.61 ms, two bins per thread with
+// 128-bit loads 0.61 ms, this layout 0.46 ms.  The draws are those of mrc_kernel, so the counts are bit-identical
+// to the windowed layout.
 template <int R, bool NOISY>
-__global__ void __launch_bounds__(128, NOISY ? 6 : 1)
-mrc_planar_kernel(const DevPlan P, const float4* __restrict__ Yd, const float2* __restrict__ Hp,
-                  const uint8_t* __restrict__ idx_tx, unsigned long long* __restrict__ errors, int S, int nslot,
-                  long long nbits, int gx, const AwgnArgs A) {
+__global__ void __launch_bounds__(128, NOISY ? 8 : 1)
+mrc_compact_kernel(const DevPlan P, const float2* __restrict__ Yd, const float2* __restrict__ Hp,
+                   const uint8_t* __restrict__ idx_tx, unsigned long long* __restrict__ errors, int S, int nslot,
+                   long long nbits, int gx, const AwgnArgs A) {
     const int chunk = blockIdx.x % gx;
     const long long b = blockIdx.x / gx;
-    const int i = chunk * blockDim.x + threadIdx.x;
+    const int d = chunk * blockDim.x + threadIdx.x;
     unsigned int e = 0;
-    if (i < P.ndp) {
-        const int d0 = 2 * i, d1 = 2 * i + 1;
-        const bool two = d1 < P.Nd;
-        const int kb[2] = {P.data_idx[d0], two ? P.data_idx[d1] : P.data_idx[d0]};
+    if (d < P.Nd) {
+        const int kb = P.data_idx[d];
         float sigma[R];
         if (NOISY) {
 #pragma unroll
             for (int r = 0; r < R; ++r) sigma[r] = lte_sigma(A.power[b * R + r], A.n_stream, A.snr_lin[b * R + r]);
         }
         const bool comb = NOISY && A.combine;
-        // pilot segment of either bin
+        // pilot segment of the bin
         const int cnt = P.pset_cnt[0];
-        int la[2], i1[2];
-        bool inner[2];
-        float div[2], t[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int lo = P.pset_seg[kb[q]];
-            la[q] = lo < 0 ? 0 : (lo >= cnt - 1 ? cnt - 1 : lo);
-            inner[q] = lo >= 0 && lo < cnt - 1;
-            i1[q] = P.pset_bin[la[q]];
-            div[q] = inner[q] ? (float)(P.pset_bin[la[q] + 1] - i1[q]) : 1.f;
-            t[q] = (float)(kb[q] - i1[q]);
-        }
+        const int lo = P.pset_seg[kb];
+        const int la = lo < 0 ? 0 : (lo >= cnt - 1 ? cnt - 1 : lo);
+        const bool inner = lo >= 0 && lo < cnt - 1;
+        const int i1 = P.pset_bin[la];
+        const float div = inner ? (float)(P.pset_bin[la + 1] - i1) : 1.f;
+        const float t = (float)(kb - i1);
         const int sym_bits = P.Nd * P.bps;
+        const int ystride = 2 * P.ndp;
         for (int slot = 0; slot < nslot; ++slot) {
-            float2 h[R][2];
-            float den[2] = {0.f, 0.f};
+            float2 h[R];
+            float den = 0.f;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const float2* hp = Hp + (((size_t)b * R + r) * nslot + slot) * P.Np;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const float2 a = hp[la[q]];
-                    float2 v = a;
-                    if (inner[q] && kb[q] != i1[q]) {
-                        const float2 c = hp[la[q] + 1];
-                        v = make_float2(fmaf(t[q], __fdiv_rn(c.x - a.x, div[q]), a.x), fmaf(t[q], __fdiv_rn(c.y - a.y, div[q]), a.y));
-                    }
-                    h[r][q] = v;
-                    den[q] += cabs2(v);
+                const float2 a = hp[la];
+                float2 v = a;
+                if (inner && kb != i1) {
+                    const float2 c = hp[la + 1];
+                    v = make_float2(fmaf(t, __fdiv_rn(c.x - a.x, div), a.x), fmaf(t, __fdiv_rn(c.y - a.y, div), a.y));
                 }
+                h[r] = v;
+                den += cabs2(v);
             }
-            float inv_den[2], csig[2] = {0.f, 0.f};
+            den += 1e-10f;
+            const float inv_den = __frcp_rn(den);
+            float csig = 0.f;
+            if (comb) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                den[q] += 1e-10f;
-                inv_den[q] = __frcp_rn(den[q]);
-                if (comb) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) csig[q] = fmaf(cabs2(h[r][q]), sigma[r] * sigma[r], csig[q]);
-                    csig[q] = sqrtf(csig[q]);
-                }
+                for (int r = 0; r < R; ++r) csig = fmaf(cabs2(h[r]), sigma[r] * sigma[r], csig);
+                csig = sqrtf(csig);
             }
             const int s0 = slot * LTE_SLOT_SYMBOLS, s_end = min(S, s0 + LTE_SLOT_SYMBOLS);
-            const float4* yp[R];
+            const float2* yp[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) yp[r] = Yd + (((size_t)b * R + r) * S + s0) * P.ndp + i;
-            const uint8_t* ip = idx_tx + ((size_t)b * S + s0) * P.Nd + d0;
-            const long long valid0 = nbits - ((long long)s0 * P.Nd + d0) * P.bps;   // bits left from (s0, d0) on
-            const bool all_valid = valid0 - (long long)(s_end - 1 - s0) * sym_bits >= 2 * P.bps;
-            float4 ya[R], yc[R];
-            unsigned ia0 = 0, ia1 = 0, ic0, ic1;
-            auto fetch = [&](int s) {
+            for (int r = 0; r < R; ++r) yp[r] = Yd + (((size_t)b * R + r) * S + s0) * ystride + d;
+            const uint8_t* ip = idx_tx + ((size_t)b * S + s0) * P.Nd + d;
+            const long long valid0 = nbits - ((long long)s0 * P.Nd + d) * P.bps;   // bits left from (s0, d) on
+            const bool all_valid = valid0 - (long long)(s_end - 1 - s0) * sym_bits >= P.bps;
+            auto fetch = [&](float2 (&y)[R], uint8_t& in, int s) {
+                in = 0;
                 if (s < s_end) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) { ya[r] = *yp[r]; yp[r] += P.ndp; }
-                    ia0 = ip[0];
-                    ia1 = two ? ip[1] : 0u;
+                    for (int r = 0; r < R; ++r) { y[r] = *yp[r]; yp[r] += ystride; }
+                    in = *ip;
                     ip += P.Nd;
                 }
             };
-            fetch(s0);
-            for (int s = s0; s < s_end; ++s) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) yc[r] = ya[r];
-                ic0 = ia0; ic1 = ia1;
-                fetch(s + 1);
-                float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+            auto combine = [&](float2 (&y)[R], uint8_t in, int s) {
+                float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    float2 y0 = make_float2(yc[r].x, yc[r].z), y1 = make_float2(yc[r].y, yc[r].w);
-                    if (NOISY && !comb) {
-                        y0 = awgn_at(A, sigma[r], b * R + r, s, P.N, kb[0], y0);
-                        if (two) y1 = awgn_at(A, sigma[r], b * R + r, s, P.N, kb[1], y1);
-                    }
-                    const float2 t0 = cmulc(h[r][0], y0), t1 = cmulc(h[r][1], y1);
-                    acc[0].x += t0.x; acc[0].y += t0.y;
-                    acc[1].x += t1.x; acc[1].y += t1.y;
+                    if (NOISY && !comb) y[r] = awgn_at(A, sigma[r], b * R + r, s, P.N, kb, y[r]);
+                    const float2 tt = cmulc(h[r], y[r]);
+                    acc.x += tt.x;
+                    acc.y += tt.y;
                 }
-                if (comb) {
-                    acc[0] = awgn_at(A, csig[0], b * R, s, P.N, kb[0], acc[0]);
-                    if (two) acc[1] = awgn_at(A, csig[1], b * R, s, P.N, kb[1], acc[1]);
+                if (comb) acc = awgn_at(A, csig, b * R, s, P.N, kb, acc);
+                const int dec = slice_symbol(P, make_float2(acc.x * inv_den, acc.y * inv_den));
+                e += all_valid ? __popc(dec ^ (int)in) : bit_errors(dec, in, P.bps, valid0 - (long long)(s - s0) * sym_bits);
+            };
+            float2 ya[R], yc[R];
+            uint8_t ia, ic;
+            fetch(ya, ia, s0);
+            if constexpr (!NOISY) {
+                // plain MRC is bandwidth bound: two register sets in ping-pong, no set is ever copied
+                for (int sg = s0; sg < s_end; sg += 2) {
+                    fetch(yc, ic, sg + 1);
+                    combine(ya, ia, sg);
+                    fetch(ya, ia, sg + 2);
+                    if (sg + 1 < s_end) combine(yc, ic, sg + 1);
                 }
-                const int dec0 = slice_symbol(P, make_float2(acc[0].x * inv_den[0], acc[0].y * inv_den[0]));
-                const int dec1 = slice_symbol(P, make_float2(acc[1].x * inv_den[1], acc[1].y * inv_den[1]));
-                if (all_valid) {
-                    e += __popc(dec0 ^ (int)ic0) + (two ? __popc(dec1 ^ (int)ic1) : 0);
-                } else {
-                    const long long v = valid0 - (long long)(s - s0) * sym_bits;
-                    e += bit_errors(dec0, (int)ic0, P.bps, v);
-                    if (two) e += bit_errors(dec1, (int)ic1, P.bps, v - P.bps);
+            } else {
+                // the lazy-AWGN variants are issue bound and live on occupancy: one prefetched set, copied into the
+                // working set every symbol
+                for (int sg = s0; sg < s_end; ++sg) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) yc[r] = ya[r];
+                    ic = ia;
+                    fetch(ya, ia, sg + 1);
+                    combine(yc, ic, sg);
                 }
             }
         }
@@ -676,37 +668,36 @@ mrc_planar_kernel(const DevPlan P, const float4* __restrict__ Yd, const float2* 
     block_add_errors(e, &errors[b]);
 }
 
-extern "C" int lte_mrc_demap_count_compact(const lte_plan* p, const float* Ydata, const lte_c32* Hp,
+extern "C" int lte_mrc_demap_count_compact(const lte_plan* p, const lte_c32* Ydata, const lte_c32* Hp,
                                            const uint8_t* idx_tx, unsigned long long* errors, int64_t nbits, int64_t B,
                                            int32_t R, int32_t S, const lte_awgn_desc* awgn, void* stream) {
     if (!p || !Ydata || !Hp || !idx_tx || !errors || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
     if (p->dev.Np == 0 || p->nsets != 1) return LTE_ERR_UNSUPPORTED;
-    if (((uintptr_t)Ydata & 15)) return LTE_ERR_INVALID_ARG;
     AwgnArgs A = {};
     int rc;
     if (awgn && (rc = make_awgn_args(A, p, awgn, S))) return rc;
     if (B == 0) return LTE_OK;
     const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
-    const int gx = (p->dev.ndp + 127) / 128;
+    const int gx = (p->dev.Nd + 127) / 128;
     const long long grid_ll = (long long)gx * B;
     if (grid_ll >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
     const unsigned grid = (unsigned)grid_ll;
     cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH_MRCP(RR)                                                                                               \
+#define LAUNCH_MRCC(RR)                                                                                               \
     case RR:                                                                                                         \
         if (awgn)                                                                                                    \
-            mrc_planar_kernel<RR, true><<<grid, 128, 0, st>>>(p->dev, (const float4*)Ydata, (const float2*)Hp, idx_tx, \
-                                                              errors, S, nslot, nbits, gx, A);                       \
-        else                                                                                                         \
-            mrc_planar_kernel<RR, false><<<grid, 128, 0, st>>>(p->dev, (const float4*)Ydata, (const float2*)Hp, idx_tx, \
+            mrc_compact_kernel<RR, true><<<grid, 128, 0, st>>>(p->dev, (const float2*)Ydata, (const float2*)Hp, idx_tx, \
                                                                errors, S, nslot, nbits, gx, A);                      \
+        else                                                                                                         \
+            mrc_compact_kernel<RR, false><<<grid, 128, 0, st>>>(p->dev, (const float2*)Ydata, (const float2*)Hp, idx_tx, \
+                                                                errors, S, nslot, nbits, gx, A);                     \
         break;
     switch (R) {
-        LAUNCH_MRCP(1) LAUNCH_MRCP(2) LAUNCH_MRCP(3) LAUNCH_MRCP(4) LAUNCH_MRCP(5) LAUNCH_MRCP(6) LAUNCH_MRCP(7)
-        LAUNCH_MRCP(8)
+        LAUNCH_MRCC(1) LAUNCH_MRCC(2) LAUNCH_MRCC(3) LAUNCH_MRCC(4) LAUNCH_MRCC(5) LAUNCH_MRCC(6) LAUNCH_MRCC(7)
+        LAUNCH_MRCC(8)
         default: return LTE_ERR_INVALID_ARG;
     }
-#undef LAUNCH_MRCP
+#undef LAUNCH_MRCC
     LTE_CHECK_CUDA(cudaGetLastError());
     return LTE_OK;
 }

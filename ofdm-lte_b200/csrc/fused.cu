@@ -232,11 +232,11 @@ static int fused_setup(const lte_plan* p, const lte_channel_desc* ch, int32_t B,
         C.w_cyc[nn] = ch->doppler_hz * cos(2.0 * M_PI * (double)(nn + 1) / LTE_JAKES_TONES) / p->desc.fs;
         if (fabs(C.w_cyc[nn]) > wmax) wmax = fabs(C.w_cyc[nn]);
     }
-    // one polynomial block per OFDM symbol; same truncation bounds as lte_channel_tdl
+    // one polynomial block per OFDM symbol, remainder kept below 5e-7 of |h| (1/20 of the 1e-5 parity budget):
+    // K = 1 is the economised linear fit (tdl.cuh), x^2/4; K = 2 / 4 are Taylor polynomials, x^3/6 and x^5/120
     const double x = M_PI * wmax * L;
-    // K = 1 uses the economised linear fit (tdl.cuh): remainder x^2/4 <= 5e-7 of |h|
     if (x <= 1.41e-3) U.K = 1;
-    else if (x <= 4.9e-3) U.K = 2;
+    else if (x <= 1.44e-2) U.K = 2;
     else if (x <= 0.075) U.K = 4;
     else return LTE_ERR_UNSUPPORTED;
     C.pb = L;

@@ -328,9 +328,9 @@ __device__ __forceinline__ void horner1(f2& hre, f2& him, f2 wre, f2 wim, f2 nwi
 // or unpacking instruction on the path.  The cyclic-prefix samples (time domain, power only) are spread over
 // the first cp / 32 warps.  Stream power stays in registers across the stream's symbols and leaves as one
 // atomic per warp and antenna.
-// PLANAR (the sweep's compact layout): a data pair leaves as ONE 128-bit store (re0, re1, im0, im1) into
-// Y [B*R][S][ndp][4]; pilot pairs only on every slot's first symbol, into Yp [B*R][slots][npp][4]; nothing
-// else is ever read downstream.  Otherwise Y is the windowed grid [B*R][S][nk] of interleaved complex.
+// PLANAR flag = the sweep's compact layout: a data pair leaves as ONE 128-bit store of two consecutive complex
+// values into Y [B*R][S][2 ndp]; pilot pairs only on every slot's first symbol, into Yp [B*R][slots][2 npp];
+// nothing else is ever read downstream.  Otherwise Y is the windowed grid [B*R][S][nk].
 template <int NT, int R2, bool PLANAR, bool Z0>
 __global__ void __launch_bounds__(32 * (SPEC_MAX_WARPS + 1), 1)
 channel_spectral_kernel(const DevPlan P, const SpecParams C, const uint8_t* __restrict__ idx,
@@ -598,8 +598,8 @@ channel_spectral_kernel(const DevPlan P, const SpecParams C, const uint8_t* __re
                         float a, c, d, e;
                         upk(yre[r], a, c);
                         upk(yim[r], d, e);
-                        if (isdat) stg128(gaddr(yb, (unsigned)(r * S) * (unsigned)P.ndp, 16u), a, c, d, e);
-                        else if (head) stg128(gaddr(pb, (unsigned)(r * nslot) * (unsigned)P.npp, 16u), a, c, d, e);
+                        if (isdat) stg128(gaddr(yb, (unsigned)(r * S) * (unsigned)P.ndp, 16u), a, d, c, e);
+                        else if (head) stg128(gaddr(pb, (unsigned)(r * nslot) * (unsigned)P.npp, 16u), a, d, c, e);
                     }
                 }
             } else {
@@ -713,7 +713,7 @@ extern "C" int64_t lte_channel_spectral_workspace_bytes(const lte_plan* p, const
 }
 
 extern "C" int lte_channel_spectral(const lte_plan* p, const lte_channel_desc* ch, const uint8_t* idx, const lte_c32* G,
-                                    const lte_c32* tail, const float* phases, void* Y, float* Ypilot,
+                                    const lte_c32* tail, const float* phases, lte_c32* Y, lte_c32* Ypilot,
                                     double* power, void* workspace, int32_t B, int32_t R, int32_t S, void* stream) {
     SpecParams C;
     int rc = spectral_setup(p, ch, R, C);

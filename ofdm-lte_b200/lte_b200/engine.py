@@ -284,8 +284,8 @@ class LinkEngine:
                          compact=False, out_pilots=None):
         """Channel side of the spectral link: -> (Y [B*R, S, Nc] noise-free on the occupied window,
         power [B, R]), or None when unsupported (use modulate + channel_rx_fft).
-        compact: -> ((Yd float32 [B*R, S, ndp, 4], Yp float32 [B*R, slots, npp, 4]), power): data bins and
-        slot-head pilot bins as planar pairs (re0, re1, im0, im1), see include/lte_b200.h."""
+        compact: -> ((Yd [B*R, S, 2 ndp], Yp [B*R, slots, 2 npp]), power): data bins in data-symbol order and
+        slot-head pilot bins, rows padded to an even length (see include/lte_b200.h)."""
         need = self.spectral_workspace_bytes(chan, B, R, S)
         if need is None:
             return None
@@ -299,8 +299,8 @@ class LinkEngine:
         Yp = None
         if compact:
             nslot = -(-S // nat.LTE_SLOT_SYMBOLS)
-            Y = out if out is not None else self._empty((B * R, S, self.ndp, 4), torch.float32)
-            Yp = out_pilots if out_pilots is not None else self._empty((B * R, nslot, self.npp, 4), torch.float32)
+            Y = out if out is not None else self._empty((B * R, S, 2 * self.ndp), torch.complex64)
+            Yp = out_pilots if out_pilots is not None else self._empty((B * R, nslot, 2 * self.npp), torch.complex64)
         else:
             Y = out if out is not None else self._empty((B * R, S, nk), torch.complex64)
         nat.check(nat.lib.lte_channel_spectral(self._plan, C.byref(chan), _ptr(idx), _ptr(G), _ptr(tail),
@@ -350,8 +350,8 @@ class LinkEngine:
         return H
 
     def estimate_compact(self, Yp, rows, S, out=None, awgn=None):
-        """LS estimate at the pilot positions of the compact layout: Yp float32 [rows, slots, npp, 4] ->
-        Hp complex64 [rows, slots, Np] (awgn: lazy frequency-domain AWGN, the draws of `estimate(..., awgn=...)`)."""
+        """LS estimate at the pilot positions of the compact layout: Yp [rows, slots, 2 npp] ->
+        Hp [rows, slots, Np] (awgn: lazy frequency-domain AWGN, the draws of `estimate(..., awgn=...)`)."""
         Hp = out if out is not None else self._empty((rows, Yp.shape[1], self.Np), torch.complex64)
         nat.check(nat.lib.lte_crs_ls_compact(self._plan, _ptr(Yp), _ptr(Hp), rows, S,
                                              C.byref(awgn) if awgn is not None else None, self._stream()),
@@ -697,8 +697,8 @@ class LinkEngine:
         return errors
 
     def mrc_demap_count_compact(self, Yd, Hp, idx_tx, B, R, S, nbits=None, errors=None, awgn=None):
-        """MRC + slicer + bit-error count on the compact layout (Yd [B*R, S, ndp, 4], Hp [B*R, slots, Np]): every
-        thread interpolates its own two bins between their pilots; counts are bit-identical to
+        """MRC + slicer + bit-error count on the compact layout (Yd [B*R, S, 2 ndp], Hp [B*R, slots, Np]): every
+        thread interpolates its own bin between its two pilots; counts are bit-identical to
         estimate + mrc_demap_count on the windowed layout."""
         if errors is None:
             errors = torch.zeros(B, dtype=torch.int64, device=self.device)
@@ -744,8 +744,8 @@ class LinkEngine:
                 nslot = -(-S // nat.LTE_SLOT_SYMBOLS)
                 ws['G'] = self._empty((B * S, nk), torch.complex64)
                 ws['tail'] = self._empty((B * S, self.cp), torch.complex64)
-                ws['Yd'] = self._empty((B * R, S, self.ndp, 4), torch.float32)
-                ws['Yp'] = self._empty((B * R, nslot, self.npp, 4), torch.float32)
+                ws['Yd'] = self._empty((B * R, S, 2 * self.ndp), torch.complex64)
+                ws['Yp'] = self._empty((B * R, nslot, 2 * self.npp), torch.complex64)
                 ws['Hp'] = self._empty((B * R, nslot, self.Np), torch.complex64)
         return ws['spectral']
 

@@ -17,10 +17,9 @@ CASES = [(20.0, '64-QAM', 'Pedestrian_A', 4, 14, 3.0), (5.0, 'QPSK', 'Pedestrian
          (2.5, '64-QAM', 'Vehicular_B', 8, 2, 2.0), (20.0, '16-QAM', 'Bad_Urban', 5, 2, 1.0)]
 
 
-def _unpair(P4, n):
-    """Planar bin pairs (re0, re1, im0, im1) [..., pairs, 4] -> complex [..., n]."""
-    c = torch.complex(P4[..., 0:2], P4[..., 2:4])
-    return c.reshape(*P4.shape[:-2], -1)[..., :n]
+def _unpair(Yc, n):
+    """Rows of the compact layout are padded to an even length: [..., 2 pairs] -> [..., n]."""
+    return Yc[..., :n]
 
 
 def _setup(bw, mod, prof, R, S, v, B=2, seed=5):

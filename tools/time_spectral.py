@@ -47,8 +47,8 @@ def main():
     out['tx_spectral_ms'] = timeit(lambda: eng.tx_spectral(S, idx, out_G=G, out_tail=tail))
     out['channel_spectral_ms'] = timeit(lambda: eng.channel_spectral(idx, G, tail, chan, B, R, S, ph, out=Y, power=power, workspace=ws))
     nslot = 1
-    Yd = torch.empty((B * R, S, eng.ndp, 4), dtype=torch.float32, device='cuda')
-    Yp = torch.empty((B * R, nslot, eng.npp, 4), dtype=torch.float32, device='cuda')
+    Yd = torch.empty((B * R, S, 2 * eng.ndp), dtype=torch.complex64, device='cuda')
+    Yp = torch.empty((B * R, nslot, 2 * eng.npp), dtype=torch.complex64, device='cuda')
     Hp = torch.empty((B * R, nslot, eng.Np), dtype=torch.complex64, device='cuda')
     errors = torch.zeros(B, dtype=torch.int64, device='cuda')
     out['channel_spectral_compact_ms'] = timeit(lambda: eng.channel_spectral(idx, G, tail, chan, B, R, S, ph, out=Yd, power=power,
