@@ -601,19 +601,22 @@ class OFDMSimulator:
     # ------------------------------------------------------------------ sweeps
     def run_ber_sweep(self, num_bits: int, snr_range, num_trials: int = 1,
                       progress_callback: Optional[callable] = None) -> Dict:
-        """reference :1795-1846 (one random bit vector, SISO).  With rng='philox' on the plain LTE chain the
-        whole SNR x trials grid is one batch of streams through LinkEngine.siso_ber (same bits, independent
+        """reference :1795-1846 (one random bit vector, SISO).  With rng='philox' on the LTE chain (OFDM or
+        SC-FDM) the whole SNR x trials grid is one batch of streams through LinkEngine.siso_ber (same bits, independent
         channel / noise draws per point and trial); with rng='numpy' every point replays the reference's draws
         call by call."""
         bits = np.random.randint(0, 2, num_bits)
         snr_values = np.atleast_1d(snr_range)
-        if (self._draws.kind == 'philox' and self.mode == 'lte' and not self.enable_sc_fdm and self.enable_equalization
-                and num_bits > 0):
+        if self._draws.kind == 'philox' and self.mode == 'lte' and self.enable_equalization and num_bits > 0:
             eng = self._engine()
             b_t = be.as_bits_tensor(bits)
             S = eng.symbols_for_bits(num_bits)
             idx1 = eng.bits_to_indices(b_t, num_bits, S)
-            _, _, stats = eng.modulate(S, idx=idx1, want_stats=True)
+            if self.enable_sc_fdm:
+                pre = eng.dft_m(eng.qam_map(idx1).view(S, eng.Nd), eng.Nd).view(1, -1)
+                _, _, stats = eng.modulate(S, symbols=pre, want_stats=True)
+            else:
+                _, _, stats = eng.modulate(S, idx=idx1, want_stats=True)
             papr_db = float(self.tx._papr_from_stats(be.to_numpy(stats)[0], S * eng.L)['papr_db'])
             n_snr = len(snr_values)
             B = n_snr * num_trials
@@ -621,7 +624,7 @@ class OFDMSimulator:
                                 device=idx1.device).repeat(num_trials).contiguous()
             err = eng.siso_ber(self.channels[0]._chan_desc(), rows, S, self._draws.seed,
                                stream_id0=self._draws.next_stream() * B, idx=idx1.expand(B, -1).contiguous(),
-                               nbits=num_bits)
+                               nbits=num_bits, sc_fdm=self.enable_sc_fdm)
             ber = be.to_numpy(err.view(num_trials, n_snr).double().mean(dim=0)) / num_bits
             if progress_callback:
                 progress_callback(100, f"{B} streams in one batch")

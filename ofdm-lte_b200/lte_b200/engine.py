@@ -435,14 +435,28 @@ class LinkEngine:
         self.launches += 1
         return out
 
-    def siso_ber(self, chan, snr_lin_rows, S, seed, stream_id0=0, idx=None, nbits=None):
+    def siso_ber(self, chan, snr_lin_rows, S, seed, stream_id0=0, idx=None, nbits=None, sc_fdm=False, noise_domain=1,
+                 papr_hist=None, papr_lo=0.0, papr_step=0.1):
         """One pass of the SISO chain with the zero-forcing equaliser Y / (H + 1e-6)
         (reference simulate_siso, core/ofdm_core.py:660-737) over B independent streams: what the GUIs
-        run for num_rx = 1.  AWGN on the kept bins in the RX epilogue (noise_domain 1)."""
+        run for num_rx = 1.  noise_domain 1: AWGN on the kept bins in the RX epilogue; 0: per time sample,
+        the very draws of the per-call API with rng='philox' (stream b = call with stream id stream_id0 + b).
+        sc_fdm: SC-FDM uplink (reference enable_sc_fdm=True): the Nd data symbols of every OFDM symbol go
+        through the unitary Nd-point DFT before the grid (core/dft_precoding.py:67-93) and through its
+        inverse after the equaliser (core/lte_receiver.py:319-333).
+        papr_hist (int64 [bins], accumulated): histogram of the per-OFDM-symbol PAPR in dB of the useful
+        samples (core/ofdm_system.py:173-229), taken in the TX kernel's epilogue -- BER and PAPR in one pass."""
         B = snr_lin_rows.shape[0]
         if idx is None:
             idx = self.random_indices(B, S, seed, stream_id0)
-        tx, _, _ = self.modulate(S, idx=idx, want_stats=False)
+        symbols = None
+        if sc_fdm:
+            symbols = self.dft_m(self.qam_map(idx).view(B * S, self.Nd), self.Nd).view(B, S * self.Nd)
+        if papr_hist is not None:
+            _, _, tx = self.modulate_papr(S, idx=None if sc_fdm else idx, symbols=symbols, write_tx=True,
+                                          hist=papr_hist, hist_lo=papr_lo, hist_step=papr_step, want_db=False)
+        else:
+            tx, _, _ = self.modulate(S, idx=None if sc_fdm else idx, symbols=symbols, want_stats=False)
         if chan.num_taps > 0:
             ph = self.random_phases(B, chan.num_taps * nat.LTE_JAKES_TONES, seed, stream_id0)
             rx, power = self.channel(tx, chan, B, 1, phases=ph)
@@ -450,9 +464,11 @@ class LinkEngine:
             _, power = self.channel(tx, chan, B, 1)
             rx = tx
         Y = self.rx_fft(rx, B, S, nat.WINDOW_USEFUL, power=power, snr_lin=snr_lin_rows, seed=seed,
-                        row_id0=stream_id0, noise_domain=1)
+                        row_id0=stream_id0, noise_domain=noise_domain)
         H = self.estimate(Y, B, S, nat.WINDOW_USEFUL)
         data = self.zf(Y, H, B, S, nat.WINDOW_USEFUL)
+        if sc_fdm:
+            data = self.dft_m(data.view(B * S, self.Nd), self.Nd, inverse=True).view(B, S * self.Nd)
         errors, _ = self.demap_count(data, idx_tx=idx, nbits=nbits)
         return errors
 
@@ -710,6 +726,16 @@ class LinkEngine:
                                                       self._stream()), 'lte_mrc_demap_count_compact')
         self.launches += 1
         return errors
+
+    # ------------------------------------------------------------------ host-buffer front end
+    def stream_host_batches(self, chan, num_rx, snr_lin_rows, B, S, nbits=None, seed=0, noise_domain=3, fused=True,
+                            depth=2):
+        """Pipeline that takes payload batches from HOST memory (np.packbits rows, ideally pinned) and returns the
+        per-stream bit-error counts in pinned host memory, overlapping the H2D copy of the next batch with the
+        kernels of the current one (lte_b200/host_stream.py)."""
+        from .host_stream import HostBatchPipeline
+        return HostBatchPipeline(self, chan, num_rx, snr_lin_rows, B, S, nbits=nbits, seed=seed,
+                                 noise_domain=noise_domain, fused=fused, depth=depth)
 
     # ------------------------------------------------------------------ batched SIMO chain
     def workspace(self, B, S, R, fading, fused=False, lazy=False):

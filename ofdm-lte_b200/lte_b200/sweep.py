@@ -44,26 +44,88 @@ def run_sweep(count_batch, n_snr, n_trials, bits_per_stream, batch_trials=256, r
     return {'errors': errors, 'bits': bits, 'ber': errors.double() / bits.clamp(min=1).double()}
 
 
+NOISE_DOMAINS = {'time': 0, 'bins': 1, 'lazy': 2, 'combined': 3}
+
+
 def simo_sweep(engine, chan, snr_db, n_trials, num_rx, symbols_per_stream=14, seed=0, batch_trials=256,
-               rank=0, world=1, noise_domain=1, fused=False):
+               rank=0, world=1, noise_domain='lazy', fused=True, bits_host=None):
     """BER of the SIMO-MRC chain at every SNR point, `n_trials` independent streams per point.
-    noise_domain / fused: see LinkEngine.simo_ber."""
+
+    The default is the engine's fast path: spectral link at low Doppler, fused channel + RX-FFT kernel
+    otherwise, staged kernels where neither applies (the engine falls back by itself), with the AWGN added
+    lazily by the consumers -- the same draws, hence bit-identical counts, as noise on the kept bins
+    (`'bins'`).  `'combined'` draws one equivalent noise sample per MRC output instead of one per antenna
+    (same BER statistics, different sample values, 1/R of the generator work): opt in by name.
+    noise_domain: 'time' | 'bins' | 'lazy' | 'combined' (or LinkEngine.simo_ber's 0..3).
+    bits_host: payload source in HOST memory instead of on-device random bits -- callable (trial_lo, n) ->
+    uint8 [n * n_snr, ceil(nbits / 8)] of np.packbits() rows (ideally a pinned tensor); batches then go
+    through LinkEngine.stream_host_batches (H2D of the next batch overlaps the current one)."""
     n_snr = len(snr_db)
     S, R = symbols_per_stream, num_rx
+    nd = NOISE_DOMAINS[noise_domain] if isinstance(noise_domain, str) else int(noise_domain)
     snr_lin = torch.tensor([10 ** (s / 10) for s in snr_db], dtype=torch.float32, device=engine.device)
+    nbits = S * engine.Nd * engine.bps
+    if bits_host is not None:
+        lo, hi = shard_range(n_trials, rank, world)
+        counts = torch.zeros((2, n_snr), dtype=torch.int64)
+        nb = min(batch_trials, max(hi - lo, 1))
+        pipe = engine.stream_host_batches(chan, R, snr_lin.repeat(nb).repeat_interleave(R).contiguous(), nb * n_snr, S,
+                                          nbits=nbits, seed=seed, noise_domain=nd)
+
+        def batches():
+            t = lo
+            while t < hi:
+                n = min(nb, hi - t)
+                bits = bits_host(t, n)
+                if n < nb:                                   # ragged last batch: pad with copies, count only the real rows
+                    bits = torch.cat([bits, bits[:1].expand((nb - n) * n_snr, -1)])
+                yield bits, t * n_snr, n
+                t += n
+        for err, n in pipe.run(batches()):
+            counts[0] += err[:n * n_snr].view(n, n_snr).sum(dim=0)
+            counts[1] += n * nbits
+        counts = counts.to(engine.device)
+        reduce_counts(counts)
+        errors, bits = counts[0].cpu(), counts[1].cpu()
+        return {'errors': errors, 'bits': bits, 'ber': errors.double() / bits.clamp(min=1).double()}
     state = {}
 
     def count_batch(trial_lo, n):
         B = n * n_snr
         if state.get('B') != B:
             state['B'] = B
-            state['ws'] = engine.workspace(B, S, R, fading=chan.num_taps > 0, fused=fused)
+            state['ws'] = engine.workspace(B, S, R, fading=chan.num_taps > 0, fused=fused, lazy=fused)
             state['snr_rows'] = snr_lin.repeat(n).repeat_interleave(R).contiguous()
         return engine.simo_ber(state['ws'], chan, state['snr_rows'], seed, stream_id0=trial_lo * n_snr,
-                               noise_domain=noise_domain, fused=fused).clone()
+                               noise_domain=nd, fused=fused).clone()
 
-    return run_sweep(count_batch, n_snr, n_trials, S * engine.Nd * engine.bps, batch_trials, rank, world,
-                     engine.device)
+    return run_sweep(count_batch, n_snr, n_trials, nbits, batch_trials, rank, world, engine.device)
+
+
+def scfdm_sweep(engine, chan, snr_db, n_trials, symbols_per_stream=14, seed=0, batch_trials=256, rank=0, world=1,
+                papr_bins=200, papr_lo=0.0, papr_step=0.1, sc_fdm=True):
+    """BASELINE config 2: BER + PAPR CCDF of the SISO SC-FDM uplink (reference simulate_siso with
+    enable_sc_fdm=True, core/ofdm_core.py:660-737; PAPR per OFDM symbol as OFDMSystem.calculate_papr_without_cp,
+    core/ofdm_system.py:173-229) in ONE pass per batch: the TX kernel's epilogue bins the PAPR of every OFDM
+    symbol it produces.  Trials shard over ranks like simo_sweep; the histogram is all-reduced with the counters.
+    Returns run_sweep's dict + 'papr_hist' [papr_bins], 'papr_edges_db', 'papr_ccdf' (P[PAPR > edge])."""
+    n_snr = len(snr_db)
+    S = symbols_per_stream
+    snr_lin = torch.tensor([10 ** (s / 10) for s in snr_db], dtype=torch.float32, device=engine.device)
+    hist = torch.zeros(papr_bins, dtype=torch.int64, device=engine.device)
+
+    def count_batch(trial_lo, n):
+        return engine.siso_ber(chan, snr_lin.repeat(n).contiguous(), S, seed, stream_id0=trial_lo * n_snr, sc_fdm=sc_fdm,
+                               papr_hist=hist, papr_lo=papr_lo, papr_step=papr_step)
+
+    out = run_sweep(count_batch, n_snr, n_trials, S * engine.Nd * engine.bps, batch_trials, rank, world, engine.device)
+    reduce_counts(hist)
+    h = hist.cpu()
+    tot = max(int(h.sum()), 1)
+    out['papr_hist'] = h
+    out['papr_edges_db'] = papr_lo + papr_step * torch.arange(papr_bins + 1, dtype=torch.float64)
+    out['papr_ccdf'] = 1.0 - torch.cumsum(h.double(), 0) / tot        # P[PAPR >= upper edge of bin i]
+    return out
 
 
 def simo_sweep_shared_channel(engine, chan, snr_db, n_trials, num_rx, symbols_per_stream=14, seed=0, batch_trials=4096,

@@ -184,3 +184,42 @@ def test_two_rank_coded_sweep_equals_single_rank(tmp_path):
     multi = torch.load(out, weights_only=False)
     assert torch.equal(multi['errors'], single['errors']) and torch.equal(multi['block_errors'], single['block_errors'])
     assert torch.equal(multi['bler'], single['bler']) and torch.equal(single['bits'], torch.tensor([29 * 20] * 2))
+
+
+class _FakeScfdmEngine:
+    """CPU stand-in for scfdm_sweep: errors and the PAPR bin of a stream's symbols depend only on the global
+    stream id, so the gloo reduction of counters + histogram can be checked exactly."""
+    device = torch.device('cpu')
+    Nd, bps = 6, 4
+
+    def siso_ber(self, chan, snr_lin_rows, S, seed, stream_id0=0, sc_fdm=False, papr_hist=None, papr_lo=0.0,
+                 papr_step=0.1, **kw):
+        assert sc_fdm
+        sid = torch.arange(stream_id0, stream_id0 + snr_lin_rows.shape[0], dtype=torch.int64)
+        db = ((sid[:, None] * S + torch.arange(S)[None, :]) * 2654435761 % 701).float() / 100.0
+        b = torch.clamp(torch.floor((db - papr_lo) / papr_step).long(), 0, papr_hist.numel() - 1)
+        papr_hist += torch.bincount(b.reshape(-1), minlength=papr_hist.numel())
+        return sid * 40503 % 17
+
+
+def _scfdm_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    sweep = _load_sweep()
+    r = sweep.scfdm_sweep(_FakeScfdmEngine(), None, [0.0, 6.0, 12.0], 31, symbols_per_stream=3, batch_trials=5,
+                          papr_bins=40, papr_step=0.2, rank=rank, world=world)
+    if rank == 0:
+        torch.save(r, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_scfdm_sweep_equals_single_rank(tmp_path):
+    sweep = _load_sweep()
+    single = sweep.scfdm_sweep(_FakeScfdmEngine(), None, [0.0, 6.0, 12.0], 31, symbols_per_stream=3, batch_trials=31,
+                               papr_bins=40, papr_step=0.2)
+    out = str(tmp_path / 's.pt')
+    mp.spawn(_scfdm_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    multi = torch.load(out, weights_only=False)
+    assert torch.equal(multi['errors'], single['errors']) and torch.equal(multi['bits'], single['bits'])
+    assert torch.equal(multi['papr_hist'], single['papr_hist']) and int(single['papr_hist'].sum()) == 31 * 3 * 3
+    assert torch.equal(multi['papr_ccdf'], single['papr_ccdf'])
