@@ -444,6 +444,12 @@ int lte_mrc_demap_count(const lte_plan*, const lte_c32* Y, const lte_c32* H, con
                         unsigned long long* errors, int window, int64_t nbits, int64_t B, int32_t R,
                         int32_t S, void* stream);
 
+/* Measurement helper (bench.py's compute roofline): launches a register-only loop of independent packed
+ * fp32 multiply-adds (fma.rn.f32x2, the instruction the FMA-bound kernels of this library issue) on the current
+ * device and returns the flops of that launch (< 0: LTE_ERR_*); the caller times the launch with CUDA events.
+ * sink: (SM count * 8 * 256) floats of scratch. */
+int64_t lte_fp32_peak_launch(float* sink, int32_t iters, void* stream);
+
 /* Engine helper: Philox-generated uniform symbol indices [B][nsym] keyed (seed, stream id). */
 int lte_random_indices(const lte_plan*, uint8_t* idx, int64_t nsym, int64_t B, uint64_t seed,
                        uint64_t stream_id0, void* stream);

@@ -259,3 +259,35 @@ extern "C" int lte_plan_window(const lte_plan* p, int window, int32_t* k0, int32
     else return LTE_ERR_INVALID_ARG;
     return LTE_OK;
 }
+
+// ------------------------------------------------------------------------------ measurement helper
+// Peak packed-fp32 throughput of the device as the kernels of this library see it: independent chains of
+// fma.rn.f32x2 (FFMA2), 8 per thread, no memory traffic.  bench.py times one launch with CUDA events and divides:
+// flops = grid * 256 threads * iters * 8 instructions * 4 (two lanes x multiply-add).  The compute roofline of the
+// FMA-bound kernels is quoted against this number, measured on the box the bench runs on.
+__global__ void __launch_bounds__(256)
+fp32_peak_kernel(float* __restrict__ sink, int iters, float s) {
+    unsigned long long p[8];
+    const unsigned long long pb = ((unsigned long long)__float_as_uint(s) << 32) | __float_as_uint(s);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = (unsigned long long)(threadIdx.x + i + 1) * 0x100000001ull;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(p[i]) : "l"(pb));
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r += __uint_as_float((unsigned)p[i]) + __uint_as_float((unsigned)(p[i] >> 32));
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+extern "C" int64_t lte_fp32_peak_launch(float* sink, int32_t iters, void* stream) {
+    if (!sink || iters < 1) return LTE_ERR_INVALID_ARG;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return LTE_ERR_CUDA;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = sms * 8;
+    fp32_peak_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sink, iters, 1.0001f);
+    if (cudaGetLastError() != cudaSuccess) return LTE_ERR_CUDA;
+    return (int64_t)grid * 256 * (int64_t)iters * 8 * 4;        // flops of this launch
+}

@@ -89,6 +89,7 @@ _SIGS = {
     'lte_mimo_detect': ([_P, _P, _P, _P, _I32, _I32, C.c_double, _I32, _P, C.c_int, _I64, _I32, _I32, _P], C.c_int),
     'lte_demap_count': ([_P, _P, _P, _P, _P, _I64, _I64, _I64, _P], C.c_int),
     'lte_mrc_demap_count': ([_P, _P, _P, _P, _P, C.c_int, _I64, _I64, _I32, _I32, _P], C.c_int),
+    'lte_fp32_peak_launch': ([_P, _I32, _P], C.c_int64),
     'lte_random_indices': ([_P, _P, _I64, _I64, _U64, _U64, _P], C.c_int),
     'lte_random_phases': ([_P, _I64, _I64, _U64, _U64, _P], C.c_int),
     'lte_tb_encode': ([_P, _I64, _P, _I32, _I64, _I64, _P, _P, _P, _P, _P, _P, _I64, _P], C.c_int),

@@ -20,14 +20,19 @@ def draws_to_device(phases, z):
 
 
 def run_chain(num, bits, snr_db, R, channel_type, itu_profile, velocity_kmh, phases, z, mode='lte',
-              equalize=True, combine='mrc', window=nat.WINDOW_FULL):
+              equalize=True, combine='mrc', window=nat.WINDOW_FULL, sc_fdm=False):
     """Returns a dict of numpy arrays mirroring oracle.simulate_siso / simulate_simo."""
     eng = LinkEngine(num.N, num.Nc, num.cp_length, num.bits_per_symbol, num.fs, mode=mode)
     nbits = len(bits)
     S = eng.symbols_for_bits(nbits)
     bits_d = to_dev(np.asarray(bits, dtype=np.uint8)[None, :], torch.uint8)
     idx = eng.bits_to_indices(bits_d, nbits, S)
-    tx, qam, stats = eng.modulate(S, idx=idx, want_qam=True)
+    if sc_fdm:      # SC-FDM: Nd-point unitary DFT of every OFDM symbol's data before the grid (core/dft_precoding.py:67-93)
+        qam = eng.qam_map(idx)
+        pre = eng.dft_m(qam.view(S, eng.Nd), eng.Nd).view(1, -1)
+        tx, _, stats = eng.modulate(S, symbols=pre)
+    else:
+        tx, qam, stats = eng.modulate(S, idx=idx, want_qam=True)
     chan = chan_for(channel_type, num.fs, itu_profile, 2.0, velocity_kmh)
     u, zc = draws_to_device(phases, z)
     faded, power = eng.channel(tx, chan, 1, R, phases=u)
@@ -47,6 +52,9 @@ def run_chain(num, bits, snr_db, R, channel_type, itu_profile, velocity_kmh, pha
             sym = eng.mrc(Y, H, 1, R, S, window)
         else:
             sym = eng.zf(Y, H if equalize else None, 1, S, window)
+            out['symbols_zf'] = sym.cpu().numpy().reshape(-1)
+            if sc_fdm:  # ... and its inverse after the equaliser (core/lte_receiver.py:319-333)
+                sym = eng.dft_m(sym.view(S, eng.Nd), eng.Nd, inverse=True).view(1, -1)
     errors, idx_rx = eng.demap_count(sym, idx_tx=idx, nbits=nbits, want_idx=True)
     bits_rx = eng.indices_to_bits(idx_rx, nbits)
     torch.cuda.synchronize()

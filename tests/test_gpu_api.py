@@ -12,12 +12,15 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-def _bits_close(got, want, symbols, modulation, bps):
+def _bits_close(got, want, symbols, modulation, bps, n_subframes=1):
+    """Identical bits, or every differing symbol lies within 1e-5 of a slicer boundary AND there are no more of
+    them than SURVEY section 7 expects of an fp32 pipeline against fp64 (about one per subframe at 1e-5)."""
     if np.array_equal(got, want):
         return True
     from gpu_chain import boundary_distance
     bad = np.unique(np.flatnonzero(got != want) // bps)
-    return bool(np.all(boundary_distance(np.asarray(symbols, dtype=complex), modulation)[bad] < 1e-4))
+    near = boundary_distance(np.asarray(symbols, dtype=complex), modulation)[bad] < TOL
+    return bool(np.all(near)) and len(bad) <= max(1, int(np.ceil(n_subframes)))
 
 
 def _make_sim(case, **extra):
@@ -44,7 +47,8 @@ def test_simulate_siso_matches_reference(case, capsys):
         assert r['transmitted_bits'] == len(bits) and isinstance(r['errors'], int) and isinstance(r['ber'], float)
         assert abs(r['papr_db'] - float(g[f'papr_db_{snr}'])) < 1e-4
         want = golden_bits_rx(g, snr)
-        assert _bits_close(r['bits_received_array'], want, r['symbols_rx'], cfg.modulation, cfg.bits_per_symbol)
+        assert _bits_close(r['bits_received_array'], want, r['symbols_rx'], cfg.modulation, cfg.bits_per_symbol,
+                           n_subframes=max(len(r['symbols_tx']) / 14.0, 1.0))
         assert abs(r['errors'] - int(g[f'errors_{snr}'])) <= np.count_nonzero(r['bits_received_array'] != want)
         if snr == case['full_snr']:
             assert rel_err(r['signal_tx'], g['signal_tx']) < TOL
@@ -52,7 +56,10 @@ def test_simulate_siso_matches_reference(case, capsys):
             sr, sg = r['symbols_rx'], g['symbols_rx']
             elem = np.abs(sr - sg) / np.maximum(np.abs(sg), 1e-30)
             assert np.median(elem) < TOL
-            assert np.quantile(elem, 0.99) < 100 * TOL      # ZF bins in deep fades amplify fp32 rounding
+            # ZF bins in deep fades amplify the fp32 rounding of H by 1 / |H|: at most 3 % of the symbols may
+            # exceed the budget, none by more than two orders of magnitude
+            assert np.mean(elem > TOL) < 0.03
+            assert np.quantile(elem, 0.99) < 100 * TOL
 
 
 @pytest.mark.parametrize('case', SIMO_CASES, ids=lambda c: c['name'])
@@ -64,7 +71,7 @@ def test_simulate_simo_matches_reference(case):
         r = sim.simulate_simo(bits, snr_db=snr, num_rx=case['R'], parallel=False)
         want = golden_bits_rx(g, snr)
         assert _bits_close(r['bits_received_array'], want, r['symbols_rx_combined'], cfg.modulation,
-                           cfg.bits_per_symbol)
+                           cfg.bits_per_symbol, n_subframes=max(len(r['symbols_rx_combined']) / (14.0 * 62), 1.0))
         assert abs(r['errors'] - int(g[f'errors_{snr}'])) <= np.count_nonzero(r['bits_received_array'] != want)
         assert r['num_rx'] == case['R'] and r['diversity_level'] == case['R'] and r['combining_method'] == 'mrc'
         assert len(r['signal_rx_list']) == case['R'] and len(r['symbols_rx_list']) == case['R']

@@ -37,6 +37,10 @@ def assert_zf_close(got, want, o, num, case):
     good = h >= 0.05 * np.median(h)
     assert good.mean() > 0.9
     assert rel_err(got[good], want[good]) < TOL
+    # the bins that needed the conditioning-scaled bound are few: a Rayleigh |H| falls below 5 % of its median
+    # with probability 1 - exp(-ln2 * 0.05^2) = 0.17 %; interpolated estimates spread that over neighbours
+    elem0 = np.abs(got - want) / np.maximum(np.abs(want), 1e-30)
+    assert np.mean(elem0 > TOL) < 0.03
     elem = np.abs(got - want) / np.maximum(np.abs(want), 1e-30)
     assert np.median(elem) < TOL / 10
     assert np.all(elem * (h / np.median(h)) < 10 * TOL)
@@ -45,8 +49,6 @@ def assert_zf_close(got, want, o, num, case):
 @pytest.mark.parametrize('case', SISO_CASES, ids=lambda c: c['name'])
 def test_siso_chain_matches_oracle(case):
     from gpu_chain import run_chain
-    if case.get('sc_fdm'):
-        pytest.skip('SC-FDM chain is exercised through the API in test_gpu_api.py')
     g = load_golden(case['name'])
     bits = golden_bits(g)
     num = numerology(case)
@@ -61,12 +63,21 @@ def test_siso_chain_matches_oracle(case):
             phases, z = reference_draws(case, S * num.L, 1)
         o = oracle_siso(case, bits, snr, phases=phases[0], z=(z[0][0], z[0][1]))
         r = run_chain(num, bits, snr, 1, case['ch'], case['prof'], case['v'], phases, z, mode=mode,
-                      equalize=case.get('equalize', True), combine='zf')
+                      equalize=case.get('equalize', True), combine='zf', sc_fdm=case.get('sc_fdm', False))
         assert np.array_equal(r['qam'], o['symbols_tx'].reshape(-1).astype(np.complex64))   # bit-exact map
         assert rel_err(r['signal_tx'], o['signal_tx']) < TOL
         assert rel_err(r['signal_rx'][0], o['signal_rx']) < TOL
         assert rel_err(r['Y'][0], o['Y']) < TOL
-        assert_zf_close(r['symbols'], o['symbols_rx'], o, num, case)
+        if case.get('sc_fdm'):
+            # equaliser output before the IDFT against the oracle's, with the conditioning-aware bound; then the
+            # Nd-point IDFT stage by itself against numpy on the very same input (core/lte_receiver.py:319-333)
+            data_idx, _ = O.grid_indices(num.N, num.Nc)
+            assert_zf_close(r['symbols_zf'], O.zf_equalize(o['Y'], o['H'])[:, data_idx].reshape(-1), o, num, case)
+            zf = r['symbols_zf'].astype(np.complex128).reshape(S, -1)
+            assert rel_err(r['symbols'], O.dft_precode(zf, inverse=True).reshape(-1)) < 2e-6
+            assert np.median(np.abs(r['symbols'] - o['symbols_rx']) / np.maximum(np.abs(o['symbols_rx']), 1e-30)) < TOL
+        else:
+            assert_zf_close(r['symbols'], o['symbols_rx'], o, num, case)
         papr_db = 10 * np.log10(r['stats'][0, 0] / (r['stats'][0, 1] / (S * num.L)))
         assert abs(papr_db - o['papr_db']) < 1e-4
         # demap of the oracle's own symbols (cast to fp32) is bit-exact by construction

@@ -6,7 +6,10 @@ python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
 python - <<PY
 import json
 d = json.load(open("gpurun_out/bench_$tag.json"))
-print(round(d["value"]), d["ms_per_step"], round(d["e2e"]["value"]))
+print(round(d["value"]), d["ms_per_step"], round(d["e2e"]["value"]), d["pipeline"])
 print({k: round(v["ms"], 4) for k, v in d["stages"].items()})
+print(d["roofline"])
+print(d["extra"])
+print(d["cpu_baseline"], d["cpu_baseline_reference"])
 PY
-cat gpurun_out/pytest_$tag.log
+cat gpurun_out/pytest_$tag.log; tail -5 gpurun_out/bench_$tag.err
