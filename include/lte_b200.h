@@ -16,6 +16,9 @@
  *    undefined afterwards).  No entry point allocates, frees or synchronises, so one plan
  *    may be used from several CUDA streams at once (with one workspace per stream).
  *  - No environment variable changes what a kernel computes.
+ *  - Random draws are Philox2x32-10 keyed (seed, stream or row id, sample); ids are 32-bit counter words.  A call
+ *    whose ids (id0 + count) would pass 2^32 returns LTE_ERR_UNSUPPORTED instead of silently repeating draws:
+ *    use a new seed for the next 2^32 streams.
  *  - Launches are asynchronous on `stream` (a cudaStream_t passed as void*).
  *  - Complex samples are interleaved float pairs (re, im): `lte_c32`.
  *  - A "stream" is one link realisation: S OFDM symbols back to back, L = N + cp
@@ -152,7 +155,10 @@ int lte_histogram(const float* x, int64_t n, float lo, float step, int32_t bins,
  * SC_FDMDecodifier wrappers (core/dft_precoding.py:67-93, :188-216, :254-348):
  * out[r][k] = sum_n in[r][n] exp(-+ j 2 pi k n / M) / sqrt(M) for every row of M symbols
  * (inverse != 0 selects the + sign).  Any M <= 1024 (Bluestein chirp-z on the power-of-two
- * FFT core; the LTE data-subcarrier counts 62..999 are not 2-3-5 smooth). */
+ * FFT core; the LTE data-subcarrier counts 62..999 are not 2-3-5 smooth).  The chirp tables of an M are
+ * plan state: lte_plan_add_dft(plan, M) builds them once (synchronous, like lte_plan_create); lte_dft_m on an
+ * M the plan does not hold returns LTE_ERR_INVALID_ARG. */
+int lte_plan_add_dft(lte_plan* plan, int32_t M);
 int lte_dft_m(const lte_plan*, const lte_c32* in, lte_c32* out, int32_t M, int32_t inverse,
               int64_t rows, void* stream);
 

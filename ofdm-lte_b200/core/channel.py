@@ -211,6 +211,10 @@ class ChannelSimulator:
             else:
                 sid = draws.next_stream()
                 ut = eng.random_phases(1, num_rx * T * taps * 16, draws.seed, sid)
+                # the reported channel matrix is the first tap's Jakes sum at sample 0 (reference impulse_response(N=1)):
+                # with Philox draws it comes from the link's own phases instead of a second, unrelated draw
+                u0 = be.to_numpy(ut.reshape(num_rx, T, taps, 16)[:, :, 0, :]).astype(np.float64)
+                Hc = float(10 ** (ray.gains[0] / 20)) * np.sqrt(2 / 16) * np.sum(np.exp(2j * np.pi * u0), axis=-1)
             faded, power = eng.channel(tx_t, chan, 1, num_rx, T=T, phases=ut)
             acc = faded.reshape(num_rx, n)
         else:

@@ -138,15 +138,7 @@ class LTEReceiver:
         bits = eng.indices_to_bits(idx, idx.shape[1] * eng.bps).reshape(-1)
         const = be.as_complex_tensor(self.qam_demodulator.constellation)
         detected = const[idx.reshape(-1).long()]
-        # pilot SNR statistic of the slot estimates (reference :78-80, :409)
-        pidx = torch.from_numpy(self.resource_grid.get_pilot_indices()).to(Y.device)
-        kp = be.as_complex_tensor(self.pilot_pattern.generate_pilots(len(pidx)))
-        snrs = []
-        for s0 in range(0, S, self.slot_size):
-            rp = Y[0, s0][pidx]
-            snr = torch.mean(rp.abs() ** 2) / (torch.mean((rp - kp).abs() ** 2) + 1e-10)
-            snrs.append(10 * np.log10(float(snr) + 1e-10))
-        snr_db = float(np.mean(snrs)) if snrs else 0.0
+        snr_db = self._pilot_snr_db(Y[0], S)
         ch0 = be.to_numpy(H.reshape(-1, eng.N)[0])
         self.channel_estimates.append(ch0)
         self.equalization_info.append({'channel_snr_db': snr_db, 'num_data_symbols': data.shape[1]})
@@ -164,6 +156,17 @@ class LTEReceiver:
             'equalization_enabled': self.enable_equalization,
         }
 
+    def _pilot_snr_db(self, Y, S):
+        """Mean over the slots of the pilot SNR statistic of their first symbol (reference :78-80, :393, :409)."""
+        pidx = torch.from_numpy(self.resource_grid.get_pilot_indices()).to(Y.device)
+        kp = be.as_complex_tensor(self.pilot_pattern.generate_pilots(len(pidx)))
+        snrs = []
+        for s0 in range(0, S, self.slot_size):
+            rp = Y[s0][pidx]
+            snr = torch.mean(rp.abs() ** 2) / (torch.mean((rp - kp).abs() ** 2) + 1e-10)
+            snrs.append(10 * np.log10(float(snr) + 1e-10))
+        return float(np.mean(snrs)) if snrs else 0.0
+
     def _estimate_channel_periodic(self, all_received_symbols: List[np.ndarray]) -> Tuple[List[np.ndarray], float]:
         """One LS estimate per 14-symbol slot, held for the slot (reference :360-411)."""
         eng = self._engine()
@@ -172,7 +175,7 @@ class LTEReceiver:
         H = eng.estimate(Y, 1, S, nat.WINDOW_FULL).reshape(-1, eng.N)
         be.reference_pilot_side_effect(self.cell_id, eng.Np)
         Hn = be.to_numpy(H)
-        return [Hn[s // self.slot_size] for s in range(S)], 0.0
+        return [Hn[s // self.slot_size] for s in range(S)], self._pilot_snr_db(Y[0], S)
 
     def _demodulate_ofdm_stream(self, received_signal) -> List[np.ndarray]:
         rx = be.as_complex_tensor(received_signal).reshape(1, -1)

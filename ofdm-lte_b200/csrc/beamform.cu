@@ -33,6 +33,7 @@ __global__ void random_channel_kernel(float2* __restrict__ h, int RT, uint32_t k
 
 extern "C" int lte_random_channel(lte_c32* h, int64_t B, int32_t R, int32_t T, uint64_t seed, uint64_t stream_id0,
                                   void* stream) {
+    if (B > 0 && !lte_ids_fit(stream_id0, (uint64_t)B)) return LTE_ERR_UNSUPPORTED;
     if (!h || B < 0 || R < 1 || R > BF_MAX_R || T < 1 || T > BF_MAX_T) return LTE_ERR_INVALID_ARG;
     if (B == 0) return LTE_OK;
     const long long total = (long long)B * R * T;
@@ -193,6 +194,7 @@ extern "C" int lte_bf_link(const lte_plan* p, const uint8_t* idx, const lte_c32*
                            const lte_c32* heff, const float* noise_std, const float* z, uint64_t seed,
                            uint64_t row_id0, lte_c32* out, unsigned long long* errors, int64_t nbits, int64_t B,
                            int32_t R, int32_t T, int32_t S, void* stream) {
+    if (!z && B > 0 && R > 0 && !lte_ids_fit(row_id0, (uint64_t)B * (uint64_t)R)) return LTE_ERR_UNSUPPORTED;
     if (!p || !idx || !h || !W || !heff || !noise_std || B < 0 || S < 1 || R < 1 || R > BF_MAX_R || T < 1 ||
         T > BF_MAX_T || (!out && !errors))
         return LTE_ERR_INVALID_ARG;

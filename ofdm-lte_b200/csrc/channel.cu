@@ -413,6 +413,7 @@ extern "C" int lte_awgn_add(const lte_plan* p, const lte_c32* x, int32_t x_div, 
                             const float* snr_lin, const lte_c32* z, uint64_t seed, uint64_t row_id0,
                             lte_c32* y, int64_t rows, int64_t n, void* stream) {
     if (!p || !x || !power || !snr_lin || !y || rows < 0 || n < 1 || x_div < 1) return LTE_ERR_INVALID_ARG;
+    if (!z && (!lte_ids_fit(row_id0, (uint64_t)rows) || n > (1ll << 32))) return LTE_ERR_UNSUPPORTED;
     if (rows == 0) return LTE_OK;
     int gx = (int)((n + 255) / 256);
     if (gx > 64) gx = 64;
@@ -448,6 +449,7 @@ __global__ void random_indices_kernel(uint8_t* __restrict__ idx, long long nsym,
 extern "C" int lte_random_indices(const lte_plan* p, uint8_t* idx, int64_t nsym, int64_t B, uint64_t seed,
                                   uint64_t stream_id0, void* stream) {
     if (!p || !idx || nsym < 1 || B < 0) return LTE_ERR_INVALID_ARG;
+    if (!lte_ids_fit(stream_id0, (uint64_t)B)) return LTE_ERR_UNSUPPORTED;
     if (B == 0) return LTE_OK;
     int gx = (int)(((nsym + 7) / 8 + 255) / 256);
     if (gx > 16) gx = 16;
@@ -475,6 +477,7 @@ __global__ void random_phases_kernel(float* __restrict__ ph, long long per_strea
 extern "C" int lte_random_phases(float* phases, int64_t per_stream, int64_t B, uint64_t seed,
                                  uint64_t stream_id0, void* stream) {
     if (!phases || per_stream < 1 || B < 0) return LTE_ERR_INVALID_ARG;
+    if (!lte_ids_fit(stream_id0, (uint64_t)B)) return LTE_ERR_UNSUPPORTED;
     if (B == 0) return LTE_OK;
     const int gx = (int)(((per_stream + 1) / 2 + 127) / 128);
     random_phases_kernel<<<(unsigned)((long long)gx * B), 128, 0, (cudaStream_t)stream>>>(

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <map>
 #include <vector>
 
 #include "../../include/lte_b200.h"
@@ -47,6 +48,14 @@ struct DevPlan {
     float inv_sqrt_n;
 };
 
+// Bluestein tables of the SC-FDM M-point DFT (dft.cu), device resident, owned by the plan
+struct DftTables {
+    int M, NB;
+    float2* w;      // [M]   chirp exp(-j pi n^2 / M)
+    float2* bf;     // [NB]  FFT of the circular chirp filter, pre-scaled by 1/(NB sqrt(M))
+    float2* tw;     // [NB]  FFT twiddles exp(-2 pi i m / NB)
+};
+
 struct lte_plan {
     lte_plan_desc desc;
     DevPlan dev;
@@ -54,6 +63,7 @@ struct lte_plan {
     int nsets;
     std::vector<int32_t> data_idx_h, pilot_idx_h;
     void* blob;                     // single device allocation holding all tables
+    std::map<int, DftTables> dft;   // M -> tables added by lte_plan_add_dft
 };
 
 // ------------------------------------------------------------------ complex helpers
@@ -106,6 +116,10 @@ __host__ __device__ __forceinline__ uint32_t lte_key(uint64_t seed, uint32_t dom
     philox2x32_10(domain, (uint32_t)seed, (uint32_t)(seed >> 32), a, b);
     return a ^ b;
 }
+
+// Stream / row identifiers are 32-bit Philox counter words: a launch whose ids would run past 2^32 would repeat
+// earlier draws (duplicate trials, overstated confidence), so the entry points refuse it instead.
+static inline bool lte_ids_fit(uint64_t id0, uint64_t count) { return id0 <= (1ull << 32) && count <= (1ull << 32) - id0; }
 
 // One complex unit normal (re, im ~ N(0,1)) for (row, sample) by Box-Muller; branch-free.
 // u1 = (r0 + 0.5) 2^-32 keeps the full 32-bit tail resolution for small r0 (fp32 is exact

@@ -169,8 +169,9 @@ __device__ __forceinline__ float2 awgn_at(const AwgnArgs& A, float sigma, long l
     return make_float2(fmaf(sigma, w.x, y.x), fmaf(sigma, w.y, y.y));
 }
 
-static int make_awgn_args(AwgnArgs& A, const lte_plan* p, const lte_awgn_desc* d, int32_t S) {
+static int make_awgn_args(AwgnArgs& A, const lte_plan* p, const lte_awgn_desc* d, int32_t S, int64_t rows) {
     if (!d->power || !d->snr_lin) return LTE_ERR_INVALID_ARG;
+    if (rows > 0 && !lte_ids_fit(d->row_id0, (uint64_t)rows)) return LTE_ERR_UNSUPPORTED;
     A.power = d->power;
     A.snr_lin = d->snr_lin;
     A.key = lte_key(d->seed, LTE_DOMAIN_NOISE);
@@ -237,7 +238,7 @@ static int launch_crs(const lte_plan* p, const lte_c32* Y, lte_c32* H, int windo
     int rc = lte_plan_window(p, window, &k0, &nk);
     if (rc) return rc;
     AwgnArgs A = {};
-    if (awgn && (rc = make_awgn_args(A, p, awgn, S))) return rc;
+    if (awgn && (rc = make_awgn_args(A, p, awgn, S, rows))) return rc;
     if (rows == 0) return LTE_OK;
     const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
     const unsigned grid = (unsigned)(rows * nslot);
@@ -453,7 +454,7 @@ static int launch_mrc(const lte_plan* p, const lte_c32* Y, const lte_c32* H, lte
     int rc = lte_plan_window(p, window, &k0, &nk);
     if (rc) return rc;
     AwgnArgs A = {};
-    if (awgn && (rc = make_awgn_args(A, p, awgn, S))) return rc;
+    if (awgn && (rc = make_awgn_args(A, p, awgn, S, B * R))) return rc;
     if (B == 0) return LTE_OK;
     const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
     const int gx = (p->dev.Nd + 127) / 128;
@@ -537,7 +538,7 @@ extern "C" int lte_crs_ls_compact(const lte_plan* p, const lte_c32* Ypilot, lte_
     if (p->dev.Np == 0 || p->nsets != 1) return LTE_ERR_UNSUPPORTED;
     AwgnArgs A = {};
     int rc;
-    if (awgn && (rc = make_awgn_args(A, p, awgn, S))) return rc;
+    if (awgn && (rc = make_awgn_args(A, p, awgn, S, rows))) return rc;
     if (rows == 0) return LTE_OK;
     const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
     const long long total = (long long)rows * nslot * p->dev.Np;
@@ -675,7 +676,7 @@ extern "C" int lte_mrc_demap_count_compact(const lte_plan* p, const lte_c32* Yda
     if (p->dev.Np == 0 || p->nsets != 1) return LTE_ERR_UNSUPPORTED;
     AwgnArgs A = {};
     int rc;
-    if (awgn && (rc = make_awgn_args(A, p, awgn, S))) return rc;
+    if (awgn && (rc = make_awgn_args(A, p, awgn, S, B * R))) return rc;
     if (B == 0) return LTE_OK;
     const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
     const int gx = (p->dev.Nd + 127) / 128;

@@ -4,73 +4,9 @@
 //
 //   X[k] = w[k] * sum_n (x[n] w[n]) conj(w[k-n]) / sqrt(M),   w[n] = exp(-j pi n^2 / M)
 // The convolution runs through two NB-point FFTs (NB = pow2 >= 2M-1) in one kernel; the
-// spectrum of the chirp filter is a per-(plan, M) table computed once on the host in fp64.
-#include <math.h>
-
-#include <map>
-#include <mutex>
-
+// spectrum of the chirp filter is a per-(plan, M) table computed once on the host in fp64 by
+// lte_plan_add_dft (plan.cu) -- the launcher itself never allocates or copies.
 #include "fft.cuh"
-
-struct DftTables {
-    int M, NB;
-    float2* w;      // [M]   chirp exp(-j pi n^2 / M)
-    float2* bf;     // [NB]  FFT of the circular chirp filter, pre-scaled by 1/(NB sqrt(M))
-    float2* tw;     // [NB]  FFT twiddles exp(-2 pi i m / NB)
-};
-
-static std::mutex g_dft_mutex;
-static std::map<std::pair<int, int>, DftTables> g_dft_tables;   // (device, M) -> tables
-
-static int get_tables(int M, DftTables* out) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> lock(g_dft_mutex);
-    auto it = g_dft_tables.find({dev, M});
-    if (it != g_dft_tables.end()) { *out = it->second; return LTE_OK; }
-    int NB = 64;
-    while (NB < 2 * M - 1) NB <<= 1;
-    if (NB > 2048) return LTE_ERR_UNSUPPORTED;
-    std::vector<double> wr(M), wi(M);
-    for (int n = 0; n < M; ++n) {
-        const long long q = ((long long)n * n) % (2LL * M);        // exact phase reduction
-        const double a = -M_PI * (double)q / (double)M;
-        wr[n] = cos(a); wi[n] = sin(a);
-    }
-    // b[m] = conj(w[|m|]) placed circularly; its NB-point DFT by the definition (fp64)
-    std::vector<double> br(NB, 0.0), bi(NB, 0.0);
-    for (int m = 0; m < M; ++m) {
-        br[m] = wr[m]; bi[m] = -wi[m];
-        if (m) { br[NB - m] = wr[m]; bi[NB - m] = -wi[m]; }
-    }
-    std::vector<double> cr(NB), ci(NB);
-    for (int i = 0; i < NB; ++i) { const double a = -2.0 * M_PI * i / NB; cr[i] = cos(a); ci[i] = sin(a); }
-    std::vector<float2> w(M), bf(NB), tw(NB);
-    for (int i = 0; i < NB; ++i) tw[i] = make_float2((float)cr[i], (float)ci[i]);
-    const double scale = 1.0 / ((double)NB * sqrt((double)M));
-    for (int k = 0; k < NB; ++k) {
-        double sr = 0.0, si = 0.0;
-        for (int m = 0; m < NB; ++m) {
-            if (br[m] == 0.0 && bi[m] == 0.0) continue;
-            const int t = (int)(((long long)k * m) & (NB - 1));
-            sr += br[m] * cr[t] - bi[m] * ci[t];
-            si += br[m] * ci[t] + bi[m] * cr[t];
-        }
-        bf[k] = make_float2((float)(sr * scale), (float)(si * scale));
-    }
-    for (int n = 0; n < M; ++n) w[n] = make_float2((float)wr[n], (float)wi[n]);
-    DftTables t;
-    t.M = M; t.NB = NB;
-    if (cudaMalloc(&t.w, sizeof(float2) * M) != cudaSuccess) return lte_set_cuda_error(cudaGetLastError());
-    if (cudaMalloc(&t.bf, sizeof(float2) * NB) != cudaSuccess) return lte_set_cuda_error(cudaGetLastError());
-    cudaMemcpy(t.w, w.data(), sizeof(float2) * M, cudaMemcpyHostToDevice);
-    if (cudaMalloc(&t.tw, sizeof(float2) * NB) != cudaSuccess) return lte_set_cuda_error(cudaGetLastError());
-    cudaMemcpy(t.bf, bf.data(), sizeof(float2) * NB, cudaMemcpyHostToDevice);
-    cudaMemcpy(t.tw, tw.data(), sizeof(float2) * NB, cudaMemcpyHostToDevice);
-    g_dft_tables[{dev, M}] = t;
-    *out = t;
-    return LTE_OK;
-}
 
 template <int NB>
 __global__ void __launch_bounds__(FFT_CTA_THREADS)
@@ -118,10 +54,10 @@ dft_m_kernel(const float2* __restrict__ in, float2* __restrict__ out, const floa
 extern "C" int lte_dft_m(const lte_plan* p, const lte_c32* in, lte_c32* out, int32_t M, int32_t inverse,
                          int64_t rows, void* stream) {
     if (!p || !in || !out || M < 1 || rows < 0) return LTE_ERR_INVALID_ARG;
+    auto it = p->dft.find(M);
+    if (it == p->dft.end()) return LTE_ERR_INVALID_ARG;           // tables are plan state: lte_plan_add_dft(plan, M) first
     if (rows == 0) return LTE_OK;
-    DftTables t;
-    int rc = get_tables(M, &t);
-    if (rc) return rc;
+    const DftTables t = it->second;
     cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_DFT(NBV)                                                                                     \
     case NBV: {                                                                                             \

@@ -489,6 +489,7 @@ extern "C" int lte_rx_fft(const lte_plan* p, const lte_c32* rx, int32_t rx_div, 
     if (power && !snr_lin) return LTE_ERR_INVALID_ARG;
     if (noise_domain != 0 && noise_domain != 1) return LTE_ERR_INVALID_ARG;
     if (noise_domain == 1 && z) return LTE_ERR_INVALID_ARG;   // replayed normals are time-domain draws
+    if (power && !z && !lte_ids_fit(row_id0, (uint64_t)rows)) return LTE_ERR_UNSUPPORTED;
     int32_t k0, nk;
     int rc = lte_plan_window(p, window, &k0, &nk);
     if (rc) return rc;

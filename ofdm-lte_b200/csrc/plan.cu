@@ -228,8 +228,63 @@ extern "C" int lte_plan_create(const lte_plan_desc* d, const lte_c32* pilots_hos
     return LTE_OK;
 }
 
+// Bluestein chirp-z tables of the M-point DFT (kernel in dft.cu): plan state, built once per M on the host in fp64.
+// Synchronous (cudaMalloc + cudaMemcpy), like lte_plan_create: call it while setting the plan up, not in a stream.
+extern "C" int lte_plan_add_dft(lte_plan* p, int32_t M) {
+    if (!p || M < 1) return LTE_ERR_INVALID_ARG;
+    if (p->dft.count(M)) return LTE_OK;
+    int NB = 64;
+    while (NB < 2 * M - 1) NB <<= 1;
+    if (NB > 2048) return LTE_ERR_UNSUPPORTED;
+    std::vector<double> wr(M), wi(M);
+    for (int n = 0; n < M; ++n) {
+        const long long q = ((long long)n * n) % (2LL * M);        // exact phase reduction
+        const double a = -M_PI * (double)q / (double)M;
+        wr[n] = cos(a); wi[n] = sin(a);
+    }
+    // b[m] = conj(w[|m|]) placed circularly; its NB-point DFT by the definition (fp64)
+    std::vector<double> br(NB, 0.0), bi(NB, 0.0);
+    for (int m = 0; m < M; ++m) {
+        br[m] = wr[m]; bi[m] = -wi[m];
+        if (m) { br[NB - m] = wr[m]; bi[NB - m] = -wi[m]; }
+    }
+    std::vector<double> cr(NB), ci(NB);
+    for (int i = 0; i < NB; ++i) { const double a = -2.0 * M_PI * i / NB; cr[i] = cos(a); ci[i] = sin(a); }
+    std::vector<float2> w(M), bf(NB), tw(NB);
+    for (int i = 0; i < NB; ++i) tw[i] = make_float2((float)cr[i], (float)ci[i]);
+    const double scale = 1.0 / ((double)NB * sqrt((double)M));
+    for (int k = 0; k < NB; ++k) {
+        double sr = 0.0, si = 0.0;
+        for (int m = 0; m < NB; ++m) {
+            if (br[m] == 0.0 && bi[m] == 0.0) continue;
+            const int t = (int)(((long long)k * m) & (NB - 1));
+            sr += br[m] * cr[t] - bi[m] * ci[t];
+            si += br[m] * ci[t] + bi[m] * cr[t];
+        }
+        bf[k] = make_float2((float)(sr * scale), (float)(si * scale));
+    }
+    for (int n = 0; n < M; ++n) w[n] = make_float2((float)wr[n], (float)wi[n]);
+    DftTables t;
+    t.M = M; t.NB = NB;
+    t.w = t.bf = t.tw = nullptr;
+    if (cudaMalloc(&t.w, sizeof(float2) * M) != cudaSuccess || cudaMalloc(&t.bf, sizeof(float2) * NB) != cudaSuccess ||
+        cudaMalloc(&t.tw, sizeof(float2) * NB) != cudaSuccess ||
+        cudaMemcpy(t.w, w.data(), sizeof(float2) * M, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(t.bf, bf.data(), sizeof(float2) * NB, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(t.tw, tw.data(), sizeof(float2) * NB, cudaMemcpyHostToDevice) != cudaSuccess) {
+        const cudaError_t e = cudaGetLastError();
+        if (t.w) cudaFree(t.w);
+        if (t.bf) cudaFree(t.bf);
+        if (t.tw) cudaFree(t.tw);
+        return lte_set_cuda_error(e);
+    }
+    p->dft[M] = t;
+    return LTE_OK;
+}
+
 extern "C" int lte_plan_destroy(lte_plan* p) {
     if (!p) return LTE_OK;
+    for (auto& kv : p->dft) { cudaFree(kv.second.w); cudaFree(kv.second.bf); cudaFree(kv.second.tw); }
     if (p->blob) cudaFree(p->blob);
     delete p;
     return LTE_OK;

@@ -208,6 +208,10 @@ class LinkEngine:
     def dft_m(self, x, M, inverse=False, out=None):
         """Unitary M-point DFT (or IDFT) of every length-M row of x (any leading shape)."""
         rows = x.numel() // M
+        have = self.__dict__.setdefault('_dft_sizes', set())
+        if int(M) not in have:                 # chirp tables are plan state, built once per M (synchronous)
+            nat.check(nat.lib.lte_plan_add_dft(self._plan, int(M)), 'lte_plan_add_dft')
+            have.add(int(M))
         y = out if out is not None else torch.empty_like(x)
         nat.check(nat.lib.lte_dft_m(self._plan, _ptr(x), _ptr(y), int(M), 1 if inverse else 0, rows,
                                     self._stream()), 'lte_dft_m')

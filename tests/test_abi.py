@@ -54,3 +54,32 @@ def test_no_cpu_fallback():
     from core.ofdm_core import OFDMSimulator
     with pytest.raises(RuntimeError):
         OFDMSimulator().simulate_siso([0, 1, 1, 0])
+
+
+def test_library_reads_no_environment():
+    """No environment variable may change what a kernel computes (round 1 shipped LTE_TDL_DEBUG / LTE_MRC_SPS
+    switches): none of the library's own object files references getenv (the statically linked CUDA runtime does,
+    so the final .so cannot be the thing inspected), and no source file mentions it."""
+    import subprocess
+    import __graft_entry__ as g
+    g.build(force=not os.path.isdir(os.path.join(ROOT, 'ofdm-lte_b200', 'csrc', 'build')))
+    csrc = os.path.join(ROOT, 'ofdm-lte_b200', 'csrc')
+    objs = [os.path.join(csrc, 'build', f) for f in os.listdir(os.path.join(csrc, 'build')) if f.endswith('.o')]
+    assert len(objs) >= 10
+    for o in objs:
+        syms = subprocess.run(['nm', '--undefined-only', o], capture_output=True, text=True).stdout
+        assert 'getenv' not in syms, o
+    for f in os.listdir(csrc):
+        if f.endswith(('.cu', '.cuh')):
+            assert 'getenv' not in open(os.path.join(csrc, f)).read(), f
+
+
+def test_no_entry_point_allocates_or_synchronises():
+    """Launchers never allocate, free or synchronise (caller-owned workspaces, round-2 boundary hygiene): the only
+    cudaMalloc / cudaFree / cudaMemcpy calls of the library are in plan creation / destruction (plan.cu)."""
+    csrc = os.path.join(ROOT, 'ofdm-lte_b200', 'csrc')
+    for f in os.listdir(csrc):
+        if f.endswith(('.cu', '.cuh')) and f != 'plan.cu':
+            text = open(os.path.join(csrc, f)).read()
+            for call in ('cudaMalloc', 'cudaFree', 'cudaDeviceSynchronize', 'cudaStreamSynchronize', 'cudaMemcpy('):
+                assert call not in text, (f, call)
