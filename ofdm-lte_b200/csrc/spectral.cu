@@ -35,10 +35,15 @@
 // core/resource_mapper.py:181-223), then instead of the time-domain stream:
 //   tail [B*S][cp]  the last cp samples of every symbol (= its cyclic prefix),
 //   G    [B*S][nk]  fft((n - n_c) u[n]) / sqrt(N) on the occupied window.
-template <int N>
+// STD: the plan uses the LTE profile's occupied-bin count for this FFT size (config.py:104-107: 76 / 150 / 300 /
+// 600 / 1200 of 128 / 256 / 512 / 1024 / 2048), so the occupied window is a compile-time constant and every
+// "is this group of 128 bins inside the window" test folds away; other layouts take the run-time tests.
+__host__ __device__ constexpr int lte_std_nc(int n) { return n == 2048 ? 1200 : n == 1024 ? 600 : n == 512 ? 300 : n == 256 ? 150 : n == 128 ? 76 : 0; }
+
+template <int N, bool STD>
 __global__ void __launch_bounds__(FFT_CTA_THREADS, 5)
 tx_spectral_kernel(const DevPlan P, const uint8_t* __restrict__ idx, float2* __restrict__ G,
-                   float2* __restrict__ tail, int k0, int nk, unsigned total) {
+                   float2* __restrict__ tail, int k0_rt, int nk_rt, unsigned total) {
     constexpr int TPF = N / FFT_ELEMS, PPC = fft2_pairs_per_cta(N);
     extern __shared__ float4 smem4[];
     __shared__ float s_lev[8];
@@ -51,7 +56,8 @@ tx_spectral_kernel(const DevPlan P, const uint8_t* __restrict__ idx, float2* __r
     const uint8_t* ip[2] = {idx + (size_t)f0 * P.Nd, idx + (size_t)(f0 + 1) * P.Nd};
     __syncthreads();          // s_lev
 
-    const int used_lo = P.k0_useful, used_hi = P.k0_useful + P.nk_useful;
+    const int k0 = STD ? (N - lte_std_nc(N)) / 2 : k0_rt, nk = STD ? lte_std_nc(N) : nk_rt;
+    const int used_lo = k0, used_hi = k0 + nk;
     int code[FFT_ELEMS];
 #pragma unroll
     for (int e = 0; e < FFT_ELEMS; ++e) {
@@ -91,7 +97,9 @@ tx_spectral_kernel(const DevPlan P, const uint8_t* __restrict__ idx, float2* __r
 
     fft2_run<N, true>(v, sbuf, P.twiddle, j);
 
-    // tails (tx samples = raw / sqrt(N)) and the ramp (n - n_c) / N: G = fft(ramp * raw) / ... / sqrt(N)
+    // tails (tx samples = raw / sqrt(N)) and the ramp (n - n_c) / N: G = fft(ramp * raw) / ... / sqrt(N).
+    // (One copy of the transform code looped twice -- forward as conj(IFFT(conj(.))) -- halves the instruction
+    // footprint but the loop-carried state spills at 96 registers: 0.58 ms against 0.47 ms, measured.)
     const int tail0 = N - P.cp;
     const float nc = 0.5f * (float)(P.L - 1) - (float)P.cp;
     const float inv_n = P.inv_sqrt_n * P.inv_sqrt_n;
@@ -661,11 +669,15 @@ extern "C" int lte_tx_spectral(const lte_plan* p, const uint8_t* idx, lte_c32* G
         const int smem = fft2_cta_smem_bytes(N);
         const long long per = 2 * fft2_pairs_per_cta(N);
         const long long grid = (total + per - 1) / per;
-        LTE_CHECK_CUDA(cudaFuncSetAttribute(tx_spectral_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        tx_spectral_kernel<N><<<(unsigned)grid, FFT_CTA_THREADS, smem, (cudaStream_t)stream>>>(
-            p->dev, idx, (float2*)G, (float2*)tail, k0, nk, (unsigned)total);
-        LTE_CHECK_CUDA(cudaGetLastError());
-        return LTE_OK;
+        const bool std_layout = !p->desc.mode_simple && nk == lte_std_nc(N) && k0 == (N - nk) / 2;
+        auto launch = [&](auto k) -> int {
+            LTE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            k<<<(unsigned)grid, FFT_CTA_THREADS, smem, (cudaStream_t)stream>>>(p->dev, idx, (float2*)G, (float2*)tail, k0, nk,
+                                                                           (unsigned)total);
+            LTE_CHECK_CUDA(cudaGetLastError());
+            return LTE_OK;
+        };
+        return std_layout ? launch(tx_spectral_kernel<N, true>) : launch(tx_spectral_kernel<N, false>);
     });
 }
 

@@ -523,11 +523,15 @@ class LinkEngine:
         ph = self.random_phases(B, R * T * chan.num_taps * nat.LTE_JAKES_TONES, seed, stream_id0)
         rx, power = self.channel(tx, chan, B, R, T=T, phases=ph)
         snr_rows = torch.full((B * R,), float(10 ** (snr_db / 10)), dtype=torch.float32, device=self.device)
-        Y = self.rx_fft(rx.view(B * R, -1), B * R, S, nat.WINDOW_FULL, power=power, snr_lin=snr_rows, seed=seed,
+        # only the occupied bins travel: FFT window, per-TX estimates (written straight into one [T, ...] tensor) and detector
+        k0, nk = self.window(nat.WINDOW_USEFUL)
+        Y = self.rx_fft(rx.view(B * R, -1), B * R, S, nat.WINDOW_USEFUL, power=power, snr_lin=snr_rows, seed=seed,
                         row_id0=stream_id0 * R, noise_domain=1)
-        H = torch.stack([self.estimate(Y.view(B * R * S, 1, self.N), B * R * S, 1, nat.WINDOW_FULL, pilot_set=t)
-                         .view(B * R, S, self.N) for t in range(T)])
-        sym = self.mimo_detect(Y, H, W, 10 ** (-snr_db / 10), detector, B, R, S, nat.WINDOW_FULL)
+        H = self._empty((T, B * R, S, nk), torch.complex64)
+        for t in range(T):
+            self.estimate(Y.view(B * R * S, 1, nk), B * R * S, 1, nat.WINDOW_USEFUL, pilot_set=t,
+                          out=H[t].view(B * R * S, 1, nk))
+        sym = self.mimo_detect(Y, H, W, 10 ** (-snr_db / 10), detector, B, R, S, nat.WINDOW_USEFUL)
         errors, _ = self.demap_count(sym, idx_tx=idx, nbits=S * self.Nd * self.bps)
         return errors
 
