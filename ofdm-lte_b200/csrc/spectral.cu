@@ -350,7 +350,7 @@ channel_spectral_kernel(const DevPlan P, const SpecParams C, const uint8_t* __re
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int cp = P.cp, L = P.L;
     const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
-    // shared memory: [mbarriers full[3], empty[3]] [X lookup: re[64], im[64]] stages x {G row | x region | coefficients}
+    // shared memory: [mbarriers full[], empty[]] [X lookup: re[64], im[64]] stages x {G row | x region | coefficients}
     const unsigned s0 = (unsigned)__cvta_generic_to_shared(smem_raw);
     const unsigned bar_full = s0, bar_empty = s0 + 8u * SPEC_STAGES;
     const unsigned lut = s0 + 64u;
@@ -410,8 +410,8 @@ channel_spectral_kernel(const DevPlan P, const SpecParams C, const uint8_t* __re
                 if (++pstage == SPEC_STAGES) { pstage = 0; pphase ^= 1u; }
             }
         };
-        produce_next();
-        produce_next();
+#pragma unroll
+        for (int i = 0; i < SPEC_STAGES - 1; ++i) produce_next();
         f2 pwc[R2];
 #pragma unroll
         for (int r = 0; r < R2; ++r) pwc[r] = pk(0.f, 0.f);
