@@ -563,7 +563,10 @@ extern "C" int lte_crs_ls_compact(const lte_plan* p, const lte_c32* Ypilot, lte_
 // the headline shape: planar pairs (re0, re1, im0, im1) read as two 32-bit loads 0.61 ms, two bins per thread with
 // 128-bit loads 0.61 ms, this layout 0.46 ms.  The draws are those of mrc_kernel, so the counts are bit-identical
 // to the windowed layout.
-template <int R, bool NOISY>
+// FULL: every bit of every symbol lies inside the first nbits (the sweep's case: nbits = S Nd bps), so the
+// per-symbol 64-bit bit budget -- which the compiler otherwise re-derives for every output at 64 registers --
+// is not needed at all: errors are a plain XOR + popcount.
+template <int R, bool NOISY, bool FULL>
 __global__ void __launch_bounds__(128, NOISY ? 8 : 1)
 mrc_compact_kernel(const DevPlan P, const float2* __restrict__ Yd, const float2* __restrict__ Hp,
                    const uint8_t* __restrict__ idx_tx, unsigned long long* __restrict__ errors, int S, int nslot,
@@ -618,8 +621,7 @@ mrc_compact_kernel(const DevPlan P, const float2* __restrict__ Yd, const float2*
 #pragma unroll
             for (int r = 0; r < R; ++r) yp[r] = Yd + (((size_t)b * R + r) * S + s0) * ystride + d;
             const uint8_t* ip = idx_tx + ((size_t)b * S + s0) * P.Nd + d;
-            const long long valid0 = nbits - ((long long)s0 * P.Nd + d) * P.bps;   // bits left from (s0, d) on
-            const bool all_valid = valid0 - (long long)(s_end - 1 - s0) * sym_bits >= P.bps;
+            const long long valid0 = FULL ? 0 : nbits - ((long long)s0 * P.Nd + d) * P.bps;   // bits left from (s0, d) on
             auto fetch = [&](float2 (&y)[R], uint8_t& in, int s) {
                 in = 0;
                 if (s < s_end) {
@@ -640,7 +642,8 @@ mrc_compact_kernel(const DevPlan P, const float2* __restrict__ Yd, const float2*
                 }
                 if (comb) acc = awgn_at(A, csig, b * R, s, P.N, kb, acc);
                 const int dec = slice_symbol(P, make_float2(acc.x * inv_den, acc.y * inv_den));
-                e += all_valid ? __popc(dec ^ (int)in) : bit_errors(dec, in, P.bps, valid0 - (long long)(s - s0) * sym_bits);
+                if (FULL) e += __popc(dec ^ (int)in);
+                else e += bit_errors(dec, in, P.bps, valid0 - (long long)(s - s0) * sym_bits);
             };
             float2 ya[R], yc[R];
             uint8_t ia, ic;
@@ -684,14 +687,14 @@ extern "C" int lte_mrc_demap_count_compact(const lte_plan* p, const lte_c32* Yda
     if (grid_ll >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
     const unsigned grid = (unsigned)grid_ll;
     cudaStream_t st = (cudaStream_t)stream;
+    const bool full = nbits >= (int64_t)S * p->dev.Nd * p->dev.bps;
+#define LAUNCH_MRCC2(RR, NN, FF)                                                                                      \
+    mrc_compact_kernel<RR, NN, FF><<<grid, 128, 0, st>>>(p->dev, (const float2*)Ydata, (const float2*)Hp, idx_tx,     \
+                                                         errors, S, nslot, nbits, gx, A)
 #define LAUNCH_MRCC(RR)                                                                                               \
     case RR:                                                                                                         \
-        if (awgn)                                                                                                    \
-            mrc_compact_kernel<RR, true><<<grid, 128, 0, st>>>(p->dev, (const float2*)Ydata, (const float2*)Hp, idx_tx, \
-                                                               errors, S, nslot, nbits, gx, A);                      \
-        else                                                                                                         \
-            mrc_compact_kernel<RR, false><<<grid, 128, 0, st>>>(p->dev, (const float2*)Ydata, (const float2*)Hp, idx_tx, \
-                                                                errors, S, nslot, nbits, gx, A);                     \
+        if (awgn) { if (full) LAUNCH_MRCC2(RR, true, true); else LAUNCH_MRCC2(RR, true, false); }                     \
+        else { if (full) LAUNCH_MRCC2(RR, false, true); else LAUNCH_MRCC2(RR, false, false); }                       \
         break;
     switch (R) {
         LAUNCH_MRCC(1) LAUNCH_MRCC(2) LAUNCH_MRCC(3) LAUNCH_MRCC(4) LAUNCH_MRCC(5) LAUNCH_MRCC(6) LAUNCH_MRCC(7)
@@ -699,6 +702,7 @@ extern "C" int lte_mrc_demap_count_compact(const lte_plan* p, const lte_c32* Yda
         default: return LTE_ERR_INVALID_ARG;
     }
 #undef LAUNCH_MRCC
+#undef LAUNCH_MRCC2
     LTE_CHECK_CUDA(cudaGetLastError());
     return LTE_OK;
 }
