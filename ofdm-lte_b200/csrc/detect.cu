@@ -1,5 +1,8 @@
 // Stage 4 (CRS LS + linear interpolation), stage 5 (ZF / MRC) and stage 6 (hard demap +
 // bit-error count), plus the bit <-> symbol-index helpers of the reference-facing API.
+#include <algorithm>
+#include <vector>
+
 #include "slicer.cuh"
 
 #include "common.cuh"
@@ -566,47 +569,66 @@ extern "C" int lte_crs_ls_compact(const lte_plan* p, const lte_c32* Ypilot, lte_
 // FULL: every bit of every symbol lies inside the first nbits (the sweep's case: nbits = S Nd bps), so the
 // per-symbol 64-bit bit budget -- which the compiler otherwise re-derives for every output at 64 registers --
 // is not needed at all: errors are a plain XOR + popcount.
-template <int R, bool NOISY, bool FULL>
-__global__ void __launch_bounds__(128, NOISY ? 8 : 1)
+// NOISE: 0 = Y already carries its noise, 1 = lazy AWGN per antenna, 2 = one combined draw per output
+#define MRCC_PILOTS 40          // pilots a CTA's 128 consecutive data bins may interpolate between (LTE CRS: 27)
+template <int R, int NOISE, bool FULL>
+__global__ void __launch_bounds__(128, NOISE ? 8 : 1)
 mrc_compact_kernel(const DevPlan P, const float2* __restrict__ Yd, const float2* __restrict__ Hp,
                    const uint8_t* __restrict__ idx_tx, unsigned long long* __restrict__ errors, int S, int nslot,
                    long long nbits, int gx, const AwgnArgs A) {
+    // (estimate, slope to the next pilot) of the pilots this CTA's 128 bins interpolate between, per antenna, and
+    // the noise sigma of every antenna: worked out once per CTA instead of once per thread (the divisions are
+    // the IEEE ones of crs_ls_interp_kernel, so the interpolated values are unchanged bit for bit)
+    __shared__ float4 seg_s[R * MRCC_PILOTS];
+    __shared__ float sigma_s[R];
     const int chunk = blockIdx.x % gx;
     const long long b = blockIdx.x / gx;
-    const int d = chunk * blockDim.x + threadIdx.x;
+    const int tid = threadIdx.x;
+    const int d0 = chunk * blockDim.x;
+    const bool act = d0 + tid < P.Nd;
+    const int d = act ? d0 + tid : P.Nd - 1;
     unsigned int e = 0;
-    if (d < P.Nd) {
-        const int kb = P.data_idx[d];
-        float sigma[R];
-        if (NOISY) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) sigma[r] = lte_sigma(A.power[b * R + r], A.n_stream, A.snr_lin[b * R + r]);
+    constexpr bool NOISY = NOISE != 0, comb = NOISE == 2;
+    const int cnt = P.pset_cnt[0];
+    auto segment = [&](int bin) { const int lo = P.pset_seg[bin]; return lo < 0 ? 0 : (lo >= cnt - 1 ? cnt - 1 : lo); };
+    const int la0 = segment(P.data_idx[d0]);
+    const int npil = segment(P.data_idx[min(d0 + (int)blockDim.x, P.Nd) - 1]) - la0 + 1;    // <= MRCC_PILOTS (host check)
+    if (NOISY && tid < R) sigma_s[tid] = lte_sigma(A.power[b * R + tid], A.n_stream, A.snr_lin[b * R + tid]);
+    const int kb = P.data_idx[d];
+    const int lo = P.pset_seg[kb];
+    const int la = segment(kb);
+    const bool inner = lo >= 0 && lo < cnt - 1;
+    const float t = inner ? (float)(kb - P.pset_bin[la]) : 0.f;     // edge bins hold their pilot: a + 0 * slope
+    const int sym_bits = P.Nd * P.bps;
+    const int ystride = 2 * P.ndp;
+    for (int slot = 0; slot < nslot; ++slot) {
+        __syncthreads();                                            // the previous slot's table has been consumed
+        for (int q = tid; q < npil * R; q += blockDim.x) {
+            const int r = q / npil, i = la0 + q - r * npil;
+            const float2* hp = Hp + (((size_t)b * R + r) * nslot + slot) * P.Np;
+            const float2 a = hp[i];
+            float2 sl = make_float2(0.f, 0.f);
+            if (i < cnt - 1) {
+                const float2 c = hp[i + 1];
+                const float div = (float)(P.pset_bin[i + 1] - P.pset_bin[i]);
+                sl = make_float2(__fdiv_rn(c.x - a.x, div), __fdiv_rn(c.y - a.y, div));
+            }
+            seg_s[r * MRCC_PILOTS + i - la0] = make_float4(a.x, a.y, sl.x, sl.y);
         }
-        const bool comb = NOISY && A.combine;
-        // pilot segment of the bin
-        const int cnt = P.pset_cnt[0];
-        const int lo = P.pset_seg[kb];
-        const int la = lo < 0 ? 0 : (lo >= cnt - 1 ? cnt - 1 : lo);
-        const bool inner = lo >= 0 && lo < cnt - 1;
-        const int i1 = P.pset_bin[la];
-        const float div = inner ? (float)(P.pset_bin[la + 1] - i1) : 1.f;
-        const float t = (float)(kb - i1);
-        const int sym_bits = P.Nd * P.bps;
-        const int ystride = 2 * P.ndp;
-        for (int slot = 0; slot < nslot; ++slot) {
+        __syncthreads();
+        {
+            float sigma[R];
+            if (NOISY) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) sigma[r] = sigma_s[r];
+            }
             float2 h[R];
             float den = 0.f;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const float2* hp = Hp + (((size_t)b * R + r) * nslot + slot) * P.Np;
-                const float2 a = hp[la];
-                float2 v = a;
-                if (inner && kb != i1) {
-                    const float2 c = hp[la + 1];
-                    v = make_float2(fmaf(t, __fdiv_rn(c.x - a.x, div), a.x), fmaf(t, __fdiv_rn(c.y - a.y, div), a.y));
-                }
-                h[r] = v;
-                den += cabs2(v);
+                const float4 as = seg_s[r * MRCC_PILOTS + la - la0];
+                h[r] = make_float2(fmaf(t, as.z, as.x), fmaf(t, as.w, as.y));
+                den += cabs2(h[r]);
             }
             den += 1e-10f;
             const float inv_den = __frcp_rn(den);
@@ -669,7 +691,7 @@ mrc_compact_kernel(const DevPlan P, const float2* __restrict__ Yd, const float2*
             }
         }
     }
-    block_add_errors(e, &errors[b]);
+    block_add_errors(act ? e : 0u, &errors[b]);
 }
 
 extern "C" int lte_mrc_demap_count_compact(const lte_plan* p, const lte_c32* Ydata, const lte_c32* Hp,
@@ -685,6 +707,19 @@ extern "C" int lte_mrc_demap_count_compact(const lte_plan* p, const lte_c32* Yda
     const int gx = (p->dev.Nd + 127) / 128;
     const long long grid_ll = (long long)gx * B;
     if (grid_ll >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
+    {   // the kernel's shared pilot table holds MRCC_PILOTS entries per antenna: pilot grids denser than that
+        // per 128 data bins (no LTE numerology) are refused rather than overrun
+        const std::vector<int32_t>& pil = p->pilot_idx_h;
+        const std::vector<int32_t>& dat = p->data_idx_h;
+        auto segment = [&](int bin) {
+            int lo = (int)(std::upper_bound(pil.begin(), pil.end(), bin) - pil.begin()) - 1;
+            return lo < 0 ? 0 : lo;
+        };
+        for (int c = 0; c < gx; ++c) {
+            const int last = std::min((c + 1) * 128, (int)dat.size()) - 1;
+            if (segment(dat[last]) - segment(dat[c * 128]) + 1 > MRCC_PILOTS) return LTE_ERR_UNSUPPORTED;
+        }
+    }
     const unsigned grid = (unsigned)grid_ll;
     cudaStream_t st = (cudaStream_t)stream;
     const bool full = nbits >= (int64_t)S * p->dev.Nd * p->dev.bps;
@@ -693,8 +728,9 @@ extern "C" int lte_mrc_demap_count_compact(const lte_plan* p, const lte_c32* Yda
                                                          errors, S, nslot, nbits, gx, A)
 #define LAUNCH_MRCC(RR)                                                                                               \
     case RR:                                                                                                         \
-        if (awgn) { if (full) LAUNCH_MRCC2(RR, true, true); else LAUNCH_MRCC2(RR, true, false); }                     \
-        else { if (full) LAUNCH_MRCC2(RR, false, true); else LAUNCH_MRCC2(RR, false, false); }                       \
+        if (awgn && A.combine) { if (full) LAUNCH_MRCC2(RR, 2, true); else LAUNCH_MRCC2(RR, 2, false); }                \
+        else if (awgn) { if (full) LAUNCH_MRCC2(RR, 1, true); else LAUNCH_MRCC2(RR, 1, false); }                     \
+        else { if (full) LAUNCH_MRCC2(RR, 0, true); else LAUNCH_MRCC2(RR, 0, false); }                       \
         break;
     switch (R) {
         LAUNCH_MRCC(1) LAUNCH_MRCC(2) LAUNCH_MRCC(3) LAUNCH_MRCC(4) LAUNCH_MRCC(5) LAUNCH_MRCC(6) LAUNCH_MRCC(7)

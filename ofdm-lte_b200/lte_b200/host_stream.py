@@ -63,7 +63,7 @@ class HostBatchPipeline:
     batch run while the current one computes."""
 
     def __init__(self, engine, chan, num_rx, snr_lin_rows, B, S, nbits=None, seed=0, noise_domain=3, fused=True,
-                 depth=2):
+                 depth=3):
         self.eng, self.chan, self.R, self.B, self.S = engine, chan, int(num_rx), int(B), int(S)
         self.nbits = int(nbits) if nbits is not None else S * engine.Nd * engine.bps
         self.nbytes = (self.nbits + 7) // 8
