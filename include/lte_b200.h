@@ -338,15 +338,17 @@ int lte_sfbc_decode(const lte_plan*, const lte_c32* Y, const lte_c32* H0, const 
  * lte_mimo_detect replaces MIMODetector.detect (core/mimo_detector.py:55-369) on
  * H_eff = H W per data position: Y [B][R][S][nk]; H [T][B*R][S][nk] (per-symbol estimates, one
  * lte_crs_ls_interp per TX pilot set); out [B][S][Nd] in the LayerMapper.demap_from_layers order
- * (core/layer_mapper.py:88-115).  detector: LTE_DET_*; SIC slices with the plan's constellation. */
+ * (core/layer_mapper.py:88-115).  detector: LTE_DET_*; SIC slices with the plan's constellation.
+ * sigma2_streams (optional, device, double [B]): one noise variance per stream, which lets a sweep put
+ * all its SNR points into one launch; NULL = the scalar `sigma2` for every stream. */
 int lte_sm_precode(const lte_plan*, const uint8_t* idx, const lte_c32* symbols, const lte_c32* W_host,
                    int32_t T, int32_t L, lte_c32* out, lte_c32* qam_out, int64_t B, int32_t S,
                    void* stream);
 int lte_flat_mimo(const lte_plan*, const lte_c32* tx, const lte_c32* h, lte_c32* out, double* power,
                   int64_t B, int32_t R, int32_t T, int64_t n, void* stream);
 int lte_mimo_detect(const lte_plan*, const lte_c32* Y, const lte_c32* H, const lte_c32* W_host,
-                    int32_t T, int32_t L, double sigma2, int32_t detector, lte_c32* out, int window,
-                    int64_t B, int32_t R, int32_t S, void* stream);
+                    int32_t T, int32_t L, double sigma2, const double* sigma2_streams, int32_t detector,
+                    lte_c32* out, int window, int64_t B, int32_t R, int32_t S, void* stream);
 
 /* --- beamforming (rank-1 precoding over a flat R x T channel) ---------------
  * The reference path OFDMSimulator.simulate_beamforming (core/ofdm_core.py:2260-2477) stays in

@@ -193,8 +193,8 @@ __device__ void mmse_solve(const cd (*Heff)[SM_MAX_LAYERS], const cd* y, int R, 
 
 __global__ void __launch_bounds__(128)
 mimo_detect_kernel(const DevPlan P, const SmPrecoder W, const float2* __restrict__ Y, const float2* __restrict__ H,
-                   float2* __restrict__ out, int k0, int nk, int R, int S, double sigma2, int detector,
-                   long long rows, long long total) {
+                   float2* __restrict__ out, int k0, int nk, int R, int S, double sigma2_all,
+                   const double* __restrict__ sigma2_streams, int detector, long long rows, long long total) {
     const int L = W.L, T = W.T;
     const int npos = (P.Nd + L - 1) / L;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
@@ -204,6 +204,7 @@ mimo_detect_kernel(const DevPlan P, const SmPrecoder W, const float2* __restrict
         const long long b = bs / S;
         const int s = (int)(bs % S);
         const int kk = P.data_idx[p] - k0;
+        const double sigma2 = sigma2_streams ? sigma2_streams[b] : sigma2_all;
         cd Heff[SM_MAX_RX][SM_MAX_LAYERS], y[SM_MAX_RX];
         for (int r = 0; r < R; ++r) {
             const size_t row = (size_t)b * R + r;
@@ -278,8 +279,8 @@ mimo_detect_kernel(const DevPlan P, const SmPrecoder W, const float2* __restrict
 }
 
 extern "C" int lte_mimo_detect(const lte_plan* p, const lte_c32* Y, const lte_c32* H, const lte_c32* W_host,
-                               int32_t T, int32_t L, double sigma2, int32_t detector, lte_c32* out, int window,
-                               int64_t B, int32_t R, int32_t S, void* stream) {
+                               int32_t T, int32_t L, double sigma2, const double* sigma2_streams, int32_t detector,
+                               lte_c32* out, int window, int64_t B, int32_t R, int32_t S, void* stream) {
     if (!p || !Y || !H || !out || B < 0 || S < 1 || R < 1 || R > SM_MAX_RX) return LTE_ERR_INVALID_ARG;
     if (detector < DET_MMSE || detector > DET_MRC) return LTE_ERR_INVALID_ARG;
     if (R < L) return LTE_ERR_INVALID_ARG;                  // core/mimo_detector.py:34-35
@@ -296,8 +297,8 @@ extern "C" int lte_mimo_detect(const lte_plan* p, const lte_c32* Y, const lte_c3
     long long grid = (total + 127) / 128;
     if (grid > 148 * 16) grid = 148 * 16;
     mimo_detect_kernel<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(
-        p->dev, W, (const float2*)Y, (const float2*)H, (float2*)out, k0, nk, R, S, sigma2, detector,
-        (long long)B * R, total);
+        p->dev, W, (const float2*)Y, (const float2*)H, (float2*)out, k0, nk, R, S, sigma2, sigma2_streams,
+        detector, (long long)B * R, total);
     LTE_CHECK_CUDA(cudaGetLastError());
     return LTE_OK;
 }

@@ -87,7 +87,7 @@ _SIGS = {
     'lte_sfbc_decode': ([_P, _P, _P, _P, _P, C.c_int, _I64, _I32, _I32, _P], C.c_int),
     'lte_sm_precode': ([_P, _P, _P, _P, _I32, _I32, _P, _P, _I64, _I32, _P], C.c_int),
     'lte_flat_mimo': ([_P, _P, _P, _P, _P, _I64, _I32, _I32, _I64, _P], C.c_int),
-    'lte_mimo_detect': ([_P, _P, _P, _P, _I32, _I32, C.c_double, _I32, _P, C.c_int, _I64, _I32, _I32, _P], C.c_int),
+    'lte_mimo_detect': ([_P, _P, _P, _P, _I32, _I32, C.c_double, _P, _I32, _P, C.c_int, _I64, _I32, _I32, _P], C.c_int),
     'lte_demap_count': ([_P, _P, _P, _P, _P, _I64, _I64, _I64, _P], C.c_int),
     'lte_mrc_demap_count': ([_P, _P, _P, _P, _P, C.c_int, _I64, _I64, _I32, _I32, _P], C.c_int),
     'lte_fp32_peak_launch': ([_P, _I32, _P], C.c_int64),

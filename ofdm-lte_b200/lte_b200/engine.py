@@ -428,13 +428,21 @@ class LinkEngine:
         return out, power
 
     def mimo_detect(self, Y, H, W, sigma2, detector, B, R, S, window=nat.WINDOW_FULL):
-        """Y [B*R, S, nk], H [T, B*R, S, nk] -> detected symbols [B, S*Nd] (demapped layer order)."""
+        """Y [B*R, S, nk], H [T, B*R, S, nk] -> detected symbols [B, S*Nd] (demapped layer order).
+        sigma2: one float for every stream, or a float64 device tensor [B] (one noise variance per stream)."""
         Wc, wp, T, L = self._w_host(W)
+        per_stream = None
+        if torch.is_tensor(sigma2):
+            per_stream = sigma2.to(device=self.device, dtype=torch.float64).contiguous()
+            if per_stream.numel() != B:
+                raise ValueError("per-stream sigma2 must hold one value per stream")
+            sigma2 = 0.0
         det = self.DETECTORS.get(str(detector).upper())
         if det is None:
             raise ValueError(f"Detector '{detector}' no soportado")
         out = torch.zeros((B, S * self.Nd), dtype=torch.complex64, device=self.device)
-        nat.check(nat.lib.lte_mimo_detect(self._plan, _ptr(Y), _ptr(H), wp, T, L, float(sigma2), det, _ptr(out),
+        nat.check(nat.lib.lte_mimo_detect(self._plan, _ptr(Y), _ptr(H), wp, T, L, float(sigma2),
+                                          _ptr(per_stream) if per_stream is not None else None, det, _ptr(out),
                                           window, B, R, S, self._stream()), 'lte_mimo_detect')
         self.launches += 1
         return out
@@ -506,8 +514,9 @@ class LinkEngine:
 
     def sm_ber(self, chan, W, snr_db, B, S, R, detector, seed, stream_id0=0, idx=None):
         """One pass of the TM4-like spatial-multiplexing chain (reference simulate_spatial_multiplexing,
-        core/ofdm_core.py:2489-2815) over B independent streams that share the precoder W [T, L] and the
-        SNR (the detectors take sigma^2 = 10^(-snr/10) as one scalar per launch): layer mapping +
+        core/ofdm_core.py:2489-2815) over B independent streams that share the precoder W [T, L].  `snr_db` is
+        one float for every stream or a sequence / tensor of B values (stream b runs at snr_db[b]; the detectors
+        then take sigma^2 = 10^(-snr/10) per stream, so a sweep's SNR points share one pass): layer mapping +
         precoding, per-TX interleaved CRS, R x T independently faded links summed per RX antenna
         (`chan` built with gain_conversions=3 as that path does), AWGN from each antenna's measured power,
         CRS estimate of every TX antenna on EVERY OFDM symbol, MMSE / ZF / SIC / MRC detection on
@@ -522,7 +531,15 @@ class LinkEngine:
         tx, _, _ = self.modulate(S, symbols=data, T=T, want_stats=False)
         ph = self.random_phases(B, R * T * chan.num_taps * nat.LTE_JAKES_TONES, seed, stream_id0)
         rx, power = self.channel(tx, chan, B, R, T=T, phases=ph)
-        snr_rows = torch.full((B * R,), float(10 ** (snr_db / 10)), dtype=torch.float32, device=self.device)
+        if torch.is_tensor(snr_db) or np.ndim(snr_db) > 0:
+            snr_b = torch.as_tensor(snr_db, dtype=torch.float64, device=self.device).reshape(-1)
+            if snr_b.numel() != B:
+                raise ValueError("per-stream snr_db must hold one value per stream")
+            snr_rows = torch.pow(10.0, snr_b / 10).to(torch.float32).repeat_interleave(R).contiguous()
+            sigma2 = torch.pow(10.0, -snr_b / 10)
+        else:
+            snr_rows = torch.full((B * R,), float(10 ** (snr_db / 10)), dtype=torch.float32, device=self.device)
+            sigma2 = 10 ** (-snr_db / 10)
         # only the occupied bins travel: FFT window, per-TX estimates (written straight into one [T, ...] tensor) and detector
         k0, nk = self.window(nat.WINDOW_USEFUL)
         Y = self.rx_fft(rx.view(B * R, -1), B * R, S, nat.WINDOW_USEFUL, power=power, snr_lin=snr_rows, seed=seed,
@@ -531,7 +548,7 @@ class LinkEngine:
         for t in range(T):
             self.estimate(Y.view(B * R * S, 1, nk), B * R * S, 1, nat.WINDOW_USEFUL, pilot_set=t,
                           out=H[t].view(B * R * S, 1, nk))
-        sym = self.mimo_detect(Y, H, W, 10 ** (-snr_db / 10), detector, B, R, S, nat.WINDOW_USEFUL)
+        sym = self.mimo_detect(Y, H, W, sigma2, detector, B, R, S, nat.WINDOW_USEFUL)
         errors, _ = self.demap_count(sym, idx_tx=idx, nbits=S * self.Nd * self.bps)
         return errors
 

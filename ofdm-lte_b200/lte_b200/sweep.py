@@ -323,8 +323,10 @@ def sm_sweep(config, snr_db, n_trials, num_tx=4, num_rx=4, rank=4, detector='MMS
     """BASELINE config 5: Monte-Carlo BER of T x R spatial multiplexing with codebook precoding and an
     MMSE / ZF / SIC / MRC detector (reference simulate_spatial_multiplexing), trials sharded over ranks.
 
-    The detectors take sigma^2 as one scalar per launch, so a launch is (one SNR point, a run of
-    consecutive trials); stream ids are SNR-major here: id = snr_index * n_trials + trial.
+    With a fixed rank all SNR points of a run of trials share one pass (the detector takes sigma^2 per stream);
+    stream ids are trial-major there, id = trial * n_snr + snr_index, so a pass is one contiguous id range.
+    With adaptive rank the precoder changes with the SNR point and the feedback block, so a pass is (one SNR
+    point, one block) and ids are SNR-major: id = snr_index * n_trials + trial.
     rank 1..4: `precoder(rank) -> W [T, rank]` (codebook entry 0, the reference's fixed-rank branch).
     rank 'adaptive': the reference draws an H_initial unrelated to the channel and feeds it to
     RankAdaptation; here one H_initial is drawn on the host per (SNR point, block of `feedback_block`
@@ -348,6 +350,13 @@ def sm_sweep(config, snr_db, n_trials, num_tx=4, num_rx=4, rank=4, detector='MMS
     rank_hist = torch.zeros((n_snr, 4), dtype=torch.int64, device=eng.device)
 
     def count_batch(trial_lo, n):
+        if not adaptive:
+            # all SNR points in one pass: stream j of the pass is (trial trial_lo + j // n_snr, snr j % n_snr)
+            snr_streams = torch.tensor(snr_db, dtype=torch.float64, device=eng.device).repeat(n)
+            err = eng.sm_ber(chan, precoder(int(rank)), snr_streams, n * n_snr, S, R, detector, seed,
+                             stream_id0=trial_lo * n_snr)
+            rank_hist[:, int(rank) - 1] += n
+            return err.reshape(-1)
         err = torch.zeros((n, n_snr), dtype=torch.int64, device=eng.device)
         for si, snr in enumerate(snr_db):
             t = trial_lo

@@ -167,3 +167,28 @@ def test_sm_sweep_fixed_and_adaptive_rank():
     assert abs(loop - big) / max(big, 1e-9) < 0.35
     with pytest.raises(ValueError):
         sm_sweep(cfg, snrs, 4, rank='adaptive', **kw)
+
+
+def test_sm_ber_per_stream_snr_equals_per_snr_passes():
+    """lte_mimo_detect with one sigma^2 per stream: a pass whose streams run at different SNR points gives, stream
+    by stream, the counts of separate single-SNR passes on the same stream ids (so a sweep may put all its SNR
+    points into one launch)."""
+    import torch
+    from config import LTEConfig
+    from core.codebook_lte import LTECodebook
+    from lte_b200 import LinkEngine, chan_for, tables
+    cfg = LTEConfig(1.25, 15.0, '16-QAM')
+    eng0 = LinkEngine.from_config(cfg)
+    eng = LinkEngine.from_config(cfg, pilot_sets=tables.mimo_pilot_sets(4, eng0.Np))
+    chan = chan_for('rayleigh_mp', cfg.fs, 'Pedestrian_A', 2.0, 3.0, gain_conversions=3)
+    W = LTECodebook(4, transmission_mode='TM4', rank=2).get_precoder(0)
+    snrs = [4.0, 12.0, 25.0]
+    for det in ('MMSE', 'SIC'):
+        B = 6
+        per_stream = [snrs[b % 3] for b in range(B)]
+        batched = eng.sm_ber(chan, W, per_stream, B, 2, 4, det, seed=3, stream_id0=50).cpu()
+        for b in range(B):
+            single = eng.sm_ber(chan, W, per_stream[b], 1, 2, 4, det, seed=3, stream_id0=50 + b).cpu()
+            assert int(single[0]) == int(batched[b]), (det, b)
+    with pytest.raises(ValueError):
+        eng.sm_ber(chan, W, [4.0, 5.0], 3, 2, 4, 'MMSE', seed=3)

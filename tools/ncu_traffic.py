@@ -2,7 +2,7 @@
 """profiles/rNN_traffic.json from an `ncu --set full` report of tools/stage_bench.py: per stage of the bench, the
 dram__bytes_read.sum + dram__bytes_write.sum and duration of ONE launch of its dominant kernel.  bench.py reads
 `roofline.traffic` from this file and refuses to run if the kernel it reports is not in it.
-usage: python tools/ncu_traffic.py report.ncu-rep subframes_per_launch out.json"""
+usage: python tools/ncu_traffic.py out.json subframes_per_launch report.ncu-rep [more.ncu-rep ...]"""
 import csv
 import json
 import subprocess
@@ -23,24 +23,26 @@ def to_bytes(v, unit):
 
 
 def main():
-    rep, per_launch, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units = rows[0], rows[1]
-    col = {h: i for i, h in enumerate(hdr)}
+    out, per_launch, reps = sys.argv[1], int(sys.argv[2]), sys.argv[3:]
     kernels = {}
-    for r in rows[2:]:
-        name = r[col['Kernel Name']]
-        for stage, sub in STAGE_KERNELS.items():
-            if sub in name and (stage != 'channel_rx_fft' or 'channel_rx_fft' in name) and (stage != 'rx_fft' or 'channel' not in name):
-                rd = to_bytes(r[col['dram__bytes_read.sum']], units[col['dram__bytes_read.sum']])
-                wr = to_bytes(r[col['dram__bytes_write.sum']], units[col['dram__bytes_write.sum']])
-                dur = float(r[col['gpu__time_duration.sum']])
-                du = units[col['gpu__time_duration.sum']]
-                dur_us = dur * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 'usecond': 1.0, 'msecond': 1e3, 'nsecond': 1e-3}.get(du, 1.0)
-                kernels[stage] = {'kernel': name[:120], 'dram_bytes': rd + wr, 'dram_read': rd, 'dram_write': wr,
-                                  'duration_us': dur_us}
-    json.dump({'source': f'ncu --set full --clock-control none, {rep.split("/")[-1]} (tools/stage_bench.py, one launch per kernel)',
+    for rep in reps:
+        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units = rows[0], rows[1]
+        col = {h: i for i, h in enumerate(hdr)}
+        for r in rows[2:]:
+            name = r[col['Kernel Name']]
+            for stage, sub in STAGE_KERNELS.items():
+                if sub in name and (stage != 'rx_fft' or 'channel' not in name) and (stage != 'mrc_demap_count' or 'compact' not in name):
+                    rd = to_bytes(r[col['dram__bytes_read.sum']], units[col['dram__bytes_read.sum']])
+                    wr = to_bytes(r[col['dram__bytes_write.sum']], units[col['dram__bytes_write.sum']])
+                    dur = float(r[col['gpu__time_duration.sum']])
+                    du = units[col['gpu__time_duration.sum']]
+                    dur_us = dur * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 'usecond': 1.0, 'msecond': 1e3, 'nsecond': 1e-3}.get(du, 1.0)
+                    kernels[stage] = {'kernel': name[:120], 'report': rep.split('/')[-1], 'dram_bytes': rd + wr, 'dram_read': rd,
+                                      'dram_write': wr, 'duration_us': dur_us}
+    json.dump({'source': 'ncu --set full --clock-control none of tools/stage_bench.py --pipeline spectral|fused|staged, one launch '
+                         'per kernel (' + ', '.join(r.split('/')[-1] for r in reps) + ')',
                'subframes_per_launch': per_launch, 'kernels': kernels}, open(out, 'w'), indent=1)
     print(json.dumps({k: round(v['dram_bytes'] / 1e9, 3) for k, v in kernels.items()}))
 
