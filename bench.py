@@ -333,7 +333,8 @@ def run_gpu(args, rank, world):
     # ---- end to end through the package's host-buffer API: packed bits in pinned memory -> errors on host
     nbytes = (nbits + 7) // 8
     host_bits = torch.from_numpy(np.random.RandomState(7 + rank).randint(0, 256, (B, nbytes), dtype=np.uint8)).pin_memory()
-    pipe = eng.stream_host_batches(chan, R, snr_rows, B, S, nbits=nbits, seed=seed + 1, noise_domain=nd, fused=fused)
+    pipe = eng.stream_host_batches(chan, R, snr_rows, B, S, nbits=nbits, seed=seed + 1, noise_domain=nd, fused=fused,
+                                   spectral=spectral)
     e2e_steps = max(2, min(args.steps, 10))
 
     def host_batches(n, i0):

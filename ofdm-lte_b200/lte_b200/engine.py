@@ -754,13 +754,13 @@ class LinkEngine:
 
     # ------------------------------------------------------------------ host-buffer front end
     def stream_host_batches(self, chan, num_rx, snr_lin_rows, B, S, nbits=None, seed=0, noise_domain=3, fused=True,
-                            depth=3):
+                            depth=3, spectral=None):
         """Pipeline that takes payload batches from HOST memory (np.packbits rows, ideally pinned) and returns the
         per-stream bit-error counts in pinned host memory, overlapping the H2D copy of the next batch with the
         kernels of the current one (lte_b200/host_stream.py)."""
         from .host_stream import HostBatchPipeline
         return HostBatchPipeline(self, chan, num_rx, snr_lin_rows, B, S, nbits=nbits, seed=seed,
-                                 noise_domain=noise_domain, fused=fused, depth=depth)
+                                 noise_domain=noise_domain, fused=fused, depth=depth, spectral=spectral)
 
     # ------------------------------------------------------------------ batched SIMO chain
     def workspace(self, B, S, R, fading, fused=False, lazy=False):

@@ -63,14 +63,16 @@ class HostBatchPipeline:
     batch run while the current one computes."""
 
     def __init__(self, engine, chan, num_rx, snr_lin_rows, B, S, nbits=None, seed=0, noise_domain=3, fused=True,
-                 depth=3):
+                 depth=3, spectral=None):
         self.eng, self.chan, self.R, self.B, self.S = engine, chan, int(num_rx), int(B), int(S)
         self.nbits = int(nbits) if nbits is not None else S * engine.Nd * engine.bps
         self.nbytes = (self.nbits + 7) // 8
         self.seed, self.noise_domain, self.fused, self.depth = int(seed), int(noise_domain), bool(fused), int(depth)
+        self.spectral = spectral                                # None: the engine picks (spectral link when it applies)
         dev = engine.device
         self.snr_rows = snr_lin_rows.to(dev).contiguous()
-        self.ws = engine.workspace(self.B, self.S, self.R, fading=chan.num_taps > 0, fused=fused, lazy=fused)
+        self.ws = engine.workspace(self.B, self.S, self.R, fading=chan.num_taps > 0, fused=fused,
+                                   lazy=fused and spectral is not False)
         self.dev_bits = [torch.empty((self.B, self.nbytes), dtype=torch.uint8, device=dev) for _ in range(depth)]
         self.host_err = [torch.empty(self.B, dtype=torch.int64).pin_memory() for _ in range(depth)]
         self.copy_stream = torch.cuda.Stream(device=dev)
@@ -95,7 +97,8 @@ class HostBatchPipeline:
         main.wait_event(self.ev_copied[k])
         idx = self.eng.bits_to_indices(self.dev_bits[k], self.nbits, self.S, packed=True)
         err = self.eng.simo_ber(self.ws, self.chan, self.snr_rows, self.seed, stream_id0=int(stream_id0), idx=idx,
-                                nbits=self.nbits, fused=self.fused, noise_domain=self.noise_domain)
+                                nbits=self.nbits, fused=self.fused, spectral=self.spectral,
+                                noise_domain=self.noise_domain)
         self.host_err[k].copy_(err, non_blocking=True)
         self.ev_free[k].record(main)
         self.ev_done[k].record(main)
