@@ -92,3 +92,38 @@ def test_sweep_passes_stay_inside_their_buffers():
     torch.cuda.synchronize()
     for gg in (g, g2, g4):
         gg.check()
+
+
+@pytest.mark.parametrize('bw,mod,prof,B,S,R', [(2.5, '16-QAM', 'Pedestrian_A', 3, 15, 3), (5.0, '64-QAM', 'Pedestrian_B', 5, 14, 4),
+                                              (20.0, '64-QAM', 'Pedestrian_A', 2, 29, 1), (10.0, 'QPSK', 'Pedestrian_A', 4, 1, 2)])
+def test_spectral_link_stays_inside_its_buffers(bw, mod, prof, B, S, R):
+    """The spectral kernels (bulk-copy ring, 128-bit pair stores into the padded compact rows, per-warp power atomics)
+    on odd stream / symbol / antenna counts: every buffer of the workspace -- G, tails, compact grid, pilot side
+    buffer, pilot estimates, errors -- keeps its guard zones, and so does the caller-owned coefficient workspace."""
+    from lte_b200 import chan_for
+    eng, g = _engine(bw, mod)
+    scratch = {}
+
+    def guarded_scratch(nbytes):                       # same contract as LinkEngine._scratch, with guard zones
+        n = max(int(nbytes), 256)
+        if 'buf' not in scratch or scratch['n'] < n:
+            flat = torch.empty(n + 2 * PAD, dtype=torch.uint8, device=eng.device)
+            flat.fill_(0xA5)
+            g.blocks.append(flat)
+            scratch.update(buf=flat[PAD:PAD + n], n=n)
+        return scratch['buf']
+    eng._scratch = guarded_scratch
+    chan = chan_for('rayleigh_mp', eng.fs, prof, 2.0, 3.0)
+    rows = torch.full((B * R,), 31.6, dtype=torch.float32, device='cuda')
+    for nd in (2, 3):
+        ws = eng.workspace(B, S, R, fading=True, fused=True, lazy=True)
+        err = eng.simo_ber(ws, chan, rows, 1, stream_id0=7, fused=True, noise_domain=nd)
+        assert ws.get('spectral') is True and err.shape == (B,)
+    # the windowed (non-compact) output of the same kernel
+    idx = eng.random_indices(B, S, 1, 0)
+    G, tail = eng.tx_spectral(S, idx)
+    ph = eng.random_phases(B, R * chan.num_taps * 16, 1, 0)
+    Y, pw = eng.channel_spectral(idx, G, tail, chan, B, R, S, ph)
+    torch.cuda.synchronize()
+    g.check()
+    assert bool(torch.isfinite(torch.view_as_real(Y)).all()) and bool((pw > 0).all())
