@@ -339,6 +339,10 @@ int lte_sfbc_decode(const lte_plan*, const lte_c32* Y, const lte_c32* H0, const 
  * H_eff = H W per data position: Y [B][R][S][nk]; H [T][B*R][S][nk] (per-symbol estimates, one
  * lte_crs_ls_interp per TX pilot set); out [B][S][Nd] in the LayerMapper.demap_from_layers order
  * (core/layer_mapper.py:88-115).  detector: LTE_DET_*; SIC slices with the plan's constellation.
+ * H may be NULL: the detector then forms the per-symbol CRS estimate of every TX antenna at its bin itself
+ * from Y's pilot bins (LS at the two neighbouring pilots of set t, linear in between, edge hold) -- bit for bit
+ * the value lte_crs_ls_interp(pilot_set = t, rows = B*R*S, S = 1) would have written, without the T passes
+ * over Y and the [T][B*R][S][nk] tensor (the plan must carry the T pilot sets).
  * sigma2_streams (optional, device, double [B]): one noise variance per stream, which lets a sweep put
  * all its SNR points into one launch; NULL = the scalar `sigma2` for every stream. */
 int lte_sm_precode(const lte_plan*, const uint8_t* idx, const lte_c32* symbols, const lte_c32* W_host,

@@ -212,7 +212,30 @@ mimo_detect_kernel(const DevPlan P, const SmPrecoder W, const float2* __restrict
             y[r] = {(double)yv.x, (double)yv.y};
             for (int l = 0; l < L; ++l) Heff[r][l] = {0.0, 0.0};
             for (int t = 0; t < T; ++t) {
-                const float2 hv = H[(((size_t)t * rows + row) * S + s) * nk + kk];
+                float2 hv;
+                if (H) {
+                    hv = H[(((size_t)t * rows + row) * S + s) * nk + kk];
+                } else {
+                    // the per-symbol CRS estimate of TX antenna t at this bin, straight from the symbol's pilot bins:
+                    // LS at the two neighbouring pilots of set t, then start + i * (delta / div) -- operation for
+                    // operation what crs_ls_interp_kernel writes into H (core/lte_receiver.py:62-133)
+                    const int cnt = P.pset_cnt[t];
+                    const int16_t* pbin = P.pset_bin + (size_t)t * P.Np;
+                    const float2* pinv = P.pset_inv + (size_t)t * P.Np;
+                    const float2* yrow = Y + (row * S + s) * nk;
+                    const int k = kk + k0;
+                    const int lo = P.pset_seg[(size_t)t * P.N + k];
+                    const int la = lo < 0 ? 0 : (lo >= cnt - 1 ? cnt - 1 : lo);
+                    const int i1 = pbin[la];
+                    const float2 a = cmul(yrow[i1 - k0], pinv[la]);
+                    hv = a;
+                    if (lo >= 0 && lo < cnt - 1 && k != i1) {
+                        const int i2 = pbin[la + 1];
+                        const float2 c = cmul(yrow[i2 - k0], pinv[la + 1]);
+                        const float div = (float)(i2 - i1), tt = (float)(k - i1);
+                        hv = make_float2(fmaf(tt, __fdiv_rn(c.x - a.x, div), a.x), fmaf(tt, __fdiv_rn(c.y - a.y, div), a.y));
+                    }
+                }
                 const cd hd = {(double)hv.x, (double)hv.y};
                 for (int l = 0; l < L; ++l)
                     Heff[r][l] = cdadd(Heff[r][l], cdmul(hd, {(double)W.w[t][l].x, (double)W.w[t][l].y}));
@@ -281,7 +304,8 @@ mimo_detect_kernel(const DevPlan P, const SmPrecoder W, const float2* __restrict
 extern "C" int lte_mimo_detect(const lte_plan* p, const lte_c32* Y, const lte_c32* H, const lte_c32* W_host,
                                int32_t T, int32_t L, double sigma2, const double* sigma2_streams, int32_t detector,
                                lte_c32* out, int window, int64_t B, int32_t R, int32_t S, void* stream) {
-    if (!p || !Y || !H || !out || B < 0 || S < 1 || R < 1 || R > SM_MAX_RX) return LTE_ERR_INVALID_ARG;
+    if (!p || !Y || !out || B < 0 || S < 1 || R < 1 || R > SM_MAX_RX) return LTE_ERR_INVALID_ARG;
+    if (!H && (p->nsets < T || p->dev.Np == 0)) return LTE_ERR_INVALID_ARG;    // estimating needs the T pilot sets
     if (detector < DET_MMSE || detector > DET_MRC) return LTE_ERR_INVALID_ARG;
     if (R < L) return LTE_ERR_INVALID_ARG;                  // core/mimo_detector.py:34-35
     if (detector == DET_MRC && L != 1) return LTE_ERR_INVALID_ARG;

@@ -429,6 +429,7 @@ class LinkEngine:
 
     def mimo_detect(self, Y, H, W, sigma2, detector, B, R, S, window=nat.WINDOW_FULL):
         """Y [B*R, S, nk], H [T, B*R, S, nk] -> detected symbols [B, S*Nd] (demapped layer order).
+        H=None: the detector forms the per-symbol CRS estimates itself from Y's pilot bins (same values, no H tensor).
         sigma2: one float for every stream, or a float64 device tensor [B] (one noise variance per stream)."""
         Wc, wp, T, L = self._w_host(W)
         per_stream = None
@@ -441,7 +442,7 @@ class LinkEngine:
         if det is None:
             raise ValueError(f"Detector '{detector}' no soportado")
         out = torch.zeros((B, S * self.Nd), dtype=torch.complex64, device=self.device)
-        nat.check(nat.lib.lte_mimo_detect(self._plan, _ptr(Y), _ptr(H), wp, T, L, float(sigma2),
+        nat.check(nat.lib.lte_mimo_detect(self._plan, _ptr(Y), _ptr(H) if H is not None else None, wp, T, L, float(sigma2),
                                           _ptr(per_stream) if per_stream is not None else None, det, _ptr(out),
                                           window, B, R, S, self._stream()), 'lte_mimo_detect')
         self.launches += 1
@@ -512,14 +513,15 @@ class LinkEngine:
         errors, _ = self.demap_count(dec, idx_tx=idx, nbits=S * nd2 * self.bps)
         return errors
 
-    def sm_ber(self, chan, W, snr_db, B, S, R, detector, seed, stream_id0=0, idx=None):
+    def sm_ber(self, chan, W, snr_db, B, S, R, detector, seed, stream_id0=0, idx=None, estimate_tensor=False):
         """One pass of the TM4-like spatial-multiplexing chain (reference simulate_spatial_multiplexing,
         core/ofdm_core.py:2489-2815) over B independent streams that share the precoder W [T, L].  `snr_db` is
         one float for every stream or a sequence / tensor of B values (stream b runs at snr_db[b]; the detectors
         then take sigma^2 = 10^(-snr/10) per stream, so a sweep's SNR points share one pass): layer mapping +
         precoding, per-TX interleaved CRS, R x T independently faded links summed per RX antenna
         (`chan` built with gain_conversions=3 as that path does), AWGN from each antenna's measured power,
-        CRS estimate of every TX antenna on EVERY OFDM symbol, MMSE / ZF / SIC / MRC detection on
+        CRS estimate of every TX antenna on EVERY OFDM symbol (formed inside the detector from the pilot bins
+        unless `estimate_tensor`), MMSE / ZF / SIC / MRC detection on
         H_eff = H W, slicer, count.  The engine must carry tables.mimo_pilot_sets(T, Np)."""
         W = np.asarray(W, dtype=complex)
         T = W.shape[0]
@@ -544,10 +546,12 @@ class LinkEngine:
         k0, nk = self.window(nat.WINDOW_USEFUL)
         Y = self.rx_fft(rx.view(B * R, -1), B * R, S, nat.WINDOW_USEFUL, power=power, snr_lin=snr_rows, seed=seed,
                         row_id0=stream_id0 * R, noise_domain=1)
-        H = self._empty((T, B * R, S, nk), torch.complex64)
-        for t in range(T):
-            self.estimate(Y.view(B * R * S, 1, nk), B * R * S, 1, nat.WINDOW_USEFUL, pilot_set=t,
-                          out=H[t].view(B * R * S, 1, nk))
+        H = None                        # the detector estimates from Y's pilot bins itself (bit-identical values)
+        if estimate_tensor:             # the explicit per-TX estimate passes, kept for the API path and the tests
+            H = self._empty((T, B * R, S, nk), torch.complex64)
+            for t in range(T):
+                self.estimate(Y.view(B * R * S, 1, nk), B * R * S, 1, nat.WINDOW_USEFUL, pilot_set=t,
+                              out=H[t].view(B * R * S, 1, nk))
         sym = self.mimo_detect(Y, H, W, sigma2, detector, B, R, S, nat.WINDOW_USEFUL)
         errors, _ = self.demap_count(sym, idx_tx=idx, nbits=S * self.Nd * self.bps)
         return errors

@@ -192,3 +192,34 @@ def test_sm_ber_per_stream_snr_equals_per_snr_passes():
             assert int(single[0]) == int(batched[b]), (det, b)
     with pytest.raises(ValueError):
         eng.sm_ber(chan, W, [4.0, 5.0], 3, 2, 4, 'MMSE', seed=3)
+
+
+def test_detector_estimating_from_the_pilot_bins_equals_the_estimate_tensor():
+    """lte_mimo_detect(H = NULL) forms the per-symbol CRS estimates from Y's pilot bins itself: symbols and counts
+    are bit-identical to the explicit lte_crs_ls_interp passes + H tensor, for every detector."""
+    import torch
+    from config import LTEConfig
+    from core.codebook_lte import LTECodebook
+    from lte_b200 import LinkEngine, chan_for, tables
+    from lte_b200 import _native as nat
+    for bw, mod, T, rank in ((1.25, '16-QAM', 4, 2), (5.0, '64-QAM', 2, 2), (2.5, 'QPSK', 4, 4)):
+        cfg = LTEConfig(bw, 15.0, mod)
+        eng0 = LinkEngine.from_config(cfg)
+        eng = LinkEngine.from_config(cfg, pilot_sets=tables.mimo_pilot_sets(T, eng0.Np))
+        chan = chan_for('rayleigh_mp', cfg.fs, 'Pedestrian_A', 2.0, 3.0, gain_conversions=3)
+        W = LTECodebook(T, transmission_mode='TM4', rank=rank).get_precoder(0)
+        for det in ('MMSE', 'ZF', 'SIC'):
+            a = eng.sm_ber(chan, W, 14.0, 5, 3, 4, det, seed=9, stream_id0=2, estimate_tensor=True)
+            b = eng.sm_ber(chan, W, 14.0, 5, 3, 4, det, seed=9, stream_id0=2)
+            assert torch.equal(a, b), (bw, det)
+        # symbols, not only counts
+        B, R, S = 3, 4, 2
+        k0, nk = eng.window(nat.WINDOW_USEFUL)
+        g = torch.Generator(device='cuda').manual_seed(1)
+        Y = torch.view_as_complex(torch.randn((B * R, S, nk, 2), generator=g, device='cuda'))
+        H = torch.empty((T, B * R, S, nk), dtype=torch.complex64, device='cuda')
+        for t in range(T):
+            eng.estimate(Y.view(B * R * S, 1, nk), B * R * S, 1, nat.WINDOW_USEFUL, pilot_set=t, out=H[t].view(B * R * S, 1, nk))
+        s1 = eng.mimo_detect(Y, H, W, 0.05, 'MMSE', B, R, S, nat.WINDOW_USEFUL)
+        s2 = eng.mimo_detect(Y, None, W, 0.05, 'MMSE', B, R, S, nat.WINDOW_USEFUL)
+        assert torch.equal(torch.view_as_real(s1), torch.view_as_real(s2))
