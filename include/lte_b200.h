@@ -325,6 +325,13 @@ int lte_sfbc_encode(const lte_plan*, const uint8_t* idx, const lte_c32* symbols,
                     lte_c32* qam_out, int64_t B, int32_t S, void* stream);
 int lte_sfbc_decode(const lte_plan*, const lte_c32* Y, const lte_c32* H0, const lte_c32* H1,
                     lte_c32* out, int window, int64_t B, int32_t R, int32_t S, void* stream);
+/* lte_sfbc_decode fused with lte_demap_count (QAMModulator.symbols_to_bits + calculate_ber,
+ * core/modulator.py:90-112, core/ofdm_core.py:245-268): the decoded symbols are sliced and compared with
+ * idx_tx [B][S][2*(Nd/2)] in registers; errors[b] (caller zeroes) += bit errors among the first nbits bits
+ * of stream b.  Same decoded values, hence the same counts, as the two separate calls. */
+int lte_sfbc_decode_count(const lte_plan*, const lte_c32* Y, const lte_c32* H0, const lte_c32* H1,
+                          const uint8_t* idx_tx, unsigned long long* errors, int64_t nbits, int window,
+                          int64_t B, int32_t R, int32_t S, void* stream);
 
 /* --- spatial multiplexing (TM4-like, up to 8 TX / 8 RX / 4 layers) ------------------------
  * lte_sm_precode replaces LayerMapper.map_to_layers (core/layer_mapper.py:35-86) and the

@@ -1,5 +1,5 @@
 // Transmit-diversity (SFBC Alamouti) stage kernels.
-#include "common.cuh"
+#include "slicer.cuh"
 
 // ------------------------------------------------------------------------------ SFBC encode
 // core/sfbc_alamouti.py:45-78: pairs (k, k+1) of data symbols -> TX0 [s0, -conj(s1)],
@@ -61,14 +61,20 @@ extern "C" int lte_sfbc_encode(const lte_plan* p, const uint8_t* idx, const lte_
 // ------------------------------------------------------------------------------ SFBC decode
 // core/sfbc_alamouti.py:132-161 per receive antenna, then the plain average over antennas of
 // core/ofdm_core.py:2204.  thread = (stream, pair); channel estimates of the slot stay in registers.
-template <int R>
+// COUNT: the decoded pair goes straight through the slicer and the bit-error count against idx_tx
+// (core/modulator.py:90-112, core/ofdm_core.py:245-268) instead of to memory -- the sweep's form.
+template <int R, bool COUNT>
 __global__ void __launch_bounds__(128)
 sfbc_decode_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restrict__ H0,
-                   const float2* __restrict__ H1, float2* __restrict__ out, int k0, int nk, int S, int nslot,
+                   const float2* __restrict__ H1, float2* __restrict__ out, const uint8_t* __restrict__ idx_tx,
+                   unsigned long long* __restrict__ errors, long long nbits, int k0, int nk, int S, int nslot,
                    int npair, int gx) {
     const long long b = blockIdx.x / gx;
-    const int pr = (blockIdx.x % gx) * blockDim.x + threadIdx.x;
-    if (pr >= npair) return;
+    const int pr0 = (blockIdx.x % gx) * blockDim.x + threadIdx.x;
+    const bool act = pr0 < npair;
+    if (!COUNT && !act) return;
+    const int pr = act ? pr0 : npair - 1;            // counting CTAs stay whole for the block reduction
+    unsigned int e = 0;
     const int ka = P.data_idx[2 * pr] - k0, kb = P.data_idx[2 * pr + 1] - k0;
     const float invR = 1.0f / (float)R;
     for (int slot = 0; slot < nslot; ++slot) {
@@ -97,29 +103,42 @@ sfbc_decode_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* 
                 a0.x += __fdiv_rn(t0.x + u0.x, nrm[r]); a0.y += __fdiv_rn(t0.y + u0.y, nrm[r]);
                 a1.x += __fdiv_rn(t1.x - u1.x, nrm[r]); a1.y += __fdiv_rn(t1.y - u1.y, nrm[r]);
             }
-            float2* o = out + ((size_t)b * S + s) * 2 * npair + 2 * pr;
-            o[0] = make_float2(a0.x * invR, a0.y * invR);
-            o[1] = make_float2(a1.x * invR, a1.y * invR);
+            const size_t q = ((size_t)b * S + s) * 2 * npair + 2 * pr;
+            const float2 d0 = make_float2(a0.x * invR, a0.y * invR), d1 = make_float2(a1.x * invR, a1.y * invR);
+            if (COUNT) {
+                const long long left = nbits - ((long long)s * 2 * npair + 2 * pr) * P.bps;    // bits of the stream from here on
+                e += bit_errors(slice_symbol(P, d0), idx_tx[q], P.bps, left);
+                e += bit_errors(slice_symbol(P, d1), idx_tx[q + 1], P.bps, left - P.bps);
+            } else {
+                out[q] = d0;
+                out[q + 1] = d1;
+            }
         }
     }
+    if (COUNT) block_add_errors(act ? e : 0u, &errors[b]);
 }
 
-extern "C" int lte_sfbc_decode(const lte_plan* p, const lte_c32* Y, const lte_c32* H0, const lte_c32* H1,
-                               lte_c32* out, int window, int64_t B, int32_t R, int32_t S, void* stream) {
-    if (!p || !Y || !H0 || !H1 || !out || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
+static int launch_sfbc_decode(const lte_plan* p, const lte_c32* Y, const lte_c32* H0, const lte_c32* H1, lte_c32* out,
+                              const uint8_t* idx_tx, unsigned long long* errors, int64_t nbits, int window, int64_t B,
+                              int32_t R, int32_t S, void* stream) {
+    const bool count = idx_tx != nullptr;
+    if (!p || !Y || !H0 || !H1 || (!count && !out) || (count && !errors) || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
     int32_t k0, nk;
     int rc = lte_plan_window(p, window, &k0, &nk);
     if (rc) return rc;
     if (B == 0) return LTE_OK;
     const int npair = p->dev.Nd / 2;
+    if (npair < 1) return LTE_ERR_INVALID_ARG;
     const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
     const int gx = (npair + 127) / 128;
     const unsigned grid = (unsigned)((long long)gx * B);
     cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH_SFBC(RR)                                                                                      \
-    case RR:                                                                                                 \
-        sfbc_decode_kernel<RR><<<grid, 128, 0, st>>>(p->dev, (const float2*)Y, (const float2*)H0,            \
-                                                     (const float2*)H1, (float2*)out, k0, nk, S, nslot, npair, gx); \
+#define LAUNCH_SFBC2(RR, CC)                                                                                  \
+    sfbc_decode_kernel<RR, CC><<<grid, 128, 0, st>>>(p->dev, (const float2*)Y, (const float2*)H0, (const float2*)H1, \
+                                                     (float2*)out, idx_tx, errors, nbits, k0, nk, S, nslot, npair, gx)
+#define LAUNCH_SFBC(RR)                                                                                       \
+    case RR:                                                                                                  \
+        if (count) LAUNCH_SFBC2(RR, true); else LAUNCH_SFBC2(RR, false);                                      \
         break;
     switch (R) {
         LAUNCH_SFBC(1) LAUNCH_SFBC(2) LAUNCH_SFBC(3) LAUNCH_SFBC(4) LAUNCH_SFBC(5) LAUNCH_SFBC(6) LAUNCH_SFBC(7)
@@ -127,6 +146,20 @@ extern "C" int lte_sfbc_decode(const lte_plan* p, const lte_c32* Y, const lte_c3
         default: return LTE_ERR_INVALID_ARG;
     }
 #undef LAUNCH_SFBC
+#undef LAUNCH_SFBC2
     LTE_CHECK_CUDA(cudaGetLastError());
     return LTE_OK;
+}
+
+extern "C" int lte_sfbc_decode(const lte_plan* p, const lte_c32* Y, const lte_c32* H0, const lte_c32* H1,
+                               lte_c32* out, int window, int64_t B, int32_t R, int32_t S, void* stream) {
+    if (!out) return LTE_ERR_INVALID_ARG;
+    return launch_sfbc_decode(p, Y, H0, H1, out, nullptr, nullptr, 0, window, B, R, S, stream);
+}
+
+extern "C" int lte_sfbc_decode_count(const lte_plan* p, const lte_c32* Y, const lte_c32* H0, const lte_c32* H1,
+                                     const uint8_t* idx_tx, unsigned long long* errors, int64_t nbits, int window,
+                                     int64_t B, int32_t R, int32_t S, void* stream) {
+    if (!idx_tx || nbits < 0) return LTE_ERR_INVALID_ARG;
+    return launch_sfbc_decode(p, Y, H0, H1, nullptr, idx_tx, errors, nbits, window, B, R, S, stream);
 }

@@ -117,9 +117,12 @@ class LinkEngine:
         self.launches += 1
         return bits
 
-    def random_indices(self, B, S, seed, stream_id0=0, out=None):
-        idx = out if out is not None else self._empty((B, S * self.Nd), torch.uint8)
-        nat.check(nat.lib.lte_random_indices(self._plan, _ptr(idx), S * self.Nd, B, int(seed), int(stream_id0),
+    def random_indices(self, B, S, seed, stream_id0=0, out=None, nsym=None):
+        """Philox symbol indices [B, nsym] (default nsym = S * Nd), keyed (seed, stream id, position): a shorter
+        row is a prefix of a longer one."""
+        nsym = S * self.Nd if nsym is None else int(nsym)
+        idx = out if out is not None else self._empty((B, nsym), torch.uint8)
+        nat.check(nat.lib.lte_random_indices(self._plan, _ptr(idx), nsym, B, int(seed), int(stream_id0),
                                              self._stream()), 'lte_random_indices')
         self.launches += 1
         return idx
@@ -400,6 +403,19 @@ class LinkEngine:
     # ------------------------------------------------------------------ spatial multiplexing
     DETECTORS = {'MMSE': 0, 'IRC': 0, 'ZF': 1, 'SIC': 2, 'MRC': 3}
 
+    def sfbc_decode_count(self, Y, H0, H1, idx_tx, B, R, S, window=nat.WINDOW_FULL, nbits=None, errors=None):
+        """Alamouti decode + slicer + bit-error count in one kernel: int64 [B] errors against idx_tx [B, S*2*(Nd//2)]."""
+        nd2 = 2 * (self.Nd // 2)
+        nbits = S * nd2 * self.bps if nbits is None else int(nbits)
+        if errors is None:
+            errors = torch.zeros(B, dtype=torch.int64, device=self.device)
+        else:
+            errors.zero_()
+        nat.check(nat.lib.lte_sfbc_decode_count(self._plan, _ptr(Y), _ptr(H0), _ptr(H1), _ptr(idx_tx), _ptr(errors), nbits,
+                                                window, B, R, S, self._stream()), 'lte_sfbc_decode_count')
+        self.launches += 1
+        return errors
+
     @staticmethod
     def _w_host(W):
         W = np.ascontiguousarray(np.asarray(W, dtype=np.complex64))
@@ -497,7 +513,7 @@ class LinkEngine:
         B = snr_lin_rows.shape[0] // R
         nd2 = 2 * (self.Nd // 2)
         if idx is None:
-            idx = self.random_indices(B, S, seed, stream_id0)[:, :S * nd2].contiguous()
+            idx = self.random_indices(B, S, seed, stream_id0, nsym=S * nd2)      # = the first S * nd2 of S * Nd draws
         data, _ = self.sfbc_encode(S, idx=idx)
         tx, _, _ = self.modulate(S, symbols=data, T=2, want_stats=False)
         if chan.num_taps > 0:
@@ -509,9 +525,7 @@ class LinkEngine:
                         snr_lin=(snr_lin_rows * 2.0).contiguous(), seed=seed, row_id0=stream_id0 * R, noise_domain=1)
         H0 = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, pilot_set=0)
         H1 = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, pilot_set=1)
-        dec = self.sfbc_decode(Y, H0, H1, B, R, S, nat.WINDOW_USEFUL)
-        errors, _ = self.demap_count(dec, idx_tx=idx, nbits=S * nd2 * self.bps)
-        return errors
+        return self.sfbc_decode_count(Y, H0, H1, idx, B, R, S, nat.WINDOW_USEFUL, nbits=S * nd2 * self.bps)
 
     def sm_ber(self, chan, W, snr_db, B, S, R, detector, seed, stream_id0=0, idx=None, estimate_tensor=False):
         """One pass of the TM4-like spatial-multiplexing chain (reference simulate_spatial_multiplexing,
