@@ -325,6 +325,10 @@ int lte_sfbc_encode(const lte_plan*, const uint8_t* idx, const lte_c32* symbols,
                     lte_c32* qam_out, int64_t B, int32_t S, void* stream);
 int lte_sfbc_decode(const lte_plan*, const lte_c32* Y, const lte_c32* H0, const lte_c32* H1,
                     lte_c32* out, int window, int64_t B, int32_t R, int32_t S, void* stream);
+/* lte_sfbc_encode fused into lte_tx_map_ifft(T = 2): idx [B][S][2*(Nd/2)] -> tx [B][2][S*L]; the encoded
+ * symbols never exist in memory (antenna 0 reads idx[c], antenna 1 idx[c ^ 1], conjugation / negation by sign).
+ * Same samples as lte_sfbc_encode + lte_tx_map_ifft(symbols). */
+int lte_tx_sfbc_ifft(const lte_plan*, const uint8_t* idx, lte_c32* tx, int32_t B, int32_t S, void* stream);
 /* lte_sfbc_decode fused with lte_demap_count (QAMModulator.symbols_to_bits + calculate_ber,
  * core/modulator.py:90-112, core/ofdm_core.py:245-268): the decoded symbols are sliced and compared with
  * idx_tx [B][S][2*(Nd/2)] in registers; errors[b] (caller zeroes) += bit errors among the first nbits bits

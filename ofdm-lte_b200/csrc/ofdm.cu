@@ -65,7 +65,10 @@ __device__ __forceinline__ void pair_reduce(float (&pmax)[2], float (&psum)[2], 
     }
 }
 
-template <int N, bool STATS, bool SYM, bool PAPR>
+// SFBC (idx only, T = 2): the Alamouti encoder of core/sfbc_alamouti.py:45-78 rides in the index load -- data
+// position c of antenna 0 carries lut[idx[c]] (negated real part on odd c: -conj), of antenna 1 lut[idx[c ^ 1]]
+// (negated imaginary part on odd c: conj); idx rows hold 2 * (Nd / 2) symbols, a last odd data bin is nulled.
+template <int N, bool STATS, bool SYM, bool PAPR, bool SFBC = false>
 __global__ void __launch_bounds__(FFT_CTA_THREADS, 5)
 tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float2* __restrict__ symbols,
                    int T, float2* __restrict__ tx, float2* __restrict__ qam_out,
@@ -96,7 +99,8 @@ tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float
     tr[1] = row[1] - tq[1] * (unsigned)T;
 #pragma unroll
     for (int m = 0; m < 2; ++m)
-        ibase[m] = SYM ? ((size_t)row[m] * S + s_sym[m]) * Nd : ((size_t)tq[m] * S + s_sym[m]) * Nd;
+        ibase[m] = SYM ? ((size_t)row[m] * S + s_sym[m]) * Nd
+                       : ((size_t)tq[m] * S + s_sym[m]) * (SFBC ? 2 * (Nd / 2) : Nd);
     // Bin-centric build straight into the IFFT's register layout (thread j owns bins j + e TPF): the
     // class of every bin comes from the plan's bin_map (data slot / pilot / null), all index or
     // symbol loads are issued first, then the constellation lookups; no shared-memory grid, no
@@ -144,7 +148,9 @@ tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float
                 ib[m][e] = 0;
                 if ((e + 1) * TPF > used_lo && e * TPF < used_hi) {
                     const int c = code[e];
-                    if (valid[m] && c >= 0 && !(c & BIN_PILOT_FLAG)) ib[m][e] = ip[m][c];
+                    if (SFBC) {
+                        if (valid[m] && c >= 0 && !(c & BIN_PILOT_FLAG) && c < 2 * (Nd / 2)) ib[m][e] = ip[m][c ^ (int)tr[m]];
+                    } else if (valid[m] && c >= 0 && !(c & BIN_PILOT_FLAG)) ib[m][e] = ip[m][c];
                 }
             }
 #pragma unroll
@@ -157,7 +163,14 @@ tx_map_ifft_kernel(const DevPlan P, const uint8_t* __restrict__ idx, const float
                     const int ia = ib[0][e], ic = ib[1][e];
                     if (valid[0]) a = make_float2(s_lev[(ia >> h) & mask], s_lev[ia & mask]);
                     if (valid[1]) g = make_float2(s_lev[(ic >> h) & mask], s_lev[ic & mask]);
-                    if (qam_out) {
+                    if (SFBC) {
+                        if (c >= 2 * (Nd / 2)) { a = make_float2(0.f, 0.f); g = a; }
+                        else if (c & 1) {
+                            a = tr[0] ? make_float2(a.x, -a.y) : make_float2(-a.x, a.y);
+                            g = tr[1] ? make_float2(g.x, -g.y) : make_float2(-g.x, g.y);
+                        }
+                    }
+                    if (!SFBC && qam_out) {
                         if (valid[0]) qam_out[ibase[0] + c] = a;
                         if (valid[1]) qam_out[ibase[1] + c] = g;
                     }
@@ -430,6 +443,27 @@ extern "C" int lte_tx_map_ifft(const lte_plan* p, const uint8_t* idx, const lte_
                                void* stream) {
     if (!p || (!idx && !symbols) || !tx || B < 0 || S < 1 || T < 1 || T > LTE_MAX_TX) return LTE_ERR_INVALID_ARG;
     return launch_tx(p, idx, symbols, T, tx, qam_out, stats, nullptr, B, S, stream);
+}
+
+extern "C" int lte_tx_sfbc_ifft(const lte_plan* p, const uint8_t* idx, lte_c32* tx, int32_t B, int32_t S, void* stream) {
+    if (!p || !idx || !tx || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
+    if (p->nsets < 2 || p->dev.Nd < 2) return LTE_ERR_INVALID_ARG;          // the two SFBC pilot sets
+    if (B == 0) return LTE_OK;
+    const long long total = (long long)B * 2 * S;
+    if (total >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
+    const PaprOut none = {nullptr, nullptr, nullptr, 0.f, 1.f, 1};
+    return dispatch_n(p->dev.N, [&](auto n) -> int {
+        constexpr int N = decltype(n)::value;
+        const int smem = fft2_cta_smem_bytes(N);
+        const long long per = 2 * fft2_pairs_per_cta(N);
+        const long long grid = (total + per - 1) / per;
+        auto k = tx_map_ifft_kernel<N, false, false, false, true>;
+        LTE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k<<<(unsigned)grid, FFT_CTA_THREADS, smem, (cudaStream_t)stream>>>(p->dev, idx, nullptr, 2, (float2*)tx, nullptr, nullptr,
+                                                                       none, S, (unsigned)total);
+        LTE_CHECK_CUDA(cudaGetLastError());
+        return LTE_OK;
+    });
 }
 
 static int make_papr_out(PaprOut& po, float* papr_db, float* peak_mean, unsigned long long* hist, float hist_lo,

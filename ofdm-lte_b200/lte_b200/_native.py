@@ -85,6 +85,7 @@ _SIGS = {
     'lte_equalize_mrc': ([_P, _P, _P, _P, C.c_int, _I64, _I32, _I32, _P], C.c_int),
     'lte_sfbc_encode': ([_P, _P, _P, _P, _P, _I64, _I32, _P], C.c_int),
     'lte_sfbc_decode': ([_P, _P, _P, _P, _P, C.c_int, _I64, _I32, _I32, _P], C.c_int),
+    'lte_tx_sfbc_ifft': ([_P, _P, _P, _I32, _I32, _P], C.c_int),
     'lte_sfbc_decode_count': ([_P, _P, _P, _P, _P, _P, _I64, C.c_int, _I64, _I32, _I32, _P], C.c_int),
     'lte_sm_precode': ([_P, _P, _P, _P, _I32, _I32, _P, _P, _I64, _I32, _P], C.c_int),
     'lte_flat_mimo': ([_P, _P, _P, _P, _P, _I64, _I32, _I32, _I64, _P], C.c_int),

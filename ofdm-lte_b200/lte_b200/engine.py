@@ -393,6 +393,15 @@ class LinkEngine:
         self.launches += 1
         return out, qam
 
+    def tx_sfbc(self, S, idx, out=None):
+        """Alamouti encode + per-TX resource grid + IFFT + CP in one kernel: idx [B, S*2*(Nd//2)] -> tx [B, 2, S*L]
+        (= sfbc_encode + modulate(symbols=..., T=2) without the encoded symbols in memory)."""
+        B = idx.shape[0]
+        tx = out if out is not None else self._empty((B, 2, S * self.L), torch.complex64)
+        nat.check(nat.lib.lte_tx_sfbc_ifft(self._plan, _ptr(idx), _ptr(tx), B, S, self._stream()), 'lte_tx_sfbc_ifft')
+        self.launches += 1
+        return tx
+
     def sfbc_decode(self, Y, H0, H1, B, R, S, window=nat.WINDOW_FULL):
         out = self._empty((B, S * 2 * (self.Nd // 2)), torch.complex64)
         nat.check(nat.lib.lte_sfbc_decode(self._plan, _ptr(Y), _ptr(H0), _ptr(H1), _ptr(out), window, B, R, S,
@@ -514,8 +523,7 @@ class LinkEngine:
         nd2 = 2 * (self.Nd // 2)
         if idx is None:
             idx = self.random_indices(B, S, seed, stream_id0, nsym=S * nd2)      # = the first S * nd2 of S * Nd draws
-        data, _ = self.sfbc_encode(S, idx=idx)
-        tx, _, _ = self.modulate(S, symbols=data, T=2, want_stats=False)
+        tx = self.tx_sfbc(S, idx)
         if chan.num_taps > 0:
             ph = self.random_phases(B, R * 2 * chan.num_taps * nat.LTE_JAKES_TONES, seed, stream_id0)
             rx, power = self.channel(tx, chan, B, R, T=2, phases=ph)
