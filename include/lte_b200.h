@@ -240,6 +240,16 @@ int64_t lte_channel_rx_fft_workspace_bytes(const lte_plan*, const lte_channel_de
 int lte_channel_rx_fft(const lte_plan*, const lte_channel_desc* ch, const lte_c32* tx,
                        const float* phases, lte_c32* Y, double* power, void* workspace, int window,
                        int32_t B, int32_t R, int32_t S, void* stream);
+/* The same for T > 1 transmit antennas (SFBC, spatial multiplexing): the R x T independently faded links of
+ * ChannelSimulator.transmit_spatial_multiplexing / the MIMO branch of OFDMChannel (core/channel.py:399-466,
+ * core/ofdm_core.py:1850-2258) summed per receive antenna, stream power, CP strip and FFT in one kernel.
+ * tx: [B][T][S*L]; phases: [B][R][T][taps][16] as in lte_channel_tdl; Y: [B*R][S][nk] noise-free; power [B][R].
+ * The AWGN joins in the consumers: lte_crs_ls_interp_awgn, lte_sfbc_decode_count(awgn), lte_mimo_detect(awgn). */
+int64_t lte_channel_rx_fft_mimo_workspace_bytes(const lte_plan*, const lte_channel_desc* ch, int32_t B,
+                                                int32_t R, int32_t T, int32_t S);
+int lte_channel_rx_fft_mimo(const lte_plan*, const lte_channel_desc* ch, const lte_c32* tx,
+                            const float* phases, lte_c32* Y, double* power, void* workspace, int window,
+                            int32_t B, int32_t R, int32_t T, int32_t S, void* stream);
 
 /* --- spectral fading link (sweep engine, T = 1, low Doppler) -------------------------------------
  * The same reference stages as lte_tx_map_ifft + lte_channel_rx_fft -- QAMModulator.bits_to_symbols,
@@ -332,10 +342,12 @@ int lte_tx_sfbc_ifft(const lte_plan*, const uint8_t* idx, lte_c32* tx, int32_t B
 /* lte_sfbc_decode fused with lte_demap_count (QAMModulator.symbols_to_bits + calculate_ber,
  * core/modulator.py:90-112, core/ofdm_core.py:245-268): the decoded symbols are sliced and compared with
  * idx_tx [B][S][2*(Nd/2)] in registers; errors[b] (caller zeroes) += bit errors among the first nbits bits
- * of stream b.  Same decoded values, hence the same counts, as the two separate calls. */
+ * of stream b.  Same decoded values, hence the same counts, as the two separate calls.
+ * awgn (optional): Y is noise free (lte_channel_rx_fft_mimo) and the noise lte_rx_fft(noise_domain = 1)
+ * would have added joins while the bins are read; H0 / H1 then come from lte_crs_ls_interp_awgn. */
 int lte_sfbc_decode_count(const lte_plan*, const lte_c32* Y, const lte_c32* H0, const lte_c32* H1,
                           const uint8_t* idx_tx, unsigned long long* errors, int64_t nbits, int window,
-                          int64_t B, int32_t R, int32_t S, void* stream);
+                          int64_t B, int32_t R, int32_t S, const lte_awgn_desc* awgn, void* stream);
 
 /* --- spatial multiplexing (TM4-like, up to 8 TX / 8 RX / 4 layers) ------------------------
  * lte_sm_precode replaces LayerMapper.map_to_layers (core/layer_mapper.py:35-86) and the
@@ -354,6 +366,8 @@ int lte_sfbc_decode_count(const lte_plan*, const lte_c32* Y, const lte_c32* H0, 
  * from Y's pilot bins (LS at the two neighbouring pilots of set t, linear in between, edge hold) -- bit for bit
  * the value lte_crs_ls_interp(pilot_set = t, rows = B*R*S, S = 1) would have written, without the T passes
  * over Y and the [T][B*R][S][nk] tensor (the plan must carry the T pilot sets).
+ * awgn (optional): Y is noise free and the AWGN joins while data and pilot bins are read (lazy AWGN, as in
+ * lte_mrc_demap_count_awgn); with a non-NULL H the estimates must already include it (lte_crs_ls_interp_awgn).
  * sigma2_streams (optional, device, double [B]): one noise variance per stream, which lets a sweep put
  * all its SNR points into one launch; NULL = the scalar `sigma2` for every stream. */
 int lte_sm_precode(const lte_plan*, const uint8_t* idx, const lte_c32* symbols, const lte_c32* W_host,
@@ -363,7 +377,8 @@ int lte_flat_mimo(const lte_plan*, const lte_c32* tx, const lte_c32* h, lte_c32*
                   int64_t B, int32_t R, int32_t T, int64_t n, void* stream);
 int lte_mimo_detect(const lte_plan*, const lte_c32* Y, const lte_c32* H, const lte_c32* W_host,
                     int32_t T, int32_t L, double sigma2, const double* sigma2_streams, int32_t detector,
-                    lte_c32* out, int window, int64_t B, int32_t R, int32_t S, void* stream);
+                    lte_c32* out, int window, int64_t B, int32_t R, int32_t S, const lte_awgn_desc* awgn,
+                    void* stream);
 
 /* --- beamforming (rank-1 precoding over a flat R x T channel) ---------------
  * The reference path OFDMSimulator.simulate_beamforming (core/ofdm_core.py:2260-2477) stays in

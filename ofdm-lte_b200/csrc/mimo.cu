@@ -1,5 +1,6 @@
 // Transmit-diversity (SFBC Alamouti) stage kernels.
 #include "slicer.cuh"
+#include "awgn.cuh"
 
 // ------------------------------------------------------------------------------ SFBC encode
 // core/sfbc_alamouti.py:45-78: pairs (k, k+1) of data symbols -> TX0 [s0, -conj(s1)],
@@ -63,12 +64,14 @@ extern "C" int lte_sfbc_encode(const lte_plan* p, const uint8_t* idx, const lte_
 // core/ofdm_core.py:2204.  thread = (stream, pair); channel estimates of the slot stay in registers.
 // COUNT: the decoded pair goes straight through the slicer and the bit-error count against idx_tx
 // (core/modulator.py:90-112, core/ofdm_core.py:245-268) instead of to memory -- the sweep's form.
-template <int R, bool COUNT>
+// NOISY: Y is noise free (lte_channel_rx_fft_mimo) and the AWGN of lte_rx_fft(noise_domain = 1) is added to the
+// two bins while they are read (awgn.cuh: same draws, so the noisy grid never exists).
+template <int R, bool COUNT, bool NOISY>
 __global__ void __launch_bounds__(128)
 sfbc_decode_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restrict__ H0,
                    const float2* __restrict__ H1, float2* __restrict__ out, const uint8_t* __restrict__ idx_tx,
                    unsigned long long* __restrict__ errors, long long nbits, int k0, int nk, int S, int nslot,
-                   int npair, int gx) {
+                   int npair, int gx, const AwgnArgs A) {
     const long long b = blockIdx.x / gx;
     const int pr0 = (blockIdx.x % gx) * blockDim.x + threadIdx.x;
     const bool act = pr0 < npair;
@@ -77,6 +80,11 @@ sfbc_decode_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* 
     unsigned int e = 0;
     const int ka = P.data_idx[2 * pr] - k0, kb = P.data_idx[2 * pr + 1] - k0;
     const float invR = 1.0f / (float)R;
+    float sigma[R];
+    if (NOISY) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) sigma[r] = lte_sigma(A.power[b * R + r], A.n_stream, A.snr_lin[b * R + r]);
+    }
     for (int slot = 0; slot < nslot; ++slot) {
         float2 h0a[R], h0b[R], h1a[R], h1b[R];
         float nrm[R];
@@ -95,7 +103,11 @@ sfbc_decode_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* 
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const size_t o = (((size_t)b * R + r) * S + s) * nk;
-                const float2 ra = Y[o + ka], rb = Y[o + kb];
+                float2 ra = Y[o + ka], rb = Y[o + kb];
+                if (NOISY) {
+                    ra = awgn_at(A, sigma[r], b * R + r, s, P.N, ka + k0, ra);
+                    rb = awgn_at(A, sigma[r], b * R + r, s, P.N, kb + k0, rb);
+                }
                 const float2 rbc = make_float2(rb.x, -rb.y);
                 // s0 = conj(h0a) ra + h1b conj(rb);  s1 = conj(h1a) ra - h0b conj(rb)
                 float2 t0 = cmulc(h0a[r], ra), u0 = cmul(h1b[r], rbc);
@@ -120,12 +132,14 @@ sfbc_decode_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* 
 
 static int launch_sfbc_decode(const lte_plan* p, const lte_c32* Y, const lte_c32* H0, const lte_c32* H1, lte_c32* out,
                               const uint8_t* idx_tx, unsigned long long* errors, int64_t nbits, int window, int64_t B,
-                              int32_t R, int32_t S, void* stream) {
+                              int32_t R, int32_t S, const lte_awgn_desc* awgn, void* stream) {
     const bool count = idx_tx != nullptr;
     if (!p || !Y || !H0 || !H1 || (!count && !out) || (count && !errors) || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
     int32_t k0, nk;
     int rc = lte_plan_window(p, window, &k0, &nk);
     if (rc) return rc;
+    AwgnArgs A = {};
+    if (awgn && (rc = make_awgn_args(A, p, awgn, S, B * R))) return rc;
     if (B == 0) return LTE_OK;
     const int npair = p->dev.Nd / 2;
     if (npair < 1) return LTE_ERR_INVALID_ARG;
@@ -133,12 +147,13 @@ static int launch_sfbc_decode(const lte_plan* p, const lte_c32* Y, const lte_c32
     const int gx = (npair + 127) / 128;
     const unsigned grid = (unsigned)((long long)gx * B);
     cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH_SFBC2(RR, CC)                                                                                  \
-    sfbc_decode_kernel<RR, CC><<<grid, 128, 0, st>>>(p->dev, (const float2*)Y, (const float2*)H0, (const float2*)H1, \
-                                                     (float2*)out, idx_tx, errors, nbits, k0, nk, S, nslot, npair, gx)
+#define LAUNCH_SFBC2(RR, CC, NN)                                                                              \
+    sfbc_decode_kernel<RR, CC, NN><<<grid, 128, 0, st>>>(p->dev, (const float2*)Y, (const float2*)H0, (const float2*)H1, \
+                                                         (float2*)out, idx_tx, errors, nbits, k0, nk, S, nslot, npair, gx, A)
 #define LAUNCH_SFBC(RR)                                                                                       \
     case RR:                                                                                                  \
-        if (count) LAUNCH_SFBC2(RR, true); else LAUNCH_SFBC2(RR, false);                                      \
+        if (count) { if (awgn) LAUNCH_SFBC2(RR, true, true); else LAUNCH_SFBC2(RR, true, false); }            \
+        else { if (awgn) LAUNCH_SFBC2(RR, false, true); else LAUNCH_SFBC2(RR, false, false); }                \
         break;
     switch (R) {
         LAUNCH_SFBC(1) LAUNCH_SFBC(2) LAUNCH_SFBC(3) LAUNCH_SFBC(4) LAUNCH_SFBC(5) LAUNCH_SFBC(6) LAUNCH_SFBC(7)
@@ -154,12 +169,12 @@ static int launch_sfbc_decode(const lte_plan* p, const lte_c32* Y, const lte_c32
 extern "C" int lte_sfbc_decode(const lte_plan* p, const lte_c32* Y, const lte_c32* H0, const lte_c32* H1,
                                lte_c32* out, int window, int64_t B, int32_t R, int32_t S, void* stream) {
     if (!out) return LTE_ERR_INVALID_ARG;
-    return launch_sfbc_decode(p, Y, H0, H1, out, nullptr, nullptr, 0, window, B, R, S, stream);
+    return launch_sfbc_decode(p, Y, H0, H1, out, nullptr, nullptr, 0, window, B, R, S, nullptr, stream);
 }
 
 extern "C" int lte_sfbc_decode_count(const lte_plan* p, const lte_c32* Y, const lte_c32* H0, const lte_c32* H1,
                                      const uint8_t* idx_tx, unsigned long long* errors, int64_t nbits, int window,
-                                     int64_t B, int32_t R, int32_t S, void* stream) {
+                                     int64_t B, int32_t R, int32_t S, const lte_awgn_desc* awgn, void* stream) {
     if (!idx_tx || nbits < 0) return LTE_ERR_INVALID_ARG;
-    return launch_sfbc_decode(p, Y, H0, H1, nullptr, idx_tx, errors, nbits, window, B, R, S, stream);
+    return launch_sfbc_decode(p, Y, H0, H1, nullptr, idx_tx, errors, nbits, window, B, R, S, awgn, stream);
 }

@@ -1,6 +1,7 @@
 // Spatial multiplexing (TM4-like) stage kernels: layer mapping + codebook precoding, flat MIMO
 // channel, and the per-subcarrier MIMO detectors (MMSE / ZF / ordered SIC / MRC) on H_eff = H W.
 #include "common.cuh"
+#include "awgn.cuh"
 
 #define SM_MAX_TX 8
 #define SM_MAX_RX 8
@@ -194,7 +195,8 @@ __device__ void mmse_solve(const cd (*Heff)[SM_MAX_LAYERS], const cd* y, int R, 
 __global__ void __launch_bounds__(128)
 mimo_detect_kernel(const DevPlan P, const SmPrecoder W, const float2* __restrict__ Y, const float2* __restrict__ H,
                    float2* __restrict__ out, int k0, int nk, int R, int S, double sigma2_all,
-                   const double* __restrict__ sigma2_streams, int detector, long long rows, long long total) {
+                   const double* __restrict__ sigma2_streams, int detector, long long rows, long long total,
+                   const AwgnArgs A, int noisy) {
     const int L = W.L, T = W.T;
     const int npos = (P.Nd + L - 1) / L;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
@@ -208,7 +210,12 @@ mimo_detect_kernel(const DevPlan P, const SmPrecoder W, const float2* __restrict
         cd Heff[SM_MAX_RX][SM_MAX_LAYERS], y[SM_MAX_RX];
         for (int r = 0; r < R; ++r) {
             const size_t row = (size_t)b * R + r;
-            const float2 yv = Y[(row * S + s) * nk + kk];
+            float2 yv = Y[(row * S + s) * nk + kk];
+            float sg = 0.f;
+            if (noisy) {                // noise-free grid: the AWGN of lte_rx_fft(noise_domain = 1) joins as it is read
+                sg = lte_sigma(A.power[row], A.n_stream, A.snr_lin[row]);
+                yv = awgn_at(A, sg, (long long)row, s, P.N, kk + k0, yv);
+            }
             y[r] = {(double)yv.x, (double)yv.y};
             for (int l = 0; l < L; ++l) Heff[r][l] = {0.0, 0.0};
             for (int t = 0; t < T; ++t) {
@@ -227,11 +234,15 @@ mimo_detect_kernel(const DevPlan P, const SmPrecoder W, const float2* __restrict
                     const int lo = P.pset_seg[(size_t)t * P.N + k];
                     const int la = lo < 0 ? 0 : (lo >= cnt - 1 ? cnt - 1 : lo);
                     const int i1 = pbin[la];
-                    const float2 a = cmul(yrow[i1 - k0], pinv[la]);
+                    float2 ya = yrow[i1 - k0];
+                    if (noisy) ya = awgn_at(A, sg, (long long)row, s, P.N, i1, ya);
+                    const float2 a = cmul(ya, pinv[la]);
                     hv = a;
                     if (lo >= 0 && lo < cnt - 1 && k != i1) {
                         const int i2 = pbin[la + 1];
-                        const float2 c = cmul(yrow[i2 - k0], pinv[la + 1]);
+                        float2 yc = yrow[i2 - k0];
+                        if (noisy) yc = awgn_at(A, sg, (long long)row, s, P.N, i2, yc);
+                        const float2 c = cmul(yc, pinv[la + 1]);
                         const float div = (float)(i2 - i1), tt = (float)(k - i1);
                         hv = make_float2(fmaf(tt, __fdiv_rn(c.x - a.x, div), a.x), fmaf(tt, __fdiv_rn(c.y - a.y, div), a.y));
                     }
@@ -303,7 +314,8 @@ mimo_detect_kernel(const DevPlan P, const SmPrecoder W, const float2* __restrict
 
 extern "C" int lte_mimo_detect(const lte_plan* p, const lte_c32* Y, const lte_c32* H, const lte_c32* W_host,
                                int32_t T, int32_t L, double sigma2, const double* sigma2_streams, int32_t detector,
-                               lte_c32* out, int window, int64_t B, int32_t R, int32_t S, void* stream) {
+                               lte_c32* out, int window, int64_t B, int32_t R, int32_t S, const lte_awgn_desc* awgn,
+                               void* stream) {
     if (!p || !Y || !out || B < 0 || S < 1 || R < 1 || R > SM_MAX_RX) return LTE_ERR_INVALID_ARG;
     if (!H && (p->nsets < T || p->dev.Np == 0)) return LTE_ERR_INVALID_ARG;    // estimating needs the T pilot sets
     if (detector < DET_MMSE || detector > DET_MRC) return LTE_ERR_INVALID_ARG;
@@ -315,6 +327,8 @@ extern "C" int lte_mimo_detect(const lte_plan* p, const lte_c32* Y, const lte_c3
     int32_t k0, nk;
     rc = lte_plan_window(p, window, &k0, &nk);
     if (rc) return rc;
+    AwgnArgs A = {};
+    if (awgn && (rc = make_awgn_args(A, p, awgn, S, B * R))) return rc;
     if (B == 0) return LTE_OK;
     const int npos = (p->dev.Nd + L - 1) / L;
     const long long total = (long long)B * S * npos;
@@ -322,7 +336,7 @@ extern "C" int lte_mimo_detect(const lte_plan* p, const lte_c32* Y, const lte_c3
     if (grid > 148 * 16) grid = 148 * 16;
     mimo_detect_kernel<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(
         p->dev, W, (const float2*)Y, (const float2*)H, (float2*)out, k0, nk, R, S, sigma2, sigma2_streams,
-        detector, (long long)B * R, total);
+        detector, (long long)B * R, total, A, awgn ? 1 : 0);
     LTE_CHECK_CUDA(cudaGetLastError());
     return LTE_OK;
 }

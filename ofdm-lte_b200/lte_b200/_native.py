@@ -70,6 +70,8 @@ _SIGS = {
     'lte_channel_tdl': ([_P, C.POINTER(ChannelDesc), _P, _P, _P, _P, _P, _I32, _I32, _I32, _I64, _P], C.c_int),
     'lte_channel_rx_fft_workspace_bytes': ([_P, C.POINTER(ChannelDesc), _I32, _I32, _I32], C.c_int64),
     'lte_channel_rx_fft': ([_P, C.POINTER(ChannelDesc), _P, _P, _P, _P, _P, C.c_int, _I32, _I32, _I32, _P], C.c_int),
+    'lte_channel_rx_fft_mimo_workspace_bytes': ([_P, C.POINTER(ChannelDesc), _I32, _I32, _I32, _I32], C.c_int64),
+    'lte_channel_rx_fft_mimo': ([_P, C.POINTER(ChannelDesc), _P, _P, _P, _P, _P, C.c_int, _I32, _I32, _I32, _I32, _P], C.c_int),
     'lte_tx_spectral': ([_P, _P, _P, _P, _I32, _I32, _P], C.c_int),
     'lte_channel_spectral_workspace_bytes': ([_P, C.POINTER(ChannelDesc), _I32, _I32, _I32], C.c_int64),
     'lte_channel_spectral': ([_P, C.POINTER(ChannelDesc), _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P], C.c_int),
@@ -86,10 +88,11 @@ _SIGS = {
     'lte_sfbc_encode': ([_P, _P, _P, _P, _P, _I64, _I32, _P], C.c_int),
     'lte_sfbc_decode': ([_P, _P, _P, _P, _P, C.c_int, _I64, _I32, _I32, _P], C.c_int),
     'lte_tx_sfbc_ifft': ([_P, _P, _P, _I32, _I32, _P], C.c_int),
-    'lte_sfbc_decode_count': ([_P, _P, _P, _P, _P, _P, _I64, C.c_int, _I64, _I32, _I32, _P], C.c_int),
+    'lte_sfbc_decode_count': ([_P, _P, _P, _P, _P, _P, _I64, C.c_int, _I64, _I32, _I32, C.POINTER(AwgnDesc), _P], C.c_int),
     'lte_sm_precode': ([_P, _P, _P, _P, _I32, _I32, _P, _P, _I64, _I32, _P], C.c_int),
     'lte_flat_mimo': ([_P, _P, _P, _P, _P, _I64, _I32, _I32, _I64, _P], C.c_int),
-    'lte_mimo_detect': ([_P, _P, _P, _P, _I32, _I32, C.c_double, _P, _I32, _P, C.c_int, _I64, _I32, _I32, _P], C.c_int),
+    'lte_mimo_detect': ([_P, _P, _P, _P, _I32, _I32, C.c_double, _P, _I32, _P, C.c_int, _I64, _I32, _I32, C.POINTER(AwgnDesc), _P],
+                        C.c_int),
     'lte_demap_count': ([_P, _P, _P, _P, _P, _I64, _I64, _I64, _P], C.c_int),
     'lte_mrc_demap_count': ([_P, _P, _P, _P, _P, C.c_int, _I64, _I64, _I32, _I32, _P], C.c_int),
     'lte_fp32_peak_launch': ([_P, _I32, _P], C.c_int64),

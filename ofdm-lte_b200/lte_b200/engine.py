@@ -243,11 +243,15 @@ class LinkEngine:
         self.launches += 2 if chan.num_taps > 0 else 1     # Jakes coefficient kernel + TDL kernel
         return faded, power
 
-    def channel_rx_fft(self, tx, chan, B, R, S, phases, window=nat.WINDOW_FULL, out=None, power=None):
-        """Fused fading channel + CP strip + FFT (T = 1): -> (Y [B*R, S, nk] noise-free, power [B, R]),
-        or None when the configuration needs the staged `channel` + `rx_fft` pair."""
+    def channel_rx_fft(self, tx, chan, B, R, S, phases, window=nat.WINDOW_FULL, out=None, power=None, T=1):
+        """Fused fading channel + CP strip + FFT: -> (Y [B*R, S, nk] noise-free, power [B, R]),
+        or None when the configuration needs the staged `channel` + `rx_fft` pair.
+        T > 1: tx [B, T, S*L], phases [B, R*T*taps*16]; the R x T links are summed per receive antenna."""
         k0, nk = self.window(window)
-        need = nat.lib.lte_channel_rx_fft_workspace_bytes(self._plan, C.byref(chan), B, R, S)
+        if T > 1:
+            need = nat.lib.lte_channel_rx_fft_mimo_workspace_bytes(self._plan, C.byref(chan), B, R, T, S)
+        else:
+            need = nat.lib.lte_channel_rx_fft_workspace_bytes(self._plan, C.byref(chan), B, R, S)
         if need == nat.LTE_ERR_UNSUPPORTED:
             return None
         if need < 0:
@@ -258,8 +262,14 @@ class LinkEngine:
         else:
             power.zero_()
         Y = out if out is not None else self._empty((B * R, S, nk), torch.complex64)
-        rc = nat.lib.lte_channel_rx_fft(self._plan, C.byref(chan), _ptr(tx), _ptr(phases), _ptr(Y), _ptr(power),
-                                        _ptr(work), window, B, R, S, self._stream())
+        if T > 1:
+            rc = nat.lib.lte_channel_rx_fft_mimo(self._plan, C.byref(chan), _ptr(tx), _ptr(phases), _ptr(Y), _ptr(power),
+                                                 _ptr(work), window, B, R, T, S, self._stream())
+            if rc == nat.LTE_ERR_UNSUPPORTED:                # shared-memory footprint: known only at launch
+                return None
+        else:
+            rc = nat.lib.lte_channel_rx_fft(self._plan, C.byref(chan), _ptr(tx), _ptr(phases), _ptr(Y), _ptr(power),
+                                            _ptr(work), window, B, R, S, self._stream())
         nat.check(rc, 'lte_channel_rx_fft')
         self.launches += 2                                   # Jakes coefficient kernel + fused kernel
         return Y, power
@@ -412,7 +422,7 @@ class LinkEngine:
     # ------------------------------------------------------------------ spatial multiplexing
     DETECTORS = {'MMSE': 0, 'IRC': 0, 'ZF': 1, 'SIC': 2, 'MRC': 3}
 
-    def sfbc_decode_count(self, Y, H0, H1, idx_tx, B, R, S, window=nat.WINDOW_FULL, nbits=None, errors=None):
+    def sfbc_decode_count(self, Y, H0, H1, idx_tx, B, R, S, window=nat.WINDOW_FULL, nbits=None, errors=None, awgn=None):
         """Alamouti decode + slicer + bit-error count in one kernel: int64 [B] errors against idx_tx [B, S*2*(Nd//2)]."""
         nd2 = 2 * (self.Nd // 2)
         nbits = S * nd2 * self.bps if nbits is None else int(nbits)
@@ -421,7 +431,8 @@ class LinkEngine:
         else:
             errors.zero_()
         nat.check(nat.lib.lte_sfbc_decode_count(self._plan, _ptr(Y), _ptr(H0), _ptr(H1), _ptr(idx_tx), _ptr(errors), nbits,
-                                                window, B, R, S, self._stream()), 'lte_sfbc_decode_count')
+                                                window, B, R, S, C.byref(awgn) if awgn is not None else None,
+                                                self._stream()), 'lte_sfbc_decode_count')
         self.launches += 1
         return errors
 
@@ -452,7 +463,7 @@ class LinkEngine:
         self.launches += 1
         return out, power
 
-    def mimo_detect(self, Y, H, W, sigma2, detector, B, R, S, window=nat.WINDOW_FULL):
+    def mimo_detect(self, Y, H, W, sigma2, detector, B, R, S, window=nat.WINDOW_FULL, awgn=None):
         """Y [B*R, S, nk], H [T, B*R, S, nk] -> detected symbols [B, S*Nd] (demapped layer order).
         H=None: the detector forms the per-symbol CRS estimates itself from Y's pilot bins (same values, no H tensor).
         sigma2: one float for every stream, or a float64 device tensor [B] (one noise variance per stream)."""
@@ -469,7 +480,8 @@ class LinkEngine:
         out = torch.zeros((B, S * self.Nd), dtype=torch.complex64, device=self.device)
         nat.check(nat.lib.lte_mimo_detect(self._plan, _ptr(Y), _ptr(H) if H is not None else None, wp, T, L, float(sigma2),
                                           _ptr(per_stream) if per_stream is not None else None, det, _ptr(out),
-                                          window, B, R, S, self._stream()), 'lte_mimo_detect')
+                                          window, B, R, S, C.byref(awgn) if awgn is not None else None,
+                                          self._stream()), 'lte_mimo_detect')
         self.launches += 1
         return out
 
@@ -510,32 +522,44 @@ class LinkEngine:
         errors, _ = self.demap_count(data, idx_tx=idx, nbits=nbits)
         return errors
 
-    def sfbc_ber(self, chan, snr_lin_rows, S, R, seed, stream_id0=0, idx=None):
+    def sfbc_ber(self, chan, snr_lin_rows, S, R, seed, stream_id0=0, idx=None, fused=True):
         """One pass of the 2-TX Alamouti SFBC chain (reference simulate_miso / simulate_mimo,
         core/ofdm_core.py:1850-2258) over B independent streams: SFBC encode, per-TX interleaved CRS,
         R x 2 independently faded links summed per RX antenna, AWGN of power (P_rx / 2) / snr, CRS
         estimates of both TX antennas per 14-symbol slot, Alamouti decode averaged over RX, slicer, count.
         The engine must have been built with tables.mimo_pilot_sets(2, Np); snr_lin_rows: float32 [B*R]
-        linear SNR per (stream, antenna).  Returns int64 [B] bit errors over S * 2 * (Nd // 2) symbols."""
+        linear SNR per (stream, antenna).  Returns int64 [B] bit errors over S * 2 * (Nd // 2) symbols.
+        fused (default): channel + FFT in one kernel and lazy AWGN, staged kernels where that does not apply."""
         if self.num_pilot_sets != 2:
             raise ValueError("sfbc_ber needs an engine with the two SFBC pilot sets")
         B = snr_lin_rows.shape[0] // R
         nd2 = 2 * (self.Nd // 2)
         if idx is None:
             idx = self.random_indices(B, S, seed, stream_id0, nsym=S * nd2)      # = the first S * nd2 of S * Nd draws
-        tx = self.tx_sfbc(S, idx)
-        if chan.num_taps > 0:
-            ph = self.random_phases(B, R * 2 * chan.num_taps * nat.LTE_JAKES_TONES, seed, stream_id0)
-            rx, power = self.channel(tx, chan, B, R, T=2, phases=ph)
-        else:
+        if chan.num_taps == 0:
             raise ValueError("sfbc_ber models the fading links of the reference's MIMO channel (rayleigh_mp)")
+        tx = self.tx_sfbc(S, idx)
+        ph = self.random_phases(B, R * 2 * chan.num_taps * nat.LTE_JAKES_TONES, seed, stream_id0)
+        snr2 = (snr_lin_rows * 2.0).contiguous()
+        if fused:
+            # fading + CP strip + FFT in one kernel, noise-free grid; the AWGN joins in the estimator and the decoder
+            # (the draws of the staged path's RX epilogue, from the stream power this kernel measures)
+            got = self.channel_rx_fft(tx, chan, B, R, S, ph, nat.WINDOW_USEFUL, T=2)
+            if got is not None:
+                Y, power = got
+                awgn = self.awgn_desc(power, snr2, seed, stream_id0 * R)
+                H0 = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, pilot_set=0, awgn=awgn)
+                H1 = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, pilot_set=1, awgn=awgn)
+                return self.sfbc_decode_count(Y, H0, H1, idx, B, R, S, nat.WINDOW_USEFUL, nbits=S * nd2 * self.bps, awgn=awgn)
+        rx, power = self.channel(tx, chan, B, R, T=2, phases=ph)
         Y = self.rx_fft(rx.view(B * R, -1), B * R, S, nat.WINDOW_USEFUL, power=power,
-                        snr_lin=(snr_lin_rows * 2.0).contiguous(), seed=seed, row_id0=stream_id0 * R, noise_domain=1)
+                        snr_lin=snr2, seed=seed, row_id0=stream_id0 * R, noise_domain=1)
         H0 = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, pilot_set=0)
         H1 = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, pilot_set=1)
         return self.sfbc_decode_count(Y, H0, H1, idx, B, R, S, nat.WINDOW_USEFUL, nbits=S * nd2 * self.bps)
 
-    def sm_ber(self, chan, W, snr_db, B, S, R, detector, seed, stream_id0=0, idx=None, estimate_tensor=False):
+    def sm_ber(self, chan, W, snr_db, B, S, R, detector, seed, stream_id0=0, idx=None, estimate_tensor=False,
+               fused=True):
         """One pass of the TM4-like spatial-multiplexing chain (reference simulate_spatial_multiplexing,
         core/ofdm_core.py:2489-2815) over B independent streams that share the precoder W [T, L].  `snr_db` is
         one float for every stream or a sequence / tensor of B values (stream b runs at snr_db[b]; the detectors
@@ -554,7 +578,9 @@ class LinkEngine:
         data, _ = self.sm_precode(S, W, idx=idx)
         tx, _, _ = self.modulate(S, symbols=data, T=T, want_stats=False)
         ph = self.random_phases(B, R * T * chan.num_taps * nat.LTE_JAKES_TONES, seed, stream_id0)
-        rx, power = self.channel(tx, chan, B, R, T=T, phases=ph)
+        got = self.channel_rx_fft(tx, chan, B, R, S, ph, nat.WINDOW_USEFUL, T=T) if (fused and not estimate_tensor) else None
+        if got is None:
+            rx, power = self.channel(tx, chan, B, R, T=T, phases=ph)
         if torch.is_tensor(snr_db) or np.ndim(snr_db) > 0:
             snr_b = torch.as_tensor(snr_db, dtype=torch.float64, device=self.device).reshape(-1)
             if snr_b.numel() != B:
@@ -566,6 +592,13 @@ class LinkEngine:
             sigma2 = 10 ** (-snr_db / 10)
         # only the occupied bins travel: FFT window, per-TX estimates (written straight into one [T, ...] tensor) and detector
         k0, nk = self.window(nat.WINDOW_USEFUL)
+        if got is not None:
+            # fused channel + FFT: noise-free grid, the AWGN joins inside the detector (data and pilot bins)
+            Y, power = got
+            awgn = self.awgn_desc(power, snr_rows, seed, stream_id0 * R)
+            sym = self.mimo_detect(Y, None, W, sigma2, detector, B, R, S, nat.WINDOW_USEFUL, awgn=awgn)
+            errors, _ = self.demap_count(sym, idx_tx=idx, nbits=S * self.Nd * self.bps)
+            return errors
         Y = self.rx_fft(rx.view(B * R, -1), B * R, S, nat.WINDOW_USEFUL, power=power, snr_lin=snr_rows, seed=seed,
                         row_id0=stream_id0 * R, noise_domain=1)
         H = None                        # the detector estimates from Y's pilot bins itself (bit-identical values)
