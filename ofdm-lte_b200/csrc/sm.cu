@@ -187,6 +187,64 @@ __device__ void mmse_solve(const cd (*Heff)[SM_MAX_LAYERS], const cd* y, int R, 
     chol_solve(A, x, nc);
 }
 
+// The same two steps with compile-time sizes: every loop unrolls, nothing is indexed at run time, so H_eff, the
+// Gram matrix and the right-hand side live in registers (the generic versions above keep them in local memory
+// because `cols` and the loop bounds are run-time values).  Same operations in the same order.
+template <int NL>
+__device__ __forceinline__ void chol_solve_fixed(cd (&A)[NL][NL], cd (&rhs)[NL]) {
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+        double d = A[j][j].x;
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= A[j][k].x * A[j][k].x + A[j][k].y * A[j][k].y;
+        d = sqrt(d);
+        A[j][j] = {d, 0.0};
+#pragma unroll
+        for (int i = j + 1; i < NL; ++i) {
+            cd s = A[i][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s = cdsub(s, cdmul(A[i][k], {A[j][k].x, -A[j][k].y}));
+            A[i][j] = {s.x / d, s.y / d};
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+        cd s = rhs[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) s = cdsub(s, cdmul(A[i][k], rhs[k]));
+        rhs[i] = {s.x / A[i][i].x, s.y / A[i][i].x};
+    }
+#pragma unroll
+    for (int i = NL - 1; i >= 0; --i) {
+        cd s = rhs[i];
+#pragma unroll
+        for (int k = i + 1; k < NL; ++k) s = cdsub(s, cdmulc(A[k][i], rhs[k]));
+        rhs[i] = {s.x / A[i][i].x, s.y / A[i][i].x};
+    }
+}
+
+template <int NR, int NL>
+__device__ __forceinline__ void mmse_solve_fixed(const cd (&Heff)[NR][NL], const cd (&y)[NR], double sigma2, cd (&x)[NL]) {
+    cd A[NL][NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+        cd r = {0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < NR; ++q) r = cdadd(r, cdmulc(Heff[q][i], y[q]));
+        x[i] = r;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            cd a = {0.0, 0.0};
+#pragma unroll
+            for (int q = 0; q < NR; ++q) a = cdadd(a, cdmulc(Heff[q][j], Heff[q][i]));
+            A[i][j] = {a.x, -a.y};
+        }
+        A[i][i].x += sigma2;
+        A[i][i].y = 0.0;
+    }
+    chol_solve_fixed<NL>(A, x);
+}
+
 #define DET_MMSE 0
 #define DET_ZF 1
 #define DET_SIC 2
@@ -312,6 +370,83 @@ mimo_detect_kernel(const DevPlan P, const SmPrecoder W, const float2* __restrict
     }
 }
 
+// MMSE / ZF with compile-time antenna and layer counts (the sweep shapes): registers instead of local memory.
+template <int NR, int NL>
+__global__ void __launch_bounds__(128)
+mimo_detect_fixed_kernel(const DevPlan P, const SmPrecoder W, const float2* __restrict__ Y, const float2* __restrict__ H,
+                   float2* __restrict__ out, int k0, int nk, int R, int S, double sigma2_all,
+                   const double* __restrict__ sigma2_streams, int detector, long long rows, long long total,
+                   const AwgnArgs A, int noisy) {
+    constexpr int L = NL;
+    const int T = W.T;
+    (void)R;
+    const int npos = (P.Nd + L - 1) / L;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(g % npos);
+        const long long bs = g / npos;
+        const long long b = bs / S;
+        const int s = (int)(bs % S);
+        const int kk = P.data_idx[p] - k0;
+        const double sigma2 = sigma2_streams ? sigma2_streams[b] : sigma2_all;
+        cd Heff[NR][NL], y[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const size_t row = (size_t)b * NR + r;
+            float2 yv = Y[(row * S + s) * nk + kk];
+            float sg = 0.f;
+            if (noisy) {                // noise-free grid: the AWGN of lte_rx_fft(noise_domain = 1) joins as it is read
+                sg = lte_sigma(A.power[row], A.n_stream, A.snr_lin[row]);
+                yv = awgn_at(A, sg, (long long)row, s, P.N, kk + k0, yv);
+            }
+            y[r] = {(double)yv.x, (double)yv.y};
+#pragma unroll
+            for (int l = 0; l < L; ++l) Heff[r][l] = {0.0, 0.0};
+            for (int t = 0; t < T; ++t) {
+                float2 hv;
+                if (H) {
+                    hv = H[(((size_t)t * rows + row) * S + s) * nk + kk];
+                } else {
+                    // the per-symbol CRS estimate of TX antenna t at this bin, straight from the symbol's pilot bins:
+                    // LS at the two neighbouring pilots of set t, then start + i * (delta / div) -- operation for
+                    // operation what crs_ls_interp_kernel writes into H (core/lte_receiver.py:62-133)
+                    const int cnt = P.pset_cnt[t];
+                    const int16_t* pbin = P.pset_bin + (size_t)t * P.Np;
+                    const float2* pinv = P.pset_inv + (size_t)t * P.Np;
+                    const float2* yrow = Y + (row * S + s) * nk;
+                    const int k = kk + k0;
+                    const int lo = P.pset_seg[(size_t)t * P.N + k];
+                    const int la = lo < 0 ? 0 : (lo >= cnt - 1 ? cnt - 1 : lo);
+                    const int i1 = pbin[la];
+                    float2 ya = yrow[i1 - k0];
+                    if (noisy) ya = awgn_at(A, sg, (long long)row, s, P.N, i1, ya);
+                    const float2 a = cmul(ya, pinv[la]);
+                    hv = a;
+                    if (lo >= 0 && lo < cnt - 1 && k != i1) {
+                        const int i2 = pbin[la + 1];
+                        float2 yc = yrow[i2 - k0];
+                        if (noisy) yc = awgn_at(A, sg, (long long)row, s, P.N, i2, yc);
+                        const float2 c = cmul(yc, pinv[la + 1]);
+                        const float div = (float)(i2 - i1), tt = (float)(k - i1);
+                        hv = make_float2(fmaf(tt, __fdiv_rn(c.x - a.x, div), a.x), fmaf(tt, __fdiv_rn(c.y - a.y, div), a.y));
+                    }
+                }
+                const cd hd = {(double)hv.x, (double)hv.y};
+#pragma unroll
+                for (int l = 0; l < L; ++l)
+                    Heff[r][l] = cdadd(Heff[r][l], cdmul(hd, {(double)W.w[t][l].x, (double)W.w[t][l].y}));
+            }
+        }
+        cd x[NL];
+        mmse_solve_fixed<NR, NL>(Heff, y, detector == DET_ZF ? 0.0 : sigma2, x);     // ZF: pinv of a full-column-rank H_eff
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            const int q = p * L + l;
+            if (q < P.Nd) out[(size_t)bs * P.Nd + q] = make_float2((float)x[l].x, (float)x[l].y);
+        }
+    }
+}
+
 extern "C" int lte_mimo_detect(const lte_plan* p, const lte_c32* Y, const lte_c32* H, const lte_c32* W_host,
                                int32_t T, int32_t L, double sigma2, const double* sigma2_streams, int32_t detector,
                                lte_c32* out, int window, int64_t B, int32_t R, int32_t S, const lte_awgn_desc* awgn,
@@ -334,6 +469,19 @@ extern "C" int lte_mimo_detect(const lte_plan* p, const lte_c32* Y, const lte_c3
     const long long total = (long long)B * S * npos;
     long long grid = (total + 127) / 128;
     if (grid > 148 * 16) grid = 148 * 16;
+#define LAUNCH_DET_FIXED(RR, LL)                                                                                  \
+    if (R == RR && L == LL) {                                                                                    \
+        mimo_detect_fixed_kernel<RR, LL><<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(                       \
+            p->dev, W, (const float2*)Y, (const float2*)H, (float2*)out, k0, nk, R, S, sigma2, sigma2_streams,   \
+            detector, (long long)B * R, total, A, awgn ? 1 : 0);                                                 \
+        LTE_CHECK_CUDA(cudaGetLastError());                                                                      \
+        return LTE_OK;                                                                                           \
+    }
+    if (detector == DET_MMSE || detector == DET_ZF) {
+        LAUNCH_DET_FIXED(2, 1) LAUNCH_DET_FIXED(2, 2) LAUNCH_DET_FIXED(4, 1) LAUNCH_DET_FIXED(4, 2) LAUNCH_DET_FIXED(4, 3)
+        LAUNCH_DET_FIXED(4, 4)
+    }
+#undef LAUNCH_DET_FIXED
     mimo_detect_kernel<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(
         p->dev, W, (const float2*)Y, (const float2*)H, (float2*)out, k0, nk, R, S, sigma2, sigma2_streams,
         detector, (long long)B * R, total, A, awgn ? 1 : 0);
