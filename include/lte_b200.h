@@ -365,7 +365,9 @@ int lte_sfbc_decode_count(const lte_plan*, const lte_c32* Y, const lte_c32* H0, 
  * H may be NULL: the detector then forms the per-symbol CRS estimate of every TX antenna at its bin itself
  * from Y's pilot bins (LS at the two neighbouring pilots of set t, linear in between, edge hold) -- bit for bit
  * the value lte_crs_ls_interp(pilot_set = t, rows = B*R*S, S = 1) would have written, without the T passes
- * over Y and the [T][B*R][S][nk] tensor (the plan must carry the T pilot sets).
+ * over Y and the [T][B*R][S][nk] tensor (the plan must carry the T pilot sets).  Hpilot (optional, with H = NULL):
+ * the LS estimates at the pilots from lte_crs_ls_pilots; the detector then only interpolates (with lazy AWGN
+ * every pilot gets its noise sample once instead of once per data bin next to it).
  * awgn (optional): Y is noise free and the AWGN joins while data and pilot bins are read (lazy AWGN, as in
  * lte_mrc_demap_count_awgn); with a non-NULL H the estimates must already include it (lte_crs_ls_interp_awgn).
  * sigma2_streams (optional, device, double [B]): one noise variance per stream, which lets a sweep put
@@ -375,7 +377,12 @@ int lte_sm_precode(const lte_plan*, const uint8_t* idx, const lte_c32* symbols, 
                    void* stream);
 int lte_flat_mimo(const lte_plan*, const lte_c32* tx, const lte_c32* h, lte_c32* out, double* power,
                   int64_t B, int32_t R, int32_t T, int64_t n, void* stream);
-int lte_mimo_detect(const lte_plan*, const lte_c32* Y, const lte_c32* H, const lte_c32* W_host,
+/* lte_crs_ls_pilots: the LS step of the per-symbol estimate alone, for every pilot set of the plan in one launch
+ * (MIMOChannelEstimator / estimate_channel per TX antenna, core/lte_receiver.py:62-87): Y [rows][S][nk] ->
+ * Hp [nsets][rows*S][Np] (the first pilots-of-set-t entries of a row are used); awgn optional (lazy AWGN). */
+int lte_crs_ls_pilots(const lte_plan*, const lte_c32* Y, lte_c32* Hp, int window, int64_t rows, int32_t S,
+                      const lte_awgn_desc* awgn, void* stream);
+int lte_mimo_detect(const lte_plan*, const lte_c32* Y, const lte_c32* H, const lte_c32* Hpilot, const lte_c32* W_host,
                     int32_t T, int32_t L, double sigma2, const double* sigma2_streams, int32_t detector,
                     lte_c32* out, int window, int64_t B, int32_t R, int32_t S, const lte_awgn_desc* awgn,
                     void* stream);

@@ -133,6 +133,47 @@ extern "C" int lte_flat_mimo(const lte_plan* p, const lte_c32* tx, const lte_c32
     return LTE_OK;
 }
 
+// ------------------------------------------------------------------------------ per-symbol pilot estimates
+// LS estimate at every pilot of every TX antenna's pilot set on EVERY OFDM symbol (the SM receiver estimates per
+// symbol, core/ofdm_core.py:2700-2760 with core/lte_receiver.py:62-87): Hp [nsets][rows * S][Np], the first
+// pset_cnt[t] entries of a row used.  With lazy AWGN each pilot gets its noise sample once here, instead of once
+// per data bin that interpolates from it inside the detector.
+__global__ void __launch_bounds__(256)
+crs_ls_pilots_kernel(const DevPlan P, const float2* __restrict__ Y, float2* __restrict__ Hp, int k0, int nk, int S,
+                     int nsets, long long rows, long long total, const AwgnArgs A, int noisy) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const int i = (int)(g % P.Np);
+    const long long q = g / P.Np;                   // t * rows * S + row * S + s
+    const long long rs = q % (rows * S);
+    const int t = (int)(q / (rows * S));
+    if (i >= P.pset_cnt[t]) return;
+    const long long row = rs / S;
+    const int s = (int)(rs % S);
+    const int bin = P.pset_bin[(size_t)t * P.Np + i];
+    float2 y = Y[(size_t)rs * nk + (bin - k0)];
+    if (noisy) y = awgn_at(A, lte_sigma(A.power[row], A.n_stream, A.snr_lin[row]), row, s, P.N, bin, y);
+    Hp[g] = cmul(y, P.pset_inv[(size_t)t * P.Np + i]);
+}
+
+extern "C" int lte_crs_ls_pilots(const lte_plan* p, const lte_c32* Y, lte_c32* Hp, int window, int64_t rows, int32_t S,
+                                 const lte_awgn_desc* awgn, void* stream) {
+    if (!p || !Y || !Hp || rows < 0 || S < 1 || p->dev.Np == 0) return LTE_ERR_INVALID_ARG;
+    int32_t k0, nk;
+    int rc = lte_plan_window(p, window, &k0, &nk);
+    if (rc) return rc;
+    AwgnArgs A = {};
+    if (awgn && (rc = make_awgn_args(A, p, awgn, S, rows))) return rc;
+    if (rows == 0) return LTE_OK;
+    const long long total = (long long)p->nsets * rows * S * p->dev.Np;
+    const long long grid = (total + 255) / 256;
+    if (grid >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
+    crs_ls_pilots_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(p->dev, (const float2*)Y, (float2*)Hp, k0, nk, S,
+                                                                          p->nsets, rows, total, A, awgn ? 1 : 0);
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}
+
 // ------------------------------------------------------------------------------ MIMO detection
 // core/mimo_detector.py:99-369 per data position.  The small-matrix algebra runs in fp64 (the
 // inputs are fp32): A = H_eff^H H_eff + sigma^2 I is solved by complex Cholesky.
@@ -252,7 +293,7 @@ __device__ __forceinline__ void mmse_solve_fixed(const cd (&Heff)[NR][NL], const
 
 __global__ void __launch_bounds__(128)
 mimo_detect_kernel(const DevPlan P, const SmPrecoder W, const float2* __restrict__ Y, const float2* __restrict__ H,
-                   float2* __restrict__ out, int k0, int nk, int R, int S, double sigma2_all,
+                   const float2* __restrict__ Hp, float2* __restrict__ out, int k0, int nk, int R, int S, double sigma2_all,
                    const double* __restrict__ sigma2_streams, int detector, long long rows, long long total,
                    const AwgnArgs A, int noisy) {
     const int L = W.L, T = W.T;
@@ -292,15 +333,24 @@ mimo_detect_kernel(const DevPlan P, const SmPrecoder W, const float2* __restrict
                     const int lo = P.pset_seg[(size_t)t * P.N + k];
                     const int la = lo < 0 ? 0 : (lo >= cnt - 1 ? cnt - 1 : lo);
                     const int i1 = pbin[la];
-                    float2 ya = yrow[i1 - k0];
-                    if (noisy) ya = awgn_at(A, sg, (long long)row, s, P.N, i1, ya);
-                    const float2 a = cmul(ya, pinv[la]);
+                    const float2* hp = Hp ? Hp + (((size_t)t * rows + row) * S + s) * P.Np : nullptr;   // lte_crs_ls_pilots
+                    float2 a;
+                    if (hp) a = hp[la];
+                    else {
+                        float2 ya = yrow[i1 - k0];
+                        if (noisy) ya = awgn_at(A, sg, (long long)row, s, P.N, i1, ya);
+                        a = cmul(ya, pinv[la]);
+                    }
                     hv = a;
                     if (lo >= 0 && lo < cnt - 1 && k != i1) {
                         const int i2 = pbin[la + 1];
-                        float2 yc = yrow[i2 - k0];
-                        if (noisy) yc = awgn_at(A, sg, (long long)row, s, P.N, i2, yc);
-                        const float2 c = cmul(yc, pinv[la + 1]);
+                        float2 c;
+                        if (hp) c = hp[la + 1];
+                        else {
+                            float2 yc = yrow[i2 - k0];
+                            if (noisy) yc = awgn_at(A, sg, (long long)row, s, P.N, i2, yc);
+                            c = cmul(yc, pinv[la + 1]);
+                        }
                         const float div = (float)(i2 - i1), tt = (float)(k - i1);
                         hv = make_float2(fmaf(tt, __fdiv_rn(c.x - a.x, div), a.x), fmaf(tt, __fdiv_rn(c.y - a.y, div), a.y));
                     }
@@ -372,9 +422,9 @@ mimo_detect_kernel(const DevPlan P, const SmPrecoder W, const float2* __restrict
 
 // MMSE / ZF with compile-time antenna and layer counts (the sweep shapes): registers instead of local memory.
 template <int NR, int NL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 mimo_detect_fixed_kernel(const DevPlan P, const SmPrecoder W, const float2* __restrict__ Y, const float2* __restrict__ H,
-                   float2* __restrict__ out, int k0, int nk, int R, int S, double sigma2_all,
+                   const float2* __restrict__ Hp, float2* __restrict__ out, int k0, int nk, int R, int S, double sigma2_all,
                    const double* __restrict__ sigma2_streams, int detector, long long rows, long long total,
                    const AwgnArgs A, int noisy) {
     constexpr int L = NL;
@@ -418,15 +468,24 @@ mimo_detect_fixed_kernel(const DevPlan P, const SmPrecoder W, const float2* __re
                     const int lo = P.pset_seg[(size_t)t * P.N + k];
                     const int la = lo < 0 ? 0 : (lo >= cnt - 1 ? cnt - 1 : lo);
                     const int i1 = pbin[la];
-                    float2 ya = yrow[i1 - k0];
-                    if (noisy) ya = awgn_at(A, sg, (long long)row, s, P.N, i1, ya);
-                    const float2 a = cmul(ya, pinv[la]);
+                    const float2* hp = Hp ? Hp + (((size_t)t * rows + row) * S + s) * P.Np : nullptr;   // lte_crs_ls_pilots
+                    float2 a;
+                    if (hp) a = hp[la];
+                    else {
+                        float2 ya = yrow[i1 - k0];
+                        if (noisy) ya = awgn_at(A, sg, (long long)row, s, P.N, i1, ya);
+                        a = cmul(ya, pinv[la]);
+                    }
                     hv = a;
                     if (lo >= 0 && lo < cnt - 1 && k != i1) {
                         const int i2 = pbin[la + 1];
-                        float2 yc = yrow[i2 - k0];
-                        if (noisy) yc = awgn_at(A, sg, (long long)row, s, P.N, i2, yc);
-                        const float2 c = cmul(yc, pinv[la + 1]);
+                        float2 c;
+                        if (hp) c = hp[la + 1];
+                        else {
+                            float2 yc = yrow[i2 - k0];
+                            if (noisy) yc = awgn_at(A, sg, (long long)row, s, P.N, i2, yc);
+                            c = cmul(yc, pinv[la + 1]);
+                        }
                         const float div = (float)(i2 - i1), tt = (float)(k - i1);
                         hv = make_float2(fmaf(tt, __fdiv_rn(c.x - a.x, div), a.x), fmaf(tt, __fdiv_rn(c.y - a.y, div), a.y));
                     }
@@ -447,12 +506,14 @@ mimo_detect_fixed_kernel(const DevPlan P, const SmPrecoder W, const float2* __re
     }
 }
 
-extern "C" int lte_mimo_detect(const lte_plan* p, const lte_c32* Y, const lte_c32* H, const lte_c32* W_host,
+extern "C" int lte_mimo_detect(const lte_plan* p, const lte_c32* Y, const lte_c32* H, const lte_c32* Hpilot,
+                               const lte_c32* W_host,
                                int32_t T, int32_t L, double sigma2, const double* sigma2_streams, int32_t detector,
                                lte_c32* out, int window, int64_t B, int32_t R, int32_t S, const lte_awgn_desc* awgn,
                                void* stream) {
     if (!p || !Y || !out || B < 0 || S < 1 || R < 1 || R > SM_MAX_RX) return LTE_ERR_INVALID_ARG;
     if (!H && (p->nsets < T || p->dev.Np == 0)) return LTE_ERR_INVALID_ARG;    // estimating needs the T pilot sets
+    if (H && Hpilot) return LTE_ERR_INVALID_ARG;
     if (detector < DET_MMSE || detector > DET_MRC) return LTE_ERR_INVALID_ARG;
     if (R < L) return LTE_ERR_INVALID_ARG;                  // core/mimo_detector.py:34-35
     if (detector == DET_MRC && L != 1) return LTE_ERR_INVALID_ARG;
@@ -472,7 +533,8 @@ extern "C" int lte_mimo_detect(const lte_plan* p, const lte_c32* Y, const lte_c3
 #define LAUNCH_DET_FIXED(RR, LL)                                                                                  \
     if (R == RR && L == LL) {                                                                                    \
         mimo_detect_fixed_kernel<RR, LL><<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(                       \
-            p->dev, W, (const float2*)Y, (const float2*)H, (float2*)out, k0, nk, R, S, sigma2, sigma2_streams,   \
+            p->dev, W, (const float2*)Y, (const float2*)H, (const float2*)Hpilot, (float2*)out, k0, nk, R, S, sigma2,   \
+            sigma2_streams,                                                                                      \
             detector, (long long)B * R, total, A, awgn ? 1 : 0);                                                 \
         LTE_CHECK_CUDA(cudaGetLastError());                                                                      \
         return LTE_OK;                                                                                           \
@@ -483,8 +545,8 @@ extern "C" int lte_mimo_detect(const lte_plan* p, const lte_c32* Y, const lte_c3
     }
 #undef LAUNCH_DET_FIXED
     mimo_detect_kernel<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(
-        p->dev, W, (const float2*)Y, (const float2*)H, (float2*)out, k0, nk, R, S, sigma2, sigma2_streams,
-        detector, (long long)B * R, total, A, awgn ? 1 : 0);
+        p->dev, W, (const float2*)Y, (const float2*)H, (const float2*)Hpilot, (float2*)out, k0, nk, R, S, sigma2,
+        sigma2_streams, detector, (long long)B * R, total, A, awgn ? 1 : 0);
     LTE_CHECK_CUDA(cudaGetLastError());
     return LTE_OK;
 }

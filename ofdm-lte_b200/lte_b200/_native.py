@@ -91,7 +91,8 @@ _SIGS = {
     'lte_sfbc_decode_count': ([_P, _P, _P, _P, _P, _P, _I64, C.c_int, _I64, _I32, _I32, C.POINTER(AwgnDesc), _P], C.c_int),
     'lte_sm_precode': ([_P, _P, _P, _P, _I32, _I32, _P, _P, _I64, _I32, _P], C.c_int),
     'lte_flat_mimo': ([_P, _P, _P, _P, _P, _I64, _I32, _I32, _I64, _P], C.c_int),
-    'lte_mimo_detect': ([_P, _P, _P, _P, _I32, _I32, C.c_double, _P, _I32, _P, C.c_int, _I64, _I32, _I32, C.POINTER(AwgnDesc), _P],
+    'lte_crs_ls_pilots': ([_P, _P, _P, C.c_int, _I64, _I32, C.POINTER(AwgnDesc), _P], C.c_int),
+    'lte_mimo_detect': ([_P, _P, _P, _P, _P, _I32, _I32, C.c_double, _P, _I32, _P, C.c_int, _I64, _I32, _I32, C.POINTER(AwgnDesc), _P],
                         C.c_int),
     'lte_demap_count': ([_P, _P, _P, _P, _P, _I64, _I64, _I64, _P], C.c_int),
     'lte_mrc_demap_count': ([_P, _P, _P, _P, _P, C.c_int, _I64, _I64, _I32, _I32, _P], C.c_int),

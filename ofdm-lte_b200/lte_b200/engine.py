@@ -463,7 +463,15 @@ class LinkEngine:
         self.launches += 1
         return out, power
 
-    def mimo_detect(self, Y, H, W, sigma2, detector, B, R, S, window=nat.WINDOW_FULL, awgn=None):
+    def estimate_pilots(self, Y, rows, S, window=nat.WINDOW_FULL, awgn=None):
+        """LS estimates at the pilots of every pilot set on every OFDM symbol: Y [rows, S, nk] -> Hp [sets, rows*S, Np]."""
+        Hp = self._empty((self.num_pilot_sets, rows * S, self.Np), torch.complex64)
+        nat.check(nat.lib.lte_crs_ls_pilots(self._plan, _ptr(Y), _ptr(Hp), window, rows, S,
+                                            C.byref(awgn) if awgn is not None else None, self._stream()), 'lte_crs_ls_pilots')
+        self.launches += 1
+        return Hp
+
+    def mimo_detect(self, Y, H, W, sigma2, detector, B, R, S, window=nat.WINDOW_FULL, awgn=None, Hpilot=None):
         """Y [B*R, S, nk], H [T, B*R, S, nk] -> detected symbols [B, S*Nd] (demapped layer order).
         H=None: the detector forms the per-symbol CRS estimates itself from Y's pilot bins (same values, no H tensor).
         sigma2: one float for every stream, or a float64 device tensor [B] (one noise variance per stream)."""
@@ -478,7 +486,8 @@ class LinkEngine:
         if det is None:
             raise ValueError(f"Detector '{detector}' no soportado")
         out = torch.zeros((B, S * self.Nd), dtype=torch.complex64, device=self.device)
-        nat.check(nat.lib.lte_mimo_detect(self._plan, _ptr(Y), _ptr(H) if H is not None else None, wp, T, L, float(sigma2),
+        nat.check(nat.lib.lte_mimo_detect(self._plan, _ptr(Y), _ptr(H) if H is not None else None,
+                                          _ptr(Hpilot) if Hpilot is not None else None, wp, T, L, float(sigma2),
                                           _ptr(per_stream) if per_stream is not None else None, det, _ptr(out),
                                           window, B, R, S, C.byref(awgn) if awgn is not None else None,
                                           self._stream()), 'lte_mimo_detect')
@@ -596,7 +605,8 @@ class LinkEngine:
             # fused channel + FFT: noise-free grid, the AWGN joins inside the detector (data and pilot bins)
             Y, power = got
             awgn = self.awgn_desc(power, snr_rows, seed, stream_id0 * R)
-            sym = self.mimo_detect(Y, None, W, sigma2, detector, B, R, S, nat.WINDOW_USEFUL, awgn=awgn)
+            Hp = self.estimate_pilots(Y, B * R, S, nat.WINDOW_USEFUL, awgn=awgn)     # each pilot's noise sample once
+            sym = self.mimo_detect(Y, None, W, sigma2, detector, B, R, S, nat.WINDOW_USEFUL, awgn=awgn, Hpilot=Hp)
             errors, _ = self.demap_count(sym, idx_tx=idx, nbits=S * self.Nd * self.bps)
             return errors
         Y = self.rx_fft(rx.view(B * R, -1), B * R, S, nat.WINDOW_USEFUL, power=power, snr_lin=snr_rows, seed=seed,

@@ -73,3 +73,24 @@ def test_fused_mimo_reports_unsupported_like_the_single_tx_kernel():
     tx = torch.zeros((2, 2, 3 * eng.L), dtype=torch.complex64, device='cuda')
     ph = eng.random_phases(2, 2 * 2 * chan.num_taps * nat.LTE_JAKES_TONES, 1, 0)
     assert eng.channel_rx_fft(tx, chan, 2, 2, 3, ph, nat.WINDOW_USEFUL, T=2) is None
+
+
+def test_detector_interpolating_from_pilot_estimates_equals_estimating_itself():
+    """lte_crs_ls_pilots + lte_mimo_detect(Hpilot) against lte_mimo_detect estimating from Y's pilot bins, with and
+    without lazy AWGN: the pilots' LS values (and noise samples) are the same numbers, so the symbols are bit-identical."""
+    from core.codebook_lte import LTECodebook
+    from lte_b200 import _native as nat
+    for bw, mod, T, rank, det in ((1.25, '16-QAM', 4, 2, 'MMSE'), (5.0, '64-QAM', 2, 2, 'ZF'), (2.5, 'QPSK', 4, 3, 'SIC')):
+        cfg, eng = _engine(bw, mod, T)
+        W = LTECodebook(T, transmission_mode='TM4', rank=rank).get_precoder(0)
+        B, R, S = 3, 4, 2
+        k0, nk = eng.window(nat.WINDOW_USEFUL)
+        g = torch.Generator(device='cuda').manual_seed(2)
+        Y = torch.view_as_complex(torch.randn((B * R, S, nk, 2), generator=g, device='cuda'))
+        power = torch.full((B, R), 3.0e3, dtype=torch.float64, device='cuda')
+        snr = torch.full((B * R,), 20.0, dtype=torch.float32, device='cuda')
+        for awgn in (None, eng.awgn_desc(power, snr, 5, 40)):
+            Hp = eng.estimate_pilots(Y, B * R, S, nat.WINDOW_USEFUL, awgn=awgn)
+            a = eng.mimo_detect(Y, None, W, 0.05, det, B, R, S, nat.WINDOW_USEFUL, awgn=awgn)
+            b = eng.mimo_detect(Y, None, W, 0.05, det, B, R, S, nat.WINDOW_USEFUL, awgn=awgn, Hpilot=Hp)
+            assert torch.equal(torch.view_as_real(a), torch.view_as_real(b)), (bw, det, awgn is not None)
