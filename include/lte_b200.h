@@ -234,7 +234,8 @@ int lte_equalize_mrc(const lte_plan*, const lte_c32* Y, const lte_c32* H, lte_c3
  * power: [B][R] sum |faded|^2 over the whole stream including the CP samples, accumulated with
  * atomics, caller zeroes.  The AWGN is then added lazily by the *_awgn consumers below.
  * Returns LTE_ERR_UNSUPPORTED for the identity link (num_taps = 0) and when the Doppler spread
- * is too large for one Jakes polynomial per OFDM symbol (> about 330 Hz): use the staged pair. */
+ * is too large for one Jakes polynomial (degree <= 6) per OFDM symbol, pi fD L / fs > 0.25 -- about
+ * 1.1 kHz at 20 MHz, 1.7 kHz at 1.25 MHz: use the staged pair. */
 int64_t lte_channel_rx_fft_workspace_bytes(const lte_plan*, const lte_channel_desc* ch, int32_t B,
                                            int32_t R, int32_t S);             /* bytes, or LTE_ERR_* (< 0) */
 int lte_channel_rx_fft(const lte_plan*, const lte_channel_desc* ch, const lte_c32* tx,

@@ -21,7 +21,7 @@
 #include "tdl.cuh"
 
 template <int N, int K>
-__global__ void __launch_bounds__(FFT_CTA_THREADS, (N == 2048 && K == 4) ? 3 : 4)
+__global__ void __launch_bounds__(FFT_CTA_THREADS, (N == 2048 && K >= 4) ? 3 : 4)
 channel_rx_fft_kernel(const DevPlan P, const TdlParams C, const float2* __restrict__ tx,
                       const float* __restrict__ coef_g, float2* __restrict__ Y, double* __restrict__ power, int k0,
                       int nk, int S, int R, int R2, int halo, unsigned total, bool wide) {
@@ -403,11 +403,12 @@ static int fused_setup(const lte_plan* p, const lte_channel_desc* ch, int32_t B,
         if (fabs(C.w_cyc[nn]) > wmax) wmax = fabs(C.w_cyc[nn]);
     }
     // one polynomial block per OFDM symbol, remainder kept below 5e-7 of |h| (1/20 of the 1e-5 parity budget):
-    // K = 1 is the economised linear fit (tdl.cuh), x^2/4; K = 2 / 4 are Taylor polynomials, x^3/6 and x^5/120
+    // K = 1 is the economised linear fit (tdl.cuh), x^2/4; K = 2 / 4 / 6 are Taylor polynomials, x^3/6, x^5/120, x^7/5040
     const double x = M_PI * wmax * L;
     if (x <= 1.41e-3) U.K = 1;
     else if (x <= 1.44e-2) U.K = 2;
     else if (x <= 0.075) U.K = 4;
+    else if (x <= 0.25) U.K = 6;                                // x^7 / 5040 <= 1.2e-8
     else return LTE_ERR_UNSUPPORTED;
     C.pb = L;
     C.nbs = S;
@@ -450,7 +451,8 @@ extern "C" int lte_channel_rx_fft(const lte_plan* p, const lte_channel_desc* ch,
     const unsigned cgrid = (unsigned)((items + 255) / 256);
     if (K == 1) jakes_coef_kernel<1><<<cgrid, 256, 0, st>>>(C, phases, coef, R, 1, R2, items);
     else if (K == 2) jakes_coef_kernel<2><<<cgrid, 256, 0, st>>>(C, phases, coef, R, 1, R2, items);
-    else jakes_coef_kernel<4><<<cgrid, 256, 0, st>>>(C, phases, coef, R, 1, R2, items);
+    else if (K == 4) jakes_coef_kernel<4><<<cgrid, 256, 0, st>>>(C, phases, coef, R, 1, R2, items);
+    else jakes_coef_kernel<6><<<cgrid, 256, 0, st>>>(C, phases, coef, R, 1, R2, items);
     LTE_CHECK_CUDA(cudaGetLastError());
 
     return dispatch_n(p->dev.N, [&](auto nn) -> int {
@@ -470,7 +472,8 @@ extern "C" int lte_channel_rx_fft(const lte_plan* p, const lte_channel_desc* ch,
             return LTE_OK;
         };
         if (K == 1) return launch(channel_rx_fft_kernel<N, 1>);
-        return K == 2 ? launch(channel_rx_fft_kernel<N, 2>) : launch(channel_rx_fft_kernel<N, 4>);
+        if (K == 2) return launch(channel_rx_fft_kernel<N, 2>);
+        return K == 4 ? launch(channel_rx_fft_kernel<N, 4>) : launch(channel_rx_fft_kernel<N, 6>);
     });
 }
 
@@ -505,7 +508,8 @@ extern "C" int lte_channel_rx_fft_mimo(const lte_plan* p, const lte_channel_desc
     const unsigned cgrid = (unsigned)((items + 255) / 256);
     if (K == 1) jakes_coef_kernel<1><<<cgrid, 256, 0, st>>>(C, phases, coef, R, T, R2, items);
     else if (K == 2) jakes_coef_kernel<2><<<cgrid, 256, 0, st>>>(C, phases, coef, R, T, R2, items);
-    else jakes_coef_kernel<4><<<cgrid, 256, 0, st>>>(C, phases, coef, R, T, R2, items);
+    else if (K == 4) jakes_coef_kernel<4><<<cgrid, 256, 0, st>>>(C, phases, coef, R, T, R2, items);
+    else jakes_coef_kernel<6><<<cgrid, 256, 0, st>>>(C, phases, coef, R, T, R2, items);
     LTE_CHECK_CUDA(cudaGetLastError());
 
     return dispatch_n(p->dev.N, [&](auto nn) -> int {
@@ -526,6 +530,7 @@ extern "C" int lte_channel_rx_fft_mimo(const lte_plan* p, const lte_channel_desc
             return LTE_OK;
         };
         if (K == 1) return launch(channel_rx_fft_mt_kernel<N, 1>);
-        return K == 2 ? launch(channel_rx_fft_mt_kernel<N, 2>) : launch(channel_rx_fft_mt_kernel<N, 4>);
+        if (K == 2) return launch(channel_rx_fft_mt_kernel<N, 2>);
+        return K == 4 ? launch(channel_rx_fft_mt_kernel<N, 4>) : launch(channel_rx_fft_mt_kernel<N, 6>);
     });
 }

@@ -96,7 +96,7 @@ def test_fused_reports_unsupported_and_sweep_falls_back():
     ph = torch.zeros((B, R * 8 * 16), dtype=torch.float32, device='cuda')
     awgn = chan_for('awgn', cfg.fs, 'Pedestrian_A', 2.0, 0.0)
     assert eng.channel_rx_fft(tx, awgn, B, R, S, ph) is None          # identity link
-    fast = chan_for('rayleigh_mp', cfg.fs, 'Vehicular_A', 2.0, 350.0)  # fD = 648 Hz: beyond one block per symbol
+    fast = chan_for('rayleigh_mp', cfg.fs, 'Vehicular_A', 2.0, 650.0)  # fD = 1.2 kHz: beyond one degree-6 polynomial per symbol
     assert eng.channel_rx_fft(tx, fast, B, R, S, ph) is None
     # the sweep path silently uses the staged kernels then, with the same lazy-noise draws
     wf = eng.workspace(B, S, R, fading=True, fused=True)
@@ -105,3 +105,30 @@ def test_fused_reports_unsupported_and_sweep_falls_back():
     a = eng.simo_ber(wf, fast, rows, seed=1, fused=True).clone()
     b = eng.simo_ber(ws, fast, rows, seed=1, noise_domain=1).clone()
     assert torch.equal(a, b) and 'faded' in wf
+
+
+@pytest.mark.parametrize('bw,v', [(1.25, 350.0), (5.0, 350.0), (20.0, 500.0)])
+def test_degree_six_polynomial_at_high_doppler_matches_oracle(bw, v):
+    """fD = 650 - 930 Hz at 2 GHz: one degree-6 Taylor polynomial per (antenna, tap, OFDM symbol) (pi fD L / fs up to
+    0.21), against the oracle's fp64 sample-by-sample Jakes process."""
+    from lte_b200 import _native as nat
+    from lte_b200 import chan_for
+    num = O.Numerology(bw, 15.0, '16-QAM')
+    eng = _engine(num)
+    R, S = 2, 3
+    rs = np.random.RandomState(11)
+    bits = rs.randint(0, 2, eng.Nd * eng.bps * S)
+    idx = eng.bits_to_indices(torch.from_numpy(bits.astype(np.uint8)).cuda()[None, :], len(bits), S)
+    tx, _, _ = eng.modulate(S, idx=idx)
+    chan = chan_for('rayleigh_mp', num.fs, 'Vehicular_A', 2.0, v)
+    delays, gains = O.itu_taps('Vehicular_A', num.fs)
+    phases = 2 * np.pi * rs.rand(R, len(delays), 16)
+    u = torch.from_numpy((phases / (2 * np.pi)).astype(np.float32)).cuda().reshape(1, -1)
+    got = eng.channel_rx_fft(tx, chan, 1, R, S, u, nat.WINDOW_FULL)
+    assert got is not None
+    Y, power = got
+    sig, _ = O.modulate_stream(bits, num)
+    for r in range(R):
+        faded = O.rayleigh_filter(sig, num.fs, O.doppler_hz(2.0, v), delays, gains, phases[r])
+        assert rel_err(Y[r].cpu().numpy(), O.rx_fft_stream(faded, num)) < 1e-5
+        assert abs(float(power.view(-1)[r]) / np.sum(np.abs(faded) ** 2) - 1) < 1e-5

@@ -69,7 +69,7 @@ def test_fused_mimo_reports_unsupported_like_the_single_tx_kernel():
     from lte_b200 import chan_for
     from lte_b200 import _native as nat
     cfg, eng = _engine(1.25, 'QPSK', 2)
-    chan = chan_for('rayleigh_mp', cfg.fs, 'Vehicular_B', 2.0, 350.0)      # Doppler beyond one polynomial per symbol
+    chan = chan_for('rayleigh_mp', cfg.fs, 'Vehicular_A', 2.0, 650.0)      # Doppler beyond one polynomial per symbol
     tx = torch.zeros((2, 2, 3 * eng.L), dtype=torch.complex64, device='cuda')
     ph = eng.random_phases(2, 2 * 2 * chan.num_taps * nat.LTE_JAKES_TONES, 1, 0)
     assert eng.channel_rx_fft(tx, chan, 2, 2, 3, ph, nat.WINDOW_USEFUL, T=2) is None
