@@ -11,13 +11,14 @@ struct AwgnArgs {
     const double* power;        // [rows] sum |y|^2 of the stream (lte_channel_tdl / lte_channel_rx_fft)
     const float* snr_lin;       // [rows]
     uint32_t key;
+    PhiloxKeys ks;              // round keys of `key` (constant-bank operands in the consumers' loops)
     unsigned long long row_id0;
     float n_stream;             // samples per stream, S * L
     int combine;                // MRC only: one draw per combiner output (see lte_awgn_desc)
 };
 
 __device__ __forceinline__ float2 awgn_at(const AwgnArgs& A, float sigma, long long row, int s, int N, int kb, float2 y) {
-    const float2 w = lte_noise_sample(A.key, (uint32_t)(A.row_id0 + (unsigned long long)row), (uint32_t)(s * N + kb));
+    const float2 w = lte_noise_sample(A.ks, (uint32_t)(A.row_id0 + (unsigned long long)row), (uint32_t)(s * N + kb));
     return make_float2(fmaf(sigma, w.x, y.x), fmaf(sigma, w.y, y.y));
 }
 
@@ -27,6 +28,7 @@ static inline int make_awgn_args(AwgnArgs& A, const lte_plan* p, const lte_awgn_
     A.power = d->power;
     A.snr_lin = d->snr_lin;
     A.key = lte_key(d->seed, LTE_DOMAIN_NOISE);
+    A.ks = philox_key_schedule(A.key);
     A.row_id0 = d->row_id0;
     A.n_stream = (float)((size_t)S * p->dev.L);
     A.combine = d->combine;

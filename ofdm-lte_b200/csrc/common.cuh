@@ -106,6 +106,26 @@ __host__ __device__ __forceinline__ void philox2x32_10(uint32_t key, uint32_t c0
     r1 = c1;
 }
 
+// The same generator with the ten round keys key + i W handed in (kernel parameters = constant-bank operands of
+// the XOR): a hot loop does not re-derive the schedule for every draw.
+struct PhiloxKeys { uint32_t k[10]; };
+static inline PhiloxKeys philox_key_schedule(uint32_t key) {
+    PhiloxKeys s;
+    for (int i = 0; i < 10; ++i) s.k[i] = key + (uint32_t)i * 0x9E3779B9u;
+    return s;
+}
+__device__ __forceinline__ void philox2x32_10_ks(const PhiloxKeys& ks, uint32_t c0, uint32_t c1, uint32_t& r0, uint32_t& r1) {
+    const uint32_t M = 0xD256D193u;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi = __umulhi(M, c0), lo = M * c0;
+        c0 = hi ^ ks.k[i] ^ c1;
+        c1 = lo;
+    }
+    r0 = c0;
+    r1 = c1;
+}
+
 // Key derivation: mixes the user seed with a domain tag so that bits, phases and
 // noise never share a stream.
 #define LTE_DOMAIN_NOISE 0x6e6f6973u
@@ -124,9 +144,18 @@ static inline bool lte_ids_fit(uint64_t id0, uint64_t count) { return id0 <= (1u
 // One complex unit normal (re, im ~ N(0,1)) for (row, sample) by Box-Muller; branch-free.
 // u1 = (r0 + 0.5) 2^-32 keeps the full 32-bit tail resolution for small r0 (fp32 is exact
 // below 2^24), so |z| reaches sqrt(-2 ln 2^-33) = 6.8 sigma.
+__device__ __forceinline__ float2 lte_noise_from_bits(uint32_t r0, uint32_t r1);
 __device__ __forceinline__ float2 lte_noise_sample(uint32_t key, uint32_t row, uint32_t sample) {
     uint32_t r0, r1;
     philox2x32_10(key, sample, row, r0, r1);
+    return lte_noise_from_bits(r0, r1);
+}
+__device__ __forceinline__ float2 lte_noise_sample(const PhiloxKeys& ks, uint32_t row, uint32_t sample) {
+    uint32_t r0, r1;
+    philox2x32_10_ks(ks, sample, row, r0, r1);
+    return lte_noise_from_bits(r0, r1);
+}
+__device__ __forceinline__ float2 lte_noise_from_bits(uint32_t r0, uint32_t r1) {
     const float u1 = fmaf((float)r0, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
     const float ang = __uint_as_float(0x3f800000u | (r1 >> 9)) - 1.5f;      // [-0.5, 0.5) turns, 23 bits
     float rad;                                                              // sqrt(-2 ln u1)
