@@ -22,6 +22,9 @@ def _engine(bw, mod, T):
     (20.0, '64-QAM', 'Pedestrian_A', 3.0, 4, 4, 2, 2),
     (10.0, 'QPSK', 'Vehicular_A', 30.0, 2, 1, 14, 2),         # degree-2 polynomial
     (2.5, '16-QAM', 'Vehicular_A', 120.0, 2, 4, 4, 2),        # degree-4 polynomial
+    (5.0, 'QPSK', 'Pedestrian_A', 3.0, 4, 8, 2, 1),           # eight receive antennas
+    (5.0, 'QPSK', 'Pedestrian_A', 3.0, 8, 2, 2, 1),           # eight transmit antennas
+    (1.25, '16-QAM', 'Vehicular_A', 350.0, 2, 2, 3, 2),       # degree-6 polynomial, 16 symbols per CTA
 ])
 def test_fused_mimo_grid_and_power_match_the_staged_kernels(bw, mod, prof, v, T, R, S, B):
     from lte_b200 import chan_for
@@ -38,9 +41,13 @@ def test_fused_mimo_grid_and_power_match_the_staged_kernels(bw, mod, prof, v, T,
         got = eng.channel_rx_fft(tx, chan, B, R, S, ph, window, T=T)
         assert got is not None
         Y, p = got
+        # at 650 Hz Doppler the STAGED kernel is the less accurate side: it linearises h over 8 samples per thread,
+        # (2 pi fD / fs 3.5)^2 / 2 = 3e-5 at 1.92 MHz (channel.cu); the fused degree-6 polynomial is checked against
+        # the oracle itself in tests/test_gpu_fused.py
+        tol = TOL if v < 300.0 else 1e-4
         err = float((Y - Y_ref).abs().max() / Y_ref.abs().max())
-        assert err < TOL, err
-        assert float(((p - p_ref) / p_ref).abs().max()) < TOL
+        assert err < tol, err
+        assert float(((p - p_ref) / p_ref).abs().max()) < tol
 
 
 def test_sfbc_and_sm_passes_with_fused_link_track_the_staged_ones():
