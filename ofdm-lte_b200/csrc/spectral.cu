@@ -345,7 +345,7 @@ channel_spectral_kernel(const DevPlan P, const SpecParams C, const uint8_t* __re
                         const float2* __restrict__ G, const float2* __restrict__ tail,
                         const float* __restrict__ coef_g, float* __restrict__ Y, float* __restrict__ Yp,
                         double* __restrict__ power, int k0, int nk, int S, int R, int B, int nwarps, int dmax2) {
-    constexpr int RP = R2 / 2, NCF = NT * 6 * R2;               // antenna pairs, coefficient floats per symbol
+    constexpr int NCF = NT * 6 * R2;                            // coefficient floats per symbol
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int cp = P.cp, L = P.L;
