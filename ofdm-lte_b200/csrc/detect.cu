@@ -82,6 +82,60 @@ bits_to_indices_x4_kernel(const uint8_t* __restrict__ bits, long long nbits, uin
     *(unsigned*)(idx + A) = out;
 }
 
+// Packed rows, one 16-byte-aligned group of idx per thread: the group's 16 symbols are 16 * bps <= 96 bits at an
+// arbitrary bit offset of the row, i.e. at most 13 bytes.  They are read as four aligned 32-bit words, turned
+// big endian (np.packbits is MSB first), shifted so that the first symbol starts at bit 0, cut into symbols at
+// compile-time positions and leave as ONE 128-bit store.  Groups that touch a row boundary, the ragged end of the
+// bit budget or the end of the buffer go through packed_symbol() byte by byte.
+template <int BPS>
+__global__ void __launch_bounds__(256)
+bits_to_indices_x16_kernel(const uint8_t* __restrict__ bits, long long nbits, uint8_t* __restrict__ idx, unsigned nsym,
+                           unsigned chunks, long long total_bytes) {
+    const unsigned row = blockIdx.x / chunks;
+    const unsigned g = (blockIdx.x - row * chunks) * 256u + threadIdx.x;
+    const unsigned long long row0 = (unsigned long long)row * nsym;           // address of the row's first index
+    const unsigned long long A = ((row0 >> 4) + g) << 4;                      // this thread's aligned group
+    const long long q0 = (long long)A - (long long)row0;                      // its first symbol (may be < 0)
+    if (q0 >= (long long)nsym) return;
+    const long long row_bytes = (nbits + 7) >> 3;
+    const uint8_t* src = bits + (size_t)row * row_bytes;
+    const long long bi0 = q0 * BPS, by = bi0 >> 3;
+    const unsigned long long addr = (unsigned long long)(src + by);
+    const unsigned long long a0 = addr & ~3ull;
+    // whole group inside the row and its bit budget, and the four aligned words inside the buffer
+    const bool fast = q0 >= 0 && q0 + 15 < (long long)nsym && (q0 + 16) * BPS <= nbits &&
+                      a0 >= (unsigned long long)bits && (long long)(a0 - (unsigned long long)bits) + 16 <= total_bytes;
+    if (!fast) {
+        for (int k = 0; k < 16; ++k) {
+            const long long q = q0 + k;
+            if (q >= 0 && q < (long long)nsym) idx[A + k] = (uint8_t)packed_symbol(src, row_bytes, nbits, q, BPS);
+        }
+        return;
+    }
+    const unsigned* wp = (const unsigned*)a0;
+    unsigned W0 = __byte_perm(__ldg(wp), 0, 0x0123), W1 = __byte_perm(__ldg(wp + 1), 0, 0x0123);
+    unsigned W2 = __byte_perm(__ldg(wp + 2), 0, 0x0123), W3 = __byte_perm(__ldg(wp + 3), 0, 0x0123);
+    const unsigned off = (unsigned)(addr & 3ull) * 8u + (unsigned)(bi0 & 7);  // < 32
+    const unsigned V[3] = {__funnelshift_l(W1, W0, off), __funnelshift_l(W2, W1, off), __funnelshift_l(W3, W2, off)};
+    constexpr unsigned m = (1u << BPS) - 1u;
+    unsigned out[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        unsigned v = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int pos = (4 * o + i) * BPS;                 // bit position of the symbol, compile time
+            const int wi = pos >> 5, sh = pos & 31;
+            unsigned x;
+            if (sh + BPS <= 32) x = V[wi] >> (32 - sh - BPS);
+            else x = __funnelshift_l(V[wi + 1 < 3 ? wi + 1 : 2], V[wi], sh) >> (32 - BPS);
+            v |= (x & m) << (8 * i);
+        }
+        out[o] = v;
+    }
+    *(uint4*)(idx + A) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
 // core/modulator.py:109-110: format(idx, '0{b}b'); output truncated to nbits.
 __global__ void indices_to_bits_kernel(const uint8_t* __restrict__ idx, long long nsym, uint8_t* __restrict__ bits,
                                        long long nbits, int bps, long long total) {
@@ -109,6 +163,18 @@ extern "C" int lte_bits_to_indices(const lte_plan* p, const uint8_t* bits, int64
     const int packed = nbits < 0;        // negative nbits: rows are np.packbits() bytes
     const long long nb = packed ? -nbits : nbits;
     if (nsym >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
+    if (packed && ((uintptr_t)idx & 15) == 0 && (p->dev.bps == 2 || p->dev.bps == 4 || p->dev.bps == 6)) {
+        const unsigned ch16 = (unsigned)(((nsym + 15) / 16 + 1 + 255) / 256);  // + 1: a row may straddle one more group
+        if ((long long)ch16 * B >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;
+        const long long total_bytes = (long long)B * ((nb + 7) >> 3);
+        const unsigned grid16 = (unsigned)((long long)ch16 * B);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (p->dev.bps == 2) bits_to_indices_x16_kernel<2><<<grid16, 256, 0, st>>>(bits, nb, idx, (unsigned)nsym, ch16, total_bytes);
+        else if (p->dev.bps == 4) bits_to_indices_x16_kernel<4><<<grid16, 256, 0, st>>>(bits, nb, idx, (unsigned)nsym, ch16, total_bytes);
+        else bits_to_indices_x16_kernel<6><<<grid16, 256, 0, st>>>(bits, nb, idx, (unsigned)nsym, ch16, total_bytes);
+        LTE_CHECK_CUDA(cudaGetLastError());
+        return LTE_OK;
+    }
     if (packed && ((uintptr_t)idx & 3) == 0) {
         const unsigned ch4 = (unsigned)(((nsym + 3) / 4 + 1 + 255) / 256);     // + 1: a row may straddle one more group
         if ((long long)ch4 * B >= (1ll << 31)) return LTE_ERR_UNSUPPORTED;

@@ -218,3 +218,25 @@ def test_packed_bits_to_indices_matches_the_byte_per_bit_path(mod, nbits_off):
         got_p = eng.bits_to_indices(torch.from_numpy(packed).cuda(), nbits, S, packed=True).cpu().numpy()
         got_u = eng.bits_to_indices(torch.from_numpy(bits).cuda(), nbits, S).cpu().numpy()
         assert np.array_equal(got_u, want) and np.array_equal(got_p, want)
+
+
+@pytest.mark.parametrize('bw,mod,S,B', [(20.0, '64-QAM', 14, 5), (10.0, '16-QAM', 3, 4), (5.0, 'QPSK', 15, 3), (2.5, '64-QAM', 1, 7)])
+def test_packed_bits_sixteen_symbols_per_thread(bw, mod, S, B):
+    """The e2e path's unpack kernel (16 symbols per thread, one 128-bit store) on the headline row length (13 986
+    symbols: rows neither start nor end on a 16-symbol group) and on ragged bit budgets."""
+    import torch
+    from config import LTEConfig
+    from lte_b200 import LinkEngine
+    eng = LinkEngine.from_config(LTEConfig(bw, 15.0, mod))
+    b = eng.bps
+    nsym = S * eng.Nd
+    for off in (0, 3, 2 * b + 1):
+        nbits = nsym * b - off
+        rs = np.random.RandomState(nsym + off)
+        bits = rs.randint(0, 2, (B, nbits)).astype(np.uint8)
+        packed = np.stack([np.packbits(r) for r in bits])
+        pad = np.zeros((B, nsym * b - nbits), dtype=np.uint8)
+        full = np.concatenate([bits, pad], axis=1).reshape(B, nsym, b)
+        want = (full * (1 << np.arange(b - 1, -1, -1))).sum(axis=2).astype(np.uint8)
+        got = eng.bits_to_indices(torch.from_numpy(packed).cuda(), nbits, S, packed=True).cpu().numpy()
+        assert np.array_equal(got, want), (bw, mod, off)
