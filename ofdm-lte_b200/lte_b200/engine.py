@@ -790,10 +790,12 @@ class LinkEngine:
         self.launches += 1
         return errors, idx_rx
 
-    def mrc_demap_count(self, Y, H, idx_tx, B, R, S, nbits=None, window=nat.WINDOW_USEFUL, errors=None, awgn=None):
+    def mrc_demap_count(self, Y, H, idx_tx, B, R, S, nbits=None, window=nat.WINDOW_USEFUL, errors=None, awgn=None,
+                        accumulate=False):
+        """accumulate: add to `errors` (the kernels count with atomics) instead of starting from zero."""
         if errors is None:
             errors = torch.zeros(B, dtype=torch.int64, device=self.device)
-        else:
+        elif not accumulate:
             errors.zero_()
         nb = int(nbits) if nbits is not None else S * self.Nd * self.bps
         if awgn is None:
@@ -806,13 +808,13 @@ class LinkEngine:
         self.launches += 1
         return errors
 
-    def mrc_demap_count_compact(self, Yd, Hp, idx_tx, B, R, S, nbits=None, errors=None, awgn=None):
+    def mrc_demap_count_compact(self, Yd, Hp, idx_tx, B, R, S, nbits=None, errors=None, awgn=None, accumulate=False):
         """MRC + slicer + bit-error count on the compact layout (Yd [B*R, S, 2 ndp], Hp [B*R, slots, Np]): every
         thread interpolates its own bin between its two pilots; counts are bit-identical to
-        estimate + mrc_demap_count on the windowed layout."""
+        estimate + mrc_demap_count on the windowed layout.  accumulate: add to `errors` instead of zeroing it."""
         if errors is None:
             errors = torch.zeros(B, dtype=torch.int64, device=self.device)
-        else:
+        elif not accumulate:
             errors.zero_()
         nb = int(nbits) if nbits is not None else S * self.Nd * self.bps
         nat.check(nat.lib.lte_mrc_demap_count_compact(self._plan, _ptr(Yd), _ptr(Hp), _ptr(idx_tx), _ptr(errors), nb, B,
@@ -870,7 +872,7 @@ class LinkEngine:
         return ws['spectral']
 
     def simo_ber(self, ws, chan, snr_lin_rows, seed, stream_id0=0, idx=None, nbits=None, noise_domain=1,
-                 fused=False, spectral=None):
+                 fused=False, spectral=None, accumulate=False):
         """One pass of the SIMO-MRC link chain over B independent streams.
 
         ws: workspace(); snr_lin_rows: float32 [B*R] linear SNR per (stream, antenna);
@@ -884,6 +886,8 @@ class LinkEngine:
         unsupported).  spectral (default: same as fused): at low Doppler use the spectral link
         (lte_tx_spectral + lte_channel_spectral, compact grid) instead of the fused time-domain kernel;
         silently falls back to `fused` outside its validity range.
+        accumulate: the counts are ADDED to ws['errors'] (a sweep whose batches keep the same SNR per stream slot
+        then needs no per-batch zeroing / reduction: the caller zeroes ws['errors'] once and reads it at the end).
         """
         B, S, R = ws['B'], ws['S'], ws['R']
         if idx is None:
@@ -900,7 +904,7 @@ class LinkEngine:
                                                     compact=True, out_pilots=ws['Yp'])
             awgn = self.awgn_desc(power, snr_lin_rows, seed, stream_id0 * R, combine=(noise_domain == 3))
             Hp = self.estimate_compact(Yp, B * R, S, out=ws['Hp'], awgn=awgn)
-            return self.mrc_demap_count_compact(Yd, Hp, idx, B, R, S, nbits=nbits, errors=ws['errors'], awgn=awgn)
+            return self.mrc_demap_count_compact(Yd, Hp, idx, B, R, S, nbits=nbits, errors=ws['errors'], awgn=awgn, accumulate=accumulate)
         if 'tx' not in ws:
             ws['tx'] = self._empty((B, S * self.L), torch.complex64)
             k0, nk = self.window(nat.WINDOW_USEFUL)
@@ -915,7 +919,7 @@ class LinkEngine:
                 Y, power = got
                 awgn = self.awgn_desc(power, snr_lin_rows, seed, stream_id0 * R, combine=(noise_domain == 3))
                 H = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, out=ws['H'], awgn=awgn)
-                return self.mrc_demap_count(Y, H, idx, B, R, S, nbits=nbits, errors=ws['errors'], awgn=awgn)
+                return self.mrc_demap_count(Y, H, idx, B, R, S, nbits=nbits, errors=ws['errors'], awgn=awgn, accumulate=accumulate)
             noise_domain = 3 if noise_domain == 3 else 2
             if 'faded' not in ws:
                 ws['faded'] = self._empty((B, R, S * self.L), torch.complex64)
@@ -931,11 +935,11 @@ class LinkEngine:
             Y = self.rx_fft(rx, B * R, S, nat.WINDOW_USEFUL, rx_div=div, out=ws['Y'])
             awgn = self.awgn_desc(power, snr_lin_rows, seed, stream_id0 * R, combine=(noise_domain == 3))
             H = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, out=ws['H'], awgn=awgn)
-            return self.mrc_demap_count(Y, H, idx, B, R, S, nbits=nbits, errors=ws['errors'], awgn=awgn)
+            return self.mrc_demap_count(Y, H, idx, B, R, S, nbits=nbits, errors=ws['errors'], awgn=awgn, accumulate=accumulate)
         Y = self.rx_fft(rx, B * R, S, nat.WINDOW_USEFUL, rx_div=div, power=power, snr_lin=snr_lin_rows, seed=seed,
                         row_id0=stream_id0 * R, out=ws['Y'], noise_domain=noise_domain)
         H = self.estimate(Y, B * R, S, nat.WINDOW_USEFUL, out=ws['H'])
-        return self.mrc_demap_count(Y, H, idx, B, R, S, nbits=nbits, errors=ws['errors'])
+        return self.mrc_demap_count(Y, H, idx, B, R, S, nbits=nbits, errors=ws['errors'], accumulate=accumulate)
 
 
 def _on_own_device(fn):

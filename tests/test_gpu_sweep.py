@@ -113,3 +113,24 @@ def test_shared_channel_sweep_matches_the_independent_sweep_statistically():
     awgn_only = __import__('lte_b200').chan_for('awgn', eng.fs, 'Pedestrian_A', 2.0, 0.0)
     with pytest.raises(ValueError):
         simo_sweep_shared_channel(eng, awgn_only, snr, 4, 2)
+
+
+def test_simo_ber_accumulate_equals_the_sum_of_separate_passes():
+    """simo_ber(accumulate=True) adds into the workspace's per-slot counters (what bench.py's timed loop does):
+    three passes accumulate to the sum of three separate passes, on the spectral, fused and staged paths."""
+    import torch
+    from config import LTEConfig
+    from lte_b200 import LinkEngine, chan_for
+    cfg = LTEConfig(2.5, 15.0, '16-QAM')
+    eng = LinkEngine.from_config(cfg)
+    B, S, R = 6, 14, 2
+    rows = torch.tensor([3.0, 30.0], dtype=torch.float32, device='cuda').repeat(B // 2).repeat_interleave(R).contiguous()
+    for prof, v, kw in (('Pedestrian_A', 3.0, dict(fused=True, noise_domain=3)), ('Vehicular_A', 60.0, dict(fused=True, noise_domain=2)),
+                        ('Pedestrian_B', 3.0, dict(fused=False, noise_domain=1))):
+        chan = chan_for('rayleigh_mp', cfg.fs, prof, 2.0, v)
+        ws = eng.workspace(B, S, R, fading=True, fused=kw['fused'], lazy=kw['fused'])
+        want = sum(eng.simo_ber(ws, chan, rows, 5, stream_id0=i * B, **kw).clone() for i in range(3))
+        ws['errors'].zero_()
+        for i in range(3):
+            got = eng.simo_ber(ws, chan, rows, 5, stream_id0=i * B, accumulate=True, **kw)
+        assert torch.equal(got, want) and int(want.sum()) > 0
