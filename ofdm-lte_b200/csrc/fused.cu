@@ -73,11 +73,11 @@ channel_rx_fft_kernel(const DevPlan P, const TdlParams C, const float2* __restri
     const int RP = R2 / 2;
     for (int p = 0; p < RP; ++p) {
         c2 v[FFT_ELEMS];
-#pragma unroll
-        for (int e = 0; e < FFT_ELEMS; ++e) v[e] = {pk(0.f, 0.f), pk(0.f, 0.f)};
         float pwa = 0.f, pwb = 0.f;
         if (valid) {
-            for (int tap = 0; tap < C.num_taps; ++tap) {
+            // FIRST = the first tap: the accumulators start from its product (no zero fill + fma on zero)
+            auto tap_pass = [&](int tap, auto first) {
+                constexpr bool FIRST = decltype(first)::value;
                 const float* ct = sc + (size_t)tap * NC * 2 * R2 + 2 * p;
                 f2 cre[K + 1], cim[K + 1];
 #pragma unroll
@@ -96,12 +96,19 @@ channel_rx_fft_kernel(const DevPlan P, const TdlParams C, const float2* __restri
                     for (int k = K - 1; k >= 0; --k) { hre = fma2(hre, tau, cre[k]); him = fma2(him, tau, cim[k]); }
                     const float2 x = xt[e * TPF];
                     const f2 xre = pk(x.x, x.x), xim = pk(x.y, x.y), nxim = pk(-x.y, -x.y);
-                    v[e].re = fma2(hre, xre, v[e].re);
-                    v[e].re = fma2(him, nxim, v[e].re);
-                    v[e].im = fma2(hre, xim, v[e].im);
-                    v[e].im = fma2(him, xre, v[e].im);
+                    if (FIRST) {
+                        v[e].re = fma2(him, nxim, mul2(hre, xre));
+                        v[e].im = fma2(him, xre, mul2(hre, xim));
+                    } else {
+                        v[e].re = fma2(hre, xre, v[e].re);
+                        v[e].re = fma2(him, nxim, v[e].re);
+                        v[e].im = fma2(hre, xim, v[e].im);
+                        v[e].im = fma2(him, xre, v[e].im);
+                    }
                 }
-            }
+            };
+            tap_pass(0, std::true_type());
+            for (int tap = 1; tap < C.num_taps; ++tap) tap_pass(tap, std::false_type());
             // power of this thread's 16 useful samples ...
             f2 acc = pk(0.f, 0.f);
 #pragma unroll
@@ -132,6 +139,10 @@ channel_rx_fft_kernel(const DevPlan P, const TdlParams C, const float2* __restri
                 acc = fma2(yim, yim, acc);
             }
             upk(acc, pwa, pwb);
+        }
+        else {
+#pragma unroll
+            for (int e = 0; e < FFT_ELEMS; ++e) v[e] = {pk(0.f, 0.f), pk(0.f, 0.f)};
         }
         // ---- stream power: one atomic per warp (or per symbol when a warp carries several) ---------
         // the tap gains carry the FFT's 1/sqrt(N) (host side), so the power is scaled back by N here

@@ -421,6 +421,7 @@ class LinkEngine:
 
     # ------------------------------------------------------------------ spatial multiplexing
     DETECTORS = {'MMSE': 0, 'IRC': 0, 'ZF': 1, 'SIC': 2, 'MRC': 3}
+    SPECTRAL_MAX_DELAY = 32          # longest tap delay in samples for which simo_ber picks the spectral link by itself
 
     def sfbc_decode_count(self, Y, H0, H1, idx_tx, B, R, S, window=nat.WINDOW_FULL, nbits=None, errors=None, awgn=None):
         """Alamouti decode + slicer + bit-error count in one kernel: int64 [B] errors against idx_tx [B, S*2*(Nd//2)]."""
@@ -883,7 +884,8 @@ class LinkEngine:
         (statistically identical, 1/R of the generator work).  fused: fading channel + RX FFT in
         one kernel (the faded streams are never written; needs noise_domain 2 or 3 -- 1 is promoted
         to 2; falls back to the staged kernels when lte_channel_rx_fft reports the configuration
-        unsupported).  spectral (default: same as fused): at low Doppler use the spectral link
+        unsupported).  spectral (default: chosen automatically when `fused`): at low Doppler and short delay spreads
+        (<= SPECTRAL_MAX_DELAY samples; True forces it wherever it is supported) use the spectral link
         (lte_tx_spectral + lte_channel_spectral, compact grid) instead of the fused time-domain kernel;
         silently falls back to `fused` outside its validity range.
         accumulate: the counts are ADDED to ws['errors'] (a sweep whose batches keep the same SNR per stream slot
@@ -893,7 +895,10 @@ class LinkEngine:
         if idx is None:
             idx = self.random_indices(B, S, seed, stream_id0, out=ws['idx'])
         if spectral is None:
-            spectral = fused
+            # automatic choice: the spectral link pays while the Horner sweep over the delay spread is short; measured
+            # at 20 MHz / 1x4 per 4096 subframes: Pedestrian_A (13 samples) 1.85 ms against 2.25 ms through the fused
+            # time-domain kernel, Vehicular_A (77) 3.09 against 2.48 ms, Pedestrian_B (114) 3.66 against 2.48 ms
+            spectral = fused and chan.num_taps > 0 and max(chan.delay[:chan.num_taps]) <= self.SPECTRAL_MAX_DELAY
         if spectral and chan.num_taps > 0 and self._spectral_buffers(ws, chan):
             # low Doppler: the spectral link (csrc/spectral.cu) -- no time-domain stream, one forward transform
             # per OFDM symbol, compact grid; the lazy AWGN draws are those of the other paths

@@ -147,7 +147,7 @@ def test_spectral_sweep_counts_track_the_fused_path(bw, mod, R, prof):
     rows = snr.repeat(B // 3).repeat_interleave(R).contiguous()
     for nd in (2, 3):
         e_fused = eng.simo_ber(wf, chan, rows, seed=4, stream_id0=11, fused=True, spectral=False, noise_domain=nd).clone()
-        e_spec = eng.simo_ber(wsp, chan, rows, seed=4, stream_id0=11, fused=True, noise_domain=nd).clone()
+        e_spec = eng.simo_ber(wsp, chan, rows, seed=4, stream_id0=11, fused=True, spectral=True, noise_domain=nd).clone()
         assert wsp['spectral'] and 'tx' not in wsp                  # the spectral link really ran
         bits = S * eng.Nd * eng.bps
         assert int(e_fused.sum()) > 0
@@ -167,3 +167,28 @@ def test_spectral_reports_unsupported():
     assert eng2.spectral_workspace_bytes(chan_for('rayleigh_mp', num2.fs, 'Vehicular_B', 2.0, 1.0), 1, 1, 1) is None
     eng3 = LinkEngine(num2.N, num2.Nc, num2.cp_length, 2, num2.fs)   # cp = 9: rows of the tail array are not 16-byte runs
     assert eng3.spectral_workspace_bytes(chan_for('rayleigh_mp', num2.fs, 'Pedestrian_A', 2.0, 3.0), 1, 1, 1) is None
+
+
+def test_automatic_choice_leaves_long_delay_spreads_to_the_time_domain_kernel():
+    """simo_ber picks the spectral link by itself only while the Horner sweep is short (<= SPECTRAL_MAX_DELAY samples):
+    Vehicular_A at 20 MHz (77 samples) goes through the fused time-domain kernel unless spectral=True asks for it;
+    both give the same counts up to slicer-boundary symbols."""
+    from config import LTEConfig
+    from lte_b200 import LinkEngine, chan_for
+    cfg = LTEConfig(20.0, 15.0, '16-QAM')
+    eng = LinkEngine.from_config(cfg)
+    B, S, R = 4, 14, 2
+    rows = torch.full((B * R,), 10.0, dtype=torch.float32, device='cuda')
+    short = chan_for('rayleigh_mp', cfg.fs, 'Pedestrian_A', 2.0, 3.0)
+    long_ = chan_for('rayleigh_mp', cfg.fs, 'Vehicular_A', 2.0, 3.0)
+    assert max(short.delay[:short.num_taps]) <= eng.SPECTRAL_MAX_DELAY < max(long_.delay[:long_.num_taps])
+    w1 = eng.workspace(B, S, R, fading=True, fused=True, lazy=True)
+    eng.simo_ber(w1, short, rows, seed=1, fused=True, noise_domain=2)
+    assert w1.get('spectral') is True and 'tx' not in w1
+    w2 = eng.workspace(B, S, R, fading=True, fused=True, lazy=True)
+    auto = eng.simo_ber(w2, long_, rows, seed=1, fused=True, noise_domain=2).clone()
+    assert 'spectral' not in w2 and 'tx' in w2
+    w3 = eng.workspace(B, S, R, fading=True, fused=True, lazy=True)
+    forced = eng.simo_ber(w3, long_, rows, seed=1, fused=True, spectral=True, noise_domain=2).clone()
+    assert w3.get('spectral') is True
+    assert int((auto - forced).abs().max()) <= 3 and int(auto.sum()) > 0
