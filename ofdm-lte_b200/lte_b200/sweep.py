@@ -51,8 +51,8 @@ def simo_sweep(engine, chan, snr_db, n_trials, num_rx, symbols_per_stream=14, se
                rank=0, world=1, noise_domain='lazy', fused=True, bits_host=None):
     """BER of the SIMO-MRC chain at every SNR point, `n_trials` independent streams per point.
 
-    The default is the engine's fast path: spectral link at low Doppler, fused channel + RX-FFT kernel
-    otherwise, staged kernels where neither applies (the engine falls back by itself), with the AWGN added
+    The default is the engine's fast path: spectral link at low Doppler and short delay spreads, fused channel +
+    RX-FFT kernel otherwise, staged kernels where neither applies (the engine falls back by itself), with the AWGN added
     lazily by the consumers -- the same draws, hence bit-identical counts, as noise on the kept bins
     (`'bins'`).  `'combined'` draws one equivalent noise sample per MRC output instead of one per antenna
     (same BER statistics, different sample values, 1/R of the generator work): opt in by name.
