@@ -159,6 +159,9 @@ int lte_histogram(const float* x, int64_t n, float lo, float step, int32_t bins,
  * plan state: lte_plan_add_dft(plan, M) builds them once (synchronous, like lte_plan_create); lte_dft_m on an
  * M the plan does not hold returns LTE_ERR_INVALID_ARG. */
 int lte_plan_add_dft(lte_plan* plan, int32_t M);
+/* lte_dft_qam = lte_qam_map + lte_dft_m(forward) in one kernel (the QAM map rides in the transform's load; same
+ * arithmetic): idx [rows][M] -> out [rows][M]. */
+int lte_dft_qam(const lte_plan*, const uint8_t* idx, lte_c32* out, int32_t M, int64_t rows, void* stream);
 int lte_dft_m(const lte_plan*, const lte_c32* in, lte_c32* out, int32_t M, int32_t inverse,
               int64_t rows, void* stream);
 
@@ -302,6 +305,9 @@ int lte_crs_ls_interp_awgn(const lte_plan*, const lte_c32* Y, lte_c32* H, int wi
 int lte_mrc_demap_count_awgn(const lte_plan*, const lte_c32* Y, const lte_c32* H, const uint8_t* idx_tx,
                              unsigned long long* errors, int window, int64_t nbits, int64_t B, int32_t R,
                              int32_t S, const lte_awgn_desc* awgn, void* stream);
+/* lte_equalize_zf on a noise-free grid (SISO through lte_channel_rx_fft): the AWGN joins as the data bins are read. */
+int lte_equalize_zf_awgn(const lte_plan*, const lte_c32* Y, const lte_c32* H, lte_c32* out, int window,
+                         int64_t B, int32_t S, const lte_awgn_desc* awgn, void* stream);
 
 /* Compact sweep layout (produced by lte_channel_spectral with Ypilot != NULL): the grid travels as
  *   Ydata  [B*R][S][2 ndp]            data symbol d of the OFDM symbol at element d, ndp = ceil(Nd / 2)

@@ -336,7 +336,7 @@ extern "C" int lte_demap_count(const lte_plan* p, const lte_c32* syms, const uin
 // ZF: Y / (H + 1e-6) (core/lte_receiver.py:174), gathered at the data bins (:303-316).
 __global__ void __launch_bounds__(256)
 zf_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restrict__ H, float2* __restrict__ out,
-          int k0, int nk, int S, int nslot, long long total) {
+          int k0, int nk, int S, int nslot, long long total, const AwgnArgs A, int noisy) {
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
          g += (long long)gridDim.x * blockDim.x) {
         const int d = (int)(g % P.Nd);
@@ -345,6 +345,7 @@ zf_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restric
         const long long b = bs / S;
         const int kk = P.data_idx[d] - k0;
         float2 y = Y[(size_t)bs * nk + kk];
+        if (noisy) y = awgn_at(A, lte_sigma(A.power[b], A.n_stream, A.snr_lin[b]), b, s, P.N, kk + k0, y);   // lazy AWGN
         if (H) {
             float2 h = H[((size_t)b * nslot + s / LTE_SLOT_SYMBOLS) * nk + kk];
             h.x += 1e-6f;
@@ -354,19 +355,32 @@ zf_kernel(const DevPlan P, const float2* __restrict__ Y, const float2* __restric
     }
 }
 
-extern "C" int lte_equalize_zf(const lte_plan* p, const lte_c32* Y, const lte_c32* H, lte_c32* out, int window,
-                               int64_t B, int32_t S, void* stream) {
+static int launch_zf(const lte_plan* p, const lte_c32* Y, const lte_c32* H, lte_c32* out, int window, int64_t B,
+                     int32_t S, const lte_awgn_desc* awgn, void* stream) {
     if (!p || !Y || !out || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
     int32_t k0, nk;
     int rc = lte_plan_window(p, window, &k0, &nk);
     if (rc) return rc;
+    AwgnArgs A = {};
+    if (awgn && (rc = make_awgn_args(A, p, awgn, S, B))) return rc;
     if (B == 0) return LTE_OK;
     const long long total = (long long)B * S * p->dev.Nd;
     const int nslot = (S + LTE_SLOT_SYMBOLS - 1) / LTE_SLOT_SYMBOLS;
     zf_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p->dev, (const float2*)Y, (const float2*)H,
-                                                                     (float2*)out, k0, nk, S, nslot, total);
+                                                                     (float2*)out, k0, nk, S, nslot, total, A, awgn ? 1 : 0);
     LTE_CHECK_CUDA(cudaGetLastError());
     return LTE_OK;
+}
+
+extern "C" int lte_equalize_zf(const lte_plan* p, const lte_c32* Y, const lte_c32* H, lte_c32* out, int window,
+                               int64_t B, int32_t S, void* stream) {
+    return launch_zf(p, Y, H, out, window, B, S, nullptr, stream);
+}
+
+extern "C" int lte_equalize_zf_awgn(const lte_plan* p, const lte_c32* Y, const lte_c32* H, lte_c32* out, int window,
+                                    int64_t B, int32_t S, const lte_awgn_desc* awgn, void* stream) {
+    if (!awgn) return LTE_ERR_INVALID_ARG;
+    return launch_zf(p, Y, H, out, window, B, S, awgn, stream);
 }
 
 // MRC (core/ofdm_core.py:1484-1532): thread = (stream, data bin); H of the slot is held in

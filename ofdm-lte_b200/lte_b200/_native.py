@@ -65,6 +65,8 @@ _SIGS = {
     'lte_papr_symbols': ([_P, _P, _I32, _P, _P, _P, C.c_float, C.c_float, _I32, _I64, _I32, _P], C.c_int),
     'lte_histogram': ([_P, _I64, C.c_float, C.c_float, _I32, _P, _P], C.c_int),
     'lte_plan_add_dft': ([_P, _I32], C.c_int),
+    'lte_dft_qam': ([_P, _P, _P, _I32, _I64, _P], C.c_int),
+    'lte_equalize_zf_awgn': ([_P, _P, _P, _P, C.c_int, _I64, _I32, C.POINTER(AwgnDesc), _P], C.c_int),
     'lte_dft_m': ([_P, _P, _P, _I32, _I32, _I64, _P], C.c_int),
     'lte_channel_tdl_workspace_bytes': ([_P, C.POINTER(ChannelDesc), _I32, _I32, _I32, _I64], C.c_int64),
     'lte_channel_tdl': ([_P, C.POINTER(ChannelDesc), _P, _P, _P, _P, _P, _I32, _I32, _I32, _I64, _P], C.c_int),

@@ -211,15 +211,27 @@ class LinkEngine:
     def dft_m(self, x, M, inverse=False, out=None):
         """Unitary M-point DFT (or IDFT) of every length-M row of x (any leading shape)."""
         rows = x.numel() // M
-        have = self.__dict__.setdefault('_dft_sizes', set())
-        if int(M) not in have:                 # chirp tables are plan state, built once per M (synchronous)
-            nat.check(nat.lib.lte_plan_add_dft(self._plan, int(M)), 'lte_plan_add_dft')
-            have.add(int(M))
+        self._need_dft(M)
         y = out if out is not None else torch.empty_like(x)
         nat.check(nat.lib.lte_dft_m(self._plan, _ptr(x), _ptr(y), int(M), 1 if inverse else 0, rows,
                                     self._stream()), 'lte_dft_m')
         self.launches += 1
         return y
+
+    def _need_dft(self, M):
+        have = self.__dict__.setdefault('_dft_sizes', set())
+        if int(M) not in have:                 # chirp tables are plan state, built once per M (synchronous)
+            nat.check(nat.lib.lte_plan_add_dft(self._plan, int(M)), 'lte_plan_add_dft')
+            have.add(int(M))
+
+    def dft_qam(self, idx, M):
+        """QAM map + unitary M-point DFT of every length-M row of symbol indices (SC-FDM precoder input), one kernel."""
+        self._need_dft(M)
+        rows = idx.numel() // M
+        out = self._empty(tuple(idx.shape), torch.complex64)
+        nat.check(nat.lib.lte_dft_qam(self._plan, _ptr(idx), _ptr(out), int(M), rows, self._stream()), 'lte_dft_qam')
+        self.launches += 1
+        return out
 
     # ------------------------------------------------------------------ stage 3 channel
     def channel(self, tx, chan, B, R, T=1, phases=None, out=None, power=None):
@@ -377,10 +389,15 @@ class LinkEngine:
         return Hp
 
     # ------------------------------------------------------------------ stage 5
-    def zf(self, Y, H, B, S, window=nat.WINDOW_FULL, out=None):
+    def zf(self, Y, H, B, S, window=nat.WINDOW_FULL, out=None, awgn=None):
+        """Zero forcing at the data bins; awgn: Y is noise free and the AWGN joins as the bins are read."""
         o = out if out is not None else self._empty((B, S * self.Nd), torch.complex64)
-        nat.check(nat.lib.lte_equalize_zf(self._plan, _ptr(Y), _ptr(H), _ptr(o), window, B, S, self._stream()),
-                  'lte_equalize_zf')
+        if awgn is not None:
+            nat.check(nat.lib.lte_equalize_zf_awgn(self._plan, _ptr(Y), _ptr(H), _ptr(o), window, B, S, C.byref(awgn),
+                                                   self._stream()), 'lte_equalize_zf_awgn')
+        else:
+            nat.check(nat.lib.lte_equalize_zf(self._plan, _ptr(Y), _ptr(H), _ptr(o), window, B, S, self._stream()),
+                      'lte_equalize_zf')
         self.launches += 1
         return o
 
@@ -496,7 +513,7 @@ class LinkEngine:
         return out
 
     def siso_ber(self, chan, snr_lin_rows, S, seed, stream_id0=0, idx=None, nbits=None, sc_fdm=False, noise_domain=1,
-                 papr_hist=None, papr_lo=0.0, papr_step=0.1):
+                 papr_hist=None, papr_lo=0.0, papr_step=0.1, fused=True):
         """One pass of the SISO chain with the zero-forcing equaliser Y / (H + 1e-6)
         (reference simulate_siso, core/ofdm_core.py:660-737) over B independent streams: what the GUIs
         run for num_rx = 1.  noise_domain 1: AWGN on the kept bins in the RX epilogue; 0: per time sample,
@@ -505,13 +522,15 @@ class LinkEngine:
         through the unitary Nd-point DFT before the grid (core/dft_precoding.py:67-93) and through its
         inverse after the equaliser (core/lte_receiver.py:319-333).
         papr_hist (int64 [bins], accumulated): histogram of the per-OFDM-symbol PAPR in dB of the useful
-        samples (core/ofdm_system.py:173-229), taken in the TX kernel's epilogue -- BER and PAPR in one pass."""
+        samples (core/ofdm_system.py:173-229), taken in the TX kernel's epilogue -- BER and PAPR in one pass.
+        fused (fading channels, noise_domain 1): fading + CP strip + FFT in one kernel and lazy AWGN in the estimator
+        and the equaliser instead of the staged TDL / FFT pair; the SC-FDM precoder takes the symbol indices directly."""
         B = snr_lin_rows.shape[0]
         if idx is None:
             idx = self.random_indices(B, S, seed, stream_id0)
         symbols = None
         if sc_fdm:
-            symbols = self.dft_m(self.qam_map(idx).view(B * S, self.Nd), self.Nd).view(B, S * self.Nd)
+            symbols = self.dft_qam(idx.view(B * S, self.Nd), self.Nd).view(B, S * self.Nd)   # QAM map inside the DFT's load
         if papr_hist is not None:
             _, _, tx = self.modulate_papr(S, idx=None if sc_fdm else idx, symbols=symbols, write_tx=True,
                                           hist=papr_hist, hist_lo=papr_lo, hist_step=papr_step, want_db=False)
@@ -519,6 +538,15 @@ class LinkEngine:
             tx, _, _ = self.modulate(S, idx=None if sc_fdm else idx, symbols=symbols, want_stats=False)
         if chan.num_taps > 0:
             ph = self.random_phases(B, chan.num_taps * nat.LTE_JAKES_TONES, seed, stream_id0)
+            if noise_domain == 1 and fused:
+                # fading + CP strip + FFT in one kernel, noise-free grid; the AWGN (the draws of the RX epilogue, from
+                # the power this kernel measures) joins in the estimator and in the equaliser
+                got = self.channel_rx_fft(tx, chan, B, 1, S, ph, nat.WINDOW_USEFUL)
+                if got is not None:
+                    Y, power = got
+                    awgn = self.awgn_desc(power, snr_lin_rows, seed, stream_id0)
+                    H = self.estimate(Y, B, S, nat.WINDOW_USEFUL, awgn=awgn)
+                    return self._siso_tail(self.zf(Y, H, B, S, nat.WINDOW_USEFUL, awgn=awgn), idx, B, S, nbits, sc_fdm)
             rx, power = self.channel(tx, chan, B, 1, phases=ph)
         else:
             _, power = self.channel(tx, chan, B, 1)
@@ -526,7 +554,9 @@ class LinkEngine:
         Y = self.rx_fft(rx, B, S, nat.WINDOW_USEFUL, power=power, snr_lin=snr_lin_rows, seed=seed,
                         row_id0=stream_id0, noise_domain=noise_domain)
         H = self.estimate(Y, B, S, nat.WINDOW_USEFUL)
-        data = self.zf(Y, H, B, S, nat.WINDOW_USEFUL)
+        return self._siso_tail(self.zf(Y, H, B, S, nat.WINDOW_USEFUL), idx, B, S, nbits, sc_fdm)
+
+    def _siso_tail(self, data, idx, B, S, nbits, sc_fdm):
         if sc_fdm:
             data = self.dft_m(data.view(B * S, self.Nd), self.Nd, inverse=True).view(B, S * self.Nd)
         errors, _ = self.demap_count(data, idx_tx=idx, nbits=nbits)

@@ -69,3 +69,25 @@ def test_run_ber_sweep_routes_scfdm_through_the_batched_chain():
     assert eng.launches - l0 < 40                       # one batch of 32 streams, not 32 per-call chains
     assert r['ber_mean'][0] > r['ber_mean'][-1]
     assert isinstance(eng, LinkEngine)
+
+
+def test_dft_qam_equals_the_separate_calls_and_the_fused_link_tracks_the_staged_one():
+    """lte_dft_qam = qam_map + dft_m (same arithmetic: bit-identical); the SISO pass through the fused channel + FFT
+    kernel with lazy AWGN in the estimator and the equaliser gives the staged pass's counts up to symbols on a slicer
+    boundary (the measured stream power differs in its last bits), for OFDM and SC-FDM."""
+    from config import LTEConfig
+    from lte_b200 import LinkEngine, chan_for
+    for bw, mod in ((10.0, '16-QAM'), (1.25, '64-QAM'), (5.0, 'QPSK')):
+        cfg = LTEConfig(bw, 15.0, mod)
+        eng = LinkEngine.from_config(cfg)
+        B, S = 6, 15
+        idx = eng.random_indices(B, S, 3, 0)
+        a = eng.dft_m(eng.qam_map(idx).view(B * S, eng.Nd), eng.Nd)
+        b = eng.dft_qam(idx.view(B * S, eng.Nd), eng.Nd)
+        assert torch.equal(torch.view_as_real(a), torch.view_as_real(b))
+        chan = chan_for('rayleigh_mp', cfg.fs, 'Pedestrian_A', 2.0, 3.0)
+        rows = torch.tensor([10 ** (s / 10) for s in (6.0, 16.0, 26.0)], dtype=torch.float32, device='cuda').repeat(B // 3).contiguous()
+        for sc in (True, False):
+            e_staged = eng.siso_ber(chan, rows, S, 9, stream_id0=4, idx=idx, sc_fdm=sc, fused=False)
+            e_fused = eng.siso_ber(chan, rows, S, 9, stream_id0=4, idx=idx, sc_fdm=sc, fused=True)
+            assert int(e_staged.sum()) > 0 and int((e_staged - e_fused).abs().sum()) <= 4 + int(e_staged.sum()) // 1000
