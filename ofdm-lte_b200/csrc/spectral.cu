@@ -295,6 +295,14 @@ __device__ __forceinline__ f2 lds32x2(unsigned a, unsigned b) {
                  : "=l"(r.v) : "r"(a), "r"(b));
     return r;
 }
+// The same with loads ptxas may not merge: two neighbouring bins' (re, im) would otherwise arrive as two 64-bit
+// loads and the (re, re) / (im, im) pairs be rebuilt with register moves wherever they are used.
+__device__ __forceinline__ f2 lds32x2v(unsigned a, unsigned b) {
+    f2 r;
+    asm volatile("{\n.reg .f32 lo, hi;\nld.volatile.shared.f32 lo, [%1];\nld.volatile.shared.f32 hi, [%2];\nmov.b64 %0, {lo, hi};\n}"
+                 : "=l"(r.v) : "r"(a), "r"(b));
+    return r;
+}
 // Horner steps acc <- u + w acc on the packed accumulator (hre, him), in place: two steps / one step.
 // One asm statement each, so the loop-carried accumulator keeps its register pair (no copies at the back edge).
 __device__ __forceinline__ void horner2(f2& hre, f2& him, f2 wre, f2 wim, f2 nwim, float2 u0, float2 u1) {
@@ -321,6 +329,22 @@ __device__ __forceinline__ void horner1(f2& hre, f2& him, f2 wre, f2 wim, f2 nwi
 
 #define SPEC_STAGES 3
 
+// Tap delays known at compile time.  The Horner sweep over the symbol tail has one segment per tap whose length is
+// the difference of two tap delays; with run-time delays that is a loop per segment (loop control on the uniform
+// datapath, a register rotation at every back edge, loads that cannot leave their trip).  For the delay sets of the
+// reference's ITU Pedestrian_A profile at the LTE sample rates (config.py:34-60 x config.py:104-107, rounded as
+// core/rayleighchannel.py:36 does) the kernel is instantiated with the delays as constants: the sweep is straight-line
+// code and every shared-memory offset is an immediate.  DK = 0 keeps the run-time loops for everything else.
+#define SPEC_NUM_DK 5
+__host__ __device__ constexpr int spec_ct_delay(int dk, int ts) {
+    return dk == 1 ? (ts == 1 ? 3 : ts == 2 ? 6 : ts == 3 ? 13 : 0)      // 30.72 MHz: 0 / 110 / 190 / 410 ns
+         : dk == 2 ? (ts == 1 ? 2 : ts == 2 ? 3 : ts == 3 ? 6 : 0)       // 15.36 MHz
+         : dk == 3 ? (ts == 1 ? 1 : ts == 2 ? 1 : ts == 3 ? 3 : 0)       //  7.68 MHz
+         : dk == 4 ? (ts == 1 ? 0 : ts == 2 ? 1 : ts == 3 ? 2 : 0)       //  3.84 MHz
+         : dk == 5 ? (ts == 1 ? 0 : ts == 2 ? 0 : ts == 3 ? 1 : 0)       //  1.92 MHz
+         : 0;
+}
+
 // Persistent, warp-specialised kernel.  A CTA walks whole streams (b = blockIdx.x, += gridDim.x) symbol by
 // symbol.  ONE producer warp feeds a 3-stage shared-memory ring with the bulk-copy (TMA) engine: per OFDM
 // symbol three contiguous runs -- the symbol's G window, the dmax + cp time samples around its cyclic prefix,
@@ -339,13 +363,14 @@ __device__ __forceinline__ void horner1(f2& hre, f2& him, f2 wre, f2 wim, f2 nwi
 // PLANAR flag = the sweep's compact layout: a data pair leaves as ONE 128-bit store of two consecutive complex
 // values into Y [B*R][S][2 ndp]; pilot pairs only on every slot's first symbol, into Yp [B*R][slots][2 npp];
 // nothing else is ever read downstream.  Otherwise Y is the windowed grid [B*R][S][nk].
-template <int NT, int R2, bool PLANAR, bool Z0>
+template <int NT, int R2, bool PLANAR, bool Z0, int DK>
 __global__ void __launch_bounds__(32 * (SPEC_MAX_WARPS + 1), 1)
 channel_spectral_kernel(const DevPlan P, const SpecParams C, const uint8_t* __restrict__ idx,
                         const float2* __restrict__ G, const float2* __restrict__ tail,
                         const float* __restrict__ coef_g, float* __restrict__ Y, float* __restrict__ Yp,
                         double* __restrict__ power, int k0, int nk, int S, int R, int B, int nwarps, int dmax2) {
     constexpr int NCF = NT * 6 * R2;                            // coefficient floats per symbol
+    constexpr bool CT = DK > 0;                                 // tap delays are compile-time constants
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int cp = P.cp, L = P.L;
@@ -385,7 +410,11 @@ channel_spectral_kernel(const DevPlan P, const SpecParams C, const uint8_t* __re
     // of symbol i: they only enter the stream power (core/channel.py:216-218 measures the whole faded stream) but
     // carry the inter-symbol leakage, so they are done in the time domain, y_r[i] = sum_t (c0 + c1 tau_i) x[i - d_t],
     // packed over sample pairs (i, i + 1) with the coefficients as scalar-broadcast operands like in the bin loop.
-    // Its work per symbol is a little under that of a bin warp, so it never is the one the others wait for.
+    // A lane owns ONE antenna (lane % R2), keeps that antenna's coefficients in registers for the symbol and walks
+    // the sample pairs lane / R2 + k (32 / R2): short rounds of 26 packed operations without idle lanes, three of
+    // them in flight.  This single warp is what the 19 bin warps end up waiting for when its rounds are long and
+    // serial (32 sample pairs x all antennas per lane, the third trip with 8 live lanes: 0.12 ms of the kernel's
+    // 0.90 ms at the headline shape, measured by leaving the CP samples out; 0.06 ms in this form).
     if (w == nwarps) {
         auto produce = [&](unsigned f, unsigned st) {
             const unsigned dst = stage0 + st * stage_bytes, bar = bar_full + 8u * st;
@@ -412,9 +441,12 @@ channel_spectral_kernel(const DevPlan P, const SpecParams C, const uint8_t* __re
         };
 #pragma unroll
         for (int i = 0; i < SPEC_STAGES - 1; ++i) produce_next();
-        f2 pwc[R2];
-#pragma unroll
-        for (int r = 0; r < R2; ++r) pwc[r] = pk(0.f, 0.f);
+        constexpr int PPR = 32 / R2;                            // sample pairs per round
+        constexpr int CPU = 3;                                  // rounds in flight
+        const int ra = lane % R2, pl = lane / R2;               // the lane's antenna and its place in a round
+        const int npair = pl < PPR ? cp / 2 : 0;                // 32 % R2 lanes stay idle (R2 = 6)
+        const float tau0 = -0.5f * (float)(L - 1);
+        f2 pwc = pk(0.f, 0.f);
         unsigned stage = 0, phase = 0;
         for (unsigned b = blockIdx.x; b < (unsigned)B; b += gridDim.x) {
             for (unsigned s = 0; s < (unsigned)S; ++s) {
@@ -422,50 +454,80 @@ channel_spectral_kernel(const DevPlan P, const SpecParams C, const uint8_t* __re
                 __syncwarp();
                 mbar_wait(bar_full + 8u * stage, phase);
                 const unsigned sb = stage0 + stage * stage_bytes;
-                for (int i0 = 2 * lane; i0 < cp; i0 += 64) {
-                    const float tf = (float)i0 - 0.5f * (float)(L - 1);
-                    const f2 tau = pk(tf, tf + 1.f);
-                    f2 yre[R2], yim[R2];
+                if (s == 0) {
+                    // nothing precedes the stream: the dmax2 samples in front of its first symbol (the previous
+                    // stream's last ones) count as zeros.  Only this warp reads them.
+                    for (int i = lane; i < dmax2; i += 32)
+                        asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(sb + gbytes + 8u * (unsigned)i), "f"(0.f) : "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the stage is refilled by the bulk-copy engine
+                    __syncwarp();
+                }
+                // the lane's antenna: (c0, c1) per tap, once per symbol
+                float2 k0[NT], k1[NT];
 #pragma unroll
-                    for (int r = 0; r < R2; ++r) { yre[r] = pk(0.f, 0.f); yim[r] = pk(0.f, 0.f); }
+                for (int ts = 0; ts < NT; ++ts) {
+                    const float4 ac = lds128(sb + co + 16u * (unsigned)ra + (unsigned)(ts * R2 * 16));   // (a.re, a.im, c1.re, c1.im)
+                    k0[ts] = lds64(sb + co + C0OFF + 8u * (unsigned)ra + (unsigned)(ts * R2 * 8));
+                    k1[ts] = make_float2(ac.z, ac.w);
+                }
+                // a round past the end works on the lane's first pair and is left out of the sum
+                for (int pp = pl; pp < npair; pp += CPU * PPR) {
+                    unsigned xa[CPU];
+                    f2 tau[CPU], yre[CPU], yim[CPU];
+                    bool ok[CPU];
+#pragma unroll
+                    for (int u = 0; u < CPU; ++u) {
+                        ok[u] = pp + u * PPR < npair;
+                        const int i0 = 2 * (ok[u] ? pp + u * PPR : pl);
+                        const float tf = (float)i0 + tau0;
+                        tau[u] = pk(tf, tf + 1.f);
+                        xa[u] = sb + xo + 8u * (unsigned)i0;
+                    }
 #pragma unroll
                     for (int ts = 0; ts < NT; ++ts) {
-                        const int d = C.delay[ts];
-                        const unsigned xa = sb + xo + 8u * (unsigned)(i0 + dmax2 - d) - 8u * (unsigned)dmax2;
-                        f2 xr = lds32x2(xa, xa + 8u), xi = lds32x2(xa + 4u, xa + 12u);
-                        if (s == 0 && i0 < d) {                                     // nothing precedes the stream
-                            const f2 m = pk(0.f, i0 + 1 < d ? 0.f : 1.f);
-                            xr = mul2(xr, m);
-                            xi = mul2(xi, m);
-                        }
-                        const unsigned ct = sb + co + (unsigned)(ts * R2 * 16);
+                        const int d = CT ? spec_ct_delay(DK, ts) : C.delay[ts];
 #pragma unroll
-                        for (int r = 0; r < R2; ++r) {
-                            const float4 ac = lds128(ct + 16u * r);                 // (a.re, a.im, c1.re, c1.im)
-                            const float2 c0 = lds64(sb + co + C0OFF + (unsigned)(ts * R2 * 8) + 8u * r);
-                            const f2 hr = fma2(tau, bc(ac.z), bc(c0.x)), hi = fma2(tau, bc(ac.w), bc(c0.y));
-                            fma2_acc(yre[r], hr, xr); fma2_acc(yre[r], neg2(hi), xi);
-                            fma2_acc(yim[r], hr, xi); fma2_acc(yim[r], hi, xr);
+                        for (int u = 0; u < CPU; ++u) {
+                            const unsigned x0 = xa[u] - 8u * (unsigned)d;
+                            const f2 xr = lds32x2v(x0, x0 + 8u), xi = lds32x2v(x0 + 4u, x0 + 12u);
+                            const f2 hr = fma2(tau[u], bc(k1[ts].x), bc(k0[ts].x)), hi = fma2(tau[u], bc(k1[ts].y), bc(k0[ts].y));
+                            if (ts == 0) {
+                                yre[u] = mul2(hr, xr);
+                                yim[u] = mul2(hr, xi);
+                            } else {
+                                fma2_acc(yre[u], hr, xr);
+                                fma2_acc(yim[u], hr, xi);
+                            }
+                            fma2_acc(yre[u], neg2(hi), xi);
+                            fma2_acc(yim[u], hi, xr);
                         }
                     }
 #pragma unroll
-                    for (int r = 0; r < R2; ++r) {
-                        fma2_acc(pwc[r], yre[r], yre[r]);
-                        fma2_acc(pwc[r], yim[r], yim[r]);
+                    for (int u = 0; u < CPU; ++u) {
+                        const f2 m = pk(ok[u] ? 1.f : 0.f, ok[u] ? 1.f : 0.f);
+                        yre[u] = mul2(yre[u], m);
+                        yim[u] = mul2(yim[u], m);
+                        fma2_acc(pwc, yre[u], yre[u]);
+                        fma2_acc(pwc, yim[u], yim[u]);
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_empty + 8u * stage);
                 if (++stage == SPEC_STAGES) { stage = 0; phase ^= 1u; }
             }
+            // the stream's CP power per antenna: sum over the lanes of the same antenna (ra + k R2)
+            float a, c;
+            upk(pwc, a, c);
+            const float mine = a + c;
+            float t = 0.f;
 #pragma unroll
-            for (int r = 0; r < R2; ++r) {
-                float a, c;
-                upk(pwc[r], a, c);
-                const float t = warp_sum(a + c);
-                if (lane == 0 && r < R) atomicAdd(&power[(size_t)b * R + r], (double)t);
-                pwc[r] = pk(0.f, 0.f);
+            for (int k = 0; k < (32 + R2 - 1) / R2; ++k) {
+                const int src = ra + k * R2;
+                const float o = __shfl_sync(0xffffffffu, mine, src & 31);
+                if (src < 32) t += o;
             }
+            if (lane < R) atomicAdd(&power[(size_t)b * R + lane], (double)t);
+            pwc = pk(0.f, 0.f);
         }
         return;
     }
@@ -493,7 +555,7 @@ channel_spectral_kernel(const DevPlan P, const SpecParams C, const uint8_t* __re
         nwim = pk(-a.y, -c.y);
 #pragma unroll
         for (int ts = 0; ts < NT; ++ts) {
-            const int d = C.delay[ts];
+            const int d = CT ? spec_ct_delay(DK, ts) : C.delay[ts];
             const float2 ea = okA ? __ldg(&P.twiddle[(binA * d) & (P.N - 1)]) : z;
             const float2 ec = okB ? __ldg(&P.twiddle[(binB * d) & (P.N - 1)]) : z;
             ere[ts] = pk(ea.x, ec.x);
@@ -513,6 +575,7 @@ channel_spectral_kernel(const DevPlan P, const SpecParams C, const uint8_t* __re
 
     unsigned stage = 0, phase = 0;
     unsigned b = blockIdx.x, s = 0;
+    unsigned sl = 0, slot = 0;                                  // s % LTE_SLOT_SYMBOLS, s / LTE_SLOT_SYMBOLS
     unsigned ibA = 0, ibB = 0;                                  // index bytes of the NEXT symbol to compute
     if (b < (unsigned)B) {
         const unsigned f = b * (unsigned)S;
@@ -536,7 +599,7 @@ channel_spectral_kernel(const DevPlan P, const SpecParams C, const uint8_t* __re
         }
         mbar_wait(bar_full + 8u * stage, phase);                // the symbol's bytes have landed
         const unsigned sb = stage0 + stage * stage_bytes;
-        const f2 gre = lds32x2(sb + gA, sb + gB), gim = lds32x2(sb + gA + 4u, sb + gB + 4u);
+        const f2 gre = lds32x2v(sb + gA, sb + gB), gim = lds32x2v(sb + gA + 4u, sb + gB + 4u);
 
         f2 hre = pk(0.f, 0.f), him = pk(0.f, 0.f);              // Horner accumulator
         f2 yre[R2], yim[R2];
@@ -544,7 +607,23 @@ channel_spectral_kernel(const DevPlan P, const SpecParams C, const uint8_t* __re
         int pstep = 0;
 #pragma unroll
         for (int ts = 0; ts < NT; ++ts) {
-            if (!(Z0 && ts == 0)) {
+            if (CT) {
+                // Horner steps up to this tap's delay as straight-line code: acc <- u + w acc
+                const int dcur = spec_ct_delay(DK, ts);
+#pragma unroll
+                for (int q = pstep; q < dcur; ++q) {
+                    const float2 u = lds64(up - 8u * (unsigned)q);
+                    if (q == 0) {
+                        hre = bc(u.x);
+                        him = bc(u.y);
+                    } else {
+                        const f2 tr = fma2(nwim, him, fma2(wre, hre, bc(u.x)));
+                        him = fma2(wim, hre, fma2(wre, him, bc(u.y)));
+                        hre = tr;
+                    }
+                }
+                pstep = dcur;
+            } else if (!(Z0 && ts == 0)) {
                 // Horner steps up to this tap's delay, two per trip: acc <- u + w acc
                 int n = C.delay[ts] - pstep;
                 pstep = C.delay[ts];
@@ -594,20 +673,23 @@ channel_spectral_kernel(const DevPlan P, const SpecParams C, const uint8_t* __re
         if (live) {
             const unsigned row0 = b * (unsigned)(R * S) + s;        // row of antenna 0; antenna r is S rows further
             if (PLANAR) {
-                const bool head = ispil && s % LTE_SLOT_SYMBOLS == 0;
-                const unsigned long long yb = gaddr((unsigned long long)Y, row0, (unsigned)P.ndp * 16u) + 16u * (unsigned)pi;
-                const unsigned long long pb = gaddr((unsigned long long)Yp, b * (unsigned)(R * nslot) + s / LTE_SLOT_SYMBOLS,
-                                                    (unsigned)P.npp * 16u) + 16u * (unsigned)(pi - P.ndp);
+                // one destination per lane: a data pair goes to its place in row (b, antenna 0, s) of Y, a pilot pair --
+                // on a slot's first symbol only -- to row (b, antenna 0, slot) of Yp; antenna r is `rstride` further
+                const bool head = ispil && sl == 0;
+                const bool dost = isdat || head;
+                const unsigned long long dst =
+                    isdat ? gaddr((unsigned long long)Y, row0 * (unsigned)P.ndp + (unsigned)pi, 16u)
+                          : gaddr((unsigned long long)Yp, (b * (unsigned)(R * nslot) + slot) * (unsigned)P.npp + (unsigned)(pi - P.ndp), 16u);
+                const unsigned rstride = isdat ? (unsigned)S * (unsigned)P.ndp : (unsigned)nslot * (unsigned)P.npp;
 #pragma unroll
                 for (int r = 0; r < R2; ++r) {
                     fma2_acc(pw[r], yre[r], yre[r]);
                     fma2_acc(pw[r], yim[r], yim[r]);
-                    if (r < R) {
+                    if ((CT || r < R) && dost) {
                         float a, c, d, e;
                         upk(yre[r], a, c);
                         upk(yim[r], d, e);
-                        if (isdat) stg128(gaddr(yb, (unsigned)(r * S) * (unsigned)P.ndp, 16u), a, d, c, e);
-                        else if (head) stg128(gaddr(pb, (unsigned)(r * nslot) * (unsigned)P.npp, 16u), a, d, c, e);
+                        stg128(gaddr(dst, (unsigned)r * rstride, 16u), a, d, c, e);
                     }
                 }
             } else {
@@ -640,6 +722,8 @@ channel_spectral_kernel(const DevPlan P, const SpecParams C, const uint8_t* __re
         }
         b = nb;
         s = ns;
+        if (++sl == LTE_SLOT_SYMBOLS) { sl = 0; ++slot; }
+        if (ns == 0) { sl = 0; slot = 0; }
     }
 }
 
@@ -767,13 +851,32 @@ extern "C" int lte_channel_spectral(const lte_plan* p, const lte_channel_desc* c
         LTE_CHECK_CUDA(cudaGetLastError());
         return LTE_OK;
     };
+    // compile-time delay sets (spec_ct_delay): four taps, first one at delay 0, compact output, two or four antennas
+    int dk = 0;
+    if (ch->num_taps == 4 && z0 && Ypilot && R2 <= 4 && R == R2)
+        for (int k = 1; k <= SPEC_NUM_DK && !dk; ++k) {
+            bool same = true;
+            for (int ts = 0; ts < 4; ++ts) same = same && C.delay[ts] == spec_ct_delay(k, ts);
+            if (same) dk = k;
+        }
 #define LAUNCH_SPEC_RP(NT, RP)                                                                                   \
-    (Ypilot ? (z0 ? launch(channel_spectral_kernel<NT, RP, true, true>) : launch(channel_spectral_kernel<NT, RP, true, false>)) \
-            : (z0 ? launch(channel_spectral_kernel<NT, RP, false, true>) : launch(channel_spectral_kernel<NT, RP, false, false>)))
+    (Ypilot ? (z0 ? launch(channel_spectral_kernel<NT, RP, true, true, 0>) : launch(channel_spectral_kernel<NT, RP, true, false, 0>)) \
+            : (z0 ? launch(channel_spectral_kernel<NT, RP, false, true, 0>) : launch(channel_spectral_kernel<NT, RP, false, false, 0>)))
 #define LAUNCH_SPEC(NT)                                                     \
     case NT:                                                                \
         return R2 == 2 ? LAUNCH_SPEC_RP(NT, 2) : R2 == 4 ? LAUNCH_SPEC_RP(NT, 4) \
              : R2 == 6 ? LAUNCH_SPEC_RP(NT, 6) : LAUNCH_SPEC_RP(NT, 8);
+#define LAUNCH_SPEC_DK(K)                                                   \
+    case K:                                                                 \
+        return R2 == 2 ? launch(channel_spectral_kernel<4, 2, true, true, K>) : launch(channel_spectral_kernel<4, 4, true, true, K>);
+    switch (dk) {
+#ifdef SPEC_DEV
+        case 1: return launch(channel_spectral_kernel<4, 4, true, true, 1>);
+#else
+        LAUNCH_SPEC_DK(1) LAUNCH_SPEC_DK(2) LAUNCH_SPEC_DK(3) LAUNCH_SPEC_DK(4) LAUNCH_SPEC_DK(5)
+#endif
+        default: break;
+    }
     switch (ch->num_taps) {
 #ifdef SPEC_DEV                     // development builds: the headline shape only (seconds instead of a minute)
         case 4: return LAUNCH_SPEC_RP(4, 4);
@@ -783,6 +886,7 @@ extern "C" int lte_channel_spectral(const lte_plan* p, const lte_channel_desc* c
 #endif
         default: return LTE_ERR_INVALID_ARG;
     }
+#undef LAUNCH_SPEC_DK
 #undef LAUNCH_SPEC
 #undef LAUNCH_SPEC_RP
 }
