@@ -76,10 +76,10 @@ def stage_bytes(N=2048, cp=144, Nd=999, Np=200, Nc=1200, b=6, R=R_ANT, S=S_SUBFR
 
 def spectral_flops(npairs=600, cp=144, R=R_ANT, S=S_SUBFRAME, NT=4, dmax=13):
     """fp32 flops per subframe of channel_spectral_kernel (csrc/spectral.cu): packed FFMA2 = 4 flops, FMUL2 = 2.
-    Per bin pair and symbol: Horner 4 dmax FFMA2; per tap with a delay V/W = 6 FFMA2 + 4 FMUL2; combine
+    Per bin pair and symbol: Horner 4 (dmax - 1) FFMA2 (the first step is a copy); per tap with a delay V/W = 6 FFMA2 + 4 FMUL2; combine
     8 FFMA2 per (tap, antenna) (first tap: 6 + 2 FMUL2); power 2 FFMA2 per antenna.  CP sample pairs:
     6 FFMA2 per (tap, antenna) + 2 for the power."""
-    per_pair = 4 * (4 * dmax) + (NT - 1) * (6 * 4 + 4 * 2) + R * ((NT - 1) * 8 * 4 + 6 * 4 + 2 * 2) + R * 2 * 4
+    per_pair = 4 * (4 * max(dmax - 1, 0)) + (NT - 1) * (6 * 4 + 4 * 2) + R * ((NT - 1) * 8 * 4 + 6 * 4 + 2 * 2) + R * 2 * 4
     per_cp = (cp // 2) * (NT * R * 6 * 4 + R * 2 * 4)
     return S * (npairs * per_pair + per_cp)
 
