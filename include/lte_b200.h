@@ -416,6 +416,17 @@ int lte_random_channel(lte_c32* h, int64_t B, int32_t R, int32_t T, uint64_t see
 int lte_bf_weights(const lte_c32* h, const lte_c32* codebook_host, int32_t ncb, int32_t mode, lte_c32* W,
                    lte_c32* heff, int32_t* pmi, float* gain_db, int64_t B, int32_t R, int32_t T,
                    void* stream);
+/* lte_rank_feedback replaces RankAdaptation.get_feedback with its default methods -- RI from the eigenvalues of
+ * H^H H with the SNR gates (core/rank_adaptation.py:41-130), PMI by the capacity metric over the rank's
+ * codebook, first maximum wins (:148-211) -- for n channel matrices at once, in fp64 like the reference:
+ * H [n][R][T] (R <= 8, T <= 4); snr_db [n] (device); codebook [max_rank][ncb_stride][T][4] (device; entry
+ * (rank - 1, pmi) holds W [T][rank] in its first `rank` columns); ncb_host [max_rank] codebook sizes per rank
+ * (host); ri / pmi [n] int32 (device).  The spatial-multiplexing sweep uses it for the reference's
+ * H_initial feedback of simulate_spatial_multiplexing (core/ofdm_core.py:2573-2583), one matrix per
+ * (SNR point, feedback block), in one launch. */
+int lte_rank_feedback(const lte_c32* H, const double* snr_db, const lte_c32* codebook, int32_t ncb_stride,
+                      const int32_t* ncb_host, double rank_threshold, int32_t max_rank, int32_t* ri, int32_t* pmi,
+                      int64_t n, int32_t R, int32_t T, void* stream);
 int lte_bf_link(const lte_plan*, const uint8_t* idx, const lte_c32* h, const lte_c32* W,
                 const lte_c32* heff, const float* noise_std, const float* z, uint64_t seed,
                 uint64_t row_id0, lte_c32* out, unsigned long long* errors, int64_t nbits, int64_t B,

@@ -122,6 +122,162 @@ extern "C" int lte_bf_weights(const lte_c32* h, const lte_c32* codebook_host, in
     return LTE_OK;
 }
 
+// ------------------------------------------------------------------ rank / precoder feedback
+// RankAdaptation.get_feedback with its default methods (core/rank_adaptation.py:41-130 `eigenvalue`,
+// :148-211 `capacity`) for n channel matrices at once, one thread per matrix, fp64 like the reference:
+//   RI  : eigenvalues of H^H H (cyclic Jacobi on the T x T Hermitian matrix), count those above
+//         rank_threshold x the largest, cap at max_rank, then the SNR gates (< 5 dB: 1, < 10 dB: <= 2)
+//   PMI : argmax over the rank's codebook of log2 det(I + snr / ri  H_eff H_eff^H), H_eff = H W, first
+//         maximum wins; the determinant is taken of the ri x ri matrix I + snr / ri  H_eff^H H_eff
+//         (Sylvester's identity: same value, at most 4 x 4) by Cholesky factorisation.
+#define RF_MAX_T 4
+#define RF_MAX_RANK 4
+struct c64 { double x, y; };
+__device__ __forceinline__ c64 c64_mulc(c64 a, c64 b) { return {a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y}; }   // a conj(b)
+
+__global__ void __launch_bounds__(64)
+rank_feedback_kernel(const float2* __restrict__ H, const double* __restrict__ snr_db, const float2* __restrict__ codebook,
+                     int ncb_stride, int4 ncb, double rank_threshold, int max_rank, int* __restrict__ ri_out,
+                     int* __restrict__ pmi_out, long long n, int R, int T) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    c64 h[BF_MAX_R][RF_MAX_T];
+    for (int r = 0; r < R; ++r)
+        for (int t = 0; t < T; ++t) {
+            const float2 v = H[((size_t)i * R + r) * T + t];
+            h[r][t] = {(double)v.x, (double)v.y};
+        }
+    // ---- Gram matrix A = H^H H and its eigenvalues
+    c64 A[RF_MAX_T][RF_MAX_T];
+    for (int a = 0; a < T; ++a)
+        for (int b = 0; b < T; ++b) {
+            c64 acc = {0.0, 0.0};
+            for (int r = 0; r < R; ++r) {                       // conj(h[r][a]) h[r][b]
+                const c64 p = c64_mulc(h[r][b], h[r][a]);
+                acc.x += p.x; acc.y += p.y;
+            }
+            A[a][b] = acc;
+        }
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        double off = 0.0, dia = 0.0;
+        for (int a = 0; a < T; ++a)
+            for (int b = 0; b < T; ++b) {
+                const double m = A[a][b].x * A[a][b].x + A[a][b].y * A[a][b].y;
+                if (a == b) dia += m; else off += m;
+            }
+        if (off <= 1e-32 * dia) break;
+        for (int p = 0; p < T - 1; ++p)
+            for (int q = p + 1; q < T; ++q) {
+                const double g = sqrt(A[p][q].x * A[p][q].x + A[p][q].y * A[p][q].y);
+                if (g == 0.0) continue;
+                // unitary rotation in the (p, q) plane that annihilates A[p][q] = g e^{j phi}
+                const c64 ph = {A[p][q].x / g, A[p][q].y / g};
+                const double tau = (A[q][q].x - A[p][p].x) / (2.0 * g);
+                const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                const double c = 1.0 / sqrt(1.0 + tt * tt), sn = tt * c;
+                // columns: A <- A J, J = [[c, s e^{j phi}], [-s e^{-j phi}, c]] on (p, q)
+                for (int k = 0; k < T; ++k) {
+                    const c64 akp = A[k][p], akq = A[k][q];
+                    // akq e^{-j phi}
+                    const c64 u = {akq.x * ph.x + akq.y * ph.y, akq.y * ph.x - akq.x * ph.y};
+                    // akp e^{j phi}
+                    const c64 v = {akp.x * ph.x - akp.y * ph.y, akp.y * ph.x + akp.x * ph.y};
+                    A[k][p] = {c * akp.x - sn * u.x, c * akp.y - sn * u.y};
+                    A[k][q] = {sn * v.x + c * akq.x, sn * v.y + c * akq.y};
+                }
+                // rows: A <- J^H A
+                for (int k = 0; k < T; ++k) {
+                    const c64 apk = A[p][k], aqk = A[q][k];
+                    // aqk e^{j phi}
+                    const c64 u = {aqk.x * ph.x - aqk.y * ph.y, aqk.y * ph.x + aqk.x * ph.y};
+                    // apk e^{-j phi}
+                    const c64 v = {apk.x * ph.x + apk.y * ph.y, apk.y * ph.x - apk.x * ph.y};
+                    A[p][k] = {c * apk.x - sn * u.x, c * apk.y - sn * u.y};
+                    A[q][k] = {sn * v.x + c * aqk.x, sn * v.y + c * aqk.y};
+                }
+            }
+    }
+    double lmax = A[0][0].x;
+    for (int a = 1; a < T; ++a) lmax = fmax(lmax, A[a][a].x);
+    const double sdb = snr_db[i];
+    int ri = 1;
+    if (lmax >= 1e-10) {
+        int sig = 0;
+        for (int a = 0; a < T; ++a) sig += (A[a][a].x / lmax > rank_threshold) ? 1 : 0;
+        ri = sig < max_rank ? sig : max_rank;
+        if (sdb < 5.0) ri = 1;
+        else if (sdb < 10.0) ri = ri < 2 ? ri : 2;
+        if (ri < 1) ri = 1;
+    }
+    // ---- precoder of that rank with the largest capacity metric
+    const double scale = pow(10.0, sdb / 10.0) / (double)ri;
+    const int nc = ri == 1 ? ncb.x : ri == 2 ? ncb.y : ri == 3 ? ncb.z : ncb.w;
+    const float2* cbr = codebook + (size_t)(ri - 1) * ncb_stride * T * RF_MAX_RANK;
+    int best = 0;
+    double best_v = -INFINITY;
+    for (int pmi = 0; pmi < nc; ++pmi) {
+        const float2* W = cbr + (size_t)pmi * T * RF_MAX_RANK;  // [T][RF_MAX_RANK], columns < ri used
+        c64 he[BF_MAX_R][RF_MAX_RANK];
+        for (int r = 0; r < R; ++r)
+            for (int l = 0; l < ri; ++l) {
+                c64 acc = {0.0, 0.0};
+                for (int t = 0; t < T; ++t) {
+                    const float2 w = W[t * RF_MAX_RANK + l];
+                    acc.x += h[r][t].x * (double)w.x - h[r][t].y * (double)w.y;
+                    acc.y += h[r][t].x * (double)w.y + h[r][t].y * (double)w.x;
+                }
+                he[r][l] = acc;
+            }
+        c64 M[RF_MAX_RANK][RF_MAX_RANK];                        // I + scale H_eff^H H_eff
+        for (int a = 0; a < ri; ++a)
+            for (int b = 0; b < ri; ++b) {
+                c64 acc = {a == b ? 1.0 : 0.0, 0.0};
+                for (int r = 0; r < R; ++r) {
+                    const c64 p = c64_mulc(he[r][b], he[r][a]);
+                    acc.x += scale * p.x; acc.y += scale * p.y;
+                }
+                M[a][b] = acc;
+            }
+        double logdet = 0.0;                                    // Cholesky: det = prod d_k^2
+        for (int k = 0; k < ri; ++k) {
+            double d = M[k][k].x;
+            for (int m = 0; m < k; ++m) d -= M[k][m].x * M[k][m].x + M[k][m].y * M[k][m].y;
+            logdet += log2(d);
+            const double rd = 1.0 / sqrt(d);
+            for (int a = k + 1; a < ri; ++a) {
+                c64 v = M[a][k];
+                for (int m = 0; m < k; ++m) {                   // M[a][m] conj(M[k][m])
+                    const c64 p = c64_mulc(M[a][m], M[k][m]);
+                    v.x -= p.x; v.y -= p.y;
+                }
+                M[a][k] = {v.x * rd, v.y * rd};
+            }
+        }
+        if (logdet > best_v) { best_v = logdet; best = pmi; }
+    }
+    ri_out[i] = ri;
+    pmi_out[i] = best;
+}
+
+extern "C" int lte_rank_feedback(const lte_c32* H, const double* snr_db, const lte_c32* codebook, int32_t ncb_stride,
+                                 const int32_t* ncb_host, double rank_threshold, int32_t max_rank, int32_t* ri,
+                                 int32_t* pmi, int64_t n, int32_t R, int32_t T, void* stream) {
+    if (!H || !snr_db || !codebook || !ncb_host || !ri || !pmi || n < 0) return LTE_ERR_INVALID_ARG;
+    if (R < 1 || R > BF_MAX_R || T < 1 || T > RF_MAX_T || max_rank < 1 || max_rank > RF_MAX_RANK || max_rank > T)
+        return LTE_ERR_INVALID_ARG;
+    int nc[RF_MAX_RANK] = {0, 0, 0, 0};
+    for (int k = 0; k < max_rank; ++k) {
+        if (ncb_host[k] < 1 || ncb_host[k] > ncb_stride) return LTE_ERR_INVALID_ARG;
+        nc[k] = ncb_host[k];
+    }
+    if (n == 0) return LTE_OK;
+    rank_feedback_kernel<<<(unsigned)((n + 63) / 64), 64, 0, (cudaStream_t)stream>>>(
+        (const float2*)H, snr_db, (const float2*)codebook, ncb_stride, make_int4(nc[0], nc[1], nc[2], nc[3]), rank_threshold,
+        max_rank, ri, pmi, n, R, T);
+    LTE_CHECK_CUDA(cudaGetLastError());
+    return LTE_OK;
+}
+
 // ------------------------------------------------------------------ the link
 // CTA = (stream b, OFDM symbol s); thread = data position d (strided).  Per data symbol
 //   x_t = w_t s            (BeamformingPrecoder.apply_precoding, W @ s)

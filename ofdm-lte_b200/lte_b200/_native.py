@@ -114,6 +114,7 @@ _SIGS = {
     'lte_gather_f32': ([_P, _I64, _P, _I64, _P, _I64, _P], C.c_int),
     'lte_random_channel': ([_P, _I64, _I32, _I32, _U64, _U64, _P], C.c_int),
     'lte_bf_weights': ([_P, _P, _I32, _I32, _P, _P, _P, _P, _I64, _I32, _I32, _P], C.c_int),
+    'lte_rank_feedback': ([_P, _P, _P, _I32, _P, C.c_double, _I32, _P, _P, _I64, _I32, _I32, _P], C.c_int),
     'lte_bf_link': ([_P, _P, _P, _P, _P, _P, _P, _U64, _U64, _P, _P, _I64, _I64, _I32, _I32, _I32, _P], C.c_int),
 }
 for _name, (_args, _res) in _SIGS.items():

@@ -785,6 +785,34 @@ class LinkEngine:
         self.launches += 1
         return W, heff, pmi, gain
 
+    def rank_codebook(self, num_tx, max_rank):
+        """The TM4 codebooks of ranks 1..max_rank as the device table lte_rank_feedback reads:
+        (complex64 [max_rank, ncb_stride, T, 4] with W [T, rank] in the first `rank` columns, int32 sizes per rank)."""
+        from core.codebook_lte import LTECodebook
+        books = [LTECodebook(num_tx, transmission_mode='TM4', rank=r) for r in range(1, max_rank + 1)]
+        sizes = np.array([b.codebook_size for b in books], dtype=np.int32)
+        tab = np.zeros((max_rank, int(sizes.max()), num_tx, 4), dtype=np.complex64)
+        for r, b in enumerate(books):
+            for i in range(b.codebook_size):
+                tab[r, i, :, :r + 1] = np.asarray(b.get_precoder(i)).reshape(num_tx, r + 1)
+        return torch.from_numpy(tab).to(self.device), sizes
+
+    def rank_feedback(self, H, snr_db, codebook, sizes, rank_threshold=0.15, max_rank=None):
+        """RankAdaptation.get_feedback (eigenvalue RI, capacity PMI) for H complex64 [n, R, T] and snr_db float64 [n]
+        (device) against `codebook, sizes` of rank_codebook() -> (ri int32 [n], pmi int32 [n])."""
+        n, R, T = H.shape
+        max_rank = int(max_rank) if max_rank is not None else min(R, T, 4)
+        ri = self._empty((n,), torch.int32)
+        pmi = self._empty((n,), torch.int32)
+        sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+        assert codebook.shape[0] >= max_rank and codebook.shape[2] == T and codebook.shape[3] == 4
+        assert snr_db.dtype == torch.float64 and snr_db.numel() == n and H.dtype == torch.complex64
+        nat.check(nat.lib.lte_rank_feedback(_ptr(H.contiguous()), _ptr(snr_db), _ptr(codebook), codebook.shape[1],
+                                            sizes.ctypes.data_as(C.c_void_p), float(rank_threshold), max_rank, _ptr(ri),
+                                            _ptr(pmi), n, R, T, self._stream()), 'lte_rank_feedback')
+        self.launches += 1
+        return ri, pmi
+
     def bf_link(self, idx, h, W, heff, noise_std, S, nbits=None, z=None, seed=0, row_id0=0, want_symbols=False,
                 errors=None, count=True):
         """idx uint8 [B, S*Nd]; h [B, R, T]; W [B, T]; heff [B, R]; noise_std float32 [B]; z optional float32

@@ -329,9 +329,12 @@ def sm_sweep(config, snr_db, n_trials, num_tx=4, num_rx=4, rank=4, detector='MMS
     point, one block) and ids are SNR-major: id = snr_index * n_trials + trial.
     rank 1..4: `precoder(rank) -> W [T, rank]` (codebook entry 0, the reference's fixed-rank branch).
     rank 'adaptive': the reference draws an H_initial unrelated to the channel and feeds it to
-    RankAdaptation; here one H_initial is drawn on the host per (SNR point, block of `feedback_block`
-    consecutive global trials) -- keyed by (seed, snr_index, block), so sharding cannot change it -- and
-    `feedback(H, snr_db) -> (ri, pmi, W)` (core.rank_adaptation's rule) picks the precoder of the block.
+    RankAdaptation (core/ofdm_core.py:2573-2583); here one H_initial is drawn per (SNR point, block of
+    `feedback_block` consecutive global trials) -- keyed by (seed, snr_index, block), so sharding cannot
+    change it.  By default (feedback=None) the draws (lte_random_channel) and the reference's rule -- RI from
+    the eigenvalues of H^H H with the SNR gates, PMI by the capacity metric (lte_rank_feedback) -- run on the
+    device, all (SNR point, block) units of a batch in one launch each; a callable
+    `feedback(H, snr_db) -> (ri, pmi, W)` keeps the rule (and NumPy draws) on the host.
     Adds 'rank_hist' [n_snr, 4] (streams per rank) to run_sweep's result."""
     import numpy as np
 
@@ -343,11 +346,26 @@ def sm_sweep(config, snr_db, n_trials, num_tx=4, num_rx=4, rank=4, detector='MMS
     n_snr = len(snr_db)
     S, R = symbols_per_stream, num_rx
     adaptive = rank == 'adaptive'
-    if adaptive and feedback is None:
-        raise ValueError("rank='adaptive' needs feedback(H, snr_db) -> (ri, pmi, W)")
     if not adaptive and precoder is None:
         raise ValueError("a fixed rank needs precoder(rank) -> W")
     rank_hist = torch.zeros((n_snr, 4), dtype=torch.int64, device=eng.device)
+    device_feedback = adaptive and feedback is None
+    if device_feedback:
+        from core.codebook_lte import LTECodebook
+        max_rank = min(num_tx, num_rx, 4)
+        cb_tab, cb_sizes = eng.rank_codebook(num_tx, max_rank)
+        books = [LTECodebook(num_tx, transmission_mode='TM4', rank=r) for r in range(1, max_rank + 1)]
+        n_blocks = -(-n_trials // feedback_block)
+        snr_t = torch.tensor([float(x) for x in snr_db], dtype=torch.float64, device=eng.device)
+
+    def device_units(trial_lo, n):
+        """(ri, pmi) of every (SNR point, feedback block) unit the trials [trial_lo, trial_lo + n) touch."""
+        blk0, blk1 = trial_lo // feedback_block, (trial_lo + n - 1) // feedback_block
+        nb = blk1 - blk0 + 1
+        H = torch.cat([eng.random_channel(nb, num_rx, num_tx, seed ^ 0x5249, stream_id0=si * n_blocks + blk0)
+                       for si in range(n_snr)]) * (1.0 / np.sqrt(num_tx))
+        ri, pmi = eng.rank_feedback(H, snr_t.repeat_interleave(nb).contiguous(), cb_tab, cb_sizes, max_rank=max_rank)
+        return blk0, ri.view(n_snr, nb).cpu().numpy(), pmi.view(n_snr, nb).cpu().numpy()
 
     def count_batch(trial_lo, n):
         if not adaptive:
@@ -358,10 +376,17 @@ def sm_sweep(config, snr_db, n_trials, num_tx=4, num_rx=4, rank=4, detector='MMS
             rank_hist[:, int(rank) - 1] += n
             return err.reshape(-1)
         err = torch.zeros((n, n_snr), dtype=torch.int64, device=eng.device)
+        if device_feedback:
+            blk0, ri_u, pmi_u = device_units(trial_lo, n)
         for si, snr in enumerate(snr_db):
             t = trial_lo
             while t < trial_lo + n:
-                if adaptive:
+                if device_feedback:
+                    blk = t // feedback_block
+                    end = min(trial_lo + n, (blk + 1) * feedback_block)
+                    ri = int(ri_u[si, blk - blk0])
+                    W = books[ri - 1].get_precoder(int(pmi_u[si, blk - blk0]))
+                elif adaptive:
                     blk = t // feedback_block
                     end = min(trial_lo + n, (blk + 1) * feedback_block)
                     rs = np.random.RandomState([seed & 0x7fffffff, si, blk])

@@ -165,8 +165,45 @@ def test_sm_sweep_fixed_and_adaptive_rank():
                     for i in range(120)])
     big = sm_sweep(cfg, [20.0], 240, rank=2, precoder=precoder, **kw)['ber'].numpy()[0]
     assert abs(loop - big) / max(big, 1e-9) < 0.35
+    # the same with the feedback rule on the device (the default): sharding invariance and the SNR gate
+    dv = sm_sweep(cfg, [3.0, 8.0, 20.0], 40, rank='adaptive', feedback_block=8, batch_trials=40, **kw)
+    dv2 = [sm_sweep(cfg, [3.0, 8.0, 20.0], 40, rank='adaptive', feedback_block=8, batch_trials=7, rank_id=r, world=3, **kw)
+           for r in range(3)]
+    assert torch.equal(sum(p['errors'] for p in dv2), dv['errors'])
+    assert torch.equal(sum(p['rank_hist'] for p in dv2), dv['rank_hist'])
+    assert dv['rank_hist'].sum(dim=1).tolist() == [40, 40, 40]
+    assert dv['rank_hist'][0].tolist() == [40, 0, 0, 0]              # below 5 dB: rank 1
+    assert int(dv['rank_hist'][1, 2:].sum()) == 0                   # below 10 dB: at most rank 2
     with pytest.raises(ValueError):
-        sm_sweep(cfg, snrs, 4, rank='adaptive', **kw)
+        sm_sweep(cfg, snrs, 4, rank=2, **kw)                        # a fixed rank needs its precoder
+
+
+@pytest.mark.parametrize('R,T', [(4, 4), (2, 4), (8, 4), (2, 2), (4, 2)])
+def test_rank_feedback_kernel_matches_the_reference_rule(R, T):
+    """lte_rank_feedback against RankAdaptation.get_feedback (core/rank_adaptation.py, the reference's rule) on the
+    same matrices: RI and PMI equal for every matrix and SNR point, including the SNR gates and weak channels."""
+    import torch
+    from core.rank_adaptation import RankAdaptation
+    from lte_b200 import LinkEngine
+    from config import LTEConfig
+    eng = LinkEngine.from_config(LTEConfig(1.25, 15.0, 'QPSK'))
+    n = 600
+    H = eng.random_channel(n, R, T, 11) * (1.0 / np.sqrt(T))
+    Hn = H.cpu().numpy().astype(np.complex128)
+    Hn[:5] *= 1e-7                                                  # lambda_max < 1e-10: rank 1
+    H = torch.from_numpy(Hn.astype(np.complex64)).to(eng.device)
+    Hn = H.cpu().numpy().astype(np.complex128)
+    snr = np.random.RandomState(3).choice([-3.0, 4.9, 5.0, 7.5, 10.0, 15.0, 22.0, 30.0], n)
+    max_rank = min(R, T, 4)
+    tab, sizes = eng.rank_codebook(T, max_rank)
+    ri, pmi = eng.rank_feedback(H, torch.from_numpy(snr).to(eng.device), tab, sizes, max_rank=max_rank)
+    ri, pmi = ri.cpu().numpy(), pmi.cpu().numpy()
+    seen = set()
+    for i in range(n):
+        fb = RankAdaptation(T, R, snr_db=float(snr[i])).get_feedback(Hn[i])
+        assert (int(ri[i]), int(pmi[i])) == (int(fb['ri']), int(fb['pmi'])), (i, snr[i])
+        seen.add(int(ri[i]))
+    assert seen == set(range(1, max_rank + 1))
 
 
 def test_sm_ber_per_stream_snr_equals_per_snr_passes():
