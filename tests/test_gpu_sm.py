@@ -198,12 +198,26 @@ def test_rank_feedback_kernel_matches_the_reference_rule(R, T):
     tab, sizes = eng.rank_codebook(T, max_rank)
     ri, pmi = eng.rank_feedback(H, torch.from_numpy(snr).to(eng.device), tab, sizes, max_rank=max_rank)
     ri, pmi = ri.cpu().numpy(), pmi.cpu().numpy()
-    seen = set()
+    from core.codebook_lte import LTECodebook
+    seen, decided = set(), 0
     for i in range(n):
         fb = RankAdaptation(T, R, snr_db=float(snr[i])).get_feedback(Hn[i])
-        assert (int(ri[i]), int(pmi[i])) == (int(fb['ri']), int(fb['pmi'])), (i, snr[i])
+        assert int(ri[i]) == int(fb['ri']), (i, snr[i])
+        # PMI: the same entry wherever the capacity metric has a winner.  A 1e-7 channel, or rank T with its unitary
+        # precoders (det(I + c H W W^H H^H) does not depend on W), leave only rounding noise between the entries:
+        # there the kernel's choice must be one of the (numerically) tied maxima.
+        cb = LTECodebook(T, transmission_mode='TM4', rank=int(ri[i]))
+        c = 10 ** (float(snr[i]) / 10) / int(ri[i])
+        m = np.array([np.log2(np.linalg.det(np.eye(R) + c * (Hn[i] @ cb.get_precoder(k)) @ (Hn[i] @ cb.get_precoder(k)).conj().T).real)
+                      for k in range(cb.codebook_size)])
+        tied = np.flatnonzero(m >= m.max() - 1e-9 * max(1.0, abs(m.max())))
+        assert int(pmi[i]) in tied, (i, snr[i], m)
+        if len(tied) == 1:
+            assert int(pmi[i]) == int(fb['pmi']), (i, snr[i])
+            decided += 1
         seen.add(int(ri[i]))
     assert seen == set(range(1, max_rank + 1))
+    assert decided > n // 3
 
 
 def test_sm_ber_per_stream_snr_equals_per_snr_passes():
