@@ -2,7 +2,7 @@
 """profiles/rNN_traffic.json from an `ncu --set full` report of tools/stage_bench.py: per stage of the bench, the
 dram__bytes_read.sum + dram__bytes_write.sum and duration of ONE launch of its dominant kernel.  bench.py reads
 `roofline.traffic` from this file and refuses to run if the kernel it reports is not in it.
-usage: python tools/ncu_traffic.py out.json subframes_per_launch report.ncu-rep [more.ncu-rep ...]"""
+usage: python tools/ncu_traffic.py [--update] out.json subframes_per_launch report.ncu-rep [more.ncu-rep ...]"""
 import csv
 import json
 import subprocess
@@ -23,8 +23,14 @@ def to_bytes(v, unit):
 
 
 def main():
-    out, per_launch, reps = sys.argv[1], int(sys.argv[2]), sys.argv[3:]
-    kernels = {}
+    # --update: keep the entries of an existing out.json for kernels the given reports do not hold
+    args = [a for a in sys.argv[1:] if a != '--update']
+    out, per_launch, reps = args[0], int(args[1]), args[2:]
+    kernels, old_reports = {}, []
+    if '--update' in sys.argv[1:]:
+        prev = json.load(open(out))
+        kernels = prev['kernels']
+        old_reports = sorted({k['report'] for k in kernels.values()})
     for rep in reps:
         raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
         rows = list(csv.reader(raw.splitlines()))
@@ -42,7 +48,7 @@ def main():
                     kernels[stage] = {'kernel': name[:120], 'report': rep.split('/')[-1], 'dram_bytes': rd + wr, 'dram_read': rd,
                                       'dram_write': wr, 'duration_us': dur_us}
     json.dump({'source': 'ncu --set full --clock-control none of tools/stage_bench.py --pipeline spectral|fused|staged, one launch '
-                         'per kernel (' + ', '.join(r.split('/')[-1] for r in reps) + ')',
+                         'per kernel (' + ', '.join(sorted(set(old_reports) | {r.split('/')[-1] for r in reps})) + ')',
                'subframes_per_launch': per_launch, 'kernels': kernels}, open(out, 'w'), indent=1)
     print(json.dumps({k: round(v['dram_bytes'] / 1e9, 3) for k, v in kernels.items()}))
 
