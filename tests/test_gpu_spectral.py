@@ -84,7 +84,9 @@ def test_spectral_matches_fused_time_domain_kernel(bw, mod, prof, R, S, v):
     assert np.allclose(power.cpu().numpy(), pf.cpu().numpy(), rtol=2e-6)
 
 
-@pytest.mark.parametrize('bw,mod,prof,R,S,v', [CASES[0], CASES[1], (5.0, '16-QAM', 'Pedestrian_A', 3, 29, 3.0)])
+@pytest.mark.parametrize('bw,mod,prof,R,S,v', [CASES[0], CASES[1], (5.0, '16-QAM', 'Pedestrian_A', 3, 29, 3.0),
+                                              (10.0, '16-QAM', 'Pedestrian_A', 4, 14, 3.0),
+                                              (2.5, 'QPSK', 'Pedestrian_A', 2, 15, 3.0)])
 def test_compact_layout_is_a_gather_of_the_window(bw, mod, prof, R, S, v):
     """COMPACT output = data bins in data-symbol order + the pilot bins of every slot's first symbol."""
     from lte_b200 import _native as nat
