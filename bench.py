@@ -76,8 +76,8 @@ def stage_bytes(N=2048, cp=144, Nd=999, Np=200, Nc=1200, b=6, R=R_ANT, S=S_SUBFR
 
 def spectral_flops(npairs=600, cp=144, R=R_ANT, S=S_SUBFRAME, NT=4, dmax=13):
     """fp32 flops per subframe of channel_spectral_kernel (csrc/spectral.cu): packed FFMA2 = 4 flops, FMUL2 = 2.
-    Per bin pair and symbol: Horner 4 (dmax - 1) FFMA2 (the first step is a copy); per tap with a delay V/W = 6 FFMA2 + 4 FMUL2; combine
-    8 FFMA2 per (tap, antenna) (first tap: 6 + 2 FMUL2); power 2 FFMA2 per antenna.  CP sample pairs:
+    Per bin pair and symbol: Horner 4 (dmax - 1) FFMA2 (the first step is a copy); per tap with a delay
+    V/W = 6 FFMA2 + 4 FMUL2; combine 8 FFMA2 per (tap, antenna) (first tap: 6 + 2 FMUL2); power 2 FFMA2 per antenna.  CP sample pairs:
     6 FFMA2 per (tap, antenna) + 2 for the power."""
     per_pair = 4 * (4 * max(dmax - 1, 0)) + (NT - 1) * (6 * 4 + 4 * 2) + R * ((NT - 1) * 8 * 4 + 6 * 4 + 2 * 2) + R * 2 * 4
     per_cp = (cp // 2) * (NT * R * 6 * 4 + R * 2 * 4)
@@ -386,8 +386,9 @@ def run_gpu(args, rank, world):
                                    'unit': 'TFLOP/s', 'peak_source': 'measured on this box (lte_fp32_peak_launch: independent '
                                    'fma.rn.f32x2 chains, CUDA events)', 'flops_per_launch': fl}
             roofline['compute']['frac'] = roofline['compute']['achieved'] / fp32
-            roofline['limiter'] = ('instruction issue / fp32 FMA pipe, not HBM: see profiles/r02_spectral_ncu_summary.md '
-                                   'and DESIGN.md 4.3')
+            roofline['limiter'] = ('packed-fp32 FMA path (register-file limited: 2.3-2.9 cycles per FFMA2 for this kernel\'s '
+                                   'operand patterns against 2.2 in the peak measurement, profiles/r02_ffma2_forms.txt), not HBM: '
+                                   'see profiles/r02_spectral_ncu_summary.md and DESIGN.md 4.3a')
         if world == 1:
             n_cpu = args.cpu_subframes
             v = cpu_subframes_per_s(n_cpu, 1)
