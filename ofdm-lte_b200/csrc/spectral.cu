@@ -357,9 +357,10 @@ __host__ __device__ constexpr int spec_ct_delay(int dk, int ts) {
 // registers.  ALL arithmetic on the bins runs packed over the pair (f32x2 lanes = the two bins): the Horner
 // sweep over the symbol tail, V_t = e_t X, W_t = e_t G - Q_t, and the per-antenna combine, whose
 // coefficients enter as scalar-broadcast operands straight from 128-bit shared-memory loads -- no packing
-// or unpacking instruction on the path.  The cyclic-prefix samples (time domain, power only) are spread over
-// the first cp / 32 warps.  Stream power stays in registers across the stream's symbols and leaves as one
-// atomic per warp and antenna.
+// or unpacking instruction on the path.  The cyclic-prefix samples (time domain, power only) are the producer
+// warp's second job, one antenna per lane.  Stream power stays in registers across the stream's symbols and
+// leaves as one atomic per warp and antenna.
+// DK > 0: the tap delays are the compile-time set spec_ct_delay(DK, .), see there.
 // PLANAR flag = the sweep's compact layout: a data pair leaves as ONE 128-bit store of two consecutive complex
 // values into Y [B*R][S][2 ndp]; pilot pairs only on every slot's first symbol, into Yp [B*R][slots][2 npp];
 // nothing else is ever read downstream.  Otherwise Y is the windowed grid [B*R][S][nk].
