@@ -61,8 +61,7 @@ def stage_bytes(N=2048, cp=144, Nd=999, Np=200, Nc=1200, b=6, R=R_ANT, S=S_SUBFR
         # spectral pipeline (sweep default at low Doppler)
         'tx_spectral': S * Nd + S * Nc * 8 + S * cp * 8,
         'channel_spectral': S * Nc * 8 + S * cp * 8 + S * Nd + coef + R * NT * 16 * 4 + R * S * 2 * ndp * 8 + R * 2 * npp * 8,
-        'crs_ls_compact': R * 2 * npp * 8 + R * Np * 8,
-        'mrc_demap_count_compact': R * S * Nd * 8 + R * Np * 8 + S * Nd + 8,
+        'mrc_demap_count_compact': R * S * Nd * 8 + R * 2 * npp * 8 + S * Nd + 8,     # LS estimate formed inside
         # fused time-domain pipeline
         'tx_map_ifft': S * Nd + S * L * 8,
         'channel_rx_fft': S * L * 8 + R * S * Nc * 8,
@@ -445,9 +444,8 @@ def time_stages(eng, ws, chan, snr_rows, idx, nbits, seed, B, S, R, nat, torch, 
             'tx_spectral': lambda: eng.tx_spectral(S, idx, out_G=ws['G'], out_tail=ws['tail']),
             'channel_spectral': lambda: eng.channel_spectral(idx, ws['G'], ws['tail'], chan, B, R, S, ph, out=ws['Yd'],
                                                              power=ws['power'], compact=True, out_pilots=ws['Yp']),
-            'crs_ls_compact': lambda: eng.estimate_compact(ws['Yp'], B * R, S, out=ws['Hp'], awgn=awgn),
-            'mrc_demap_count_compact': lambda: eng.mrc_demap_count_compact(ws['Yd'], ws['Hp'], idx, B, R, S, nbits=nbits,
-                                                                           errors=ws['errors'], awgn=awgn),
+            'mrc_demap_count_compact': lambda: eng.mrc_demap_count_compact(ws['Yd'], None, idx, B, R, S, nbits=nbits,
+                                                                           errors=ws['errors'], awgn=awgn, Yp=ws['Yp']),
         }
     elif pipeline == 'fused':
         calls = {

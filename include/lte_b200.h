@@ -328,6 +328,14 @@ int lte_crs_ls_compact(const lte_plan*, const lte_c32* Ypilot, lte_c32* Hp, int6
 int lte_mrc_demap_count_compact(const lte_plan*, const lte_c32* Ydata, const lte_c32* Hp,
                                 const uint8_t* idx_tx, unsigned long long* errors, int64_t nbits, int64_t B,
                                 int32_t R, int32_t S, const lte_awgn_desc* awgn, void* stream);
+/* lte_crs_ls_compact + lte_mrc_demap_count_compact in one launch (the sweep's form): every CTA forms the LS
+ * estimates of the <= 28 pilots its 128 data bins interpolate between from Ypilot itself, with the very
+ * operations and lazy-AWGN draws of lte_crs_ls_compact, so the counts are bit-identical to the two calls and
+ * no estimate tensor exists (LTEChannelEstimator.estimate_channel + _interpolate_channel,
+ * core/lte_receiver.py:62-133, inside the combiner of core/ofdm_core.py:1484-1532). */
+int lte_crs_mrc_demap_count_compact(const lte_plan*, const lte_c32* Ydata, const lte_c32* Ypilot,
+                                    const uint8_t* idx_tx, unsigned long long* errors, int64_t nbits, int64_t B,
+                                    int32_t R, int32_t S, const lte_awgn_desc* awgn, void* stream);
 
 /* --- SFBC Alamouti transmit diversity (2 TX) ---------------------------------------------
  * lte_sfbc_encode replaces SFBCAlamouti.encode (core/sfbc_alamouti.py:45-78) fused with the QAM

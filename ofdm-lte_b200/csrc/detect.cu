@@ -624,12 +624,13 @@ extern "C" int lte_crs_ls_compact(const lte_plan* p, const lte_c32* Ypilot, lte_
 template <int R, int NOISE, bool FULL>
 __global__ void __launch_bounds__(128, NOISE ? 8 : 1)
 mrc_compact_kernel(const DevPlan P, const float2* __restrict__ Yd, const float2* __restrict__ Hp,
-                   const uint8_t* __restrict__ idx_tx, unsigned long long* __restrict__ errors, int S, int nslot,
-                   long long nbits, int gx, const AwgnArgs A) {
+                   const float2* __restrict__ Yp, const uint8_t* __restrict__ idx_tx,
+                   unsigned long long* __restrict__ errors, int S, int nslot, long long nbits, int gx, const AwgnArgs A) {
     // (estimate, slope to the next pilot) of the pilots this CTA's 128 bins interpolate between, per antenna, and
     // the noise sigma of every antenna: worked out once per CTA instead of once per thread (the divisions are
     // the IEEE ones of crs_ls_interp_kernel, so the interpolated values are unchanged bit for bit)
     __shared__ float4 seg_s[R * MRCC_PILOTS];
+    __shared__ float2 ls_s[R * (MRCC_PILOTS + 1)];              // Yp != NULL: the LS estimates formed here (Hp unused)
     __shared__ float sigma_s[R];
     const int chunk = blockIdx.x % gx;
     const long long b = blockIdx.x / gx;
@@ -653,9 +654,23 @@ mrc_compact_kernel(const DevPlan P, const float2* __restrict__ Yd, const float2*
     const int ystride = 2 * P.ndp;
     for (int slot = 0; slot < nslot; ++slot) {
         __syncthreads();                                            // the previous slot's table has been consumed
+        if (Yp) {
+            // the LS step of crs_ls_compact_kernel for the npil + 1 pilots this CTA needs, with its very operations
+            // (and lazy-AWGN draws): no Hp tensor, no estimator launch
+            for (int q = tid; q < (npil + 1) * R; q += blockDim.x) {
+                const int r = q / (npil + 1), i = la0 + q - r * (npil + 1);
+                if (i < cnt) {
+                    const long long row = b * R + r;
+                    float2 yp = Yp[((size_t)row * nslot + slot) * (2 * P.npp) + i];
+                    if (NOISY) yp = awgn_at(A, sigma_s[r], row, slot * LTE_SLOT_SYMBOLS, P.N, P.pset_bin[i], yp);
+                    ls_s[r * (MRCC_PILOTS + 1) + i - la0] = cmul(yp, P.pset_inv[i]);
+                }
+            }
+            __syncthreads();
+        }
         for (int q = tid; q < npil * R; q += blockDim.x) {
             const int r = q / npil, i = la0 + q - r * npil;
-            const float2* hp = Hp + (((size_t)b * R + r) * nslot + slot) * P.Np;
+            const float2* hp = Yp ? ls_s + r * (MRCC_PILOTS + 1) - la0 : Hp + (((size_t)b * R + r) * nslot + slot) * P.Np;
             const float2 a = hp[i];
             float2 sl = make_float2(0.f, 0.f);
             if (i < cnt - 1) {
@@ -744,10 +759,10 @@ mrc_compact_kernel(const DevPlan P, const float2* __restrict__ Yd, const float2*
     block_add_errors(act ? e : 0u, &errors[b]);
 }
 
-extern "C" int lte_mrc_demap_count_compact(const lte_plan* p, const lte_c32* Ydata, const lte_c32* Hp,
-                                           const uint8_t* idx_tx, unsigned long long* errors, int64_t nbits, int64_t B,
-                                           int32_t R, int32_t S, const lte_awgn_desc* awgn, void* stream) {
-    if (!p || !Ydata || !Hp || !idx_tx || !errors || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
+static int mrc_compact_launch(const lte_plan* p, const lte_c32* Ydata, const lte_c32* Hp, const lte_c32* Ypilot,
+                              const uint8_t* idx_tx, unsigned long long* errors, int64_t nbits, int64_t B,
+                              int32_t R, int32_t S, const lte_awgn_desc* awgn, void* stream) {
+    if (!p || !Ydata || (!Hp == !Ypilot) || !idx_tx || !errors || B < 0 || S < 1) return LTE_ERR_INVALID_ARG;
     if (p->dev.Np == 0 || p->nsets != 1) return LTE_ERR_UNSUPPORTED;
     AwgnArgs A = {};
     int rc;
@@ -774,8 +789,8 @@ extern "C" int lte_mrc_demap_count_compact(const lte_plan* p, const lte_c32* Yda
     cudaStream_t st = (cudaStream_t)stream;
     const bool full = nbits >= (int64_t)S * p->dev.Nd * p->dev.bps;
 #define LAUNCH_MRCC2(RR, NN, FF)                                                                                      \
-    mrc_compact_kernel<RR, NN, FF><<<grid, 128, 0, st>>>(p->dev, (const float2*)Ydata, (const float2*)Hp, idx_tx,     \
-                                                         errors, S, nslot, nbits, gx, A)
+    mrc_compact_kernel<RR, NN, FF><<<grid, 128, 0, st>>>(p->dev, (const float2*)Ydata, (const float2*)Hp,            \
+                                                         (const float2*)Ypilot, idx_tx, errors, S, nslot, nbits, gx, A)
 #define LAUNCH_MRCC(RR)                                                                                               \
     case RR:                                                                                                         \
         if (awgn && A.combine) { if (full) LAUNCH_MRCC2(RR, 2, true); else LAUNCH_MRCC2(RR, 2, false); }                \
@@ -791,4 +806,16 @@ extern "C" int lte_mrc_demap_count_compact(const lte_plan* p, const lte_c32* Yda
 #undef LAUNCH_MRCC2
     LTE_CHECK_CUDA(cudaGetLastError());
     return LTE_OK;
+}
+
+extern "C" int lte_mrc_demap_count_compact(const lte_plan* p, const lte_c32* Ydata, const lte_c32* Hp,
+                                           const uint8_t* idx_tx, unsigned long long* errors, int64_t nbits, int64_t B,
+                                           int32_t R, int32_t S, const lte_awgn_desc* awgn, void* stream) {
+    return mrc_compact_launch(p, Ydata, Hp, nullptr, idx_tx, errors, nbits, B, R, S, awgn, stream);
+}
+
+extern "C" int lte_crs_mrc_demap_count_compact(const lte_plan* p, const lte_c32* Ydata, const lte_c32* Ypilot,
+                                               const uint8_t* idx_tx, unsigned long long* errors, int64_t nbits,
+                                               int64_t B, int32_t R, int32_t S, const lte_awgn_desc* awgn, void* stream) {
+    return mrc_compact_launch(p, Ydata, nullptr, Ypilot, idx_tx, errors, nbits, B, R, S, awgn, stream);
 }

@@ -85,6 +85,7 @@ _SIGS = {
                                  C.c_int),
     'lte_crs_ls_compact': ([_P, _P, _P, _I64, _I32, C.POINTER(AwgnDesc), _P], C.c_int),
     'lte_mrc_demap_count_compact': ([_P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, C.POINTER(AwgnDesc), _P], C.c_int),
+    'lte_crs_mrc_demap_count_compact': ([_P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, C.POINTER(AwgnDesc), _P], C.c_int),
     'lte_equalize_zf': ([_P, _P, _P, _P, C.c_int, _I64, _I32, _P], C.c_int),
     'lte_equalize_mrc': ([_P, _P, _P, _P, C.c_int, _I64, _I32, _I32, _P], C.c_int),
     'lte_sfbc_encode': ([_P, _P, _P, _P, _P, _I64, _I32, _P], C.c_int),

@@ -867,18 +867,26 @@ class LinkEngine:
         self.launches += 1
         return errors
 
-    def mrc_demap_count_compact(self, Yd, Hp, idx_tx, B, R, S, nbits=None, errors=None, awgn=None, accumulate=False):
+    def mrc_demap_count_compact(self, Yd, Hp, idx_tx, B, R, S, nbits=None, errors=None, awgn=None, accumulate=False,
+                                Yp=None):
         """MRC + slicer + bit-error count on the compact layout (Yd [B*R, S, 2 ndp], Hp [B*R, slots, Np]): every
         thread interpolates its own bin between its two pilots; counts are bit-identical to
-        estimate + mrc_demap_count on the windowed layout.  accumulate: add to `errors` instead of zeroing it."""
+        estimate + mrc_demap_count on the windowed layout.  accumulate: add to `errors` instead of zeroing it.
+        With Hp = None and Yp [B*R, slots, 2 npp] the LS estimate of estimate_compact is formed inside the same
+        launch (lte_crs_mrc_demap_count_compact): same counts, no estimate tensor."""
         if errors is None:
             errors = torch.zeros(B, dtype=torch.int64, device=self.device)
         elif not accumulate:
             errors.zero_()
         nb = int(nbits) if nbits is not None else S * self.Nd * self.bps
-        nat.check(nat.lib.lte_mrc_demap_count_compact(self._plan, _ptr(Yd), _ptr(Hp), _ptr(idx_tx), _ptr(errors), nb, B,
-                                                      R, S, C.byref(awgn) if awgn is not None else None,
-                                                      self._stream()), 'lte_mrc_demap_count_compact')
+        aw = C.byref(awgn) if awgn is not None else None
+        if Hp is None:
+            nat.check(nat.lib.lte_crs_mrc_demap_count_compact(self._plan, _ptr(Yd), _ptr(Yp), _ptr(idx_tx), _ptr(errors),
+                                                              nb, B, R, S, aw, self._stream()),
+                      'lte_crs_mrc_demap_count_compact')
+        else:
+            nat.check(nat.lib.lte_mrc_demap_count_compact(self._plan, _ptr(Yd), _ptr(Hp), _ptr(idx_tx), _ptr(errors), nb, B,
+                                                          R, S, aw, self._stream()), 'lte_mrc_demap_count_compact')
         self.launches += 1
         return errors
 
@@ -966,8 +974,9 @@ class LinkEngine:
             (Yd, Yp), power = self.channel_spectral(idx, G, tail, chan, B, R, S, ph, out=ws['Yd'], power=ws['power'],
                                                     compact=True, out_pilots=ws['Yp'])
             awgn = self.awgn_desc(power, snr_lin_rows, seed, stream_id0 * R, combine=(noise_domain == 3))
-            Hp = self.estimate_compact(Yp, B * R, S, out=ws['Hp'], awgn=awgn)
-            return self.mrc_demap_count_compact(Yd, Hp, idx, B, R, S, nbits=nbits, errors=ws['errors'], awgn=awgn, accumulate=accumulate)
+            # LS estimate, interpolation, MRC, slicer and count in one launch
+            return self.mrc_demap_count_compact(Yd, None, idx, B, R, S, nbits=nbits, errors=ws['errors'], awgn=awgn,
+                                                accumulate=accumulate, Yp=Yp)
         if 'tx' not in ws:
             ws['tx'] = self._empty((B, S * self.L), torch.complex64)
             k0, nk = self.window(nat.WINDOW_USEFUL)

@@ -124,6 +124,9 @@ def test_compact_consumers_count_exactly_like_the_windowed_ones(bw, mod, prof, R
         want = eng.mrc_demap_count(Y, H, idx, B, R, S, nbits=nbits, awgn=awgn).clone()
         Hp = eng.estimate_compact(Yp, B * R, S, awgn=awgn)
         got = eng.mrc_demap_count_compact(Yd, Hp, idx, B, R, S, nbits=nbits, awgn=awgn)
+        # ... and with the LS estimate formed inside the MRC launch (what the sweep runs)
+        one = eng.mrc_demap_count_compact(Yd, None, idx, B, R, S, nbits=nbits, awgn=awgn, Yp=Yp)
+        assert torch.equal(one, got)
         assert torch.equal(got, want)
         if awgn is not None:
             assert int(want.sum()) > 0

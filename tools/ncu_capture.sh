@@ -3,7 +3,7 @@
 # after the same command has exited 0 without the profiler.  usage: bash tools/ncu_capture.sh spectral r02
 pipe=${1:-spectral}; tag=${2:-r02}
 case $pipe in
-  spectral) rx='tx_spectral|spectral_coef|channel_spectral|crs_ls_compact|mrc_compact'; n=5 ;;
+  spectral) rx='tx_spectral|spectral_coef|channel_spectral|mrc_compact'; n=4 ;;
   fused)    rx='tx_map_ifft|jakes_coef|channel_rx_fft|crs_ls_interp|mrc_kernel'; n=5 ;;
   staged)   rx='tx_map_ifft|jakes_coef|tdl_kernel|rx_fft_kernel|crs_ls_interp|mrc_kernel'; n=6 ;;
 esac

@@ -57,6 +57,7 @@ def main():
     awgn = eng.awgn_desc(power, snr, 3, 0, combine=True)
     out['crs_ls_compact_ms'] = timeit(lambda: eng.estimate_compact(Yp, B * R, S, out=Hp, awgn=awgn))
     out['mrc_compact_ms'] = timeit(lambda: eng.mrc_demap_count_compact(Yd, Hp, idx, B, R, S, errors=errors, awgn=awgn))
+    out['crs_mrc_compact_ms'] = timeit(lambda: eng.mrc_demap_count_compact(Yd, None, idx, B, R, S, errors=errors, awgn=awgn, Yp=Yp))
     wsl = eng.workspace(B, S, R, fading=True, fused=True, lazy=True)
     out['simo_ber_spectral_ms'] = timeit(lambda: eng.simo_ber(wsl, chan, snr, 5, idx=idx, fused=True, noise_domain=3))
     out['tx_map_ifft_ms'] = timeit(lambda: eng.modulate(S, idx=idx, want_stats=False, out=tx))
