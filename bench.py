@@ -274,7 +274,9 @@ def run_gpu(args, rank, world):
     S, R = S_SUBFRAME, R_ANT
     fused = args.pipeline != 'staged'
     spectral = args.pipeline == 'spectral'
-    ws = eng.workspace(B, S, R, fading=True, fused=fused, lazy=spectral)
+    # two workspaces: LinkEngine.simo_ber_batches keeps two batches in flight on two streams
+    wss = [eng.workspace(B, S, R, fading=True, fused=fused, lazy=spectral) for _ in range(args.inflight)]
+    ws = wss[0]
     snr_lin = torch.tensor([10 ** (s / 10) for s in SNR_POINTS], dtype=torch.float32, device=dev)
     snr_rows = snr_lin.repeat(args.trials).repeat_interleave(R).contiguous()       # [B*R], SNR fastest over b
     nbits = S * eng.Nd * eng.bps
@@ -286,12 +288,12 @@ def run_gpu(args, rank, world):
     totals = torch.zeros(n_snr, dtype=torch.int64, device=dev)
 
     def step(i):
-        for j in range(args.batches):
-            sid0 = (((i * world) + rank) * args.batches + j) * B      # global stream ids: independent of the GPU count
-            # stream slot b always runs at the same SNR point, so the per-slot counts simply accumulate in the
-            # workspace (the MRC kernel counts with atomics); they are reduced per SNR point once, after the run
-            eng.simo_ber(ws, chan, snr_rows, seed, stream_id0=sid0, idx=idx, nbits=nbits, fused=fused,
-                         spectral=spectral, noise_domain=nd, accumulate=True)
+        # global stream ids: independent of the GPU count.  Stream slot b always runs at the same SNR point, so the
+        # per-slot counts simply accumulate in the workspaces (the MRC kernel counts with atomics); they are reduced
+        # per SNR point once, after the run
+        sids = [(((i * world) + rank) * args.batches + j) * B for j in range(args.batches)]
+        eng.simo_ber_batches(wss, chan, snr_rows, seed, sids, idx=idx, nbits=nbits, fused=fused, spectral=spectral,
+                             noise_domain=nd)
 
     def sync():
         torch.cuda.synchronize(dev)
@@ -302,7 +304,8 @@ def run_gpu(args, rank, world):
     for i in range(args.warmup):
         step(i)
     pipeline_used = 'spectral' if ws.get('spectral') else ('fused' if fused and 'faded' not in ws else 'staged')
-    ws['errors'].zero_()                        # per-slot counters of the timed run start here
+    for w in wss:
+        w['errors'].zero_()                     # per-slot counters of the timed run start here
     sync()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -315,7 +318,7 @@ def run_gpu(args, rank, world):
     e0.record()
     for i in range(args.steps):
         step(args.warmup + i)
-    totals.copy_(ws['errors'].view(args.trials, n_snr).sum(0))      # per SNR point, inside the timed region
+    totals.copy_(sum(w['errors'] for w in wss).view(args.trials, n_snr).sum(0))     # per SNR point, inside the timed region
     if world > 1:
         dist.all_reduce(totals)                 # the only collective: int64[16] error counters
     e1.record()
@@ -402,7 +405,7 @@ def run_gpu(args, rank, world):
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': cfgd, 'pipeline': pipeline_used,
+                'config': cfgd, 'pipeline': pipeline_used, 'batches_in_flight': args.inflight,
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': pipe.h2d_bytes_per_batch * args.batches,
                         'd2h_bytes_per_step': pipe.d2h_bytes_per_batch * args.batches,
                         'api': 'LinkEngine.stream_host_batches (lte_b200/host_stream.py): pinned host bits -> H2D -> '
@@ -589,6 +592,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--trials', type=int, default=256, help='trials per SNR point per GPU per batch')
+    ap.add_argument('--inflight', type=int, default=2, help='batches in flight side by side (workspaces / streams)')
     ap.add_argument('--batches', type=int, default=32, help='chain passes (batches of 16 x trials subframes) per step')
     ap.add_argument('--pipeline', default='spectral', choices=['spectral', 'fused', 'staged'],
                     help='spectral: spectral link (one forward transform per OFDM symbol, compact grid, lazy AWGN); '

@@ -60,7 +60,7 @@ class HostBatchPipeline:
     uint8 [B, ceil(nbits / 8)] in host memory (pinned memory makes the copy asynchronous).  Per batch, inside
     one CUDA stream order: H2D copy (copy stream) -> lte_bits_to_indices -> the SIMO-MRC chain -> D2H of the
     int64 [B] error counts into a pinned host buffer.  `depth` device input buffers let the copy of the next
-    batch run while the current one computes."""
+    batch run while the current one computes; consecutive batches alternate between two compute streams."""
 
     def __init__(self, engine, chan, num_rx, snr_lin_rows, B, S, nbits=None, seed=0, noise_domain=3, fused=True,
                  depth=3, spectral=None):
@@ -71,8 +71,12 @@ class HostBatchPipeline:
         self.spectral = spectral                                # None: the engine picks (spectral link when it applies)
         dev = engine.device
         self.snr_rows = snr_lin_rows.to(dev).contiguous()
-        self.ws = engine.workspace(self.B, self.S, self.R, fading=chan.num_taps > 0, fused=fused,
-                                   lazy=fused and spectral is not False)
+        # two batches in flight on two compute streams (the front of one fills the SMs the tail of the other leaves
+        # idle, LinkEngine.simo_ber_batches), each with its own workspace
+        self.wss = [engine.workspace(self.B, self.S, self.R, fading=chan.num_taps > 0, fused=fused,
+                                     lazy=fused and spectral is not False) for _ in range(2)]
+        self.ws = self.wss[0]
+        self.cstreams = engine.side_streams(2)
         self.dev_bits = [torch.empty((self.B, self.nbytes), dtype=torch.uint8, device=dev) for _ in range(depth)]
         self.host_err = [torch.empty(self.B, dtype=torch.int64).pin_memory() for _ in range(depth)]
         self.copy_stream = torch.cuda.Stream(device=dev)
@@ -92,16 +96,17 @@ class HostBatchPipeline:
             self.ev_copied[k].record(self.copy_stream)
         return main
 
-    def _compute(self, k, stream_id0):
-        main = torch.cuda.current_stream(self.eng.device)
-        main.wait_event(self.ev_copied[k])
-        idx = self.eng.bits_to_indices(self.dev_bits[k], self.nbits, self.S, packed=True)
-        err = self.eng.simo_ber(self.ws, self.chan, self.snr_rows, self.seed, stream_id0=int(stream_id0), idx=idx,
-                                nbits=self.nbits, fused=self.fused, spectral=self.spectral,
-                                noise_domain=self.noise_domain)
-        self.host_err[k].copy_(err, non_blocking=True)
-        self.ev_free[k].record(main)
-        self.ev_done[k].record(main)
+    def _compute(self, k, stream_id0, i):
+        cs = self.cstreams[i & 1]
+        cs.wait_event(self.ev_copied[k])
+        with torch.cuda.stream(cs):
+            idx = self.eng.bits_to_indices(self.dev_bits[k], self.nbits, self.S, packed=True)
+            err = self.eng.simo_ber(self.wss[i & 1], self.chan, self.snr_rows, self.seed, stream_id0=int(stream_id0),
+                                    idx=idx, nbits=self.nbits, fused=self.fused, spectral=self.spectral,
+                                    noise_domain=self.noise_domain)
+            self.host_err[k].copy_(err, non_blocking=True)
+            self.ev_free[k].record(cs)
+            self.ev_done[k].record(cs)
 
     def run(self, batches):
         """batches: iterable of (host_bits, stream_id0, tag).  Yields (errors, tag) per batch in order; `errors` is
@@ -109,6 +114,8 @@ class HostBatchPipeline:
         main = torch.cuda.current_stream(self.eng.device)
         for k in range(self.depth):
             self.ev_free[k].record(main)
+        for cs in self.cstreams:
+            cs.wait_stream(main)
         it = iter(batches)
         pending = []                                            # (slot, tag) whose results are not yet handed out
         nxt = next(it, None)
@@ -124,9 +131,11 @@ class HostBatchPipeline:
                     self.ev_done[ks].synchronize()
                     yield self.host_err[ks], tag
                 self._upload((i + 1) % self.depth, nxt[0])
-            self._compute(k, cur[1])
+            self._compute(k, cur[1], i)
             pending.append((k, cur[2]))
             i += 1
+        for cs in self.cstreams:
+            main.wait_stream(cs)                                # events the caller records on its stream cover all batches
         for ks, tag in pending:
             self.ev_done[ks].synchronize()
             yield self.host_err[ks], tag

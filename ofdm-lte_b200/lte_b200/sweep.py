@@ -88,18 +88,34 @@ def simo_sweep(engine, chan, snr_db, n_trials, num_rx, symbols_per_stream=14, se
         reduce_counts(counts)
         errors, bits = counts[0].cpu(), counts[1].cpu()
         return {'errors': errors, 'bits': bits, 'ber': errors.double() / bits.clamp(min=1).double()}
-    state = {}
-
-    def count_batch(trial_lo, n):
-        B = n * n_snr
-        if state.get('B') != B:
-            state['B'] = B
-            state['ws'] = engine.workspace(B, S, R, fading=chan.num_taps > 0, fused=fused, lazy=fused)
-            state['snr_rows'] = snr_lin.repeat(n).repeat_interleave(R).contiguous()
-        return engine.simo_ber(state['ws'], chan, state['snr_rows'], seed, stream_id0=trial_lo * n_snr,
-                               noise_domain=nd, fused=fused).clone()
-
-    return run_sweep(count_batch, n_snr, n_trials, nbits, batch_trials, rank, world, engine.device)
+    # whole batches of `batch_trials` trials: two in flight (LinkEngine.simo_ber_batches); slot b of a batch always
+    # runs at SNR point b % n_snr, so the per-slot counts accumulate in the workspaces and are reduced per point at
+    # the end.  A ragged last batch follows on its own.
+    lo, hi = shard_range(n_trials, rank, world)
+    counts = torch.zeros((2, n_snr), dtype=torch.int64, device=engine.device)
+    nfull = (hi - lo) // batch_trials
+    if nfull > 0:
+        B = batch_trials * n_snr
+        wss = [engine.workspace(B, S, R, fading=chan.num_taps > 0, fused=fused, lazy=fused) for _ in range(min(2, nfull))]
+        for w in wss:
+            w['errors'].zero_()
+        rows = snr_lin.repeat(batch_trials).repeat_interleave(R).contiguous()
+        engine.simo_ber_batches(wss, chan, rows, seed, [(lo + k * batch_trials) * n_snr for k in range(nfull)],
+                                noise_domain=nd, fused=fused)
+        counts[0] += sum(w['errors'] for w in wss).view(batch_trials, n_snr).sum(dim=0)
+        counts[1] += nfull * batch_trials * nbits
+        del wss
+    rest = (hi - lo) - nfull * batch_trials
+    if rest > 0:
+        t0 = lo + nfull * batch_trials
+        ws = engine.workspace(rest * n_snr, S, R, fading=chan.num_taps > 0, fused=fused, lazy=fused)
+        err = engine.simo_ber(ws, chan, snr_lin.repeat(rest).repeat_interleave(R).contiguous(), seed,
+                              stream_id0=t0 * n_snr, noise_domain=nd, fused=fused)
+        counts[0] += err.view(rest, n_snr).sum(dim=0)
+        counts[1] += rest * nbits
+    reduce_counts(counts)
+    errors, bits = counts[0].cpu(), counts[1].cpu()
+    return {'errors': errors, 'bits': bits, 'ber': errors.double() / bits.clamp(min=1).double()}
 
 
 def scfdm_sweep(engine, chan, snr_db, n_trials, symbols_per_stream=14, seed=0, batch_trials=256, rank=0, world=1,
