@@ -275,7 +275,8 @@ def run_gpu(args, rank, world):
     fused = args.pipeline != 'staged'
     spectral = args.pipeline == 'spectral'
     # two workspaces: LinkEngine.simo_ber_batches keeps two batches in flight on two streams
-    wss = [eng.workspace(B, S, R, fading=True, fused=fused, lazy=spectral) for _ in range(args.inflight)]
+    inflight = args.inflight or eng.batches_in_flight(chan, B, R, S, fused=fused, spectral=spectral)
+    wss = [eng.workspace(B, S, R, fading=True, fused=fused, lazy=spectral) for _ in range(inflight)]
     ws = wss[0]
     snr_lin = torch.tensor([10 ** (s / 10) for s in SNR_POINTS], dtype=torch.float32, device=dev)
     snr_rows = snr_lin.repeat(args.trials).repeat_interleave(R).contiguous()       # [B*R], SNR fastest over b
@@ -405,7 +406,7 @@ def run_gpu(args, rank, world):
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': cfgd, 'pipeline': pipeline_used, 'batches_in_flight': args.inflight,
+                'config': cfgd, 'pipeline': pipeline_used, 'batches_in_flight': inflight,
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': pipe.h2d_bytes_per_batch * args.batches,
                         'd2h_bytes_per_step': pipe.d2h_bytes_per_batch * args.batches,
                         'api': 'LinkEngine.stream_host_batches (lte_b200/host_stream.py): pinned host bits -> H2D -> '
@@ -592,7 +593,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--trials', type=int, default=256, help='trials per SNR point per GPU per batch')
-    ap.add_argument('--inflight', type=int, default=2, help='batches in flight side by side (workspaces / streams)')
+    ap.add_argument('--inflight', type=int, default=0,
+                    help='batches in flight side by side (workspaces / streams); 0 = the engine picks (2 through the spectral link)')
     ap.add_argument('--batches', type=int, default=32, help='chain passes (batches of 16 x trials subframes) per step')
     ap.add_argument('--pipeline', default='spectral', choices=['spectral', 'fused', 'staged'],
                     help='spectral: spectral link (one forward transform per OFDM symbol, compact grid, lazy AWGN); '

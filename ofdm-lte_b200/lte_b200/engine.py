@@ -897,6 +897,17 @@ class LinkEngine:
             have.append(torch.cuda.Stream(device=self.device))
         return have[:n]
 
+    def batches_in_flight(self, chan, B, R, S, fused=True, spectral=None):
+        """How many batches simo_ber_batches should keep in flight: two where the spectral link runs (measured
+        2.28-2.32 -> 2.39 M subframes/s on one box), one through the time-domain kernels, where a second batch in
+        flight gains nothing (fused pipeline on one box: 1.75 / 1.79 M with one, 1.75 / 1.75 M with two -- it runs at
+        the board's power cap either way)."""
+        if spectral is None:
+            spectral = fused and chan.num_taps > 0 and max(chan.delay[:chan.num_taps]) <= self.SPECTRAL_MAX_DELAY
+        ok = bool(spectral) and fused and chan.num_taps > 0 and self.Np > 0 and self.num_pilot_sets == 1 \
+            and self.spectral_workspace_bytes(chan, B, R, S) is not None
+        return 2 if ok else 1
+
     def simo_ber_batches(self, workspaces, chan, snr_lin_rows, seed, stream_ids, idx=None, nbits=None, noise_domain=3,
                          fused=True, spectral=None):
         """Several batches of one shape through simo_ber, round-robin over len(workspaces) workspaces and as many

@@ -71,12 +71,13 @@ class HostBatchPipeline:
         self.spectral = spectral                                # None: the engine picks (spectral link when it applies)
         dev = engine.device
         self.snr_rows = snr_lin_rows.to(dev).contiguous()
-        # two batches in flight on two compute streams (the front of one fills the SMs the tail of the other leaves
-        # idle, LinkEngine.simo_ber_batches), each with its own workspace
+        # through the spectral link two batches in flight on two compute streams (the front of one fills the SMs the
+        # tail of the other leaves idle, LinkEngine.simo_ber_batches), each with its own workspace
+        nfl = engine.batches_in_flight(chan, self.B, self.R, self.S, fused=fused, spectral=spectral)
         self.wss = [engine.workspace(self.B, self.S, self.R, fading=chan.num_taps > 0, fused=fused,
-                                     lazy=fused and spectral is not False) for _ in range(2)]
+                                     lazy=fused and spectral is not False) for _ in range(nfl)]
         self.ws = self.wss[0]
-        self.cstreams = engine.side_streams(2)
+        self.cstreams = engine.side_streams(nfl)
         self.dev_bits = [torch.empty((self.B, self.nbytes), dtype=torch.uint8, device=dev) for _ in range(depth)]
         self.host_err = [torch.empty(self.B, dtype=torch.int64).pin_memory() for _ in range(depth)]
         self.copy_stream = torch.cuda.Stream(device=dev)
@@ -97,11 +98,12 @@ class HostBatchPipeline:
         return main
 
     def _compute(self, k, stream_id0, i):
-        cs = self.cstreams[i & 1]
+        j = i % len(self.cstreams)
+        cs = self.cstreams[j]
         cs.wait_event(self.ev_copied[k])
         with torch.cuda.stream(cs):
             idx = self.eng.bits_to_indices(self.dev_bits[k], self.nbits, self.S, packed=True)
-            err = self.eng.simo_ber(self.wss[i & 1], self.chan, self.snr_rows, self.seed, stream_id0=int(stream_id0),
+            err = self.eng.simo_ber(self.wss[j], self.chan, self.snr_rows, self.seed, stream_id0=int(stream_id0),
                                     idx=idx, nbits=self.nbits, fused=self.fused, spectral=self.spectral,
                                     noise_domain=self.noise_domain)
             self.host_err[k].copy_(err, non_blocking=True)

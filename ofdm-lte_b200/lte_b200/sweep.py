@@ -88,7 +88,7 @@ def simo_sweep(engine, chan, snr_db, n_trials, num_rx, symbols_per_stream=14, se
         reduce_counts(counts)
         errors, bits = counts[0].cpu(), counts[1].cpu()
         return {'errors': errors, 'bits': bits, 'ber': errors.double() / bits.clamp(min=1).double()}
-    # whole batches of `batch_trials` trials: two in flight (LinkEngine.simo_ber_batches); slot b of a batch always
+    # whole batches of `batch_trials` trials, two in flight where that pays (LinkEngine.simo_ber_batches); slot b of a batch always
     # runs at SNR point b % n_snr, so the per-slot counts accumulate in the workspaces and are reduced per point at
     # the end.  A ragged last batch follows on its own.
     lo, hi = shard_range(n_trials, rank, world)
@@ -96,7 +96,8 @@ def simo_sweep(engine, chan, snr_db, n_trials, num_rx, symbols_per_stream=14, se
     nfull = (hi - lo) // batch_trials
     if nfull > 0:
         B = batch_trials * n_snr
-        wss = [engine.workspace(B, S, R, fading=chan.num_taps > 0, fused=fused, lazy=fused) for _ in range(min(2, nfull))]
+        nfl = min(engine.batches_in_flight(chan, B, R, S, fused=fused), nfull)
+        wss = [engine.workspace(B, S, R, fading=chan.num_taps > 0, fused=fused, lazy=fused) for _ in range(nfl)]
         for w in wss:
             w['errors'].zero_()
         rows = snr_lin.repeat(batch_trials).repeat_interleave(R).contiguous()
