@@ -134,3 +134,29 @@ def test_simo_ber_accumulate_equals_the_sum_of_separate_passes():
         for i in range(3):
             got = eng.simo_ber(ws, chan, rows, 5, stream_id0=i * B, accumulate=True, **kw)
         assert torch.equal(got, want) and int(want.sum()) > 0
+
+
+@pytest.mark.parametrize('bw,mod,R,B', [(20.0, '64-QAM', 4, 320), (5.0, '16-QAM', 2, 48)])
+def test_batches_in_flight_count_like_batches_in_sequence(bw, mod, R, B):
+    """LinkEngine.simo_ber_batches (what bench.py times and simo_sweep runs): seven batches alternating between two
+    workspaces on two streams accumulate exactly the per-slot counts of the same batches one after the other, and the
+    engine asks for two batches in flight only where the spectral link runs."""
+    from config import LTEConfig
+    from lte_b200 import LinkEngine, chan_for
+    cfg = LTEConfig(bw, 15.0, mod)
+    eng = LinkEngine.from_config(cfg)
+    S = 14
+    chan = chan_for('rayleigh_mp', cfg.fs, 'Pedestrian_A', 2.0, 3.0)
+    rows = torch.tensor([6.0, 40.0, 300.0, 2000.0], dtype=torch.float32, device='cuda').repeat(B // 4).repeat_interleave(R).contiguous()
+    sids = [k * B for k in range(7)]
+    one = eng.workspace(B, S, R, fading=True, fused=True, lazy=True)
+    want = sum(eng.simo_ber(one, chan, rows, 8, stream_id0=s, fused=True, noise_domain=3).clone() for s in sids)
+    assert eng.batches_in_flight(chan, B, R, S) == 2
+    assert eng.batches_in_flight(chan_for('rayleigh_mp', cfg.fs, 'Vehicular_A', 2.0, 60.0), B, R, S) == 1
+    wss = [eng.workspace(B, S, R, fading=True, fused=True, lazy=True) for _ in range(2)]
+    for _ in range(2):                                          # twice: the accumulators restart from zero
+        for w in wss:
+            w['errors'].zero_()
+        eng.simo_ber_batches(wss, chan, rows, 8, sids, noise_domain=3)
+        got = wss[0]['errors'] + wss[1]['errors']               # on the current stream: simo_ber_batches has joined it
+        assert torch.equal(got, want) and int(want.sum()) > 0
